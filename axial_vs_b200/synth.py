@@ -1,0 +1,133 @@
+"""Deterministic synthetic weights and inputs for the hot path (tests, smoke, bench).
+
+Follows SURVEY.md section 8(d) "Synthetic inputs": xavier_uniform_ on every dim>1 parameter (what the
+reference's `_reset_parameters` does, WC/msdeformattn.py:70-73 and CC:148-151), nn.Linear-style
+uniform biases, `src ~ N(0,1)`.  LayerNorm affine parameters are perturbed away from (1, 0) so that
+the affine part of the norms is actually exercised by the parity tests.
+
+All generators are seeded CPU `torch.Generator`s, so the same call reproduces the same tensors in the
+authoring container (where the golden fixtures are made) and on the GPU box.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List
+
+import torch
+
+Params = Dict[str, torch.Tensor]
+
+
+def _xavier(g: torch.Generator, *shape: int) -> torch.Tensor:
+    fan_out, fan_in = shape[0], shape[1]
+    rf = 1
+    for s in shape[2:]:
+        rf *= s
+    bound = math.sqrt(6.0 / ((fan_in + fan_out) * rf))
+    return (torch.rand(*shape, generator=g) * 2 - 1) * bound
+
+
+def _bias(g: torch.Generator, n: int, fan_in: int) -> torch.Tensor:
+    b = 1.0 / math.sqrt(fan_in)
+    return (torch.rand(n, generator=g) * 2 - 1) * b
+
+
+def _ln(g: torch.Generator, n: int, prefix: str, out: Params) -> None:
+    out[prefix + ".weight"] = 1.0 + 0.1 * torch.randn(n, generator=g)
+    out[prefix + ".bias"] = 0.1 * torch.randn(n, generator=g)
+
+
+def _linear(g: torch.Generator, prefix: str, n_out: int, n_in: int, out: Params) -> None:
+    out[prefix + ".weight"] = _xavier(g, n_out, n_in)
+    out[prefix + ".bias"] = _bias(g, n_out, n_in)
+
+
+def traj_attn_params(g: torch.Generator, prefix: str, C: int, out: Params, fused_qkv: bool = False) -> None:
+    """Leaf names of `TrajectoryAttention` (WC/temporal_attention.py:27-33; CC:85-89 for fused qkv)."""
+    if fused_qkv:
+        _linear(g, prefix + "qkv", 3 * C, C, out)
+    else:
+        for nm in ("q", "k", "v"):
+            _linear(g, prefix + nm, C, C, out)
+    _linear(g, prefix + "proj_q", C, C, out)
+    _linear(g, prefix + "proj_kv", 2 * C, C, out)
+    _linear(g, prefix + "proj", C, C, out)
+
+
+def axial_layer_params(seed: int, C: int = 256, d_ffn: int = 1024, axial: bool = True) -> Params:
+    """State dict of one Temporal(Axial)TrajectoryAttentionLayer (WC/temporal_attention.py:159-175)."""
+    g = torch.Generator().manual_seed(seed)
+    p: Params = {}
+    if axial:
+        traj_attn_params(g, "height_attn.", C, p)
+        traj_attn_params(g, "width_attn.", C, p)
+    else:
+        traj_attn_params(g, "temporal_attn.", C, p)
+    _ln(g, C, "norm1", p)
+    _linear(g, "linear1", d_ffn, C, p)
+    _linear(g, "linear2", C, d_ffn, p)
+    _ln(g, C, "norm2", p)
+    return p
+
+
+def encoder_params(seed: int, num_layers: int = 2, C: int = 256, d_ffn: int = 1024, axial: bool = True) -> Params:
+    """State dict of a TemporalEncoder: 'temporal_layers.{i}.<leaf>' (WC/temporal_attention.py:85-88)."""
+    out: Params = {}
+    for i in range(num_layers):
+        for k, v in axial_layer_params(seed * 1000 + i, C, d_ffn, axial).items():
+            out[f"temporal_layers.{i}.{k}"] = v
+    return out
+
+
+def cross_clip_params(seed: int, num_layers: int, num_classes: int = 124, C: int = 256) -> Params:
+    """State dict of CrossClipTrackingModule (CC:204-272) with non-trivial BN running statistics."""
+    g = torch.Generator().manual_seed(seed)
+    p: Params = {}
+
+    def bn(prefix: str, n: int, weight: float = 1.0):
+        p[prefix + ".weight"] = weight * (1.0 + 0.1 * torch.randn(n, generator=g))
+        p[prefix + ".bias"] = 0.1 * torch.randn(n, generator=g)
+        p[prefix + ".running_mean"] = 0.1 * torch.randn(n, generator=g)
+        p[prefix + ".running_var"] = 1.0 + 0.2 * torch.rand(n, generator=g)
+        p[prefix + ".num_batches_tracked"] = torch.tensor(1, dtype=torch.long)
+
+    for i in range(num_layers):
+        pre = f"transformer_trajectory_self_attention_layers.{i}."
+        traj_attn_params(g, pre + "self_attn.", C, p, fused_qkv=True)
+        _ln(g, C, pre + "norm", p)
+        pre = f"conv_short_aggregate_layers.{i}."
+        for j in range(3):
+            p[pre + f"_aspp_conv{j}.weight"] = _xavier(g, C, C, 3)
+            p[pre + f"_aspp_conv{j}.bias"] = _bias(g, C, 3 * C)
+        p[pre + "_proj_conv_bn_act.conv.weight"] = _xavier(g, C, 3 * C, 1)
+        _ln(g, C, pre + "_proj_conv_bn_act.norm", p)
+        _ln(g, C, f"conv_norms.{i}", p)
+    for nm in ("_class_embedding_projection", "_mask_embedding_projection"):
+        p[nm + ".conv.weight"] = _xavier(g, C, C, 1)
+        bn(nm + ".norm", C)
+    p["_predictor._transformer_mask_head.conv.weight"] = _xavier(g, 128, C, 1)
+    bn("_predictor._transformer_mask_head.norm", 128)
+    p["_predictor._transformer_class_head.conv.weight"] = 0.01 * torch.randn(num_classes + 1, C, 1, generator=g)
+    p["_predictor._transformer_class_head.conv.bias"] = torch.zeros(num_classes + 1)
+    p["_predictor._transformer_class_activation_head.conv.weight"] = 0.01 * torch.randn(1, C, 1, generator=g)
+    p["_predictor._transformer_class_activation_head.conv.bias"] = torch.zeros(1)
+    bn("_predictor._pixel_space_mask_batch_norm", 1, weight=0.1)
+    return p
+
+
+def randn(seed: int, *shape: int) -> torch.Tensor:
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def level_embed(seed: int, levels: int = 2, C: int = 256) -> torch.Tensor:
+    """`level_embed_3d ~ N(0,1)` (WC/msdeformattn.py:79-80)."""
+    return randn(seed, levels, C)
+
+
+def checksum(p: Params) -> float:
+    """Order-independent fingerprint of a parameter dict (stored in the golden fixtures)."""
+    tot = 0.0
+    for k in sorted(p):
+        t = p[k].double()
+        tot += float((t * torch.arange(1, t.numel() + 1, dtype=torch.float64).reshape(t.shape).remainder(7.0)).sum())
+    return tot

@@ -1,0 +1,120 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules on seeded inputs.
+
+Run in the authoring container only (needs /root/reference):
+
+    python oracle/make_golden.py
+
+Every fixture stores the seeds/shapes needed to regenerate inputs and weights with
+``axial_vs_b200.synth`` plus the reference's fp32 outputs, and a checksum of the weights so a
+generator drift is detected instead of silently mis-comparing.  TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from axial_vs_b200 import synth  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+from oracle import traj_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def save(name: str, **arrs):
+    os.makedirs(OUT, exist_ok=True)
+    conv = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        conv[k] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **conv)
+    print("wrote", name, {k: tuple(np.shape(v)) for k, v in conv.items()})
+
+
+@torch.no_grad()
+def main():
+    torch.manual_seed(0)
+    TA = ref_loader.temporal_attention()
+    PE = ref_loader.pos_embeddings()
+    CC = ref_loader.cross_clip()
+
+    # ---- 1. TrajectoryAttention alone (Vk, with attention maps) -------------------------------
+    for tag, (Bp, F, n, seed) in {"a": (3, 2, 5, 11), "b": (2, 3, 7, 12)}.items():
+        g = torch.Generator().manual_seed(seed)
+        p = {}
+        synth.traj_attn_params(g, "", 256, p)
+        m = TA.TrajectoryAttention(256, 8, 0.0).eval()
+        m.load_state_dict(p, strict=True)
+        q = synth.randn(seed + 100, Bp, F * n, 256)
+        v = synth.randn(seed + 200, Bp, F * n, 256)
+        y, maps = m(q, q, v, num_frames=F)
+        save(f"ta_vk_{tag}", Bp=Bp, F=F, n=n, seed=seed, y=y, maps=maps, wsum=synth.checksum(p))
+
+    # ---- 2. axial layer, encoder, non-axial layer ---------------------------------------------
+    for tag, (B, T, H, W, seed) in {"a": (1, 2, 6, 5, 21), "b": (2, 3, 4, 7, 22)}.items():
+        p = synth.axial_layer_params(seed)
+        m = TA.TemporalAxialTrajectoryAttentionLayer(256, 1024, 0.0, 0.0, "relu", 8).eval()
+        m.load_state_dict(p, strict=True)
+        src = synth.randn(seed + 100, B * T, H * W, 256)
+        pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 200)[0])
+        out, hm, wm = m(src, pos)
+        save(f"axial_layer_{tag}", B=B, T=T, H=H, W=W, seed=seed, out=out, hmap=hm, wmap=wm,
+             wsum=synth.checksum(p))
+
+    B, T, H, W, seed = 1, 2, 5, 6, 31
+    p = synth.encoder_params(seed, 2)
+    m = TA.TemporalEncoder(256, 1024, 0.0, 0.0, "relu", 8, "axial-trajectory", 2).eval()
+    m.load_state_dict(p, strict=True)
+    src = synth.randn(seed + 100, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 200)[1])
+    out, hm, wm = m(src, pos)
+    save("encoder_axial", B=B, T=T, H=H, W=W, seed=seed, out=out, hmap=hm, wmap=wm, wsum=synth.checksum(p))
+
+    B, T, H, W, seed = 1, 2, 4, 5, 41
+    p = synth.encoder_params(seed, 1, axial=False)
+    m = TA.TemporalEncoder(256, 1024, 0.0, 0.0, "relu", 8, "trajectory", 1).eval()
+    m.load_state_dict(p, strict=True)
+    src = synth.randn(seed + 100, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 200)[0])
+    out, _, _ = m(src, pos)
+    save("encoder_trajectory", B=B, T=T, H=H, W=W, seed=seed, out=out, wsum=synth.checksum(p))
+
+    # ---- 3. 3-D sine positional table -----------------------------------------------------------
+    pe = PE.PositionEmbeddingSine3D(128, normalize=True)
+    for tag, (B, T, H, W) in {"a": (1, 2, 5, 7), "b": (2, 5, 3, 4)}.items():
+        tab = pe(torch.zeros(B, T, 256, H, W), fmt="btchw")             # [B,T,C,H,W]
+        save(f"pos3d_{tag}", B=B, T=T, H=H, W=W, table=tab.permute(0, 1, 3, 4, 2).contiguous())
+
+    # ---- 4. cross-clip: attention alone, full module ----------------------------------------------
+    Q, Tc, seed = 16, 3, 51
+    g = torch.Generator().manual_seed(seed)
+    p = {}
+    synth.traj_attn_params(g, "", 256, p, fused_qkv=True)
+    m = CC.TrajectoryAttention(256, 8, 0.0).eval()
+    m.load_state_dict(p, strict=True)
+    x = synth.randn(seed + 100, 2, Tc * Q, 256)
+    save("cc_ta", b=2, Q=Q, T=Tc, seed=seed, y=m(x, seq_len=Q, num_frames=Tc), wsum=synth.checksum(p))
+
+    Q, Tc, V, Hh, Ww, L, K, seed = 16, 4, 2, 6, 5, 2, 124, 61
+    p = synth.cross_clip_params(seed, L, K)
+    m = CC.CrossClipTrackingModule(num_layers=L, num_classes=K, attn_drop=0.0, aspp_drop=0.0,
+                                   kernel_sizes=[3, 3, 3], atrous_rates=[1, 2, 3], norm_fn="ln",
+                                   num_clip_frames=V).eval()
+    m.load_state_dict(p, strict=True)
+    cq = synth.randn(seed + 100, 1, Q, Tc, 256)
+    pf = synth.randn(seed + 200, 1, 128, Tc * V, Hh, Ww)
+    o = m(cq, pf)
+    save("cc_module", Q=Q, T=Tc, V=V, H=Hh, W=Ww, L=L, K=K, seed=seed, pred_logits=o["pred_logits"],
+         pred_masks=o["pred_masks"], aux_masks=o["aux_outputs"][0]["pred_masks"], wsum=synth.checksum(p))
+
+
+if __name__ == "__main__":
+    if not ref_loader.available():
+        raise SystemExit("reference tree not found; golden fixtures can only be generated where it is mounted")
+    main()

@@ -1,0 +1,111 @@
+"""CPU: the oracle restatement against the committed golden fixtures (reference outputs, fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from axial_vs_b200 import synth
+from oracle import traj_oracle as O
+
+ATOL = 2e-5  # fp32 restatement vs fp32 reference: different summation order only
+
+
+def _close(a, b, atol=ATOL):
+    a = torch.as_tensor(np.asarray(a)).float()
+    b = torch.as_tensor(np.asarray(b)).float()
+    assert a.shape == b.shape
+    err = (a - b).abs().max().item()
+    assert err <= atol * max(1.0, b.abs().max().item()), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_trajectory_attention(golden, tag):
+    gz = golden(f"ta_vk_{tag}")
+    Bp, F, n, seed = int(gz["Bp"]), int(gz["F"]), int(gz["n"]), int(gz["seed"])
+    p = {}
+    synth.traj_attn_params(torch.Generator().manual_seed(seed), "", 256, p)
+    assert synth.checksum(p) == pytest.approx(float(gz["wsum"]), rel=1e-12)
+    q = synth.randn(seed + 100, Bp, F * n, 256)
+    v = synth.randn(seed + 200, Bp, F * n, 256)
+    y, maps = O.trajectory_attention(q, q, v, p, F, return_maps=True)
+    _close(y, gz["y"])
+    _close(maps, gz["maps"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_axial_layer(golden, tag):
+    gz = golden(f"axial_layer_{tag}")
+    B, T, H, W, seed = (int(gz[k]) for k in "B T H W seed".split())
+    p = synth.axial_layer_params(seed)
+    assert synth.checksum(p) == pytest.approx(float(gz["wsum"]), rel=1e-12)
+    src = synth.randn(seed + 100, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 200)[0])
+    out, hm, wm = O.axial_layer(src, pos, p, return_maps=True)
+    _close(out, gz["out"])
+    _close(hm, gz["hmap"])
+    _close(wm, gz["wmap"])
+
+
+def test_encoder_axial(golden):
+    gz = golden("encoder_axial")
+    B, T, H, W, seed = (int(gz[k]) for k in "B T H W seed".split())
+    p = synth.encoder_params(seed, 2)
+    src = synth.randn(seed + 100, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 200)[1])
+    out, hm, wm = O.temporal_encoder(src, pos, O.split_encoder_params(p), return_maps=True)
+    _close(out, gz["out"])
+    _close(hm, gz["hmap"])
+    _close(wm, gz["wmap"])
+
+
+def test_encoder_trajectory(golden):
+    gz = golden("encoder_trajectory")
+    B, T, H, W, seed = (int(gz[k]) for k in "B T H W seed".split())
+    p = synth.encoder_params(seed, 1, axial=False)
+    src = synth.randn(seed + 100, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 200)[0])
+    out, _, _ = O.temporal_encoder(src, pos, O.split_encoder_params(p), attn_type="trajectory")
+    _close(out, gz["out"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_pos3d(golden, tag):
+    gz = golden(f"pos3d_{tag}")
+    B, T, H, W = (int(gz[k]) for k in "B T H W".split())
+    _close(O.pos3d_table(B, T, H, W), gz["table"], atol=1e-6)
+
+
+def test_cc_trajectory_attention(golden):
+    gz = golden("cc_ta")
+    b, Q, T, seed = (int(gz[k]) for k in "b Q T seed".split())
+    p = {}
+    synth.traj_attn_params(torch.Generator().manual_seed(seed), "", 256, p, fused_qkv=True)
+    x = synth.randn(seed + 100, b, T * Q, 256)
+    _close(O.cc_trajectory_attention(x, p, Q, T), gz["y"])
+
+
+def test_cc_module(golden):
+    gz = golden("cc_module")
+    Q, T, V, H, W, L, K, seed = (int(gz[k]) for k in "Q T V H W L K seed".split())
+    p = synth.cross_clip_params(seed, L, K)
+    assert synth.checksum(p) == pytest.approx(float(gz["wsum"]), rel=1e-12)
+    cq = synth.randn(seed + 100, 1, Q, T, 256)
+    pf = synth.randn(seed + 200, 1, 128, T * V, H, W)
+    o = O.cross_clip_module(cq, pf, p, L, V)
+    _close(o["pred_logits"], gz["pred_logits"])
+    _close(o["pred_masks"], gz["pred_masks"], atol=5e-5)
+
+
+def test_fp64_oracle_agrees_with_fp32():
+    """The oracle is dtype-generic: fp64 run bounds the fp32 reference's own rounding noise."""
+    p = synth.axial_layer_params(5)
+    src = synth.randn(6, 2, 12, 256)
+    pos = O.level_pos3d(1, 2, 3, 4, synth.level_embed(7)[0])
+    o32, _, _ = O.axial_layer(src, pos, p)
+    o64, _, _ = O.axial_layer(src.double(), pos.double(), p)
+    assert (o32.double() - o64).abs().max().item() < 2e-5
+
+
+def test_flop_formulas_match_baseline_md():
+    assert abs(O.flops_axial_layer(1, 2, 41, 41) / 1e9 - 12.04) < 0.01
+    assert abs(O.flops_axial_layer(1, 2, 21, 21) / 1e9 - 3.09) < 0.01
+    assert abs(O.flops_axial_layer(1, 10, 161, 161) / 1e9 - 2830.56) < 0.1
