@@ -1,0 +1,75 @@
+"""ctypes binding of libaxvs.so (the C ABI declared in include/axvs.h).
+
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised
+(mirrors `ModuleNotFoundError` on the reference's native op, WC/ops/functions/ms_deform_attn_func.py:21-29,
+and `AT_ERROR` -> RuntimeError, WC/ops/src/ms_deform_attn.h:43).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaxvs.so")
+
+AXIS_NONE, AXIS_H, AXIS_W = 0, 1, 2
+
+
+class TaWeights(Structure):
+    _fields_ = [("w_qkv", c_void_p), ("b_qkv", c_void_p), ("w_pq", c_void_p), ("b_pq", c_void_p),
+                ("w_pkv", c_void_p), ("b_pkv", c_void_p), ("w_proj", c_void_p), ("b_proj", c_void_p)]
+
+
+class LayerWeights(Structure):
+    _fields_ = [("attn_h", TaWeights), ("attn_w", TaWeights), ("ln1_g", c_void_p), ("ln1_b", c_void_p),
+                ("w_ffn1", c_void_p), ("b_ffn1", c_void_p), ("w_ffn2", c_void_p), ("b_ffn2", c_void_p),
+                ("ln2_g", c_void_p), ("ln2_b", c_void_p), ("d_ffn", c_int)]
+
+
+# name -> (restype, argtypes); every symbol include/axvs.h declares
+SIGNATURES = {
+    "axvs_version": (c_int, []),
+    "axvs_last_error": (c_char_p, []),
+    "axvs_packed_weight_bytes": (c_size_t, [c_int, c_int]),
+    "axvs_pack_weight": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "axvs_linear": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p,
+                            c_int, c_int, c_void_p, c_void_p]),
+    "axvs_spatial_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "axvs_traj_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "axvs_traj_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(TaWeights), c_int, c_int, c_int,
+                                   c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "axvs_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
+    "axvs_ffn_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "axvs_ln_ffn_fwd": (c_int, [c_void_p, c_void_p, POINTER(LayerWeights), c_int, c_void_p, c_size_t, c_void_p]),
+    "axvs_layer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "axvs_axial_layer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(LayerWeights), c_int, c_int, c_int, c_int,
+                                     c_int, c_void_p, c_size_t, c_void_p]),
+    "axvs_pos3d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libaxvs.so (built by `__graft_entry__.build()`); raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"axial_vs_b200: native library not found at {LIB_PATH}. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). There is no CPU/PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().axvs_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,198 @@
+// Per-frame-softmax spatial attention of TrajectoryAttention (Appendix A steps 2-5):
+//   x[s, q, f, head*32 + :] = softmax_i( scale * Q[s,q,head,:] . K[s, f*n+i, head, :] ) @ V[s, f*n+i, head, :]
+// Reference: WC/temporal_attention.py:47-60 (the softmax is taken independently inside every key frame).
+//
+// v1 implementation: warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate), flash-style online softmax
+// over 64-key tiles so that any tokens-per-frame n works (n = H or W for the axial layers, H*W for the
+// non-axial "trajectory" layer, Q for the cross-clip module).  One CTA = 64 queries of one (sequence, head);
+// K/V tiles are double-buffered with cp.async; the score matrix never leaves registers.
+#pragma once
+#include "ptx.cuh"
+
+namespace axvs {
+
+constexpr int ATT_QT = 64;   // queries per CTA (4 warps x 16)
+constexpr int ATT_KT = 64;   // keys per tile
+constexpr int ATT_D = 32;    // head dim
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = smem_u32(smem_dst);
+  const int sz = valid ? 16 : 0;   // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// smem tiles are [rows][32] bf16 = 64 B rows = 4 chunks of 16 B, chunk index XOR-swizzled with (row>>1)&3
+__device__ __forceinline__ int att_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
+
+// qkv: [num_seq*N, ld] bf16 with q at column q_col, k at k_col, v at v_col (+ head*32);  x: [num_seq*N, F, 256] bf16
+__global__ void __launch_bounds__(128) spatial_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int q_col, int k_col,
+                                                           int v_col, __nv_bfloat16* __restrict__ x, int N, int n, int F,
+                                                           float scale_log2e) {
+  __shared__ __align__(128) uint8_t sQ[ATT_QT * 64];
+  __shared__ __align__(128) uint8_t sK[2][ATT_KT * 64];
+  __shared__ __align__(128) uint8_t sV[2][ATT_KT * 64];
+
+  const int q0 = blockIdx.x * ATT_QT;
+  const int seq = blockIdx.y;
+  const int head = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t seq_row0 = (size_t)seq * N;
+
+  // ---- Q tile -> smem (64 rows x 4 chunks = 256 chunks, 2 per thread)
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = i * 128 + tid;
+    const int r = c >> 2, ch = c & 3;
+    const bool ok = (q0 + r) < N;
+    const __nv_bfloat16* src = qkv + (seq_row0 + (ok ? q0 + r : 0)) * ld + q_col + head * ATT_D + ch * 8;
+    cp_async16(sQ + att_off(r, ch), src, ok);
+  }
+  const int tiles_per_frame = (n + ATT_KT - 1) / ATT_KT;
+  const int total_tiles = F * tiles_per_frame;
+
+  auto load_kv = [&](int it, int buf) {
+    const int f = it / tiles_per_frame, kt = it % tiles_per_frame;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = i * 128 + tid;
+      const int r = c >> 2, ch = c & 3;
+      const int key = kt * ATT_KT + r;
+      const bool ok = key < n;
+      const __nv_bfloat16* base = qkv + (seq_row0 + (size_t)f * n + (ok ? key : 0)) * ld + head * ATT_D + ch * 8;
+      cp_async16(sK[buf] + att_off(r, ch), base + k_col, ok);
+      cp_async16(sV[buf] + att_off(r, ch), base + v_col, ok);
+    }
+  };
+  load_kv(0, 0);
+  cp_async_commit();
+
+  // wait for Q (+ first K/V tile), build the Q fragments once
+  cp_async_wait<0>();
+  __syncthreads();
+  uint32_t qa[2][4];
+  {
+    const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) ldmatrix_x4(qa[ks], sQ + att_off(r, ks * 2 + (lane >> 4)));
+  }
+
+  const int g = lane >> 2, t4 = lane & 3;
+  float m_run[2], l_run[2], acc[4][4];
+
+  for (int it = 0; it < total_tiles; ++it) {
+    const int buf = it & 1;
+    const int f = it / tiles_per_frame, kt = it % tiles_per_frame;
+    if (kt == 0) {
+      m_run[0] = m_run[1] = -INFINITY;
+      l_run[0] = l_run[1] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    }
+    if (it + 1 < total_tiles) load_kv(it + 1, buf ^ 1);
+    cp_async_commit();
+    if (it > 0) {
+      cp_async_wait<1>();   // tile `it` has landed (tile it+1 may still be in flight)
+      __syncthreads();
+    }
+
+    // ---- S = Q K^T for 16 queries x 64 keys
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      uint32_t kb[4];
+      ldmatrix_x4(kb, sK[buf] + att_off(j * 8 + (lane & 7), lane >> 3));
+      mma_bf16_16816(s[j], qa[0], kb[0], kb[1]);
+      mma_bf16_16816(s[j], qa[1], kb[2], kb[3]);
+    }
+    // ---- mask keys beyond the frame, online softmax (log2 domain)
+    const int key_base = kt * ATT_KT;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = key_base + j * 8 + t4 * 2 + (e & 1);
+        const float v = (key < n) ? s[j][e] * scale_log2e : -INFINITY;
+        s[j][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+    float corr[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+      const float mn = fmaxf(m_run[h], mx[h]);   // finite: every tile has >= 1 valid key
+      corr[h] = exp2f(m_run[h] - mn);
+      m_run[h] = mn;
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f(s[j][0] - m_run[0]), p1 = exp2f(s[j][1] - m_run[0]);
+      const float p2 = exp2f(s[j][2] - m_run[1]), p3 = exp2f(s[j][3] - m_run[1]);
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) l_run[h] = l_run[h] * corr[h] + rs[h];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[j][0] *= corr[0]; acc[j][1] *= corr[0];
+      acc[j][2] *= corr[1]; acc[j][3] *= corr[1];
+    }
+    // ---- acc += P V   (16 x 64) x (64 x 32)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int jn = 0; jn < 4; jn += 2) {
+        uint32_t vb[4];
+        const int key = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4_trans(vb, sV[buf] + att_off(key, jn + (lane >> 4)));
+        mma_bf16_16816(acc[jn], pa[ks], vb[0], vb[1]);
+        mma_bf16_16816(acc[jn + 1], pa[ks], vb[2], vb[3]);
+      }
+    }
+    // ---- end of frame: normalise and write x[q, f, head*32 : head*32+32]
+    if (kt == tiles_per_frame - 1) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float l = l_run[h];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        const float inv = 1.f / l;
+        const int q = q0 + warp * 16 + g + h * 8;
+        if (q < N) {
+          __nv_bfloat16* dst = x + ((seq_row0 + q) * F + f) * 256 + head * ATT_D + t4 * 2;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint32_t*>(dst + j * 8) = pack_bf16x2(acc[j][h * 2] * inv, acc[j][h * 2 + 1] * inv);
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with buf before it is refilled two iterations later
+  }
+}
+
+}  // namespace axvs

@@ -1,0 +1,366 @@
+// libaxvs.so -- C ABI (include/axvs.h) over the sm_100a kernels.  No torch types, no exceptions across the ABI,
+// no host synchronisation, no allocation: everything is enqueued on the caller's stream.
+#include "../../include/axvs.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "attn.cuh"
+#include "gemm.cuh"
+#include "simt.cuh"
+
+using namespace axvs;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define AXVS_CHECK_LAUNCH(what)                                                            \
+  do {                                                                                     \
+    cudaError_t e_ = cudaGetLastError();                                                   \
+    if (e_ != cudaSuccess) return fail(AXVS_E_CUDA, "%s: %s", what, cudaGetErrorString(e_)); \
+  } while (0)
+
+struct DeviceInfo {
+  int sms = 0;
+  bool gemm_attr = false;
+};
+DeviceInfo g_dev[64];
+
+int device_info(DeviceInfo** out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(AXVS_E_CUDA, "cudaGetDevice failed");
+  DeviceInfo& d = g_dev[dev];
+  if (d.sms == 0) {
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return fail(AXVS_E_UNSUPPORTED, "libaxvs is built for sm_100a only (device major %d)", major);
+    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (!d.gemm_attr) {
+    if (cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(gemm) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    d.gemm_attr = true;
+  }
+  *out = &d;
+  return AXVS_OK;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+int check_gemm_shape(int M, int K, int n_out) {
+  if (M <= 0) return fail(AXVS_E_INVALID, "gemm: M must be positive (got %d)", M);
+  if (K <= 0 || K % GEMM_BK) return fail(AXVS_E_UNSUPPORTED, "gemm: K must be a positive multiple of %d (got %d)", GEMM_BK, K);
+  if (n_out <= 0 || n_out % GEMM_BN) return fail(AXVS_E_UNSUPPORTED, "gemm: n_out must be a positive multiple of %d (got %d)", GEMM_BN, n_out);
+  return AXVS_OK;
+}
+
+int launch_gemm(const GemmParams& p, cudaStream_t st) {
+  int rc = check_gemm_shape(p.M, p.K, p.n_out);
+  if (rc) return rc;
+  DeviceInfo* d;
+  rc = device_info(&d);
+  if (rc) return rc;
+  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * (p.n_out / GEMM_BN);
+  const int grid = tiles < d->sms ? tiles : d->sms;
+  gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p);
+  AXVS_CHECK_LAUNCH("gemm_bf16_kernel");
+  return AXVS_OK;
+}
+
+GemmParams gemm_params(const void* A, int lda, int M, int K, const void* Wp, int w_rows_total, int w_row0, const float* bias,
+                       int n_out, float scale, int relu, void* out, int ldo, int out_col0, int out_bf16, const float* resid) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.A = reinterpret_cast<const __nv_bfloat16*>(A);
+  p.lda = lda; p.M = M; p.K = K;
+  p.a_diag = 0; p.a_N = 1; p.a_n = 1; p.a_F = 1;
+  p.Wp = reinterpret_cast<const uint8_t*>(Wp);
+  p.w_rows_total = w_rows_total; p.w_row0 = w_row0;
+  p.n_out = n_out;
+  p.bias = bias ? bias + w_row0 : nullptr;
+  p.scale = scale; p.relu = relu;
+  p.out = out; p.ldo = ldo; p.out_col0 = out_col0; p.out_bf16 = out_bf16;
+  p.resid = resid;
+  p.map_mode = MAP_NONE;
+  p.dims = AxialDims{1, 1, 1, 1};
+  return p;
+}
+
+struct TaWorkspace {
+  __nv_bfloat16 *a1, *a2, *a3, *qkv, *x, *q2, *kv2, *o;
+  size_t bytes;
+};
+
+TaWorkspace carve_ta(void* base, size_t rows, int F) {
+  TaWorkspace w;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t n) { __nv_bfloat16* r = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(n); return r; };
+  w.a1 = take(rows * 256 * 2);
+  w.a2 = take(rows * 256 * 2);
+  w.a3 = take(rows * 256 * 2);
+  w.qkv = take(rows * 768 * 2);
+  w.x = take(rows * (size_t)F * 256 * 2);
+  w.q2 = take(rows * 256 * 2);
+  w.kv2 = take(rows * (size_t)F * 512 * 2);
+  w.o = take(rows * 256 * 2);
+  w.bytes = off;
+  return w;
+}
+
+struct FfnWorkspace {
+  float* s3;
+  __nv_bfloat16* s3b;
+  __nv_bfloat16* hid;
+  float* t;
+  size_t bytes;
+};
+
+FfnWorkspace carve_ffn(void* base, size_t rows, int d_ffn) {
+  FfnWorkspace w;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  w.s3 = reinterpret_cast<float*>(p + off); off += align256(rows * 256 * 4);
+  w.s3b = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(rows * 256 * 2);
+  w.hid = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(rows * (size_t)d_ffn * 2);
+  w.t = reinterpret_cast<float*>(p + off); off += align256(rows * 256 * 4);
+  w.bytes = off;
+  return w;
+}
+
+int check_dims(int B, int T, int H, int W) {
+  if (B <= 0 || T <= 0 || H <= 0 || W <= 0) return fail(AXVS_E_INVALID, "dims must be positive (B=%d T=%d H=%d W=%d)", B, T, H, W);
+  if ((long long)B * T * H * W > (1ll << 30)) return fail(AXVS_E_UNSUPPORTED, "too many tokens (%lld)", (long long)B * T * H * W);
+  return AXVS_OK;
+}
+
+int blocks_for(long long work_items, int per_block, int sms) {
+  long long b = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)sms * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+extern "C" {
+
+int axvs_version(void) { return 100; }
+const char* axvs_last_error(void) { return g_err; }
+
+size_t axvs_packed_weight_bytes(int n_out, int k) {
+  if (n_out <= 0 || k <= 0) return 0;
+  return (size_t)n_out * (size_t)k * 2;
+}
+
+int axvs_pack_weight(const float* w, int n_out, int k, void* packed, axvs_stream_t stream) {
+  if (!w || !packed) return fail(AXVS_E_INVALID, "pack_weight: null pointer");
+  if (n_out <= 0 || n_out % 8 || k <= 0 || k % 64) return fail(AXVS_E_UNSUPPORTED, "pack_weight: need n_out %% 8 == 0 and k %% 64 == 0 (got %d, %d)", n_out, k);
+  const int total = n_out * (k / 8);
+  pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_out, k, reinterpret_cast<uint8_t*>(packed));
+  AXVS_CHECK_LAUNCH("pack_weight_kernel");
+  return AXVS_OK;
+}
+
+int axvs_linear(const void* a_bf16, int lda, int M, int K, const void* w_packed, const float* bias, int n_out, float scale,
+                int relu, void* out, int ldo, int out_bf16, const float* resid, axvs_stream_t stream) {
+  if (!a_bf16 || !w_packed || !out) return fail(AXVS_E_INVALID, "linear: null pointer");
+  if (lda < K || ldo < n_out) return fail(AXVS_E_INVALID, "linear: leading dimension too small");
+  if ((lda % 8) || (ldo % 8)) return fail(AXVS_E_UNSUPPORTED, "linear: leading dimensions must be multiples of 8");
+  if (resid && out_bf16) return fail(AXVS_E_UNSUPPORTED, "linear: residual add is only available on the fp32 output path");
+  GemmParams p = gemm_params(a_bf16, lda, M, K, w_packed, n_out, 0, bias, n_out, scale, relu, out, ldo, 0, out_bf16, resid);
+  return launch_gemm(p, (cudaStream_t)stream);
+}
+
+int axvs_spatial_attention(const void* qkv_bf16, void* x_bf16, int num_seq, int F, int n, axvs_stream_t stream) {
+  if (!qkv_bf16 || !x_bf16) return fail(AXVS_E_INVALID, "spatial_attention: null pointer");
+  if (num_seq <= 0 || F <= 0 || n <= 0) return fail(AXVS_E_INVALID, "spatial_attention: sizes must be positive");
+  if (num_seq > 65535) return fail(AXVS_E_UNSUPPORTED, "spatial_attention: at most 65535 sequences per call (got %d)", num_seq);
+  const int N = F * n;
+  dim3 grid((N + ATT_QT - 1) / ATT_QT, num_seq, 8);
+  const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;   // 32^-0.5 * log2(e)
+  spatial_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), 768, 0, 256, 512,
+                                                              reinterpret_cast<__nv_bfloat16*>(x_bf16), N, n, F, scale_log2e);
+  AXVS_CHECK_LAUNCH("spatial_attn_kernel");
+  return AXVS_OK;
+}
+
+size_t axvs_traj_attn_workspace_bytes(int B, int T, int H, int W) {
+  if (B <= 0 || T <= 0 || H <= 0 || W <= 0) return 0;
+  return carve_ta(nullptr, (size_t)B * T * H * W, T).bytes;
+}
+
+int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, const float* pos, const float* resid, float* out,
+                       const axvs_ta_weights* w, int B, int T, int H, int W, int axis, void* workspace, size_t workspace_bytes,
+                       axvs_stream_t stream) {
+  if (!q_in || !k_in || !v_in || !out || !w || !workspace) return fail(AXVS_E_INVALID, "traj_attn: null pointer");
+  if (!w->w_qkv || !w->w_pq || !w->w_pkv || !w->w_proj) return fail(AXVS_E_INVALID, "traj_attn: null weight pointer");
+  int rc = check_dims(B, T, H, W);
+  if (rc) return rc;
+  if (axis != AXVS_AXIS_NONE && axis != AXVS_AXIS_H && axis != AXVS_AXIS_W) return fail(AXVS_E_INVALID, "traj_attn: bad axis %d", axis);
+  const size_t rows = (size_t)B * T * H * W;
+  const int F = T;
+  int num_seq, n;
+  if (axis == AXVS_AXIS_H) { num_seq = B * W; n = H; }
+  else if (axis == AXVS_AXIS_W) { num_seq = B * H; n = W; }
+  else { num_seq = B; n = H * W; }
+  const int N = F * n;
+  TaWorkspace ws = carve_ta(workspace, rows, F);
+  if (ws.bytes > workspace_bytes) return fail(AXVS_E_WORKSPACE, "traj_attn: workspace %zu < required %zu", workspace_bytes, ws.bytes);
+  DeviceInfo* d;
+  rc = device_info(&d);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const AxialDims dims{B, T, H, W};
+  const int map = axis;   // AXVS_AXIS_* == RowMap values
+  const int pk_blocks = blocks_for((long long)rows, 8, d->sms);
+
+  // 1. permute + pos add + cast (pass order):  a1 = bf16(q_in + pos), a2 = bf16(v_in), a3 = bf16(k_in + pos)
+  // 2. q | k | v projections -> qkv [rows, 768] bf16
+  const bool same_qk = (k_in == q_in);
+  const bool same_all = same_qk && (v_in == q_in) && !pos;
+  const bool v_from_q = (v_in == q_in);
+  pack_kq_kernel<<<pk_blocks, 256, 0, st>>>(q_in, pos, ws.a1, (v_from_q && !same_all) ? ws.a2 : nullptr, (int)rows, map, dims);
+  AXVS_CHECK_LAUNCH("pack_kq_kernel");
+  if (!v_from_q) {
+    pack_kq_kernel<<<pk_blocks, 256, 0, st>>>(v_in, nullptr, ws.a2, nullptr, (int)rows, map, dims);
+    AXVS_CHECK_LAUNCH("pack_kq_kernel(v)");
+  }
+  if (!same_qk) {
+    pack_kq_kernel<<<pk_blocks, 256, 0, st>>>(k_in, pos, ws.a3, nullptr, (int)rows, map, dims);
+    AXVS_CHECK_LAUNCH("pack_kq_kernel(k)");
+  }
+  if (same_all) {
+    GemmParams p = gemm_params(ws.a1, 256, (int)rows, 256, w->w_qkv, 768, 0, w->b_qkv, 768, 1.f, 0, ws.qkv, 768, 0, 1, nullptr);
+    if ((rc = launch_gemm(p, st))) return rc;
+  } else {
+    if (same_qk) {
+      GemmParams p = gemm_params(ws.a1, 256, (int)rows, 256, w->w_qkv, 768, 0, w->b_qkv, 512, 1.f, 0, ws.qkv, 768, 0, 1, nullptr);
+      if ((rc = launch_gemm(p, st))) return rc;
+    } else {
+      GemmParams p = gemm_params(ws.a1, 256, (int)rows, 256, w->w_qkv, 768, 0, w->b_qkv, 256, 1.f, 0, ws.qkv, 768, 0, 1, nullptr);
+      if ((rc = launch_gemm(p, st))) return rc;
+      p = gemm_params(ws.a3, 256, (int)rows, 256, w->w_qkv, 768, 256, w->b_qkv, 256, 1.f, 0, ws.qkv, 768, 256, 1, nullptr);
+      if ((rc = launch_gemm(p, st))) return rc;
+    }
+    GemmParams p = gemm_params(ws.a2, 256, (int)rows, 256, w->w_qkv, 768, 512, w->b_qkv, 256, 1.f, 0, ws.qkv, 768, 512, 1, nullptr);
+    if ((rc = launch_gemm(p, st))) return rc;
+  }
+  // 3. per-frame-softmax attention -> x [rows, F, 256]
+  for (int s0 = 0; s0 < num_seq; s0 += 65535) {
+    const int ns = (num_seq - s0) < 65535 ? (num_seq - s0) : 65535;
+    rc = axvs_spatial_attention(ws.qkv + (size_t)s0 * N * 768, ws.x + (size_t)s0 * N * F * 256, ns, F, n, stream);
+    if (rc) return rc;
+  }
+  // 4. q2 = proj_q(x_diag) * scale
+  {
+    GemmParams p = gemm_params(ws.x, 256, (int)rows, 256, w->w_pq, 256, 0, w->b_pq, 256, 0.17677669529663687f, 0, ws.q2, 256, 0, 1, nullptr);
+    p.a_diag = 1; p.a_N = N; p.a_n = n; p.a_F = F;
+    if ((rc = launch_gemm(p, st))) return rc;
+  }
+  // 5. k2 | v2 = proj_kv(x)  -> [rows*F, 512]
+  {
+    if (rows * (size_t)F > (size_t)0x7fffffff) return fail(AXVS_E_UNSUPPORTED, "traj_attn: rows*F overflows int");
+    GemmParams p = gemm_params(ws.x, 256, (int)(rows * F), 256, w->w_pkv, 512, 0, w->b_pkv, 512, 1.f, 0, ws.kv2, 512, 0, 1, nullptr);
+    if ((rc = launch_gemm(p, st))) return rc;
+  }
+  // 6. temporal softmax over frames -> o
+  temporal_attn_kernel<<<(int)((rows * 8 + 127) / 128), 128, 0, st>>>(ws.q2, ws.kv2, ws.o, (int)rows, F);
+  AXVS_CHECK_LAUNCH("temporal_attn_kernel");
+  // 7. out[c] = resid[c] + proj(o)[p]   (scatter back to canonical order)
+  {
+    GemmParams p = gemm_params(ws.o, 256, (int)rows, 256, w->w_proj, 256, 0, w->b_proj, 256, 1.f, 0, out, 256, 0, 0, resid);
+    p.map_mode = map; p.dims = dims;
+    if ((rc = launch_gemm(p, st))) return rc;
+  }
+  return AXVS_OK;
+}
+
+int axvs_layernorm(const float* x, const float* gamma, const float* beta, float* y32, void* y16_bf16, int rows, float eps,
+                   axvs_stream_t stream) {
+  if (!x || !gamma || !beta || (!y32 && !y16_bf16)) return fail(AXVS_E_INVALID, "layernorm: null pointer");
+  if (rows <= 0) return fail(AXVS_E_INVALID, "layernorm: rows must be positive");
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  layernorm256_kernel<<<blocks_for(rows, 8, d->sms), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y32, reinterpret_cast<__nv_bfloat16*>(y16_bf16), rows, eps);
+  AXVS_CHECK_LAUNCH("layernorm256_kernel");
+  return AXVS_OK;
+}
+
+size_t axvs_ffn_workspace_bytes(int rows, int d_ffn) {
+  if (rows <= 0 || d_ffn <= 0) return 0;
+  return carve_ffn(nullptr, (size_t)rows, d_ffn).bytes;
+}
+
+int axvs_ln_ffn_fwd(const float* x, float* out, const axvs_layer_weights* w, int rows, void* workspace, size_t workspace_bytes,
+                    axvs_stream_t stream) {
+  if (!x || !out || !w || !workspace) return fail(AXVS_E_INVALID, "ln_ffn: null pointer");
+  if (rows <= 0) return fail(AXVS_E_INVALID, "ln_ffn: rows must be positive");
+  if (w->d_ffn <= 0 || w->d_ffn % 256) return fail(AXVS_E_UNSUPPORTED, "ln_ffn: d_ffn must be a multiple of 256 (got %d)", w->d_ffn);
+  FfnWorkspace ws = carve_ffn(workspace, (size_t)rows, w->d_ffn);
+  if (ws.bytes > workspace_bytes) return fail(AXVS_E_WORKSPACE, "ln_ffn: workspace %zu < required %zu", workspace_bytes, ws.bytes);
+  int rc;
+  if ((rc = axvs_layernorm(x, w->ln1_g, w->ln1_b, ws.s3, ws.s3b, rows, 1e-5f, stream))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmParams p = gemm_params(ws.s3b, 256, rows, 256, w->w_ffn1, w->d_ffn, 0, w->b_ffn1, w->d_ffn, 1.f, 1, ws.hid, w->d_ffn, 0, 1, nullptr);
+  if ((rc = launch_gemm(p, st))) return rc;
+  p = gemm_params(ws.hid, w->d_ffn, rows, w->d_ffn, w->w_ffn2, 256, 0, w->b_ffn2, 256, 1.f, 0, ws.t, 256, 0, 0, ws.s3);
+  if ((rc = launch_gemm(p, st))) return rc;
+  return axvs_layernorm(ws.t, w->ln2_g, w->ln2_b, out, nullptr, rows, 1e-5f, stream);
+}
+
+size_t axvs_layer_workspace_bytes(int B, int T, int H, int W, int d_ffn) {
+  if (B <= 0 || T <= 0 || H <= 0 || W <= 0 || d_ffn <= 0) return 0;
+  const size_t rows = (size_t)B * T * H * W;
+  const size_t ta = carve_ta(nullptr, rows, T).bytes;
+  const size_t ffn = carve_ffn(nullptr, rows, d_ffn).bytes;
+  return 2 * align256(rows * 256 * 4) + (ta > ffn ? ta : ffn);
+}
+
+int axvs_axial_layer_fwd(const float* src, const float* pos, float* out, const axvs_layer_weights* w, int B, int T, int H, int W,
+                         int axial, void* workspace, size_t workspace_bytes, axvs_stream_t stream) {
+  if (!src || !pos || !out || !w || !workspace) return fail(AXVS_E_INVALID, "axial_layer: null pointer");
+  int rc = check_dims(B, T, H, W);
+  if (rc) return rc;
+  const size_t need = axvs_layer_workspace_bytes(B, T, H, W, w->d_ffn);
+  if (need > workspace_bytes) return fail(AXVS_E_WORKSPACE, "axial_layer: workspace %zu < required %zu", workspace_bytes, need);
+  const size_t rows = (size_t)B * T * H * W;
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  float* s1 = reinterpret_cast<float*>(base);
+  float* s2 = reinterpret_cast<float*>(base + align256(rows * 256 * 4));
+  void* sub = base + 2 * align256(rows * 256 * 4);
+  const size_t sub_bytes = workspace_bytes - 2 * align256(rows * 256 * 4);
+  if (axial) {
+    // S1 = S0 + TA_h(S0 + P, S0 + P, S0);  S2 = S1 + TA_w(S1 + P, S1 + P, S1)      WC/temporal_attention.py:197-213
+    if ((rc = axvs_traj_attn_fwd(src, src, src, pos, src, s1, &w->attn_h, B, T, H, W, AXVS_AXIS_H, sub, sub_bytes, stream))) return rc;
+    if ((rc = axvs_traj_attn_fwd(s1, s1, s1, pos, s1, s2, &w->attn_w, B, T, H, W, AXVS_AXIS_W, sub, sub_bytes, stream))) return rc;
+  } else {
+    // non-axial: one attention over all T*H*W tokens of a clip                       WC/temporal_attention.py:141-150
+    if ((rc = axvs_traj_attn_fwd(src, src, src, pos, src, s2, &w->attn_h, B, T, H, W, AXVS_AXIS_NONE, sub, sub_bytes, stream))) return rc;
+  }
+  return axvs_ln_ffn_fwd(s2, out, w, (int)rows, sub, sub_bytes, stream);
+}
+
+int axvs_pos3d(float* out, const float* level_embed, int B, int T, int H, int W, axvs_stream_t stream) {
+  if (!out) return fail(AXVS_E_INVALID, "pos3d: null pointer");
+  int rc = check_dims(B, T, H, W);
+  if (rc) return rc;
+  DeviceInfo* d;
+  if ((rc = device_info(&d))) return rc;
+  const long long total = (long long)T * H * W * 128;
+  pos3d_kernel<<<blocks_for(total, 256, d->sms), 256, 0, (cudaStream_t)stream>>>(out, level_embed, B, T, H, W);
+  AXVS_CHECK_LAUNCH("pos3d_kernel");
+  return AXVS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,288 @@
+// Persistent warp-specialised tcgen05 GEMM:  out = epilogue( A[M,K] (bf16, row-major) * W[n_out,K]^T + bias ).
+//
+//  * A K-blocks (128 rows x 64 bf16) are gathered by producer warps (arbitrary row map) into SWIZZLE_128B
+//    K-major shared-memory tiles; W K-blocks (256 rows x 64 bf16) arrive by 1-D TMA bulk copies from a
+//    pre-swizzled packed image (see pack_weight_kernel), so no tensor map is needed.
+//  * One elected thread issues tcgen05.mma (M=128, N=256, K=16) into a double-buffered TMEM accumulator
+//    (2 x 256 fp32 columns); four epilogue warps drain it with tcgen05.ld (one row per thread).
+//  * mbarrier rings: full/empty per smem stage, full/empty per TMEM stage.  Tiles are assigned
+//    round-robin to a grid of min(#tiles, #SMs) CTAs.
+#pragma once
+#include "ptx.cuh"
+
+namespace axvs {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 256;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KiB
+constexpr int GEMM_W_BYTES = GEMM_BN * GEMM_BK * 2;   // 32 KiB
+constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_W_BYTES;
+constexpr int GEMM_EPI_WARPS = 4;
+constexpr int GEMM_APROD_WARPS = 4;
+constexpr int GEMM_THREADS = (GEMM_EPI_WARPS + 2 + GEMM_APROD_WARPS) * 32;   // 320
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum RowMap : int { MAP_NONE = 0, MAP_HPASS = 1, MAP_WPASS = 2 };
+
+struct AxialDims {
+  int B, T, H, W;
+};
+
+// pass-order row index -> canonical token index ((b*T + t)*H + h)*W + w
+__device__ __forceinline__ int pass_to_canonical(int p, int mode, const AxialDims& d) {
+  if (mode == MAP_HPASS) {   // p = ((b*W + w)*T + t)*H + h
+    int h = p % d.H;
+    int r = p / d.H;
+    int t = r % d.T;
+    r /= d.T;
+    int w = r % d.W;
+    int b = r / d.W;
+    return ((b * d.T + t) * d.H + h) * d.W + w;
+  } else if (mode == MAP_WPASS) {   // p = ((b*H + h)*T + t)*W + w
+    int w = p % d.W;
+    int r = p / d.W;
+    int t = r % d.T;
+    r /= d.T;
+    int h = r % d.H;
+    int b = r / d.H;
+    return ((b * d.T + t) * d.H + h) * d.W + w;
+  }
+  return p;
+}
+
+struct GemmParams {
+  // A operand
+  const __nv_bfloat16* A;
+  int lda;      // elements
+  int M;        // logical rows
+  int K;        // multiple of 64
+  int a_diag;   // 1: logical row r reads A row r*F + (r % N) / n   (own-frame rows of x[rows, F, C])
+  int a_N, a_n, a_F;
+  // W operand (packed) and bias
+  const uint8_t* Wp;
+  int w_rows_total;   // rows of the packed image (K-block stride = w_rows_total * 128 B)
+  int w_row0;         // first weight row used by this GEMM (multiple of 8)
+  int n_out;    // multiple of 256
+  const float* bias;
+  // epilogue
+  float scale;  // applied after bias
+  int relu;
+  void* out;    // bf16 or fp32
+  int ldo;      // elements
+  int out_col0; // column offset inside out rows
+  int out_bf16;
+  const float* resid;   // optional fp32 residual, same row map / ld as out (fp32 path only)
+  int map_mode;         // RowMap applied to output (and residual) rows
+  AxialDims dims;
+};
+
+__device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, int row, int col, float (&v)[32]) {
+  // v holds acc for columns col..col+31 of logical row `row`
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float x = v[i] + (p.bias ? __ldg(p.bias + col + i) : 0.f);
+    x *= p.scale;
+    if (p.relu) x = fmaxf(x, 0.f);
+    v[i] = x;
+  }
+  int orow = pass_to_canonical(row, p.map_mode, p.dims);
+  if (p.out_bf16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)orow * p.ldo + p.out_col0 + col;
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+      u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+      u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+      u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      o4[i] = u;
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(p.out) + (size_t)orow * p.ldo + p.out_col0 + col;
+    float4* o4 = reinterpret_cast<float4*>(o);
+    if (p.resid) {
+      const float4* r4 = reinterpret_cast<const float4*>(p.resid + (size_t)orow * p.ldo + p.out_col0 + col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 r = __ldg(r4 + i);
+        o4[i] = make_float4(v[4 * i] + r.x, v[4 * i + 1] + r.y, v[4 * i + 2] + r.z, v[4 * i + 3] + r.w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + GEMM_STAGES;        // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * GEMM_STAGES;    // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int n_chunks = p.n_out / GEMM_BN;
+  const int num_tiles = m_tiles * n_chunks;
+  const int num_kb = p.K / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1 + GEMM_APROD_WARPS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == GEMM_EPI_WARPS + 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < GEMM_EPI_WARPS) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / n_chunks, nc = tile % n_chunks;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = mt * GEMM_BM + warp * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * GEMM_BN;
+#pragma unroll 1
+      for (int c = 0; c < GEMM_BN; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (row < p.M) gemm_epilogue_store(p, row, nc * GEMM_BN + c, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp == GEMM_EPI_WARPS) {
+    // ===================== W producer: TMA bulk copies of packed weight K-blocks =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nc = tile % n_chunks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* dst = smem + stage * GEMM_STAGE_BYTES + GEMM_A_BYTES;
+          const uint8_t* src = p.Wp + ((size_t)kb * p.w_rows_total + (size_t)p.w_row0 + (size_t)nc * GEMM_BN) * 128;
+          mbar_arrive_expect_tx(&full_bar[stage], GEMM_W_BYTES);
+          tma_bulk_g2s(dst, src, GEMM_W_BYTES, &full_bar[stage]);
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == GEMM_EPI_WARPS + 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16(GEMM_BM, GEMM_BN);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * GEMM_STAGE_BYTES);
+          const uint32_t w_addr = a_addr + GEMM_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            umma_bf16(tmem_base + acc * GEMM_BN, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_addr + k * 32),
+                      idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);                      // frees the smem stage when the MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ===================== A producers: gather rows -> swizzled smem =====================
+    const int ptid = threadIdx.x - (GEMM_EPI_WARPS + 2) * 32;   // 0..127
+    constexpr int PT = GEMM_APROD_WARPS * 32;
+    constexpr int ITERS = GEMM_BM * 8 / PT;                     // 16-byte chunks per thread per K-block
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / n_chunks;
+      // source row pointers are K-block independent
+      const __nv_bfloat16* rowp[ITERS];
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const int q = i * PT + ptid;
+        const int r = mt * GEMM_BM + (q >> 3);
+        if (r < p.M) {
+          size_t ar = p.a_diag ? (size_t)r * p.a_F + (size_t)((r % p.a_N) / p.a_n) : (size_t)r;
+          rowp[i] = p.A + ar * p.lda + (q & 7) * 8;
+        } else {
+          rowp[i] = nullptr;
+        }
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        uint4 v[ITERS];
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i)
+          v[i] = rowp[i] ? ldg_nc_v4(rowp[i] + kb * GEMM_BK) : make_uint4(0, 0, 0, 0);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* dst = smem + stage * GEMM_STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i) {
+          const int q = i * PT + ptid;
+          *reinterpret_cast<uint4*>(dst + sw128_offset(q >> 3, q & 7)) = v[i];
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[stage]);
+        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == GEMM_EPI_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// fp32 [n_out, K] row-major -> bf16 packed image: [K/64][n_out/8][8 rows x 128 B, 16-B chunks XOR-swizzled by row&7]
+__global__ void pack_weight_kernel(const float* __restrict__ w, int n_out, int K, uint8_t* __restrict__ packed) {
+  const int total = n_out * (K / 8);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / (K / 8);
+    const int c8 = idx % (K / 8);     // 8-element chunk along K
+    const int kb = c8 >> 3, ch = c8 & 7;
+    const float4* s = reinterpret_cast<const float4*>(w + (size_t)r * K + c8 * 8);
+    float4 a = s[0], b = s[1];
+    uint4 u;
+    u.x = pack_bf16x2(a.x, a.y);
+    u.y = pack_bf16x2(a.z, a.w);
+    u.z = pack_bf16x2(b.x, b.y);
+    u.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(packed + (size_t)kb * n_out * 128 + sw128_offset(r, ch)) = u;
+  }
+}
+
+}  // namespace axvs

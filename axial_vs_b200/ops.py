@@ -1,0 +1,287 @@
+"""Host-side operators over the C ABI (include/axvs.h): tensor checks, output/workspace allocation with the
+caching allocator, current-stream plumbing, and `torch.library` registration (`torch.ops.axialvs.*`).
+
+PyTorch is used for device memory and streams only; all arithmetic runs in libaxvs.so.  CPU tensors are
+rejected with a RuntimeError -- there is no CPU fallback (BASELINE.json north_star; same behaviour as the
+reference's native op, WC/ops/src/ms_deform_attn.h:43 `AT_ERROR("Not implemented on the CPU")`).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AXIS_H, AXIS_NONE, AXIS_W, LayerWeights, TaWeights  # noqa: F401
+
+C = 256          # d_model the kernels are specialised for
+HEADS = 8
+HEAD_DIM = 32
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _check(t: torch.Tensor, name: str, dtype: torch.dtype, shape: Optional[Sequence[int]] = None) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: axial_vs_b200 has no CPU implementation")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def workspace(nbytes: int, dev: torch.device) -> torch.Tensor:
+    """Per-(device, stream) scratch buffer, grown on demand; reuse is ordered by the stream itself."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(dev))
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _workspaces[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------ weights
+def pack_weight(w: torch.Tensor) -> torch.Tensor:
+    """fp32 nn.Linear weight [n_out, k] -> bf16 UMMA shared-memory image (uint8 tensor)."""
+    _check(w, "weight", torch.float32)
+    n_out, k = w.shape
+    lib = _lib.load()
+    out = torch.empty(lib.axvs_packed_weight_bytes(n_out, k), dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(lib.axvs_pack_weight(w.data_ptr(), n_out, k, out.data_ptr(), _stream(w.device)), "axvs_pack_weight")
+    return out
+
+
+@dataclass
+class PackedTA:
+    """Device-resident packed parameters of one TrajectoryAttention (struct axvs_ta_weights)."""
+    w_qkv: torch.Tensor
+    b_qkv: torch.Tensor
+    w_pq: torch.Tensor
+    b_pq: torch.Tensor
+    w_pkv: torch.Tensor
+    b_pkv: torch.Tensor
+    w_proj: torch.Tensor
+    b_proj: torch.Tensor
+
+    def tensors(self) -> List[torch.Tensor]:
+        return [self.w_qkv, self.b_qkv, self.w_pq, self.b_pq, self.w_pkv, self.b_pkv, self.w_proj, self.b_proj]
+
+    def struct(self) -> TaWeights:
+        return TaWeights(*[t.data_ptr() for t in self.tensors()])
+
+    @staticmethod
+    def from_tensors(ts: Sequence[torch.Tensor]) -> "PackedTA":
+        return PackedTA(*ts)
+
+
+def pack_ta(p: Dict[str, torch.Tensor], prefix: str = "") -> PackedTA:
+    """Pack a TrajectoryAttention state dict (leaf names q/k/v or qkv, proj_q, proj_kv, proj)."""
+    def g(name):
+        return p[prefix + name].detach().float().contiguous()
+
+    if prefix + "qkv.weight" in p:
+        wqkv, bqkv = g("qkv.weight"), g("qkv.bias")
+    else:
+        wqkv = torch.cat([g("q.weight"), g("k.weight"), g("v.weight")], 0).contiguous()
+        bqkv = torch.cat([g("q.bias"), g("k.bias"), g("v.bias")], 0).contiguous()
+    return PackedTA(pack_weight(wqkv), bqkv, pack_weight(g("proj_q.weight")), g("proj_q.bias"),
+                    pack_weight(g("proj_kv.weight")), g("proj_kv.bias"), pack_weight(g("proj.weight")), g("proj.bias"))
+
+
+@dataclass
+class PackedLayer:
+    """struct axvs_layer_weights."""
+    attn_h: PackedTA
+    attn_w: Optional[PackedTA]
+    ln1_g: torch.Tensor
+    ln1_b: torch.Tensor
+    w_ffn1: torch.Tensor
+    b_ffn1: torch.Tensor
+    w_ffn2: torch.Tensor
+    b_ffn2: torch.Tensor
+    ln2_g: torch.Tensor
+    ln2_b: torch.Tensor
+    d_ffn: int
+
+    def tensors(self) -> List[torch.Tensor]:
+        aw = self.attn_w if self.attn_w is not None else self.attn_h
+        return self.attn_h.tensors() + aw.tensors() + [self.ln1_g, self.ln1_b, self.w_ffn1, self.b_ffn1, self.w_ffn2,
+                                                       self.b_ffn2, self.ln2_g, self.ln2_b]
+
+    def struct(self) -> LayerWeights:
+        aw = self.attn_w if self.attn_w is not None else self.attn_h
+        return LayerWeights(self.attn_h.struct(), aw.struct(), self.ln1_g.data_ptr(), self.ln1_b.data_ptr(),
+                            self.w_ffn1.data_ptr(), self.b_ffn1.data_ptr(), self.w_ffn2.data_ptr(), self.b_ffn2.data_ptr(),
+                            self.ln2_g.data_ptr(), self.ln2_b.data_ptr(), self.d_ffn)
+
+    @staticmethod
+    def from_tensors(ts: Sequence[torch.Tensor], d_ffn: int) -> "PackedLayer":
+        return PackedLayer(PackedTA.from_tensors(ts[0:8]), PackedTA.from_tensors(ts[8:16]), *ts[16:24], d_ffn=d_ffn)
+
+
+def pack_layer(p: Dict[str, torch.Tensor], axial: bool = True) -> PackedLayer:
+    """Pack the state dict of a Temporal(Axial)TrajectoryAttentionLayer (WC/temporal_attention.py:159-175)."""
+    def g(name):
+        return p[name].detach().float().contiguous()
+
+    ah = pack_ta(p, "height_attn." if axial else "temporal_attn.")
+    aw = pack_ta(p, "width_attn.") if axial else None
+    return PackedLayer(ah, aw, g("norm1.weight"), g("norm1.bias"), pack_weight(g("linear1.weight")), g("linear1.bias"),
+                       pack_weight(g("linear2.weight")), g("linear2.bias"), g("norm2.weight"), g("norm2.bias"),
+                       d_ffn=p["linear1.weight"].shape[0])
+
+
+# ------------------------------------------------------------------------------------------------ operators
+def linear(a: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], n_out: int, *, scale: float = 1.0,
+           relu: bool = False, out_dtype: torch.dtype = torch.bfloat16, resid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act((a @ W^T + bias) * scale) (+ resid): tcgen05 GEMM.  a bf16 [M, K]."""
+    _check(a, "a", torch.bfloat16)
+    M, K = a.shape
+    out = torch.empty(M, n_out, dtype=out_dtype, device=a.device)
+    if resid is not None:
+        _check(resid, "resid", torch.float32, (M, n_out))
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        rc = lib.axvs_linear(a.data_ptr(), K, M, K, w_packed.data_ptr(), _ptr(bias), n_out, scale, int(relu), out.data_ptr(),
+                             n_out, int(out_dtype == torch.bfloat16), _ptr(resid), _stream(a.device))
+    _lib.check(rc, "axvs_linear")
+    return out
+
+
+def spatial_attention(qkv: torch.Tensor, num_seq: int, F: int, n: int) -> torch.Tensor:
+    """Per-frame-softmax attention: qkv bf16 [num_seq*F*n, 768] -> x bf16 [num_seq*F*n, F, 256]."""
+    _check(qkv, "qkv", torch.bfloat16, (num_seq * F * n, 768))
+    x = torch.empty(num_seq * F * n, F, C, dtype=torch.bfloat16, device=qkv.device)
+    lib = _lib.load()
+    with torch.cuda.device(qkv.device):
+        _lib.check(lib.axvs_spatial_attention(qkv.data_ptr(), x.data_ptr(), num_seq, F, n, _stream(qkv.device)),
+                   "axvs_spatial_attention")
+    return x
+
+
+def traj_attn_fwd(q_in: torch.Tensor, k_in: torch.Tensor, v_in: torch.Tensor, pos: Optional[torch.Tensor],
+                  resid: Optional[torch.Tensor], w: PackedTA, B: int, T: int, H: int, W: int, axis: int) -> torch.Tensor:
+    """out = resid + TrajectoryAttention(q_in + pos, k_in + pos, v_in) on canonical [(B T)(H W), 256] fp32 tensors."""
+    rows = B * T * H * W
+    for nm, t in (("q_in", q_in), ("k_in", k_in), ("v_in", v_in)):
+        _check(t, nm, torch.float32)
+        if t.numel() != rows * C:
+            raise RuntimeError(f"{nm} has {t.numel()} elements, expected {rows}x{C}")
+    if pos is not None:
+        _check(pos, "pos", torch.float32)
+        if pos.numel() != rows * C:
+            raise RuntimeError("pos size mismatch")
+    if resid is not None:
+        _check(resid, "resid", torch.float32)
+    out = torch.empty(rows, C, dtype=torch.float32, device=q_in.device)
+    lib = _lib.load()
+    nbytes = lib.axvs_traj_attn_workspace_bytes(B, T, H, W)
+    with torch.cuda.device(q_in.device):
+        ws = workspace(nbytes, q_in.device)
+        st = w.struct()
+        rc = lib.axvs_traj_attn_fwd(q_in.data_ptr(), k_in.data_ptr(), v_in.data_ptr(), _ptr(pos), _ptr(resid), out.data_ptr(),
+                                    ctypes.byref(st), B, T, H, W, axis, ws.data_ptr(), ws.numel(), _stream(q_in.device))
+    _lib.check(rc, "axvs_traj_attn_fwd")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    _check(x, "x", torch.float32)
+    rows = x.numel() // C
+    y = torch.empty_like(x)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.axvs_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), None, rows, eps,
+                                      _stream(x.device)), "axvs_layernorm")
+    return y
+
+
+def axial_layer_fwd(src: torch.Tensor, pos: torch.Tensor, w: PackedLayer, axial: bool = True) -> torch.Tensor:
+    """Temporal(Axial)TrajectoryAttentionLayer.forward: src [(B T), (H W), 256], pos [B, T, H, W, 256] (fp32)."""
+    _check(src, "src", torch.float32)
+    _check(pos, "pos", torch.float32)
+    if pos.dim() != 5 or pos.shape[-1] != C:
+        raise RuntimeError(f"pos must be [B, T, H, W, {C}], got {tuple(pos.shape)}")
+    B, T, H, W, _ = pos.shape
+    if tuple(src.shape) != (B * T, H * W, C):
+        raise RuntimeError(f"src must be [(B T)={B * T}, (H W)={H * W}, {C}], got {tuple(src.shape)}")
+    if src.device != pos.device:
+        raise RuntimeError("src and pos must be on the same device")
+    out = torch.empty_like(src)
+    lib = _lib.load()
+    nbytes = lib.axvs_layer_workspace_bytes(B, T, H, W, w.d_ffn)
+    with torch.cuda.device(src.device):
+        ws = workspace(nbytes, src.device)
+        st = w.struct()
+        rc = lib.axvs_axial_layer_fwd(src.data_ptr(), pos.data_ptr(), out.data_ptr(), ctypes.byref(st), B, T, H, W, int(axial),
+                                      ws.data_ptr(), ws.numel(), _stream(src.device))
+    _lib.check(rc, "axvs_axial_layer_fwd")
+    return out
+
+
+def pos3d(B: int, T: int, H: int, W: int, level_embed: Optional[torch.Tensor], device) -> torch.Tensor:
+    """PositionEmbeddingSine3D(128, normalize=True) table + level embed, channels-last fp32 [B,T,H,W,256]."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("pos3d: CUDA device required (no CPU implementation)")
+    if level_embed is not None:
+        _check(level_embed, "level_embed", torch.float32, (C,))
+    out = torch.empty(B, T, H, W, C, dtype=torch.float32, device=device)
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        _lib.check(lib.axvs_pos3d(out.data_ptr(), _ptr(level_embed), B, T, H, W, _stream(device)), "axvs_pos3d")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ torch.library
+# Thin custom-op registration so the kernels are visible as torch.ops.axialvs.* (schema-checked, fake-tensor aware).
+@torch.library.custom_op("axialvs::axial_layer_fwd", mutates_args=(), device_types="cuda")
+def _axial_layer_op(src: torch.Tensor, pos: torch.Tensor, weights: Sequence[torch.Tensor], d_ffn: int, axial: bool) -> torch.Tensor:
+    return axial_layer_fwd(src, pos, PackedLayer.from_tensors(list(weights), d_ffn), axial)
+
+
+@_axial_layer_op.register_fake
+def _(src, pos, weights, d_ffn, axial):
+    return torch.empty_like(src)
+
+
+@torch.library.custom_op("axialvs::pos3d", mutates_args=(), device_types="cuda")
+def _pos3d_op(like: torch.Tensor, level_embed: torch.Tensor, B: int, T: int, H: int, W: int) -> torch.Tensor:
+    return pos3d(B, T, H, W, level_embed, like.device)
+
+
+@_pos3d_op.register_fake
+def _(like, level_embed, B, T, H, W):
+    return like.new_empty(B, T, H, W, C, dtype=torch.float32)
+
+
+def ln_ffn_fwd(x: torch.Tensor, w: PackedLayer) -> torch.Tensor:
+    """out = LN2(s + W2 relu(W1 s + b1) + b2), s = LN1(x);  x fp32 [rows, 256]."""
+    _check(x, "x", torch.float32)
+    rows = x.numel() // C
+    out = torch.empty_like(x)
+    lib = _lib.load()
+    nbytes = lib.axvs_ffn_workspace_bytes(rows, w.d_ffn)
+    with torch.cuda.device(x.device):
+        ws = workspace(nbytes, x.device)
+        st = w.struct()
+        rc = lib.axvs_ln_ffn_fwd(x.data_ptr(), out.data_ptr(), ctypes.byref(st), rows, ws.data_ptr(), ws.numel(), _stream(x.device))
+    _lib.check(rc, "axvs_ln_ffn_fwd")
+    return out

@@ -1,0 +1,125 @@
+/* axvs.h -- C ABI of libaxvs.so: B200 (sm_100a) kernels for Axial-VS / MaXTron's axial-trajectory attention.
+ *
+ * Drop-in boundary.  The reference has no FFI of its own for this path: it is eager PyTorch
+ * (nn.Linear / einsum / softmax / LayerNorm).  Each entry point below names the reference lines it
+ * replaces ("Vk/" = MaXTron_Video-kMaX/, "WC/" = Vk/maxtron_deeplab/modeling/within_clip_tracking_module/,
+ * "CC" = Vk/maxtron_deeplab/modeling/cross_clip_tracking_module/maxtron_cross_clip_tracking_module.py,
+ * "TL/" = MaXTron_Tube-Link/).  The convention mirrors the reference's one native op
+ * (WC/ops/src/cuda/ms_deform_attn_cuda.cu:25-85): contiguous device tensors in, work enqueued on the caller's
+ * stream, nothing retained after the call.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer in the current CUDA context unless it says "host";
+ *   - `stream` is a cudaStream_t / CUstream passed as void* (0 = legacy default stream);
+ *   - return 0 on success, a negative AXVS_E_* code otherwise; axvs_last_error() gives the message
+ *     (thread-local).  No C++ exception crosses this boundary.  No host synchronisation, no allocation:
+ *     the caller owns all buffers including the workspace -> every call is CUDA-graph capturable;
+ *   - fp32 tensors are the reference's tensors (row-major, channels last, C = 256); bf16 buffers are internal;
+ *   - the path is specialised for d_model C = 256, 8 heads of 32 (every shipped config: Vk config.py:21-34,
+ *     CC:236-246, TL configs embed_dims=256 num_heads=8); other sizes return AXVS_E_UNSUPPORTED.
+ */
+#ifndef AXVS_H_
+#define AXVS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AXVS_OK 0
+#define AXVS_E_INVALID (-1)     /* bad argument (null pointer, non-positive size, misalignment) */
+#define AXVS_E_UNSUPPORTED (-2) /* shape outside the specialisation (C != 256, K % 64, n_out % 256 ...) */
+#define AXVS_E_WORKSPACE (-3)   /* workspace too small */
+#define AXVS_E_CUDA (-4)        /* CUDA runtime error at launch */
+
+typedef void* axvs_stream_t;
+
+/* Row order of the sequences handed to a trajectory attention call. */
+#define AXVS_AXIS_NONE 0   /* rows already in sequence order (cross-clip, non-axial "trajectory" layer)      */
+#define AXVS_AXIS_H 1      /* height pass: '(B T)(H W) C -> (B W)(T H) C'   WC/temporal_attention.py:197     */
+#define AXVS_AXIS_W 2      /* width pass:  '... -> (B H)(T W) C'            WC/temporal_attention.py:206     */
+
+int axvs_version(void);
+const char* axvs_last_error(void);
+
+/* ---- weights ------------------------------------------------------------------------------------------------
+ * nn.Linear weights [n_out, k] fp32 are converted once to bf16 and laid out as the shared-memory image the
+ * tensor-core kernels consume (K-blocks of 64, 8-row x 128-byte swizzle atoms), so that one TMA bulk copy
+ * brings a weight tile in.  n_out % 8 == 0, k % 64 == 0. */
+size_t axvs_packed_weight_bytes(int n_out, int k);
+int axvs_pack_weight(const float* w, int n_out, int k, void* packed, axvs_stream_t stream);
+
+/* One TrajectoryAttention's parameters (WC/temporal_attention.py:27-33; CC:85-89; TL .../msdeformattn_pixel_decoder.py:659-665).
+ * w_qkv packs rows [Wq; Wk; Wv] (or the fused `qkv` Linear of the cross-clip variant): [768, 256]. */
+typedef struct axvs_ta_weights {
+  const void* w_qkv;  const float* b_qkv;    /* packed [768,256], bias [768] */
+  const void* w_pq;   const float* b_pq;     /* proj_q   [256,256]           */
+  const void* w_pkv;  const float* b_pkv;    /* proj_kv  [512,256]           */
+  const void* w_proj; const float* b_proj;   /* proj     [256,256]           */
+} axvs_ta_weights;
+
+/* One Temporal(Axial)TrajectoryAttentionLayer (WC/temporal_attention.py:159-175 / :104-119). */
+typedef struct axvs_layer_weights {
+  axvs_ta_weights attn_h;                    /* height_attn  (or temporal_attn of the non-axial layer) */
+  axvs_ta_weights attn_w;                    /* width_attn   (unused for the non-axial layer)          */
+  const float* ln1_g; const float* ln1_b;    /* norm1 */
+  const void* w_ffn1; const float* b_ffn1;   /* linear1 packed [1024,256] */
+  const void* w_ffn2; const float* b_ffn2;   /* linear2 packed [256,1024] */
+  const float* ln2_g; const float* ln2_b;    /* norm2 */
+  int d_ffn;                                 /* 1024 */
+} axvs_layer_weights;
+
+/* ---- building blocks (each is also a test surface) ------------------------------------------------------------ */
+
+/* out[M, n_out] = act((A[M,K] @ W^T + bias) * scale) (+ resid), tcgen05 GEMM.  A bf16 row-major (lda elements).
+ * out_bf16 != 0 -> bf16 output, else fp32 (+ optional fp32 residual with the same leading dimension).
+ * Replaces every nn.Linear on the path (WC/temporal_attention.py:42-44,64-65,75,182). */
+int axvs_linear(const void* a_bf16, int lda, int M, int K, const void* w_packed, const float* bias, int n_out,
+                float scale, int relu, void* out, int ldo, int out_bf16, const float* resid, axvs_stream_t stream);
+
+/* Per-frame-softmax spatial attention (WC/temporal_attention.py:47-60; CC:101-110).
+ * qkv bf16 [num_seq*N, 768] (q | k | v, heads of 32), N = F*n.  x bf16 [num_seq*N, F, 256]. */
+int axvs_spatial_attention(const void* qkv_bf16, void* x_bf16, int num_seq, int F, int n, axvs_stream_t stream);
+
+/* Full TrajectoryAttention forward + residual:
+ *     out = resid + TA(query = q_in + pos, key = k_in + pos, value = v_in)
+ * (WC/temporal_attention.py:35-76 and the residual add :204 / :213; CC:91-130,158-159 with pos = NULL and
+ * q_in = k_in = v_in).  q_in/k_in/v_in/pos/resid/out fp32 canonical [(B T)(H W), 256]; the layer passes
+ * q_in = k_in = v_in = src (:200-202).  `axis` selects how canonical tokens form sequences:
+ *   AXVS_AXIS_H: B*W sequences of T*H tokens, AXVS_AXIS_W: B*H sequences of T*W tokens,
+ *   AXVS_AXIS_NONE: B sequences of T*(H*W) tokens in storage order (frames of n = H*W tokens).
+ * pos and resid may be NULL (resid NULL = the bare nn.Module `TrajectoryAttention.forward`). */
+size_t axvs_traj_attn_workspace_bytes(int B, int T, int H, int W);
+int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, const float* pos, const float* resid,
+                       float* out, const axvs_ta_weights* w, int B, int T, int H, int W, int axis,
+                       void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+
+/* y = LayerNorm(x) over C = 256 (nn.LayerNorm, biased variance).  y32 and/or y16 may be NULL. */
+int axvs_layernorm(const float* x, const float* gamma, const float* beta, float* y32, void* y16_bf16, int rows,
+                   float eps, axvs_stream_t stream);
+
+/* out = LN2(s + W2 relu(W1 s + b1) + b2), s = LN1(x)   (WC/temporal_attention.py:181-185,217-218). */
+size_t axvs_ffn_workspace_bytes(int rows, int d_ffn);
+int axvs_ln_ffn_fwd(const float* x, float* out, const axvs_layer_weights* w, int rows,
+                    void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+
+/* ---- layers --------------------------------------------------------------------------------------------------- */
+
+/* TemporalAxialTrajectoryAttentionLayer.forward (WC/temporal_attention.py:187-220; TL copy :753-791):
+ * src [(B T), (H W), 256], pos [B, T, H, W, 256] -> out (same shape as src).  axial = 0 runs the non-axial
+ * TemporalTrajectoryAttentionLayer (:131-155) using attn_h only. */
+size_t axvs_layer_workspace_bytes(int B, int T, int H, int W, int d_ffn);
+int axvs_axial_layer_fwd(const float* src, const float* pos, float* out, const axvs_layer_weights* w,
+                         int B, int T, int H, int W, int axial,
+                         void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+
+/* PositionEmbeddingSine3D(num_pos_feats=128, normalize=True) + level_embed_3d[lvl], channels-last
+ * (WC/pos_embeddings.py:86-130, WC/msdeformattn.py:112-115).  out fp32 [B,T,H,W,256]; level_embed may be NULL. */
+int axvs_pos3d(float* out, const float* level_embed, int B, int T, int H, int W, axvs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AXVS_H_ */

@@ -1,0 +1,247 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed reference goldens.
+
+Tolerance (BASELINE.json north_star): bf16 compute / fp32 accumulate, max-abs error normalised by the
+max-abs of the reference tensor <= 1e-2 on attention / layer outputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from axial_vs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+def nerr(a: torch.Tensor, ref: torch.Tensor) -> float:
+    a, ref = a.detach().float().cpu(), ref.detach().float().cpu()
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    assert torch.isfinite(a).all(), "non-finite values in CUDA output"
+    return ((a - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from axial_vs_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import traj_oracle
+    return traj_oracle
+
+
+# --------------------------------------------------------------------------------------------- GEMM engine
+@pytest.mark.parametrize("M,K,N", [(128, 256, 256), (300, 256, 512), (1000, 1024, 256), (77, 64, 768), (20000, 256, 1024)])
+def test_linear_bf16(ops, M, K, N):
+    g = torch.Generator().manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    out = ops.linear(a, ops.pack_weight(w), b, N)
+    ref = a.float() @ w.bfloat16().float().t() + b
+    assert nerr(out, ref) < 6e-3   # bf16 output rounding only
+
+
+def test_linear_epilogues(ops):
+    g = torch.Generator().manual_seed(7)
+    M, K, N = 513, 256, 256
+    a = torch.randn(M, K, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / 16).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    r = torch.randn(M, N, generator=g).cuda()
+    wp = ops.pack_weight(w)
+    base = a.float() @ w.bfloat16().float().t() + b
+    assert nerr(ops.linear(a, wp, b, N, out_dtype=torch.float32), base) < 1e-5
+    assert nerr(ops.linear(a, wp, b, N, out_dtype=torch.float32, resid=r), base + r) < 1e-5
+    assert nerr(ops.linear(a, wp, b, N, relu=True, out_dtype=torch.float32), base.relu()) < 1e-5
+    assert nerr(ops.linear(a, wp, b, N, scale=0.25, out_dtype=torch.float32), base * 0.25) < 1e-5
+    assert nerr(ops.linear(a, wp, None, N, out_dtype=torch.float32), base - b) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------- spatial attention
+@pytest.mark.parametrize("S,F,n", [(3, 2, 5), (2, 3, 41), (1, 2, 70), (2, 1, 130), (1, 5, 64)])
+def test_spatial_attention(ops, S, F, n):
+    g = torch.Generator().manual_seed(S * 100 + F * 10 + n)
+    N = F * n
+    qkv = torch.randn(S * N, 768, generator=g).bfloat16().cuda()
+    x = ops.spatial_attention(qkv, S, F, n)                      # [S*N, F, 256]
+    q, k, v = (t.float().reshape(S, N, 8, 32).permute(0, 2, 1, 3) for t in qkv.split(256, dim=1))
+    ref = torch.empty(S, N, F, 256, device="cuda")
+    for f in range(F):
+        kf, vf = k[:, :, f * n:(f + 1) * n], v[:, :, f * n:(f + 1) * n]
+        a = torch.softmax(32 ** -0.5 * q @ kf.transpose(-1, -2), -1)
+        ref[:, :, f] = (a @ vf).permute(0, 2, 1, 3).reshape(S, N, 256)
+    assert nerr(x.reshape(S, N, F, 256), ref) < 1e-2
+
+
+# --------------------------------------------------------------------------------------------- trajectory attention
+def _ta_case(ops, O, Bp, F, n, seed, fused_qkv=False):
+    p = {}
+    synth.traj_attn_params(torch.Generator().manual_seed(seed), "", 256, p, fused_qkv=fused_qkv)
+    q = synth.randn(seed + 100, Bp, F * n, 256)
+    v = synth.randn(seed + 200, Bp, F * n, 256)
+    pk = ops.pack_ta({k_: t.cuda() for k_, t in p.items()})
+    return p, q, v, pk
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_trajectory_attention_golden(ops, golden, tag):
+    gz = golden(f"ta_vk_{tag}")
+    Bp, F, n, seed = int(gz["Bp"]), int(gz["F"]), int(gz["n"]), int(gz["seed"])
+    p, q, v, pk = _ta_case(ops, None, Bp, F, n, seed)
+    assert synth.checksum(p) == pytest.approx(float(gz["wsum"]), rel=1e-12)
+    qc, vc = q.reshape(-1, 256).cuda(), v.reshape(-1, 256).cuda()
+    out = ops.traj_attn_fwd(qc, qc, vc, None, None, pk, Bp, F, n, 1, ops.AXIS_NONE)
+    assert nerr(out.reshape(Bp, F * n, 256), torch.from_numpy(gz["y"])) < TOL
+
+
+@pytest.mark.parametrize("Bp,F,n", [(5, 2, 41), (2, 5, 30), (1, 10, 33), (1, 2, 200)])
+def test_trajectory_attention_oracle(ops, O, Bp, F, n):
+    p, q, v, pk = _ta_case(ops, O, Bp, F, n, 1000 + Bp + F + n)
+    ref, _ = O.trajectory_attention(q, q, v, p, F)
+    qc, vc = q.reshape(-1, 256).cuda(), v.reshape(-1, 256).cuda()
+    out = ops.traj_attn_fwd(qc, qc, vc, None, None, pk, Bp, F, n, 1, ops.AXIS_NONE)
+    assert nerr(out.reshape(Bp, F * n, 256), ref) < TOL
+
+
+def test_trajectory_attention_module_separate_key(O):
+    """nn.Module API with key is not query (general reference signature)."""
+    from axial_vs_b200 import modules
+    p = {}
+    synth.traj_attn_params(torch.Generator().manual_seed(9), "", 256, p)
+    q, k, v = synth.randn(1, 2, 24, 256), synth.randn(2, 2, 24, 256), synth.randn(3, 2, 24, 256)
+    ref, _ = O.trajectory_attention(q, k, v, p, 3)
+    m = modules.TrajectoryAttention(256, 8, 0.0).eval()
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    with torch.no_grad():
+        out, maps = m(q.cuda(), k.cuda(), v.cuda(), num_frames=3)
+    assert maps is None
+    assert nerr(out, ref) < TOL
+
+
+# --------------------------------------------------------------------------------------------- layers / encoder
+def _layer(p, axial=True):
+    from axial_vs_b200 import modules
+    cls = modules.TemporalAxialTrajectoryAttentionLayer if axial else modules.TemporalTrajectoryAttentionLayer
+    m = cls(256, 1024, 0.0, 0.0, "relu", 8).eval()
+    m.load_state_dict(p, strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_axial_layer_golden(O, golden, tag):
+    gz = golden(f"axial_layer_{tag}")
+    B, T, H, W, seed = (int(gz[k]) for k in "B T H W seed".split())
+    p = synth.axial_layer_params(seed)
+    src = synth.randn(seed + 100, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 200)[0])
+    with torch.no_grad():
+        out, hm, wm = _layer(p)(src.cuda(), pos.cuda())
+    assert hm is None and wm is None
+    assert nerr(out, torch.from_numpy(gz["out"])) < TOL
+
+
+def test_encoder_golden(O, golden):
+    from axial_vs_b200 import modules
+    gz = golden("encoder_axial")
+    B, T, H, W, seed = (int(gz[k]) for k in "B T H W seed".split())
+    p = synth.encoder_params(seed, 2)
+    enc = modules.TemporalEncoder(256, 1024, 0.0, 0.0, "relu", 8, "axial-trajectory", 2).eval()
+    enc.load_state_dict(p, strict=True)
+    enc.cuda()
+    src = synth.randn(seed + 100, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 200)[1])
+    with torch.no_grad():
+        out, _, _ = enc(src.cuda(), pos.cuda())
+    assert nerr(out, torch.from_numpy(gz["out"])) < TOL
+
+
+def test_trajectory_encoder_golden(O, golden):
+    from axial_vs_b200 import modules
+    gz = golden("encoder_trajectory")
+    B, T, H, W, seed = (int(gz[k]) for k in "B T H W seed".split())
+    p = synth.encoder_params(seed, 1, axial=False)
+    enc = modules.TemporalEncoder(256, 1024, 0.0, 0.0, "relu", 8, "trajectory", 1).eval()
+    enc.load_state_dict(p, strict=True)
+    enc.cuda()
+    src = synth.randn(seed + 100, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 200)[0])
+    with torch.no_grad():
+        out, _, _ = enc(src.cuda(), pos.cuda())
+    assert nerr(out, torch.from_numpy(gz["out"])) < TOL
+
+
+@pytest.mark.parametrize("B,T,H,W", [(1, 2, 41, 41), (1, 2, 21, 21), (2, 5, 15, 20), (3, 2, 13, 29)])
+def test_axial_layer_oracle_config_sizes(O, B, T, H, W):
+    """BASELINE config 1 (T=2, 41x41), res5 level, Tube-Link-shaped (T=5, 15x20) and a ragged batch."""
+    seed = 500 + B + T + H + W
+    p = synth.axial_layer_params(seed)
+    src = synth.randn(seed + 1, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 2)[0])
+    ref, _, _ = O.axial_layer(src, pos, p)
+    with torch.no_grad():
+        out, _, _ = _layer(p)(src.cuda(), pos.cuda())
+    e = nerr(out, ref)
+    cos = torch.nn.functional.cosine_similarity(out.cpu().flatten(), ref.flatten(), dim=0).item()
+    assert e < TOL and cos > 0.9999, (e, cos)
+
+
+def test_encoder_config1_two_layers(O):
+    """BASELINE config 1: TemporalEncoder(axial-trajectory, 2 layers) on T=2, 41x41x256."""
+    from axial_vs_b200 import modules
+    B, T, H, W, seed = 1, 2, 41, 41, 0
+    p = synth.encoder_params(seed, 2)
+    enc = modules.TemporalEncoder(256, 1024, 0.0, 0.0, "relu", 8, "axial-trajectory", 2).eval()
+    enc.load_state_dict(p, strict=True)
+    enc.cuda()
+    src = synth.randn(1, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(2)[1])
+    ref, _, _ = O.temporal_encoder(src, pos, O.split_encoder_params(p))
+    with torch.no_grad():
+        out, _, _ = enc(src.cuda(), pos.cuda())
+    assert nerr(out, ref) < TOL
+
+
+# --------------------------------------------------------------------------------------------- positional table
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_pos3d_golden(ops, golden, tag):
+    gz = golden(f"pos3d_{tag}")
+    B, T, H, W = (int(gz[k]) for k in "B T H W".split())
+    out = ops.pos3d(B, T, H, W, None, "cuda")
+    assert (out.cpu() - torch.from_numpy(gz["table"])).abs().max().item() < 2e-5
+    le = synth.level_embed(3)[1].cuda()
+    out2 = ops.pos3d(B, T, H, W, le, "cuda")
+    assert (out2 - out - le).abs().max().item() < 1e-6
+
+
+# --------------------------------------------------------------------------------------------- properties / errors
+def test_batch_independence(O):
+    """Clips are independent (the sharding invariant): batching B clips == running them one at a time."""
+    B, T, H, W = 3, 2, 9, 11
+    p = synth.axial_layer_params(123)
+    layer = _layer(p)
+    src = synth.randn(5, B * T, H * W, 256).cuda()
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(6)[0]).cuda()
+    with torch.no_grad():
+        full, _, _ = layer(src, pos)
+        for b in range(B):
+            one, _, _ = layer(src[b * T:(b + 1) * T].contiguous(), pos[b:b + 1].contiguous())
+            assert torch.equal(one, full[b * T:(b + 1) * T]), "per-clip result differs from the batched result"
+
+
+def test_cpu_tensor_is_rejected():
+    from axial_vs_b200 import modules
+    layer = modules.TemporalAxialTrajectoryAttentionLayer().eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        layer(torch.zeros(2, 4, 256), torch.zeros(1, 2, 2, 2, 256))
+
+
+def test_training_mode_is_rejected():
+    from axial_vs_b200 import modules
+    layer = modules.TemporalAxialTrajectoryAttentionLayer().cuda().train()
+    with pytest.raises(RuntimeError, match="inference"):
+        layer(torch.zeros(2, 4, 256, device="cuda"), torch.zeros(1, 2, 2, 2, 256, device="cuda"))
