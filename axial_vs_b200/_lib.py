@@ -46,6 +46,10 @@ SIGNATURES = {
     "axvs_axial_layer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(LayerWeights), c_int, c_int, c_int, c_int,
                                      c_int, c_void_p, c_size_t, c_void_p]),
     "axvs_pos3d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "axvs_profile_enable": (c_int, [c_int]),
+    "axvs_profile_num_classes": (c_int, []),
+    "axvs_profile_class_name": (c_char_p, [c_int]),
+    "axvs_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

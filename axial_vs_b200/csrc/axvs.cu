@@ -24,6 +24,35 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_COUNT };
+const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
+                                            "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel"};
+struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
+constexpr int PROF_MAX = 8192;
+struct Profiler {
+  bool on = false;
+  int n = 0;
+  int created = 0;
+  ProfRec rec[PROF_MAX];
+  long long launches[KC_COUNT] = {0};
+} g_prof;
+
+struct ProfScope {
+  int idx = -1;
+  cudaStream_t st;
+  ProfScope(int cls, double flops, double bytes, cudaStream_t s) : st(s) {
+    g_prof.launches[cls]++;
+    if (!g_prof.on || g_prof.n >= PROF_MAX) return;
+    idx = g_prof.n++;
+    ProfRec& r = g_prof.rec[idx];
+    if (idx >= g_prof.created) { cudaEventCreate(&r.a); cudaEventCreate(&r.b); g_prof.created = idx + 1; }
+    r.cls = cls; r.flops = flops; r.bytes = bytes;
+    cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof.rec[idx].b, st); }
+};
+
 #define AXVS_CHECK_LAUNCH(what)                                                            \
   do {                                                                                     \
     cudaError_t e_ = cudaGetLastError();                                                   \
@@ -72,7 +101,12 @@ int launch_gemm(const GemmParams& p, cudaStream_t st) {
   if (rc) return rc;
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * (p.n_out / GEMM_BN);
   const int grid = tiles < d->sms ? tiles : d->sms;
-  gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p);
+  {
+    const double out_b = p.out_bf16 ? 2.0 : 4.0;
+    ProfScope ps(KC_GEMM, 2.0 * p.M * (double)p.K * p.n_out,
+                 (double)p.M * p.K * 2 + (double)p.n_out * p.K * 2 + (double)p.M * p.n_out * (out_b + (p.resid ? 4.0 : 0.0)), st);
+    gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p);
+  }
   AXVS_CHECK_LAUNCH("gemm_bf16_kernel");
   return AXVS_OK;
 }
@@ -166,7 +200,10 @@ int axvs_pack_weight(const float* w, int n_out, int k, void* packed, axvs_stream
   if (!w || !packed) return fail(AXVS_E_INVALID, "pack_weight: null pointer");
   if (n_out <= 0 || n_out % 8 || k <= 0 || k % 64) return fail(AXVS_E_UNSUPPORTED, "pack_weight: need n_out %% 8 == 0 and k %% 64 == 0 (got %d, %d)", n_out, k);
   const int total = n_out * (k / 8);
-  pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_out, k, reinterpret_cast<uint8_t*>(packed));
+  {
+    ProfScope ps(KC_PACKW, 0, (double)n_out * k * 6, (cudaStream_t)stream);
+    pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_out, k, reinterpret_cast<uint8_t*>(packed));
+  }
   AXVS_CHECK_LAUNCH("pack_weight_kernel");
   return AXVS_OK;
 }
@@ -188,8 +225,11 @@ int axvs_spatial_attention(const void* qkv_bf16, void* x_bf16, int num_seq, int 
   const int N = F * n;
   dim3 grid((N + ATT_QT - 1) / ATT_QT, num_seq, 8);
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;   // 32^-0.5 * log2(e)
-  spatial_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), 768, 0, 256, 512,
-                                                              reinterpret_cast<__nv_bfloat16*>(x_bf16), N, n, F, scale_log2e);
+  {
+    ProfScope ps(KC_ATTN, 4.0 * num_seq * (double)N * N * 256, (double)num_seq * N * (768.0 * 2 + F * 512.0), (cudaStream_t)stream);
+    spatial_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), 768, 0, 256, 512,
+                                                                reinterpret_cast<__nv_bfloat16*>(x_bf16), N, n, F, scale_log2e);
+  }
   AXVS_CHECK_LAUNCH("spatial_attn_kernel");
   return AXVS_OK;
 }
@@ -229,13 +269,18 @@ int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, 
   const bool same_qk = (k_in == q_in);
   const bool same_all = same_qk && (v_in == q_in) && !pos;
   const bool v_from_q = (v_in == q_in);
-  pack_kq_kernel<<<pk_blocks, 256, 0, st>>>(q_in, pos, ws.a1, (v_from_q && !same_all) ? ws.a2 : nullptr, (int)rows, map, dims);
+  {
+    ProfScope ps(KC_PACK, 0, (double)rows * 256 * ((pos ? 8.0 : 4.0) + ((v_from_q && !same_all) ? 4.0 : 2.0)), st);
+    pack_kq_kernel<<<pk_blocks, 256, 0, st>>>(q_in, pos, ws.a1, (v_from_q && !same_all) ? ws.a2 : nullptr, (int)rows, map, dims);
+  }
   AXVS_CHECK_LAUNCH("pack_kq_kernel");
   if (!v_from_q) {
+    ProfScope ps(KC_PACK, 0, (double)rows * 256 * 6.0, st);
     pack_kq_kernel<<<pk_blocks, 256, 0, st>>>(v_in, nullptr, ws.a2, nullptr, (int)rows, map, dims);
     AXVS_CHECK_LAUNCH("pack_kq_kernel(v)");
   }
   if (!same_qk) {
+    ProfScope ps(KC_PACK, 0, (double)rows * 256 * (pos ? 10.0 : 6.0), st);
     pack_kq_kernel<<<pk_blocks, 256, 0, st>>>(k_in, pos, ws.a3, nullptr, (int)rows, map, dims);
     AXVS_CHECK_LAUNCH("pack_kq_kernel(k)");
   }
@@ -274,7 +319,10 @@ int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, 
     if ((rc = launch_gemm(p, st))) return rc;
   }
   // 6. temporal softmax over frames -> o
-  temporal_attn_kernel<<<(int)((rows * 8 + 127) / 128), 128, 0, st>>>(ws.q2, ws.kv2, ws.o, (int)rows, F);
+  {
+    ProfScope ps(KC_TEMPORAL, 4.0 * rows * F * 256, (double)rows * (1024.0 + F * 1024.0), st);
+    temporal_attn_kernel<<<(int)((rows * 8 + 127) / 128), 128, 0, st>>>(ws.q2, ws.kv2, ws.o, (int)rows, F);
+  }
   AXVS_CHECK_LAUNCH("temporal_attn_kernel");
   // 7. out[c] = resid[c] + proj(o)[p]   (scatter back to canonical order)
   {
@@ -292,7 +340,10 @@ int axvs_layernorm(const float* x, const float* gamma, const float* beta, float*
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
-  layernorm256_kernel<<<blocks_for(rows, 8, d->sms), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y32, reinterpret_cast<__nv_bfloat16*>(y16_bf16), rows, eps);
+  {
+    ProfScope ps(KC_LN, 0, (double)rows * 256 * (4.0 + (y32 ? 4.0 : 0.0) + (y16_bf16 ? 2.0 : 0.0)), (cudaStream_t)stream);
+    layernorm256_kernel<<<blocks_for(rows, 8, d->sms), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y32, reinterpret_cast<__nv_bfloat16*>(y16_bf16), rows, eps);
+  }
   AXVS_CHECK_LAUNCH("layernorm256_kernel");
   return AXVS_OK;
 }
@@ -358,8 +409,34 @@ int axvs_pos3d(float* out, const float* level_embed, int B, int T, int H, int W,
   DeviceInfo* d;
   if ((rc = device_info(&d))) return rc;
   const long long total = (long long)T * H * W * 128;
-  pos3d_kernel<<<blocks_for(total, 256, d->sms), 256, 0, (cudaStream_t)stream>>>(out, level_embed, B, T, H, W);
+  {
+    ProfScope ps(KC_POS, 0, (double)B * T * H * W * 1024.0, (cudaStream_t)stream);
+    pos3d_kernel<<<blocks_for(total, 256, d->sms), 256, 0, (cudaStream_t)stream>>>(out, level_embed, B, T, H, W);
+  }
   AXVS_CHECK_LAUNCH("pos3d_kernel");
+  return AXVS_OK;
+}
+
+int axvs_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.n = 0;
+  for (int i = 0; i < KC_COUNT; ++i) g_prof.launches[i] = 0;
+  return AXVS_OK;
+}
+
+int axvs_profile_num_classes(void) { return KC_COUNT; }
+const char* axvs_profile_class_name(int cls) { return (cls >= 0 && cls < KC_COUNT) ? kclass_names[cls] : ""; }
+
+int axvs_profile_read(double* ms, double* flops, double* bytes, long long* launches, long long* timed) {
+  if (!ms || !flops || !bytes || !launches || !timed) return fail(AXVS_E_INVALID, "profile_read: null pointer");
+  for (int i = 0; i < KC_COUNT; ++i) { ms[i] = flops[i] = bytes[i] = 0; launches[i] = g_prof.launches[i]; timed[i] = 0; }
+  for (int i = 0; i < g_prof.n; ++i) {
+    ProfRec& r = g_prof.rec[i];
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return fail(AXVS_E_CUDA, "profile_read: %s", cudaGetErrorString(cudaGetLastError()));
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; timed[r.cls]++;
+  }
   return AXVS_OK;
 }
 

@@ -285,3 +285,20 @@ def ln_ffn_fwd(x: torch.Tensor, w: PackedLayer) -> torch.Tensor:
         rc = lib.axvs_ln_ffn_fwd(x.data_ptr(), out.data_ptr(), ctypes.byref(st), rows, ws.data_ptr(), ws.numel(), _stream(x.device))
     _lib.check(rc, "axvs_ln_ffn_fwd")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ measurement hooks
+def profile_enable(on: bool) -> None:
+    """Reset the library's launch counters; with on=True every launch is bracketed by CUDA events (bench.py)."""
+    _lib.check(_lib.load().axvs_profile_enable(int(on)), "axvs_profile_enable")
+
+
+def profile_read() -> Dict[str, Dict[str, float]]:
+    """Per kernel class: device ms, algorithmic flops/bytes, launches since enable, event-timed launches."""
+    lib = _lib.load()
+    n = lib.axvs_profile_num_classes()
+    ms, fl, by = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_double * n)()
+    la, ti = (ctypes.c_longlong * n)(), (ctypes.c_longlong * n)()
+    _lib.check(lib.axvs_profile_read(ms, fl, by, la, ti), "axvs_profile_read")
+    return {lib.axvs_profile_class_name(i).decode(): dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(la[i]), timed=int(ti[i]))
+            for i in range(n)}

@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- clips/s of the within-clip tracking module's temporal hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--clips C] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): Video-kMaX R50 + MaXTron within-clip tracking on VIPSeg-shaped synthetic clips,
+T=2 frames of 641x641 -> temporal levels res5 (21x21) and res4 (41x41), C=256, 2 stages x TemporalEncoder(2 axial-
+trajectory layers), random-init weights (xavier), synthetic N(0,1) features.  One step = that hot path over one
+batch of `--clips` clips per GPU (weak scaling: every rank processes its own clips, no collective in the data path;
+a small per-clip output summary is all-gathered once per step).  Algorithmic work: 60.5 GFLOP per clip.
+
+`--impl reference` times the reference's CPU implementation of the same path (the oracle port checked against the
+reference in tests/; the Python reference tree itself cannot travel to the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_FRAMES = 2
+LEVELS = [(21, 21), (41, 41)]       # res5, res4 of a 641x641 frame (low -> high resolution, WC/msdeformattn.py:413)
+STAGES = 2                           # NUM_STAGES
+LAYERS_PER_STAGE = 2                 # TEMPORAL_LAYERS // NUM_STAGES  (maxtron_wc_r50.yaml)
+METRIC = "video clips/sec"
+
+
+def flops_per_clip() -> float:
+    C, dffn, T = 256, 1024, T_FRAMES
+    tot = 0.0
+    for (H, W) in LEVELS:
+        tokens = T * H * W
+        tot += tokens * C * (20 * C + 8 * T * C + 4 * T * (H + W) + 8 * T + 4 * dffn)
+    return tot * STAGES * LAYERS_PER_STAGE
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], source="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def oracle_clip_runner():
+    """Returns fn() that runs the hot path of ONE clip on the CPU (fp32 oracle port) and the thread count used."""
+    from axial_vs_b200 import synth
+    from oracle import traj_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    stages = [O.split_encoder_params(synth.encoder_params(s, LAYERS_PER_STAGE)) for s in range(STAGES)]
+    le = synth.level_embed(99)
+    srcs = [synth.randn(10 + i, T_FRAMES, H * W, 256) for i, (H, W) in enumerate(LEVELS)]
+    poss = [O.level_pos3d(1, T_FRAMES, H, W, le[i]) for i, (H, W) in enumerate(LEVELS)]
+
+    @torch.no_grad()
+    def run():
+        cur = list(srcs)
+        for st in stages:
+            for i in range(len(LEVELS)):
+                cur[i], _, _ = O.temporal_encoder(cur[i], poss[i], st)
+        return cur
+
+    return run, torch.get_num_threads()
+
+
+def cpu_baseline_sample(budget_s: float = 12.0):
+    run, cores = oracle_clip_runner()
+    run()                                  # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        run()
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= 200:
+            break
+    return {"value": n / el, "unit": METRIC, "cores": cores, "kind": "port",
+            "sample": f"{n} clips (T=2, res5 21x21 + res4 41x41, 2 stages x 2 layers) in {el:.1f} s, fp32 torch-CPU oracle port"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    run, cores = oracle_clip_runner()
+    for _ in range(max(1, min(args.warmup, 2))):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    el = time.perf_counter() - t0
+    val = args.steps / el
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(1),
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
+                             "sample": "1 clip per step; the oracle port of the reference modules (oracle/traj_oracle.py), all host threads"},
+            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(clips):
+    return {"workload": "Video-kMaX R50 + MaXTron within-clip tracking hot path (BASELINE configs[1]): T=2, 641x641 -> "
+                        "res5 21x21 + res4 41x41, C=256, 2 stages x TemporalEncoder(2 axial-trajectory layers)",
+            "clips_per_gpu_per_step": clips, "gflop_per_clip": round(flops_per_clip() / 1e9, 2),
+            "l2": "per-step activations exceed the 126 MB L2 and two input sets alternate"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--clips", type=int, default=32, help="clips per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    from axial_vs_b200 import modules, ops, sharding, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: a CUDA device is required (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    clips = args.clips
+    encoders = []
+    for s in range(STAGES):
+        enc = modules.TemporalEncoder(256, 1024, 0.0, 0.0, "relu", 8, "axial-trajectory", LAYERS_PER_STAGE).eval()
+        enc.load_state_dict(synth.encoder_params(s, LAYERS_PER_STAGE), strict=True)
+        encoders.append(enc.to(dev))
+    le = synth.level_embed(99).to(dev)
+    pos = [ops.pos3d(clips, T_FRAMES, H, W, le[i].contiguous(), dev) for i, (H, W) in enumerate(LEVELS)]
+    # two alternating input sets (device-resident for `value`, pinned host copies for `e2e`)
+    host_in = [[torch.randn(clips * T_FRAMES, H * W, 256, generator=torch.Generator().manual_seed(1000 * k + 10 * rank + i)).pin_memory()
+                for i, (H, W) in enumerate(LEVELS)] for k in range(2)]
+    dev_in = [[t.to(dev) for t in hs] for hs in host_in]
+    host_out = [torch.empty_like(t).pin_memory() for t in host_in[0]]
+
+    @torch.no_grad()
+    def hot_path(srcs):
+        cur = list(srcs)
+        for enc in encoders:                       # the same TemporalEncoder object serves both levels (WC/msdeformattn.py:261-263)
+            for i in range(len(LEVELS)):
+                cur[i], _, _ = enc(cur[i], pos[i])
+        return cur
+
+    def gather_summary(outs):
+        if world > 1:                              # per-clip summary, all-gathered after the path (never inside it)
+            summ = outs[1].view(clips, -1, 256).mean(1)
+            sharding.gather_clip_outputs(summ, clips * world)
+
+    def step_resident(k):
+        outs = hot_path(dev_in[k & 1])
+        gather_summary(outs)
+        return outs
+
+    def step_e2e(k):
+        srcs = [h.to(dev, non_blocking=True) for h in host_in[k & 1]]
+        outs = hot_path(srcs)
+        gather_summary(outs)
+        for o, h in zip(outs, host_out):
+            h.copy_(o, non_blocking=True)
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            fn(k)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for k in range(args.warmup):
+        step_resident(k)
+        step_e2e(k)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.profile_enable(False)                       # reset launch counters
+    ms_total = timed(step_resident, args.steps)
+    prof0 = ops.profile_read()
+    launches = sum(v["launches"] for v in prof0.values())
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline leg: the same steps with CUDA events around every kernel launch (separate pass, not the `value` timing)
+    ops.profile_enable(True)
+    prof_steps = min(args.steps, 5)
+    barrier()
+    for k in range(prof_steps):
+        step_resident(k)
+    barrier()
+    prof = ops.profile_read()
+    ops.profile_enable(False)
+
+    if rank == 0:
+        peaks = load_peaks()
+        total_clips = clips * n_gpus * args.steps
+        value = total_clips / (ms_total / 1e3)
+        e2e_value = total_clips / (ms_e2e / 1e3)
+        in_bytes = sum(t.numel() * 4 for t in host_in[0])
+        out_bytes = sum(t.numel() * 4 for t in host_out)
+        tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+        dom_name, dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        kernels = {k: {"ms_per_step": round(v["ms"] / prof_steps, 4), "share": round(v["ms"] / tot_ms, 4),
+                       "launches_per_step": v["timed"] // prof_steps,
+                       "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 and v["flops"] > 0 else None,
+                       "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
+                   for k, v in prof.items() if v["timed"]}
+        achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["flops"] > 0 else dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
+        tensor_bound = dom["flops"] > 0 and dom_name in ("gemm_bf16_kernel", "spatial_attn_kernel")
+        peak = peaks["tf_sustained"] if tensor_bound else peaks["hbm"]
+        roofline = {"kernel": dom_name, "bound": "tensor" if tensor_bound else "hbm", "achieved": round(achieved, 2), "peak": peak,
+                    "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                    "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}; sustained bf16 figure: kernel timed inside a long step)",
+                    "avg_launch_ms": round(dom["ms"] / max(dom["timed"], 1), 5),
+                    "step_tflops": round(flops_per_clip() * clips / (ms_total / args.steps * 1e-3) / 1e12, 2),
+                    "step_frac_of_tensor_peak": round(flops_per_clip() * clips / (ms_total / args.steps * 1e-3) / 1e12 / peaks["tf_sustained"], 4),
+                    "kernels": kernels}
+        line = {"metric": METRIC, "value": round(value, 2), "unit": "clips/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic", "config": workload_config(clips),
+                "e2e": {"value": round(e2e_value, 2), "unit": "clips/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                        "ms_per_step": round(ms_e2e / args.steps, 4)},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -119,6 +119,17 @@ int axvs_axial_layer_fwd(const float* src, const float* pos, float* out, const a
  * (WC/pos_embeddings.py:86-130, WC/msdeformattn.py:112-115).  out fp32 [B,T,H,W,256]; level_embed may be NULL. */
 int axvs_pos3d(float* out, const float* level_embed, int B, int T, int H, int W, axvs_stream_t stream);
 
+/* ---- measurement hooks (bench.py) ---------------------------------------------------------------------------------
+ * axvs_profile_enable(1) resets the counters and brackets every kernel launch made through this library with CUDA
+ * events on the launching stream (up to 8192 launches); axvs_profile_enable(0) only counts launches.
+ * axvs_profile_read synchronises the recorded events and returns, per kernel class (arrays of
+ * axvs_profile_num_classes() entries): summed device ms, algorithmic FLOPs, algorithmic bytes, launch count since the
+ * last enable, and how many of those launches were event-timed.  Host-synchronising; never call inside graph capture. */
+int axvs_profile_enable(int on);
+int axvs_profile_num_classes(void);
+const char* axvs_profile_class_name(int cls);
+int axvs_profile_read(double* ms, double* flops, double* bytes, long long* launches, long long* timed);
+
 #ifdef __cplusplus
 }
 #endif
