@@ -18,7 +18,7 @@ AXIS_NONE, AXIS_H, AXIS_W = 0, 1, 2
 
 class TaWeights(Structure):
     _fields_ = [("w_qkv", c_void_p), ("b_qkv", c_void_p), ("w_pq", c_void_p), ("b_pq", c_void_p),
-                ("w_pkv", c_void_p), ("b_pkv", c_void_p), ("w_proj", c_void_p), ("b_proj", c_void_p)]
+                ("w_pkv", c_void_p), ("b_pkv", c_void_p), ("w_pkv_c", c_void_p), ("w_proj", c_void_p), ("b_proj", c_void_p)]
 
 
 class LayerWeights(Structure):
@@ -31,6 +31,7 @@ class LayerWeights(Structure):
 SIGNATURES = {
     "axvs_version": (c_int, []),
     "axvs_last_error": (c_char_p, []),
+    "axvs_set_fusion": (c_int, [c_int]),
     "axvs_packed_weight_bytes": (c_size_t, [c_int, c_int]),
     "axvs_pack_weight": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "axvs_linear": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p,

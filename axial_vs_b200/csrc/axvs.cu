@@ -9,6 +9,8 @@
 #include "attn.cuh"
 #include "gemm.cuh"
 #include "simt.cuh"
+#include "traj_fused.cuh"
+#include "ffn_fused.cuh"
 
 using namespace axvs;
 
@@ -25,9 +27,11 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
-                                            "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel"};
+                                            "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
+                                            "x_to_image_kernel", "ffn_fused_kernel"};
+int g_fusion = 2;
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
 struct Profiler {
@@ -62,6 +66,8 @@ struct ProfScope {
 struct DeviceInfo {
   int sms = 0;
   bool gemm_attr = false;
+  bool traj_attr = false;
+  bool ffn_attr = false;
 };
 DeviceInfo g_dev[64];
 
@@ -79,6 +85,16 @@ int device_info(DeviceInfo** out) {
     if (cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(gemm) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.gemm_attr = true;
+  }
+  if (!d.traj_attr) {
+    if (cudaFuncSetAttribute(traj_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(traj_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    d.traj_attr = true;
+  }
+  if (!d.ffn_attr) {
+    if (cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(ffn_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    d.ffn_attr = true;
   }
   *out = &d;
   return AXVS_OK;
@@ -132,6 +148,7 @@ GemmParams gemm_params(const void* A, int lda, int M, int K, const void* Wp, int
 
 struct TaWorkspace {
   __nv_bfloat16 *a1, *a2, *a3, *qkv, *x, *q2, *kv2, *o;
+  uint8_t *x_img, *xd_img;
   size_t bytes;
 };
 
@@ -148,6 +165,9 @@ TaWorkspace carve_ta(void* base, size_t rows, int F) {
   w.q2 = take(rows * 256 * 2);
   w.kv2 = take(rows * (size_t)F * 512 * 2);
   w.o = take(rows * 256 * 2);
+  const size_t tiles = (rows + 127) / 128;
+  w.x_img = reinterpret_cast<uint8_t*>(take(tiles * (size_t)F * 4 * TF_KB));
+  w.xd_img = reinterpret_cast<uint8_t*>(take(tiles * 4 * TF_KB));
   w.bytes = off;
   return w;
 }
@@ -188,7 +208,12 @@ int blocks_for(long long work_items, int per_block, int sms) {
 
 extern "C" {
 
-int axvs_version(void) { return 100; }
+int axvs_version(void) { return 102; }
+int axvs_set_fusion(int level) {
+  const int prev = g_fusion;
+  g_fusion = level < 0 ? 0 : (level > 2 ? 2 : level);
+  return prev;
+}
 const char* axvs_last_error(void) { return g_err; }
 
 size_t axvs_packed_weight_bytes(int n_out, int k) {
@@ -306,6 +331,33 @@ int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, 
     rc = axvs_spatial_attention(ws.qkv + (size_t)s0 * N * 768, ws.x + (size_t)s0 * N * F * 256, ns, F, n, stream);
     if (rc) return rc;
   }
+  if (g_fusion >= 1) {
+    if (!w->w_pkv_c) return fail(AXVS_E_INVALID, "traj_attn: w_pkv_c (head-pair ordered proj_kv) is required by the fused kernel");
+    const int tiles = (int)((rows + 127) / 128);
+    {
+      ProfScope ps(KC_X2IMG, 0, (double)rows * F * 512.0 * 2 + (double)rows * 512.0, st);
+      x_to_image_kernel<<<blocks_for((long long)rows * F * 32, 256, d->sms), 256, 0, st>>>(ws.x, ws.x_img, ws.xd_img, (int)rows, tiles, F, N, n);
+    }
+    AXVS_CHECK_LAUNCH("x_to_image_kernel");
+    TrajParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.x_img = ws.x_img; tp.xd_img = ws.xd_img;
+    tp.w_pq = reinterpret_cast<const uint8_t*>(w->w_pq);
+    tp.w_pkv = reinterpret_cast<const uint8_t*>(w->w_pkv_c);
+    tp.w_proj = reinterpret_cast<const uint8_t*>(w->w_proj);
+    tp.b_pq = w->b_pq; tp.b_v2 = w->b_pkv + 256; tp.b_proj = w->b_proj;
+    tp.resid = resid; tp.out = out;
+    tp.rows = (int)rows; tp.tiles = tiles; tp.F = F;
+    tp.map_mode = map; tp.dims = dims;
+    tp.scale_log2e = 0.17677669529663687f * 1.4426950408889634f;
+    {
+      ProfScope ps(KC_TRAJ, 2.0 * rows * 256.0 * 256.0 * (2.0 + 2.0 * F) + 4.0 * rows * F * 256.0,
+                   (double)rows * (512.0 * (F + 1) + 1024.0 + (resid ? 1024.0 : 0.0)), st);
+      traj_fused_kernel<<<tiles < d->sms ? tiles : d->sms, TF_THREADS, TF_SMEM_BYTES, st>>>(tp);
+    }
+    AXVS_CHECK_LAUNCH("traj_fused_kernel");
+    return AXVS_OK;
+  }
   // 4. q2 = proj_q(x_diag) * scale
   {
     GemmParams p = gemm_params(ws.x, 256, (int)rows, 256, w->w_pq, 256, 0, w->b_pq, 256, 0.17677669529663687f, 0, ws.q2, 256, 0, 1, nullptr);
@@ -358,9 +410,27 @@ int axvs_ln_ffn_fwd(const float* x, float* out, const axvs_layer_weights* w, int
   if (!x || !out || !w || !workspace) return fail(AXVS_E_INVALID, "ln_ffn: null pointer");
   if (rows <= 0) return fail(AXVS_E_INVALID, "ln_ffn: rows must be positive");
   if (w->d_ffn <= 0 || w->d_ffn % 256) return fail(AXVS_E_UNSUPPORTED, "ln_ffn: d_ffn must be a multiple of 256 (got %d)", w->d_ffn);
+  if (!w->ln1_g || !w->ln1_b || !w->ln2_g || !w->ln2_b || !w->w_ffn1 || !w->w_ffn2 || !w->b_ffn1 || !w->b_ffn2) return fail(AXVS_E_INVALID, "ln_ffn: null weight pointer");
   FfnWorkspace ws = carve_ffn(workspace, (size_t)rows, w->d_ffn);
   if (ws.bytes > workspace_bytes) return fail(AXVS_E_WORKSPACE, "ln_ffn: workspace %zu < required %zu", workspace_bytes, ws.bytes);
   int rc;
+  if (g_fusion >= 2 && w->d_ffn >= 512) {
+    DeviceInfo* d;
+    if ((rc = device_info(&d))) return rc;
+    FfnParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.x = x; fp.out = out;
+    fp.ln1_g = w->ln1_g; fp.ln1_b = w->ln1_b; fp.ln2_g = w->ln2_g; fp.ln2_b = w->ln2_b;
+    fp.w1 = reinterpret_cast<const uint8_t*>(w->w_ffn1); fp.w2 = reinterpret_cast<const uint8_t*>(w->w_ffn2);
+    fp.b1 = w->b_ffn1; fp.b2 = w->b_ffn2;
+    fp.rows = rows; fp.tiles = (rows + 127) / 128; fp.d_ffn = w->d_ffn; fp.eps = 1e-5f;
+    {
+      ProfScope ps(KC_FFN, 4.0 * rows * 256.0 * w->d_ffn, (double)rows * 256 * 12.0, (cudaStream_t)stream);
+      ffn_fused_kernel<<<fp.tiles < d->sms ? fp.tiles : d->sms, FF_THREADS, FF_SMEM_BYTES, (cudaStream_t)stream>>>(fp);
+    }
+    AXVS_CHECK_LAUNCH("ffn_fused_kernel");
+    return AXVS_OK;
+  }
   if ((rc = axvs_layernorm(x, w->ln1_g, w->ln1_b, ws.s3, ws.s3b, rows, 1e-5f, stream))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   GemmParams p = gemm_params(ws.s3b, 256, rows, 256, w->w_ffn1, w->d_ffn, 0, w->b_ffn1, w->d_ffn, 1.f, 1, ws.hid, w->d_ffn, 0, 1, nullptr);

@@ -37,15 +37,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (context error, visible to the host) instead of hanging the GPU.
+// (No printf on the failure path: a call site inside the epilogue loops would force the accumulator registers
+// to be spilled around it.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifndef AXVS_NO_DEADLOCK_TRAP
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("axvs: mbarrier deadlock block %d thread %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
-    }
+    if (++spins > (1u << 24)) __trap();
   }
 #else
   while (!mbar_try_wait(bar, parity)) {
@@ -128,6 +126,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ misc
@@ -152,4 +160,35 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   return r;
 }
 
+}  // namespace axvs
+
+namespace axvs {
+// registers -> TMEM, 32 lanes x 32 columns (inverse of tmem_ld32)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// warp-group register re-allocation (all 4 warps of an aligned warpgroup must execute the same instruction)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// Issue the 4 UMMAs (K = 64 = 4 x 16) of one K-block: D[128 x N] (+)= A_kblock[128 x 64] * W_kblock[N x 64]^T.
+// a_addr / w_addr: shared-memory byte addresses of SWIZZLE_128B K-major tiles (1024 B aligned).
+__device__ __forceinline__ void umma_kblock(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint32_t idesc, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc, (accumulate || k) ? 1u : 0u);
+}
 }  // namespace axvs

@@ -1,0 +1,355 @@
+// Fused "temporal half" of TrajectoryAttention (Appendix A steps 6-8 + residual), one persistent tcgen05 kernel:
+//
+//   q2  = (x_diag Wpq^T + bpq) * scale                     (GEMM 1, accumulator resident in TMEM columns [0,256))
+//   for every frame f:  [k2 | v2]_f = x_f Wpkv^T + bpkv     (GEMM 2, 128-column chunks = 2 heads, double-buffered TMEM)
+//        a_f = softmax_f(q2 . k2_f)   online over f,  o += a_f v2_f      (epilogue warps, fp32 registers)
+//   out[canonical row] = resid + o Wproj^T + bproj          (GEMM 3, A operand = o written to smem by the epilogue)
+//
+// so k2|v2 (the largest intermediate of the reference, [B', N, F, 2C]), q2 and o never touch HBM.
+// Reference: WC/temporal_attention.py:61-75 (+ residual add :204 / :213).  The k2 bias is dropped: it adds the same
+// constant q2.bk2 to every frame's logit and softmax over frames is shift-invariant.
+//
+// Inputs are "tile images": x_f and x_diag stored as [tile][K-block][128 rows x 128 B, SWIZZLE_128B] so that one
+// 16 KiB TMA bulk copy lands a ready-to-use UMMA A-operand K-block (written in that layout by the attention kernel).
+//
+// Warp roles (384 threads): warps 0-3 = epilogue group 0 (heads 0-3, TMEM stage 0), warps 4-7 = epilogue group 1
+// (heads 4-7, stage 1), warp 8 = A-tile TMA producer, warp 9 = weight TMA producer, warp 10 = MMA issuer.
+#pragma once
+#include "gemm.cuh"
+
+namespace axvs {
+
+constexpr int TF_THREADS = 384;
+constexpr int TF_A_SLOTS = 6;
+constexpr int TF_W_SLOTS = 4;
+constexpr int TF_KB = 16384;                       // one K-block tile: 128 rows x 64 bf16
+constexpr int TF_O_BYTES = 4 * TF_KB;              // o operand, 128 x 256 bf16
+constexpr int TF_SMEM_BYTES = TF_O_BYTES + TF_A_SLOTS * TF_KB + TF_W_SLOTS * TF_KB + 1024 + 512;
+
+struct TrajParams {
+  const uint8_t* x_img;    // [F][tiles][4][16 KiB]
+  const uint8_t* xd_img;   // [tiles][4][16 KiB]
+  const uint8_t* w_pq;     // packed [4][256 rows][128 B]
+  const uint8_t* w_pkv;    // packed, rows re-ordered per head pair: chunk c = [k2 heads 2c,2c+1 | v2 heads 2c,2c+1]
+  const uint8_t* w_proj;   // packed [4][256][128 B]
+  const float* b_pq;
+  const float* b_v2;       // proj_kv.bias[256:512]
+  const float* b_proj;
+  const float* resid;      // fp32 canonical, may be null
+  float* out;              // fp32 canonical
+  int rows, tiles, F;
+  int map_mode;
+  AxialDims dims;
+  float scale_log2e;       // head_dim^-0.5 * log2(e): logits are produced directly in the exp2 domain
+};
+
+__global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* o_buf = smem;
+  uint8_t* a_ring = smem + TF_O_BYTES;
+  uint8_t* w_ring = a_ring + TF_A_SLOTS * TF_KB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + TF_W_SLOTS * TF_KB);
+  uint64_t* a_full = bars;                       // [6]
+  uint64_t* a_empty = a_full + TF_A_SLOTS;       // [6]
+  uint64_t* w_full = a_empty + TF_A_SLOTS;       // [4]
+  uint64_t* w_empty = w_full + TF_W_SLOTS;       // [4]
+  uint64_t* s_full = w_empty + TF_W_SLOTS;       // [2]
+  uint64_t* s_empty = s_full + 2;                // [2]
+  uint64_t* q2_full = s_empty + 2;
+  uint64_t* q2_free = q2_full + 1;
+  uint64_t* o_ready = q2_free + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TF_A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < TF_W_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
+    mbar_init(q2_full, 1);
+    mbar_init(q2_free, 8);
+    mbar_init(o_ready, 8);
+    fence_barrier_init();
+  }
+  if (warp == 10) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int F = p.F;
+
+  if (warp < 8) {
+    // =============================================================== epilogue groups
+    setmaxnreg_inc<224>();   // 256*224 + 128*56 = 64512 = the CTA register pool at launch (384 x 168)
+    const int g = warp >> 2;                                     // group = TMEM stage = head quad
+    const int row_in_tile = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t t_q2 = tmem + lane_base + 128 * g;            // my 4 heads of q2
+    const uint32_t t_s = tmem + lane_base + 256 + 128 * g;       // my accumulator stage
+    uint32_t s_cnt = 0;                                          // items consumed on my stage
+    uint32_t it = 0;                                             // tile iteration
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      // ---- finalise q2: (acc + bias) * scale*log2e, written back to TMEM
+      mbar_wait(q2_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        float v[32];
+        tmem_ld32(t_q2 + 32 * j, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (v[i] + __ldg(p.b_pq + 128 * g + 32 * j + i)) * p.scale_log2e;
+        tmem_st32(t_q2 + 32 * j, v);
+      }
+      tmem_st_wait();
+
+      float m_run[4], l_run[4], o[4][32];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        m_run[h] = -INFINITY;
+        l_run[h] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[h][i] = 0.f;
+      }
+      // ---- frames: two 128-column chunks (2 heads each) per frame on my stage
+      for (int f = 0; f < F; ++f) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          mbar_wait(&s_full[g], s_cnt & 1);
+          ++s_cnt;
+          tc_fence_after();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int lh = cc * 2 + hh;
+            float s = 0.f;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              float k2[16], q2[16];
+              tmem_ld16(t_s + 32 * hh + 16 * hf, k2);
+              tmem_ld16(t_q2 + 32 * lh + 16 * hf, q2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) s = fmaf(q2[i], k2[i], s);
+            }
+            const float mn = fmaxf(m_run[lh], s);
+            const float corr = exp2f(m_run[lh] - mn);
+            const float pe = exp2f(s - mn);
+            l_run[lh] = l_run[lh] * corr + pe;
+            m_run[lh] = mn;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              float v2[16];
+              tmem_ld16(t_s + 64 + 32 * hh + 16 * hf, v2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[lh][16 * hf + i] = fmaf(pe, v2[i], o[lh][16 * hf + i] * corr);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[g]);
+        }
+      }
+      // ---- o = o / l + bv2  -> bf16 A operand of the output projection (K-blocks 2g, 2g+1 of o_buf)
+#pragma unroll
+      for (int lh = 0; lh < 4; ++lh) {
+        const float inv = 1.f / l_run[lh];
+        const int col0 = 128 * g + 32 * lh;
+        uint8_t* kb_base = o_buf + (col0 >> 6) * TF_KB;
+        const int chunk0 = (col0 & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = fmaf(o[lh][8 * q + i], inv, __ldg(p.b_v2 + col0 + 8 * q + i));
+          uint4 u;
+          u.x = pack_bf16x2(t[0], t[1]); u.y = pack_bf16x2(t[2], t[3]);
+          u.z = pack_bf16x2(t[4], t[5]); u.w = pack_bf16x2(t[6], t[7]);
+          *reinterpret_cast<uint4*>(kb_base + sw128_offset(row_in_tile, chunk0 + q)) = u;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(o_ready);
+        mbar_arrive(q2_free);
+      }
+      // ---- output projection item on my stage: out = resid + acc + bproj (my 128 output columns)
+      mbar_wait(&s_full[g], s_cnt & 1);
+      ++s_cnt;
+      tc_fence_after();
+      const int r = tile * 128 + row_in_tile;
+      const bool valid = r < p.rows;
+      const size_t orow = valid ? (size_t)pass_to_canonical(r, p.map_mode, p.dims) : 0;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        float v[32];
+        tmem_ld32(t_s + 32 * j, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int col = 128 * g + 32 * j;
+          float4* o4 = reinterpret_cast<float4*>(p.out + orow * 256 + col);
+          const float4* b4 = reinterpret_cast<const float4*>(p.b_proj + col);
+          if (p.resid) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.resid + orow * 256 + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 rr = __ldg(r4 + i), bb = __ldg(b4 + i);
+              o4[i] = make_float4(v[4 * i] + bb.x + rr.x, v[4 * i + 1] + bb.y + rr.y, v[4 * i + 2] + bb.z + rr.z, v[4 * i + 3] + bb.w + rr.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 bb = __ldg(b4 + i);
+              o4[i] = make_float4(v[4 * i] + bb.x, v[4 * i + 1] + bb.y, v[4 * i + 2] + bb.z, v[4 * i + 3] + bb.w);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[g]);
+    }
+  } else {
+    setmaxnreg_dec<56>();
+    if (warp == 8 && lane == 0) {
+      // =============================================================== A-tile producer (x_diag, x_0 .. x_{F-1})
+      uint32_t cnt = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int item = 0; item < 4 * (F + 1); ++item, ++cnt) {
+          const uint32_t slot = cnt % TF_A_SLOTS, phase = (cnt / TF_A_SLOTS) & 1;
+          const uint8_t* src = (item < 4) ? p.xd_img + ((size_t)tile * 4 + item) * TF_KB
+                                          : p.x_img + (((size_t)((item >> 2) - 1) * p.tiles + tile) * 4 + (item & 3)) * TF_KB;
+          mbar_wait(&a_empty[slot], phase ^ 1);
+          mbar_arrive_expect_tx(&a_full[slot], TF_KB);
+          tma_bulk_g2s(a_ring + slot * TF_KB, src, TF_KB, &a_full[slot]);
+        }
+      }
+    } else if (warp == 9 && lane == 0) {
+      // =============================================================== weight producer (128-row x 64-K stages)
+      uint32_t cnt = 0;
+      auto push = [&](const uint8_t* img, int rows_total, int kb, int row0) {
+        const uint32_t slot = cnt % TF_W_SLOTS, phase = (cnt / TF_W_SLOTS) & 1;
+        mbar_wait(&w_empty[slot], phase ^ 1);
+        mbar_arrive_expect_tx(&w_full[slot], TF_KB);
+        tma_bulk_g2s(w_ring + slot * TF_KB, img + ((size_t)kb * rows_total + row0) * 128, TF_KB, &w_full[slot]);
+        ++cnt;
+      };
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) push(p.w_pq, 256, i >> 1, (i & 1) * 128);
+#pragma unroll 1
+        for (int i = 0; i < 16 * F; ++i) {
+          const int ci = (i >> 2) & 3;
+          const int c = ((ci & 1) << 1) | (ci >> 1);             // chunk order 0,2,1,3: stages alternate
+          push(p.w_pkv, 512, i & 3, c * 128);
+        }
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) push(p.w_proj, 256, i >> 1, (i & 1) * 128);
+      }
+    } else if (warp == 10 && lane == 0) {
+      // =============================================================== MMA issuer
+      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring), o_addr = smem_u32(o_buf);
+      uint32_t a_cnt = 0, w_cnt = 0, s_cnt0 = 0, s_cnt1 = 0, it = 0;
+      auto w_wait = [&]() -> uint32_t {
+        const uint32_t slot = w_cnt % TF_W_SLOTS, phase = (w_cnt / TF_W_SLOTS) & 1;
+        mbar_wait(&w_full[slot], phase);
+        tc_fence_after();
+        return slot;
+      };
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+        // ---- GEMM 1: q2 accumulators (columns [0,256))
+        mbar_wait(q2_free, (it & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb, ++a_cnt) {
+          const uint32_t aslot = a_cnt % TF_A_SLOTS, aphase = (a_cnt / TF_A_SLOTS) & 1;
+          mbar_wait(&a_full[aslot], aphase);
+          tc_fence_after();
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half, ++w_cnt) {
+            const uint32_t ws = w_wait();
+            umma_kblock(tmem + half * 128, a_ring_addr + aslot * TF_KB, w_ring_addr + ws * TF_KB, idesc, kb != 0);
+            umma_commit(&w_empty[ws]);
+          }
+          umma_commit(&a_empty[aslot]);
+        }
+        umma_commit(q2_full);
+        // ---- GEMM 2: per frame, four 128-column chunks alternating between the two TMEM stages
+#pragma unroll 1
+        for (int f = 0; f < F; ++f) {
+#pragma unroll 1
+          for (int ci = 0; ci < 4; ++ci) {
+            const int g = ci & 1;                               // chunk order 0,2,1,3 -> stage 0,1,0,1
+            const uint32_t sc = g ? s_cnt1 : s_cnt0;
+            mbar_wait(&s_empty[g], (sc & 1) ^ 1);
+            if (g) ++s_cnt1; else ++s_cnt0;
+            tc_fence_after();
+#pragma unroll 1
+            for (int kb = 0; kb < 4; ++kb, ++w_cnt) {
+              const uint32_t ac = a_cnt + kb;
+              const uint32_t aslot = ac % TF_A_SLOTS, aphase = (ac / TF_A_SLOTS) & 1;
+              if (ci == 0) {
+                mbar_wait(&a_full[aslot], aphase);
+                tc_fence_after();
+              }
+              const uint32_t ws = w_wait();
+              umma_kblock(tmem + 256 + g * 128, a_ring_addr + aslot * TF_KB, w_ring_addr + ws * TF_KB, idesc, kb != 0);
+              umma_commit(&w_empty[ws]);
+              if (ci == 3) umma_commit(&a_empty[aslot]);
+            }
+            umma_commit(&s_full[g]);
+          }
+          a_cnt += 4;
+        }
+        // ---- GEMM 3: output projection, A = o (written by the epilogue), accumulators = both stages
+        mbar_wait(o_ready, it & 1);
+        mbar_wait(&s_empty[0], (s_cnt0 & 1) ^ 1);
+        ++s_cnt0;
+        mbar_wait(&s_empty[1], (s_cnt1 & 1) ^ 1);
+        ++s_cnt1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i, ++w_cnt) {
+          const int kb = i >> 1, half = i & 1;
+          const uint32_t ws = w_wait();
+          umma_kblock(tmem + 256 + half * 128, o_addr + kb * TF_KB, w_ring_addr + ws * TF_KB, idesc, kb != 0);
+          umma_commit(&w_empty[ws]);
+        }
+        umma_commit(&s_full[0]);
+        umma_commit(&s_full[1]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// x [rows, F, 256] bf16 (row-major, v1 attention output) -> tile images for traj_fused_kernel (test / bridge path)
+__global__ void x_to_image_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ x_img, uint8_t* __restrict__ xd_img,
+                                  int rows, int tiles, int F, int N, int n) {
+  const size_t total = (size_t)rows * F * 32;   // 16-byte chunks
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx & 31);
+    const size_t rf = idx >> 5;
+    const int f = (int)(rf % F);
+    const int r = (int)(rf / F);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + (rf * 256) + ch * 8);
+    const int tile = r >> 7, rr = r & 127, kb = ch >> 3, c8 = ch & 7;
+    const size_t off = (size_t)kb * TF_KB + sw128_offset(rr, c8);
+    *reinterpret_cast<uint4*>(x_img + ((size_t)f * tiles + tile) * 4 * TF_KB + off) = v;
+    if (f == (r % N) / n) *reinterpret_cast<uint4*>(xd_img + (size_t)tile * 4 * TF_KB + off) = v;
+  }
+}
+
+}  // namespace axvs

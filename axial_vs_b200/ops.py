@@ -77,11 +77,12 @@ class PackedTA:
     b_pq: torch.Tensor
     w_pkv: torch.Tensor
     b_pkv: torch.Tensor
+    w_pkv_c: torch.Tensor
     w_proj: torch.Tensor
     b_proj: torch.Tensor
 
     def tensors(self) -> List[torch.Tensor]:
-        return [self.w_qkv, self.b_qkv, self.w_pq, self.b_pq, self.w_pkv, self.b_pkv, self.w_proj, self.b_proj]
+        return [self.w_qkv, self.b_qkv, self.w_pq, self.b_pq, self.w_pkv, self.b_pkv, self.w_pkv_c, self.w_proj, self.b_proj]
 
     def struct(self) -> TaWeights:
         return TaWeights(*[t.data_ptr() for t in self.tensors()])
@@ -101,8 +102,12 @@ def pack_ta(p: Dict[str, torch.Tensor], prefix: str = "") -> PackedTA:
     else:
         wqkv = torch.cat([g("q.weight"), g("k.weight"), g("v.weight")], 0).contiguous()
         bqkv = torch.cat([g("q.bias"), g("k.bias"), g("v.bias")], 0).contiguous()
+    wkv = g("proj_kv.weight")
+    # rows re-ordered per head pair c: [k2 rows 64c..64c+63 ; v2 rows 256+64c..256+64c+63]  (fused trajectory kernel)
+    order = torch.cat([torch.cat([torch.arange(64 * c, 64 * c + 64), torch.arange(256 + 64 * c, 256 + 64 * c + 64)]) for c in range(4)])
+    wkv_c = wkv[order.to(wkv.device)].contiguous()
     return PackedTA(pack_weight(wqkv), bqkv, pack_weight(g("proj_q.weight")), g("proj_q.bias"),
-                    pack_weight(g("proj_kv.weight")), g("proj_kv.bias"), pack_weight(g("proj.weight")), g("proj.bias"))
+                    pack_weight(wkv), g("proj_kv.bias"), pack_weight(wkv_c), pack_weight(g("proj.weight")), g("proj.bias"))
 
 
 @dataclass
@@ -133,7 +138,7 @@ class PackedLayer:
 
     @staticmethod
     def from_tensors(ts: Sequence[torch.Tensor], d_ffn: int) -> "PackedLayer":
-        return PackedLayer(PackedTA.from_tensors(ts[0:8]), PackedTA.from_tensors(ts[8:16]), *ts[16:24], d_ffn=d_ffn)
+        return PackedLayer(PackedTA.from_tensors(ts[0:9]), PackedTA.from_tensors(ts[9:18]), *ts[18:26], d_ffn=d_ffn)
 
 
 def pack_layer(p: Dict[str, torch.Tensor], axial: bool = True) -> PackedLayer:
@@ -285,6 +290,11 @@ def ln_ffn_fwd(x: torch.Tensor, w: PackedLayer) -> torch.Tensor:
         rc = lib.axvs_ln_ffn_fwd(x.data_ptr(), out.data_ptr(), ctypes.byref(st), rows, ws.data_ptr(), ws.numel(), _stream(x.device))
     _lib.check(rc, "axvs_ln_ffn_fwd")
     return out
+
+
+def set_fusion(level: int) -> int:
+    """Select the fusion level of the composite calls (0 = unfused validation baseline ... highest = default)."""
+    return _lib.load().axvs_set_fusion(int(level))
 
 
 # ------------------------------------------------------------------------------------------------ measurement hooks

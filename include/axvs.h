@@ -44,6 +44,13 @@ typedef void* axvs_stream_t;
 int axvs_version(void);
 const char* axvs_last_error(void);
 
+/* Fusion level of the composite entry points (process-wide; default = highest).
+ *   0: one kernel per reference op group (tcgen05 GEMMs + attention + SIMT helpers; validation baseline)
+ *   1: + proj_q / proj_kv / temporal softmax / proj / residual fused in one tcgen05 kernel
+ *   2: + LayerNorm1 / FFN / residual / LayerNorm2 fused in one tcgen05 kernel
+ * Returns the previous level; values outside the range are clamped. */
+int axvs_set_fusion(int level);
+
 /* ---- weights ------------------------------------------------------------------------------------------------
  * nn.Linear weights [n_out, k] fp32 are converted once to bf16 and laid out as the shared-memory image the
  * tensor-core kernels consume (K-blocks of 64, 8-row x 128-byte swizzle atoms), so that one TMA bulk copy
@@ -57,6 +64,8 @@ typedef struct axvs_ta_weights {
   const void* w_qkv;  const float* b_qkv;    /* packed [768,256], bias [768] */
   const void* w_pq;   const float* b_pq;     /* proj_q   [256,256]           */
   const void* w_pkv;  const float* b_pkv;    /* proj_kv  [512,256]           */
+  const void* w_pkv_c;                       /* proj_kv packed with rows re-ordered per head pair c = 0..3:
+                                                [k2 rows 64c..64c+63 ; v2 rows 256+64c..256+64c+63] (fused kernel) */
   const void* w_proj; const float* b_proj;   /* proj     [256,256]           */
 } axvs_ta_weights;
 

@@ -245,3 +245,24 @@ def test_training_mode_is_rejected():
     layer = modules.TemporalAxialTrajectoryAttentionLayer().cuda().train()
     with pytest.raises(RuntimeError, match="inference"):
         layer(torch.zeros(2, 4, 256, device="cuda"), torch.zeros(1, 2, 2, 2, 256, device="cuda"))
+
+
+# --------------------------------------------------------------------------------------------- fusion levels
+@pytest.mark.parametrize("Bp,F,n", [(5, 2, 41), (3, 5, 30), (1, 10, 33), (7, 2, 21), (1, 1, 50)])
+def test_fusion_levels_agree(ops, O, Bp, F, n):
+    """Every fusion level of the composite call must match the oracle, and the levels must agree with each other."""
+    p, q, v, pk = _ta_case(ops, O, Bp, F, n, 2000 + Bp + F + n)
+    ref, _ = O.trajectory_attention(q, q, v, p, F)
+    qc, vc = q.reshape(-1, 256).cuda(), v.reshape(-1, 256).cuda()
+    res = torch.randn(Bp * F * n, 256, generator=torch.Generator().manual_seed(1)).cuda()
+    outs = []
+    try:
+        for level in (0, 1, 2):
+            ops.set_fusion(level)
+            out = ops.traj_attn_fwd(qc, qc, vc, None, res, pk, Bp, F, n, 1, ops.AXIS_NONE)
+            torch.cuda.synchronize()
+            assert nerr(out.cpu() - res.cpu(), ref.reshape(-1, 256)) < TOL, f"fusion level {level}"
+            outs.append(out)
+    finally:
+        ops.set_fusion(99)
+    assert nerr(outs[1], outs[0]) < 5e-3
