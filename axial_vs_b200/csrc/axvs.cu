@@ -27,10 +27,10 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
-                                            "x_to_image_kernel", "ffn_fused_kernel"};
+                                            "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel"};
 int g_fusion = 2;
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
@@ -177,6 +177,7 @@ struct FfnWorkspace {
   __nv_bfloat16* s3b;
   __nv_bfloat16* hid;
   float* t;
+  uint8_t* s_img;
   size_t bytes;
 };
 
@@ -188,6 +189,7 @@ FfnWorkspace carve_ffn(void* base, size_t rows, int d_ffn) {
   w.s3b = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(rows * 256 * 2);
   w.hid = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(rows * (size_t)d_ffn * 2);
   w.t = reinterpret_cast<float*>(p + off); off += align256(rows * 256 * 4);
+  w.s_img = p + off; off += align256(((rows + 127) / 128) * 4 * (size_t)TF_KB);
   w.bytes = off;
   return w;
 }
@@ -417,15 +419,20 @@ int axvs_ln_ffn_fwd(const float* x, float* out, const axvs_layer_weights* w, int
   if (g_fusion >= 2 && w->d_ffn >= 512) {
     DeviceInfo* d;
     if ((rc = device_info(&d))) return rc;
+    {
+      ProfScope ps(KC_LNIMG, 0, (double)rows * 256 * 10.0, (cudaStream_t)stream);
+      ln_image_kernel<<<blocks_for(rows, 8, d->sms), 256, 0, (cudaStream_t)stream>>>(x, w->ln1_g, w->ln1_b, ws.s3, ws.s_img, rows, 1e-5f);
+    }
+    AXVS_CHECK_LAUNCH("ln_image_kernel");
     FfnParams fp;
     memset(&fp, 0, sizeof(fp));
-    fp.x = x; fp.out = out;
-    fp.ln1_g = w->ln1_g; fp.ln1_b = w->ln1_b; fp.ln2_g = w->ln2_g; fp.ln2_b = w->ln2_b;
+    fp.s_img = ws.s_img; fp.s32 = ws.s3; fp.out = out;
+    fp.ln2_g = w->ln2_g; fp.ln2_b = w->ln2_b;
     fp.w1 = reinterpret_cast<const uint8_t*>(w->w_ffn1); fp.w2 = reinterpret_cast<const uint8_t*>(w->w_ffn2);
     fp.b1 = w->b_ffn1; fp.b2 = w->b_ffn2;
     fp.rows = rows; fp.tiles = (rows + 127) / 128; fp.d_ffn = w->d_ffn; fp.eps = 1e-5f;
     {
-      ProfScope ps(KC_FFN, 4.0 * rows * 256.0 * w->d_ffn, (double)rows * 256 * 12.0, (cudaStream_t)stream);
+      ProfScope ps(KC_FFN, 4.0 * rows * 256.0 * w->d_ffn, (double)rows * 256 * 10.0, (cudaStream_t)stream);
       ffn_fused_kernel<<<fp.tiles < d->sms ? fp.tiles : d->sms, FF_THREADS, FF_SMEM_BYTES, (cudaStream_t)stream>>>(fp);
     }
     AXVS_CHECK_LAUNCH("ffn_fused_kernel");

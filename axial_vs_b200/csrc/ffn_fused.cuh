@@ -1,31 +1,31 @@
-// Fused tail of the layer (WC/temporal_attention.py:181-185, 217-218), one persistent tcgen05 kernel per 128-token tile:
+// Fused FFN tail of the layer (WC/temporal_attention.py:181-185, 218), one persistent tcgen05 kernel per 128-token tile:
 //
-//   s   = LayerNorm1(x)                                  (producer warps: fp32 row -> bf16 SWIZZLE_128B A operand + row stats)
+//   s   = LayerNorm1(x)            -- produced by ln_image_kernel as fp32 rows + a bf16 tile image (UMMA A operand)
 //   h_j = relu(s W1[j]^T + b1[j])   j = 0..d_ffn/128-1   (GEMM 1, 128-column chunks into two alternating TMEM stages;
 //                                                          epilogue: bias, ReLU, bf16 -> shared-memory A operand of GEMM 2)
 //   acc2 += h_j W2[:, j]^T                               (GEMM 2, K-chunk j, accumulator resident in TMEM columns [0,256))
-//   out = LayerNorm2(s + acc2 + b2)                      (final epilogue; s is recomputed in fp32 from x and the row stats)
+//   out = LayerNorm2(s + acc2 + b2)                      (final epilogue, coalesced through a shared-memory transpose)
 //
 // The d_ffn-wide hidden activation never leaves the SM.
 // Warp roles (384 threads): warps 0-3 / 4-7 = epilogue groups (even / odd chunks; output columns 0-127 / 128-255),
-// warps 8 and 11 = LayerNorm1 producers, warp 9 = weight TMA producer, warp 10 = MMA issuer.
+// warp 8 = A-tile TMA producer, warp 9 = weight TMA producer, warp 10 = MMA issuer.
 #pragma once
 #include "traj_fused.cuh"
 
 namespace axvs {
 
 constexpr int FF_THREADS = 384;
+constexpr int FF_A_SLOTS = 5;
 constexpr int FF_W_SLOTS = 6;
-constexpr int FF_A_BYTES = 4 * TF_KB;     // 128 x 256 bf16
-constexpr int FF_H_BYTES = 2 * TF_KB;     // 128 x 128 bf16
-constexpr int FF_STATS_BYTES = 128 * 8;   // (mean, rstd) per row
+constexpr int FF_H_BYTES = 2 * TF_KB;     // 128 x 128 bf16; doubles as the transpose staging of the final epilogue
 constexpr int FF_XCHG_BYTES = 2 * 2 * 128 * 8;
-constexpr int FF_SMEM_BYTES = FF_A_BYTES + FF_H_BYTES + FF_W_SLOTS * TF_KB + FF_STATS_BYTES + FF_XCHG_BYTES + 1024 + 512;
+constexpr int FF_SMEM_BYTES = FF_A_SLOTS * TF_KB + FF_H_BYTES + FF_W_SLOTS * TF_KB + FF_XCHG_BYTES + 1024 + 512;
 
 struct FfnParams {
-  const float* x;        // [rows, 256] fp32
+  const uint8_t* s_img;  // LayerNorm1 output, bf16 tile image [tiles][4][16 KiB]
+  const float* s32;      // LayerNorm1 output, fp32 [rows, 256] (residual)
   float* out;            // [rows, 256] fp32
-  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const float *ln2_g, *ln2_b;
   const uint8_t* w1;     // packed [4 kb][d_ffn rows][128 B]
   const uint8_t* w2;     // packed [d_ffn/64 kb][256 rows][128 B]
   const float *b1, *b2;
@@ -36,19 +36,18 @@ struct FfnParams {
 __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* a_buf = smem;
-  uint8_t* h_buf = a_buf + FF_A_BYTES;
+  uint8_t* a_ring = smem;
+  uint8_t* h_buf = a_ring + FF_A_SLOTS * TF_KB;
   uint8_t* w_ring = h_buf + FF_H_BYTES;
-  float2* stats = reinterpret_cast<float2*>(w_ring + FF_W_SLOTS * TF_KB);            // [128]
-  float2* xchg = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(stats) + FF_STATS_BYTES);   // [2 parity][2 group][128]
+  float2* xchg = reinterpret_cast<float2*>(w_ring + FF_W_SLOTS * TF_KB);   // [2 parity][2 group][128] (sum, sumsq)
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + FF_XCHG_BYTES);
-  uint64_t* w_full = bars;                    // [6]
+  uint64_t* a_full = bars;                    // [FF_A_SLOTS]
+  uint64_t* a_empty = a_full + FF_A_SLOTS;    // [FF_A_SLOTS]
+  uint64_t* w_full = a_empty + FF_A_SLOTS;    // [6]
   uint64_t* w_empty = w_full + FF_W_SLOTS;    // [6]
   uint64_t* s_full = w_empty + FF_W_SLOTS;    // [2]
   uint64_t* s_empty = s_full + 2;             // [2]
-  uint64_t* a_ready = s_empty + 2;            // LN1 producers -> MMA / epilogue
-  uint64_t* a_free = a_ready + 1;             // MMA (GEMM 1 of the tile retired) -> LN1 producers
-  uint64_t* h_ready = a_free + 1;             // epilogue -> MMA
+  uint64_t* h_ready = s_empty + 2;            // epilogue -> MMA
   uint64_t* h_free = h_ready + 1;             // MMA -> epilogue
   uint64_t* acc_full = h_free + 1;            // MMA -> epilogue
   uint64_t* acc_free = acc_full + 1;          // epilogue -> MMA
@@ -59,10 +58,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
   const int NJ = p.d_ffn / 128;
 
   if (threadIdx.x == 0) {
+    for (int i = 0; i < FF_A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < FF_W_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
-    mbar_init(a_ready, 2);
-    mbar_init(a_free, 1);
     mbar_init(h_ready, 4);
     mbar_init(h_free, 1);
     mbar_init(acc_full, 1);
@@ -79,15 +77,15 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
     // =============================================================== epilogue groups
     setmaxnreg_inc<224>();   // 256*224 + 128*56 = 64512 = the CTA register pool at launch (384 x 168)
     const int g = warp >> 2;
-    const int row_in_tile = (warp & 3) * 32 + lane;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int wq = warp & 3;
+    const int row_in_tile = wq * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     const uint32_t t_acc = tmem + lane_base + 128 * g;          // my 128 output columns of acc2
     const uint32_t t_s = tmem + lane_base + 256 + 128 * g;      // my GEMM-1 stage
+    const int sub = lane >> 3, piece = lane & 7;
+    uint8_t* stg = h_buf + warp * 4096;                         // per-warp transpose staging (final epilogue only)
     uint32_t s_cnt = 0, it = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-      // row statistics of this tile (read now: the producers may refill `stats` once GEMM 1 of this tile has retired)
-      mbar_wait(a_ready, it & 1);
-      const float2 st = stats[row_in_tile];
       // ---- hidden chunks j = g, g+2, ...: bias + ReLU -> bf16 -> h_buf
       for (int j = g; j < NJ; j += 2) {
         mbar_wait(&s_full[g], s_cnt & 1);
@@ -121,100 +119,91 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
         __syncwarp();
         if (lane == 0) mbar_arrive(h_ready);
       }
-      // ---- final: t = acc2 + b2 + s (s recomputed in fp32), LayerNorm2, store
+      // ---- final: t = acc2 + b2 + s, LayerNorm2, store.  Rows are one-per-thread in TMEM; a per-warp transpose through
+      // shared memory (h_buf is idle: every GEMM 2 of this tile has retired) makes the global traffic row-segment
+      // coalesced.  In the transposed domain lane (sub, piece) owns 4 columns of rows {4*i + sub}.
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
-      const int r = tile * 128 + row_in_tile;
-      const bool valid = r < p.rows;
-      float t[128];
+      float4 t[4][8];
+      float ps[8], pq[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ps[i] = pq[i] = 0.f;
+      const int row0 = tile * 128 + wq * 32;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(t_acc + 32 * c, v);
-        tmem_ld_wait();
-        const int col = 128 * g + 32 * c;
-        const float4* x4 = reinterpret_cast<const float4*>(p.x + (size_t)(valid ? r : 0) * 256 + col);
-        const float4* g4 = reinterpret_cast<const float4*>(p.ln1_g + col);
-        const float4* be4 = reinterpret_cast<const float4*>(p.ln1_b + col);
-        const float4* b4 = reinterpret_cast<const float4*>(p.b2 + col);
+        {
+          float v[32];
+          tmem_ld32(t_acc + 32 * c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
+        __syncwarp();
+        const int col = 128 * g + 32 * c + piece * 4;
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 xx = __ldg(x4 + i), gg = __ldg(g4 + i), be = __ldg(be4 + i), bb = __ldg(b4 + i);
-          t[32 * c + 4 * i] = v[4 * i] + bb.x + ((xx.x - st.x) * st.y * gg.x + be.x);
-          t[32 * c + 4 * i + 1] = v[4 * i + 1] + bb.y + ((xx.y - st.x) * st.y * gg.y + be.y);
-          t[32 * c + 4 * i + 2] = v[4 * i + 2] + bb.z + ((xx.z - st.x) * st.y * gg.z + be.z);
-          t[32 * c + 4 * i + 3] = v[4 * i + 3] + bb.w + ((xx.w - st.x) * st.y * gg.w + be.w);
+          const int rl = i * 4 + sub;
+          const int r = row0 + rl;
+          const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((piece ^ (rl & 7)) << 4));
+          const float4 sres = (r < p.rows) ? __ldg(reinterpret_cast<const float4*>(p.s32 + (size_t)r * 256 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 tv = make_float4(a.x + bb.x + sres.x, a.y + bb.y + sres.y, a.z + bb.z + sres.z, a.w + bb.w + sres.w);
+          t[c][i] = tv;
+          ps[i] += tv.x + tv.y + tv.z + tv.w;
+          pq[i] += tv.x * tv.x + tv.y * tv.y + tv.z * tv.z + tv.w * tv.w;
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_free);                      // acc2 columns drained into registers
-      // partial statistics over my 128 columns, combined with the sibling thread (other group, same row)
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 128; ++i) sum += t[i];
-      const float mean_p = sum * (1.f / 128.f);
-      float m2 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 128; ++i) { const float d = t[i] - mean_p; m2 = fmaf(d, d, m2); }
+      // row statistics: reduce over the 8 lanes sharing a row, then combine with the other column half (other group)
       float2* xc = xchg + (it & 1) * 256;
-      xc[g * 128 + row_in_tile] = make_float2(mean_p, m2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], o);
+          pq[i] += __shfl_xor_sync(0xffffffffu, pq[i], o);
+        }
+        if (piece == 0) xc[g * 128 + wq * 32 + i * 4 + sub] = make_float2(ps[i], pq[i]);
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float2 other = xc[(g ^ 1) * 128 + row_in_tile];
-      const float mean = 0.5f * (mean_p + other.x);
-      const float dm = mean_p - other.x;
-      const float var = (m2 + other.y + dm * dm * 64.f) * (1.f / 256.f);
-      const float rstd = rsqrtf(var + p.eps);
-      if (valid) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int col = 128 * g + 32 * c;
-          float4* o4 = reinterpret_cast<float4*>(p.out + (size_t)r * 256 + col);
-          const float4* g4 = reinterpret_cast<const float4*>(p.ln2_g + col);
-          const float4* be4 = reinterpret_cast<const float4*>(p.ln2_b + col);
+      for (int i = 0; i < 8; ++i) {
+        const int rl = i * 4 + sub;
+        const float2 other = xc[(g ^ 1) * 128 + wq * 32 + rl];
+        const float mean = (ps[i] + other.x) * (1.f / 256.f);
+        const float var = fmaxf((pq[i] + other.y) * (1.f / 256.f) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+        const int r = row0 + rl;
+        if (r < p.rows) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 gg = __ldg(g4 + i), be = __ldg(be4 + i);
-            o4[i] = make_float4((t[32 * c + 4 * i] - mean) * rstd * gg.x + be.x, (t[32 * c + 4 * i + 1] - mean) * rstd * gg.y + be.y,
-                                (t[32 * c + 4 * i + 2] - mean) * rstd * gg.z + be.z, (t[32 * c + 4 * i + 3] - mean) * rstd * gg.w + be.w);
+          for (int c = 0; c < 4; ++c) {
+            const int col = 128 * g + 32 * c + piece * 4;
+            const float4 gg = __ldg(reinterpret_cast<const float4*>(p.ln2_g + col)), be = __ldg(reinterpret_cast<const float4*>(p.ln2_b + col));
+            const float4 tv = t[c][i];
+            *reinterpret_cast<float4*>(p.out + (size_t)r * 256 + col) =
+                make_float4((tv.x - mean) * rstd * gg.x + be.x, (tv.y - mean) * rstd * gg.y + be.y, (tv.z - mean) * rstd * gg.z + be.z,
+                            (tv.w - mean) * rstd * gg.w + be.w);
           }
         }
       }
     }
   } else {
     setmaxnreg_dec<56>();
-    if (warp == 8 || warp == 11) {
-      // =============================================================== LayerNorm1 producers (one warp per row)
-      const int pw = (warp == 8) ? 0 : 1;
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln1_g) + lane * 2), g1 = __ldg(reinterpret_cast<const float4*>(p.ln1_g) + lane * 2 + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln1_b) + lane * 2), b1 = __ldg(reinterpret_cast<const float4*>(p.ln1_b) + lane * 2 + 1);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        mbar_wait(a_free, (it & 1) ^ 1);                         // GEMM 1 of the previous tile has retired
-#pragma unroll 2
-        for (int rr = pw; rr < 128; rr += 2) {
-          const int r = tile * 128 + rr;
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-          if (r < p.rows) {
-            const float4* x4 = reinterpret_cast<const float4*>(p.x + (size_t)r * 256) + lane * 2;
-            a = __ldg(x4);
-            c = __ldg(x4 + 1);
-          }
-          const float mu = warp_sum(a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w) * (1.f / 256.f);
-          a.x -= mu; a.y -= mu; a.z -= mu; a.w -= mu; c.x -= mu; c.y -= mu; c.z -= mu; c.w -= mu;
-          const float rstd = rsqrtf(warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w) * (1.f / 256.f) + p.eps);
-          uint4 u;
-          u.x = pack_bf16x2(a.x * rstd * g0.x + b0.x, a.y * rstd * g0.y + b0.y);
-          u.y = pack_bf16x2(a.z * rstd * g0.z + b0.z, a.w * rstd * g0.w + b0.w);
-          u.z = pack_bf16x2(c.x * rstd * g1.x + b1.x, c.y * rstd * g1.y + b1.y);
-          u.w = pack_bf16x2(c.z * rstd * g1.z + b1.z, c.w * rstd * g1.w + b1.w);
-          // lane l holds columns 8l..8l+7 = K-block l/8, 16-byte chunk l%8
-          *reinterpret_cast<uint4*>(a_buf + (lane >> 3) * TF_KB + sw128_offset(rr, lane & 7)) = u;
-          if (lane == 0) stats[rr] = make_float2(mu, rstd);
+    if (warp == 8 && lane == 0) {
+      // =============================================================== A-tile producer
+      uint32_t cnt = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb, ++cnt) {
+          const uint32_t slot = cnt % FF_A_SLOTS, phase = (cnt / FF_A_SLOTS) & 1;
+          mbar_wait(&a_empty[slot], phase ^ 1);
+          mbar_arrive_expect_tx(&a_full[slot], TF_KB);
+          tma_bulk_g2s(a_ring + slot * TF_KB, p.s_img + ((size_t)tile * 4 + kb) * TF_KB, TF_KB, &a_full[slot]);
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready);
       }
     } else if (warp == 9 && lane == 0) {
       // =============================================================== weight producer
@@ -242,8 +231,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
     } else if (warp == 10 && lane == 0) {
       // =============================================================== MMA issuer
       const uint32_t idesc = umma_idesc_bf16(128, 128);
-      const uint32_t a_addr = smem_u32(a_buf), h_addr = smem_u32(h_buf), w_ring_addr = smem_u32(w_ring);
-      uint32_t w_cnt = 0, s_cnt0 = 0, s_cnt1 = 0, it = 0;
+      const uint32_t a_ring_addr = smem_u32(a_ring), h_addr = smem_u32(h_buf), w_ring_addr = smem_u32(w_ring);
+      uint32_t a_cnt = 0, w_cnt = 0, s_cnt0 = 0, s_cnt1 = 0, it = 0;
       auto w_wait = [&]() -> uint32_t {
         const uint32_t slot = w_cnt % FF_W_SLOTS, phase = (w_cnt / FF_W_SLOTS) & 1;
         mbar_wait(&w_full[slot], phase);
@@ -251,8 +240,6 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
         return slot;
       };
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        mbar_wait(a_ready, it & 1);
-        tc_fence_after();
 #pragma unroll 1
         for (int j = 0; j <= NJ; ++j) {
           if (j < NJ) {
@@ -264,20 +251,24 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
             tc_fence_after();
 #pragma unroll 1
             for (int kb = 0; kb < 4; ++kb, ++w_cnt) {
+              const uint32_t ac = a_cnt + kb;
+              const uint32_t aslot = ac % FF_A_SLOTS, aphase = (ac / FF_A_SLOTS) & 1;
+              if (j == 0) {
+                mbar_wait(&a_full[aslot], aphase);
+                tc_fence_after();
+              }
               const uint32_t ws = w_wait();
-              umma_kblock(tmem + 256 + g * 128, a_addr + kb * TF_KB, w_ring_addr + ws * TF_KB, idesc, kb != 0);
+              umma_kblock(tmem + 256 + g * 128, a_ring_addr + aslot * TF_KB, w_ring_addr + ws * TF_KB, idesc, kb != 0);
               umma_commit(&w_empty[ws]);
+              if (j == NJ - 1) umma_commit(&a_empty[aslot]);     // last use of this A K-block
             }
             umma_commit(&s_full[g]);
-            if (j == NJ - 1) umma_commit(a_free);                // a_buf may be overwritten by the next tile's LayerNorm1
           }
           if (j >= 1) {
             // GEMM 2, K-chunk j-1: acc2 += h (128 x 128) * W2[:, 128(j-1) : 128j]^T
             const int jj = j - 1;
             const uint32_t hc = it * NJ + jj;
-            if (jj == 0) {
-              mbar_wait(acc_free, (it & 1) ^ 1);                 // previous tile's final epilogue has drained acc2
-            }
+            if (jj == 0) mbar_wait(acc_free, (it & 1) ^ 1);      // previous tile's final epilogue has drained acc2
             mbar_wait(h_ready, hc & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -291,6 +282,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
           }
         }
         umma_commit(acc_full);
+        a_cnt += 4;
       }
     }
   }
@@ -303,4 +295,32 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
   }
 }
 
+// s = LayerNorm(x): fp32 rows [rows,256] (residual of the FFN) and the bf16 tile image consumed by ffn_fused_kernel.
+// One warp per row; lane l owns columns 8l..8l+7 = K-block l/8, 16-byte chunk l%8 of the image row.
+__global__ void ln_image_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                                float* __restrict__ y32, uint8_t* __restrict__ img, int rows, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + lane * 2), g1 = __ldg(reinterpret_cast<const float4*>(g) + lane * 2 + 1);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + lane * 2), b1 = __ldg(reinterpret_cast<const float4*>(b) + lane * 2 + 1);
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const float4* x4 = reinterpret_cast<const float4*>(x + (size_t)r * C256) + lane * 2;
+    float4 a = __ldg(x4), c = __ldg(x4 + 1);
+    const float mu = warp_sum(a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w) * (1.f / C256);
+    a.x -= mu; a.y -= mu; a.z -= mu; a.w -= mu; c.x -= mu; c.y -= mu; c.z -= mu; c.w -= mu;
+    const float rstd = rsqrtf(warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w) * (1.f / C256) + eps);
+    a.x = a.x * rstd * g0.x + b0.x; a.y = a.y * rstd * g0.y + b0.y; a.z = a.z * rstd * g0.z + b0.z; a.w = a.w * rstd * g0.w + b0.w;
+    c.x = c.x * rstd * g1.x + b1.x; c.y = c.y * rstd * g1.y + b1.y; c.z = c.z * rstd * g1.z + b1.z; c.w = c.w * rstd * g1.w + b1.w;
+    float4* o = reinterpret_cast<float4*>(y32 + (size_t)r * C256) + lane * 2;
+    o[0] = a; o[1] = c;
+    uint4 u;
+    u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
+    u.z = pack_bf16x2(c.x, c.y); u.w = pack_bf16x2(c.z, c.w);
+    *reinterpret_cast<uint4*>(img + ((size_t)(r >> 7) * 4 + (lane >> 3)) * TF_KB + sw128_offset(r & 127, lane & 7)) = u;
+  }
+}
+
 }  // namespace axvs
+static_assert(axvs::FF_SMEM_BYTES <= 232448, "ffn_fused_kernel exceeds the 227 KiB shared-memory limit");
+static_assert(axvs::TF_SMEM_BYTES <= 232448, "traj_fused_kernel exceeds the 227 KiB shared-memory limit");
+static_assert(axvs::GEMM_SMEM_BYTES <= 232448, "gemm_bf16_kernel exceeds the 227 KiB shared-memory limit");

@@ -177,36 +177,45 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
         mbar_arrive(o_ready);
         mbar_arrive(q2_free);
       }
-      // ---- output projection item on my stage: out = resid + acc + bproj (my 128 output columns)
+      // ---- output projection item on my stage: out = resid + acc + bproj (my 128 output columns).
+      // TMEM rows are one-per-thread; a 4 KiB per-warp transpose through shared memory (o_buf is idle here: the
+      // projection MMAs that read it have retired) turns the global accesses into full 128-byte row segments.
       mbar_wait(&s_full[g], s_cnt & 1);
       ++s_cnt;
       tc_fence_after();
-      const int r = tile * 128 + row_in_tile;
-      const bool valid = r < p.rows;
-      const size_t orow = valid ? (size_t)pass_to_canonical(r, p.map_mode, p.dims) : 0;
+      {
+        const int r = tile * 128 + row_in_tile;
+        const int my_orow = (r < p.rows) ? pass_to_canonical(r, p.map_mode, p.dims) : -1;
+        uint8_t* stg = o_buf + warp * 4096;
+        const int sub = lane >> 3, piece = lane & 7;
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        float v[32];
-        tmem_ld32(t_s + 32 * j, v);
-        tmem_ld_wait();
-        if (valid) {
-          const int col = 128 * g + 32 * j;
-          float4* o4 = reinterpret_cast<float4*>(p.out + orow * 256 + col);
-          const float4* b4 = reinterpret_cast<const float4*>(p.b_proj + col);
-          if (p.resid) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.resid + orow * 256 + col);
+        for (int j = 0; j < 4; ++j) {
+          float v[32];
+          tmem_ld32(t_s + 32 * j, v);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 rr = __ldg(r4 + i), bb = __ldg(b4 + i);
-              o4[i] = make_float4(v[4 * i] + bb.x + rr.x, v[4 * i + 1] + bb.y + rr.y, v[4 * i + 2] + bb.z + rr.z, v[4 * i + 3] + bb.w + rr.w);
-            }
-          } else {
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          __syncwarp();
+          const int col = 128 * g + 32 * j + piece * 4;
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b_proj + col));
+          int orow[8];
+          float4 rr[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 bb = __ldg(b4 + i);
-              o4[i] = make_float4(v[4 * i] + bb.x, v[4 * i + 1] + bb.y, v[4 * i + 2] + bb.z, v[4 * i + 3] + bb.w);
-            }
+          for (int it = 0; it < 8; ++it) {
+            orow[it] = __shfl_sync(0xffffffffu, my_orow, it * 4 + sub);
+            rr[it] = (p.resid && orow[it] >= 0) ? __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)orow[it] * 256 + col))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rl = it * 4 + sub;
+            const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((piece ^ (rl & 7)) << 4));
+            if (orow[it] >= 0)
+              *reinterpret_cast<float4*>(p.out + (size_t)orow[it] * 256 + col) =
+                  make_float4(a.x + bb.x + rr[it].x, a.y + bb.y + rr[it].y, a.z + bb.z + rr[it].z, a.w + bb.w + rr[it].w);
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
