@@ -18,13 +18,13 @@ AXIS_NONE, AXIS_H, AXIS_W = 0, 1, 2
 
 class TaWeights(Structure):
     _fields_ = [("w_qkv", c_void_p), ("b_qkv", c_void_p), ("w_pq", c_void_p), ("b_pq", c_void_p),
-                ("w_pkv", c_void_p), ("b_pkv", c_void_p), ("w_pkv_c", c_void_p), ("w_proj", c_void_p), ("b_proj", c_void_p)]
+                ("w_pkv", c_void_p), ("b_pkv", c_void_p), ("w_pq_u", c_void_p), ("w_pkv_u", c_void_p), ("w_proj_u", c_void_p), ("w_proj", c_void_p), ("b_proj", c_void_p)]
 
 
 class LayerWeights(Structure):
     _fields_ = [("attn_h", TaWeights), ("attn_w", TaWeights), ("ln1_g", c_void_p), ("ln1_b", c_void_p),
                 ("w_ffn1", c_void_p), ("b_ffn1", c_void_p), ("w_ffn2", c_void_p), ("b_ffn2", c_void_p),
-                ("ln2_g", c_void_p), ("ln2_b", c_void_p), ("d_ffn", c_int)]
+                ("w_ffn1_u", c_void_p), ("w_ffn2_u", c_void_p), ("ln2_g", c_void_p), ("ln2_b", c_void_p), ("d_ffn", c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/axvs.h declares
@@ -34,6 +34,7 @@ SIGNATURES = {
     "axvs_set_fusion": (c_int, [c_int]),
     "axvs_packed_weight_bytes": (c_size_t, [c_int, c_int]),
     "axvs_pack_weight": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "axvs_pack_weight_units": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "axvs_linear": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p,
                             c_int, c_int, c_void_p, c_void_p]),
     "axvs_spatial_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -210,7 +210,7 @@ int blocks_for(long long work_items, int per_block, int sms) {
 
 extern "C" {
 
-int axvs_version(void) { return 102; }
+int axvs_version(void) { return 103; }
 int axvs_set_fusion(int level) {
   const int prev = g_fusion;
   g_fusion = level < 0 ? 0 : (level > 2 ? 2 : level);
@@ -232,6 +232,18 @@ int axvs_pack_weight(const float* w, int n_out, int k, void* packed, axvs_stream
     pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_out, k, reinterpret_cast<uint8_t*>(packed));
   }
   AXVS_CHECK_LAUNCH("pack_weight_kernel");
+  return AXVS_OK;
+}
+
+int axvs_pack_weight_units(const float* w, int n_out, int k, int k_major, void* packed, axvs_stream_t stream) {
+  if (!w || !packed) return fail(AXVS_E_INVALID, "pack_weight_units: null pointer");
+  if (n_out <= 0 || n_out % 128 || k <= 0 || k % 128) return fail(AXVS_E_UNSUPPORTED, "pack_weight_units: need n_out %% 128 == 0 and k %% 128 == 0 (got %d, %d)", n_out, k);
+  const int total = n_out * (k / 8);
+  {
+    ProfScope ps(KC_PACKW, 0, (double)n_out * k * 6, (cudaStream_t)stream);
+    pack_weight_units_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_out, k, k_major, reinterpret_cast<uint8_t*>(packed));
+  }
+  AXVS_CHECK_LAUNCH("pack_weight_units_kernel");
   return AXVS_OK;
 }
 
@@ -334,7 +346,7 @@ int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, 
     if (rc) return rc;
   }
   if (g_fusion >= 1) {
-    if (!w->w_pkv_c) return fail(AXVS_E_INVALID, "traj_attn: w_pkv_c (head-pair ordered proj_kv) is required by the fused kernel");
+    if (!w->w_pq_u || !w->w_pkv_u || !w->w_proj_u) return fail(AXVS_E_INVALID, "traj_attn: unit-format weights (w_pq_u, w_pkv_u, w_proj_u) are required by the fused kernel");
     const int tiles = (int)((rows + 127) / 128);
     {
       ProfScope ps(KC_X2IMG, 0, (double)rows * F * 512.0 * 2 + (double)rows * 512.0, st);
@@ -344,9 +356,9 @@ int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, 
     TrajParams tp;
     memset(&tp, 0, sizeof(tp));
     tp.x_img = ws.x_img; tp.xd_img = ws.xd_img;
-    tp.w_pq = reinterpret_cast<const uint8_t*>(w->w_pq);
-    tp.w_pkv = reinterpret_cast<const uint8_t*>(w->w_pkv_c);
-    tp.w_proj = reinterpret_cast<const uint8_t*>(w->w_proj);
+    tp.w_pq = reinterpret_cast<const uint8_t*>(w->w_pq_u);
+    tp.w_pkv = reinterpret_cast<const uint8_t*>(w->w_pkv_u);
+    tp.w_proj = reinterpret_cast<const uint8_t*>(w->w_proj_u);
     tp.b_pq = w->b_pq; tp.b_v2 = w->b_pkv + 256; tp.b_proj = w->b_proj;
     tp.resid = resid; tp.out = out;
     tp.rows = (int)rows; tp.tiles = tiles; tp.F = F;
@@ -416,7 +428,7 @@ int axvs_ln_ffn_fwd(const float* x, float* out, const axvs_layer_weights* w, int
   FfnWorkspace ws = carve_ffn(workspace, (size_t)rows, w->d_ffn);
   if (ws.bytes > workspace_bytes) return fail(AXVS_E_WORKSPACE, "ln_ffn: workspace %zu < required %zu", workspace_bytes, ws.bytes);
   int rc;
-  if (g_fusion >= 2 && w->d_ffn >= 512) {
+  if (g_fusion >= 2 && w->d_ffn >= 512 && w->w_ffn1_u && w->w_ffn2_u) {
     DeviceInfo* d;
     if ((rc = device_info(&d))) return rc;
     {
@@ -428,7 +440,7 @@ int axvs_ln_ffn_fwd(const float* x, float* out, const axvs_layer_weights* w, int
     memset(&fp, 0, sizeof(fp));
     fp.s_img = ws.s_img; fp.s32 = ws.s3; fp.out = out;
     fp.ln2_g = w->ln2_g; fp.ln2_b = w->ln2_b;
-    fp.w1 = reinterpret_cast<const uint8_t*>(w->w_ffn1); fp.w2 = reinterpret_cast<const uint8_t*>(w->w_ffn2);
+    fp.w1 = reinterpret_cast<const uint8_t*>(w->w_ffn1_u); fp.w2 = reinterpret_cast<const uint8_t*>(w->w_ffn2_u);
     fp.b1 = w->b_ffn1; fp.b2 = w->b_ffn2;
     fp.rows = rows; fp.tiles = (rows + 127) / 128; fp.d_ffn = w->d_ffn; fp.eps = 1e-5f;
     {

@@ -16,18 +16,18 @@ namespace axvs {
 
 constexpr int FF_THREADS = 384;
 constexpr int FF_A_SLOTS = 5;
-constexpr int FF_W_SLOTS = 6;
+constexpr int FF_W_SLOTS = 3;                  // 32 KiB weight units
 constexpr int FF_H_BYTES = 2 * TF_KB;     // 128 x 128 bf16; doubles as the transpose staging of the final epilogue
 constexpr int FF_XCHG_BYTES = 2 * 2 * 128 * 8;
-constexpr int FF_SMEM_BYTES = FF_A_SLOTS * TF_KB + FF_H_BYTES + FF_W_SLOTS * TF_KB + FF_XCHG_BYTES + 1024 + 512;
+constexpr int FF_SMEM_BYTES = FF_A_SLOTS * TF_KB + FF_H_BYTES + FF_W_SLOTS * TF_WU + FF_XCHG_BYTES + 1024 + 512;
 
 struct FfnParams {
   const uint8_t* s_img;  // LayerNorm1 output, bf16 tile image [tiles][4][16 KiB]
   const float* s32;      // LayerNorm1 output, fp32 [rows, 256] (residual)
   float* out;            // [rows, 256] fp32
   const float *ln2_g, *ln2_b;
-  const uint8_t* w1;     // packed [4 kb][d_ffn rows][128 B]
-  const uint8_t* w2;     // packed [d_ffn/64 kb][256 rows][128 B]
+  const uint8_t* w1;     // unit format, (row tile j, K group): unit = 2 j + kg
+  const uint8_t* w2;     // unit format, K-major: unit = 2 jj + half
   const float *b1, *b2;
   int rows, tiles, d_ffn;
   float eps;
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
   uint8_t* a_ring = smem;
   uint8_t* h_buf = a_ring + FF_A_SLOTS * TF_KB;
   uint8_t* w_ring = h_buf + FF_H_BYTES;
-  float2* xchg = reinterpret_cast<float2*>(w_ring + FF_W_SLOTS * TF_KB);   // [2 parity][2 group][128] (sum, sumsq)
+  float2* xchg = reinterpret_cast<float2*>(w_ring + FF_W_SLOTS * TF_WU);   // [2 parity][2 group][128] (sum, sumsq)
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + FF_XCHG_BYTES);
   uint64_t* a_full = bars;                    // [FF_A_SLOTS]
   uint64_t* a_empty = a_full + FF_A_SLOTS;    // [FF_A_SLOTS]
@@ -206,38 +206,32 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
         }
       }
     } else if (warp == 9 && lane == 0) {
-      // =============================================================== weight producer
-      uint32_t cnt = 0;
-      auto push = [&](const uint8_t* img, int rows_total, int kb, int row0) {
-        const uint32_t slot = cnt % FF_W_SLOTS, phase = (cnt / FF_W_SLOTS) & 1;
+      // =============================================================== weight producer (32 KiB units)
+      uint32_t slot = 0, phase = 0;
+      auto push = [&](const uint8_t* img, int unit) {
         mbar_wait(&w_empty[slot], phase ^ 1);
-        mbar_arrive_expect_tx(&w_full[slot], TF_KB);
-        tma_bulk_g2s(w_ring + slot * TF_KB, img + ((size_t)kb * rows_total + row0) * 128, TF_KB, &w_full[slot]);
-        ++cnt;
+        mbar_arrive_expect_tx(&w_full[slot], TF_WU);
+        tma_bulk_g2s(w_ring + slot * TF_WU, img + (size_t)unit * TF_WU, TF_WU, &w_full[slot]);
+        if (++slot == FF_W_SLOTS) { slot = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
 #pragma unroll 1
         for (int j = 0; j <= NJ; ++j) {
-          if (j < NJ) {
-#pragma unroll 1
-            for (int kb = 0; kb < 4; ++kb) push(p.w1, p.d_ffn, kb, j * 128);
-          }
-          if (j >= 1) {
-#pragma unroll 1
-            for (int i = 0; i < 4; ++i) push(p.w2, 256, 2 * (j - 1) + (i >> 1), (i & 1) * 128);
-          }
+          if (j < NJ) { push(p.w1, 2 * j); push(p.w1, 2 * j + 1); }
+          if (j >= 1) { push(p.w2, 2 * (j - 1)); push(p.w2, 2 * (j - 1) + 1); }
         }
       }
-    } else if (warp == 10 && lane == 0) {
-      // =============================================================== MMA issuer
+    } else if (warp == 10) {
+      // =============================================================== MMA issuer (converged warp, elected lane issues)
       const uint32_t idesc = umma_idesc_bf16(128, 128);
       const uint32_t a_ring_addr = smem_u32(a_ring), h_addr = smem_u32(h_buf), w_ring_addr = smem_u32(w_ring);
-      uint32_t a_cnt = 0, w_cnt = 0, s_cnt0 = 0, s_cnt1 = 0, it = 0;
+      uint32_t a_cnt = 0, w_slot = 0, w_phase = 0, s_cnt0 = 0, s_cnt1 = 0, it = 0;
       auto w_wait = [&]() -> uint32_t {
-        const uint32_t slot = w_cnt % FF_W_SLOTS, phase = (w_cnt / FF_W_SLOTS) & 1;
-        mbar_wait(&w_full[slot], phase);
+        mbar_wait(&w_full[w_slot], w_phase);
         tc_fence_after();
-        return slot;
+        const uint32_t ws = w_slot;
+        if (++w_slot == FF_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
+        return ws;
       };
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
 #pragma unroll 1
@@ -250,38 +244,35 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
             if (g) ++s_cnt1; else ++s_cnt0;
             tc_fence_after();
 #pragma unroll 1
-            for (int kb = 0; kb < 4; ++kb, ++w_cnt) {
-              const uint32_t ac = a_cnt + kb;
-              const uint32_t aslot = ac % FF_A_SLOTS, aphase = (ac / FF_A_SLOTS) & 1;
+            for (int kg = 0; kg < 2; ++kg) {
+              const uint32_t ac0 = a_cnt + 2 * kg, ac1 = ac0 + 1;
+              const uint32_t s0 = ac0 % FF_A_SLOTS, s1 = ac1 % FF_A_SLOTS;
               if (j == 0) {
-                mbar_wait(&a_full[aslot], aphase);
+                mbar_wait(&a_full[s0], (ac0 / FF_A_SLOTS) & 1);
+                mbar_wait(&a_full[s1], (ac1 / FF_A_SLOTS) & 1);
                 tc_fence_after();
               }
               const uint32_t ws = w_wait();
-              umma_kblock(tmem + 256 + g * 128, a_ring_addr + aslot * TF_KB, w_ring_addr + ws * TF_KB, idesc, kb != 0);
-              umma_commit(&w_empty[ws]);
-              if (j == NJ - 1) umma_commit(&a_empty[aslot]);     // last use of this A K-block
+              // last chunk: final use of the A K-blocks; last K group: the chunk accumulator is complete
+              umma_unit_elect(tmem + 256 + g * 128, a_ring_addr + s0 * TF_KB, a_ring_addr + s1 * TF_KB, w_ring_addr + ws * TF_WU, idesc, kg != 0,
+                              &w_empty[ws], j == NJ - 1 ? &a_empty[s0] : nullptr, j == NJ - 1 ? &a_empty[s1] : nullptr, kg == 1 ? &s_full[g] : nullptr);
             }
-            umma_commit(&s_full[g]);
           }
           if (j >= 1) {
-            // GEMM 2, K-chunk j-1: acc2 += h (128 x 128) * W2[:, 128(j-1) : 128j]^T
+            // GEMM 2, K-chunk j-1: acc2 += h (128 x 128) * W2[:, 128(j-1) : 128j]^T, one unit per output-column half
             const int jj = j - 1;
             const uint32_t hc = it * NJ + jj;
             if (jj == 0) mbar_wait(acc_free, (it & 1) ^ 1);      // previous tile's final epilogue has drained acc2
             mbar_wait(h_ready, hc & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int i = 0; i < 4; ++i, ++w_cnt) {
-              const int kb2 = i >> 1, half = i & 1;
+            for (int half = 0; half < 2; ++half) {
               const uint32_t ws = w_wait();
-              umma_kblock(tmem + half * 128, h_addr + kb2 * TF_KB, w_ring_addr + ws * TF_KB, idesc, (jj | kb2) != 0);
-              umma_commit(&w_empty[ws]);
+              umma_unit_elect(tmem + half * 128, h_addr, h_addr + TF_KB, w_ring_addr + ws * TF_WU, idesc, jj != 0,
+                              &w_empty[ws], half ? h_free : nullptr, (half && j == NJ) ? acc_full : nullptr, nullptr);
             }
-            umma_commit(h_free);
           }
         }
-        umma_commit(acc_full);
         a_cnt += 4;
       }
     }

@@ -285,4 +285,27 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int n_out, int K
   }
 }
 
+// fp32 [n_out, K] -> bf16 "unit" image for the fused kernels: 32 KiB units = [2 K-blocks][128 rows x 128 B, SWIZZLE_128B],
+// i.e. one TMA bulk copy brings the operand of 8 UMMAs (N = 128, K = 128).  Unit order: k_major == 0 -> unit(rt, kg) =
+// rt * (K/128) + kg (all K of a 128-row tile contiguous); k_major == 1 -> unit = kg * (n_out/128) + rt.
+__global__ void pack_weight_units_kernel(const float* __restrict__ w, int n_out, int K, int k_major, uint8_t* __restrict__ packed) {
+  const int total = n_out * (K / 8);
+  const int KG = K / 128, RT = n_out / 128;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / (K / 8);
+    const int c8 = idx % (K / 8);
+    const int kb = c8 >> 3, ch = c8 & 7;
+    const int rt = r >> 7, rl = r & 127, kg = kb >> 1, kb2 = kb & 1;
+    const size_t unit = k_major ? (size_t)kg * RT + rt : (size_t)rt * KG + kg;
+    const float4* s = reinterpret_cast<const float4*>(w + (size_t)r * K + c8 * 8);
+    float4 a = s[0], b = s[1];
+    uint4 u;
+    u.x = pack_bf16x2(a.x, a.y);
+    u.y = pack_bf16x2(a.z, a.w);
+    u.z = pack_bf16x2(b.x, b.y);
+    u.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(packed + unit * 32768 + (size_t)kb2 * 16384 + sw128_offset(rl, ch)) = u;
+  }
+}
+
 }  // namespace axvs

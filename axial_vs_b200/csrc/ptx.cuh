@@ -184,6 +184,58 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// ---- warp-converged issue path (measured in tools/microbench/umma_issue.cu: a lone diverged thread pays ~570 clk per
+// K-block for descriptor build + R2UR traffic; a converged warp with an elected lane reaches the tensor-pipe rate)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+constexpr uint32_t UMMA_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(UMMA_DESC_HI), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One K-block (4 UMMAs) + up to two commits, executed by the elected lane of a converged warp.
+__device__ __forceinline__ void umma_kblock_elect(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint32_t idesc, bool accumulate,
+                                                  uint64_t* commit_a, uint64_t* commit_b) {
+  const uint32_t a_lo = umma_desc_lo(a_addr), w_lo = umma_desc_lo(w_addr);
+  if (elect_one()) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_lo(tmem_d, a_lo + 2 * k, w_lo + 2 * k, idesc, (accumulate || k) ? 1u : 0u);
+    if (commit_a) umma_commit(commit_a);
+    if (commit_b) umma_commit(commit_b);
+  }
+  __syncwarp();
+}
+// One 32 KiB weight unit = two K-blocks (8 UMMAs, N = 128, K = 128) + up to four commits, elected lane of a converged warp.
+// a0 / a1: shared-memory addresses of the two A K-blocks; w: address of the unit (its K-blocks are 16 KiB apart).
+__device__ __forceinline__ void umma_unit_elect(uint32_t tmem_d, uint32_t a0, uint32_t a1, uint32_t w, uint32_t idesc, bool accumulate,
+                                                uint64_t* c0, uint64_t* c1, uint64_t* c2, uint64_t* c3) {
+  const uint32_t a0_lo = umma_desc_lo(a0), a1_lo = umma_desc_lo(a1), w_lo = umma_desc_lo(w);
+  if (elect_one()) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_lo(tmem_d, a0_lo + 2 * k, w_lo + 2 * k, idesc, (accumulate || k) ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_lo(tmem_d, a1_lo + 2 * k, w_lo + (16384 >> 4) + 2 * k, idesc, 1u);
+    if (c0) umma_commit(c0);
+    if (c1) umma_commit(c1);
+    if (c2) umma_commit(c2);
+    if (c3) umma_commit(c3);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  if (elect_one()) umma_commit(bar);
+  __syncwarp();
+}
+
 // Issue the 4 UMMAs (K = 64 = 4 x 16) of one K-block: D[128 x N] (+)= A_kblock[128 x 64] * W_kblock[N x 64]^T.
 // a_addr / w_addr: shared-memory byte addresses of SWIZZLE_128B K-major tiles (1024 B aligned).
 __device__ __forceinline__ void umma_kblock(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint32_t idesc, bool accumulate) {

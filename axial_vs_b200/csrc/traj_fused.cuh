@@ -20,18 +20,19 @@
 namespace axvs {
 
 constexpr int TF_THREADS = 384;
-constexpr int TF_A_SLOTS = 6;
-constexpr int TF_W_SLOTS = 4;
+constexpr int TF_A_SLOTS = 4;
+constexpr int TF_W_SLOTS = 3;
 constexpr int TF_KB = 16384;                       // one K-block tile: 128 rows x 64 bf16
+constexpr int TF_WU = 32768;                       // one weight unit: 128 rows x 128 K (two K-blocks), one TMA bulk copy
 constexpr int TF_O_BYTES = 4 * TF_KB;              // o operand, 128 x 256 bf16
-constexpr int TF_SMEM_BYTES = TF_O_BYTES + TF_A_SLOTS * TF_KB + TF_W_SLOTS * TF_KB + 1024 + 512;
+constexpr int TF_SMEM_BYTES = TF_O_BYTES + TF_A_SLOTS * TF_KB + TF_W_SLOTS * TF_WU + 1024 + 512;
 
 struct TrajParams {
   const uint8_t* x_img;    // [F][tiles][4][16 KiB]
   const uint8_t* xd_img;   // [tiles][4][16 KiB]
-  const uint8_t* w_pq;     // packed [4][256 rows][128 B]
-  const uint8_t* w_pkv;    // packed, rows re-ordered per head pair: chunk c = [k2 heads 2c,2c+1 | v2 heads 2c,2c+1]
-  const uint8_t* w_proj;   // packed [4][256][128 B]
+  const uint8_t* w_pq;     // unit format (row tile, K group): 4 units
+  const uint8_t* w_pkv;    // unit format, rows re-ordered per head pair: chunk c = [k2 heads 2c,2c+1 | v2 heads 2c,2c+1]: 8 units
+  const uint8_t* w_proj;   // unit format: 4 units
   const float* b_pq;
   const float* b_v2;       // proj_kv.bias[256:512]
   const float* b_proj;
@@ -49,11 +50,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
   uint8_t* o_buf = smem;
   uint8_t* a_ring = smem + TF_O_BYTES;
   uint8_t* w_ring = a_ring + TF_A_SLOTS * TF_KB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + TF_W_SLOTS * TF_KB);
-  uint64_t* a_full = bars;                       // [6]
-  uint64_t* a_empty = a_full + TF_A_SLOTS;       // [6]
-  uint64_t* w_full = a_empty + TF_A_SLOTS;       // [4]
-  uint64_t* w_empty = w_full + TF_W_SLOTS;       // [4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + TF_W_SLOTS * TF_WU);
+  uint64_t* a_full = bars;                       // [TF_A_SLOTS]
+  uint64_t* a_empty = a_full + TF_A_SLOTS;       // [TF_A_SLOTS]
+  uint64_t* w_full = a_empty + TF_A_SLOTS;       // [TF_W_SLOTS]
+  uint64_t* w_empty = w_full + TF_W_SLOTS;       // [TF_W_SLOTS]
   uint64_t* s_full = w_empty + TF_W_SLOTS;       // [2]
   uint64_t* s_empty = s_full + 2;                // [2]
   uint64_t* q2_full = s_empty + 2;
@@ -239,56 +240,57 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
         }
       }
     } else if (warp == 9 && lane == 0) {
-      // =============================================================== weight producer (128-row x 64-K stages)
-      uint32_t cnt = 0;
-      auto push = [&](const uint8_t* img, int rows_total, int kb, int row0) {
-        const uint32_t slot = cnt % TF_W_SLOTS, phase = (cnt / TF_W_SLOTS) & 1;
+      // =============================================================== weight producer (32 KiB units)
+      uint32_t slot = 0, phase = 0;
+      auto push = [&](const uint8_t* img, int unit) {
         mbar_wait(&w_empty[slot], phase ^ 1);
-        mbar_arrive_expect_tx(&w_full[slot], TF_KB);
-        tma_bulk_g2s(w_ring + slot * TF_KB, img + ((size_t)kb * rows_total + row0) * 128, TF_KB, &w_full[slot]);
-        ++cnt;
+        mbar_arrive_expect_tx(&w_full[slot], TF_WU);
+        tma_bulk_g2s(w_ring + slot * TF_WU, img + (size_t)unit * TF_WU, TF_WU, &w_full[slot]);
+        if (++slot == TF_W_SLOTS) { slot = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
 #pragma unroll 1
-        for (int i = 0; i < 8; ++i) push(p.w_pq, 256, i >> 1, (i & 1) * 128);
+        for (int u = 0; u < 4; ++u) push(p.w_pq, u);               // (half, kg) = (u >> 1, u & 1)
 #pragma unroll 1
-        for (int i = 0; i < 16 * F; ++i) {
-          const int ci = (i >> 2) & 3;
-          const int c = ((ci & 1) << 1) | (ci >> 1);             // chunk order 0,2,1,3: stages alternate
-          push(p.w_pkv, 512, i & 3, c * 128);
+        for (int i = 0; i < 8 * F; ++i) {
+          const int ci = (i >> 1) & 3;
+          const int c = ((ci & 1) << 1) | (ci >> 1);               // chunk order 0,2,1,3: stages alternate
+          push(p.w_pkv, c * 2 + (i & 1));
         }
 #pragma unroll 1
-        for (int i = 0; i < 8; ++i) push(p.w_proj, 256, i >> 1, (i & 1) * 128);
+        for (int u = 0; u < 4; ++u) push(p.w_proj, u);
       }
-    } else if (warp == 10 && lane == 0) {
-      // =============================================================== MMA issuer
+    } else if (warp == 10) {
+      // =============================================================== MMA issuer (converged warp, elected lane issues)
       const uint32_t idesc = umma_idesc_bf16(128, 128);
       const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring), o_addr = smem_u32(o_buf);
-      uint32_t a_cnt = 0, w_cnt = 0, s_cnt0 = 0, s_cnt1 = 0, it = 0;
+      uint32_t a_cnt = 0, w_slot = 0, w_phase = 0, s_cnt0 = 0, s_cnt1 = 0, it = 0;
       auto w_wait = [&]() -> uint32_t {
-        const uint32_t slot = w_cnt % TF_W_SLOTS, phase = (w_cnt / TF_W_SLOTS) & 1;
-        mbar_wait(&w_full[slot], phase);
+        mbar_wait(&w_full[w_slot], w_phase);
         tc_fence_after();
-        return slot;
+        const uint32_t ws = w_slot;
+        if (++w_slot == TF_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
+        return ws;
       };
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        // ---- GEMM 1: q2 accumulators (columns [0,256))
+        // ---- GEMM 1: q2 accumulators (columns [0,256)); the 4 x_diag K-blocks stay resident for both column halves
         mbar_wait(q2_free, (it & 1) ^ 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int kb = 0; kb < 4; ++kb, ++a_cnt) {
-          const uint32_t aslot = a_cnt % TF_A_SLOTS, aphase = (a_cnt / TF_A_SLOTS) & 1;
-          mbar_wait(&a_full[aslot], aphase);
-          tc_fence_after();
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half, ++w_cnt) {
-            const uint32_t ws = w_wait();
-            umma_kblock(tmem + half * 128, a_ring_addr + aslot * TF_KB, w_ring_addr + ws * TF_KB, idesc, kb != 0);
-            umma_commit(&w_empty[ws]);
+        for (int u = 0; u < 4; ++u) {
+          const int half = u >> 1, kg = u & 1;
+          const uint32_t ac0 = a_cnt + 2 * kg, ac1 = ac0 + 1;
+          const uint32_t s0 = ac0 % TF_A_SLOTS, s1 = ac1 % TF_A_SLOTS;
+          if (half == 0) {
+            mbar_wait(&a_full[s0], (ac0 / TF_A_SLOTS) & 1);
+            mbar_wait(&a_full[s1], (ac1 / TF_A_SLOTS) & 1);
+            tc_fence_after();
           }
-          umma_commit(&a_empty[aslot]);
+          const uint32_t ws = w_wait();
+          umma_unit_elect(tmem + half * 128, a_ring_addr + s0 * TF_KB, a_ring_addr + s1 * TF_KB, w_ring_addr + ws * TF_WU, idesc, kg != 0,
+                          &w_empty[ws], half ? &a_empty[s0] : nullptr, half ? &a_empty[s1] : nullptr, u == 3 ? q2_full : nullptr);
         }
-        umma_commit(q2_full);
+        a_cnt += 4;
         // ---- GEMM 2: per frame, four 128-column chunks alternating between the two TMEM stages
 #pragma unroll 1
         for (int f = 0; f < F; ++f) {
@@ -300,19 +302,18 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
             if (g) ++s_cnt1; else ++s_cnt0;
             tc_fence_after();
 #pragma unroll 1
-            for (int kb = 0; kb < 4; ++kb, ++w_cnt) {
-              const uint32_t ac = a_cnt + kb;
-              const uint32_t aslot = ac % TF_A_SLOTS, aphase = (ac / TF_A_SLOTS) & 1;
+            for (int kg = 0; kg < 2; ++kg) {
+              const uint32_t ac0 = a_cnt + 2 * kg, ac1 = ac0 + 1;
+              const uint32_t s0 = ac0 % TF_A_SLOTS, s1 = ac1 % TF_A_SLOTS;
               if (ci == 0) {
-                mbar_wait(&a_full[aslot], aphase);
+                mbar_wait(&a_full[s0], (ac0 / TF_A_SLOTS) & 1);
+                mbar_wait(&a_full[s1], (ac1 / TF_A_SLOTS) & 1);
                 tc_fence_after();
               }
               const uint32_t ws = w_wait();
-              umma_kblock(tmem + 256 + g * 128, a_ring_addr + aslot * TF_KB, w_ring_addr + ws * TF_KB, idesc, kb != 0);
-              umma_commit(&w_empty[ws]);
-              if (ci == 3) umma_commit(&a_empty[aslot]);
+              umma_unit_elect(tmem + 256 + g * 128, a_ring_addr + s0 * TF_KB, a_ring_addr + s1 * TF_KB, w_ring_addr + ws * TF_WU, idesc, kg != 0,
+                              &w_empty[ws], ci == 3 ? &a_empty[s0] : nullptr, ci == 3 ? &a_empty[s1] : nullptr, kg == 1 ? &s_full[g] : nullptr);
             }
-            umma_commit(&s_full[g]);
           }
           a_cnt += 4;
         }
@@ -324,14 +325,12 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
         ++s_cnt1;
         tc_fence_after();
 #pragma unroll 1
-        for (int i = 0; i < 8; ++i, ++w_cnt) {
-          const int kb = i >> 1, half = i & 1;
+        for (int u = 0; u < 4; ++u) {
+          const int half = u >> 1, kg = u & 1;
           const uint32_t ws = w_wait();
-          umma_kblock(tmem + 256 + half * 128, o_addr + kb * TF_KB, w_ring_addr + ws * TF_KB, idesc, kb != 0);
-          umma_commit(&w_empty[ws]);
+          umma_unit_elect(tmem + 256 + half * 128, o_addr + (2 * kg) * TF_KB, o_addr + (2 * kg + 1) * TF_KB, w_ring_addr + ws * TF_WU, idesc, kg != 0,
+                          &w_empty[ws], kg == 1 ? &s_full[half] : nullptr, nullptr, nullptr);
         }
-        umma_commit(&s_full[0]);
-        umma_commit(&s_full[1]);
       }
     }
   }

@@ -68,6 +68,18 @@ def pack_weight(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pack_weight_units(w: torch.Tensor, k_major: bool = False) -> torch.Tensor:
+    """fp32 weight [n_out, k] -> 32 KiB-unit image of the fused kernels (see include/axvs.h)."""
+    _check(w, "weight", torch.float32)
+    n_out, k = w.shape
+    lib = _lib.load()
+    out = torch.empty(lib.axvs_packed_weight_bytes(n_out, k), dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(lib.axvs_pack_weight_units(w.data_ptr(), n_out, k, int(k_major), out.data_ptr(), _stream(w.device)),
+                   "axvs_pack_weight_units")
+    return out
+
+
 @dataclass
 class PackedTA:
     """Device-resident packed parameters of one TrajectoryAttention (struct axvs_ta_weights)."""
@@ -77,12 +89,15 @@ class PackedTA:
     b_pq: torch.Tensor
     w_pkv: torch.Tensor
     b_pkv: torch.Tensor
-    w_pkv_c: torch.Tensor
+    w_pq_u: torch.Tensor
+    w_pkv_u: torch.Tensor
+    w_proj_u: torch.Tensor
     w_proj: torch.Tensor
     b_proj: torch.Tensor
 
     def tensors(self) -> List[torch.Tensor]:
-        return [self.w_qkv, self.b_qkv, self.w_pq, self.b_pq, self.w_pkv, self.b_pkv, self.w_pkv_c, self.w_proj, self.b_proj]
+        return [self.w_qkv, self.b_qkv, self.w_pq, self.b_pq, self.w_pkv, self.b_pkv, self.w_pq_u, self.w_pkv_u, self.w_proj_u,
+                self.w_proj, self.b_proj]
 
     def struct(self) -> TaWeights:
         return TaWeights(*[t.data_ptr() for t in self.tensors()])
@@ -107,7 +122,8 @@ def pack_ta(p: Dict[str, torch.Tensor], prefix: str = "") -> PackedTA:
     order = torch.cat([torch.cat([torch.arange(64 * c, 64 * c + 64), torch.arange(256 + 64 * c, 256 + 64 * c + 64)]) for c in range(4)])
     wkv_c = wkv[order.to(wkv.device)].contiguous()
     return PackedTA(pack_weight(wqkv), bqkv, pack_weight(g("proj_q.weight")), g("proj_q.bias"),
-                    pack_weight(wkv), g("proj_kv.bias"), pack_weight(wkv_c), pack_weight(g("proj.weight")), g("proj.bias"))
+                    pack_weight(wkv), g("proj_kv.bias"), pack_weight_units(g("proj_q.weight")), pack_weight_units(wkv_c),
+                    pack_weight_units(g("proj.weight")), pack_weight(g("proj.weight")), g("proj.bias"))
 
 
 @dataclass
@@ -121,6 +137,8 @@ class PackedLayer:
     b_ffn1: torch.Tensor
     w_ffn2: torch.Tensor
     b_ffn2: torch.Tensor
+    w_ffn1_u: torch.Tensor
+    w_ffn2_u: torch.Tensor
     ln2_g: torch.Tensor
     ln2_b: torch.Tensor
     d_ffn: int
@@ -128,17 +146,17 @@ class PackedLayer:
     def tensors(self) -> List[torch.Tensor]:
         aw = self.attn_w if self.attn_w is not None else self.attn_h
         return self.attn_h.tensors() + aw.tensors() + [self.ln1_g, self.ln1_b, self.w_ffn1, self.b_ffn1, self.w_ffn2,
-                                                       self.b_ffn2, self.ln2_g, self.ln2_b]
+                                                       self.b_ffn2, self.w_ffn1_u, self.w_ffn2_u, self.ln2_g, self.ln2_b]
 
     def struct(self) -> LayerWeights:
         aw = self.attn_w if self.attn_w is not None else self.attn_h
         return LayerWeights(self.attn_h.struct(), aw.struct(), self.ln1_g.data_ptr(), self.ln1_b.data_ptr(),
                             self.w_ffn1.data_ptr(), self.b_ffn1.data_ptr(), self.w_ffn2.data_ptr(), self.b_ffn2.data_ptr(),
-                            self.ln2_g.data_ptr(), self.ln2_b.data_ptr(), self.d_ffn)
+                            self.w_ffn1_u.data_ptr(), self.w_ffn2_u.data_ptr(), self.ln2_g.data_ptr(), self.ln2_b.data_ptr(), self.d_ffn)
 
     @staticmethod
     def from_tensors(ts: Sequence[torch.Tensor], d_ffn: int) -> "PackedLayer":
-        return PackedLayer(PackedTA.from_tensors(ts[0:9]), PackedTA.from_tensors(ts[9:18]), *ts[18:26], d_ffn=d_ffn)
+        return PackedLayer(PackedTA.from_tensors(ts[0:11]), PackedTA.from_tensors(ts[11:22]), *ts[22:32], d_ffn=d_ffn)
 
 
 def pack_layer(p: Dict[str, torch.Tensor], axial: bool = True) -> PackedLayer:
@@ -149,7 +167,8 @@ def pack_layer(p: Dict[str, torch.Tensor], axial: bool = True) -> PackedLayer:
     ah = pack_ta(p, "height_attn." if axial else "temporal_attn.")
     aw = pack_ta(p, "width_attn.") if axial else None
     return PackedLayer(ah, aw, g("norm1.weight"), g("norm1.bias"), pack_weight(g("linear1.weight")), g("linear1.bias"),
-                       pack_weight(g("linear2.weight")), g("linear2.bias"), g("norm2.weight"), g("norm2.bias"),
+                       pack_weight(g("linear2.weight")), g("linear2.bias"), pack_weight_units(g("linear1.weight")),
+                       pack_weight_units(g("linear2.weight"), k_major=True), g("norm2.weight"), g("norm2.bias"),
                        d_ffn=p["linear1.weight"].shape[0])
 
 

@@ -57,6 +57,10 @@ int axvs_set_fusion(int level);
  * brings a weight tile in.  n_out % 8 == 0, k % 64 == 0. */
 size_t axvs_packed_weight_bytes(int n_out, int k);
 int axvs_pack_weight(const float* w, int n_out, int k, void* packed, axvs_stream_t stream);
+/* "Unit" format of the fused kernels: 32 KiB units = [2 K-blocks][128 rows x 128 B swizzled] so one TMA bulk copy feeds
+ * eight tensor-core instructions.  k_major = 0: units ordered (row tile, K group); 1: (K group, row tile).
+ * n_out % 128 == 0, k % 128 == 0.  Same size as axvs_packed_weight_bytes. */
+int axvs_pack_weight_units(const float* w, int n_out, int k, int k_major, void* packed, axvs_stream_t stream);
 
 /* One TrajectoryAttention's parameters (WC/temporal_attention.py:27-33; CC:85-89; TL .../msdeformattn_pixel_decoder.py:659-665).
  * w_qkv packs rows [Wq; Wk; Wv] (or the fused `qkv` Linear of the cross-clip variant): [768, 256]. */
@@ -64,8 +68,11 @@ typedef struct axvs_ta_weights {
   const void* w_qkv;  const float* b_qkv;    /* packed [768,256], bias [768] */
   const void* w_pq;   const float* b_pq;     /* proj_q   [256,256]           */
   const void* w_pkv;  const float* b_pkv;    /* proj_kv  [512,256]           */
-  const void* w_pkv_c;                       /* proj_kv packed with rows re-ordered per head pair c = 0..3:
-                                                [k2 rows 64c..64c+63 ; v2 rows 256+64c..256+64c+63] (fused kernel) */
+  /* unit-format copies for the fused kernel (axvs_pack_weight_units, k_major = 0) */
+  const void* w_pq_u;                        /* proj_q                                                       */
+  const void* w_pkv_u;                       /* proj_kv with rows re-ordered per head pair c = 0..3:
+                                                [k2 rows 64c..64c+63 ; v2 rows 256+64c..256+64c+63]          */
+  const void* w_proj_u;                      /* proj                                                         */
   const void* w_proj; const float* b_proj;   /* proj     [256,256]           */
 } axvs_ta_weights;
 
@@ -76,6 +83,8 @@ typedef struct axvs_layer_weights {
   const float* ln1_g; const float* ln1_b;    /* norm1 */
   const void* w_ffn1; const float* b_ffn1;   /* linear1 packed [1024,256] */
   const void* w_ffn2; const float* b_ffn2;   /* linear2 packed [256,1024] */
+  const void* w_ffn1_u;                      /* linear1, unit format, k_major = 0 (fused kernel) */
+  const void* w_ffn2_u;                      /* linear2, unit format, k_major = 1 (fused kernel) */
   const float* ln2_g; const float* ln2_b;    /* norm2 */
   int d_ffn;                                 /* 1024 */
 } axvs_layer_weights;
