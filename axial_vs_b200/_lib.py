@@ -11,7 +11,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaxvs.so")
+LIB_PATH = os.environ.get("AXVS_LIB", os.path.join(_HERE, "libaxvs.so"))   # AXVS_LIB: debug/profiling builds
 
 AXIS_NONE, AXIS_H, AXIS_W = 0, 1, 2
 

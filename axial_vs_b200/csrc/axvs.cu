@@ -428,7 +428,7 @@ int axvs_ln_ffn_fwd(const float* x, float* out, const axvs_layer_weights* w, int
   FfnWorkspace ws = carve_ffn(workspace, (size_t)rows, w->d_ffn);
   if (ws.bytes > workspace_bytes) return fail(AXVS_E_WORKSPACE, "ln_ffn: workspace %zu < required %zu", workspace_bytes, ws.bytes);
   int rc;
-  if (g_fusion >= 2 && w->d_ffn >= 512 && w->w_ffn1_u && w->w_ffn2_u) {
+  if (g_fusion >= 2 && w->d_ffn >= 512 && w->d_ffn <= FF_MAX_DFFN && w->w_ffn1_u && w->w_ffn2_u) {
     DeviceInfo* d;
     if ((rc = device_info(&d))) return rc;
     {
@@ -528,5 +528,16 @@ int axvs_profile_read(double* ms, double* flops, double* bytes, long long* launc
   }
   return AXVS_OK;
 }
+
+#ifdef AXVS_WAIT_PROFILE
+// debug builds only: read (and clear) the wait-cycle counters of the fused kernels
+int axvs_debug_read_waits(unsigned long long* out64) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out64, g_wait_prof, sizeof(unsigned long long) * 64);
+  unsigned long long z[64] = {0};
+  cudaMemcpyToSymbol(g_wait_prof, z, sizeof(z));
+  return AXVS_OK;
+}
+#endif
 
 }  // extern "C"

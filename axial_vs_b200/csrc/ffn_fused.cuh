@@ -19,7 +19,9 @@ constexpr int FF_A_SLOTS = 5;
 constexpr int FF_W_SLOTS = 3;                  // 32 KiB weight units
 constexpr int FF_H_BYTES = 2 * TF_KB;     // 128 x 128 bf16; doubles as the transpose staging of the final epilogue
 constexpr int FF_XCHG_BYTES = 2 * 2 * 128 * 8;
-constexpr int FF_SMEM_BYTES = FF_A_SLOTS * TF_KB + FF_H_BYTES + FF_W_SLOTS * TF_WU + FF_XCHG_BYTES + 1024 + 512;
+constexpr int FF_MAX_DFFN = 1024;
+constexpr int FF_BIAS_BYTES = (FF_MAX_DFFN + 3 * 256) * 4;   // b1 | b2 | ln2 gamma | ln2 beta staged in shared memory
+constexpr int FF_SMEM_BYTES = FF_A_SLOTS * TF_KB + FF_H_BYTES + FF_W_SLOTS * TF_WU + FF_XCHG_BYTES + FF_BIAS_BYTES + 512;
 
 struct FfnParams {
   const uint8_t* s_img;  // LayerNorm1 output, bf16 tile image [tiles][4][16 KiB]
@@ -34,13 +36,17 @@ struct FfnParams {
 };
 
 __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need a 1024 B aligned base (no static smem in this kernel)
   uint8_t* a_ring = smem;
   uint8_t* h_buf = a_ring + FF_A_SLOTS * TF_KB;
   uint8_t* w_ring = h_buf + FF_H_BYTES;
   float2* xchg = reinterpret_cast<float2*>(w_ring + FF_W_SLOTS * TF_WU);   // [2 parity][2 group][128] (sum, sumsq)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + FF_XCHG_BYTES);
+  float* sb1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xchg) + FF_XCHG_BYTES);   // b1 [d_ffn]
+  float* sb2 = sb1 + FF_MAX_DFFN;                                                           // b2 [256]
+  float* sg2 = sb2 + 256;                                                                   // ln2 gamma
+  float* sbe2 = sg2 + 256;                                                                  // ln2 beta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbe2 + 256);
   uint64_t* a_full = bars;                    // [FF_A_SLOTS]
   uint64_t* a_empty = a_full + FF_A_SLOTS;    // [FF_A_SLOTS]
   uint64_t* w_full = a_empty + FF_A_SLOTS;    // [6]
@@ -68,6 +74,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
     fence_barrier_init();
   }
   if (warp == 10) tmem_alloc(tmem_slot, 512);
+  // biases / LayerNorm2 affine -> shared memory (the ~10 KiB of L1 left beside 217 KiB of smem cannot keep them hot)
+  for (int i = threadIdx.x; i < p.d_ffn; i += FF_THREADS) sb1[i] = p.b1[i];
+  for (int i = threadIdx.x; i < 256; i += FF_THREADS) { sb2[i] = p.b2[i]; sg2[i] = p.ln2_g[i]; sbe2[i] = p.ln2_b[i]; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -85,22 +94,22 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
     const int sub = lane >> 3, piece = lane & 7;
     uint8_t* stg = h_buf + warp * 4096;                         // per-warp transpose staging (final epilogue only)
     uint32_t s_cnt = 0, it = 0;
+    AXVS_PROF_DECL(7)
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
       // ---- hidden chunks j = g, g+2, ...: bias + ReLU -> bf16 -> h_buf
       for (int j = g; j < NJ; j += 2) {
-        mbar_wait(&s_full[g], s_cnt & 1);
+        AXVS_PROF_WAIT(0, mbar_wait(&s_full[g], s_cnt & 1))
         ++s_cnt;
         tc_fence_after();
         uint32_t hpk[64];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float v[32];
-          tmem_ld32(t_s + 32 * c, v);
-          tmem_ld_wait();
-          const float4* b4 = reinterpret_cast<const float4*>(p.b1 + j * 128 + c * 32);
+          tmem_ld32(t_s + 32 * c, v); tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(sb1 + j * 128 + c * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 bb = __ldg(b4 + i);
+            const float4 bb = b4[i];
             hpk[c * 16 + 2 * i] = pack_bf16x2(fmaxf(v[4 * i] + bb.x, 0.f), fmaxf(v[4 * i + 1] + bb.y, 0.f));
             hpk[c * 16 + 2 * i + 1] = pack_bf16x2(fmaxf(v[4 * i + 2] + bb.z, 0.f), fmaxf(v[4 * i + 3] + bb.w, 0.f));
           }
@@ -109,55 +118,71 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[g]);                 // TMEM stage drained
         const uint32_t hc = it * NJ + j;                         // global chunk counter: h_buf is free once GEMM 2 of chunk hc-1 retired
-        mbar_wait(h_free, (hc & 1) ^ 1);
+        AXVS_PROF_WAIT(1, mbar_wait(h_free, (hc & 1) ^ 1))
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           uint4 u = make_uint4(hpk[4 * q], hpk[4 * q + 1], hpk[4 * q + 2], hpk[4 * q + 3]);
           *reinterpret_cast<uint4*>(h_buf + (q >> 3) * TF_KB + sw128_offset(row_in_tile, q & 7)) = u;
         }
-        fence_proxy_async_smem();
-        __syncwarp();
+        AXVS_PROF_WAIT(6, fence_proxy_async_smem(); __syncwarp())
         if (lane == 0) mbar_arrive(h_ready);
       }
       // ---- final: t = acc2 + b2 + s, LayerNorm2, store.  Rows are one-per-thread in TMEM; a per-warp transpose through
       // shared memory (h_buf is idle: every GEMM 2 of this tile has retired) makes the global traffic row-segment
       // coalesced.  In the transposed domain lane (sub, piece) owns 4 columns of rows {4*i + sub}.
-      mbar_wait(acc_full, it & 1);
-      tc_fence_after();
+      // The residual (s + b2) is fetched BEFORE waiting for the accumulator so its latency hides behind the last GEMMs.
+      const int row0 = tile * 128 + wq * 32;
       float4 t[4][8];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col = 128 * g + 32 * c + piece * 4;
+        const float4 bb = *reinterpret_cast<const float4*>(sb2 + col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = row0 + i * 4 + sub;
+          float4 sres = (r < p.rows) ? __ldg(reinterpret_cast<const float4*>(p.s32 + (size_t)r * 256 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          t[c][i] = make_float4(sres.x + bb.x, sres.y + bb.y, sres.z + bb.z, sres.w + bb.w);
+        }
+      }
+      AXVS_PROF_WAIT(2, mbar_wait(acc_full, it & 1))
+      tc_fence_after();
+#ifdef AXVS_WAIT_PROFILE
+      const long long tf0_ = clock64();
+#endif
       float ps[8], pq[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) ps[i] = pq[i] = 0.f;
-      const int row0 = tile * 128 + wq * 32;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         {
           float v[32];
           tmem_ld32(t_acc + 32 * c, v);
           tmem_ld_wait();
+          if (c == 3) {                                            // acc2 fully read: release it for the next tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_free);
+          }
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
         }
         __syncwarp();
-        const int col = 128 * g + 32 * c + piece * 4;
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + sub;
-          const int r = row0 + rl;
           const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((piece ^ (rl & 7)) << 4));
-          const float4 sres = (r < p.rows) ? __ldg(reinterpret_cast<const float4*>(p.s32 + (size_t)r * 256 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 tv = make_float4(a.x + bb.x + sres.x, a.y + bb.y + sres.y, a.z + bb.z + sres.z, a.w + bb.w + sres.w);
+          float4 tv = t[c][i];
+          tv.x += a.x; tv.y += a.y; tv.z += a.z; tv.w += a.w;
           t[c][i] = tv;
           ps[i] += tv.x + tv.y + tv.z + tv.w;
           pq[i] += tv.x * tv.x + tv.y * tv.y + tv.z * tv.z + tv.w * tv.w;
         }
         __syncwarp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_free);                      // acc2 columns drained into registers
+#ifdef AXVS_WAIT_PROFILE
+      prof_acc_[4] += clock64() - tf0_;
+#endif
       // row statistics: reduce over the 8 lanes sharing a row, then combine with the other column half (other group)
       float2* xc = xchg + (it & 1) * 256;
 #pragma unroll
@@ -169,28 +194,35 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
         }
         if (piece == 0) xc[g * 128 + wq * 32 + i * 4 + sub] = make_float2(ps[i], pq[i]);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      AXVS_PROF_WAIT(3, asm volatile("bar.sync 1, 256;" ::: "memory"))
+      float mean[8], rstd[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int rl = i * 4 + sub;
-        const float2 other = xc[(g ^ 1) * 128 + wq * 32 + rl];
-        const float mean = (ps[i] + other.x) * (1.f / 256.f);
-        const float var = fmaxf((pq[i] + other.y) * (1.f / 256.f) - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + p.eps);
-        const int r = row0 + rl;
-        if (r < p.rows) {
+        const float2 other = xc[(g ^ 1) * 128 + wq * 32 + i * 4 + sub];
+        mean[i] = (ps[i] + other.x) * (1.f / 256.f);
+        const float var = fmaxf((pq[i] + other.y) * (1.f / 256.f) - mean[i] * mean[i], 0.f);
+        rstd[i] = rsqrtf(var + p.eps);
+      }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int col = 128 * g + 32 * c + piece * 4;
-            const float4 gg = __ldg(reinterpret_cast<const float4*>(p.ln2_g + col)), be = __ldg(reinterpret_cast<const float4*>(p.ln2_b + col));
+      for (int c = 0; c < 4; ++c) {
+        const int col = 128 * g + 32 * c + piece * 4;
+        const float4 gg = *reinterpret_cast<const float4*>(sg2 + col), be = *reinterpret_cast<const float4*>(sbe2 + col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = row0 + i * 4 + sub;
+          if (r < p.rows) {
             const float4 tv = t[c][i];
             *reinterpret_cast<float4*>(p.out + (size_t)r * 256 + col) =
-                make_float4((tv.x - mean) * rstd * gg.x + be.x, (tv.y - mean) * rstd * gg.y + be.y, (tv.z - mean) * rstd * gg.z + be.z,
-                            (tv.w - mean) * rstd * gg.w + be.w);
+                make_float4((tv.x - mean[i]) * rstd[i] * gg.x + be.x, (tv.y - mean[i]) * rstd[i] * gg.y + be.y,
+                            (tv.z - mean[i]) * rstd[i] * gg.z + be.z, (tv.w - mean[i]) * rstd[i] * gg.w + be.w);
           }
         }
       }
+#ifdef AXVS_WAIT_PROFILE
+      prof_acc_[5] += clock64() - tf0_;
+#endif
     }
+    AXVS_PROF_FLUSH(8 + 8 * g, 7, (warp & 3) == 0 && lane == 0)
   } else {
     setmaxnreg_dec<56>();
     if (warp == 8 && lane == 0) {
@@ -208,8 +240,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
     } else if (warp == 9 && lane == 0) {
       // =============================================================== weight producer (32 KiB units)
       uint32_t slot = 0, phase = 0;
+      AXVS_PROF_DECL(1)
       auto push = [&](const uint8_t* img, int unit) {
-        mbar_wait(&w_empty[slot], phase ^ 1);
+        AXVS_PROF_WAIT(0, mbar_wait(&w_empty[slot], phase ^ 1))
         mbar_arrive_expect_tx(&w_full[slot], TF_WU);
         tma_bulk_g2s(w_ring + slot * TF_WU, img + (size_t)unit * TF_WU, TF_WU, &w_full[slot]);
         if (++slot == FF_W_SLOTS) { slot = 0; phase ^= 1; }
@@ -221,13 +254,15 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
           if (j >= 1) { push(p.w2, 2 * (j - 1)); push(p.w2, 2 * (j - 1) + 1); }
         }
       }
+      AXVS_PROF_FLUSH(32, 1, true)
     } else if (warp == 10) {
       // =============================================================== MMA issuer (converged warp, elected lane issues)
       const uint32_t idesc = umma_idesc_bf16(128, 128);
       const uint32_t a_ring_addr = smem_u32(a_ring), h_addr = smem_u32(h_buf), w_ring_addr = smem_u32(w_ring);
       uint32_t a_cnt = 0, w_slot = 0, w_phase = 0, s_cnt0 = 0, s_cnt1 = 0, it = 0;
+      AXVS_PROF_DECL(5)
       auto w_wait = [&]() -> uint32_t {
-        mbar_wait(&w_full[w_slot], w_phase);
+        AXVS_PROF_WAIT(0, mbar_wait(&w_full[w_slot], w_phase))
         tc_fence_after();
         const uint32_t ws = w_slot;
         if (++w_slot == FF_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
@@ -240,7 +275,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
             // GEMM 1, chunk j -> stage j & 1
             const int g = j & 1;
             const uint32_t sc = g ? s_cnt1 : s_cnt0;
-            mbar_wait(&s_empty[g], (sc & 1) ^ 1);
+            AXVS_PROF_WAIT(1, mbar_wait(&s_empty[g], (sc & 1) ^ 1))
             if (g) ++s_cnt1; else ++s_cnt0;
             tc_fence_after();
 #pragma unroll 1
@@ -248,8 +283,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
               const uint32_t ac0 = a_cnt + 2 * kg, ac1 = ac0 + 1;
               const uint32_t s0 = ac0 % FF_A_SLOTS, s1 = ac1 % FF_A_SLOTS;
               if (j == 0) {
-                mbar_wait(&a_full[s0], (ac0 / FF_A_SLOTS) & 1);
-                mbar_wait(&a_full[s1], (ac1 / FF_A_SLOTS) & 1);
+                AXVS_PROF_WAIT(2, mbar_wait(&a_full[s0], (ac0 / FF_A_SLOTS) & 1); mbar_wait(&a_full[s1], (ac1 / FF_A_SLOTS) & 1))
                 tc_fence_after();
               }
               const uint32_t ws = w_wait();
@@ -262,8 +296,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
             // GEMM 2, K-chunk j-1: acc2 += h (128 x 128) * W2[:, 128(j-1) : 128j]^T, one unit per output-column half
             const int jj = j - 1;
             const uint32_t hc = it * NJ + jj;
-            if (jj == 0) mbar_wait(acc_free, (it & 1) ^ 1);      // previous tile's final epilogue has drained acc2
-            mbar_wait(h_ready, hc & 1);
+            if (jj == 0) AXVS_PROF_WAIT(4, mbar_wait(acc_free, (it & 1) ^ 1))   // previous tile's final epilogue has drained acc2
+            AXVS_PROF_WAIT(3, mbar_wait(h_ready, hc & 1))
             tc_fence_after();
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
@@ -275,6 +309,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
         }
         a_cnt += 4;
       }
+      AXVS_PROF_FLUSH(0, 5, lane == 0)
     }
   }
 

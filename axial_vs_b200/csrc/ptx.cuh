@@ -7,6 +7,20 @@
 
 namespace axvs {
 
+// Optional wait-time profile (debug builds with -DAXVS_WAIT_PROFILE): cycles spent in each class of mbarrier wait,
+// accumulated per role and summed over CTAs into g_wait_prof[]; read back with axvs_debug_read_waits().
+#ifdef AXVS_WAIT_PROFILE
+__device__ unsigned long long g_wait_prof[64];
+#define AXVS_PROF_DECL(n) long long prof_acc_[n] = {}; const long long prof_t0_ = clock64();
+#define AXVS_PROF_WAIT(i, stmt) { const long long t_ = clock64(); stmt; prof_acc_[i] += clock64() - t_; }
+#define AXVS_PROF_FLUSH(base, n, cond) if (cond) { for (int i_ = 0; i_ < (n); ++i_) atomicAdd(&g_wait_prof[(base) + i_], (unsigned long long)prof_acc_[i_]); \
+                                                   atomicAdd(&g_wait_prof[(base) + (n)], (unsigned long long)(clock64() - prof_t0_)); }
+#else
+#define AXVS_PROF_DECL(n)
+#define AXVS_PROF_WAIT(i, stmt) stmt;
+#define AXVS_PROF_FLUSH(base, n, cond)
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

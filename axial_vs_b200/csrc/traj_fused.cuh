@@ -25,7 +25,8 @@ constexpr int TF_W_SLOTS = 3;
 constexpr int TF_KB = 16384;                       // one K-block tile: 128 rows x 64 bf16
 constexpr int TF_WU = 32768;                       // one weight unit: 128 rows x 128 K (two K-blocks), one TMA bulk copy
 constexpr int TF_O_BYTES = 4 * TF_KB;              // o operand, 128 x 256 bf16
-constexpr int TF_SMEM_BYTES = TF_O_BYTES + TF_A_SLOTS * TF_KB + TF_W_SLOTS * TF_WU + 1024 + 512;
+constexpr int TF_BIAS_BYTES = 2 * 256 * 4;          // b_pq | b_v2 staged in shared memory
+constexpr int TF_SMEM_BYTES = TF_O_BYTES + TF_A_SLOTS * TF_KB + TF_W_SLOTS * TF_WU + TF_BIAS_BYTES + 512;
 
 struct TrajParams {
   const uint8_t* x_img;    // [F][tiles][4][16 KiB]
@@ -45,12 +46,14 @@ struct TrajParams {
 };
 
 __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need a 1024 B aligned base (no static smem in this kernel)
   uint8_t* o_buf = smem;
   uint8_t* a_ring = smem + TF_O_BYTES;
   uint8_t* w_ring = a_ring + TF_A_SLOTS * TF_KB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + TF_W_SLOTS * TF_WU);
+  float* sb_pq = reinterpret_cast<float*>(w_ring + TF_W_SLOTS * TF_WU);
+  float* sb_v2 = sb_pq + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb_v2 + 256);
   uint64_t* a_full = bars;                       // [TF_A_SLOTS]
   uint64_t* a_empty = a_full + TF_A_SLOTS;       // [TF_A_SLOTS]
   uint64_t* w_full = a_empty + TF_A_SLOTS;       // [TF_W_SLOTS]
@@ -75,6 +78,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
     fence_barrier_init();
   }
   if (warp == 10) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < 256; i += TF_THREADS) { sb_pq[i] = p.b_pq[i]; sb_v2[i] = p.b_v2[i]; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
         tmem_ld32(t_q2 + 32 * j, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (v[i] + __ldg(p.b_pq + 128 * g + 32 * j + i)) * p.scale_log2e;
+        for (int i = 0; i < 32; ++i) v[i] = (v[i] + sb_pq[128 * g + 32 * j + i]) * p.scale_log2e;
         tmem_st32(t_q2 + 32 * j, v);
       }
       tmem_st_wait();
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
         for (int q = 0; q < 4; ++q) {
           float t[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) t[i] = fmaf(o[lh][8 * q + i], inv, __ldg(p.b_v2 + col0 + 8 * q + i));
+          for (int i = 0; i < 8; ++i) t[i] = fmaf(o[lh][8 * q + i], inv, sb_v2[col0 + 8 * q + i]);
           uint4 u;
           u.x = pack_bf16x2(t[0], t[1]); u.y = pack_bf16x2(t[2], t[3]);
           u.z = pack_bf16x2(t[4], t[5]); u.w = pack_bf16x2(t[6], t[7]);
@@ -181,44 +185,55 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
       // ---- output projection item on my stage: out = resid + acc + bproj (my 128 output columns).
       // TMEM rows are one-per-thread; a 4 KiB per-warp transpose through shared memory (o_buf is idle here: the
       // projection MMAs that read it have retired) turns the global accesses into full 128-byte row segments.
-      mbar_wait(&s_full[g], s_cnt & 1);
-      ++s_cnt;
-      tc_fence_after();
+      // resid + bias are fetched BEFORE waiting for the accumulator, so their latency hides behind the projection GEMM.
       {
         const int r = tile * 128 + row_in_tile;
         const int my_orow = (r < p.rows) ? pass_to_canonical(r, p.map_mode, p.dims) : -1;
         uint8_t* stg = o_buf + warp * 4096;
         const int sub = lane >> 3, piece = lane & 7;
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          float v[32];
-          tmem_ld32(t_s + 32 * j, v);
-          tmem_ld_wait();
+        int orow[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          __syncwarp();
+        for (int i = 0; i < 8; ++i) orow[i] = __shfl_sync(0xffffffffu, my_orow, i * 4 + sub);
+        float4 rr[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
           const int col = 128 * g + 32 * j + piece * 4;
           const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b_proj + col));
-          int orow[8];
-          float4 rr[8];
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            orow[it] = __shfl_sync(0xffffffffu, my_orow, it * 4 + sub);
-            rr[it] = (p.resid && orow[it] >= 0) ? __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)orow[it] * 256 + col))
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 8; ++i) {
+            float4 x = (p.resid && orow[i] >= 0) ? __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)orow[i] * 256 + col))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            rr[j][i] = make_float4(x.x + bb.x, x.y + bb.y, x.z + bb.z, x.w + bb.w);
           }
+        }
+        mbar_wait(&s_full[g], s_cnt & 1);
+        ++s_cnt;
+        tc_fence_after();
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rl = it * 4 + sub;
+        for (int j = 0; j < 4; ++j) {
+          {
+            float v[32];
+            tmem_ld32(t_s + 32 * j, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
+          __syncwarp();
+          const int col = 128 * g + 32 * j + piece * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + sub;
             const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((piece ^ (rl & 7)) << 4));
-            if (orow[it] >= 0)
-              *reinterpret_cast<float4*>(p.out + (size_t)orow[it] * 256 + col) =
-                  make_float4(a.x + bb.x + rr[it].x, a.y + bb.y + rr[it].y, a.z + bb.z + rr[it].z, a.w + bb.w + rr[it].w);
+            if (orow[i] >= 0)
+              *reinterpret_cast<float4*>(p.out + (size_t)orow[i] * 256 + col) =
+                  make_float4(a.x + rr[j][i].x, a.y + rr[j][i].y, a.z + rr[j][i].z, a.w + rr[j][i].w);
           }
           __syncwarp();
         }
       }
+      // released only now: the staging area aliases o_buf, which the other group refills once this stage's next
+      // chunks have been drained (see the ordering argument in DESIGN.md)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[g]);
@@ -328,8 +343,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
         for (int u = 0; u < 4; ++u) {
           const int half = u >> 1, kg = u & 1;
           const uint32_t ws = w_wait();
+          // both stages are published only after the LAST read of o_buf: the epilogue reuses o_buf as transpose staging
           umma_unit_elect(tmem + 256 + half * 128, o_addr + (2 * kg) * TF_KB, o_addr + (2 * kg + 1) * TF_KB, w_ring_addr + ws * TF_WU, idesc, kg != 0,
-                          &w_empty[ws], kg == 1 ? &s_full[half] : nullptr, nullptr, nullptr);
+                          &w_empty[ws], u == 3 ? &s_full[0] : nullptr, u == 3 ? &s_full[1] : nullptr, nullptr);
         }
       }
     }

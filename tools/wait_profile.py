@@ -1,0 +1,41 @@
+"""Debug: run one fused kernel on a libaxvs build with -DAXVS_WAIT_PROFILE and print the wait-cycle breakdown.
+usage: AXVS_LIB=axial_vs_b200/libaxvs_prof.so python tools/wait_profile.py [ffn|traj] [clips]"""
+import ctypes, sys, torch
+sys.path.insert(0, ".")
+from axial_vs_b200 import _lib, ops, synth
+which = sys.argv[1] if len(sys.argv) > 1 else "ffn"
+clips = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+lib = _lib.load()
+rows = clips * 2 * 41 * 41
+p = {k: v.cuda() for k, v in synth.axial_layer_params(0).items()}
+pk = ops.pack_layer(p)
+x = torch.randn(rows, 256, device="cuda")
+buf = (ctypes.c_ulonglong * 64)()
+def run():
+    if which == "ffn":
+        return ops.ln_ffn_fwd(x, pk)
+    return ops.traj_attn_fwd(x, x, x, None, x, pk.attn_h, clips, 2, 41, 41, ops.AXIS_H)
+for _ in range(2): run()
+lib.axvs_debug_read_waits(buf)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); run(); e1.record(); torch.cuda.synchronize()
+lib.axvs_debug_read_waits(buf)
+v = list(buf)
+tiles = (rows + 127) // 128
+ctas = min(tiles, 148)
+print(f"{which}: rows {rows} tiles {tiles} time {e0.elapsed_time(e1):.3f} ms")
+def show(name, base, labels):
+    tot = v[base + len(labels)] / ctas
+    print(f"  {name}: total {tot:,.0f} clk/CTA ({tot / (tiles / ctas):,.0f} per tile)")
+    for i, l in enumerate(labels):
+        print(f"      wait {l:10s} {v[base + i] / ctas:12,.0f}  ({100.0 * v[base + i] / max(v[base + len(labels)], 1):5.1f} %)")
+if which == "ffn":
+    show("MMA warp", 0, ["w_full", "s_empty", "a_full", "h_ready", "acc_free"])
+    show("epilogue g0 warp0", 8, ["s_full", "h_free", "acc_full", "bar.sync", "final:chunks", "final:all", "fence"])
+    show("epilogue g1 warp4", 16, ["s_full", "h_free", "acc_full", "bar.sync", "final:chunks", "final:all", "fence"])
+    show("W producer", 32, ["w_empty"])
+else:
+    show("MMA warp", 0, ["w_full", "s_empty", "a_full", "o_ready", "q2_free"])
+    show("epilogue g0 warp0", 8, ["q2_full", "s_full(fr)", "s_full(pj)"])
+    show("epilogue g1 warp4", 16, ["q2_full", "s_full(fr)", "s_full(pj)"])
+    show("W producer", 32, ["w_empty"])
