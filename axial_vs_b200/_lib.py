@@ -18,7 +18,7 @@ AXIS_NONE, AXIS_H, AXIS_W = 0, 1, 2
 
 class TaWeights(Structure):
     _fields_ = [("w_qkv", c_void_p), ("b_qkv", c_void_p), ("w_pq", c_void_p), ("b_pq", c_void_p),
-                ("w_pkv", c_void_p), ("b_pkv", c_void_p), ("w_pq_u", c_void_p), ("w_pkv_u", c_void_p), ("w_proj_u", c_void_p), ("w_proj", c_void_p), ("b_proj", c_void_p)]
+                ("w_pkv", c_void_p), ("b_pkv", c_void_p), ("w_qkv_u", c_void_p), ("w_pq_u", c_void_p), ("w_pkv_u", c_void_p), ("w_proj_u", c_void_p), ("w_proj", c_void_p), ("b_proj", c_void_p)]
 
 
 class LayerWeights(Structure):

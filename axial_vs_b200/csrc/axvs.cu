@@ -11,6 +11,7 @@
 #include "simt.cuh"
 #include "traj_fused.cuh"
 #include "ffn_fused.cuh"
+#include "qkv_fused.cuh"
 
 using namespace axvs;
 
@@ -27,11 +28,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
-                                            "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel"};
-int g_fusion = 2;
+                                            "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
+                                            "spatial_attn_v2_kernel"};
+int g_fusion = 3;
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
 struct Profiler {
@@ -68,6 +70,8 @@ struct DeviceInfo {
   bool gemm_attr = false;
   bool traj_attr = false;
   bool ffn_attr = false;
+  bool qkv_attr = false;
+  bool attn2_attr = false;
 };
 DeviceInfo g_dev[64];
 
@@ -90,6 +94,22 @@ int device_info(DeviceInfo** out) {
     if (cudaFuncSetAttribute(traj_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(traj_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.traj_attr = true;
+  }
+  if (!d.qkv_attr) {
+    if (cudaFuncSetAttribute(qkv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QK_SMEM_BYTES) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(qkv_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    d.qkv_attr = true;
+  }
+  if (!d.attn2_attr) {
+    const int mx = 200 * 1024;
+    if (cudaFuncSetAttribute(spatial_attn_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_v2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_v2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_v2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_v2_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(spatial_attn_v2) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    d.attn2_attr = true;
   }
   if (!d.ffn_attr) {
     if (cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES) != cudaSuccess)
@@ -148,7 +168,7 @@ GemmParams gemm_params(const void* A, int lda, int M, int K, const void* Wp, int
 
 struct TaWorkspace {
   __nv_bfloat16 *a1, *a2, *a3, *qkv, *x, *q2, *kv2, *o;
-  uint8_t *x_img, *xd_img;
+  uint8_t *x_img, *xd_img, *a1_img, *a2_img;
   size_t bytes;
 };
 
@@ -168,6 +188,8 @@ TaWorkspace carve_ta(void* base, size_t rows, int F) {
   const size_t tiles = (rows + 127) / 128;
   w.x_img = reinterpret_cast<uint8_t*>(take(tiles * (size_t)F * 4 * TF_KB));
   w.xd_img = reinterpret_cast<uint8_t*>(take(tiles * 4 * TF_KB));
+  w.a1_img = reinterpret_cast<uint8_t*>(take(tiles * 4 * TF_KB));
+  w.a2_img = reinterpret_cast<uint8_t*>(take(tiles * 4 * TF_KB));
   w.bytes = off;
   return w;
 }
@@ -210,10 +232,10 @@ int blocks_for(long long work_items, int per_block, int sms) {
 
 extern "C" {
 
-int axvs_version(void) { return 103; }
+int axvs_version(void) { return 104; }
 int axvs_set_fusion(int level) {
   const int prev = g_fusion;
-  g_fusion = level < 0 ? 0 : (level > 2 ? 2 : level);
+  g_fusion = level < 0 ? 0 : (level > 3 ? 3 : level);
   return prev;
 }
 const char* axvs_last_error(void) { return g_err; }
@@ -266,7 +288,7 @@ int axvs_spatial_attention(const void* qkv_bf16, void* x_bf16, int num_seq, int 
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;   // 32^-0.5 * log2(e)
   {
     ProfScope ps(KC_ATTN, 4.0 * num_seq * (double)N * N * 256, (double)num_seq * N * (768.0 * 2 + F * 512.0), (cudaStream_t)stream);
-    spatial_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), 768, 0, 256, 512,
+    spatial_attn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), 768, 256, 32,
                                                                 reinterpret_cast<__nv_bfloat16*>(x_bf16), N, n, F, scale_log2e);
   }
   AXVS_CHECK_LAUNCH("spatial_attn_kernel");
@@ -302,6 +324,79 @@ int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, 
   const AxialDims dims{B, T, H, W};
   const int map = axis;   // AXVS_AXIS_* == RowMap values
   const int pk_blocks = blocks_for((long long)rows, 8, d->sms);
+
+  const float kScaleLog2e = 0.17677669529663687f * 1.4426950408889634f;   // 32^-0.5 * log2(e)
+  if (g_fusion >= 3 && k_in == q_in && w->w_qkv_u && w->w_pq_u && w->w_pkv_u && w->w_proj_u && num_seq <= (1 << 27)) {
+    // ---- fused front end: tile-image pack -> TMA-fed q|k|v GEMM (head-major) -> one-shot attention writing tile images
+    const int tiles = (int)((rows + 127) / 128);
+    const bool v_same = (v_in == q_in);
+    const bool one_input = v_same && !pos;
+    {
+      ProfScope ps(KC_PACKIMG, 0, (double)rows * 256 * ((pos ? 8.0 : 4.0) + ((v_same && !one_input) ? 4.0 : 2.0)), st);
+      pack_image_kernel<<<pk_blocks, 256, 0, st>>>(q_in, pos, ws.a1_img, (v_same && !one_input) ? ws.a2_img : nullptr, (int)rows, map, dims);
+    }
+    AXVS_CHECK_LAUNCH("pack_image_kernel");
+    if (!v_same) {
+      ProfScope ps(KC_PACKIMG, 0, (double)rows * 256 * 6.0, st);
+      pack_image_kernel<<<pk_blocks, 256, 0, st>>>(v_in, nullptr, ws.a2_img, nullptr, (int)rows, map, dims);
+      AXVS_CHECK_LAUNCH("pack_image_kernel(v)");
+    }
+    QkvParams qp;
+    memset(&qp, 0, sizeof(qp));
+    qp.a1_img = ws.a1_img; qp.a2_img = one_input ? ws.a1_img : ws.a2_img;
+    qp.w = reinterpret_cast<const uint8_t*>(w->w_qkv_u); qp.bias = w->b_qkv;
+    qp.qkv = ws.qkv; qp.rows = (int)rows; qp.tiles = tiles;
+    {
+      ProfScope ps(KC_QKV, 2.0 * rows * 256.0 * 768.0, (double)rows * (1024.0 + 1536.0), st);
+      qkv_fused_kernel<<<tiles < d->sms ? tiles : d->sms, QK_THREADS, QK_SMEM_BYTES, st>>>(qp);
+    }
+    AXVS_CHECK_LAUNCH("qkv_fused_kernel");
+    const int nt16 = (n + 15) / 16;
+    const size_t att_smem = (size_t)((N + 15) / 16) * 16 * 64 + 4096;
+    if (nt16 <= 11 && att_smem + 4 * 176 * 64 <= 200 * 1024) {
+      ProfScope ps(KC_ATTN2, 4.0 * num_seq * (double)N * N * 256, (double)rows * (1536.0 + (F + 1) * 512.0), st);
+      const dim3 grid((unsigned)num_seq * 8);
+#define AXVS_ATT2(NT) spatial_attn_v2_kernel<NT><<<grid, 128, att_smem + 4 * 16 * NT * 64, st>>>(ws.qkv, rows, ws.x_img, ws.xd_img, tiles, N, n, F, kScaleLog2e)
+      if (nt16 <= 2) AXVS_ATT2(2);
+      else if (nt16 <= 3) AXVS_ATT2(3);
+      else if (nt16 <= 4) AXVS_ATT2(4);
+      else if (nt16 <= 6) AXVS_ATT2(6);
+      else if (nt16 <= 8) AXVS_ATT2(8);
+      else AXVS_ATT2(11);
+#undef AXVS_ATT2
+    } else {
+      // long frames (non-axial "trajectory" layer): online-softmax kernel on the head-major operands, then the image bridge
+      for (int s0 = 0; s0 < num_seq; s0 += 65535) {
+        const int ns = (num_seq - s0) < 65535 ? (num_seq - s0) : 65535;
+        dim3 grid((N + ATT_QT - 1) / ATT_QT, ns, 8);
+        ProfScope ps(KC_ATTN, 4.0 * ns * (double)N * N * 256, (double)ns * N * (768.0 * 2 + F * 512.0), st);
+        spatial_attn_kernel<<<grid, 128, 0, st>>>(ws.qkv + (size_t)s0 * N * 32, 32, (size_t)8 * rows * 32, (size_t)rows * 32,
+                                                  ws.x + (size_t)s0 * N * F * 256, N, n, F, kScaleLog2e);
+      }
+      AXVS_CHECK_LAUNCH("spatial_attn_kernel(head-major)");
+      ProfScope ps(KC_X2IMG, 0, (double)rows * F * 512.0 * 2 + (double)rows * 512.0, st);
+      x_to_image_kernel<<<blocks_for((long long)rows * F * 32, 256, d->sms), 256, 0, st>>>(ws.x, ws.x_img, ws.xd_img, (int)rows, tiles, F, N, n);
+    }
+    AXVS_CHECK_LAUNCH("spatial attention");
+    TrajParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.x_img = ws.x_img; tp.xd_img = ws.xd_img;
+    tp.w_pq = reinterpret_cast<const uint8_t*>(w->w_pq_u);
+    tp.w_pkv = reinterpret_cast<const uint8_t*>(w->w_pkv_u);
+    tp.w_proj = reinterpret_cast<const uint8_t*>(w->w_proj_u);
+    tp.b_pq = w->b_pq; tp.b_v2 = w->b_pkv + 256; tp.b_proj = w->b_proj;
+    tp.resid = resid; tp.out = out;
+    tp.rows = (int)rows; tp.tiles = tiles; tp.F = F;
+    tp.map_mode = map; tp.dims = dims;
+    tp.scale_log2e = kScaleLog2e;
+    {
+      ProfScope ps(KC_TRAJ, 2.0 * rows * 256.0 * 256.0 * (2.0 + 2.0 * F) + 4.0 * rows * F * 256.0,
+                   (double)rows * (512.0 * (F + 1) + 1024.0 + (resid ? 1024.0 : 0.0)), st);
+      traj_fused_kernel<<<tiles < d->sms ? tiles : d->sms, TF_THREADS, TF_SMEM_BYTES, st>>>(tp);
+    }
+    AXVS_CHECK_LAUNCH("traj_fused_kernel");
+    return AXVS_OK;
+  }
 
   // 1. permute + pos add + cast (pass order):  a1 = bf16(q_in + pos), a2 = bf16(v_in), a3 = bf16(k_in + pos)
   // 2. q | k | v projections -> qkv [rows, 768] bf16

@@ -89,6 +89,7 @@ class PackedTA:
     b_pq: torch.Tensor
     w_pkv: torch.Tensor
     b_pkv: torch.Tensor
+    w_qkv_u: torch.Tensor
     w_pq_u: torch.Tensor
     w_pkv_u: torch.Tensor
     w_proj_u: torch.Tensor
@@ -96,8 +97,8 @@ class PackedTA:
     b_proj: torch.Tensor
 
     def tensors(self) -> List[torch.Tensor]:
-        return [self.w_qkv, self.b_qkv, self.w_pq, self.b_pq, self.w_pkv, self.b_pkv, self.w_pq_u, self.w_pkv_u, self.w_proj_u,
-                self.w_proj, self.b_proj]
+        return [self.w_qkv, self.b_qkv, self.w_pq, self.b_pq, self.w_pkv, self.b_pkv, self.w_qkv_u, self.w_pq_u, self.w_pkv_u,
+                self.w_proj_u, self.w_proj, self.b_proj]
 
     def struct(self) -> TaWeights:
         return TaWeights(*[t.data_ptr() for t in self.tensors()])
@@ -122,7 +123,7 @@ def pack_ta(p: Dict[str, torch.Tensor], prefix: str = "") -> PackedTA:
     order = torch.cat([torch.cat([torch.arange(64 * c, 64 * c + 64), torch.arange(256 + 64 * c, 256 + 64 * c + 64)]) for c in range(4)])
     wkv_c = wkv[order.to(wkv.device)].contiguous()
     return PackedTA(pack_weight(wqkv), bqkv, pack_weight(g("proj_q.weight")), g("proj_q.bias"),
-                    pack_weight(wkv), g("proj_kv.bias"), pack_weight_units(g("proj_q.weight")), pack_weight_units(wkv_c),
+                    pack_weight(wkv), g("proj_kv.bias"), pack_weight_units(wqkv), pack_weight_units(g("proj_q.weight")), pack_weight_units(wkv_c),
                     pack_weight_units(g("proj.weight")), pack_weight(g("proj.weight")), g("proj.bias"))
 
 
@@ -156,7 +157,7 @@ class PackedLayer:
 
     @staticmethod
     def from_tensors(ts: Sequence[torch.Tensor], d_ffn: int) -> "PackedLayer":
-        return PackedLayer(PackedTA.from_tensors(ts[0:11]), PackedTA.from_tensors(ts[11:22]), *ts[22:32], d_ffn=d_ffn)
+        return PackedLayer(PackedTA.from_tensors(ts[0:12]), PackedTA.from_tensors(ts[12:24]), *ts[24:34], d_ffn=d_ffn)
 
 
 def pack_layer(p: Dict[str, torch.Tensor], axial: bool = True) -> PackedLayer:

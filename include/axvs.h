@@ -48,6 +48,7 @@ const char* axvs_last_error(void);
  *   0: one kernel per reference op group (tcgen05 GEMMs + attention + SIMT helpers; validation baseline)
  *   1: + proj_q / proj_kv / temporal softmax / proj / residual fused in one tcgen05 kernel
  *   2: + LayerNorm1 / FFN / residual / LayerNorm2 fused in one tcgen05 kernel
+ *   3: + TMA-fed q|k|v projection with head-major output, one-shot per-frame attention writing UMMA tile images
  * Returns the previous level; values outside the range are clamped. */
 int axvs_set_fusion(int level);
 
@@ -69,6 +70,7 @@ typedef struct axvs_ta_weights {
   const void* w_pq;   const float* b_pq;     /* proj_q   [256,256]           */
   const void* w_pkv;  const float* b_pkv;    /* proj_kv  [512,256]           */
   /* unit-format copies for the fused kernel (axvs_pack_weight_units, k_major = 0) */
+  const void* w_qkv_u;                       /* [Wq; Wk; Wv] (768 x 256)                                     */
   const void* w_pq_u;                        /* proj_q                                                       */
   const void* w_pkv_u;                       /* proj_kv with rows re-ordered per head pair c = 0..3:
                                                 [k2 rows 64c..64c+63 ; v2 rows 256+64c..256+64c+63]          */

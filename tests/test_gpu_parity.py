@@ -98,7 +98,7 @@ def test_trajectory_attention_golden(ops, golden, tag):
     assert nerr(out.reshape(Bp, F * n, 256), torch.from_numpy(gz["y"])) < TOL
 
 
-@pytest.mark.parametrize("Bp,F,n", [(5, 2, 41), (2, 5, 30), (1, 10, 33), (1, 2, 200)])
+@pytest.mark.parametrize("Bp,F,n", [(5, 2, 41), (2, 5, 30), (1, 10, 33), (1, 2, 200), (1, 2, 161), (2, 3, 100), (3, 2, 21), (1, 4, 64), (1, 2, 128)])
 def test_trajectory_attention_oracle(ops, O, Bp, F, n):
     p, q, v, pk = _ta_case(ops, O, Bp, F, n, 1000 + Bp + F + n)
     ref, _ = O.trajectory_attention(q, q, v, p, F)
@@ -257,7 +257,7 @@ def test_fusion_levels_agree(ops, O, Bp, F, n):
     res = torch.randn(Bp * F * n, 256, generator=torch.Generator().manual_seed(1)).cuda()
     outs = []
     try:
-        for level in (0, 1, 2):
+        for level in (0, 1, 2, 3):
             ops.set_fusion(level)
             out = ops.traj_attn_fwd(qc, qc, vc, None, res, pk, Bp, F, n, 1, ops.AXIS_NONE)
             torch.cuda.synchronize()
@@ -265,4 +265,4 @@ def test_fusion_levels_agree(ops, O, Bp, F, n):
             outs.append(out)
     finally:
         ops.set_fusion(99)
-    assert nerr(outs[1], outs[0]) < 5e-3
+    assert nerr(outs[1], outs[0]) < 5e-3 and nerr(outs[3], outs[0]) < 5e-3
