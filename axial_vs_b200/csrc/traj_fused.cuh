@@ -95,9 +95,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
     const uint32_t t_s = tmem + lane_base + 256 + 128 * g;       // my accumulator stage
     uint32_t s_cnt = 0;                                          // items consumed on my stage
     uint32_t it = 0;                                             // tile iteration
+    AXVS_PROF_DECL(3)
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
       // ---- finalise q2: (acc + bias) * scale*log2e, written back to TMEM
-      mbar_wait(q2_full, it & 1);
+      AXVS_PROF_WAIT(0, mbar_wait(q2_full, it & 1))
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
       for (int f = 0; f < F; ++f) {
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
-          mbar_wait(&s_full[g], s_cnt & 1);
+          AXVS_PROF_WAIT(1, mbar_wait(&s_full[g], s_cnt & 1))
           ++s_cnt;
           tc_fence_after();
 #pragma unroll
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
             rr[j][i] = make_float4(x.x + bb.x, x.y + bb.y, x.z + bb.z, x.w + bb.w);
           }
         }
-        mbar_wait(&s_full[g], s_cnt & 1);
+        AXVS_PROF_WAIT(2, mbar_wait(&s_full[g], s_cnt & 1))
         ++s_cnt;
         tc_fence_after();
 #pragma unroll
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[g]);
     }
+    AXVS_PROF_FLUSH(8 + 8 * g, 3, (warp & 3) == 0 && lane == 0)
   } else {
     setmaxnreg_dec<56>();
     if (warp == 8 && lane == 0) {
@@ -257,8 +259,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
     } else if (warp == 9 && lane == 0) {
       // =============================================================== weight producer (32 KiB units)
       uint32_t slot = 0, phase = 0;
+      AXVS_PROF_DECL(1)
       auto push = [&](const uint8_t* img, int unit) {
-        mbar_wait(&w_empty[slot], phase ^ 1);
+        AXVS_PROF_WAIT(0, mbar_wait(&w_empty[slot], phase ^ 1))
         mbar_arrive_expect_tx(&w_full[slot], TF_WU);
         tma_bulk_g2s(w_ring + slot * TF_WU, img + (size_t)unit * TF_WU, TF_WU, &w_full[slot]);
         if (++slot == TF_W_SLOTS) { slot = 0; phase ^= 1; }
@@ -275,13 +278,15 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) push(p.w_proj, u);
       }
+      AXVS_PROF_FLUSH(32, 1, true)
     } else if (warp == 10) {
       // =============================================================== MMA issuer (converged warp, elected lane issues)
       const uint32_t idesc = umma_idesc_bf16(128, 128);
       const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring), o_addr = smem_u32(o_buf);
       uint32_t a_cnt = 0, w_slot = 0, w_phase = 0, s_cnt0 = 0, s_cnt1 = 0, it = 0;
+      AXVS_PROF_DECL(5)
       auto w_wait = [&]() -> uint32_t {
-        mbar_wait(&w_full[w_slot], w_phase);
+        AXVS_PROF_WAIT(0, mbar_wait(&w_full[w_slot], w_phase))
         tc_fence_after();
         const uint32_t ws = w_slot;
         if (++w_slot == TF_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
       };
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
         // ---- GEMM 1: q2 accumulators (columns [0,256)); the 4 x_diag K-blocks stay resident for both column halves
-        mbar_wait(q2_free, (it & 1) ^ 1);
+        AXVS_PROF_WAIT(4, mbar_wait(q2_free, (it & 1) ^ 1))
         tc_fence_after();
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) {
@@ -297,8 +302,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
           const uint32_t ac0 = a_cnt + 2 * kg, ac1 = ac0 + 1;
           const uint32_t s0 = ac0 % TF_A_SLOTS, s1 = ac1 % TF_A_SLOTS;
           if (half == 0) {
-            mbar_wait(&a_full[s0], (ac0 / TF_A_SLOTS) & 1);
-            mbar_wait(&a_full[s1], (ac1 / TF_A_SLOTS) & 1);
+            AXVS_PROF_WAIT(2, mbar_wait(&a_full[s0], (ac0 / TF_A_SLOTS) & 1); mbar_wait(&a_full[s1], (ac1 / TF_A_SLOTS) & 1))
             tc_fence_after();
           }
           const uint32_t ws = w_wait();
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
           for (int ci = 0; ci < 4; ++ci) {
             const int g = ci & 1;                               // chunk order 0,2,1,3 -> stage 0,1,0,1
             const uint32_t sc = g ? s_cnt1 : s_cnt0;
-            mbar_wait(&s_empty[g], (sc & 1) ^ 1);
+            AXVS_PROF_WAIT(1, mbar_wait(&s_empty[g], (sc & 1) ^ 1))
             if (g) ++s_cnt1; else ++s_cnt0;
             tc_fence_after();
 #pragma unroll 1
@@ -321,8 +325,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
               const uint32_t ac0 = a_cnt + 2 * kg, ac1 = ac0 + 1;
               const uint32_t s0 = ac0 % TF_A_SLOTS, s1 = ac1 % TF_A_SLOTS;
               if (ci == 0) {
-                mbar_wait(&a_full[s0], (ac0 / TF_A_SLOTS) & 1);
-                mbar_wait(&a_full[s1], (ac1 / TF_A_SLOTS) & 1);
+                AXVS_PROF_WAIT(2, mbar_wait(&a_full[s0], (ac0 / TF_A_SLOTS) & 1); mbar_wait(&a_full[s1], (ac1 / TF_A_SLOTS) & 1))
                 tc_fence_after();
               }
               const uint32_t ws = w_wait();
@@ -333,10 +336,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
           a_cnt += 4;
         }
         // ---- GEMM 3: output projection, A = o (written by the epilogue), accumulators = both stages
-        mbar_wait(o_ready, it & 1);
-        mbar_wait(&s_empty[0], (s_cnt0 & 1) ^ 1);
+        AXVS_PROF_WAIT(3, mbar_wait(o_ready, it & 1))
+        AXVS_PROF_WAIT(1, mbar_wait(&s_empty[0], (s_cnt0 & 1) ^ 1))
         ++s_cnt0;
-        mbar_wait(&s_empty[1], (s_cnt1 & 1) ^ 1);
+        AXVS_PROF_WAIT(1, mbar_wait(&s_empty[1], (s_cnt1 & 1) ^ 1))
         ++s_cnt1;
         tc_fence_after();
 #pragma unroll 1
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
                           &w_empty[ws], u == 3 ? &s_full[0] : nullptr, u == 3 ? &s_full[1] : nullptr, nullptr);
         }
       }
+      AXVS_PROF_FLUSH(0, 5, lane == 0)
     }
   }
 
