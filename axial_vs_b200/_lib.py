@@ -41,6 +41,8 @@ SIGNATURES = {
     "axvs_traj_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "axvs_traj_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(TaWeights), c_int, c_int, c_int,
                                    c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "axvs_traj_attn_maps": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(TaWeights), c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p, c_size_t, c_void_p]),
     "axvs_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
     "axvs_ffn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "axvs_ln_ffn_fwd": (c_int, [c_void_p, c_void_p, POINTER(LayerWeights), c_int, c_void_p, c_size_t, c_void_p]),

@@ -494,6 +494,42 @@ int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, 
   return AXVS_OK;
 }
 
+int axvs_traj_attn_maps(const float* q_in, const float* k_in, const float* pos, float* maps, const axvs_ta_weights* w, int B, int T, int H,
+                        int W, int axis, void* workspace, size_t workspace_bytes, axvs_stream_t stream) {
+  if (!q_in || !k_in || !maps || !w || !workspace) return fail(AXVS_E_INVALID, "traj_attn_maps: null pointer");
+  if (k_in != q_in) return fail(AXVS_E_UNSUPPORTED, "traj_attn_maps: key must be the query tensor (every reference call site)");
+  if (!w->w_qkv_u) return fail(AXVS_E_INVALID, "traj_attn_maps: w_qkv_u required");
+  int rc = check_dims(B, T, H, W);
+  if (rc) return rc;
+  const size_t rows = (size_t)B * T * H * W;
+  const int F = T;
+  int num_seq, n;
+  if (axis == AXVS_AXIS_H) { num_seq = B * W; n = H; }
+  else if (axis == AXVS_AXIS_W) { num_seq = B * H; n = W; }
+  else if (axis == AXVS_AXIS_NONE) { num_seq = B; n = H * W; }
+  else return fail(AXVS_E_INVALID, "traj_attn_maps: bad axis %d", axis);
+  const int N = F * n;
+  TaWorkspace ws = carve_ta(workspace, rows, F);
+  if (ws.bytes > workspace_bytes) return fail(AXVS_E_WORKSPACE, "traj_attn_maps: workspace %zu < required %zu", workspace_bytes, ws.bytes);
+  DeviceInfo* d;
+  if ((rc = device_info(&d))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const AxialDims dims{B, T, H, W};
+  const int tiles = (int)((rows + 127) / 128);
+  pack_image_kernel<<<blocks_for((long long)rows, 8, d->sms), 256, 0, st>>>(q_in, pos, ws.a1_img, nullptr, (int)rows, axis, dims);
+  AXVS_CHECK_LAUNCH("pack_image_kernel");
+  QkvParams qp;
+  memset(&qp, 0, sizeof(qp));
+  qp.a1_img = ws.a1_img; qp.a2_img = ws.a1_img;
+  qp.w = reinterpret_cast<const uint8_t*>(w->w_qkv_u); qp.bias = w->b_qkv;
+  qp.qkv = ws.qkv; qp.rows = (int)rows; qp.tiles = tiles;
+  qkv_fused_kernel<<<tiles < d->sms ? tiles : d->sms, QK_THREADS, QK_SMEM_BYTES, st>>>(qp);
+  AXVS_CHECK_LAUNCH("qkv_fused_kernel");
+  attn_maps_kernel<<<blocks_for((long long)num_seq * 8 * N * F, 8, d->sms), 256, 0, st>>>(ws.qkv, rows, maps, num_seq, N, n, F, 0.17677669529663687f);
+  AXVS_CHECK_LAUNCH("attn_maps_kernel");
+  return AXVS_OK;
+}
+
 int axvs_layernorm(const float* x, const float* gamma, const float* beta, float* y32, void* y16_bf16, int rows, float eps,
                    axvs_stream_t stream) {
   if (!x || !gamma || !beta || (!y32 && !y16_bf16)) return fail(AXVS_E_INVALID, "layernorm: null pointer");

@@ -134,6 +134,38 @@ __global__ void temporal_attn_kernel(const __nv_bfloat16* __restrict__ q2, const
   }
 }
 
+// Slow path for the attention visualiser (Vk/maxtron_deeplab/maxtron_wc_model.py:598-611): materialise the per-frame
+// softmax maps  maps[(seq*8 + head), q, f, i] = softmax_i(scale * Q[q] . K[f*n + i])  in fp32 (the reference's
+// `space_attn`, WC/temporal_attention.py:54,76).  One warp per (seq, head, q, f); qkv head-major bf16.
+__global__ void attn_maps_kernel(const __nv_bfloat16* __restrict__ qkv, size_t rows_total, float* __restrict__ maps, int num_seq, int N, int n,
+                                 int F, float scale) {
+  const int lane = threadIdx.x & 31;
+  const size_t total = (size_t)num_seq * 8 * N * F;
+  for (size_t w = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += (size_t)gridDim.x * (blockDim.x >> 5)) {
+    const int f = (int)(w % F);
+    size_t r = w / F;
+    const int q = (int)(r % N); r /= N;
+    const int head = (int)(r % 8);
+    const int seq = (int)(r / 8);
+    const __nv_bfloat16* qp = qkv + ((size_t)head * rows_total + (size_t)seq * N + q) * 32;
+    const __nv_bfloat16* kp = qkv + ((size_t)(8 + head) * rows_total + (size_t)seq * N + (size_t)f * n) * 32;
+    const float qv = __bfloat162float(qp[lane]);
+    float* out = maps + w * n;
+    float mx = -INFINITY;
+    for (int i = 0; i < n; ++i) {                     // logits: lane = head-dim element, reduce over the 32 lanes
+      float s = warp_sum(qv * __bfloat162float(kp[(size_t)i * 32 + lane])) * scale;
+      if (lane == 0) out[i] = s;
+      mx = fmaxf(mx, s);
+    }
+    __syncwarp();
+    float sum = 0.f;
+    for (int i = lane; i < n; i += 32) { const float e = __expf(out[i] - mx); out[i] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int i = lane; i < n; i += 32) out[i] *= inv;
+  }
+}
+
 // pos[b,t,h,w,c] = cat(sine(y), sine(x))[c] + sine(z)[c] + level_embed[c]      (channels-last, fp32)
 // Reference: PositionEmbeddingSine3D.forward (normalize=True, scale=2pi, temperature 1e4), WC/pos_embeddings.py:86-130,
 // plus the level embedding add, WC/msdeformattn.py:112-115.  One thread per (t,h,w, channel pair).

@@ -84,7 +84,9 @@ class TrajectoryAttention(nn.Module):
         out = ops.traj_attn_fwd(q, k, v, None, None, self.packed(query.device), Bp, F, n, 1, ops.AXIS_NONE)
         maps = None
         if self.return_attn_maps:
-            maps = ops.spatial_attention_maps(q, k, self.packed(query.device), Bp, F, n)
+            if key is not query:
+                raise NotImplementedError("return_attn_maps requires key is query (all reference call sites)")
+            maps = ops.traj_attn_maps(q, None, self.packed(query.device), Bp, F, n, 1, ops.AXIS_NONE)
         return out.view(Bp, N, C).to(query.dtype), maps
 
 
@@ -156,9 +158,9 @@ class TemporalAxialTrajectoryAttentionLayer(_LayerBase):
         p = pos.contiguous().float().view(B * T * H * W, C)
         pk = self.packed(src.device)
         s1 = ops.traj_attn_fwd(s0, s0, s0, p, s0, pk.attn_h, B, T, H, W, ops.AXIS_H)
-        hmap = ops.spatial_attention_maps_axial(s0, p, pk.attn_h, B, T, H, W, ops.AXIS_H)
+        hmap = ops.traj_attn_maps(s0, p, pk.attn_h, B, T, H, W, ops.AXIS_H)
         s2 = ops.traj_attn_fwd(s1, s1, s1, p, s1, pk.attn_w, B, T, H, W, ops.AXIS_W)
-        wmap = ops.spatial_attention_maps_axial(s1, p, pk.attn_w, B, T, H, W, ops.AXIS_W)
+        wmap = ops.traj_attn_maps(s1, p, pk.attn_w, B, T, H, W, ops.AXIS_W)
         out = ops.ln_ffn_fwd(s2, pk)
         return out.view(B * T, H * W, C).to(src.dtype), hmap, wmap
 
@@ -182,3 +184,11 @@ class TemporalEncoder(nn.Module):
         for layer in self.temporal_layers:
             src, height_traj_attn, width_traj_attn = layer(src, pos)
         return src, height_traj_attn, width_traj_attn
+
+    def set_return_attn_maps(self, flag: bool = True) -> "TemporalEncoder":
+        """Enable the slow path that materialises the attention maps of the LAST layer (what the reference returns)."""
+        layers = list(self.temporal_layers)
+        for i, layer in enumerate(layers):
+            if hasattr(layer, "return_attn_maps"):
+                layer.return_attn_maps = bool(flag) and i == len(layers) - 1
+        return self

@@ -227,6 +227,26 @@ def traj_attn_fwd(q_in: torch.Tensor, k_in: torch.Tensor, v_in: torch.Tensor, po
     return out
 
 
+def traj_attn_maps(q_in: torch.Tensor, pos: Optional[torch.Tensor], w: PackedTA, B: int, T: int, H: int, W: int, axis: int) -> torch.Tensor:
+    """The reference's `space_attn` maps: fp32 [(num_seq*8), N, F, n] (slow path for the attention visualiser)."""
+    rows = B * T * H * W
+    _check(q_in, "q_in", torch.float32)
+    if pos is not None:
+        _check(pos, "pos", torch.float32)
+    num_seq, n = {AXIS_H: (B * W, H), AXIS_W: (B * H, W), AXIS_NONE: (B, H * W)}[axis]
+    N = T * n
+    maps = torch.empty(num_seq * HEADS, N, T, n, dtype=torch.float32, device=q_in.device)
+    lib = _lib.load()
+    nbytes = lib.axvs_traj_attn_workspace_bytes(B, T, H, W)
+    with torch.cuda.device(q_in.device):
+        ws = workspace(nbytes, q_in.device)
+        st = w.struct()
+        rc = lib.axvs_traj_attn_maps(q_in.data_ptr(), q_in.data_ptr(), _ptr(pos), maps.data_ptr(), ctypes.byref(st), B, T, H, W, axis,
+                                     ws.data_ptr(), ws.numel(), _stream(q_in.device))
+    _lib.check(rc, "axvs_traj_attn_maps")
+    return maps
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     _check(x, "x", torch.float32)
     rows = x.numel() // C

@@ -116,6 +116,12 @@ int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, 
                        float* out, const axvs_ta_weights* w, int B, int T, int H, int W, int axis,
                        void* workspace, size_t workspace_bytes, axvs_stream_t stream);
 
+/* Attention-map side output of TrajectoryAttention (the `space_attn` return value, WC/temporal_attention.py:54,76; consumed
+ * only by the visualiser, Vk/maxtron_deeplab/maxtron_wc_model.py:598-611).  Same inputs / axis convention as
+ * axvs_traj_attn_fwd; maps fp32 [(num_seq * 8), N, F, n] with head the fast factor of the fused dim.  Slow path. */
+int axvs_traj_attn_maps(const float* q_in, const float* k_in, const float* pos, float* maps, const axvs_ta_weights* w,
+                        int B, int T, int H, int W, int axis, void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+
 /* y = LayerNorm(x) over C = 256 (nn.LayerNorm, biased variance).  y32 and/or y16 may be NULL. */
 int axvs_layernorm(const float* x, const float* gamma, const float* beta, float* y32, void* y16_bf16, int rows,
                    float eps, axvs_stream_t stream);

@@ -266,3 +266,105 @@ def test_fusion_levels_agree(ops, O, Bp, F, n):
     finally:
         ops.set_fusion(99)
     assert nerr(outs[1], outs[0]) < 5e-3 and nerr(outs[3], outs[0]) < 5e-3
+
+
+# --------------------------------------------------------------------------------------------- maps, pos module, TL, cross-clip
+def test_attention_maps_golden(O, golden):
+    """return_attn_maps=True reproduces the reference's `space_attn` tuple members (layout [(B' h), N, F, n], fp32)."""
+    gz = golden("axial_layer_a")
+    B, T, H, W, seed = (int(gz[k]) for k in "B T H W seed".split())
+    p = synth.axial_layer_params(seed)
+    layer = _layer(p)
+    layer.return_attn_maps = True
+    src = synth.randn(seed + 100, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 200)[0])
+    with torch.no_grad():
+        out, hm, wm = layer(src.cuda(), pos.cuda())
+    assert nerr(out, torch.from_numpy(gz["out"])) < TOL
+    assert tuple(hm.shape) == gz["hmap"].shape and tuple(wm.shape) == gz["wmap"].shape
+    assert (hm.cpu() - torch.from_numpy(gz["hmap"])).abs().max().item() < 2e-2      # probabilities, absolute tolerance
+    assert (wm.cpu() - torch.from_numpy(gz["wmap"])).abs().max().item() < 2e-2
+    assert (hm.sum(-1) - 1).abs().max().item() < 1e-4
+
+
+def test_pos_module_matches_reference_layout(golden):
+    from axial_vs_b200.pos import PositionEmbeddingSine3D
+    gz = golden("pos3d_b")
+    B, T, H, W = (int(gz[k]) for k in "B T H W".split())
+    pe = PositionEmbeddingSine3D(128, normalize=True)
+    out = pe(torch.zeros(B, T, 256, H, W, device="cuda"), fmt="btchw")
+    assert tuple(out.shape) == (B, T, 256, H, W)
+    assert (out.permute(0, 1, 3, 4, 2).cpu() - torch.from_numpy(gz["table"])).abs().max().item() < 2e-5
+
+
+def test_tube_link_wrappers(O):
+    """TL flavour: features only, gamma skip (TL msdeformattn_pixel_decoder.py:620-627)."""
+    from axial_vs_b200 import tube_link
+    B, T, H, W, seed = 1, 5, 6, 8, 321
+    p = synth.encoder_params(seed, 1)
+    enc = tube_link.TemporalEncoder(256, 1024, 0.0, 0.0, "relu", 8, 1).eval()
+    enc.load_state_dict(p, strict=True)
+    enc.cuda()
+    f = synth.randn(seed + 1, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 2)[0])
+    gamma = torch.full((256,), 0.5)
+    ref, _, _ = O.temporal_encoder(f, pos, O.split_encoder_params(p))
+    ref = f + gamma * ref
+    with torch.no_grad():
+        out = tube_link.temporal_branch([f.cuda(), f.cuda()], [pos.cuda()], enc, gamma.cuda(), 1)
+    assert nerr(out[0], ref) < TOL and torch.equal(out[1].cpu(), f)
+
+
+def test_cross_clip_attention_golden(golden):
+    from axial_vs_b200 import cross_clip
+    gz = golden("cc_ta")
+    b, Q, T, seed = (int(gz[k]) for k in "b Q T seed".split())
+    p = {}
+    synth.traj_attn_params(torch.Generator().manual_seed(seed), "", 256, p, fused_qkv=True)
+    m = cross_clip.TrajectoryAttention(256, 8, 0.0).eval()
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    x = synth.randn(seed + 100, b, T * Q, 256)
+    with torch.no_grad():
+        y = m(x.cuda(), seq_len=Q, num_frames=T)
+    assert nerr(y, torch.from_numpy(gz["y"])) < TOL
+
+
+def test_cross_clip_layer_oracle(O):
+    """cfg3-shaped: Q = 128 queries per clip, 8 clips (a per-GPU shard of the 64-clip video)."""
+    from axial_vs_b200 import cross_clip
+    b, Q, T, seed = 1, 128, 8, 654
+    p = {}
+    g = torch.Generator().manual_seed(seed)
+    synth.traj_attn_params(g, "self_attn.", 256, p, fused_qkv=True)
+    p["norm.weight"] = 1 + 0.1 * torch.randn(256, generator=g)
+    p["norm.bias"] = 0.1 * torch.randn(256, generator=g)
+    m = cross_clip.TrajectoryAttentionLayer(256, 8).eval()
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    x = synth.randn(seed + 1, b, T * Q, 256)
+    ref = O.cc_attention_layer(x, p, Q, T)
+    with torch.no_grad():
+        y = m(x.cuda(), Q, T)
+    assert nerr(y, ref) < TOL
+
+
+def test_level_plumbing(O):
+    from axial_vs_b200 import modules, within_clip
+    from axial_vs_b200.pos import PositionEmbeddingSine3D
+    B, T, seed = 1, 2, 77
+    shapes = [(5, 6), (9, 11), (17, 21)]
+    p = synth.encoder_params(seed, 1)
+    enc = modules.TemporalEncoder(256, 1024, 0.0, 0.0, "relu", 8, "axial-trajectory", 1).eval()
+    enc.load_state_dict(p, strict=True)
+    enc.cuda()
+    le = synth.level_embed(seed + 1)
+    mem = synth.randn(seed + 2, B * T, sum(h * w for h, w in shapes), 256)
+    pe = PositionEmbeddingSine3D(128, normalize=True)
+    pos = within_clip.level_positions(pe, le.cuda(), B, T, shapes[:2], "cuda")
+    with torch.no_grad():
+        out, _, _ = within_clip.run_temporal_levels(enc, mem.cuda(), shapes, pos, 2)
+    parts = list(torch.split(mem, [h * w for h, w in shapes], dim=1))
+    for i in range(2):
+        parts[i], _, _ = O.temporal_encoder(parts[i].contiguous(), O.level_pos3d(B, T, *shapes[i], le[i]), O.split_encoder_params(p))
+    assert nerr(out, torch.cat(parts, 1)) < TOL
