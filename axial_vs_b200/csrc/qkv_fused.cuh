@@ -15,10 +15,11 @@
 namespace axvs {
 
 constexpr int QK_THREADS = 384;
-constexpr int QK_A_SLOTS = 7;
+constexpr int QK_A_SLOTS = 6;
 constexpr int QK_W_SLOTS = 3;
 constexpr int QK_BIAS_BYTES = 768 * 4;
-constexpr int QK_SMEM_BYTES = QK_A_SLOTS * TF_KB + QK_W_SLOTS * TF_WU + QK_BIAS_BYTES + 512;
+constexpr int QK_STAGE_BYTES = 8 * 2048;     // per-warp 32 rows x 64 B transpose tile for the head-major stores
+constexpr int QK_SMEM_BYTES = QK_A_SLOTS * TF_KB + QK_W_SLOTS * TF_WU + QK_STAGE_BYTES + QK_BIAS_BYTES + 512;
 
 struct QkvParams {
   const uint8_t* a1_img;   // [tiles][4][16 KiB]   q/k input (+pos)
@@ -34,7 +35,8 @@ __global__ void __launch_bounds__(QK_THREADS, 1) qkv_fused_kernel(const QkvParam
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* a_ring = smem;
   uint8_t* w_ring = a_ring + QK_A_SLOTS * TF_KB;
-  float* sbias = reinterpret_cast<float*>(w_ring + QK_W_SLOTS * TF_WU);
+  uint8_t* stage_all = w_ring + QK_W_SLOTS * TF_WU;
+  float* sbias = reinterpret_cast<float*>(stage_all + QK_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 768);
   uint64_t* a_full = bars;                      // [QK_A_SLOTS]
   uint64_t* a_empty = a_full + QK_A_SLOTS;
@@ -63,16 +65,16 @@ __global__ void __launch_bounds__(QK_THREADS, 1) qkv_fused_kernel(const QkvParam
   if (warp < 8) {
     // =============================================================== epilogue: group g drains chunks rt with rt & 1 == g
     const int g = warp >> 2;
-    const int row_in_tile = (warp & 3) * 32 + lane;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint8_t* stg = stage_all + warp * 2048;
     uint32_t cnt = 0;                                          // chunks consumed by this group (stage = 2 * (cnt & 1) + g)
+    AXVS_PROF_DECL(1)
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-      const int r = tile * 128 + row_in_tile;
-      const bool valid = r < p.rows;
+      const int row0 = tile * 128 + (warp & 3) * 32;           // first row of this warp
 #pragma unroll 1
       for (int rt = g; rt < 6; rt += 2, ++cnt) {
         const int stage = 2 * (cnt & 1) + g;
-        mbar_wait(&s_full[stage], (cnt >> 1) & 1);
+        AXVS_PROF_WAIT(0, mbar_wait(&s_full[stage], (cnt >> 1) & 1))
         tc_fence_after();
         const uint32_t t_s = tmem + lane_base + stage * 128;
 #pragma unroll
@@ -85,10 +87,10 @@ __global__ void __launch_bounds__(QK_THREADS, 1) qkv_fused_kernel(const QkvParam
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[stage]);
           }
-          if (valid) {
+          // bias + bf16, then a 2 KiB per-warp transpose so every store instruction writes 512 contiguous bytes
+          // (one row per thread would emit 16-byte pieces at a 64-byte stride: 32 half-filled sectors per instruction)
+          {
             const float4* b4 = reinterpret_cast<const float4*>(sbias + rt * 128 + c * 32);
-            const int which = rt >> 1, head = (rt & 1) * 4 + c;
-            uint4* dst = reinterpret_cast<uint4*>(p.qkv + ((size_t)(which * 8 + head) * p.rows + r) * 32);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 b0 = b4[2 * q], b1 = b4[2 * q + 1];
@@ -97,12 +99,25 @@ __global__ void __launch_bounds__(QK_THREADS, 1) qkv_fused_kernel(const QkvParam
               u.y = pack_bf16x2(v[8 * q + 2] + b0.z, v[8 * q + 3] + b0.w);
               u.z = pack_bf16x2(v[8 * q + 4] + b1.x, v[8 * q + 5] + b1.y);
               u.w = pack_bf16x2(v[8 * q + 6] + b1.z, v[8 * q + 7] + b1.w);
-              dst[q] = u;
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = u;
             }
           }
+          __syncwarp();
+          {
+            const int which = rt >> 1, head = (rt & 1) * 4 + c;
+            uint8_t* dst = reinterpret_cast<uint8_t*>(p.qkv + ((size_t)(which * 8 + head) * p.rows + row0) * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rl = 8 * i + (lane >> 2), piece = lane & 3;
+              const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((piece ^ ((rl >> 1) & 3)) << 4));
+              if (row0 + rl < p.rows) *reinterpret_cast<uint4*>(dst + rl * 64 + piece * 16) = u;
+            }
+          }
+          __syncwarp();
         }
       }
     }
+    AXVS_PROF_FLUSH(44 + 2 * g, 1, (warp & 3) == 0 && lane == 0)
   } else if (warp == 8 && lane == 0) {
     // =============================================================== A-tile producer: A1 kb0..3, then A2 kb0..3
     uint32_t cnt = 0;
@@ -133,13 +148,14 @@ __global__ void __launch_bounds__(QK_THREADS, 1) qkv_fused_kernel(const QkvParam
     const uint32_t idesc = umma_idesc_bf16(128, 128);
     const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring);
     uint32_t a_cnt = 0, w_slot = 0, w_phase = 0, ccnt = 0;     // ccnt: chunks issued (stage = 2 * ((ccnt >> 1) & 1) + (ccnt & 1))
+    AXVS_PROF_DECL(3)
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
 #pragma unroll 1
       for (int rt = 0; rt < 6; ++rt, ++ccnt) {
         const int g = rt & 1;
         const uint32_t gc = ccnt >> 1;                         // chunks already issued to group g (6 per tile: even count)
         const int stage = 2 * (gc & 1) + g;
-        mbar_wait(&s_empty[stage], ((gc >> 1) & 1) ^ 1);
+        AXVS_PROF_WAIT(1, mbar_wait(&s_empty[stage], ((gc >> 1) & 1) ^ 1))
         tc_fence_after();
         const uint32_t abase = a_cnt + (rt < 4 ? 0 : 4);       // A1 items for q/k chunks, A2 items for v chunks
 #pragma unroll 1
@@ -147,11 +163,10 @@ __global__ void __launch_bounds__(QK_THREADS, 1) qkv_fused_kernel(const QkvParam
           const uint32_t ac0 = abase + 2 * kg, ac1 = ac0 + 1;
           const uint32_t s0 = ac0 % QK_A_SLOTS, s1 = ac1 % QK_A_SLOTS;
           if (rt == 0 || rt == 4) {
-            mbar_wait(&a_full[s0], (ac0 / QK_A_SLOTS) & 1);
-            mbar_wait(&a_full[s1], (ac1 / QK_A_SLOTS) & 1);
+            AXVS_PROF_WAIT(2, mbar_wait(&a_full[s0], (ac0 / QK_A_SLOTS) & 1); mbar_wait(&a_full[s1], (ac1 / QK_A_SLOTS) & 1))
             tc_fence_after();
           }
-          mbar_wait(&w_full[w_slot], w_phase);
+          AXVS_PROF_WAIT(0, mbar_wait(&w_full[w_slot], w_phase))
           tc_fence_after();
           const uint32_t ws = w_slot;
           if (++w_slot == QK_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
@@ -162,6 +177,7 @@ __global__ void __launch_bounds__(QK_THREADS, 1) qkv_fused_kernel(const QkvParam
       }
       a_cnt += 8;
     }
+    AXVS_PROF_FLUSH(40, 3, lane == 0)
   }
 
   tc_fence_before();
@@ -203,3 +219,4 @@ __global__ void pack_image_kernel(const float* __restrict__ src, const float* __
 }
 
 }  // namespace axvs
+static_assert(axvs::QK_SMEM_BYTES <= 232448, "qkv_fused_kernel exceeds the 227 KiB shared-memory limit");

@@ -14,6 +14,9 @@ buf = (ctypes.c_ulonglong * 64)()
 def run():
     if which == "ffn":
         return ops.ln_ffn_fwd(x, pk)
+    if which == "qkv":
+        ops.set_fusion(3)
+        return ops.traj_attn_fwd(x, x, x, None, x, pk.attn_h, clips, 2, 41, 41, ops.AXIS_H)
     return ops.traj_attn_fwd(x, x, x, None, x, pk.attn_h, clips, 2, 41, 41, ops.AXIS_H)
 for _ in range(2): run()
 lib.axvs_debug_read_waits(buf)
@@ -34,6 +37,10 @@ if which == "ffn":
     show("epilogue g0 warp0", 8, ["s_full", "h_free", "acc_full", "bar.sync", "final:chunks", "final:all", "fence"])
     show("epilogue g1 warp4", 16, ["s_full", "h_free", "acc_full", "bar.sync", "final:chunks", "final:all", "fence"])
     show("W producer", 32, ["w_empty"])
+elif which == "qkv":
+    show("qkv MMA warp", 40, ["w_full", "s_empty", "a_full"])
+    show("qkv epilogue g0", 44, ["s_full"])
+    show("qkv epilogue g1", 46, ["s_full"])
 else:
     show("MMA warp", 0, ["w_full", "s_empty", "a_full", "o_ready", "q2_free"])
     show("epilogue g0 warp0", 8, ["q2_full", "s_full(fr)", "s_full(pj)"])
