@@ -300,9 +300,14 @@ size_t axvs_traj_attn_workspace_bytes(int B, int T, int H, int W) {
   return carve_ta(nullptr, (size_t)B * T * H * W, T).bytes;
 }
 
-int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, const float* pos, const float* resid, float* out,
-                       const axvs_ta_weights* w, int B, int T, int H, int W, int axis, void* workspace, size_t workspace_bytes,
-                       axvs_stream_t stream) {
+}  // extern "C"
+
+namespace {
+// ln_g/ln_b/ln_img != null: the output epilogue additionally applies LayerNorm (norm1 of the layer) and emits the FFN's
+// bf16 tile image; only available on the fully fused path (returns AXVS_E_UNSUPPORTED otherwise).
+int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, const float* pos, const float* resid, float* out,
+                   const axvs_ta_weights* w, int B, int T, int H, int W, int axis, void* workspace, size_t workspace_bytes,
+                   axvs_stream_t stream, const float* ln_g, const float* ln_b, uint8_t* ln_img) {
   if (!q_in || !k_in || !v_in || !out || !w || !workspace) return fail(AXVS_E_INVALID, "traj_attn: null pointer");
   if (!w->w_qkv || !w->w_pq || !w->w_pkv || !w->w_proj) return fail(AXVS_E_INVALID, "traj_attn: null weight pointer");
   int rc = check_dims(B, T, H, W);
@@ -389,6 +394,7 @@ int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, 
     tp.rows = (int)rows; tp.tiles = tiles; tp.F = F;
     tp.map_mode = map; tp.dims = dims;
     tp.scale_log2e = kScaleLog2e;
+    tp.ln_g = ln_g; tp.ln_b = ln_b; tp.ln_img = ln_img; tp.ln_eps = 1e-5f;
     {
       ProfScope ps(KC_TRAJ, 2.0 * rows * 256.0 * 256.0 * (2.0 + 2.0 * F) + 4.0 * rows * F * 256.0,
                    (double)rows * (512.0 * (F + 1) + 1024.0 + (resid ? 1024.0 : 0.0)), st);
@@ -398,6 +404,7 @@ int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, 
     return AXVS_OK;
   }
 
+  if (ln_g) return fail(AXVS_E_UNSUPPORTED, "traj_attn: fused LayerNorm epilogue needs fusion level 3 and unit-format weights");
   // 1. permute + pos add + cast (pass order):  a1 = bf16(q_in + pos), a2 = bf16(v_in), a3 = bf16(k_in + pos)
   // 2. q | k | v projections -> qkv [rows, 768] bf16
   const bool same_qk = (k_in == q_in);
@@ -494,6 +501,35 @@ int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, 
   return AXVS_OK;
 }
 
+// fused FFN tail given LayerNorm1 output as fp32 rows (s32) + bf16 tile image (s_img)
+int ffn_fused_launch(const uint8_t* s_img, const float* s32, float* out, const axvs_layer_weights* w, int rows, cudaStream_t st) {
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  FfnParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.s_img = s_img; fp.s32 = s32; fp.out = out;
+  fp.ln2_g = w->ln2_g; fp.ln2_b = w->ln2_b;
+  fp.w1 = reinterpret_cast<const uint8_t*>(w->w_ffn1_u); fp.w2 = reinterpret_cast<const uint8_t*>(w->w_ffn2_u);
+  fp.b1 = w->b_ffn1; fp.b2 = w->b_ffn2;
+  fp.rows = rows; fp.tiles = (rows + 127) / 128; fp.d_ffn = w->d_ffn; fp.eps = 1e-5f;
+  {
+    ProfScope ps(KC_FFN, 4.0 * rows * 256.0 * w->d_ffn, (double)rows * 256 * 10.0, st);
+    ffn_fused_kernel<<<fp.tiles < d->sms ? fp.tiles : d->sms, FF_THREADS, FF_SMEM_BYTES, st>>>(fp);
+  }
+  AXVS_CHECK_LAUNCH("ffn_fused_kernel");
+  return AXVS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, const float* pos, const float* resid, float* out,
+                       const axvs_ta_weights* w, int B, int T, int H, int W, int axis, void* workspace, size_t workspace_bytes,
+                       axvs_stream_t stream) {
+  return traj_attn_impl(q_in, k_in, v_in, pos, resid, out, w, B, T, H, W, axis, workspace, workspace_bytes, stream, nullptr, nullptr, nullptr);
+}
+
 int axvs_traj_attn_maps(const float* q_in, const float* k_in, const float* pos, float* maps, const axvs_ta_weights* w, int B, int T, int H,
                         int W, int axis, void* workspace, size_t workspace_bytes, axvs_stream_t stream) {
   if (!q_in || !k_in || !maps || !w || !workspace) return fail(AXVS_E_INVALID, "traj_attn_maps: null pointer");
@@ -567,19 +603,7 @@ int axvs_ln_ffn_fwd(const float* x, float* out, const axvs_layer_weights* w, int
       ln_image_kernel<<<blocks_for(rows, 8, d->sms), 256, 0, (cudaStream_t)stream>>>(x, w->ln1_g, w->ln1_b, ws.s3, ws.s_img, rows, 1e-5f);
     }
     AXVS_CHECK_LAUNCH("ln_image_kernel");
-    FfnParams fp;
-    memset(&fp, 0, sizeof(fp));
-    fp.s_img = ws.s_img; fp.s32 = ws.s3; fp.out = out;
-    fp.ln2_g = w->ln2_g; fp.ln2_b = w->ln2_b;
-    fp.w1 = reinterpret_cast<const uint8_t*>(w->w_ffn1_u); fp.w2 = reinterpret_cast<const uint8_t*>(w->w_ffn2_u);
-    fp.b1 = w->b_ffn1; fp.b2 = w->b_ffn2;
-    fp.rows = rows; fp.tiles = (rows + 127) / 128; fp.d_ffn = w->d_ffn; fp.eps = 1e-5f;
-    {
-      ProfScope ps(KC_FFN, 4.0 * rows * 256.0 * w->d_ffn, (double)rows * 256 * 10.0, (cudaStream_t)stream);
-      ffn_fused_kernel<<<fp.tiles < d->sms ? fp.tiles : d->sms, FF_THREADS, FF_SMEM_BYTES, (cudaStream_t)stream>>>(fp);
-    }
-    AXVS_CHECK_LAUNCH("ffn_fused_kernel");
-    return AXVS_OK;
+    return ffn_fused_launch(ws.s_img, ws.s3, out, w, rows, (cudaStream_t)stream);
   }
   if ((rc = axvs_layernorm(x, w->ln1_g, w->ln1_b, ws.s3, ws.s3b, rows, 1e-5f, stream))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -595,7 +619,7 @@ size_t axvs_layer_workspace_bytes(int B, int T, int H, int W, int d_ffn) {
   const size_t rows = (size_t)B * T * H * W;
   const size_t ta = carve_ta(nullptr, rows, T).bytes;
   const size_t ffn = carve_ffn(nullptr, rows, d_ffn).bytes;
-  return 2 * align256(rows * 256 * 4) + (ta > ffn ? ta : ffn);
+  return 2 * align256(rows * 256 * 4) + align256(((rows + 127) / 128) * 4 * (size_t)TF_KB) + (ta > ffn ? ta : ffn);
 }
 
 int axvs_axial_layer_fwd(const float* src, const float* pos, float* out, const axvs_layer_weights* w, int B, int T, int H, int W,
@@ -609,16 +633,26 @@ int axvs_axial_layer_fwd(const float* src, const float* pos, float* out, const a
   uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
   float* s1 = reinterpret_cast<float*>(base);
   float* s2 = reinterpret_cast<float*>(base + align256(rows * 256 * 4));
-  void* sub = base + 2 * align256(rows * 256 * 4);
-  const size_t sub_bytes = workspace_bytes - 2 * align256(rows * 256 * 4);
+  uint8_t* ln_img = base + 2 * align256(rows * 256 * 4);
+  const size_t head = 2 * align256(rows * 256 * 4) + align256(((rows + 127) / 128) * 4 * (size_t)TF_KB);
+  void* sub = base + head;
+  const size_t sub_bytes = workspace_bytes - head;
+  // LayerNorm1 fused into the epilogue of the last trajectory attention (fusion level 3 only)
+  const axvs_ta_weights* last = axial ? &w->attn_w : &w->attn_h;
+  const bool fuse_ln = g_fusion >= 3 && last->w_qkv_u && last->w_pq_u && last->w_pkv_u && last->w_proj_u && w->w_ffn1_u && w->w_ffn2_u &&
+                       w->d_ffn >= 512 && w->d_ffn <= FF_MAX_DFFN && w->d_ffn % 256 == 0;
+  const float* lg = fuse_ln ? w->ln1_g : nullptr;
+  const float* lb = fuse_ln ? w->ln1_b : nullptr;
+  uint8_t* li = fuse_ln ? ln_img : nullptr;
   if (axial) {
     // S1 = S0 + TA_h(S0 + P, S0 + P, S0);  S2 = S1 + TA_w(S1 + P, S1 + P, S1)      WC/temporal_attention.py:197-213
-    if ((rc = axvs_traj_attn_fwd(src, src, src, pos, src, s1, &w->attn_h, B, T, H, W, AXVS_AXIS_H, sub, sub_bytes, stream))) return rc;
-    if ((rc = axvs_traj_attn_fwd(s1, s1, s1, pos, s1, s2, &w->attn_w, B, T, H, W, AXVS_AXIS_W, sub, sub_bytes, stream))) return rc;
+    if ((rc = traj_attn_impl(src, src, src, pos, src, s1, &w->attn_h, B, T, H, W, AXVS_AXIS_H, sub, sub_bytes, stream, nullptr, nullptr, nullptr))) return rc;
+    if ((rc = traj_attn_impl(s1, s1, s1, pos, s1, s2, &w->attn_w, B, T, H, W, AXVS_AXIS_W, sub, sub_bytes, stream, lg, lb, li))) return rc;
   } else {
     // non-axial: one attention over all T*H*W tokens of a clip                       WC/temporal_attention.py:141-150
-    if ((rc = axvs_traj_attn_fwd(src, src, src, pos, src, s2, &w->attn_h, B, T, H, W, AXVS_AXIS_NONE, sub, sub_bytes, stream))) return rc;
+    if ((rc = traj_attn_impl(src, src, src, pos, src, s2, &w->attn_h, B, T, H, W, AXVS_AXIS_NONE, sub, sub_bytes, stream, lg, lb, li))) return rc;
   }
+  if (fuse_ln) return ffn_fused_launch(ln_img, s2, out, w, (int)rows, (cudaStream_t)stream);   // s2 already holds LN1(S2)
   return axvs_ln_ffn_fwd(s2, out, w, (int)rows, sub, sub_bytes, stream);
 }
 

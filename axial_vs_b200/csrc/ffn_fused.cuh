@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
   if (threadIdx.x == 0) {
     for (int i = 0; i < FF_A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < FF_W_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
-    mbar_init(h_ready, 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
+    mbar_init(h_ready, 8);
     mbar_init(h_free, 1);
     mbar_init(acc_full, 1);
     mbar_init(acc_free, 8);
@@ -90,23 +90,26 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
     const int row_in_tile = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     const uint32_t t_acc = tmem + lane_base + 128 * g;          // my 128 output columns of acc2
-    const uint32_t t_s = tmem + lane_base + 256 + 128 * g;      // my GEMM-1 stage
     const int sub = lane >> 3, piece = lane & 7;
     uint8_t* stg = h_buf + warp * 4096;                         // per-warp transpose staging (final epilogue only)
-    uint32_t s_cnt = 0, it = 0;
+    uint32_t it = 0;
     AXVS_PROF_DECL(7)
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-      // ---- hidden chunks j = g, g+2, ...: bias + ReLU -> bf16 -> h_buf
-      for (int j = g; j < NJ; j += 2) {
-        AXVS_PROF_WAIT(0, mbar_wait(&s_full[g], s_cnt & 1))
-        ++s_cnt;
+      // ---- hidden chunks: BOTH groups drain every chunk (group g takes its 64 columns = K-block g of h_buf), which halves
+      // the drain latency that sits on the GEMM 1 -> GEMM 2 critical path: bias + ReLU -> bf16 -> h_buf
+#pragma unroll 1
+      for (int j = 0; j < NJ; ++j) {
+        const uint32_t hc = it * NJ + j;                         // global chunk counter (NJ is even: stage = hc & 1)
+        const int stage = j & 1;
+        AXVS_PROF_WAIT(0, mbar_wait(&s_full[stage], (hc >> 1) & 1))
         tc_fence_after();
-        uint32_t hpk[64];
+        const uint32_t t_s = tmem + lane_base + 256 + stage * 128 + 64 * g;
+        uint32_t hpk[32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           float v[32];
           tmem_ld32(t_s + 32 * c, v); tmem_ld_wait();
-          const float4* b4 = reinterpret_cast<const float4*>(sb1 + j * 128 + c * 32);
+          const float4* b4 = reinterpret_cast<const float4*>(sb1 + j * 128 + 64 * g + c * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 bb = b4[i];
@@ -116,13 +119,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[g]);                 // TMEM stage drained
-        const uint32_t hc = it * NJ + j;                         // global chunk counter: h_buf is free once GEMM 2 of chunk hc-1 retired
-        AXVS_PROF_WAIT(1, mbar_wait(h_free, (hc & 1) ^ 1))
+        if (lane == 0) mbar_arrive(&s_empty[stage]);             // my half of the TMEM stage is drained
+        AXVS_PROF_WAIT(1, mbar_wait(h_free, (hc & 1) ^ 1))        // h_buf is free once GEMM 2 of chunk hc-1 retired
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
+        for (int q = 0; q < 8; ++q) {
           uint4 u = make_uint4(hpk[4 * q], hpk[4 * q + 1], hpk[4 * q + 2], hpk[4 * q + 3]);
-          *reinterpret_cast<uint4*>(h_buf + (q >> 3) * TF_KB + sw128_offset(row_in_tile, q & 7)) = u;
+          *reinterpret_cast<uint4*>(h_buf + g * TF_KB + sw128_offset(row_in_tile, q)) = u;
         }
         AXVS_PROF_WAIT(6, fence_proxy_async_smem(); __syncwarp())
         if (lane == 0) mbar_arrive(h_ready);

@@ -43,6 +43,12 @@ struct TrajParams {
   int map_mode;
   AxialDims dims;
   float scale_log2e;       // head_dim^-0.5 * log2(e): logits are produced directly in the exp2 domain
+  // optional fused LayerNorm of the output row (norm1 of the layer, WC/temporal_attention.py:217): when ln_g != null the
+  // kernel writes out = LN(resid + proj(o) + b) as fp32 rows AND as the bf16 tile image the FFN kernel consumes
+  const float* ln_g;
+  const float* ln_b;
+  uint8_t* ln_img;         // [ceil(rows/128)][4][16 KiB], indexed by CANONICAL row
+  float ln_eps;
 };
 
 __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajParams p) {
@@ -210,27 +216,99 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajPar
         AXVS_PROF_WAIT(2, mbar_wait(&s_full[g], s_cnt & 1))
         ++s_cnt;
         tc_fence_after();
+        if (p.ln_g == nullptr) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          {
-            float v[32];
-            tmem_ld32(t_s + 32 * j, v);
-            tmem_ld_wait();
+          for (int j = 0; j < 4; ++j) {
+            {
+              float v[32];
+              tmem_ld32(t_s + 32 * j, v);
+              tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<float4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+              for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            }
+            __syncwarp();
+            const int col = 128 * g + 32 * j + piece * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rl = i * 4 + sub;
+              const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((piece ^ (rl & 7)) << 4));
+              if (orow[i] >= 0)
+                *reinterpret_cast<float4*>(p.out + (size_t)orow[i] * 256 + col) =
+                    make_float4(a.x + rr[j][i].x, a.y + rr[j][i].y, a.z + rr[j][i].z, a.w + rr[j][i].w);
+            }
+            __syncwarp();
           }
-          __syncwarp();
-          const int col = 128 * g + 32 * j + piece * 4;
+        } else {
+          // ---- fused LayerNorm: keep the row values in registers, combine the statistics of the two column halves through
+          // shared memory (upper half of o_buf), then write fp32 rows + the bf16 tile image of the normalised row
+          float ps[8], pq[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ps[i] = pq[i] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            {
+              float v[32];
+              tmem_ld32(t_s + 32 * j, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rl = i * 4 + sub;
+              const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((piece ^ (rl & 7)) << 4));
+              float4 tv = rr[j][i];
+              tv.x += a.x; tv.y += a.y; tv.z += a.z; tv.w += a.w;
+              rr[j][i] = tv;
+              ps[i] += tv.x + tv.y + tv.z + tv.w;
+              pq[i] += tv.x * tv.x + tv.y * tv.y + tv.z * tv.z + tv.w * tv.w;
+            }
+            __syncwarp();
+          }
+          float2* xc = reinterpret_cast<float2*>(o_buf + 32768) + (it & 1) * 256;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rl = i * 4 + sub;
-            const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((piece ^ (rl & 7)) << 4));
-            if (orow[i] >= 0)
-              *reinterpret_cast<float4*>(p.out + (size_t)orow[i] * 256 + col) =
-                  make_float4(a.x + rr[j][i].x, a.y + rr[j][i].y, a.z + rr[j][i].z, a.w + rr[j][i].w);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], o);
+              pq[i] += __shfl_xor_sync(0xffffffffu, pq[i], o);
+            }
+            if (piece == 0) xc[g * 128 + (warp & 3) * 32 + i * 4 + sub] = make_float2(ps[i], pq[i]);
           }
-          __syncwarp();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          float mean[8], rstd[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 other = xc[(g ^ 1) * 128 + (warp & 3) * 32 + i * 4 + sub];
+            mean[i] = (ps[i] + other.x) * (1.f / 256.f);
+            const float var = fmaxf((pq[i] + other.y) * (1.f / 256.f) - mean[i] * mean[i], 0.f);
+            rstd[i] = rsqrtf(var + p.ln_eps);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = 128 * g + 32 * j + piece * 4;
+            const float4 gg = __ldg(reinterpret_cast<const float4*>(p.ln_g + col)), be = __ldg(reinterpret_cast<const float4*>(p.ln_b + col));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 tv = rr[j][i];
+              const float4 y = make_float4((tv.x - mean[i]) * rstd[i] * gg.x + be.x, (tv.y - mean[i]) * rstd[i] * gg.y + be.y,
+                                           (tv.z - mean[i]) * rstd[i] * gg.z + be.z, (tv.w - mean[i]) * rstd[i] * gg.w + be.w);
+              // 16-byte image chunk = 8 channels = this lane (even piece) + its odd neighbour
+              const uint32_t lo = pack_bf16x2(y.x, y.y), hi = pack_bf16x2(y.z, y.w);
+              const uint32_t nlo = __shfl_down_sync(0xffffffffu, lo, 1), nhi = __shfl_down_sync(0xffffffffu, hi, 1);
+              if (orow[i] >= 0) {
+                *reinterpret_cast<float4*>(p.out + (size_t)orow[i] * 256 + col) = y;
+                if ((piece & 1) == 0) {
+                  const uint32_t orw = (uint32_t)orow[i];
+                  *reinterpret_cast<uint4*>(p.ln_img + ((size_t)(orw >> 7) * 4 + (col >> 6)) * TF_KB + sw128_offset(orw & 127u, (col & 63) >> 3)) =
+                      make_uint4(lo, hi, nlo, nhi);
+                }
+              }
+            }
+          }
         }
       }
       // released only now: the staging area aliases o_buf, which the other group refills once this stage's next
