@@ -213,13 +213,15 @@ constexpr int ATT2_KB = 16384;   // bytes of one 128-row x 64-column image K-blo
 
 template <int NT16>
 __global__ void __launch_bounds__(128) spatial_attn_v2_kernel(const __nv_bfloat16* __restrict__ qkv, size_t rows_total, uint8_t* __restrict__ x_img,
-                                                              uint8_t* __restrict__ xd_img, int tiles, int N, int n, int F, float scale_log2e) {
+                                                              uint8_t* __restrict__ xd_img, int tiles, int N, int n, int F, float scale_log2e,
+                                                              int all_frames) {
   extern __shared__ __align__(128) uint8_t att_smem[];
   constexpr int NP = 16 * NT16;
   const int n_mblk = (N + 15) >> 4;
+  const int kv_bufs = all_frames ? F : 2;
   uint8_t* sQ = att_smem;                                  // [n_mblk*16][64 B]
-  uint8_t* sKV = sQ + (size_t)n_mblk * 16 * 64;            // [2 buffers][K | V][NP][64 B]
-  uint8_t* sStage = sKV + 4 * NP * 64;                     // [4 warps][16 rows][64 B]
+  uint8_t* sKV = sQ + (size_t)n_mblk * 16 * 64;            // [kv_bufs][K | V][NP][64 B]
+  uint8_t* sStage = sKV + (size_t)kv_bufs * 2 * NP * 64;   // [4 warps][16 rows][64 B]
 
   const int seq = blockIdx.x >> 3, head = blockIdx.x & 7;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(128) spatial_attn_v2_kernel(const __nv_bfloat1
     cp_async16(sQ + att_off(r, ch), gq + (size_t)(ok ? r : 0) * 32 + ch * 8, ok);
   }
   auto load_kv = [&](int f, int buf) {
-    uint8_t* sK = sKV + buf * 2 * NP * 64;
+    uint8_t* sK = sKV + (size_t)buf * 2 * NP * 64;
     uint8_t* sV = sK + NP * 64;
     for (int c = tid; c < NP * 4; c += 128) {
       const int r = c >> 2, ch = c & 3;
@@ -244,107 +246,121 @@ __global__ void __launch_bounds__(128) spatial_attn_v2_kernel(const __nv_bfloat1
       cp_async16(sV + att_off(r, ch), gv + off, ok);
     }
   };
-  load_kv(0, 0);
-  cp_async_commit();
 
   const int g = lane >> 2, t4 = lane & 3;
   uint8_t* stg = sStage + warp * 1024;
   const int kb = head >> 1, ch0 = (head & 1) * 4;
 
-  for (int f = 0; f < F; ++f) {
-    const int buf = f & 1;
-    if (f + 1 < F) load_kv(f + 1, buf ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    const uint8_t* sK = sKV + buf * 2 * NP * 64;
-    const uint8_t* sV = sK + NP * 64;
-
-    for (int mb = warp; mb < n_mblk; mb += 4) {
-      uint32_t qa[2][4];
-      {
-        const int r = mb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  // one (16-query block, key frame) work item: S = Q K_f^T, one-shot softmax, P V_f, write x_f (+ x_diag) image rows
+  auto process = [&](int mb, int f, const uint8_t* sK, const uint8_t* sV) {
+    uint32_t qa[2][4];
+    {
+      const int r = mb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) ldmatrix_x4(qa[ks], sQ + att_off(r, ks * 2 + (lane >> 4)));
-      }
-      float s[2 * NT16][4];
-#pragma unroll
-      for (int j = 0; j < 2 * NT16; ++j) {
-        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-        uint32_t kf[4];
-        ldmatrix_x4(kf, sK + att_off(j * 8 + (lane & 7), lane >> 3));
-        mma_bf16_16816(s[j], qa[0], kf[0], kf[1]);
-        mma_bf16_16816(s[j], qa[1], kf[2], kf[3]);
-      }
-      float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-      for (int j = 0; j < 2 * NT16; ++j) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int key = j * 8 + t4 * 2 + (e & 1);
-          const float v = (key < n) ? s[j][e] * scale_log2e : -INFINITY;
-          s[j][e] = v;
-          mx[e >> 1] = fmaxf(mx[e >> 1], v);
-        }
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
-        mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-      }
-      float rs[2] = {0.f, 0.f};
-      uint32_t pa[NT16][4];
-#pragma unroll
-      for (int j = 0; j < 2 * NT16; ++j) {
-        const float p0 = exp2f(s[j][0] - mx[0]), p1 = exp2f(s[j][1] - mx[0]);
-        const float p2 = exp2f(s[j][2] - mx[1]), p3 = exp2f(s[j][3] - mx[1]);
-        rs[0] += p0 + p1;
-        rs[1] += p2 + p3;
-        pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-        pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
-      }
-      float acc[4][4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < NT16; ++ks) {
-#pragma unroll
-        for (int jn = 0; jn < 4; jn += 2) {
-          uint32_t vb[4];
-          const int key = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-          ldmatrix_x4_trans(vb, sV + att_off(key, jn + (lane >> 4)));
-          mma_bf16_16816(acc[jn], pa[ks], vb[0], vb[1]);
-          mma_bf16_16816(acc[jn + 1], pa[ks], vb[2], vb[3]);
-        }
-      }
-      // normalise -> per-warp staging (16 rows x 64 B) -> 16-byte stores into the tile images
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float l = rs[h];
-        l += __shfl_xor_sync(0xffffffffu, l, 1);
-        l += __shfl_xor_sync(0xffffffffu, l, 2);
-        const float inv = 1.f / l;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint32_t*>(stg + att_off(g + h * 8, j) + t4 * 4) = pack_bf16x2(acc[j][h * 2] * inv, acc[j][h * 2 + 1] * inv);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int idx = lane + 32 * i;
-        const int row = idx >> 2, chunk = idx & 3;
-        const int qi = mb * 16 + row;                     // query index inside the sequence
-        if (qi < N) {
-          const uint4 v = *reinterpret_cast<const uint4*>(stg + att_off(row, chunk));
-          const size_t r = seq_row0 + qi;
-          const size_t off = ((r >> 7) * 4 + kb) * ATT2_KB + sw128_offset((uint32_t)(r & 127), ch0 + chunk);
-          *reinterpret_cast<uint4*>(x_img + (size_t)f * tiles * 4 * ATT2_KB + off) = v;
-          if (qi / n == f) *reinterpret_cast<uint4*>(xd_img + off) = v;
-        }
-      }
-      __syncwarp();
+      for (int ks = 0; ks < 2; ++ks) ldmatrix_x4(qa[ks], sQ + att_off(r, ks * 2 + (lane >> 4)));
     }
-    __syncthreads();   // all warps done with this frame's K/V buffer before it is refilled
+    float s[2 * NT16][4];
+#pragma unroll
+    for (int j = 0; j < 2 * NT16; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      uint32_t kf[4];
+      ldmatrix_x4(kf, sK + att_off(j * 8 + (lane & 7), lane >> 3));
+      mma_bf16_16816(s[j], qa[0], kf[0], kf[1]);
+      mma_bf16_16816(s[j], qa[1], kf[2], kf[3]);
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 2 * NT16; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = j * 8 + t4 * 2 + (e & 1);
+        const float v = (key < n) ? s[j][e] * scale_log2e : -INFINITY;
+        s[j][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pa[NT16][4];
+#pragma unroll
+    for (int j = 0; j < 2 * NT16; ++j) {
+      const float p0 = exp2f(s[j][0] - mx[0]), p1 = exp2f(s[j][1] - mx[0]);
+      const float p2 = exp2f(s[j][2] - mx[1]), p3 = exp2f(s[j][3] - mx[1]);
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < NT16; ++ks) {
+#pragma unroll
+      for (int jn = 0; jn < 4; jn += 2) {
+        uint32_t vb[4];
+        const int key = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4_trans(vb, sV + att_off(key, jn + (lane >> 4)));
+        mma_bf16_16816(acc[jn], pa[ks], vb[0], vb[1]);
+        mma_bf16_16816(acc[jn + 1], pa[ks], vb[2], vb[3]);
+      }
+    }
+    // normalise -> per-warp staging (16 rows x 64 B) -> 16-byte stores into the tile images
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float l = rs[h];
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      const float inv = 1.f / l;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint32_t*>(stg + att_off(g + h * 8, j) + t4 * 4) = pack_bf16x2(acc[j][h * 2] * inv, acc[j][h * 2 + 1] * inv);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = lane + 32 * i;
+      const int row = idx >> 2, chunk = idx & 3;
+      const int qi = mb * 16 + row;                     // query index inside the sequence
+      if (qi < N) {
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + att_off(row, chunk));
+        const size_t r = seq_row0 + qi;
+        const size_t off = ((r >> 7) * 4 + kb) * ATT2_KB + sw128_offset((uint32_t)(r & 127), ch0 + chunk);
+        *reinterpret_cast<uint4*>(x_img + (size_t)f * tiles * 4 * ATT2_KB + off) = v;
+        if (qi / n == f) *reinterpret_cast<uint4*>(xd_img + off) = v;
+      }
+    }
+    __syncwarp();
+  };
+
+  if (all_frames) {
+    // every frame's K/V resident: the (query block, frame) items are spread evenly over the 4 warps
+    for (int f = 0; f < F; ++f) load_kv(f, f);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int item = warp; item < n_mblk * F; item += 4) {
+      const int mb = item / F, f = item - mb * F;
+      const uint8_t* sK = sKV + (size_t)f * 2 * NP * 64;
+      process(mb, f, sK, sK + NP * 64);
+    }
+  } else {
+    load_kv(0, 0);
+    cp_async_commit();
+    for (int f = 0; f < F; ++f) {
+      const int buf = f & 1;
+      if (f + 1 < F) load_kv(f + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+      const uint8_t* sK = sKV + (size_t)buf * 2 * NP * 64;
+      for (int mb = warp; mb < n_mblk; mb += 4) process(mb, f, sK, sK + NP * 64);
+      __syncthreads();   // all warps done with this frame's K/V buffer before it is refilled
+    }
   }
 }
 

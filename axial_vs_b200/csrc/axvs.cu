@@ -357,16 +357,20 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
     }
     AXVS_CHECK_LAUNCH("qkv_fused_kernel");
     const int nt16 = (n + 15) / 16;
-    const size_t att_smem = (size_t)((N + 15) / 16) * 16 * 64 + 4096;
-    if (nt16 <= 11 && att_smem + 4 * 176 * 64 <= 200 * 1024) {
+    const int np_sel = nt16 <= 2 ? 2 : nt16 <= 3 ? 3 : nt16 <= 4 ? 4 : nt16 <= 6 ? 6 : nt16 <= 8 ? 8 : 11;
+    const size_t att_q = (size_t)((N + 15) / 16) * 16 * 64 + 4096;
+    const size_t kv_all = (size_t)F * 2 * 16 * np_sel * 64;
+    const int all_frames = (att_q + kv_all <= 64 * 1024) ? 1 : 0;          // small sequences: every frame's K/V resident
+    const size_t att_smem = att_q + (all_frames ? kv_all : (size_t)4 * 16 * np_sel * 64);
+    if (nt16 <= 11 && att_smem <= 200 * 1024) {
       ProfScope ps(KC_ATTN2, 4.0 * num_seq * (double)N * N * 256, (double)rows * (1536.0 + (F + 1) * 512.0), st);
       const dim3 grid((unsigned)num_seq * 8);
-#define AXVS_ATT2(NT) spatial_attn_v2_kernel<NT><<<grid, 128, att_smem + 4 * 16 * NT * 64, st>>>(ws.qkv, rows, ws.x_img, ws.xd_img, tiles, N, n, F, kScaleLog2e)
-      if (nt16 <= 2) AXVS_ATT2(2);
-      else if (nt16 <= 3) AXVS_ATT2(3);
-      else if (nt16 <= 4) AXVS_ATT2(4);
-      else if (nt16 <= 6) AXVS_ATT2(6);
-      else if (nt16 <= 8) AXVS_ATT2(8);
+#define AXVS_ATT2(NT) spatial_attn_v2_kernel<NT><<<grid, 128, att_smem, st>>>(ws.qkv, rows, ws.x_img, ws.xd_img, tiles, N, n, F, kScaleLog2e, all_frames)
+      if (np_sel == 2) AXVS_ATT2(2);
+      else if (np_sel == 3) AXVS_ATT2(3);
+      else if (np_sel == 4) AXVS_ATT2(4);
+      else if (np_sel == 6) AXVS_ATT2(6);
+      else if (np_sel == 8) AXVS_ATT2(8);
       else AXVS_ATT2(11);
 #undef AXVS_ATT2
     } else {
