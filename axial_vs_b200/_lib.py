@@ -21,6 +21,11 @@ class TaWeights(Structure):
                 ("w_pkv", c_void_p), ("b_pkv", c_void_p), ("w_qkv_u", c_void_p), ("w_pq_u", c_void_p), ("w_pkv_u", c_void_p), ("w_proj_u", c_void_p), ("w_proj", c_void_p), ("b_proj", c_void_p)]
 
 
+class AsppWeights(Structure):
+    _fields_ = [("w_conv", c_void_p * 3), ("b_conv", c_void_p * 3), ("dilation", c_int * 3), ("w_proj", c_void_p),
+                ("lncf_g", c_void_p), ("lncf_b", c_void_p), ("ln_g", c_void_p), ("ln_b", c_void_p)]
+
+
 class LayerWeights(Structure):
     _fields_ = [("attn_h", TaWeights), ("attn_w", TaWeights), ("ln1_g", c_void_p), ("ln1_b", c_void_p),
                 ("w_ffn1", c_void_p), ("b_ffn1", c_void_p), ("w_ffn2", c_void_p), ("b_ffn2", c_void_p),
@@ -49,6 +54,11 @@ SIGNATURES = {
     "axvs_layer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "axvs_axial_layer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(LayerWeights), c_int, c_int, c_int, c_int,
                                      c_int, c_void_p, c_size_t, c_void_p]),
+    "axvs_cast_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "axvs_cc_aspp_workspace_bytes": (c_size_t, [c_int]),
+    "axvs_cc_aspp_fwd": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(AsppWeights), c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "axvs_cc_class_pool": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p]),
+    "axvs_mask_einsum": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "axvs_pos3d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "axvs_profile_enable": (c_int, [c_int]),
     "axvs_profile_num_classes": (c_int, []),

@@ -81,3 +81,160 @@ class TrajectoryAttentionLayer(nn.Module):
         if self.normalize_before:
             return self.forward_pre(x, seq_len, num_frames)
         return self.forward_post(x, seq_len, num_frames)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The rest of the cross-clip tracking module (CC:30-75, 176-331): temporal ASPP, embedding projections, predictor.
+# Parameter names mirror the reference state dict (`conv_short_aggregate_layers.{i}._aspp_conv{j}`, `conv_norms.{i}`,
+# `_class_embedding_projection.{conv,norm}`, `_mask_embedding_projection.{conv,norm}`, `_predictor.*`).
+# ------------------------------------------------------------------------------------------------------------------
+import math
+from typing import List
+
+
+class _ConvBN1d(nn.Module):
+    """`ConvBN(conv_type='1d', kernel_size=1)` (Vk/kmax_deeplab/modeling/pixel_decoder/kmax_pixel_decoder.py:42-72), eval only.
+    The 1x1 conv + eval-mode (Sync)BatchNorm is folded into one GEMM: W' = W * g/sqrt(rv+eps), b' = beta - rm*g/sqrt(rv+eps) (+ conv bias)."""
+
+    def __init__(self, cin, cout, bias=True, norm=None, act=None):
+        super().__init__()
+        self.conv = nn.Conv1d(cin, cout, kernel_size=1, bias=bias)
+        self.norm = nn.BatchNorm1d(cout, eps=1e-3, momentum=0.01) if norm == "syncbn" else nn.Identity()
+        self.act_code = {None: 0, "relu": 1, "gelu": 2}[act]
+        self.cout = cout
+        self._cache = _PackedCache()
+
+    def folded(self):
+        w = self.conv.weight.detach().float()[:, :, 0]
+        b = self.conv.bias.detach().float() if self.conv.bias is not None else torch.zeros(self.cout, device=w.device)
+        if isinstance(self.norm, nn.BatchNorm1d):
+            sc = self.norm.weight.detach().float() / torch.sqrt(self.norm.running_var.float() + self.norm.eps)
+            w = w * sc[:, None]
+            b = (b - self.norm.running_mean.float()) * sc + self.norm.bias.detach().float()
+        return w, b
+
+    def packed(self, device):
+        def build():
+            w, b = self.folded()
+            n_pad = (self.cout + 255) // 256 * 256                      # the GEMM works on 256-column chunks
+            wp = torch.zeros(n_pad, w.shape[1], device=w.device)
+            wp[: self.cout] = w
+            bp = torch.zeros(n_pad, device=w.device)
+            bp[: self.cout] = b
+            return ops.pack_weight(wp.contiguous()), bp.contiguous(), n_pad
+        key_mod = nn.ModuleList([self.conv, self.norm]) if isinstance(self.norm, nn.BatchNorm1d) else self.conv
+        return self._cache.get(key_mod, device, build)
+
+    def run(self, a_bf16: Tensor, out_dtype=torch.bfloat16, extra_bias: Tensor = None) -> Tensor:
+        wp, bp, n_pad = self.packed(a_bf16.device)
+        if extra_bias is not None:
+            bp = bp.clone()
+            bp[: self.cout] += extra_bias
+        return ops.linear_act(a_bf16, wp, bp, n_pad, self.act_code, out_dtype)
+
+
+class ASPP(nn.Module):
+    """CC:176-201 (parameters only; the arithmetic is fused with the residual + conv_norms LayerNorm in `axvs_cc_aspp_fwd`)."""
+
+    def __init__(self, in_channels, output_channels, kernel_sizes, atrous_rates, dropout_rate, norm_fn):
+        super().__init__()
+        if norm_fn != "ln" or list(kernel_sizes) != [3, 3, 3] or in_channels != 256 or output_channels != 256:
+            raise NotImplementedError("axial_vs_b200: ASPP supports 256 channels, kernel_sizes [3,3,3], norm_fn 'ln' (every shipped config)")
+        for j in range(3):
+            setattr(self, f"_aspp_conv{j}", nn.Conv1d(in_channels, output_channels, kernel_size=3, dilation=atrous_rates[j], padding="same",
+                                                      padding_mode="replicate"))
+        self._proj_conv_bn_act = nn.Module()
+        self._proj_conv_bn_act.conv = nn.Conv1d(output_channels * 3, output_channels, kernel_size=1, bias=False)
+        self._proj_conv_bn_act.norm = nn.Module()
+        self._proj_conv_bn_act.norm.weight = nn.Parameter(torch.ones(output_channels))
+        self._proj_conv_bn_act.norm.bias = nn.Parameter(torch.zeros(output_channels))
+        self.atrous_rates = list(atrous_rates)
+
+
+class MaXTronCCPredictor(nn.Module):
+    """CC:30-75, eval branch."""
+
+    def __init__(self, num_classes=133 + 1):
+        super().__init__()
+        self._transformer_mask_head = _ConvBN1d(256, 128, bias=False, norm="syncbn")
+        self._transformer_class_head = _ConvBN1d(256, num_classes)
+        self._transformer_class_activation_head = _ConvBN1d(256, 1)
+        self._pixel_space_mask_batch_norm = nn.BatchNorm1d(1, eps=1e-3, momentum=0.01)
+        nn.init.constant_(self._pixel_space_mask_batch_norm.weight, 0.1)
+        self.num_classes = num_classes
+
+    def forward(self, mask_embeddings, class_embeddings, pixel_feature, num_clips, num_clip_frames):
+        """mask/class embeddings: bf16 [T*Q, 256] rows (t, q); pixel_feature fp32 [T, 128, V*H, W]."""
+        T = num_clips
+        Q = class_embeddings.shape[0] // T
+        act = self._transformer_class_activation_head
+        pooled = ops.cc_class_pool(class_embeddings, act.conv.weight.detach().float().reshape(-1).contiguous(),
+                                   float(act.conv.bias.detach()), T, Q)                                      # [Q, 256]
+        void = torch.zeros(self.num_classes, device=pooled.device)
+        void[-1] = math.log((self.num_classes - 1) * 0.9 / (1 - 0.9))                                         # add_bias_towards_void
+        cls = self._transformer_class_head.run(pooled, torch.float32, extra_bias=void)[:, : self.num_classes]  # [Q, K+1]
+        mk = self._transformer_mask_head.run(mask_embeddings)                                                  # bf16 [T*Q, 256], 128 valid
+        bn = self._pixel_space_mask_batch_norm
+        sc = float(bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps))
+        sh = float(bn.bias.detach() - bn.running_mean * sc)
+        _, Cp, VH, Wd = pixel_feature.shape
+        P = VH * Wd
+        ml = ops.mask_einsum(pixel_feature.contiguous().float(), mk, T, Q, P, sc, sh)                          # [Q, T, P]
+        V = num_clip_frames
+        return {"class_logits": cls.unsqueeze(0), "mask_logits": ml.view(1, Q, T * V, VH // V, Wd)}
+
+
+class CrossClipTrackingModule(nn.Module):
+    """CC:204-331.  forward(clip_query [1, Q, T, C], panoptic_features [1, 128, T*V, H, W]) -> dict (eval, batch of one video)."""
+
+    def __init__(self, *, num_layers: int, num_classes: int, attn_drop: float, aspp_drop: float, kernel_sizes: List[int],
+                 atrous_rates: List[int], norm_fn: str, num_clip_frames: int):
+        super().__init__()
+        self.kernel_sizes, self.atrous_rates = kernel_sizes, atrous_rates
+        self.attn_drop, self.aspp_drop, self.norm_fn, self.num_clip_frames = attn_drop, aspp_drop, norm_fn, num_clip_frames
+        self.num_heads = 8
+        self.num_layers = num_layers
+        self.transformer_trajectory_self_attention_layers = nn.ModuleList()
+        self.conv_short_aggregate_layers = nn.ModuleList()
+        self.conv_norms = nn.ModuleList()
+        for _ in range(num_layers):
+            self.transformer_trajectory_self_attention_layers.append(
+                TrajectoryAttentionLayer(d_model=256, nhead=8, dropout=0.0, attn_drop=attn_drop, normalize_before=False))
+            self.conv_short_aggregate_layers.append(ASPP(256, 256, kernel_sizes, atrous_rates, aspp_drop, norm_fn))
+            self.conv_norms.append(nn.LayerNorm(256))
+        self._class_embedding_projection = _ConvBN1d(256, 256, bias=False, norm="syncbn", act="gelu")
+        self._mask_embedding_projection = _ConvBN1d(256, 256, bias=False, norm="syncbn", act="gelu")
+        self._predictor = MaXTronCCPredictor(num_classes=num_classes + 1)
+        self._aspp_cache = [_PackedCache() for _ in range(num_layers)]
+
+    def _packed_aspp(self, i, device):
+        mods = nn.ModuleList([self.conv_short_aggregate_layers[i], self.conv_norms[i]])
+        return self._aspp_cache[i].get(mods, device, lambda: ops.pack_aspp(dict(self.conv_short_aggregate_layers[i].state_dict()),
+                                                                            self.conv_norms[i].weight, self.conv_norms[i].bias, self.atrous_rates))
+
+    def forward(self, clip_query, panoptic_features):
+        _require_inference(self, clip_query, panoptic_features)
+        b, Q, T, C = clip_query.shape
+        if b != 1:
+            raise NotImplementedError("axial_vs_b200: the cross-clip module runs one video at a time at inference (as the reference does)")
+        V = self.num_clip_frames
+        _, Cp, TV, Hh, Ww = panoptic_features.shape
+        pf = panoptic_features.reshape(b, Cp, T, V, Hh, Ww).permute(0, 2, 1, 3, 4, 5).reshape(b * T, Cp, V * Hh, Ww).contiguous()   # CC:278
+        x = clip_query.permute(0, 2, 1, 3).reshape(b, T * Q, C).contiguous().float()          # 'b q t c -> b (t q) c': rows (t, q)
+        predictions_class, predictions_mask = [], []
+        for i in range(self.num_layers):
+            x = self.transformer_trajectory_self_attention_layers[i](x, seq_len=Q, num_frames=T)                 # LN(x + TA(x))
+            x32, x16 = ops.cc_aspp_fwd(x.view(-1, C), self._packed_aspp(i, x.device), b, T, Q)                     # LN(ASPP(z) + z)
+            x = x32.view(b, T * Q, C)
+            ce = self._class_embedding_projection.run(x16)
+            me = self._mask_embedding_projection.run(x16)
+            r = self._predictor(me, ce, pf, T, V)
+            predictions_class.append(r["class_logits"])
+            predictions_mask.append(r["mask_logits"])
+        self.last_clip_query = x.view(b, T, Q, C).permute(0, 2, 1, 3)
+        aux = []
+        target_size = predictions_mask[-1].shape[-3:]
+        align_corners = (target_size[-1] % 2 == 1)
+        for a, m in zip(predictions_class[:-1], predictions_mask[:-1]):
+            aux.append({"pred_logits": a, "pred_masks": torch.nn.functional.interpolate(m, size=target_size, mode="trilinear", align_corners=align_corners)})
+        return {"pred_logits": predictions_class[-1], "pred_masks": predictions_mask[-1], "aux_outputs": aux}

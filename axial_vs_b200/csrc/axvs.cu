@@ -12,6 +12,7 @@
 #include "traj_fused.cuh"
 #include "ffn_fused.cuh"
 #include "qkv_fused.cuh"
+#include "cc_tail.cuh"
 
 using namespace axvs;
 
@@ -28,11 +29,11 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
-                                            "spatial_attn_v2_kernel"};
+                                            "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel"};
 int g_fusion = 3;
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
@@ -72,6 +73,7 @@ struct DeviceInfo {
   bool ffn_attr = false;
   bool qkv_attr = false;
   bool attn2_attr = false;
+  bool mask_attr = false;
 };
 DeviceInfo g_dev[64];
 
@@ -110,6 +112,11 @@ int device_info(DeviceInfo** out) {
         cudaFuncSetAttribute(spatial_attn_v2_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(spatial_attn_v2) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.attn2_attr = true;
+  }
+  if (!d.mask_attr) {
+    if (cudaFuncSetAttribute(mask_einsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 256) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(mask_einsum) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    d.mask_attr = true;
   }
   if (!d.ffn_attr) {
     if (cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES) != cudaSuccess)
@@ -232,7 +239,7 @@ int blocks_for(long long work_items, int per_block, int sms) {
 
 extern "C" {
 
-int axvs_version(void) { return 104; }
+int axvs_version(void) { return 105; }
 int axvs_set_fusion(int level) {
   const int prev = g_fusion;
   g_fusion = level < 0 ? 0 : (level > 3 ? 3 : level);
@@ -658,6 +665,96 @@ int axvs_axial_layer_fwd(const float* src, const float* pos, float* out, const a
   }
   if (fuse_ln) return ffn_fused_launch(ln_img, s2, out, w, (int)rows, (cudaStream_t)stream);   // s2 already holds LN1(S2)
   return axvs_ln_ffn_fwd(s2, out, w, (int)rows, sub, sub_bytes, stream);
+}
+
+int axvs_cast_bf16(const float* x, void* out_bf16, int rows, axvs_stream_t stream) {
+  if (!x || !out_bf16) return fail(AXVS_E_INVALID, "cast_bf16: null pointer");
+  if (rows <= 0) return fail(AXVS_E_INVALID, "cast_bf16: rows must be positive");
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  {
+    ProfScope ps(KC_PACK, 0, (double)rows * 256 * 6.0, (cudaStream_t)stream);
+    pack_kq_kernel<<<blocks_for(rows, 8, d->sms), 256, 0, (cudaStream_t)stream>>>(x, nullptr, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, rows, MAP_NONE,
+                                                                                 AxialDims{1, 1, 1, 1});
+  }
+  AXVS_CHECK_LAUNCH("pack_kq_kernel(cast)");
+  return AXVS_OK;
+}
+
+size_t axvs_cc_aspp_workspace_bytes(int rows) {
+  if (rows <= 0) return 0;
+  return align256((size_t)rows * 256 * 2) + align256((size_t)rows * 768 * 2) + align256((size_t)rows * 256 * 4);
+}
+
+int axvs_cc_aspp_fwd(const float* x, float* out, void* out_bf16, const axvs_aspp_weights* w, int b, int T, int Q, void* workspace,
+                     size_t workspace_bytes, axvs_stream_t stream) {
+  if (!x || !out || !w || !workspace) return fail(AXVS_E_INVALID, "cc_aspp: null pointer");
+  if (b <= 0 || T <= 0 || Q <= 0) return fail(AXVS_E_INVALID, "cc_aspp: sizes must be positive");
+  for (int i = 0; i < 3; ++i)
+    if (!w->w_conv[i] || w->dilation[i] <= 0) return fail(AXVS_E_INVALID, "cc_aspp: bad conv branch %d", i);
+  if (!w->w_proj || !w->lncf_g || !w->lncf_b || !w->ln_g || !w->ln_b) return fail(AXVS_E_INVALID, "cc_aspp: null weight pointer");
+  const long long rows_ll = (long long)b * T * Q;
+  if (rows_ll > (1ll << 30)) return fail(AXVS_E_UNSUPPORTED, "cc_aspp: too many rows");
+  const int rows = (int)rows_ll;
+  if (axvs_cc_aspp_workspace_bytes(rows) > workspace_bytes) return fail(AXVS_E_WORKSPACE, "cc_aspp: workspace too small");
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* cat = reinterpret_cast<__nv_bfloat16*>(base + align256((size_t)rows * 256 * 2));
+  float* y = reinterpret_cast<float*>(base + align256((size_t)rows * 256 * 2) + align256((size_t)rows * 768 * 2));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = axvs_cast_bf16(x, xb, rows, stream))) return rc;
+  for (int i = 0; i < 3; ++i) {       // three dilated k=3 convs over time = GEMMs with K = 3 x 256 on time-shifted rows
+    GemmParams p = gemm_params(xb, 256, rows, 768, w->w_conv[i], 256, 0, w->b_conv[i], 256, 1.f, 0, cat, 768, 256 * i, 1, nullptr);
+    p.a_diag = 2; p.a_N = T; p.a_n = Q; p.a_F = w->dilation[i];
+    if ((rc = launch_gemm(p, st))) return rc;
+  }
+  {
+    GemmParams p = gemm_params(cat, 768, rows, 768, w->w_proj, 256, 0, nullptr, 256, 1.f, 0, y, 256, 0, 0, nullptr);
+    if ((rc = launch_gemm(p, st))) return rc;
+  }
+  DeviceInfo* d;
+  if ((rc = device_info(&d))) return rc;
+  {
+    ProfScope ps(KC_CCTAIL, 0, (double)rows * 256 * 14.0, st);
+    aspp_tail_kernel<<<blocks_for(rows, 8, d->sms), 256, 0, st>>>(y, x, w->lncf_g, w->lncf_b, w->ln_g, w->ln_b, out,
+                                                                reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, 1e-6f, 1e-5f);
+  }
+  AXVS_CHECK_LAUNCH("aspp_tail_kernel");
+  return AXVS_OK;
+}
+
+int axvs_cc_class_pool(const void* ce_bf16, const float* w_act, float b_act, void* pooled_bf16, int T, int Q, axvs_stream_t stream) {
+  if (!ce_bf16 || !w_act || !pooled_bf16) return fail(AXVS_E_INVALID, "cc_class_pool: null pointer");
+  if (T <= 0 || Q <= 0) return fail(AXVS_E_INVALID, "cc_class_pool: sizes must be positive");
+  {
+    ProfScope ps(KC_CCTAIL, 0, (double)T * Q * 512.0, (cudaStream_t)stream);
+    cc_class_pool_kernel<<<(Q + 7) / 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(ce_bf16), w_act, b_act,
+                                                                        reinterpret_cast<__nv_bfloat16*>(pooled_bf16), T, Q);
+  }
+  AXVS_CHECK_LAUNCH("cc_class_pool_kernel");
+  return AXVS_OK;
+}
+
+int axvs_mask_einsum(const float* pixel, const void* mk_bf16, int ld_mk, float* out, int T, int Q, int P, float bn_scale, float bn_shift,
+                     axvs_stream_t stream) {
+  if (!pixel || !mk_bf16 || !out) return fail(AXVS_E_INVALID, "mask_einsum: null pointer");
+  if (T <= 0 || Q <= 0 || P <= 0) return fail(AXVS_E_INVALID, "mask_einsum: sizes must be positive");
+  if (Q > 128) return fail(AXVS_E_UNSUPPORTED, "mask_einsum: at most 128 queries per clip (got %d)", Q);
+  if (ld_mk < 128 || ld_mk % 8) return fail(AXVS_E_INVALID, "mask_einsum: ld_mk must be >= 128 and a multiple of 8");
+  if (T > 65535) return fail(AXVS_E_UNSUPPORTED, "mask_einsum: at most 65535 clips");
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  dim3 grid((P + ME_PT - 1) / ME_PT, T);
+  {
+    ProfScope ps(KC_MASK, 2.0 * T * (double)Q * P * 128, (double)T * P * (512.0 + 4.0 * Q), (cudaStream_t)stream);
+    mask_einsum_kernel<<<grid, 256, 2 * 128 * 256, (cudaStream_t)stream>>>(pixel, reinterpret_cast<const __nv_bfloat16*>(mk_bf16), ld_mk, out, T, Q, P, bn_scale,
+                                                                          bn_shift);
+  }
+  AXVS_CHECK_LAUNCH("mask_einsum_kernel");
+  return AXVS_OK;
 }
 
 int axvs_pos3d(float* out, const float* level_embed, int B, int T, int H, int W, axvs_stream_t stream) {

@@ -59,6 +59,9 @@ struct GemmParams {
   int M;        // logical rows
   int K;        // multiple of 64
   int a_diag;   // 1: logical row r reads A row r*F + (r % N) / n   (own-frame rows of x[rows, F, C])
+                // 2: temporal 3-tap gather for the cross-clip ASPP convs (K = 3*256): rows are (b, t, q) with a_n = Q rows
+                //    per time step, a_N = T steps, a_F = dilation; K-block kb reads channels (kb&3)*64.. of the row at
+                //    time clamp(t + (kb/4 - 1) * dilation, 0, T-1)  (Conv1d k=3, padding 'same', replicate; CC:180-182)
   int a_N, a_n, a_F;
   // W operand (packed) and bias
   const uint8_t* Wp;
@@ -68,7 +71,7 @@ struct GemmParams {
   const float* bias;
   // epilogue
   float scale;  // applied after bias
-  int relu;
+  int relu;     // activation: 0 none, 1 ReLU, 2 GELU (erf form, nn.GELU default)
   void* out;    // bf16 or fp32
   int ldo;      // elements
   int out_col0; // column offset inside out rows
@@ -84,7 +87,8 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, int row
   for (int i = 0; i < 32; ++i) {
     float x = v[i] + (p.bias ? __ldg(p.bias + col + i) : 0.f);
     x *= p.scale;
-    if (p.relu) x = fmaxf(x, 0.f);
+    if (p.relu == 1) x = fmaxf(x, 0.f);
+    else if (p.relu == 2) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
     v[i] = x;
   }
   int orow = pass_to_canonical(row, p.map_mode, p.dims);
@@ -228,13 +232,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
       const int mt = tile / n_chunks;
       // source row pointers are K-block independent
       const __nv_bfloat16* rowp[ITERS];
+      int tstep[ITERS];
 #pragma unroll
       for (int i = 0; i < ITERS; ++i) {
         const int q = i * PT + ptid;
         const int r = mt * GEMM_BM + (q >> 3);
+        tstep[i] = 0;
         if (r < p.M) {
-          size_t ar = p.a_diag ? (size_t)r * p.a_F + (size_t)((r % p.a_N) / p.a_n) : (size_t)r;
+          size_t ar = (p.a_diag == 1) ? (size_t)r * p.a_F + (size_t)((r % p.a_N) / p.a_n) : (size_t)r;
           rowp[i] = p.A + ar * p.lda + (q & 7) * 8;
+          if (p.a_diag == 2) tstep[i] = (r / p.a_n) % p.a_N;
         } else {
           rowp[i] = nullptr;
         }
@@ -242,8 +249,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
       for (int kb = 0; kb < num_kb; ++kb) {
         uint4 v[ITERS];
 #pragma unroll
-        for (int i = 0; i < ITERS; ++i)
-          v[i] = rowp[i] ? ldg_nc_v4(rowp[i] + kb * GEMM_BK) : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < ITERS; ++i) {
+          if (p.a_diag == 2) {
+            int t2 = tstep[i] + ((kb >> 2) - 1) * p.a_F;
+            t2 = t2 < 0 ? 0 : (t2 >= p.a_N ? p.a_N - 1 : t2);
+            v[i] = rowp[i] ? ldg_nc_v4(rowp[i] + (ptrdiff_t)(t2 - tstep[i]) * p.a_n * p.lda + (kb & 3) * GEMM_BK) : make_uint4(0, 0, 0, 0);
+          } else {
+            v[i] = rowp[i] ? ldg_nc_v4(rowp[i] + kb * GEMM_BK) : make_uint4(0, 0, 0, 0);
+          }
+        }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* dst = smem + stage * GEMM_STAGE_BYTES;
 #pragma unroll

@@ -352,3 +352,113 @@ def profile_read() -> Dict[str, Dict[str, float]]:
     _lib.check(lib.axvs_profile_read(ms, fl, by, la, ti), "axvs_profile_read")
     return {lib.axvs_profile_class_name(i).decode(): dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(la[i]), timed=int(ti[i]))
             for i in range(n)}
+
+
+# ------------------------------------------------------------------------------------------------ cross-clip tail
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, 256] -> bf16 [rows, 256]."""
+    _check(x, "x", torch.float32)
+    rows = x.numel() // C
+    out = torch.empty(rows, C, dtype=torch.bfloat16, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.axvs_cast_bf16(x.data_ptr(), out.data_ptr(), rows, _stream(x.device)), "axvs_cast_bf16")
+    return out
+
+
+@dataclass
+class PackedAspp:
+    """struct axvs_aspp_weights (+ the tensors that keep the pointers alive)."""
+    w_conv: List[torch.Tensor]
+    b_conv: List[torch.Tensor]
+    dilation: List[int]
+    w_proj: torch.Tensor
+    lncf_g: torch.Tensor
+    lncf_b: torch.Tensor
+    ln_g: torch.Tensor
+    ln_b: torch.Tensor
+
+    def struct(self) -> "_lib.AsppWeights":
+        s = _lib.AsppWeights()
+        for i in range(3):
+            s.w_conv[i] = self.w_conv[i].data_ptr()
+            s.b_conv[i] = self.b_conv[i].data_ptr()
+            s.dilation[i] = int(self.dilation[i])
+        s.w_proj = self.w_proj.data_ptr()
+        s.lncf_g, s.lncf_b, s.ln_g, s.ln_b = (t.data_ptr() for t in (self.lncf_g, self.lncf_b, self.ln_g, self.ln_b))
+        return s
+
+
+def pack_aspp(p: Dict[str, torch.Tensor], ln_w: torch.Tensor, ln_b: torch.Tensor, atrous_rates: Sequence[int]) -> PackedAspp:
+    """Pack an `ASPP` state dict (CC:176-201) + the following `conv_norms[i]` LayerNorm."""
+    def g(name):
+        return p[name].detach().float().contiguous()
+
+    wc, bc = [], []
+    for i in range(3):
+        w = g(f"_aspp_conv{i}.weight")                                  # [256, 256, 3] (out, in, tap)
+        if w.shape[-1] != 3:
+            raise NotImplementedError("axial_vs_b200: ASPP kernel_size must be 3 (every shipped config)")
+        wc.append(pack_weight(w.permute(0, 2, 1).reshape(256, 768).contiguous()))   # K index = tap * 256 + c_in
+        bc.append(g(f"_aspp_conv{i}.bias"))
+    wproj = pack_weight(g("_proj_conv_bn_act.conv.weight")[:, :, 0].contiguous())   # [256, 768]
+    return PackedAspp(wc, bc, [int(r) for r in atrous_rates], wproj, g("_proj_conv_bn_act.norm.weight"), g("_proj_conv_bn_act.norm.bias"),
+                      ln_w.detach().float().contiguous(), ln_b.detach().float().contiguous())
+
+
+def cc_aspp_fwd(x: torch.Tensor, w: PackedAspp, b: int, T: int, Q: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """out = LN(GELU(LN_cf(proj(cat_d conv_d(z)))) + z) on rows (b, t, q); returns (fp32, bf16)."""
+    _check(x, "x", torch.float32)
+    rows = b * T * Q
+    if x.numel() != rows * C:
+        raise RuntimeError("cc_aspp_fwd: x size mismatch")
+    out = torch.empty(rows, C, dtype=torch.float32, device=x.device)
+    out16 = torch.empty(rows, C, dtype=torch.bfloat16, device=x.device)
+    lib = _lib.load()
+    nbytes = lib.axvs_cc_aspp_workspace_bytes(rows)
+    with torch.cuda.device(x.device):
+        ws = workspace(nbytes, x.device)
+        st = w.struct()
+        rc = lib.axvs_cc_aspp_fwd(x.data_ptr(), out.data_ptr(), out16.data_ptr(), ctypes.byref(st), b, T, Q, ws.data_ptr(), ws.numel(),
+                                  _stream(x.device))
+    _lib.check(rc, "axvs_cc_aspp_fwd")
+    return out, out16
+
+
+def linear_act(a: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], n_out: int, act: int,
+               out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """axvs_linear with activation code (0 none, 1 ReLU, 2 GELU)."""
+    _check(a, "a", torch.bfloat16)
+    M, K = a.shape
+    out = torch.empty(M, n_out, dtype=out_dtype, device=a.device)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        rc = lib.axvs_linear(a.data_ptr(), K, M, K, w_packed.data_ptr(), _ptr(bias), n_out, 1.0, int(act), out.data_ptr(), n_out,
+                             int(out_dtype == torch.bfloat16), None, _stream(a.device))
+    _lib.check(rc, "axvs_linear")
+    return out
+
+
+def cc_class_pool(ce: torch.Tensor, w_act: torch.Tensor, b_act: float, T: int, Q: int) -> torch.Tensor:
+    _check(ce, "ce", torch.bfloat16, (T * Q, C))
+    out = torch.empty(Q, C, dtype=torch.bfloat16, device=ce.device)
+    lib = _lib.load()
+    with torch.cuda.device(ce.device):
+        _lib.check(lib.axvs_cc_class_pool(ce.data_ptr(), w_act.data_ptr(), float(b_act), out.data_ptr(), T, Q, _stream(ce.device)),
+                   "axvs_cc_class_pool")
+    return out
+
+
+def mask_einsum(pixel: torch.Tensor, mk: torch.Tensor, T: int, Q: int, P: int, bn_scale: float, bn_shift: float) -> torch.Tensor:
+    """out[q, t, p] = bn_scale * sum_c pixel[t, c, p] mk[t*Q + q, c] + bn_shift; pixel fp32 [T, 128, P], mk bf16 [T*Q, ld >= 128]."""
+    _check(pixel, "pixel", torch.float32)
+    _check(mk, "mk", torch.bfloat16)
+    if pixel.numel() != T * 128 * P or mk.shape[0] != T * Q:
+        raise RuntimeError("mask_einsum: size mismatch")
+    out = torch.empty(Q, T, P, dtype=torch.float32, device=pixel.device)
+    lib = _lib.load()
+    with torch.cuda.device(pixel.device):
+        rc = lib.axvs_mask_einsum(pixel.data_ptr(), mk.data_ptr(), mk.shape[1], out.data_ptr(), T, Q, P, float(bn_scale), float(bn_shift),
+                                  _stream(pixel.device))
+    _lib.check(rc, "axvs_mask_einsum")
+    return out

@@ -95,6 +95,7 @@ typedef struct axvs_layer_weights {
 
 /* out[M, n_out] = act((A[M,K] @ W^T + bias) * scale) (+ resid), tcgen05 GEMM.  A bf16 row-major (lda elements).
  * out_bf16 != 0 -> bf16 output, else fp32 (+ optional fp32 residual with the same leading dimension).
+ * `relu`: 0 = no activation, 1 = ReLU, 2 = GELU (erf form).
  * Replaces every nn.Linear on the path (WC/temporal_attention.py:42-44,64-65,75,182). */
 int axvs_linear(const void* a_bf16, int lda, int M, int K, const void* w_packed, const float* bias, int n_out,
                 float scale, int relu, void* out, int ldo, int out_bf16, const float* resid, axvs_stream_t stream);
@@ -140,6 +141,35 @@ size_t axvs_layer_workspace_bytes(int B, int T, int H, int W, int d_ffn);
 int axvs_axial_layer_fwd(const float* src, const float* pos, float* out, const axvs_layer_weights* w,
                          int B, int T, int H, int W, int axial,
                          void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+
+/* ---- cross-clip module, after the trajectory attention (SURVEY.md section 8 rows A9 tail, A10) ------------------------------ */
+
+/* fp32 [rows,256] -> bf16 [rows,256] (A operand of axvs_linear). */
+int axvs_cast_bf16(const float* x, void* out_bf16, int rows, axvs_stream_t stream);
+
+/* Temporal ASPP + residual + LayerNorm of the cross-clip layer (CC:176-201, 293-295; TL cc head :929-947):
+ *   out = LN( GELU(LN_cf(proj(cat_d conv_d(z)))) + z ),  conv_d = Conv1d(256,256,k=3,dilation d,'same',replicate) over time.
+ * x / out fp32 [b*T*Q, 256] with rows ordered (b, t, q) (the trajectory attention's order); out_bf16 optional copy.
+ * Conv weights: packed with axvs_pack_weight as [256, 768] where K index = tap*256 + c_in. */
+typedef struct axvs_aspp_weights {
+  const void* w_conv[3];  const float* b_conv[3];  int dilation[3];
+  const void* w_proj;                              /* 1x1 conv [256, 768], no bias */
+  const float* lncf_g; const float* lncf_b;        /* channels-first LayerNorm, eps 1e-6 */
+  const float* ln_g;   const float* ln_b;          /* conv_norms[i], eps 1e-5 */
+} axvs_aspp_weights;
+size_t axvs_cc_aspp_workspace_bytes(int rows);
+int axvs_cc_aspp_fwd(const float* x, float* out, void* out_bf16, const axvs_aspp_weights* w, int b, int T, int Q,
+                     void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+
+/* MaXTronCCPredictor class branch (CC:47-50): logit = w_act . ce[t,q,:] + b_act, softmax over the T clips, pooled[q,:] =
+ * sum_t a[t,q] ce[t,q,:].  ce bf16 [T*Q, 256] rows (t, q); pooled bf16 [Q, 256]. */
+int axvs_cc_class_pool(const void* ce_bf16, const float* w_act, float b_act, void* pooled_bf16, int T, int Q, axvs_stream_t stream);
+
+/* Mask logits (CC:62-69): out[q, t, p] = bn_scale * sum_c pixel[t, c, p] * mk[t*Q + q, c] + bn_shift, c < 128, q < Q <= 128.
+ * pixel fp32 [T, 128, P] (P = V*H*W pixels of clip t), mk bf16 rows (t, q) with leading dimension ld_mk (elements),
+ * out fp32 [Q, T, P] == the reference's final [1, Q, (T V), H, W]. */
+int axvs_mask_einsum(const float* pixel, const void* mk_bf16, int ld_mk, float* out, int T, int Q, int P, float bn_scale,
+                     float bn_shift, axvs_stream_t stream);
 
 /* PositionEmbeddingSine3D(num_pos_feats=128, normalize=True) + level_embed_3d[lvl], channels-last
  * (WC/pos_embeddings.py:86-130, WC/msdeformattn.py:112-115).  out fp32 [B,T,H,W,256]; level_embed may be NULL. */

@@ -368,3 +368,45 @@ def test_level_plumbing(O):
     for i in range(2):
         parts[i], _, _ = O.temporal_encoder(parts[i].contiguous(), O.level_pos3d(B, T, *shapes[i], le[i]), O.split_encoder_params(p))
     assert nerr(out, torch.cat(parts, 1)) < TOL
+
+
+def test_cross_clip_module_golden(golden):
+    """Full CrossClipTrackingModule (trajectory attention + ASPP + projections + predictor) against the reference output."""
+    from axial_vs_b200 import cross_clip
+    gz = golden("cc_module")
+    Q, T, V, H, W, L, K, seed = (int(gz[k]) for k in "Q T V H W L K seed".split())
+    p = synth.cross_clip_params(seed, L, K)
+    m = cross_clip.CrossClipTrackingModule(num_layers=L, num_classes=K, attn_drop=0.0, aspp_drop=0.0, kernel_sizes=[3, 3, 3],
+                                           atrous_rates=[1, 2, 3], norm_fn="ln", num_clip_frames=V).eval()
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    cq = synth.randn(seed + 100, 1, Q, T, 256)
+    pf = synth.randn(seed + 200, 1, 128, T * V, H, W)
+    with torch.no_grad():
+        o = m(cq.cuda(), pf.cuda())
+    ref_logits, ref_masks = torch.from_numpy(gz["pred_logits"]), torch.from_numpy(gz["pred_masks"])
+    assert tuple(o["pred_logits"].shape) == tuple(ref_logits.shape) and tuple(o["pred_masks"].shape) == tuple(ref_masks.shape)
+    assert nerr(o["pred_logits"], ref_logits) < TOL
+    assert nerr(o["pred_masks"], ref_masks) < 2e-2          # bf16 pixel features x bf16 mask kernels, K = 128
+    agree = (o["pred_masks"].cpu().argmax(1) == ref_masks.argmax(1)).float().mean().item()
+    assert agree >= 0.97, agree                            # tiny random-init logits: near-ties dominate the disagreements
+    assert nerr(o["aux_outputs"][0]["pred_masks"], torch.from_numpy(gz["aux_masks"])) < 2e-2
+
+
+def test_cross_clip_module_oracle_cfg3_shard(O):
+    """cfg3-shaped shard: Q = 128 queries, 8 clips of 2 frames, 4 layers, 40x40 mask features."""
+    from axial_vs_b200 import cross_clip
+    Q, T, V, H, W, L, K, seed = 128, 8, 2, 40, 40, 4, 124, 909
+    p = synth.cross_clip_params(seed, L, K)
+    m = cross_clip.CrossClipTrackingModule(num_layers=L, num_classes=K, attn_drop=0.0, aspp_drop=0.0, kernel_sizes=[3, 3, 3],
+                                           atrous_rates=[1, 2, 3], norm_fn="ln", num_clip_frames=V).eval()
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    cq = synth.randn(seed + 1, 1, Q, T, 256)
+    pf = synth.randn(seed + 2, 1, 128, T * V, H, W)
+    ref = O.cross_clip_module(cq, pf, p, L, V)
+    with torch.no_grad():
+        o = m(cq.cuda(), pf.cuda())
+    assert nerr(o["pred_logits"], ref["pred_logits"]) < TOL
+    assert nerr(o["pred_masks"], ref["pred_masks"]) < 2e-2
+    assert nerr(m.last_clip_query, ref["clip_query"]) < TOL
