@@ -13,6 +13,7 @@
 #include "ffn_fused.cuh"
 #include "qkv_fused.cuh"
 #include "cc_tail.cuh"
+#include "ffn_pair.cuh"
 
 using namespace axvs;
 
@@ -35,6 +36,7 @@ const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel"
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel"};
 int g_fusion = 3;
+int g_pair = 0;   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
 struct Profiler {
@@ -74,6 +76,7 @@ struct DeviceInfo {
   bool qkv_attr = false;
   bool attn2_attr = false;
   bool mask_attr = false;
+  bool pair_attr = false;
 };
 DeviceInfo g_dev[64];
 
@@ -112,6 +115,11 @@ int device_info(DeviceInfo** out) {
         cudaFuncSetAttribute(spatial_attn_v2_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(spatial_attn_v2) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.attn2_attr = true;
+  }
+  if (!d.pair_attr) {
+    if (cudaFuncSetAttribute(ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_BYTES) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(ffn_pair) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    d.pair_attr = true;
   }
   if (!d.mask_attr) {
     if (cudaFuncSetAttribute(mask_einsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 256) != cudaSuccess)
@@ -240,6 +248,11 @@ int blocks_for(long long work_items, int per_block, int sms) {
 extern "C" {
 
 int axvs_version(void) { return 105; }
+int axvs_set_pair_mode(int on) {
+  const int prev = g_pair;
+  g_pair = on ? 1 : 0;
+  return prev;
+}
 int axvs_set_fusion(int level) {
   const int prev = g_fusion;
   g_fusion = level < 0 ? 0 : (level > 3 ? 3 : level);
@@ -526,7 +539,12 @@ int ffn_fused_launch(const uint8_t* s_img, const float* s32, float* out, const a
   fp.rows = rows; fp.tiles = (rows + 127) / 128; fp.d_ffn = w->d_ffn; fp.eps = 1e-5f;
   {
     ProfScope ps(KC_FFN, 4.0 * rows * 256.0 * w->d_ffn, (double)rows * 256 * 10.0, st);
-    ffn_fused_kernel<<<fp.tiles < d->sms ? fp.tiles : d->sms, FF_THREADS, FF_SMEM_BYTES, st>>>(fp);
+    if (g_pair) {
+      const int pair_tiles = (fp.tiles + 1) / 2, max_pairs = d->sms / 2;
+      ffn_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), FF_THREADS, FP_SMEM_BYTES, st>>>(fp);
+    } else {
+      ffn_fused_kernel<<<fp.tiles < d->sms ? fp.tiles : d->sms, FF_THREADS, FF_SMEM_BYTES, st>>>(fp);
+    }
   }
   AXVS_CHECK_LAUNCH("ffn_fused_kernel");
   return AXVS_OK;

@@ -258,3 +258,87 @@ __device__ __forceinline__ void umma_kblock(uint32_t tmem_d, uint32_t a_addr, ui
     umma_bf16(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc, (accumulate || k) ? 1u : 0u);
 }
 }  // namespace axvs
+
+namespace axvs {
+// ------------------------------------------------------------------ CTA pairs (cta_group::2), validated in tools/microbench/umma_2cta.cu
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// same, default (CTA-scope release) semantics: enough when the hand-off carries no generic-proxy data (e.g. "TMEM stage
+// drained", ordered by tcgen05.fence) -- a cluster-scope release makes the warp wait for all its earlier writes
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t cta) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// wait with acquire at cluster scope (arrivals may come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+#ifndef AXVS_NO_DEADLOCK_TRAP
+    if (++spins > (1u << 24)) __trap();
+#endif
+  }
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem, both CTAs] (+)= [A_cta0; A_cta1] (256 x 16) * [B_cta0; B_cta1]^T (N x 16); issued by the leader CTA only
+__device__ __forceinline__ void umma_bf16_lo_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(UMMA_DESC_HI), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit: arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// One weight unit for a CTA pair: each CTA holds HALF of the unit's rows as [2 K-blocks][64 rows x 128 B] (K-blocks 8 KiB
+// apart); 8 UMMAs with M = 256 (128 rows per CTA), N = 128.  Elected lane of a converged warp in the leader CTA.
+__device__ __forceinline__ void umma_unit_elect_pair(uint32_t tmem_d, uint32_t a0, uint32_t a1, uint32_t w, uint32_t idesc, bool accumulate,
+                                                     uint64_t* c0, uint64_t* c1, uint64_t* c2, uint64_t* c3) {
+  const uint32_t a0_lo = umma_desc_lo(a0), a1_lo = umma_desc_lo(a1), w_lo = umma_desc_lo(w);
+  if (elect_one()) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_lo_pair(tmem_d, a0_lo + 2 * k, w_lo + 2 * k, idesc, (accumulate || k) ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_lo_pair(tmem_d, a1_lo + 2 * k, w_lo + (8192 >> 4) + 2 * k, idesc, 1u);
+    if (c0) umma_commit_pair(c0);
+    if (c1) umma_commit_pair(c1);
+    if (c2) umma_commit_pair(c2);
+    if (c3) umma_commit_pair(c3);
+  }
+  __syncwarp();
+}
+}  // namespace axvs

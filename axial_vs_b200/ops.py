@@ -337,6 +337,11 @@ def set_fusion(level: int) -> int:
     return _lib.load().axvs_set_fusion(int(level))
 
 
+def set_pair_mode(on: bool) -> int:
+    """Enable / disable the CTA-pair (cta_group::2) FFN kernel (default off); returns the previous setting."""
+    return _lib.load().axvs_set_pair_mode(int(on))
+
+
 # ------------------------------------------------------------------------------------------------ measurement hooks
 def profile_enable(on: bool) -> None:
     """Reset the library's launch counters; with on=True every launch is bracketed by CUDA events (bench.py)."""

@@ -51,6 +51,9 @@ const char* axvs_last_error(void);
  *   3: + TMA-fed q|k|v projection with head-major output, one-shot per-frame attention writing UMMA tile images
  * Returns the previous level; values outside the range are clamped. */
 int axvs_set_fusion(int level);
+/* CTA-pair FFN kernel (tcgen05 cta_group::2, two SMs per M = 256 instruction stream) on/off.  Default OFF: it is validated
+ * and its UMMAs run at the full 64 clk rate, but the per-SM epilogue becomes the bottleneck (profiles/README.md).  Returns previous. */
+int axvs_set_pair_mode(int on);
 
 /* ---- weights ------------------------------------------------------------------------------------------------
  * nn.Linear weights [n_out, k] fp32 are converted once to bf16 and laid out as the shared-memory image the

@@ -410,3 +410,22 @@ def test_cross_clip_module_oracle_cfg3_shard(O):
     assert nerr(o["pred_logits"], ref["pred_logits"]) < TOL
     assert nerr(o["pred_masks"], ref["pred_masks"]) < 2e-2
     assert nerr(m.last_clip_query, ref["clip_query"]) < TOL
+
+
+def test_pair_mode_ffn_matches(ops, O):
+    """The cta_group::2 (CTA-pair) FFN kernel is opt-in; it must give the same result as the single-CTA kernel."""
+    p = synth.axial_layer_params(3)
+    pk = ops.pack_layer({k: v.cuda() for k, v in p.items()})
+    for rows in (100, 129, 5000):
+        x = synth.randn(5 + rows, rows, 256)
+        ref = O._ffn_tail(x, p)
+        outs = []
+        try:
+            for pair in (0, 1):
+                ops.set_pair_mode(pair)
+                outs.append(ops.ln_ffn_fwd(x.cuda(), pk))
+                torch.cuda.synchronize()
+        finally:
+            ops.set_pair_mode(0)
+        assert nerr(outs[0], ref) < TOL and nerr(outs[1], ref) < TOL
+        assert torch.equal(outs[0], outs[1])

@@ -26,6 +26,9 @@ lib.axvs_debug_read_waits(buf)
 v = list(buf)
 tiles = (rows + 127) // 128
 ctas = min(tiles, 148)
+if "--pair-ctas" in sys.argv:      # pair kernels: counters are flushed by the leader CTA of each pair only
+    ctas = min((tiles + 1) // 2, 74)
+    tiles = (tiles + 1) // 2
 print(f"{which}: rows {rows} tiles {tiles} time {e0.elapsed_time(e1):.3f} ms")
 def show(name, base, labels):
     tot = v[base + len(labels)] / ctas
