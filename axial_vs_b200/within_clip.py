@@ -20,6 +20,68 @@ def level_positions(pe: PositionEmbeddingSine3D, level_embed_3d: Tensor, B: int,
     return [pe.table(B, T, H, W, device, level_embed_3d[i]) for i, (H, W) in enumerate(shapes)]
 
 
+_level_streams = {}
+
+
+def run_levels_concurrent(temporal_layer, feats: Sequence[Tensor], pos_3d: Sequence[Tensor], clip_chunks: int = 1):
+    if clip_chunks > 1:
+        return _run_chunked(temporal_layer, feats, pos_3d, clip_chunks)
+    return _run_levels(temporal_layer, feats, pos_3d)
+
+
+def _run_chunked(temporal_layer, feats: Sequence[Tensor], pos_3d: Sequence[Tensor], clip_chunks: int):
+    """Clips are independent too: split every level's batch into `clip_chunks` groups and give each (level, group) its own
+    stream, so that memory-bound and tensor-bound kernels of different groups overlap on the GPU."""
+    tasks_f, tasks_p, owner = [], [], []
+    for li, (f, p) in enumerate(zip(feats, pos_3d)):
+        B, T = p.shape[0], p.shape[1]
+        n = min(clip_chunks, B)
+        bounds = [(B * k) // n for k in range(n + 1)]
+        for k in range(n):
+            b0, b1 = bounds[k], bounds[k + 1]
+            tasks_f.append(f[b0 * T:b1 * T])
+            tasks_p.append(p[b0:b1])
+            owner.append(li)
+    outs = _run_levels(temporal_layer, tasks_f, tasks_p)
+    merged = []
+    for li in range(len(feats)):
+        parts = [o for o, ow in zip(outs, owner) if ow == li]
+        merged.append((torch.cat([q[0] for q in parts], 0), parts[-1][1], parts[-1][2]))
+    return merged
+
+
+def _run_levels(temporal_layer, feats: Sequence[Tensor], pos_3d: Sequence[Tensor]):
+    """Run the SAME temporal layer on several pyramid levels (WC/msdeformattn.py:261-263), one CUDA stream per level.
+
+    The levels are independent, and each level is a chain of persistent one-CTA-per-SM kernels whose last wave leaves SMs
+    idle (res5 at 32 clips: 221 tiles on 148 SMs); with one stream per level the block scheduler fills those SMs with the
+    other level's CTAs.  Returns a list of (features, h_map, w_map) tuples in level order; the calling stream waits for all."""
+    if len(feats) == 1:
+        return [temporal_layer(src=feats[0], pos=pos_3d[0])]
+    dev = feats[0].device
+    cur = torch.cuda.current_stream(dev)
+    key = (dev.index, len(feats))
+    if key not in _level_streams:
+        _level_streams[key] = [torch.cuda.Stream(dev) for _ in range(len(feats) - 1)]
+    streams = [cur] + _level_streams[key]
+    start = torch.cuda.Event()
+    start.record(cur)
+    outs = []
+    for st, f, p in zip(streams, feats, pos_3d):
+        if st is not cur:
+            st.wait_event(start)
+        with torch.cuda.stream(st):
+            o = temporal_layer(src=f, pos=p)
+            outs.append(o)
+            if st is not cur:
+                for t in o:
+                    if isinstance(t, torch.Tensor):
+                        t.record_stream(cur)
+    for st in streams[1:]:
+        cur.wait_stream(st)
+    return outs
+
+
 def run_temporal_levels(temporal_layer, memory: Tensor, spatial_shapes: Sequence[Tuple[int, int]], pos_3d: Sequence[Tensor],
                         num_temporal_levels: int):
     """memory [B*T, sum(H_l*W_l), C] -> same shape; returns (memory, height_traj_attn, width_traj_attn) like the reference."""
