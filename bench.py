@@ -218,10 +218,10 @@ def main():
     from axial_vs_b200 import within_clip
 
     @torch.no_grad()
-    def hot_path(srcs):
+    def hot_path(srcs, concurrent=True):
         cur = list(srcs)
         for enc in encoders:                       # the same TemporalEncoder object serves both levels (WC/msdeformattn.py:261-263)
-            if args.level_streams:
+            if args.level_streams and concurrent:
                 outs = within_clip.run_levels_concurrent(enc, cur, pos, args.clip_chunks)    # independent levels / clip groups: one stream each
                 cur = [o[0] for o in outs]
             else:
@@ -336,11 +336,13 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline leg: the same steps with CUDA events around every kernel launch (separate pass, not the `value` timing)
+    # (levels run serially here: with one stream per level the kernels of the two levels overlap and per-launch event times
+    # would include each other)
     ops.profile_enable(True)
     prof_steps = min(args.steps, 5)
     barrier()
     for k in range(prof_steps):
-        step_resident(k)
+        hot_path(dev_in[k & 1], concurrent=False)
     barrier()
     prof = ops.profile_read()
     ops.profile_enable(False)
@@ -360,14 +362,23 @@ def main():
                        "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
                    for k, v in prof.items() if v["timed"]}
         achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["flops"] > 0 else dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
-        tensor_bound = dom["flops"] > 0 and dom_name in ("gemm_bf16_kernel", "spatial_attn_kernel")
+        tensor_bound = dom["flops"] > 0 and dom_name in ("gemm_bf16_kernel", "spatial_attn_kernel", "spatial_attn_v2_kernel", "traj_fused_kernel",
+                                                          "ffn_fused_kernel", "qkv_fused_kernel")
         peak = peaks["tf_sustained"] if tensor_bound else peaks["hbm"]
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                traffic = json.load(f).get(dom_name, {}).get("bytes_per_launch")
+        except Exception:
+            pass
         roofline = {"kernel": dom_name, "bound": "tensor" if tensor_bound else "hbm", "achieved": round(achieved, 2), "peak": peak,
-                    "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                    "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                    "traffic_note": "DRAM read+write bytes per launch of this kernel from the committed ncu --set full capture (profiles/r01_traffic.json)",
                     "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}; sustained bf16 figure: kernel timed inside a long step)",
                     "avg_launch_ms": round(dom["ms"] / max(dom["timed"], 1), 5),
                     "step_tflops": round(flops_per_clip() * clips / (ms_total / args.steps * 1e-3) / 1e12, 2),
                     "step_frac_of_tensor_peak": round(flops_per_clip() * clips / (ms_total / args.steps * 1e-3) / 1e12 / peaks["tf_sustained"], 4),
+                    "note": "per-kernel times from a separate pass with CUDA events around every launch, pyramid levels run serially",
                     "kernels": kernels}
         line = {"metric": METRIC, "value": round(value, 2), "unit": "clips/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
