@@ -13,6 +13,7 @@
 #include "ffn_fused.cuh"
 #include "qkv_fused.cuh"
 #include "cc_tail.cuh"
+#include "decoder_attn.cuh"
 #include "ffn_pair.cuh"
 
 using namespace axvs;
@@ -30,11 +31,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
-                                            "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel"};
+                                            "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
+                                            "kmeans_update_kernels"};
 int g_fusion = 3;
 int g_pair = 0;   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
@@ -77,6 +79,7 @@ struct DeviceInfo {
   bool attn2_attr = false;
   bool mask_attr = false;
   bool pair_attr = false;
+  bool dec_attr = false;
 };
 DeviceInfo g_dev[64];
 
@@ -125,6 +128,12 @@ int device_info(DeviceInfo** out) {
     if (cudaFuncSetAttribute(mask_einsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 256) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(mask_einsum) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.mask_attr = true;
+  }
+  if (!d.dec_attr) {
+    if (cudaFuncSetAttribute(kmeans_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(query_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(decoder attention) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    d.dec_attr = true;
   }
   if (!d.ffn_attr) {
     if (cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES) != cudaSuccess)
@@ -247,7 +256,7 @@ int blocks_for(long long work_items, int per_block, int sms) {
 
 extern "C" {
 
-int axvs_version(void) { return 105; }
+int axvs_version(void) { return 106; }
 int axvs_set_pair_mode(int on) {
   const int prev = g_pair;
   g_pair = on ? 1 : 0;
@@ -772,6 +781,63 @@ int axvs_mask_einsum(const float* pixel, const void* mk_bf16, int ld_mk, float* 
                                                                           bn_shift);
   }
   AXVS_CHECK_LAUNCH("mask_einsum_kernel");
+  return AXVS_OK;
+}
+
+int axvs_query_self_attn(const float* q, const float* k, const float* v, const float* sim_affine, const float* val_affine, float* out, int N,
+                         int heads, int L, axvs_stream_t stream) {
+  if (!q || !k || !v || !sim_affine || !val_affine || !out) return fail(AXVS_E_INVALID, "query_self_attn: null pointer");
+  if (N <= 0 || heads <= 0 || L <= 0) return fail(AXVS_E_INVALID, "query_self_attn: sizes must be positive");
+  if (N > 65535) return fail(AXVS_E_UNSUPPORTED, "query_self_attn: at most 65535 clips per call");
+  const size_t smem = (size_t)(QSA_DK + QSA_DV) * L * sizeof(float);
+  if (smem > 200 * 1024) return fail(AXVS_E_UNSUPPORTED, "query_self_attn: at most %d queries (got %d)", 200 * 1024 / ((QSA_DK + QSA_DV) * 4), L);
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  {
+    ProfScope ps(KC_QSA, 2.0 * N * heads * (double)L * L * (QSA_DK + QSA_DV), 4.0 * N * heads * L * (2.0 * QSA_DK + 2.0 * QSA_DV), (cudaStream_t)stream);
+    query_self_attn_kernel<<<dim3(heads, N), 128, smem, (cudaStream_t)stream>>>(q, k, v, sim_affine, val_affine, out, heads, L);
+  }
+  AXVS_CHECK_LAUNCH("query_self_attn_kernel");
+  return AXVS_OK;
+}
+
+static int kmeans_chunks(int N, int M) {   // pixel chunks per clip: about two waves of CTAs over the 148 SMs
+  const int tiles = (M + KM_PT - 1) / KM_PT;
+  int chunks = (2 * 148 + N - 1) / N;
+  if (chunks < 1) chunks = 1;
+  if (chunks > tiles) chunks = tiles;
+  if (chunks > 65535) chunks = 65535;
+  return chunks;
+}
+
+size_t axvs_kmeans_update_workspace_bytes(int N, int L, int M) {
+  if (N <= 0 || L <= 0 || M <= 0) return 0;
+  const int chunks = kmeans_chunks(N, M);
+  return (size_t)N * chunks * L * (KM_D + 1) * sizeof(float) + 256;
+}
+
+int axvs_kmeans_update(const float* mask_logits, const float* pixel_value, float* out, int* assign, int N, int L, int M, int advanced,
+                       void* workspace, size_t workspace_bytes, axvs_stream_t stream) {
+  if (!mask_logits || !pixel_value || !out) return fail(AXVS_E_INVALID, "kmeans_update: null pointer");
+  if (N <= 0 || L <= 0 || M <= 0) return fail(AXVS_E_INVALID, "kmeans_update: sizes must be positive");
+  if (L > KM_LMAX) return fail(AXVS_E_UNSUPPORTED, "kmeans_update: at most %d cluster centres (got %d)", KM_LMAX, L);
+  if (N > 65535) return fail(AXVS_E_UNSUPPORTED, "kmeans_update: at most 65535 clips per call");
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  const int chunks = kmeans_chunks(N, M);
+  const size_t need = (size_t)N * chunks * L * (KM_D + 1) * sizeof(float) + 256;
+  if (!workspace || workspace_bytes < need) return fail(AXVS_E_WORKSPACE, "kmeans_update: workspace of %zu bytes required (got %zu)", need, workspace_bytes);
+  const int tiles = (M + KM_PT - 1) / KM_PT;
+  const int chunk_pixels = ((tiles + chunks - 1) / chunks) * KM_PT;
+  float* partial = reinterpret_cast<float*>(workspace);
+  int* counts = reinterpret_cast<int*>(partial + (size_t)N * chunks * L * KM_D);
+  {
+    ProfScope ps(KC_KMEANS, 2.0 * N * (double)M * KM_D, 4.0 * N * (double)M * (L + KM_D), (cudaStream_t)stream);
+    kmeans_partial_kernel<<<dim3(chunks, N), 256, KM_SMEM_BYTES, (cudaStream_t)stream>>>(mask_logits, pixel_value, partial, counts, assign, L, M,
+                                                                                       chunk_pixels);
+    kmeans_reduce_kernel<<<dim3(KM_D / 32, (L + 31) / 32, N), 256, 0, (cudaStream_t)stream>>>(partial, counts, out, chunks, L, advanced ? 1 : 0);
+  }
+  AXVS_CHECK_LAUNCH("kmeans_update kernels");
   return AXVS_OK;
 }
 

@@ -454,6 +454,48 @@ def cc_class_pool(ce: torch.Tensor, w_act: torch.Tensor, b_act: float, T: int, Q
     return out
 
 
+def query_self_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, sim_affine: torch.Tensor, val_affine: torch.Tensor) -> torch.Tensor:
+    """AttentionOperation core: q, k fp32 [N, heads, 16, L], v fp32 [N, heads, 32, L] -> GELU(BN(softmax(BN(q.k)) v)) fp32 [N, heads*32, L]."""
+    for t, nm in ((q, "query"), (k, "key"), (v, "value"), (sim_affine, "sim_affine"), (val_affine, "val_affine")):
+        _check(t, nm, torch.float32)
+    if q.dim() != 4 or q.shape != k.shape or v.dim() != 4 or v.shape[:2] != q.shape[:2] or v.shape[3] != q.shape[3]:
+        raise RuntimeError("query_self_attn: expected query/key [N, heads, dk, L] and value [N, heads, dv, L]")
+    N, heads, dk, L = q.shape
+    if dk != 16 or v.shape[2] != 32:
+        raise RuntimeError(f"query_self_attn: built for key depth 16 and value depth 32 per head (got {dk}, {v.shape[2]})")
+    if sim_affine.numel() != 2 * heads or val_affine.numel() != 2 * heads * 32:
+        raise RuntimeError("query_self_attn: folded BatchNorm sizes do not match the number of heads")
+    out = torch.empty(N, heads * 32, L, dtype=torch.float32, device=q.device)
+    lib = _lib.load()
+    with torch.cuda.device(q.device):
+        rc = lib.axvs_query_self_attn(q.data_ptr(), k.data_ptr(), v.data_ptr(), sim_affine.data_ptr(), val_affine.data_ptr(), out.data_ptr(),
+                                      N, heads, L, _stream(q.device))
+    _lib.check(rc, "axvs_query_self_attn")
+    return out
+
+
+def kmeans_update(mask_logits: torch.Tensor, pixel_value: torch.Tensor, advanced: bool = False,
+                  return_assignment: bool = False):
+    """k-means cluster update: mask_logits fp32 [N, L, M], pixel_value fp32 [N, 256, M] -> fp32 [N, 256, L] (and int32 [N, M])."""
+    _check(mask_logits, "mask_logits", torch.float32)
+    _check(pixel_value, "pixel_value", torch.float32)
+    if mask_logits.dim() != 3 or pixel_value.dim() != 3 or pixel_value.shape[0] != mask_logits.shape[0] or \
+            pixel_value.shape[2] != mask_logits.shape[2] or pixel_value.shape[1] != C:
+        raise RuntimeError("kmeans_update: expected mask_logits [N, L, M] and pixel_value [N, 256, M]")
+    N, L, M = mask_logits.shape
+    out = torch.empty(N, C, L, dtype=torch.float32, device=mask_logits.device)
+    assign = torch.empty(N, M, dtype=torch.int32, device=mask_logits.device) if return_assignment else None
+    lib = _lib.load()
+    nbytes = lib.axvs_kmeans_update_workspace_bytes(N, L, M)
+    with torch.cuda.device(mask_logits.device):
+        ws = workspace(nbytes, mask_logits.device)
+        rc = lib.axvs_kmeans_update(mask_logits.data_ptr(), pixel_value.data_ptr(), out.data_ptr(),
+                                    assign.data_ptr() if assign is not None else None, N, L, M, int(bool(advanced)),
+                                    ws.data_ptr(), ws.numel(), _stream(mask_logits.device))
+    _lib.check(rc, "axvs_kmeans_update")
+    return (out, assign) if return_assignment else out
+
+
 def mask_einsum(pixel: torch.Tensor, mk: torch.Tensor, T: int, Q: int, P: int, bn_scale: float, bn_shift: float) -> torch.Tensor:
     """out[q, t, p] = bn_scale * sum_c pixel[t, c, p] mk[t*Q + q, c] + bn_shift; pixel fp32 [T, 128, P], mk bf16 [T*Q, ld >= 128]."""
     _check(pixel, "pixel", torch.float32)

@@ -174,6 +174,24 @@ int axvs_cc_class_pool(const void* ce_bf16, const float* w_act, float b_act, voi
 int axvs_mask_einsum(const float* pixel, const void* mk_bf16, int ld_mk, float* out, int T, int Q, int P, float bn_scale,
                      float bn_shift, axvs_stream_t stream);
 
+/* ---- clip-level kMaX decoder attention, query side ----------------------------------------
+ * DEC = Vk/maxtron_deeplab/modeling/transformer_decoder/maxtron_transformer_decoder.py
+ *
+ * AttentionOperation.forward (DEC:49-71) in eval mode: logits = einsum('bhdl,bhdm->bhlm', q, k), per-head BatchNorm on the logits,
+ * fp32 softmax over m, retrieved = einsum('bhlm,bhdm->bhdl'), per-channel BatchNorm, GELU.  All fp32.
+ * q, k [N, heads*16, L]; v, out [N, heads*32, L] (channel = head*depth + d, DEC:215-217).  sim_affine [heads][2] and
+ * val_affine [heads*32][2] are the folded eval-mode BN (scale = w / sqrt(var + eps), shift = b - mean*scale). */
+int axvs_query_self_attn(const float* q, const float* k, const float* v, const float* sim_affine, const float* val_affine, float* out,
+                         int N, int heads, int L, axvs_stream_t stream);
+
+/* k-means cross-attention update (DEC:196-208): assign[n, m] = argmax_l mask_logits[n, l, m] (first maximum),
+ * out[n, d, l] = sum over the pixels assigned to l of pixel_value[n, d, m]; divided by max(count, 1) when advanced != 0
+ * (advanced_kmax, DEC:206-208).  mask_logits fp32 [N, L, M], pixel_value fp32 [N, 256, M], out fp32 [N, 256, L], L <= 128;
+ * assign (int32 [N, M]) may be NULL.  Deterministic (no floating-point atomics). */
+size_t axvs_kmeans_update_workspace_bytes(int N, int L, int M);
+int axvs_kmeans_update(const float* mask_logits, const float* pixel_value, float* out, int* assign, int N, int L, int M, int advanced,
+                       void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+
 /* PositionEmbeddingSine3D(num_pos_feats=128, normalize=True) + level_embed_3d[lvl], channels-last
  * (WC/pos_embeddings.py:86-130, WC/msdeformattn.py:112-115).  out fp32 [B,T,H,W,256]; level_embed may be NULL. */
 int axvs_pos3d(float* out, const float* level_embed, int B, int T, int H, int W, axvs_stream_t stream);

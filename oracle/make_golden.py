@@ -114,6 +114,36 @@ def main():
          pred_masks=o["pred_masks"], aux_masks=o["aux_outputs"][0]["pred_masks"], wsum=synth.checksum(p))
 
 
+    # ---- 5. clip-level decoder attention (row A11): tensors captured inside the reference kMaXTransformerLayer ---------
+    DEC = sys.modules["maxtron_deeplab.modeling.transformer_decoder.maxtron_transformer_decoder"]
+    for tag, (N, L, Cp, TH, Wd, seed) in {"a": (2, 128, 64, 10, 7, 71), "b": (1, 37, 32, 6, 5, 72)}.items():
+        torch.manual_seed(seed)
+        layer = DEC.kMaXTransformerLayer(num_classes=20, in_channel_pixel=Cp, in_channel_query=256, base_filters=128, num_heads=8,
+                                         bottleneck_expansion=2, key_expansion=1, value_expansion=2).eval()
+        g = torch.Generator().manual_seed(seed)
+        for m in layer.modules():                       # non-trivial BN statistics and affine (norm_init=0 would zero the updates)
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                m.weight.copy_(1.0 + 0.2 * torch.randn(m.weight.shape, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(1.0 + 0.3 * torch.rand(m.running_var.shape, generator=g))
+        cap = {}
+        hooks = [
+            layer._query_self_attention.register_forward_hook(lambda mod, i, o: cap.update(q=i[0], k=i[1], v=i[2], attn_out=o)),
+            layer._pixel_v_conv_bn.register_forward_hook(lambda mod, i, o: cap.update(pixel_value=o.flatten(2))),
+            layer._predictor.register_forward_hook(lambda mod, i, o: cap.update(mask_logits=o["mask_logits"].flatten(2))),
+            layer._kmeans_query_batch_norm_retrieved_value.register_forward_hook(lambda mod, i, o: cap.update(kmeans_update=i[0])),
+        ]
+        layer(synth.randn(seed + 100, N, Cp, TH, Wd), synth.randn(seed + 200, N, 256, L))
+        for h in hooks:
+            h.remove()
+        ao = layer._query_self_attention
+        bn = {f"{nm}.{k}": v for nm in ("_batch_norm_similarity", "_batch_norm_retrieved_value")
+              for k, v in getattr(ao, nm).state_dict().items()}
+        save(f"decoder_attn_{tag}", N=N, L=L, seed=seed, **{k: v for k, v in cap.items()},
+             **{"bn." + k: v for k, v in bn.items()})
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found; golden fixtures can only be generated where it is mounted")

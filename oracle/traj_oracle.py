@@ -386,6 +386,34 @@ def cross_clip_module(clip_query: Tensor, panoptic_features: Tensor, p: Params, 
 # --------------------------------------------------------------------------------------------
 # algorithmic work -- shared by bench.py and the tests
 # --------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------ clip-level decoder attention (row A11)
+# DEC = Vk/maxtron_deeplab/modeling/transformer_decoder/maxtron_transformer_decoder.py
+def query_self_attention(q: Tensor, k: Tensor, v: Tensor, p: Params) -> Tensor:
+    """AttentionOperation.forward, eval mode -- DEC:56-71.  q, k [N,h,dk,L]; v [N,h,dv,L] -> [N, h*dv, L]."""
+    N, h, dv, L = v.shape
+    sim = torch.einsum("bhdl,bhdm->bhlm", q, k)                                   # :58
+    sim = batch_norm_eval(sim, p, "_batch_norm_similarity")                       # :59  (per-head BN on the logits)
+    w = torch.softmax(sim, dim=-1)                                                # :61-62
+    r = torch.einsum("bhlm,bhdm->bhdl", w, v).reshape(N, h * dv, L)               # :63-65
+    r = batch_norm_eval(r, p, "_batch_norm_retrieved_value")                      # :66-67
+    return gelu(r)                                                                # :68
+
+
+def kmeans_update(mask_logits: Tensor, pixel_value: Tensor, advanced: bool = False):
+    """k-means assignment + update of kMaXTransformerLayer.forward -- DEC:196-208.
+
+    mask_logits [N, L, M], pixel_value [N, D, M] -> (update [N, D, L], assignment [N, M]).  The assignment is the first
+    maximum over the L cluster centres (torch.max semantics on CPU).
+    """
+    N, L, M = mask_logits.shape
+    index = mask_logits.max(1, keepdim=True)[1]                                   # :199
+    onehot = torch.zeros_like(mask_logits).scatter_(1, index, 1.0)                # :200
+    upd = torch.einsum("blm,bdm->bdl", onehot, pixel_value)                       # :204
+    if advanced:
+        upd = upd / torch.clamp(onehot.sum(-1).unsqueeze(1), min=1.0)             # :206-208
+    return upd, index[:, 0]
+
+
 def flops_trajectory_attention(Bp: int, N: int, F: int, C: int = 256) -> int:
     return Bp * N * C * (10 * C + 4 * F * C + 4 * N + 4 * F)
 

@@ -429,3 +429,61 @@ def test_pair_mode_ffn_matches(ops, O):
             ops.set_pair_mode(0)
         assert nerr(outs[0], ref) < TOL and nerr(outs[1], ref) < TOL
         assert torch.equal(outs[0], outs[1])
+
+
+# --------------------------------------------------------------------------------------------- clip-level decoder attention (A11)
+def _bn_module_state(gz, name):
+    return {k[len("bn." + name) + 1:]: torch.as_tensor(gz[k]) for k in gz.files if k.startswith("bn." + name + ".")}
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_decoder_attention_golden(golden, tag):
+    from axial_vs_b200.decoder_attn import AttentionOperation, kmeans_cluster_update
+    gz = golden(f"decoder_attn_{tag}")
+    t = lambda k: torch.as_tensor(gz[k]).cuda()
+    m = AttentionOperation(channels_v=256, num_heads=8).eval()
+    sd = {f"{nm}.{k}": v for nm in ("_batch_norm_similarity", "_batch_norm_retrieved_value") for k, v in _bn_module_state(gz, nm).items()}
+    m.load_state_dict(sd, strict=True)
+    out = m.cuda()(t("q"), t("k"), t("v"))
+    assert nerr(out, torch.as_tensor(gz["attn_out"])) < 1e-5          # fp32 kernel against the fp32 reference
+    upd, idx = kmeans_cluster_update(t("mask_logits"), t("pixel_value"), return_assignment=True)
+    assert torch.equal(idx.cpu().long(), torch.as_tensor(gz["mask_logits"]).argmax(1))       # index work: bit-exact
+    assert nerr(upd, torch.as_tensor(gz["kmeans_update"])) < 1e-5
+
+
+@pytest.mark.parametrize("N,L,M,advanced", [(3, 128, 3362, False), (2, 128, 13122, True), (5, 100, 882, False), (1, 7, 63, True),
+                                            (32, 128, 3362, False)])
+def test_kmeans_update_oracle(ops, O, N, L, M, advanced):
+    g = torch.Generator().manual_seed(N * 1000 + L + M)
+    logits = torch.randn(N, L, M, generator=g)
+    logits[:, :, ::5] = logits[:, :, ::5].round()           # exact ties between cluster centres: first maximum must win
+    logits[0, :, 1] = 0.25                                   # a pixel whose logits are all equal -> cluster 0
+    pv = torch.randn(N, 256, M, generator=g)
+    ref, ridx = O.kmeans_update(logits.double(), pv.double(), advanced)
+    out, idx = ops.kmeans_update(logits.cuda(), pv.cuda(), advanced=advanced, return_assignment=True)
+    assert torch.equal(idx.cpu().long(), ridx)
+    assert nerr(out, ref.float()) < 2e-6
+    # determinism and a size-independent property: without the division the update sums to the per-channel pixel total
+    out2 = ops.kmeans_update(logits.cuda(), pv.cuda(), advanced=advanced)
+    assert torch.equal(out, out2)
+    if not advanced:
+        assert torch.allclose(out.sum(-1).cpu().double(), pv.double().sum(-1), atol=1e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize("N,L", [(1, 128), (4, 100), (2, 1), (3, 333)])
+def test_query_self_attention_oracle(ops, O, N, L):
+    g = torch.Generator().manual_seed(N + L)
+    q, k = torch.randn(N, 8, 16, L, generator=g), torch.randn(N, 8, 16, L, generator=g)
+    v = torch.randn(N, 8, 32, L, generator=g)
+    bn = {}
+    for nm, n in (("_batch_norm_similarity", 8), ("_batch_norm_retrieved_value", 256)):
+        bn[nm + ".weight"] = 1.0 + 0.2 * torch.randn(n, generator=g)
+        bn[nm + ".bias"] = 0.1 * torch.randn(n, generator=g)
+        bn[nm + ".running_mean"] = 0.1 * torch.randn(n, generator=g)
+        bn[nm + ".running_var"] = 1.0 + 0.3 * torch.rand(n, generator=g)
+    ref = O.query_self_attention(q.double(), k.double(), v.double(), bn).float()
+    fold = lambda nm: torch.stack([bn[nm + ".weight"] / torch.sqrt(bn[nm + ".running_var"] + 1e-3),
+                                   bn[nm + ".bias"] - bn[nm + ".running_mean"] * bn[nm + ".weight"] / torch.sqrt(bn[nm + ".running_var"] + 1e-3)], 1)
+    out = ops.query_self_attn(q.cuda(), k.cuda(), v.cuda(), fold("_batch_norm_similarity").contiguous().cuda(),
+                              fold("_batch_norm_retrieved_value").contiguous().cuda())
+    assert nerr(out, ref) < 1e-5

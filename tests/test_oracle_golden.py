@@ -109,3 +109,15 @@ def test_flop_formulas_match_baseline_md():
     assert abs(O.flops_axial_layer(1, 2, 41, 41) / 1e9 - 12.04) < 0.01
     assert abs(O.flops_axial_layer(1, 2, 21, 21) / 1e9 - 3.09) < 0.01
     assert abs(O.flops_axial_layer(1, 10, 161, 161) / 1e9 - 2830.56) < 0.1
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_decoder_attention(golden, tag):
+    """Row A11: AttentionOperation and the k-means update against tensors captured inside the reference kMaXTransformerLayer."""
+    gz = golden(f"decoder_attn_{tag}")
+    bn = {k[3:]: torch.as_tensor(gz[k]) for k in gz.files if k.startswith("bn.")}
+    t = lambda k: torch.as_tensor(gz[k])
+    _close(O.query_self_attention(t("q"), t("k"), t("v"), bn), gz["attn_out"])
+    upd, idx = O.kmeans_update(t("mask_logits"), t("pixel_value"))
+    _close(upd, gz["kmeans_update"])
+    assert torch.equal(idx, t("mask_logits").argmax(1))
