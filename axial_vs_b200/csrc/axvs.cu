@@ -130,7 +130,8 @@ int device_info(DeviceInfo** out) {
     d.mask_attr = true;
   }
   if (!d.dec_attr) {
-    if (cudaFuncSetAttribute(kmeans_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_SMEM_BYTES) != cudaSuccess ||
+    if (cudaFuncSetAttribute(kmeans_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(kmeans_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(query_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(decoder attention) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.dec_attr = true;
@@ -803,7 +804,7 @@ int axvs_query_self_attn(const float* q, const float* k, const float* v, const f
 
 static int kmeans_chunks(int N, int M) {   // pixel chunks per clip: about two waves of CTAs over the 148 SMs
   const int tiles = (M + KM_PT - 1) / KM_PT;
-  int chunks = (2 * 148 + N - 1) / N;
+  int chunks = (2 * 148) / N;
   if (chunks < 1) chunks = 1;
   if (chunks > tiles) chunks = tiles;
   if (chunks > 65535) chunks = 65535;
@@ -833,8 +834,13 @@ int axvs_kmeans_update(const float* mask_logits, const float* pixel_value, float
   int* counts = reinterpret_cast<int*>(partial + (size_t)N * chunks * L * KM_D);
   {
     ProfScope ps(KC_KMEANS, 2.0 * N * (double)M * KM_D, 4.0 * N * (double)M * (L + KM_D), (cudaStream_t)stream);
-    kmeans_partial_kernel<<<dim3(chunks, N), 256, KM_SMEM_BYTES, (cudaStream_t)stream>>>(mask_logits, pixel_value, partial, counts, assign, L, M,
-                                                                                       chunk_pixels);
+    const bool vec = (M % 2 == 0) && (reinterpret_cast<uintptr_t>(mask_logits) % 8 == 0) && (reinterpret_cast<uintptr_t>(pixel_value) % 8 == 0);
+    if (vec)
+      kmeans_partial_kernel<true><<<dim3(chunks, N), KM_THREADS, KM_SMEM_BYTES, (cudaStream_t)stream>>>(mask_logits, pixel_value, partial, counts,
+                                                                                                         assign, L, M, chunk_pixels);
+    else
+      kmeans_partial_kernel<false><<<dim3(chunks, N), KM_THREADS, KM_SMEM_BYTES, (cudaStream_t)stream>>>(mask_logits, pixel_value, partial, counts,
+                                                                                                          assign, L, M, chunk_pixels);
     kmeans_reduce_kernel<<<dim3(KM_D / 32, (L + 31) / 32, N), 256, 0, (cudaStream_t)stream>>>(partial, counts, out, chunks, L, advanced ? 1 : 0);
   }
   AXVS_CHECK_LAUNCH("kmeans_update kernels");
