@@ -12,6 +12,7 @@
 #include "traj_fused.cuh"
 #include "ffn_fused.cuh"
 #include "qkv_fused.cuh"
+#include "qkv_direct.cuh"
 #include "cc_tail.cuh"
 #include "decoder_attn.cuh"
 #include "ffn_pair.cuh"
@@ -31,13 +32,13 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels"};
-int g_fusion = 3;
+                                            "kmeans_update_kernels", "qkv_direct_kernel"};
+int g_fusion = 4;
 int g_pair = 0;   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
@@ -104,7 +105,8 @@ int device_info(DeviceInfo** out) {
     d.traj_attr = true;
   }
   if (!d.qkv_attr) {
-    if (cudaFuncSetAttribute(qkv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QK_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(qkv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QK_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(qkv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QK_SMEM_BYTES) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(qkv_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.qkv_attr = true;
   }
@@ -265,7 +267,7 @@ int axvs_set_pair_mode(int on) {
 }
 int axvs_set_fusion(int level) {
   const int prev = g_fusion;
-  g_fusion = level < 0 ? 0 : (level > 3 ? 3 : level);
+  g_fusion = level < 0 ? 0 : (level > 4 ? 4 : level);
   return prev;
 }
 const char* axvs_last_error(void) { return g_err; }
@@ -364,6 +366,19 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
   if (g_fusion >= 3 && k_in == q_in && w->w_qkv_u && w->w_pq_u && w->w_pkv_u && w->w_proj_u && num_seq <= (1 << 27)) {
     // ---- fused front end: tile-image pack -> TMA-fed q|k|v GEMM (head-major) -> one-shot attention writing tile images
     const int tiles = (int)((rows + 127) / 128);
+    if (g_fusion >= 4) {
+      // the q|k|v GEMM reads the fp32 residual stream (+ pos) itself: no tile-image pack, no a1/a2 round trip
+      QkvDirectParams qp;
+      memset(&qp, 0, sizeof(qp));
+      qp.q_in = q_in; qp.v_in = v_in; qp.pos = pos;
+      qp.w = reinterpret_cast<const uint8_t*>(w->w_qkv_u); qp.bias = w->b_qkv;
+      qp.qkv = ws.qkv; qp.rows = (int)rows; qp.tiles = tiles; qp.map_mode = map; qp.dims = dims;
+      {
+        ProfScope ps(KC_QKVD, 2.0 * rows * 256.0 * 768.0, (double)rows * ((pos ? 2048.0 : 1024.0) + (v_in != q_in ? 1024.0 : 0.0) + 1536.0), st);
+        qkv_direct_kernel<<<tiles < d->sms ? tiles : d->sms, QD_THREADS, QK_SMEM_BYTES, st>>>(qp);
+      }
+      AXVS_CHECK_LAUNCH("qkv_direct_kernel");
+    } else {
     const bool v_same = (v_in == q_in);
     const bool one_input = v_same && !pos;
     {
@@ -386,6 +401,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       qkv_fused_kernel<<<tiles < d->sms ? tiles : d->sms, QK_THREADS, QK_SMEM_BYTES, st>>>(qp);
     }
     AXVS_CHECK_LAUNCH("qkv_fused_kernel");
+    }
     const int nt16 = (n + 15) / 16;
     const int np_sel = nt16 <= 2 ? 2 : nt16 <= 3 ? 3 : nt16 <= 4 ? 4 : nt16 <= 6 ? 6 : nt16 <= 8 ? 8 : 11;
     const size_t att_q = (size_t)((N + 15) / 16) * 16 * 64 + 4096;

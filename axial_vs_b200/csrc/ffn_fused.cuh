@@ -2,8 +2,10 @@
 //
 //   s   = LayerNorm1(x)            -- produced by ln_image_kernel as fp32 rows + a bf16 tile image (UMMA A operand)
 //   h_j = relu(s W1[j]^T + b1[j])   j = 0..d_ffn/128-1   (GEMM 1, 128-column chunks into two alternating TMEM stages;
-//                                                          epilogue: bias, ReLU, bf16 -> shared-memory A operand of GEMM 2)
-//   acc2 += h_j W2[:, j]^T                               (GEMM 2, K-chunk j, accumulator resident in TMEM columns [0,256))
+//                                                          epilogue: bias, ReLU, bf16 pairs written back IN PLACE over the
+//                                                          stage with tcgen05.st -> tensor-memory A operand of GEMM 2)
+//   acc2 += h_j W2[:, j]^T                               (GEMM 2, K-chunk j, A from TMEM: N = 128 UMMAs at the full 64 clk
+//                                                          rate; accumulator resident in TMEM columns [0,256))
 //   out = LayerNorm2(s + acc2 + b2)                      (final epilogue, coalesced through a shared-memory transpose)
 //
 // The d_ffn-wide hidden activation never leaves the SM.
@@ -17,7 +19,7 @@ namespace axvs {
 constexpr int FF_THREADS = 384;
 constexpr int FF_A_SLOTS = 5;
 constexpr int FF_W_SLOTS = 3;                  // 32 KiB weight units
-constexpr int FF_H_BYTES = 2 * TF_KB;     // 128 x 128 bf16; doubles as the transpose staging of the final epilogue
+constexpr int FF_H_BYTES = 2 * TF_KB;     // per-warp 4 KiB transpose staging of the final epilogue
 constexpr int FF_XCHG_BYTES = 2 * 2 * 128 * 8;
 constexpr int FF_MAX_DFFN = 1024;
 constexpr int FF_BIAS_BYTES = (FF_MAX_DFFN + 3 * 256) * 4;   // b1 | b2 | ln2 gamma | ln2 beta staged in shared memory
@@ -52,10 +54,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
   uint64_t* w_full = a_empty + FF_A_SLOTS;    // [6]
   uint64_t* w_empty = w_full + FF_W_SLOTS;    // [6]
   uint64_t* s_full = w_empty + FF_W_SLOTS;    // [2]
-  uint64_t* s_empty = s_full + 2;             // [2]
-  uint64_t* h_ready = s_empty + 2;            // epilogue -> MMA
-  uint64_t* h_free = h_ready + 1;             // MMA -> epilogue
-  uint64_t* acc_full = h_free + 1;            // MMA -> epilogue
+  uint64_t* h_ready = s_full + 2;             // [2] epilogue -> MMA: the bf16 hidden chunk is in place in TMEM stage j & 1
+  uint64_t* acc_full = h_ready + 2;           // MMA -> epilogue
   uint64_t* acc_free = acc_full + 1;          // epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
 
@@ -66,9 +66,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
   if (threadIdx.x == 0) {
     for (int i = 0; i < FF_A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < FF_W_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
-    mbar_init(h_ready, 8);
-    mbar_init(h_free, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&h_ready[i], 8); }
     mbar_init(acc_full, 1);
     mbar_init(acc_free, 8);
     fence_barrier_init();
@@ -117,17 +115,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
             hpk[c * 16 + 2 * i + 1] = pack_bf16x2(fmaxf(v[4 * i + 2] + bb.z, 0.f), fmaxf(v[4 * i + 3] + bb.w, 0.f));
           }
         }
+        // the 64 fp32 columns this thread just read become 32 columns of bf16 pairs at the start of the same region
+        tmem_st32u(t_s, hpk);
+        AXVS_PROF_WAIT(6, tmem_st_wait())
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[stage]);             // my half of the TMEM stage is drained
-        AXVS_PROF_WAIT(1, mbar_wait(h_free, (hc & 1) ^ 1))        // h_buf is free once GEMM 2 of chunk hc-1 retired
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint4 u = make_uint4(hpk[4 * q], hpk[4 * q + 1], hpk[4 * q + 2], hpk[4 * q + 3]);
-          *reinterpret_cast<uint4*>(h_buf + g * TF_KB + sw128_offset(row_in_tile, q)) = u;
-        }
-        AXVS_PROF_WAIT(6, fence_proxy_async_smem(); __syncwarp())
-        if (lane == 0) mbar_arrive(h_ready);
+        if (lane == 0) mbar_arrive(&h_ready[stage]);
       }
       // ---- final: t = acc2 + b2 + s, LayerNorm2, store.  Rows are one-per-thread in TMEM; a per-warp transpose through
       // shared memory (h_buf is idle: every GEMM 2 of this tile has retired) makes the global traffic row-segment
@@ -260,8 +253,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
     } else if (warp == 10) {
       // =============================================================== MMA issuer (converged warp, elected lane issues)
       const uint32_t idesc = umma_idesc_bf16(128, 128);
-      const uint32_t a_ring_addr = smem_u32(a_ring), h_addr = smem_u32(h_buf), w_ring_addr = smem_u32(w_ring);
-      uint32_t a_cnt = 0, w_slot = 0, w_phase = 0, s_cnt0 = 0, s_cnt1 = 0, it = 0;
+      const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring);
+      uint32_t a_cnt = 0, w_slot = 0, w_phase = 0, it = 0;
       AXVS_PROF_DECL(5)
       auto w_wait = [&]() -> uint32_t {
         AXVS_PROF_WAIT(0, mbar_wait(&w_full[w_slot], w_phase))
@@ -275,11 +268,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
         for (int j = 0; j <= NJ; ++j) {
           if (j < NJ) {
             // GEMM 1, chunk j -> stage j & 1
+            // (the stage's previous occupant, chunk j-2, was consumed by GEMM 2 of that chunk, issued earlier by this thread:
+            //  the tensor pipe executes in issue order, so no barrier is needed before overwriting it)
             const int g = j & 1;
-            const uint32_t sc = g ? s_cnt1 : s_cnt0;
-            AXVS_PROF_WAIT(1, mbar_wait(&s_empty[g], (sc & 1) ^ 1))
-            if (g) ++s_cnt1; else ++s_cnt0;
-            tc_fence_after();
 #pragma unroll 1
             for (int kg = 0; kg < 2; ++kg) {
               const uint32_t ac0 = a_cnt + 2 * kg, ac1 = ac0 + 1;
@@ -299,13 +290,14 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
             const int jj = j - 1;
             const uint32_t hc = it * NJ + jj;
             if (jj == 0) AXVS_PROF_WAIT(4, mbar_wait(acc_free, (it & 1) ^ 1))   // previous tile's final epilogue has drained acc2
-            AXVS_PROF_WAIT(3, mbar_wait(h_ready, hc & 1))
+            AXVS_PROF_WAIT(3, mbar_wait(&h_ready[jj & 1], (hc >> 1) & 1))
             tc_fence_after();
+            const uint32_t t_h = tmem + 256 + (jj & 1) * 128;                 // K 0..63 at columns [0,32), K 64..127 at [64,96)
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
               const uint32_t ws = w_wait();
-              umma_unit_elect(tmem + half * 128, h_addr, h_addr + TF_KB, w_ring_addr + ws * TF_WU, idesc, jj != 0,
-                              &w_empty[ws], half ? h_free : nullptr, (half && j == NJ) ? acc_full : nullptr, nullptr);
+              umma_unit_elect_ts(tmem + half * 128, t_h, t_h + 64, w_ring_addr + ws * TF_WU, idesc, jj != 0,
+                                 &w_empty[ws], (half && j == NJ) ? acc_full : nullptr, nullptr);
             }
           }
         }

@@ -245,6 +245,47 @@ __device__ __forceinline__ void umma_unit_elect(uint32_t tmem_d, uint32_t a0, ui
   }
   __syncwarp();
 }
+// ---- A operand in TENSOR MEMORY (validated in tools/microbench/umma_tmem_a.cu): row m of A in lane m, 32-bit column c of the
+// A region holds the bf16 elements k = 2c (low half) and k = 2c + 1 (high half); one K = 16 UMMA consumes 8 columns.
+// Measured: N = 128 UMMAs run at 64 clk (the full tensor rate) in this form against ~90 clk with A in shared memory, where
+// the 4 KiB (A) + 4 KiB (B) operand reads per instruction saturate the 128 B/clk shared-memory port.
+__device__ __forceinline__ void umma_bf16_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(UMMA_DESC_HI), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One 32 KiB weight unit (8 UMMAs, N = 128, K = 128) with A in tensor memory: ta0 / ta1 = TMEM addresses (lane 0) of the
+// 32 packed columns holding K = 0..63 / 64..127.
+__device__ __forceinline__ void umma_unit_elect_ts(uint32_t tmem_d, uint32_t ta0, uint32_t ta1, uint32_t w, uint32_t idesc, bool accumulate,
+                                                   uint64_t* c0, uint64_t* c1, uint64_t* c2) {
+  const uint32_t w_lo = umma_desc_lo(w);
+  if (elect_one()) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_ts_lo(tmem_d, ta0 + 8 * k, w_lo + 2 * k, idesc, (accumulate || k) ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_ts_lo(tmem_d, ta1 + 8 * k, w_lo + (16384 >> 4) + 2 * k, idesc, 1u);
+    if (c0) umma_commit(c0);
+    if (c1) umma_commit(c1);
+    if (c2) umma_commit(c2);
+  }
+  __syncwarp();
+}
+// registers -> TMEM, 32 lanes x 32 columns of raw 32-bit words (packed bf16 pairs)
+__device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   if (elect_one()) umma_commit(bar);
   __syncwarp();

@@ -49,6 +49,7 @@ const char* axvs_last_error(void);
  *   1: + proj_q / proj_kv / temporal softmax / proj / residual fused in one tcgen05 kernel
  *   2: + LayerNorm1 / FFN / residual / LayerNorm2 fused in one tcgen05 kernel
  *   3: + TMA-fed q|k|v projection with head-major output, one-shot per-frame attention writing UMMA tile images
+ *   4: + the q|k|v projection reads the fp32 residual stream (+ pos) itself (permute, add and cast inside its A producers)
  * Returns the previous level; values outside the range are clamped. */
 int axvs_set_fusion(int level);
 /* CTA-pair FFN kernel (tcgen05 cta_group::2, two SMs per M = 256 instruction stream) on/off.  Default OFF: it is validated

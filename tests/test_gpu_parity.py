@@ -257,7 +257,7 @@ def test_fusion_levels_agree(ops, O, Bp, F, n):
     res = torch.randn(Bp * F * n, 256, generator=torch.Generator().manual_seed(1)).cuda()
     outs = []
     try:
-        for level in (0, 1, 2, 3):
+        for level in (0, 1, 2, 3, 4):
             ops.set_fusion(level)
             out = ops.traj_attn_fwd(qc, qc, vc, None, res, pk, Bp, F, n, 1, ops.AXIS_NONE)
             torch.cuda.synchronize()
@@ -266,6 +266,7 @@ def test_fusion_levels_agree(ops, O, Bp, F, n):
     finally:
         ops.set_fusion(99)
     assert nerr(outs[1], outs[0]) < 5e-3 and nerr(outs[3], outs[0]) < 5e-3
+    assert torch.equal(outs[4], outs[3])      # level 4 only moves the permute / add / cast into the GEMM's producers
 
 
 # --------------------------------------------------------------------------------------------- maps, pos module, TL, cross-clip

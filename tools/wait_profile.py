@@ -14,6 +14,9 @@ buf = (ctypes.c_ulonglong * 64)()
 def run():
     if which == "ffn":
         return ops.ln_ffn_fwd(x, pk)
+    if which == "qkvd":
+        ops.set_fusion(4)
+        return ops.traj_attn_fwd(x, x, x, x, x, pk.attn_h, clips, 2, 41, 41, ops.AXIS_H)
     if which == "qkv":
         ops.set_fusion(3)
         return ops.traj_attn_fwd(x, x, x, None, x, pk.attn_h, clips, 2, 41, 41, ops.AXIS_H)
@@ -40,6 +43,11 @@ if which == "ffn":
     show("epilogue g0 warp0", 8, ["s_full", "h_free", "acc_full", "bar.sync", "final:chunks", "final:all", "fence"])
     show("epilogue g1 warp4", 16, ["s_full", "h_free", "acc_full", "bar.sync", "final:chunks", "final:all", "fence"])
     show("W producer", 32, ["w_empty"])
+elif which == "qkvd":
+    show("qkv_direct MMA warp", 40, ["w_full", "s_empty", "a_full"])
+    show("qkv_direct epilogue g0", 44, ["s_full"])
+    show("qkv_direct epilogue g1", 46, ["s_full"])
+    show("qkv_direct A producer warp 0", 48, ["a_empty", "-"])
 elif which == "qkv":
     show("qkv MMA warp", 40, ["w_full", "s_empty", "a_full"])
     show("qkv epilogue g0", 44, ["s_full"])
