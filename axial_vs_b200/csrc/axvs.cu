@@ -106,7 +106,7 @@ int device_info(DeviceInfo** out) {
   }
   if (!d.qkv_attr) {
     if (cudaFuncSetAttribute(qkv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QK_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(qkv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QK_SMEM_BYTES) != cudaSuccess)
+        cudaFuncSetAttribute(qkv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QD_SMEM_BYTES) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(qkv_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.qkv_attr = true;
   }
@@ -366,16 +366,16 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
   if (g_fusion >= 3 && k_in == q_in && w->w_qkv_u && w->w_pq_u && w->w_pkv_u && w->w_proj_u && num_seq <= (1 << 27)) {
     // ---- fused front end: tile-image pack -> TMA-fed q|k|v GEMM (head-major) -> one-shot attention writing tile images
     const int tiles = (int)((rows + 127) / 128);
-    if (g_fusion >= 4) {
+    if (g_fusion >= 4 && v_in == q_in) {
       // the q|k|v GEMM reads the fp32 residual stream (+ pos) itself: no tile-image pack, no a1/a2 round trip
       QkvDirectParams qp;
       memset(&qp, 0, sizeof(qp));
-      qp.q_in = q_in; qp.v_in = v_in; qp.pos = pos;
+      qp.src = q_in; qp.pos = pos;
       qp.w = reinterpret_cast<const uint8_t*>(w->w_qkv_u); qp.bias = w->b_qkv;
       qp.qkv = ws.qkv; qp.rows = (int)rows; qp.tiles = tiles; qp.map_mode = map; qp.dims = dims;
       {
-        ProfScope ps(KC_QKVD, 2.0 * rows * 256.0 * 768.0, (double)rows * ((pos ? 2048.0 : 1024.0) + (v_in != q_in ? 1024.0 : 0.0) + 1536.0), st);
-        qkv_direct_kernel<<<tiles < d->sms ? tiles : d->sms, QD_THREADS, QK_SMEM_BYTES, st>>>(qp);
+        ProfScope ps(KC_QKVD, 2.0 * rows * 256.0 * 768.0, (double)rows * ((pos ? 2048.0 : 1024.0) + 1536.0), st);
+        qkv_direct_kernel<<<tiles < d->sms ? tiles : d->sms, QD_THREADS, QD_SMEM_BYTES, st>>>(qp);
       }
       AXVS_CHECK_LAUNCH("qkv_direct_kernel");
     } else {

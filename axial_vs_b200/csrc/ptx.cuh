@@ -274,6 +274,21 @@ __device__ __forceinline__ void umma_unit_elect_ts(uint32_t tmem_d, uint32_t ta0
   }
   __syncwarp();
 }
+// shared memory -> TMEM: 128 rows x 32 bytes (one K = 16 slice of a SWIZZLE_128B K-major bf16 tile) -> 128 lanes x 8 columns,
+// i.e. exactly the tensor-memory A operand of one UMMA (validated in tools/microbench/umma_tmem_a.cu).  Executes in issue order
+// with the tcgen05.mma of the same thread; completion is tracked by tcgen05.commit like an MMA.
+__device__ __forceinline__ void tmem_cp_128x256b_lo(uint32_t taddr, uint32_t desc_lo) {
+  asm volatile(
+      "{\n\t.reg .b64 d;\n\tmov.b64 d, {%1, %2};\n\t"
+      "tcgen05.cp.cta_group::1.128x256b [%0], d;\n\t}" ::"r"(taddr), "r"(desc_lo), "r"(UMMA_DESC_HI)
+      : "memory");
+}
+// One K-block image (128 rows x 64 bf16) -> 32 TMEM columns.
+__device__ __forceinline__ void tmem_cp_kblock(uint32_t taddr, uint32_t smem_addr) {
+  const uint32_t lo = umma_desc_lo(smem_addr);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) tmem_cp_128x256b_lo(taddr + 8 * k, lo + 2 * k);
+}
 // registers -> TMEM, 32 lanes x 32 columns of raw 32-bit words (packed bf16 pairs)
 __device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(

@@ -1,16 +1,19 @@
 // q | k | v projections reading the fp32 residual stream directly (fusion level 4): the tile-image pack kernel and its
-// 2 KiB/token round trip through HBM disappear.  Same GEMM schedule, TMEM staging and head-major epilogue as
-// qkv_fused_kernel; the single TMA A-producer warp is replaced by eight converting producer warps:
+// 2 KiB/token round trip through HBM disappear.
 //
-//   item 0..3 : A1 K-block kb = bf16(q_in[c(row)][64 kb ..] + pos[c(row)][64 kb ..])      (pos optional)
-//   item 4..7 : A2 K-block kb = bf16(v_in[c(row)][64 kb ..])                              (second read of the rows: L2 hit)
+//   A1 = bf16(src[c(row)] + pos[c(row)]),  A2 = bf16(src[c(row)])        c(row) = canonical token of pass-order row `row`
+//   [q | k] = A1 [Wq; Wk]^T + b,   v = A2 Wv^T + b                        (the reference's axis permutes, WC/temporal_attention.py:197,206,
+//                                                                          exist only as this index map)
 //
-// c(row) = canonical token of pass-order row `row` (the reference's axis permutes, WC/temporal_attention.py:197,206, as an
-// index map).  A producer warp owns 16 rows of the item; half a warp reads one 256-byte row segment per instruction,
-// converts and writes 8-byte pieces of the SWIZZLE_128B K-major image the MMA consumes, then fence.proxy.async + one mbarrier
-// arrive per warp.  Loads are software-pipelined over two register sets (up to 16 x LDG.128 in flight per lane).
+// Eight converting producer warps read 256-byte row segments (half a warp per segment, software-pipelined over two register
+// sets), and write BOTH images of a K-block from the one src load into a 32 KiB "pair slot" (SWIZZLE_128B K-major).  The MMA
+// warp moves each image into TENSOR MEMORY with tcgen05.cp (columns [0,128) = A1, [128,256) = A2) and frees the slot at once,
+// so the shared-memory ring only decouples producers and tensor pipe -- the whole tile's A operand lives in TMEM, and the
+// N = 128 UMMAs read it from there at the full 64 clk rate (A in shared memory: ~90 clk, operand reads saturate the smem port).
+// Six 128-column chunks (q heads 0-3, 4-7, k, k, v, v) alternate between two TMEM accumulator stages, one per epilogue group;
+// the epilogue adds the bias and writes bf16 HEAD-MAJOR  qkv[which][head][row][32]  through a per-warp transpose.
 //
-// Warp roles (576 threads, 112 registers each, no setmaxnreg): warps 0-7 epilogue, 8-15 A producers, 16 weight TMA, 17 MMA.
+// Warp roles (576 threads, no setmaxnreg): warps 0-7 epilogue, 8-15 A producers, 16 weight TMA, 17 MMA / tcgen05.cp issuer.
 #pragma once
 #include "qkv_fused.cuh"
 
@@ -18,10 +21,12 @@ namespace axvs {
 
 constexpr int QD_THREADS = 576;
 constexpr int QD_PRODUCER_WARPS = 8;
+constexpr int QD_A_SLOTS = 3;                 // pair slots: [A1 K-block image | A2 K-block image] = 32 KiB
+constexpr int QD_SMEM_BYTES = QD_A_SLOTS * 2 * TF_KB + QK_W_SLOTS * TF_WU + QK_STAGE_BYTES + QK_BIAS_BYTES + 512;
+static_assert(QD_SMEM_BYTES <= 232448, "qkv_direct_kernel exceeds the 227 KiB shared-memory limit");
 
 struct QkvDirectParams {
-  const float* q_in;       // fp32 [tokens, 256] canonical order
-  const float* v_in;       // fp32 [tokens, 256] (may equal q_in)
+  const float* src;        // fp32 [tokens, 256] canonical order: q = k input (before the positional term) and v input
   const float* pos;        // fp32 [tokens, 256] or null
   const uint8_t* w;        // unit format of [Wq; Wk; Wv]
   const float* bias;       // [768]
@@ -34,25 +39,25 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* a_ring = smem;
-  uint8_t* w_ring = a_ring + QK_A_SLOTS * TF_KB;
+  uint8_t* w_ring = a_ring + QD_A_SLOTS * 2 * TF_KB;
   uint8_t* stage_all = w_ring + QK_W_SLOTS * TF_WU;
   float* sbias = reinterpret_cast<float*>(stage_all + QK_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 768);
-  uint64_t* a_full = bars;                      // [QK_A_SLOTS], one arrive per producer warp
-  uint64_t* a_empty = a_full + QK_A_SLOTS;
-  uint64_t* w_full = a_empty + QK_A_SLOTS;      // [QK_W_SLOTS]
+  uint64_t* a_full = bars;                      // [QD_A_SLOTS], one arrive per producer warp
+  uint64_t* a_empty = a_full + QD_A_SLOTS;      // tcgen05.commit after the slot's copies
+  uint64_t* w_full = a_empty + QD_A_SLOTS;      // [QK_W_SLOTS]
   uint64_t* w_empty = w_full + QK_W_SLOTS;
-  uint64_t* s_full = w_empty + QK_W_SLOTS;      // [4]
-  uint64_t* s_empty = s_full + 4;               // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 4);
+  uint64_t* s_full = w_empty + QK_W_SLOTS;      // [2] accumulator stage of group g complete
+  uint64_t* s_empty = s_full + 2;               // [2] drained by the 4 warps of group g
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < QK_A_SLOTS; ++i) { mbar_init(&a_full[i], QD_PRODUCER_WARPS); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < QD_A_SLOTS; ++i) { mbar_init(&a_full[i], QD_PRODUCER_WARPS); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < QK_W_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 17) tmem_alloc(tmem_slot, 512);
@@ -67,16 +72,15 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
     const int g = warp >> 2;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint8_t* stg = stage_all + warp * 2048;
-    uint32_t cnt = 0;                                          // chunks consumed by this group (stage = 2 * (cnt & 1) + g)
+    const uint32_t t_s = tmem + lane_base + 256 + g * 128;
+    uint32_t cnt = 0;                                          // chunks consumed by this group
     AXVS_PROF_DECL(1)
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
       const int row0 = tile * 128 + (warp & 3) * 32;           // first row of this warp
 #pragma unroll 1
       for (int rt = g; rt < 6; rt += 2, ++cnt) {
-        const int stage = 2 * (cnt & 1) + g;
-        AXVS_PROF_WAIT(0, mbar_wait(&s_full[stage], (cnt >> 1) & 1))
+        AXVS_PROF_WAIT(0, mbar_wait(&s_full[g], cnt & 1))
         tc_fence_after();
-        const uint32_t t_s = tmem + lane_base + stage * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {                          // one head (32 columns) at a time
           float v[32];
@@ -85,8 +89,9 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
           if (c == 3) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[stage]);
+            if (lane == 0) mbar_arrive(&s_empty[g]);
           }
+          // bias + bf16, then a 2 KiB per-warp transpose so every store instruction writes 512 contiguous bytes
           {
             const float4* b4 = reinterpret_cast<const float4*>(sbias + rt * 128 + c * 32);
 #pragma unroll
@@ -118,8 +123,8 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
     AXVS_PROF_FLUSH(44 + 2 * g, 1, (warp & 3) == 0 && lane == 0)
   } else if (warp < 8 + QD_PRODUCER_WARPS) {
     // =============================================================== converting A producers
-    // Work unit = batch: 4 of the lane's 8 rows of one item (4 src + 4 pos loads).  Two register sets alternate so the loads
-    // of batch b+1 (also across item and tile boundaries) are in flight while batch b is converted and stored.
+    // Work unit = batch: 4 of the lane's 8 rows of one K-block (4 src + 4 pos loads).  Two register sets alternate so the
+    // loads of batch b+1 (also across K-block and tile boundaries) are in flight while batch b is converted and stored.
     const int pw = warp - 8;
     const int half = lane >> 4, c16 = lane & 15;               // row of the pair, 16-byte piece (4 channels) of the 256-byte segment
     uint32_t cnt = 0;
@@ -133,16 +138,14 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
         cr[j] = pr < p.rows ? (uint32_t)pass_to_canonical(pr, p.map_mode, p.dims) : 0xFFFFFFFFu;
       }
     };
-    auto issue = [&](float4 (&s)[4], float4 (&q)[4], const uint32_t (&cr)[8], int item, int hf) {
-      const int kb = item & 3;
-      const float* src = item < 4 ? p.q_in : p.v_in;
+    auto issue = [&](float4 (&s)[4], float4 (&q)[4], const uint32_t (&cr)[8], int kb, int hf) {
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t c = cr[4 * hf + j];
-        s[j] = c != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const float4*>(src + (size_t)c * C256 + kb * 64) + c16) : z;
+        s[j] = c != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const float4*>(p.src + (size_t)c * C256 + kb * 64) + c16) : z;
       }
-      if (item < 4 && p.pos) {
+      if (p.pos) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t c = cr[4 * hf + j];
@@ -154,16 +157,20 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
       }
     };
     auto consume = [&](float4 (&s)[4], float4 (&q)[4], int hf) {
-      const uint32_t slot = cnt % QK_A_SLOTS, phase = (cnt / QK_A_SLOTS) & 1;
+      const uint32_t slot = cnt % QD_A_SLOTS, phase = (cnt / QD_A_SLOTS) & 1;
       if (hf == 0) { AXVS_PROF_WAIT(0, mbar_wait(&a_empty[slot], phase ^ 1)) }
-      uint8_t* dst = a_ring + slot * TF_KB;
+      uint8_t* dst = a_ring + slot * 2 * TF_KB;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = pw * 16 + 2 * (4 * hf + j) + half;
+        const uint32_t off = sw128_offset(r, c16 >> 1) + (c16 & 1) * 8;
         uint2 u;
         u.x = pack_bf16x2(s[j].x + q[j].x, s[j].y + q[j].y);
         u.y = pack_bf16x2(s[j].z + q[j].z, s[j].w + q[j].w);
-        *reinterpret_cast<uint2*>(dst + sw128_offset(r, c16 >> 1) + (c16 & 1) * 8) = u;
+        *reinterpret_cast<uint2*>(dst + off) = u;                                   // A1 K-block image
+        u.x = pack_bf16x2(s[j].x, s[j].y);
+        u.y = pack_bf16x2(s[j].z, s[j].w);
+        *reinterpret_cast<uint2*>(dst + TF_KB + off) = u;                           // A2 K-block image
       }
       if (hf == 1) {
         fence_proxy_async_smem();
@@ -179,8 +186,8 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
       const bool has_next = tile + (int)gridDim.x < p.tiles;
 #pragma unroll
-      for (int b = 0; b < 16; ++b) {
-        if (b < 15) {
+      for (int b = 0; b < 8; ++b) {
+        if (b < 7) {
           issue(sv[(b + 1) & 1], qv[(b + 1) & 1], crow, (b + 1) >> 1, (b + 1) & 1);
         } else if (has_next) {
           rows_of_tile(tile + gridDim.x, crow_n);
@@ -205,38 +212,44 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
       }
     }
   } else if (warp == 17) {
-    // =============================================================== MMA issuer
+    // =============================================================== tcgen05.cp + MMA issuer (converged warp, elected lane)
     const uint32_t idesc = umma_idesc_bf16(128, 128);
     const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring);
-    uint32_t a_cnt = 0, w_slot = 0, w_phase = 0, ccnt = 0;     // ccnt: chunks issued (stage = 2 * ((ccnt >> 1) & 1) + (ccnt & 1))
+    uint32_t a_cnt = 0, w_slot = 0, w_phase = 0, ccnt = 0;     // ccnt: chunks issued
     AXVS_PROF_DECL(3)
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      // the tile's A operand: four pair slots -> TMEM.  These copies are ordered by the tensor pipe behind every UMMA of the
+      // previous tile (issued earlier by this thread), which still reads the old contents.
+#pragma unroll 1
+      for (int kb = 0; kb < 4; ++kb, ++a_cnt) {
+        const uint32_t slot = a_cnt % QD_A_SLOTS;
+        AXVS_PROF_WAIT(2, mbar_wait(&a_full[slot], (a_cnt / QD_A_SLOTS) & 1))
+        tc_fence_after();
+        const uint32_t sa = a_ring_addr + slot * 2 * TF_KB;
+        if (elect_one()) {
+          tmem_cp_kblock(tmem + 32 * kb, sa);
+          tmem_cp_kblock(tmem + 128 + 32 * kb, sa + TF_KB);
+          umma_commit(&a_empty[slot]);
+        }
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int rt = 0; rt < 6; ++rt, ++ccnt) {
         const int g = rt & 1;
-        const uint32_t gc = ccnt >> 1;
-        const int stage = 2 * (gc & 1) + g;
-        AXVS_PROF_WAIT(1, mbar_wait(&s_empty[stage], ((gc >> 1) & 1) ^ 1))
+        const uint32_t gc = ccnt >> 1;                         // chunks already issued to group g (6 per tile: even count)
+        AXVS_PROF_WAIT(1, mbar_wait(&s_empty[g], (gc & 1) ^ 1))
         tc_fence_after();
-        const uint32_t abase = a_cnt + (rt < 4 ? 0 : 4);       // A1 items for q/k chunks, A2 items for v chunks
+        const uint32_t t_a = tmem + (rt < 4 ? 0 : 128);        // A1 for the q / k chunks, A2 for the v chunks
 #pragma unroll 1
         for (int kg = 0; kg < 2; ++kg) {
-          const uint32_t ac0 = abase + 2 * kg, ac1 = ac0 + 1;
-          const uint32_t s0 = ac0 % QK_A_SLOTS, s1 = ac1 % QK_A_SLOTS;
-          if (rt == 0 || rt == 4) {
-            AXVS_PROF_WAIT(2, mbar_wait(&a_full[s0], (ac0 / QK_A_SLOTS) & 1); mbar_wait(&a_full[s1], (ac1 / QK_A_SLOTS) & 1))
-            tc_fence_after();
-          }
           AXVS_PROF_WAIT(0, mbar_wait(&w_full[w_slot], w_phase))
           tc_fence_after();
           const uint32_t ws = w_slot;
           if (++w_slot == QK_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
-          const bool last_use = (rt == 3 || rt == 5);
-          umma_unit_elect(tmem + stage * 128, a_ring_addr + s0 * TF_KB, a_ring_addr + s1 * TF_KB, w_ring_addr + ws * TF_WU, idesc, kg != 0,
-                          &w_empty[ws], last_use ? &a_empty[s0] : nullptr, last_use ? &a_empty[s1] : nullptr, kg == 1 ? &s_full[stage] : nullptr);
+          umma_unit_elect_ts(tmem + 256 + g * 128, t_a + 64 * kg, t_a + 64 * kg + 32, w_ring_addr + ws * TF_WU, idesc, kg != 0,
+                             &w_empty[ws], kg == 1 ? &s_full[g] : nullptr, nullptr);
         }
       }
-      a_cnt += 8;
     }
     AXVS_PROF_FLUSH(40, 3, lane == 0)
   }

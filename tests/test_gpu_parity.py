@@ -190,6 +190,28 @@ def test_axial_layer_oracle_config_sizes(O, B, T, H, W):
     assert e < TOL and cos > 0.9999, (e, cos)
 
 
+@pytest.mark.parametrize("B,T,H,W", [(2, 2, 41, 41), (1, 5, 15, 20), (3, 2, 13, 29)])
+def test_direct_qkv_matches_packed_front_end(ops, B, T, H, W):
+    """Fusion level 4 (q|k|v GEMM reads the fp32 stream, A operand staged into tensor memory) must reproduce level 3
+    (tile-image pack kernel + TMA-fed GEMM) bit for bit: same bf16 operands, same accumulation order."""
+    seed = 900 + B + T + H + W
+    p = synth.axial_layer_params(seed)
+    src = synth.randn(seed + 1, B * T, H * W, 256).cuda()
+    pos = synth.randn(seed + 2, B, T, H, W, 256).cuda()
+    layer = _layer(p)
+    outs = []
+    try:
+        for level in (3, 4):
+            ops.set_fusion(level)
+            with torch.no_grad():
+                outs.append(layer(src, pos)[0])
+            torch.cuda.synchronize()
+    finally:
+        ops.set_fusion(99)
+    assert torch.isfinite(outs[1]).all()
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_encoder_config1_two_layers(O):
     """BASELINE config 1: TemporalEncoder(axial-trajectory, 2 layers) on T=2, 41x41x256."""
     from axial_vs_b200 import modules

@@ -20,8 +20,14 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+
 // a: [128][64] bf16 row-major, b: [128 n][64 k] bf16 row-major (K-major), d: [128][128] fp32
-__global__ void __launch_bounds__(128, 1) k_check(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d, int iters, long long* clk) {
+// use_cp = 0: A written to TMEM with tcgen05.st (thread = row);  use_cp = 1: A staged in shared memory as a SWIZZLE_128B
+// K-major tile image and moved with four tcgen05.cp.128x256b (one per K = 16 slice: 32 bytes per row -> 8 TMEM columns)
+__global__ void __launch_bounds__(128, 1) k_check(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d, int iters, long long* clk, int use_cp) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -32,6 +38,11 @@ __global__ void __launch_bounds__(128, 1) k_check(const __nv_bfloat16* a, const 
     const int r = i >> 3, c = i & 7;
     *reinterpret_cast<uint4*>(smem + sw128_offset(r, c)) = *reinterpret_cast<const uint4*>(b + r * 64 + c * 8);
   }
+  uint8_t* a_img = smem + 16384;
+  for (int i = tid; i < 128 * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(a_img + sw128_offset(r, c)) = *reinterpret_cast<const uint4*>(a + r * 64 + c * 8);
+  }
   if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(&slot, 512);
   fence_proxy_async_smem();
@@ -39,7 +50,7 @@ __global__ void __launch_bounds__(128, 1) k_check(const __nv_bfloat16* a, const 
   const uint32_t tmem = slot;
   const uint32_t t_d = tmem, t_a = tmem + 256;                 // D: columns [0,128), A: columns [256, 288)
   // A -> TMEM: thread = row; 64 bf16 = 32 packed columns
-  {
+  if (!use_cp) {
     float v[32];
     uint32_t* u = reinterpret_cast<uint32_t*>(v);
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a + tid * 64);
@@ -52,6 +63,8 @@ __global__ void __launch_bounds__(128, 1) k_check(const __nv_bfloat16* a, const 
   if (tid == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, 128);
     const uint32_t b0 = smem_u32(smem);
+    if (use_cp)
+      for (int kk = 0; kk < 4; ++kk) tmem_cp_128x256b(t_a + 8 * kk, umma_desc_sw128(smem_u32(a_img) + kk * 32));
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it)
       for (int kk = 0; kk < 4; ++kk) umma_bf16_ts(t_d, t_a + 8 * kk, umma_desc_sw128(b0 + kk * 32), idesc, (it | kk) ? 1u : 0u);
@@ -88,7 +101,8 @@ int main() {
   cudaMemcpy(da, ha.data(), 128 * 64 * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(db, hb.data(), 128 * 64 * 2, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(k_check, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  k_check<<<1, 128, 64 * 1024>>>(da, db, dd, 1, dc);
+  for (int use_cp = 0; use_cp < 2; ++use_cp) {
+  k_check<<<1, 128, 64 * 1024>>>(da, db, dd, 1, dc, use_cp);
   cudaError_t e = cudaDeviceSynchronize();
   printf("launch: %s\n", cudaGetErrorString(e));
   if (e != cudaSuccess) return 1;
@@ -101,10 +115,11 @@ int main() {
       for (int k = 0; k < 64; ++k) r += (double)fa[m * 64 + k] * fb[n * 64 + k];
       maxerr = fmax(maxerr, fabs(r - hd[m * 128 + n])); maxref = fmax(maxref, fabs(r));
     }
-  printf("A-from-TMEM (packed bf16 pairs, k = 2c low / 2c+1 high): max abs err %.3e (max |ref| %.3f) -> %s\n", maxerr, maxref,
-         maxerr < 1e-3 * maxref ? "LAYOUT OK" : "MISMATCH");
+  printf("A-from-TMEM via %s: max abs err %.3e (max |ref| %.3f) -> %s\n", use_cp ? "tcgen05.cp.128x256b from a SW128 smem image" : "tcgen05.st (packed bf16 pairs, k = 2c low / 2c+1 high)",
+         maxerr, maxref, maxerr < 1e-3 * maxref ? "LAYOUT OK" : "MISMATCH");
+  }
   const int iters = 2048;
-  k_check<<<1, 128, 64 * 1024>>>(da, db, dd, iters, dc);
+  k_check<<<1, 128, 64 * 1024>>>(da, db, dd, iters, dc, 0);
   cudaDeviceSynchronize();
   long long hc[2]; cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost);
   printf("rate, N = 128, A in TMEM: issue %.1f clk/MMA, total %.1f clk/MMA\n", hc[0] / (iters * 4.0), hc[1] / (iters * 4.0));

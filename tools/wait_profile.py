@@ -39,9 +39,9 @@ def show(name, base, labels):
     for i, l in enumerate(labels):
         print(f"      wait {l:10s} {v[base + i] / ctas:12,.0f}  ({100.0 * v[base + i] / max(v[base + len(labels)], 1):5.1f} %)")
 if which == "ffn":
-    show("MMA warp", 0, ["w_full", "s_empty", "a_full", "h_ready", "acc_free"])
-    show("epilogue g0 warp0", 8, ["s_full", "h_free", "acc_full", "bar.sync", "final:chunks", "final:all", "fence"])
-    show("epilogue g1 warp4", 16, ["s_full", "h_free", "acc_full", "bar.sync", "final:chunks", "final:all", "fence"])
+    show("MMA warp", 0, ["w_full", "-", "a_full", "h_ready", "acc_free"])
+    show("epilogue g0 warp0", 8, ["s_full", "-", "acc_full", "bar.sync", "final:chunks", "final:all", "st_wait"])
+    show("epilogue g1 warp4", 16, ["s_full", "-", "acc_full", "bar.sync", "final:chunks", "final:all", "st_wait"])
     show("W producer", 32, ["w_empty"])
 elif which == "qkvd":
     show("qkv_direct MMA warp", 40, ["w_full", "s_empty", "a_full"])
