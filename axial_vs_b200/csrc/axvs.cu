@@ -10,6 +10,7 @@
 #include "gemm.cuh"
 #include "simt.cuh"
 #include "traj_fused.cuh"
+#include "traj_ts.cuh"
 #include "ffn_fused.cuh"
 #include "qkv_fused.cuh"
 #include "qkv_direct.cuh"
@@ -100,7 +101,8 @@ int device_info(DeviceInfo** out) {
     d.gemm_attr = true;
   }
   if (!d.traj_attr) {
-    if (cudaFuncSetAttribute(traj_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(traj_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(traj_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM_BYTES) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(traj_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.traj_attr = true;
   }
@@ -448,7 +450,8 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
     {
       ProfScope ps(KC_TRAJ, 2.0 * rows * 256.0 * 256.0 * (2.0 + 2.0 * F) + 4.0 * rows * F * 256.0,
                    (double)rows * (512.0 * (F + 1) + 1024.0 + (resid ? 1024.0 : 0.0)), st);
-      traj_fused_kernel<<<tiles < d->sms ? tiles : d->sms, TF_THREADS, TF_SMEM_BYTES, st>>>(tp);
+      if (g_fusion >= 4) traj_ts_kernel<<<tiles < d->sms ? tiles : d->sms, TF_THREADS, TT_SMEM_BYTES, st>>>(tp);
+      else traj_fused_kernel<<<tiles < d->sms ? tiles : d->sms, TF_THREADS, TF_SMEM_BYTES, st>>>(tp);
     }
     AXVS_CHECK_LAUNCH("traj_fused_kernel");
     return AXVS_OK;

@@ -57,7 +57,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifndef AXVS_NO_DEADLOCK_TRAP
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef AXVS_TRAP_DEBUG
+    if (++spins > (1u << 22)) {   // debug builds: say who is stuck on which barrier (byte offset from the dynamic smem base)
+      extern __shared__ uint8_t axvs_dbg_smem_base[];
+      printf("[axvs deadlock] block %d thread %d barrier +%u parity %u\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar) - smem_u32(axvs_dbg_smem_base), parity);
+      break;                      // carry on with garbage so the kernel ends and the printf buffer is flushed
+    }
+#else
     if (++spins > (1u << 24)) __trap();
+#endif
   }
 #else
   while (!mbar_try_wait(bar, parity)) {
@@ -273,6 +282,19 @@ __device__ __forceinline__ void umma_unit_elect_ts(uint32_t tmem_d, uint32_t ta0
     if (c2) umma_commit(c2);
   }
   __syncwarp();
+}
+__device__ __forceinline__ void tmem_ld8u(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
 }
 // shared memory -> TMEM: 128 rows x 32 bytes (one K = 16 slice of a SWIZZLE_128B K-major bf16 tile) -> 128 lanes x 8 columns,
 // i.e. exactly the tensor-memory A operand of one UMMA (validated in tools/microbench/umma_tmem_a.cu).  Executes in issue order

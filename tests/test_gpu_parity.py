@@ -192,8 +192,8 @@ def test_axial_layer_oracle_config_sizes(O, B, T, H, W):
 
 @pytest.mark.parametrize("B,T,H,W", [(2, 2, 41, 41), (1, 5, 15, 20), (3, 2, 13, 29)])
 def test_direct_qkv_matches_packed_front_end(ops, B, T, H, W):
-    """Fusion level 4 (q|k|v GEMM reads the fp32 stream, A operand staged into tensor memory) must reproduce level 3
-    (tile-image pack kernel + TMA-fed GEMM) bit for bit: same bf16 operands, same accumulation order."""
+    """Fusion level 4 (q|k|v GEMM reading the fp32 stream, every A operand in tensor memory, q2 held as bf16) against
+    level 3 (tile-image pack kernel, shared-memory operands, fp32 q2): same bf16 GEMM operands otherwise."""
     seed = 900 + B + T + H + W
     p = synth.axial_layer_params(seed)
     src = synth.randn(seed + 1, B * T, H * W, 256).cuda()
@@ -209,7 +209,7 @@ def test_direct_qkv_matches_packed_front_end(ops, B, T, H, W):
     finally:
         ops.set_fusion(99)
     assert torch.isfinite(outs[1]).all()
-    assert torch.equal(outs[0], outs[1])
+    assert nerr(outs[1], outs[0]) < 4e-3
 
 
 def test_encoder_config1_two_layers(O):
@@ -288,7 +288,7 @@ def test_fusion_levels_agree(ops, O, Bp, F, n):
     finally:
         ops.set_fusion(99)
     assert nerr(outs[1], outs[0]) < 5e-3 and nerr(outs[3], outs[0]) < 5e-3
-    assert torch.equal(outs[4], outs[3])      # level 4 only moves the permute / add / cast into the GEMM's producers
+    assert nerr(outs[4], outs[3]) < 4e-3      # level 4: tensor-memory operands, q2 rounded to bf16
 
 
 # --------------------------------------------------------------------------------------------- maps, pos module, TL, cross-clip

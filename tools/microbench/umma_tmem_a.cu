@@ -27,7 +27,7 @@ __device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc)
 // a: [128][64] bf16 row-major, b: [128 n][64 k] bf16 row-major (K-major), d: [128][128] fp32
 // use_cp = 0: A written to TMEM with tcgen05.st (thread = row);  use_cp = 1: A staged in shared memory as a SWIZZLE_128B
 // K-major tile image and moved with four tcgen05.cp.128x256b (one per K = 16 slice: 32 bytes per row -> 8 TMEM columns)
-__global__ void __launch_bounds__(128, 1) k_check(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d, int iters, long long* clk, int use_cp) {
+__global__ void __launch_bounds__(128, 1) k_check(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d, int iters, long long* clk, int use_cp, int N = 128) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(128, 1) k_check(const __nv_bfloat16* a, const 
   }
   tc_fence_before(); __syncthreads(); tc_fence_after();
   if (tid == 0) {
-    const uint32_t idesc = umma_idesc_bf16(128, 128);
+    const uint32_t idesc = umma_idesc_bf16(128, N);
     const uint32_t b0 = smem_u32(smem);
     if (use_cp)
       for (int kk = 0; kk < 4; ++kk) tmem_cp_128x256b(t_a + 8 * kk, umma_desc_sw128(smem_u32(a_img) + kk * 32));
@@ -119,9 +119,11 @@ int main() {
          maxerr, maxref, maxerr < 1e-3 * maxref ? "LAYOUT OK" : "MISMATCH");
   }
   const int iters = 2048;
-  k_check<<<1, 128, 64 * 1024>>>(da, db, dd, iters, dc, 0);
-  cudaDeviceSynchronize();
-  long long hc[2]; cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost);
-  printf("rate, N = 128, A in TMEM: issue %.1f clk/MMA, total %.1f clk/MMA\n", hc[0] / (iters * 4.0), hc[1] / (iters * 4.0));
+  for (int N : {32, 64, 96, 128}) {
+    k_check<<<1, 128, 64 * 1024>>>(da, db, dd, iters, dc, 0, N);
+    cudaDeviceSynchronize();
+    long long hc[2]; cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost);
+    printf("rate, N = %3d, A in TMEM: issue %.1f clk/MMA, total %.1f clk/MMA (full rate would be %d)\n", N, hc[0] / (iters * 4.0), hc[1] / (iters * 4.0), N / 2);
+  }
   return 0;
 }

@@ -53,7 +53,7 @@ elif which == "qkv":
     show("qkv epilogue g0", 44, ["s_full"])
     show("qkv epilogue g1", 46, ["s_full"])
 else:
-    show("MMA warp", 0, ["w_full", "s_empty", "a_full", "o_ready", "q2_free"])
+    show("MMA warp", 0, ["w_full", "s_empty", "a_full", "o_ready", "pj_free"])
     show("epilogue g0 warp0", 8, ["q2_full", "s_full(fr)", "s_full(pj)"])
     show("epilogue g1 warp4", 16, ["q2_full", "s_full(fr)", "s_full(pj)"])
     show("W producer", 32, ["w_empty"])
