@@ -10,8 +10,10 @@
 // warp moves each image into TENSOR MEMORY with tcgen05.cp (columns [0,128) = A1, [128,256) = A2) and frees the slot at once,
 // so the shared-memory ring only decouples producers and tensor pipe -- the whole tile's A operand lives in TMEM, and the
 // N = 128 UMMAs read it from there at the full 64 clk rate (A in shared memory: ~90 clk, operand reads saturate the smem port).
-// Six 128-column chunks (q heads 0-3, 4-7, k, k, v, v) alternate between two TMEM accumulator stages, one per epilogue group;
-// the epilogue adds the bias and writes bf16 HEAD-MAJOR  qkv[which][head][row][32]  through a per-warp transpose.
+// Six 128-column chunks (q heads 0-3, 4-7, k, k, v, v) alternate between two TMEM accumulator stages; BOTH epilogue groups
+// drain every chunk (two heads each), which halves the time a stage stays occupied -- the issuer's stage waits would otherwise
+// delay the next tile's tcgen05.cp and stall the producers.  The epilogue adds the bias and writes bf16 HEAD-MAJOR
+// qkv[which][head][row][32]  through a per-warp transpose.
 //
 // Warp roles (576 threads, no setmaxnreg): warps 0-7 epilogue, 8-15 A producers, 16 weight TMA, 17 MMA / tcgen05.cp issuer.
 #pragma once
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
   if (threadIdx.x == 0) {
     for (int i = 0; i < QD_A_SLOTS; ++i) { mbar_init(&a_full[i], QD_PRODUCER_WARPS); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < QK_W_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 17) tmem_alloc(tmem_slot, 512);
@@ -68,28 +70,30 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 8) {
-    // =============================================================== epilogue: group g drains chunks rt with rt & 1 == g
+    // =============================================================== epilogue: group g drains heads 2g, 2g+1 of every chunk
     const int g = warp >> 2;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint8_t* stg = stage_all + warp * 2048;
-    const uint32_t t_s = tmem + lane_base + 256 + g * 128;
-    uint32_t cnt = 0;                                          // chunks consumed by this group
+    uint32_t cnt = 0;                                          // chunks consumed (stage = cnt & 1)
     AXVS_PROF_DECL(1)
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
       const int row0 = tile * 128 + (warp & 3) * 32;           // first row of this warp
 #pragma unroll 1
-      for (int rt = g; rt < 6; rt += 2, ++cnt) {
-        AXVS_PROF_WAIT(0, mbar_wait(&s_full[g], cnt & 1))
+      for (int rt = 0; rt < 6; ++rt, ++cnt) {
+        const int st = cnt & 1;                                // 6 chunks per tile: even, so st == rt & 1
+        AXVS_PROF_WAIT(0, mbar_wait(&s_full[st], (cnt >> 1) & 1))
         tc_fence_after();
+        const uint32_t t_s = tmem + lane_base + 256 + st * 128;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {                          // one head (32 columns) at a time
+        for (int cc = 0; cc < 2; ++cc) {                       // one head (32 columns) at a time
+          const int c = 2 * g + cc;
           float v[32];
           tmem_ld32(t_s + 32 * c, v);
           tmem_ld_wait();
-          if (c == 3) {
+          if (cc == 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[g]);
+            if (lane == 0) mbar_arrive(&s_empty[st]);
           }
           // bias + bf16, then a 2 KiB per-warp transpose so every store instruction writes 512 contiguous bytes
           {

@@ -174,10 +174,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--clips", type=int, default=32, help="clips per GPU per step")
+    ap.add_argument("--clips", type=int, default=42, help="clips per GPU per step (42: res5 = 1.96 and res4 = 7.45 waves of 128-row tiles over 148 SMs)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", type=int, default=0, help="1: replay the resident step from a CUDA graph (launch overhead removed)")
+    ap.add_argument("--graph", type=int, default=1, help="1 (default): replay each step's kernels from a CUDA graph (launch overhead removed); 0: eager launches")
     ap.add_argument("--clip-chunks", type=int, default=1, help="split each level's clips into this many groups, one CUDA stream per (level, group)")
     ap.add_argument("--level-streams", type=int, default=1, help="1: run the two pyramid levels on two CUDA streams (default), 0: serially")
     args = ap.parse_args()
@@ -264,6 +264,7 @@ def main():
     ev_comp = [torch.cuda.Event() for _ in range(2)]      # compute of slot finished
     ev_out = [torch.cuda.Event() for _ in range(2)]       # D2H of slot finished
     e2e_state = {"n": 0, "keep": [None, None]}
+    e2e_graphs = {}
 
     def step_e2e(k):
         slot = e2e_state["n"] & 1
@@ -277,7 +278,21 @@ def main():
                 d_.copy_(h, non_blocking=True)
             ev_in[slot].record(s_in)
         cur.wait_event(ev_in[slot])
-        outs = hot_path(stage_in[slot])
+        if args.graph:
+            # the kernels of the step replay from a CUDA graph captured on this slot's staging buffers; its output buffers are
+            # rewritten two steps later, after the D2H of this slot has been waited for
+            if not first:
+                cur.wait_event(ev_out[slot])
+            g = e2e_graphs.get(slot)
+            if g is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    e2e_graphs[("out", slot)] = hot_path(stage_in[slot])
+                e2e_graphs[slot] = g
+            g.replay()
+            outs = e2e_graphs[("out", slot)]
+        else:
+            outs = hot_path(stage_in[slot])
         ev_used[slot].record(cur)
         gather_summary(outs)
         ev_comp[slot].record(cur)
@@ -287,7 +302,8 @@ def main():
                 pass                                   # host_out2[slot] was drained two steps ago (same stream, in order)
             for o, h in zip(outs, host_out2[slot]):
                 h.copy_(o, non_blocking=True)
-                o.record_stream(s_out)
+                if not args.graph:
+                    o.record_stream(s_out)
             ev_out[slot].record(s_out)
         e2e_state["keep"][slot] = outs
         return outs
@@ -316,22 +332,31 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for k in range(args.warmup):
-        step_resident(k)
-        step_e2e(k)
-    e2e_drain()
-
+    # the clock sampler is started BEFORE the warm-up: nvidia-smi / NVML initialisation takes driver locks for tens of
+    # milliseconds, which must not fall inside the timed regions (it did: 10x outliers of the e2e figure)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.6)
+    # kernels launched per step: counted by the library on one eager step (graph replays do not pass through its entry points)
+    step_resident(0)
+    torch.cuda.synchronize()
     ops.profile_enable(False)                       # reset launch counters
-    if args.graph:
+    step_resident(1)
+    torch.cuda.synchronize()
+    launches_per_step = sum(v["launches"] for v in ops.profile_read().values())
+    if args.graph:                                  # capture outside the warm-up / timed regions (both input sets, both e2e slots)
         for k in range(2):
             step_resident_graph(k)
         torch.cuda.synchronize()
-    ms_total = timed(step_resident_graph if args.graph else step_resident, args.steps)
-    prof0 = ops.profile_read()
-    launches = sum(v["launches"] for v in prof0.values())
+    resident = step_resident_graph if args.graph else step_resident
+    for k in range(args.warmup):
+        resident(k)
+        step_e2e(k)
+    e2e_drain()
+    torch.cuda.synchronize()
+    ms_total = timed(resident, args.steps)
+    launches = launches_per_step * args.steps
     ms_e2e = timed(step_e2e, args.steps, e2e_drain)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -385,7 +410,7 @@ def main():
                 "dtype": "bf16", "data": "synthetic", "config": workload_config(clips),
                 "e2e": {"value": round(e2e_value, 2), "unit": "clips/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                         "ms_per_step": round(ms_e2e / args.steps, 4),
-                        "how": "nn.Module API, pinned host fp32 in/out every step, H2D / kernels / D2H pipelined on 3 streams"},
+                        "how": "nn.Module API, pinned host fp32 in/out every step, H2D / kernels / D2H pipelined on 3 streams" + (", kernels replayed from a CUDA graph" if args.graph else "")},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
