@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(128) spatial_attn_v2_kernel(const __nv_bfloat1
         const size_t r = seq_row0 + qi;
         const size_t off = ((r >> 7) * 4 + kb) * ATT2_KB + sw128_offset((uint32_t)(r & 127), ch0 + chunk);
         *reinterpret_cast<uint4*>(x_img + (size_t)f * tiles * 4 * ATT2_KB + off) = v;
-        if (qi / n == f) *reinterpret_cast<uint4*>(xd_img + off) = v;
+        if ((unsigned)(qi - f * n) < (unsigned)n) *reinterpret_cast<uint4*>(xd_img + off) = v;   // qi / n == f without the division
       }
     }
     __syncwarp();
@@ -343,10 +343,12 @@ __global__ void __launch_bounds__(128) spatial_attn_v2_kernel(const __nv_bfloat1
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
+    int mb = warp / F, f = warp - mb * F;                 // item = mb * F + f, advanced by 4 per iteration without divisions
     for (int item = warp; item < n_mblk * F; item += 4) {
-      const int mb = item / F, f = item - mb * F;
       const uint8_t* sK = sKV + (size_t)f * 2 * NP * 64;
       process(mb, f, sK, sK + NP * 64);
+      f += 4;
+      while (f >= F) { f -= F; ++mb; }
     }
   } else {
     load_kv(0, 0);

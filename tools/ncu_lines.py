@@ -32,7 +32,9 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
-mangled = re.sub(r"\(.*", "", kname).split("::")[-1]
+base_name = re.sub(r"[<(].*", "", kname.replace("void ", "")).split("::")[-1]
+targ = re.search(r"<\(int\)(\d+)>", kname)
+mangled = base_name + (f"ILi{targ.group(1)}E" if targ else "")
 line_of = {}
 cur = None
 infunc = False
