@@ -163,8 +163,8 @@ class MaXTronCCPredictor(nn.Module):
         nn.init.constant_(self._pixel_space_mask_batch_norm.weight, 0.1)
         self.num_classes = num_classes
 
-    def forward(self, mask_embeddings, class_embeddings, pixel_feature, num_clips, num_clip_frames):
-        """mask/class embeddings: bf16 [T*Q, 256] rows (t, q); pixel_feature fp32 [T, 128, V*H, W]."""
+    def class_logits(self, class_embeddings, num_clips):
+        """CC:47-51: class activation softmax over the clips, pooled class embedding, class head + void bias -> [1, Q, K+1]."""
         T = num_clips
         Q = class_embeddings.shape[0] // T
         act = self._transformer_class_activation_head
@@ -173,15 +173,31 @@ class MaXTronCCPredictor(nn.Module):
         void = torch.zeros(self.num_classes, device=pooled.device)
         void[-1] = math.log((self.num_classes - 1) * 0.9 / (1 - 0.9))                                         # add_bias_towards_void
         cls = self._transformer_class_head.run(pooled, torch.float32, extra_bias=void)[:, : self.num_classes]  # [Q, K+1]
-        mk = self._transformer_mask_head.run(mask_embeddings)                                                  # bf16 [T*Q, 256], 128 valid
+        return cls.unsqueeze(0)
+
+    def mask_kernels(self, mask_embeddings):
+        """CC:53: bf16 [T*Q, 256] rows (t, q), 128 valid columns."""
+        return self._transformer_mask_head.run(mask_embeddings)
+
+    def mask_logits(self, mk, pixel_feature, num_clips):
+        """CC:62-68 for `num_clips` clips: mk rows (t, q) of those clips, pixel_feature fp32 [T, 128, V*H, W] -> fp32 [Q, T, V*H*W]."""
+        T = num_clips
+        Q = mk.shape[0] // T
         bn = self._pixel_space_mask_batch_norm
         sc = float(bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps))
         sh = float(bn.bias.detach() - bn.running_mean * sc)
         _, Cp, VH, Wd = pixel_feature.shape
-        P = VH * Wd
-        ml = ops.mask_einsum(pixel_feature.contiguous().float(), mk, T, Q, P, sc, sh)                          # [Q, T, P]
+        return ops.mask_einsum(pixel_feature.contiguous().float(), mk.contiguous(), T, Q, VH * Wd, sc, sh)
+
+    def forward(self, mask_embeddings, class_embeddings, pixel_feature, num_clips, num_clip_frames):
+        """mask/class embeddings: bf16 [T*Q, 256] rows (t, q); pixel_feature fp32 [T, 128, V*H, W]."""
+        T = num_clips
+        Q = class_embeddings.shape[0] // T
+        cls = self.class_logits(class_embeddings, T)
+        ml = self.mask_logits(self.mask_kernels(mask_embeddings), pixel_feature, T)                            # [Q, T, P]
+        _, Cp, VH, Wd = pixel_feature.shape
         V = num_clip_frames
-        return {"class_logits": cls.unsqueeze(0), "mask_logits": ml.view(1, Q, T * V, VH // V, Wd)}
+        return {"class_logits": cls, "mask_logits": ml.view(1, Q, T * V, VH // V, Wd)}
 
 
 class CrossClipTrackingModule(nn.Module):
@@ -238,3 +254,36 @@ class CrossClipTrackingModule(nn.Module):
         for a, m in zip(predictions_class[:-1], predictions_mask[:-1]):
             aux.append({"pred_logits": a, "pred_masks": torch.nn.functional.interpolate(m, size=target_size, mode="trilinear", align_corners=align_corners)})
         return {"pred_logits": predictions_class[-1], "pred_masks": predictions_mask[-1], "aux_outputs": aux}
+
+    def forward_sharded(self, clip_query_local, panoptic_local, n_clips, group=None, gather=None):
+        """Clip-sharded video (one process per GPU): `clip_query_local` [1, Q, T_local, C] and
+        `panoptic_local` [1, 128, T_local*V, H, W] hold this rank's contiguous clips; returns the FINAL layer's
+        {'pred_logits', 'pred_masks'} for the whole video on every rank.  One all-gather of the clip queries before the
+        layers (run redundantly), one of the mask logits after; see `sharding.cross_clip_sharded`."""
+        from . import sharding
+        _require_inference(self, clip_query_local, panoptic_local)
+        b, Q, T_local, C = clip_query_local.shape
+        if b != 1:
+            raise NotImplementedError("axial_vs_b200: the cross-clip module runs one video at a time at inference (as the reference does)")
+        V = self.num_clip_frames
+        _, Cp, TV, Hh, Ww = panoptic_local.shape
+        pf = panoptic_local.reshape(1, Cp, T_local, V, Hh, Ww).permute(0, 2, 1, 3, 4, 5).reshape(T_local, Cp, V * Hh, Ww).contiguous()
+
+        def refine(cq_full):
+            T = cq_full.shape[2]
+            x = cq_full.permute(0, 2, 1, 3).reshape(1, T * Q, C).contiguous().float()
+            x16 = None
+            for i in range(self.num_layers):
+                x = self.transformer_trajectory_self_attention_layers[i](x, seq_len=Q, num_frames=T)
+                x32, x16 = ops.cc_aspp_fwd(x.view(-1, C), self._packed_aspp(i, x.device), 1, T, Q)
+                x = x32.view(1, T * Q, C)
+            ce = self._class_embedding_projection.run(x16)
+            me = self._mask_embedding_projection.run(x16)
+            return self._predictor.class_logits(ce, T), self._predictor.mask_kernels(me)
+
+        def masks(mk_local, pf_local, t_local):
+            return self._predictor.mask_logits(mk_local, pf_local, t_local)
+
+        cls, ml = sharding.cross_clip_sharded(refine, masks, clip_query_local.float(), pf, n_clips, group, gather)
+        T = ml.shape[1]
+        return {"pred_logits": cls, "pred_masks": ml.view(1, Q, T * V, Hh, Ww)}

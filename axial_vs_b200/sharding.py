@@ -40,3 +40,32 @@ def gather_clip_outputs(local: torch.Tensor, n_items: int, group=None) -> torch.
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad.contiguous(), group=group)
     return torch.cat([o[:s] for o, s in zip(out, sizes)], 0)
+
+
+def cross_clip_sharded(refine_fn, mask_fn, clip_query_local: torch.Tensor, pixel_local: torch.Tensor, n_clips: int,
+                       group=None, gather=None):
+    """Cross-clip tracking module over a clip-sharded video.
+
+    Inside one video the module needs every clip's queries, so there is ONE exchange step: the clip queries
+    (`cluster_centers`, [1, Q, T_local, C] per rank) are all-gathered; the cross-clip layers then run REDUNDANTLY on every
+    rank (cheaper than a second exchange); each rank computes mask logits only for its own clips (the mask einsum is
+    per clip, CC:62-67) and the low-resolution mask logits are all-gathered at the end.
+
+    refine_fn(clip_query_full [1, Q, T, C]) -> (class_logits [1, Q, K+1], mask_kernels [T*Q, ...] rows (t, q))
+    mask_fn(mask_kernels_local [T_local*Q, ...], pixel_local, T_local) -> mask logits of the local clips [Q, T_local, ...]
+    gather(x [n_local, ...], n_items) -> [n_items, ...]  (default: `gather_clip_outputs` over `group`)
+    Returns (class_logits, mask_logits [Q, T, ...]) on every rank.
+    """
+    if gather is None:
+        gather = lambda x, n: gather_clip_outputs(x, n, group)
+    _, Q, T_local, C = clip_query_local.shape
+    cq_full = gather(clip_query_local[0].permute(1, 0, 2).contiguous(), n_clips)          # [T, Q, C] in clip order
+    cls, mk = refine_fn(cq_full.permute(1, 0, 2).unsqueeze(0).contiguous())               # redundant on every rank
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    t0, t1 = shard_range(n_clips, rank, world) if world > 1 else (0, T_local)
+    if t1 - t0 != T_local:
+        raise ValueError(f"rank {rank} holds {T_local} clips, the contiguous partition of {n_clips} expects {t1 - t0}")
+    ml_local = mask_fn(mk[t0 * Q:t1 * Q], pixel_local, T_local)                           # [Q, T_local, ...]
+    ml = gather(ml_local.transpose(0, 1).contiguous(), n_clips).transpose(0, 1).contiguous()
+    return cls, ml

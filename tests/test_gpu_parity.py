@@ -435,6 +435,47 @@ def test_cross_clip_module_oracle_cfg3_shard(O):
     assert nerr(m.last_clip_query, ref["clip_query"]) < TOL
 
 
+def test_cross_clip_forward_sharded_equals_unsharded():
+    """Clip-sharded cross-clip module: two emulated ranks (5 clips -> 3 + 2) with an injected gather must give
+    the unsharded module's final predictions bit for bit (the layers run redundantly, the mask einsum is per clip)."""
+    from axial_vs_b200 import cross_clip, sharding
+    Q, T, V, H, W, L, K, seed = 32, 5, 2, 12, 10, 2, 19, 911
+    p = synth.cross_clip_params(seed, L, K)
+    m = cross_clip.CrossClipTrackingModule(num_layers=L, num_classes=K, attn_drop=0.0, aspp_drop=0.0, kernel_sizes=[3, 3, 3],
+                                           atrous_rates=[1, 2, 3], norm_fn="ln", num_clip_frames=V).eval()
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    cq = synth.randn(seed + 1, 1, Q, T, 256).cuda()
+    pf = synth.randn(seed + 2, 1, 128, T * V, H, W).cuda()
+    with torch.no_grad():
+        full = m(cq, pf)
+        # what an all-gather would return on every rank: the concatenation of the shards in clip order
+        bounds = [sharding.shard_range(T, r, 2) for r in range(2)]
+        cq_parts = [cq[0, :, a:b].permute(1, 0, 2).contiguous() for a, b in bounds]
+        masks = []
+        for rank, (a, b) in enumerate(bounds):
+            def gather(x, n, rank=rank):
+                if x.shape[1:] == cq_parts[0].shape[1:]:                       # the clip queries
+                    return torch.cat(cq_parts, 0)
+                masks.append(x)                                                # this rank's mask logits [T_local, Q, P]
+                return torch.cat([x.new_zeros((a,) + x.shape[1:]), x, x.new_zeros((T - b,) + x.shape[1:])], 0)
+            out = _forward_sharded_as_rank(m, cq[:, :, a:b].contiguous(), pf[:, :, a * V:b * V].contiguous(), T, rank, 2, gather)
+            assert torch.equal(out["pred_logits"], full["pred_logits"])
+            assert torch.equal(out["pred_masks"][:, :, a * V:b * V], full["pred_masks"][:, :, a * V:b * V])
+
+
+def _forward_sharded_as_rank(m, cq_local, pf_local, n_clips, rank, world, gather):
+    """forward_sharded with shard_range evaluated for an emulated (rank, world) -- no process group in the GPU tests."""
+    from axial_vs_b200 import sharding
+    import torch.distributed as dist
+    orig_ws, orig_rk, orig_init = dist.get_world_size, dist.get_rank, dist.is_initialized
+    dist.get_world_size, dist.get_rank, dist.is_initialized = (lambda group=None: world), (lambda group=None: rank), (lambda: True)
+    try:
+        return m.forward_sharded(cq_local, pf_local, n_clips, gather=gather)
+    finally:
+        dist.get_world_size, dist.get_rank, dist.is_initialized = orig_ws, orig_rk, orig_init
+
+
 def test_pair_mode_ffn_matches(ops, O):
     """The cta_group::2 (CTA-pair) FFN kernel is opt-in; it must give the same result as the single-CTA kernel."""
     p = synth.axial_layer_params(3)
