@@ -14,6 +14,7 @@
 #include "ffn_fused.cuh"
 #include "qkv_fused.cuh"
 #include "qkv_direct.cuh"
+#include "qkv_attn.cuh"
 #include "cc_tail.cuh"
 #include "decoder_attn.cuh"
 #include "ffn_pair.cuh"
@@ -33,13 +34,13 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel"};
-int g_fusion = 4;
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel"};
+int g_fusion = 4;   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
 int g_pair = 0;   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
@@ -108,7 +109,10 @@ int device_info(DeviceInfo** out) {
   }
   if (!d.qkv_attr) {
     if (cudaFuncSetAttribute(qkv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QK_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(qkv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QD_SMEM_BYTES) != cudaSuccess)
+        cudaFuncSetAttribute(qkv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QD_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(qkv_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(qkv_attn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(qkv_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(qkv_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.qkv_attr = true;
   }
@@ -269,7 +273,7 @@ int axvs_set_pair_mode(int on) {
 }
 int axvs_set_fusion(int level) {
   const int prev = g_fusion;
-  g_fusion = level < 0 ? 0 : (level > 4 ? 4 : level);
+  g_fusion = level < 0 ? 0 : (level > 5 ? 5 : level);
   return prev;
 }
 const char* axvs_last_error(void) { return g_err; }
@@ -368,6 +372,27 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
   if (g_fusion >= 3 && k_in == q_in && w->w_qkv_u && w->w_pq_u && w->w_pkv_u && w->w_proj_u && num_seq <= (1 << 27)) {
     // ---- fused front end: tile-image pack -> TMA-fed q|k|v GEMM (head-major) -> one-shot attention writing tile images
     const int tiles = (int)((rows + 127) / 128);
+    const int nt16_f = (n + 15) / 16;
+    if (g_fusion >= 5 && v_in == q_in && N <= 128 && nt16_f <= 4) {
+      // q|k|v projections and the per-frame attention in one kernel: q, k, v never leave the SM
+      QkvAttnParams ap;
+      memset(&ap, 0, sizeof(ap));
+      ap.src = q_in; ap.pos = pos;
+      ap.w = reinterpret_cast<const uint8_t*>(w->w_qkv_u); ap.bias = w->b_qkv;
+      ap.x_img = ws.x_img; ap.xd_img = ws.xd_img;
+      ap.rows = (int)rows; ap.num_seq = num_seq; ap.N = N; ap.n = n; ap.F = F;
+      ap.S = 128 / N; ap.tiles = (num_seq + ap.S - 1) / ap.S; ap.img_tiles = tiles;
+      ap.map_mode = map; ap.dims = dims; ap.scale_log2e = kScaleLog2e;
+      {
+        ProfScope ps(KC_QKVA, 2.0 * rows * 256.0 * 768.0 + 4.0 * num_seq * (double)N * N * 256,
+                     (double)rows * ((pos ? 2048.0 : 1024.0) + (F + 1) * 512.0), st);
+        const int grid = ap.tiles < d->sms ? ap.tiles : d->sms;
+        if (nt16_f <= 2) qkv_attn_kernel<2><<<grid, QA_THREADS, QA_SMEM_BYTES, st>>>(ap);
+        else if (nt16_f == 3) qkv_attn_kernel<3><<<grid, QA_THREADS, QA_SMEM_BYTES, st>>>(ap);
+        else qkv_attn_kernel<4><<<grid, QA_THREADS, QA_SMEM_BYTES, st>>>(ap);
+      }
+      AXVS_CHECK_LAUNCH("qkv_attn_kernel");
+    } else {
     if (g_fusion >= 4 && v_in == q_in) {
       // the q|k|v GEMM reads the fp32 residual stream (+ pos) itself: no tile-image pack, no a1/a2 round trip
       QkvDirectParams qp;
@@ -435,6 +460,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       x_to_image_kernel<<<blocks_for((long long)rows * F * 32, 256, d->sms), 256, 0, st>>>(ws.x, ws.x_img, ws.xd_img, (int)rows, tiles, F, N, n);
     }
     AXVS_CHECK_LAUNCH("spatial attention");
+    }
     TrajParams tp;
     memset(&tp, 0, sizeof(tp));
     tp.x_img = ws.x_img; tp.xd_img = ws.xd_img;

@@ -332,8 +332,11 @@ def ln_ffn_fwd(x: torch.Tensor, w: PackedLayer) -> torch.Tensor:
     return out
 
 
+DEFAULT_FUSION = 4     # fastest measured level (include/axvs.h lists them); 5 = attention inside the q|k|v kernel, opt-in
+
+
 def set_fusion(level: int) -> int:
-    """Select the fusion level of the composite calls (0 = unfused validation baseline ... highest = default)."""
+    """Select the fusion level of the composite calls (0 = unfused validation baseline ... 5); returns the previous level."""
     return _lib.load().axvs_set_fusion(int(level))
 
 

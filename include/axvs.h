@@ -44,12 +44,15 @@ typedef void* axvs_stream_t;
 int axvs_version(void);
 const char* axvs_last_error(void);
 
-/* Fusion level of the composite entry points (process-wide; default = highest).
+/* Fusion level of the composite entry points (process-wide; default = 4, the fastest measured).
  *   0: one kernel per reference op group (tcgen05 GEMMs + attention + SIMT helpers; validation baseline)
  *   1: + proj_q / proj_kv / temporal softmax / proj / residual fused in one tcgen05 kernel
  *   2: + LayerNorm1 / FFN / residual / LayerNorm2 fused in one tcgen05 kernel
  *   3: + TMA-fed q|k|v projection with head-major output, one-shot per-frame attention writing UMMA tile images
- *   4: + the q|k|v projection reads the fp32 residual stream (+ pos) itself (permute, add and cast inside its A producers)
+ *   4: + the q|k|v projection reads the fp32 residual stream (+ pos) itself (permute, add and cast inside its A producers);
+ *        every UMMA A operand lives in tensor memory
+ *   5: + the per-frame spatial attention runs inside the q|k|v kernel (sequences of at most 128 tokens, frames of at most 64);
+ *        opt-in: bit-identical to level 4 but its 8 drain/attention warps are issue-bound (230 vs 192 us per res4 call)
  * Returns the previous level; values outside the range are clamped. */
 int axvs_set_fusion(int level);
 /* CTA-pair FFN kernel (tcgen05 cta_group::2, two SMs per M = 256 instruction stream) on/off.  Default OFF: it is validated

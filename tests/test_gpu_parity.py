@@ -190,7 +190,7 @@ def test_axial_layer_oracle_config_sizes(O, B, T, H, W):
     assert e < TOL and cos > 0.9999, (e, cos)
 
 
-@pytest.mark.parametrize("B,T,H,W", [(2, 2, 41, 41), (1, 5, 15, 20), (3, 2, 13, 29)])
+@pytest.mark.parametrize("B,T,H,W", [(2, 2, 41, 41), (1, 5, 15, 20), (3, 2, 13, 29), (5, 2, 21, 21), (2, 3, 7, 40), (1, 1, 50, 3)])
 def test_direct_qkv_matches_packed_front_end(ops, B, T, H, W):
     """Fusion level 4 (q|k|v GEMM reading the fp32 stream, every A operand in tensor memory, q2 held as bf16) against
     level 3 (tile-image pack kernel, shared-memory operands, fp32 q2): same bf16 GEMM operands otherwise."""
@@ -201,15 +201,17 @@ def test_direct_qkv_matches_packed_front_end(ops, B, T, H, W):
     layer = _layer(p)
     outs = []
     try:
-        for level in (3, 4):
+        for level in (3, 4, 5):
             ops.set_fusion(level)
             with torch.no_grad():
                 outs.append(layer(src, pos)[0])
             torch.cuda.synchronize()
     finally:
-        ops.set_fusion(99)
+        ops.set_fusion(ops.DEFAULT_FUSION)
     assert torch.isfinite(outs[1]).all()
     assert nerr(outs[1], outs[0]) < 4e-3
+    # level 5 runs the same attention arithmetic on the same bf16 q | k | v inside the projection kernel
+    assert torch.equal(outs[2], outs[1])
 
 
 def test_encoder_config1_two_layers(O):
@@ -286,7 +288,7 @@ def test_fusion_levels_agree(ops, O, Bp, F, n):
             assert nerr(out.cpu() - res.cpu(), ref.reshape(-1, 256)) < TOL, f"fusion level {level}"
             outs.append(out)
     finally:
-        ops.set_fusion(99)
+        ops.set_fusion(ops.DEFAULT_FUSION)
     assert nerr(outs[1], outs[0]) < 5e-3 and nerr(outs[3], outs[0]) < 5e-3
     assert nerr(outs[4], outs[3]) < 4e-3      # level 4: tensor-memory operands, q2 rounded to bf16
 
