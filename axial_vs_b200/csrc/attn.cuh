@@ -38,6 +38,13 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// 2^x for x <= 0 (and -inf -> 0): the hardware approximation without exp2f's range handling
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // smem tiles are [rows][32] bf16 = 64 B rows = 4 chunks of 16 B, chunk index XOR-swizzled with (row>>1)&3
 __device__ __forceinline__ int att_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 
@@ -268,28 +275,31 @@ __global__ void __launch_bounds__(128) spatial_attn_v2_kernel(const __nv_bfloat1
       mma_bf16_16816(s[j], qa[0], kf[0], kf[1]);
       mma_bf16_16816(s[j], qa[1], kf[2], kf[3]);
     }
+    // row maxima over the raw scores (keys >= n masked; only 8-key tiles straddling n need the per-element test), then
+    // p = 2^(s * scale - max * scale) with the scale folded into one FMA per element
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int j = 0; j < 2 * NT16; ++j) {
+      if (j * 8 + 8 > n) {                               // warp-uniform
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = j * 8 + t4 * 2 + (e & 1);
-        const float v = (key < n) ? s[j][e] * scale_log2e : -INFINITY;
-        s[j][e] = v;
-        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        for (int e = 0; e < 4; ++e)
+          if (j * 8 + t4 * 2 + (e & 1) >= n) s[j][e] = -INFINITY;
       }
+      mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
       mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+      mx[h] *= -scale_log2e;                             // every row has at least one valid key: finite
     }
     float rs[2] = {0.f, 0.f};
     uint32_t pa[NT16][4];
 #pragma unroll
     for (int j = 0; j < 2 * NT16; ++j) {
-      const float p0 = exp2f(s[j][0] - mx[0]), p1 = exp2f(s[j][1] - mx[0]);
-      const float p2 = exp2f(s[j][2] - mx[1]), p3 = exp2f(s[j][3] - mx[1]);
+      const float p0 = ex2_approx(fmaf(s[j][0], scale_log2e, mx[0])), p1 = ex2_approx(fmaf(s[j][1], scale_log2e, mx[0]));
+      const float p2 = ex2_approx(fmaf(s[j][2], scale_log2e, mx[1])), p3 = ex2_approx(fmaf(s[j][3], scale_log2e, mx[1]));
       rs[0] += p0 + p1;
       rs[1] += p2 + p3;
       pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(128) spatial_attn_v2_kernel(const __nv_bfloat1
       float l = rs[h];
       l += __shfl_xor_sync(0xffffffffu, l, 1);
       l += __shfl_xor_sync(0xffffffffu, l, 2);
-      const float inv = 1.f / l;
+      const float inv = __frcp_rn(l);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint32_t*>(stg + att_off(g + h * 8, j) + t4 * 4) = pack_bf16x2(acc[j][h * 2] * inv, acc[j][h * 2 + 1] * inv);

@@ -155,28 +155,29 @@ __global__ void __launch_bounds__(QA_THREADS, 1) qkv_attn_kernel(const QkvAttnPa
               mma_bf16_16816(sc[j], qa[0], kf[0], kf[1]);
               mma_bf16_16816(sc[j], qa[1], kf[2], kf[3]);
             }
-            float mx[2] = {-INFINITY, -INFINITY};
+            float mx[2] = {-INFINITY, -INFINITY};          // same arithmetic as spatial_attn_v2_kernel (bit-identical results)
 #pragma unroll
             for (int j = 0; j < 2 * NT16; ++j) {
+              if (j * 8 + 8 > p.n) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int key = j * 8 + t4 * 2 + (e & 1);
-                const float v = (key < p.n) ? sc[j][e] * p.scale_log2e : -INFINITY;
-                sc[j][e] = v;
-                mx[e >> 1] = fmaxf(mx[e >> 1], v);
+                for (int e = 0; e < 4; ++e)
+                  if (j * 8 + t4 * 2 + (e & 1) >= p.n) sc[j][e] = -INFINITY;
               }
+              mx[0] = fmaxf(mx[0], fmaxf(sc[j][0], sc[j][1]));
+              mx[1] = fmaxf(mx[1], fmaxf(sc[j][2], sc[j][3]));
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
               mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+              mx[h] *= -p.scale_log2e;
             }
             float rs[2] = {0.f, 0.f};
             uint32_t pa[NT16][4];
 #pragma unroll
             for (int j = 0; j < 2 * NT16; ++j) {
-              const float p0 = exp2f(sc[j][0] - mx[0]), p1 = exp2f(sc[j][1] - mx[0]);
-              const float p2 = exp2f(sc[j][2] - mx[1]), p3 = exp2f(sc[j][3] - mx[1]);
+              const float p0 = ex2_approx(fmaf(sc[j][0], p.scale_log2e, mx[0])), p1 = ex2_approx(fmaf(sc[j][1], p.scale_log2e, mx[0]));
+              const float p2 = ex2_approx(fmaf(sc[j][2], p.scale_log2e, mx[1])), p3 = ex2_approx(fmaf(sc[j][3], p.scale_log2e, mx[1]));
               rs[0] += p0 + p1;
               rs[1] += p2 + p3;
               pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(QA_THREADS, 1) qkv_attn_kernel(const QkvAttnPa
               float l = rs[h];
               l += __shfl_xor_sync(0xffffffffu, l, 1);
               l += __shfl_xor_sync(0xffffffffu, l, 2);
-              const float inv = 1.f / l;
+              const float inv = __frcp_rn(l);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 *reinterpret_cast<uint32_t*>(stg + att_off(gq + h * 8, j) + t4 * 4) = pack_bf16x2(acc[j][h * 2] * inv, acc[j][h * 2 + 1] * inv);
