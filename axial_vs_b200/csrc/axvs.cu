@@ -34,12 +34,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel"};
 int g_fusion = 4;   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
 int g_pair = 0;   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
@@ -474,12 +474,12 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
     tp.scale_log2e = kScaleLog2e;
     tp.ln_g = ln_g; tp.ln_b = ln_b; tp.ln_img = ln_img; tp.ln_eps = 1e-5f;
     {
-      ProfScope ps(KC_TRAJ, 2.0 * rows * 256.0 * 256.0 * (2.0 + 2.0 * F) + 4.0 * rows * F * 256.0,
-                   (double)rows * (512.0 * (F + 1) + 1024.0 + (resid ? 1024.0 : 0.0)), st);
+      ProfScope ps(g_fusion >= 4 ? KC_TRAJTS : KC_TRAJ, 2.0 * rows * 256.0 * 256.0 * (2.0 + 2.0 * F) + 4.0 * rows * F * 256.0,
+                   (double)rows * (512.0 * (F + 1) + 1024.0 + (resid ? 1024.0 : 0.0) + (ln_img ? 1536.0 : 0.0)), st);
       if (g_fusion >= 4) traj_ts_kernel<<<tiles < d->sms ? tiles : d->sms, TF_THREADS, TT_SMEM_BYTES, st>>>(tp);
       else traj_fused_kernel<<<tiles < d->sms ? tiles : d->sms, TF_THREADS, TF_SMEM_BYTES, st>>>(tp);
     }
-    AXVS_CHECK_LAUNCH("traj_fused_kernel");
+    AXVS_CHECK_LAUNCH("traj_ts_kernel / traj_fused_kernel");
     return AXVS_OK;
   }
 
