@@ -218,48 +218,15 @@ namespace axvs {
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int ATT2_KB = 16384;   // bytes of one 128-row x 64-column image K-block
 
+// One (16-query block, key frame) work item of a (sequence, head): S = Q K_f^T, one-shot softmax over the frame's n keys, P V_f,
+// then the x_f (+ x_diag) rows written as 16-byte pieces of the SWIZZLE_128B tile images traj_*_kernel consumes.
+// sQ / sK / sV: [rows][64 B] tiles (att_off swizzle); stg: this warp's 1 KiB staging; kb / ch0: K-block and first 16-byte chunk
+// of the head's 32 channels inside an image row.
 template <int NT16>
-__global__ void __launch_bounds__(128) spatial_attn_v2_kernel(const __nv_bfloat16* __restrict__ qkv, size_t rows_total, uint8_t* __restrict__ x_img,
-                                                              uint8_t* __restrict__ xd_img, int tiles, int N, int n, int F, float scale_log2e,
-                                                              int all_frames) {
-  extern __shared__ __align__(128) uint8_t att_smem[];
-  constexpr int NP = 16 * NT16;
-  const int n_mblk = (N + 15) >> 4;
-  const int kv_bufs = all_frames ? F : 2;
-  uint8_t* sQ = att_smem;                                  // [n_mblk*16][64 B]
-  uint8_t* sKV = sQ + (size_t)n_mblk * 16 * 64;            // [kv_bufs][K | V][NP][64 B]
-  uint8_t* sStage = sKV + (size_t)kv_bufs * 2 * NP * 64;   // [4 warps][16 rows][64 B]
-
-  const int seq = blockIdx.x >> 3, head = blockIdx.x & 7;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const size_t seq_row0 = (size_t)seq * N;
-  const __nv_bfloat16* gq = qkv + ((size_t)(0 * 8 + head) * rows_total + seq_row0) * 32;
-  const __nv_bfloat16* gk = qkv + ((size_t)(1 * 8 + head) * rows_total + seq_row0) * 32;
-  const __nv_bfloat16* gv = qkv + ((size_t)(2 * 8 + head) * rows_total + seq_row0) * 32;
-
-  for (int c = tid; c < n_mblk * 16 * 4; c += 128) {
-    const int r = c >> 2, ch = c & 3;
-    const bool ok = r < N;
-    cp_async16(sQ + att_off(r, ch), gq + (size_t)(ok ? r : 0) * 32 + ch * 8, ok);
-  }
-  auto load_kv = [&](int f, int buf) {
-    uint8_t* sK = sKV + (size_t)buf * 2 * NP * 64;
-    uint8_t* sV = sK + NP * 64;
-    for (int c = tid; c < NP * 4; c += 128) {
-      const int r = c >> 2, ch = c & 3;
-      const bool ok = r < n;
-      const size_t off = (size_t)(f * n + (ok ? r : 0)) * 32 + ch * 8;
-      cp_async16(sK + att_off(r, ch), gk + off, ok);
-      cp_async16(sV + att_off(r, ch), gv + off, ok);
-    }
-  };
-
+__device__ __forceinline__ void attn_item(const uint8_t* sQ, const uint8_t* sK, const uint8_t* sV, uint8_t* stg, int mb, int f, int N, int n,
+                                          float scale_log2e, size_t seq_row0, int kb, int ch0, int tiles, uint8_t* __restrict__ x_img,
+                                          uint8_t* __restrict__ xd_img, int lane) {
   const int g = lane >> 2, t4 = lane & 3;
-  uint8_t* stg = sStage + warp * 1024;
-  const int kb = head >> 1, ch0 = (head & 1) * 4;
-
-  // one (16-query block, key frame) work item: S = Q K_f^T, one-shot softmax, P V_f, write x_f (+ x_diag) image rows
-  auto process = [&](int mb, int f, const uint8_t* sK, const uint8_t* sV) {
     uint32_t qa[2][4];
     {
       const int r = mb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -345,6 +312,50 @@ __global__ void __launch_bounds__(128) spatial_attn_v2_kernel(const __nv_bfloat1
       }
     }
     __syncwarp();
+}
+
+
+template <int NT16>
+__global__ void __launch_bounds__(128) spatial_attn_v2_kernel(const __nv_bfloat16* __restrict__ qkv, size_t rows_total, uint8_t* __restrict__ x_img,
+                                                              uint8_t* __restrict__ xd_img, int tiles, int N, int n, int F, float scale_log2e,
+                                                              int all_frames) {
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  constexpr int NP = 16 * NT16;
+  const int n_mblk = (N + 15) >> 4;
+  const int kv_bufs = all_frames ? F : 2;
+  uint8_t* sQ = att_smem;                                  // [n_mblk*16][64 B]
+  uint8_t* sKV = sQ + (size_t)n_mblk * 16 * 64;            // [kv_bufs][K | V][NP][64 B]
+  uint8_t* sStage = sKV + (size_t)kv_bufs * 2 * NP * 64;   // [4 warps][16 rows][64 B]
+
+  const int seq = blockIdx.x >> 3, head = blockIdx.x & 7;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t seq_row0 = (size_t)seq * N;
+  const __nv_bfloat16* gq = qkv + ((size_t)(0 * 8 + head) * rows_total + seq_row0) * 32;
+  const __nv_bfloat16* gk = qkv + ((size_t)(1 * 8 + head) * rows_total + seq_row0) * 32;
+  const __nv_bfloat16* gv = qkv + ((size_t)(2 * 8 + head) * rows_total + seq_row0) * 32;
+
+  for (int c = tid; c < n_mblk * 16 * 4; c += 128) {
+    const int r = c >> 2, ch = c & 3;
+    const bool ok = r < N;
+    cp_async16(sQ + att_off(r, ch), gq + (size_t)(ok ? r : 0) * 32 + ch * 8, ok);
+  }
+  auto load_kv = [&](int f, int buf) {
+    uint8_t* sK = sKV + (size_t)buf * 2 * NP * 64;
+    uint8_t* sV = sK + NP * 64;
+    for (int c = tid; c < NP * 4; c += 128) {
+      const int r = c >> 2, ch = c & 3;
+      const bool ok = r < n;
+      const size_t off = (size_t)(f * n + (ok ? r : 0)) * 32 + ch * 8;
+      cp_async16(sK + att_off(r, ch), gk + off, ok);
+      cp_async16(sV + att_off(r, ch), gv + off, ok);
+    }
+  };
+
+  uint8_t* stg = sStage + warp * 1024;
+  const int kb = head >> 1, ch0 = (head & 1) * 4;
+
+  auto process = [&](int mb, int f, const uint8_t* sK, const uint8_t* sV) {
+    attn_item<NT16>(sQ, sK, sV, stg, mb, f, N, n, scale_log2e, seq_row0, kb, ch0, tiles, x_img, xd_img, lane);
   };
 
   if (all_frames) {
@@ -373,6 +384,71 @@ __global__ void __launch_bounds__(128) spatial_attn_v2_kernel(const __nv_bfloat1
       for (int mb = warp; mb < n_mblk; mb += 4) process(mb, f, sK, sK + NP * 64);
       __syncthreads();   // all warps done with this frame's K/V buffer before it is refilled
     }
+  }
+}
+
+// Persistent, double-buffered variant for sequences whose q | k | v of one head fit twice in shared memory (the axial passes):
+// each CTA walks (sequence, head) work items with a grid stride and loads the NEXT item's operands with cp.async while the four
+// warps compute the current one, so the ~2 us load round trip that made up 30 % of the one-shot kernel's samples is hidden.
+template <int NT16>
+__global__ void __launch_bounds__(128) spatial_attn_v3_kernel(const __nv_bfloat16* __restrict__ qkv, size_t rows_total, uint8_t* __restrict__ x_img,
+                                                              uint8_t* __restrict__ xd_img, int tiles, int N, int n, int F, float scale_log2e,
+                                                              int num_work) {
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  constexpr int NP = 16 * NT16;
+  const int n_mblk = (N + 15) >> 4;
+  const size_t q_bytes = (size_t)n_mblk * 16 * 64, kv_bytes = (size_t)F * 2 * NP * 64, buf_bytes = q_bytes + kv_bytes;
+  uint8_t* sStage = att_smem + 2 * buf_bytes;              // [4 warps][16 rows][64 B]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* stg = sStage + warp * 1024;
+
+  auto load_item = [&](int w, int buf) {
+    const int seq = w >> 3, head = w & 7;
+    const size_t seq_row0 = (size_t)seq * N;
+    const __nv_bfloat16* gq = qkv + ((size_t)(0 * 8 + head) * rows_total + seq_row0) * 32;
+    const __nv_bfloat16* gk = qkv + ((size_t)(1 * 8 + head) * rows_total + seq_row0) * 32;
+    const __nv_bfloat16* gv = qkv + ((size_t)(2 * 8 + head) * rows_total + seq_row0) * 32;
+    uint8_t* sQ = att_smem + (size_t)buf * buf_bytes;
+    uint8_t* sKV = sQ + q_bytes;
+    for (int c = tid; c < n_mblk * 16 * 4; c += 128) {
+      const int r = c >> 2, ch = c & 3;
+      const bool ok = r < N;
+      cp_async16(sQ + att_off(r, ch), gq + (size_t)(ok ? r : 0) * 32 + ch * 8, ok);
+    }
+    for (int f = 0; f < F; ++f) {
+      uint8_t* sK = sKV + (size_t)f * 2 * NP * 64;
+      uint8_t* sV = sK + NP * 64;
+      for (int c = tid; c < NP * 4; c += 128) {
+        const int r = c >> 2, ch = c & 3;
+        const bool ok = r < n;
+        const size_t off = (size_t)(f * n + (ok ? r : 0)) * 32 + ch * 8;
+        cp_async16(sK + att_off(r, ch), gk + off, ok);
+        cp_async16(sV + att_off(r, ch), gv + off, ok);
+      }
+    }
+  };
+
+  int w = blockIdx.x;
+  if (w < num_work) load_item(w, 0);
+  cp_async_commit();
+  const int mb0 = warp / F, f0 = warp - mb0 * F;
+  for (int it = 0; w < num_work; w += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (w + (int)gridDim.x < num_work) load_item(w + gridDim.x, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();                                    // the current item's operands have landed
+    __syncthreads();
+    const int seq = w >> 3, head = w & 7;
+    const uint8_t* sQ = att_smem + (size_t)buf * buf_bytes;
+    const uint8_t* sKV = sQ + q_bytes;
+    int mb = mb0, f = f0;                                  // item = mb * F + f, advanced by 4 per iteration without divisions
+    for (int item = warp; item < n_mblk * F; item += 4) {
+      const uint8_t* sK = sKV + (size_t)f * 2 * NP * 64;
+      attn_item<NT16>(sQ, sK, sK + NP * 64, stg, mb, f, N, n, scale_log2e, (size_t)seq * N, head >> 1, (head & 1) * 4, tiles, x_img, xd_img, lane);
+      f += 4;
+      while (f >= F) { f -= F; ++mb; }
+    }
+    __syncthreads();                                       // every warp is done with this buffer before it is refilled
   }
 }
 

@@ -123,7 +123,12 @@ int device_info(DeviceInfo** out) {
         cudaFuncSetAttribute(spatial_attn_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
         cudaFuncSetAttribute(spatial_attn_v2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
         cudaFuncSetAttribute(spatial_attn_v2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
-        cudaFuncSetAttribute(spatial_attn_v2_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
+        cudaFuncSetAttribute(spatial_attn_v2_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_v3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_v3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_v3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_v3_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_v3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(spatial_attn_v2) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.attn2_attr = true;
   }
@@ -435,7 +440,23 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
     const size_t kv_all = (size_t)F * 2 * 16 * np_sel * 64;
     const int all_frames = (att_q + kv_all <= 64 * 1024) ? 1 : 0;          // small sequences: every frame's K/V resident
     const size_t att_smem = att_q + (all_frames ? kv_all : (size_t)4 * 16 * np_sel * 64);
-    if (nt16 <= 11 && att_smem <= 200 * 1024) {
+    const size_t att3_smem = 2 * (att_q - 4096 + kv_all) + 4096;                // persistent kernel: two operand buffers + staging
+    if (all_frames && nt16 <= 8 && att3_smem <= 100 * 1024 && num_seq <= (1 << 27)) {
+      ProfScope ps(KC_ATTN2, 4.0 * num_seq * (double)N * N * 256, (double)rows * (1536.0 + (F + 1) * 512.0), st);
+      int per_sm = (int)((size_t)(227 * 1024) / (att3_smem + 1024));
+      const int reg_cap = np_sel == 2 ? 8 : np_sel == 3 ? 6 : np_sel == 4 ? 5 : np_sel == 6 ? 3 : 2;   // 128 threads x 56 / 79 / 96 / 143 / 168 registers
+      if (per_sm > reg_cap) per_sm = reg_cap;
+      const int num_work = num_seq * 8;
+      int grid = d->sms * per_sm;
+      if (grid > num_work) grid = num_work;
+#define AXVS_ATT3(NT) spatial_attn_v3_kernel<NT><<<grid, 128, att3_smem, st>>>(ws.qkv, rows, ws.x_img, ws.xd_img, tiles, N, n, F, kScaleLog2e, num_work)
+      if (np_sel == 2) AXVS_ATT3(2);
+      else if (np_sel == 3) AXVS_ATT3(3);
+      else if (np_sel == 4) AXVS_ATT3(4);
+      else if (np_sel == 6) AXVS_ATT3(6);
+      else AXVS_ATT3(8);
+#undef AXVS_ATT3
+    } else if (nt16 <= 11 && att_smem <= 200 * 1024) {
       ProfScope ps(KC_ATTN2, 4.0 * num_seq * (double)N * N * 256, (double)rows * (1536.0 + (F + 1) * 512.0), st);
       const dim3 grid((unsigned)num_seq * 8);
 #define AXVS_ATT2(NT) spatial_attn_v2_kernel<NT><<<grid, 128, att_smem, st>>>(ws.qkv, rows, ws.x_img, ws.xd_img, tiles, N, n, F, kScaleLog2e, all_frames)
