@@ -77,6 +77,8 @@ class TrajectoryAttention(nn.Module):
         if N % F:
             raise RuntimeError(f"sequence length {N} is not a multiple of num_frames {F}")
         n = N // F
+        if query.numel() == 0:                    # empty batch of sequences
+            return query.new_empty(Bp, N, C), None
         q = query.contiguous().float()
         k = q if key is query else key.contiguous().float()
         v = q if value is query else value.contiguous().float()
@@ -117,6 +119,8 @@ class _LayerBase(nn.Module):
 
     def _run(self, src: Tensor, pos: Tensor) -> Tensor:
         _require_inference(self, src, pos)
+        if src.numel() == 0:                      # empty batch of clips: nothing to launch (the reference returns an empty tensor too)
+            return src.clone()
         out = ops.axial_layer_fwd(src.contiguous().float(), pos.contiguous().float(), self.packed(src.device), self.axial)
         return out.to(src.dtype)
 

@@ -264,6 +264,40 @@ def test_cpu_tensor_is_rejected():
         layer(torch.zeros(2, 4, 256), torch.zeros(1, 2, 2, 2, 256))
 
 
+def test_sweep_max_size_sequence_independence():
+    """BASELINE configs[4] corner (T=10, 161x161: 161 sequences of 1610 tokens, frames of 161 keys) -- far beyond what the CPU
+    oracle can check, so use the size-independent property: every sequence's result is independent of the rest of the batch
+    (bit-exact), finite, and the attention over a single frame (F=1 slice) matches the oracle on a small sub-problem."""
+    from axial_vs_b200.modules import TrajectoryAttention
+    g = torch.Generator().manual_seed(4242)
+    p = {}
+    synth.traj_attn_params(g, "", 256, p)
+    ta = TrajectoryAttention(256, 8, 0.0).eval()
+    ta.load_state_dict(p, strict=True)
+    ta.cuda()
+    Bp, F, n = 161, 10, 161
+    x = torch.randn(Bp, F * n, 256, generator=g).cuda()
+    with torch.no_grad():
+        full, _ = ta(x, x, x, num_frames=F)
+        part, _ = ta(x[:3].contiguous(), x[:3].contiguous(), x[:3].contiguous(), num_frames=F)
+    assert torch.isfinite(full).all()
+    assert torch.equal(full[:3], part)
+
+
+def test_empty_batch_returns_empty():
+    """Zero clips: the modules return empty tensors of the right shape without launching anything (reference behaviour)."""
+    p = synth.axial_layer_params(5)
+    layer = _layer(p)
+    with torch.no_grad():
+        out, hm, wm = layer(torch.empty(0, 6 * 5, 256, device="cuda"), torch.empty(0, 2, 6, 5, 256, device="cuda"))
+    assert out.shape == (0, 30, 256) and hm is None and wm is None
+    from axial_vs_b200.modules import TrajectoryAttention
+    ta = TrajectoryAttention(256, 8, 0.0).eval().cuda()
+    with torch.no_grad():
+        y, maps = ta(torch.empty(0, 10, 256, device="cuda"), torch.empty(0, 10, 256, device="cuda"), torch.empty(0, 10, 256, device="cuda"), num_frames=2)
+    assert y.shape == (0, 10, 256) and maps is None
+
+
 def test_training_mode_is_rejected():
     from axial_vs_b200 import modules
     layer = modules.TemporalAxialTrajectoryAttentionLayer().cuda().train()
