@@ -103,16 +103,19 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnParam
         tc_fence_after();
         const uint32_t t_s = tmem + lane_base + 256 + stage * 128 + 64 * g;
         uint32_t hpk[32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float v[32];
-          tmem_ld32(t_s + 32 * c, v); tmem_ld_wait();
-          const float4* b4 = reinterpret_cast<const float4*>(sb1 + j * 128 + 64 * g + c * 32);
+        {
+          float v0[32], v1[32];                                    // both halves in flight: one TMEM round trip per chunk
+          tmem_ld32(t_s, v0);
+          tmem_ld32(t_s + 32, v1);
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(sb1 + j * 128 + 64 * g);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 bb = b4[i];
-            hpk[c * 16 + 2 * i] = pack_bf16x2(fmaxf(v[4 * i] + bb.x, 0.f), fmaxf(v[4 * i + 1] + bb.y, 0.f));
-            hpk[c * 16 + 2 * i + 1] = pack_bf16x2(fmaxf(v[4 * i + 2] + bb.z, 0.f), fmaxf(v[4 * i + 3] + bb.w, 0.f));
+            const float4 bb = b4[i], bc = b4[8 + i];
+            hpk[2 * i] = pack_bf16x2(fmaxf(v0[4 * i] + bb.x, 0.f), fmaxf(v0[4 * i + 1] + bb.y, 0.f));
+            hpk[2 * i + 1] = pack_bf16x2(fmaxf(v0[4 * i + 2] + bb.z, 0.f), fmaxf(v0[4 * i + 3] + bb.w, 0.f));
+            hpk[16 + 2 * i] = pack_bf16x2(fmaxf(v1[4 * i] + bc.x, 0.f), fmaxf(v1[4 * i + 1] + bc.y, 0.f));
+            hpk[16 + 2 * i + 1] = pack_bf16x2(fmaxf(v1[4 * i + 2] + bc.z, 0.f), fmaxf(v1[4 * i + 3] + bc.w, 0.f));
           }
         }
         // the 64 fp32 columns this thread just read become 32 columns of bf16 pairs at the start of the same region
