@@ -62,6 +62,9 @@ SIGNATURES = {
     "axvs_query_self_attn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "axvs_kmeans_update_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "axvs_kmeans_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "axvs_proj_workspace_bytes": (c_size_t, [c_int]),
+    "axvs_input_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    "axvs_output_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "axvs_mask_einsum": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "axvs_pos3d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "axvs_profile_enable": (c_int, [c_int]),

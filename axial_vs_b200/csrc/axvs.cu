@@ -17,6 +17,7 @@
 #include "qkv_attn.cuh"
 #include "cc_tail.cuh"
 #include "decoder_attn.cuh"
+#include "proj.cuh"
 #include "ffn_pair.cuh"
 
 using namespace axvs;
@@ -34,12 +35,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels"};
 int g_fusion = 4;   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
 int g_pair = 0;   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
@@ -910,6 +911,51 @@ int axvs_kmeans_update(const float* mask_logits, const float* pixel_value, float
     kmeans_reduce_kernel<<<dim3(KM_D / 32, (L + 31) / 32, N), 256, 0, (cudaStream_t)stream>>>(partial, counts, out, chunks, L, advanced ? 1 : 0);
   }
   AXVS_CHECK_LAUNCH("kmeans_update kernels");
+  return AXVS_OK;
+}
+
+size_t axvs_proj_workspace_bytes(int images) {
+  if (images <= 0) return 0;
+  return (size_t)images * GN_CHUNKS * GN_GROUPS * sizeof(float2) + 256;
+}
+
+int axvs_input_proj_fwd(const float* x_nchw, const void* w_packed, const float* bias, const float* gn_w, const float* gn_b, float* out_tokens,
+                        int images, int c_in, int hw, float eps, void* workspace, size_t workspace_bytes, axvs_stream_t stream) {
+  if (!x_nchw || !w_packed || !gn_w || !gn_b || !out_tokens) return fail(AXVS_E_INVALID, "input_proj: null pointer");
+  if (images <= 0 || c_in <= 0 || hw <= 0) return fail(AXVS_E_INVALID, "input_proj: sizes must be positive");
+  if (c_in % 64) return fail(AXVS_E_UNSUPPORTED, "input_proj: the channel count must be a multiple of 64 (got %d)", c_in);
+  if ((long long)images * hw > 0x7fffffffLL) return fail(AXVS_E_UNSUPPORTED, "input_proj: too many pixels");
+  const size_t need = axvs_proj_workspace_bytes(images);
+  if (!workspace || workspace_bytes < need) return fail(AXVS_E_WORKSPACE, "input_proj: workspace of %zu bytes required (got %zu)", need, workspace_bytes);
+  const int M = images * hw;
+  GemmParams p = gemm_params(nullptr, c_in, M, c_in, w_packed, 256, 0, bias, 256, 1.f, 0, out_tokens, 256, 0, 0, nullptr);
+  p.a_diag = 3; p.A32 = x_nchw; p.a_n = hw;
+  if (int rc = launch_gemm(p, (cudaStream_t)stream)) return rc;
+  float2* partial = reinterpret_cast<float2*>(workspace);
+  {
+    ProfScope ps(KC_GN, 0, (double)M * 256 * 12.0, (cudaStream_t)stream);
+    gn_tokens_stats_kernel<<<dim3(GN_CHUNKS, images), 256, 0, (cudaStream_t)stream>>>(out_tokens, partial, hw);
+    gn_tokens_apply_kernel<<<dim3(GN_CHUNKS, images), 256, 0, (cudaStream_t)stream>>>(out_tokens, partial, gn_w, gn_b, hw, eps);
+  }
+  AXVS_CHECK_LAUNCH("gn_tokens kernels");
+  return AXVS_OK;
+}
+
+int axvs_output_proj_fwd(const float* tokens, const void* w_packed, const float* bias, const float* gn_w, const float* gn_b, float* out_nchw,
+                         int images, int c_out, int hw, float eps, axvs_stream_t stream) {
+  if (!tokens || !w_packed || !gn_w || !gn_b || !out_nchw) return fail(AXVS_E_INVALID, "output_proj: null pointer");
+  if (images <= 0 || c_out <= 0 || hw <= 0) return fail(AXVS_E_INVALID, "output_proj: sizes must be positive");
+  if (c_out % 256) return fail(AXVS_E_UNSUPPORTED, "output_proj: the channel count must be a multiple of 256 (got %d)", c_out);
+  if ((long long)images * hw > 0x7fffffffLL || images > 65535) return fail(AXVS_E_UNSUPPORTED, "output_proj: too many pixels / images");
+  const int M = images * hw;
+  GemmParams p = gemm_params(nullptr, 256, M, 256, w_packed, c_out, 0, bias, c_out, 1.f, 0, out_nchw, c_out, 0, 0, nullptr);
+  p.a_diag = 4; p.A32 = tokens; p.out_nchw = hw;
+  if (int rc = launch_gemm(p, (cudaStream_t)stream)) return rc;
+  {
+    ProfScope ps(KC_GN, 0, (double)M * c_out * 12.0, (cudaStream_t)stream);
+    gn_nchw_kernel<<<dim3(GN_GROUPS, images), 256, 0, (cudaStream_t)stream>>>(out_nchw, gn_w, gn_b, c_out, hw, eps);
+  }
+  AXVS_CHECK_LAUNCH("gn_nchw_kernel");
   return AXVS_OK;
 }
 

@@ -62,7 +62,12 @@ struct GemmParams {
                 // 2: temporal 3-tap gather for the cross-clip ASPP convs (K = 3*256): rows are (b, t, q) with a_n = Q rows
                 //    per time step, a_N = T steps, a_F = dilation; K-block kb reads channels (kb&3)*64.. of the row at
                 //    time clamp(t + (kb/4 - 1) * dilation, 0, T-1)  (Conv1d k=3, padding 'same', replicate; CC:180-182)
+                // 3: A32 is an fp32 NCHW feature map [images, K channels, a_n pixels] (Conv2d 1x1 input, WC/msdeformattn.py:355-358):
+                //    logical row r = image r / a_n, pixel r % a_n; the producers transpose while converting (thread = pixel row,
+                //    eight 4-byte loads at a stride of a_n floats -> one 16-byte chunk of the K-major image)
+                // 4: A32 is an fp32 row-major matrix [M, lda] (token rows), converted to bf16 on the fly
   int a_N, a_n, a_F;
+  const float* A32;
   // W operand (packed) and bias
   const uint8_t* Wp;
   int w_rows_total;   // rows of the packed image (K-block stride = w_rows_total * 128 B)
@@ -79,6 +84,8 @@ struct GemmParams {
   const float* resid;   // optional fp32 residual, same row map / ld as out (fp32 path only)
   int map_mode;         // RowMap applied to output (and residual) rows
   AxialDims dims;
+  int out_nchw;         // > 0: fp32 output is NCHW [images, n_out, out_nchw pixels] (Conv2d 1x1 output): row r = image r / out_nchw,
+                        //      pixel r % out_nchw; every column is one coalesced 4-byte store per lane (lanes = consecutive pixels)
 };
 
 __device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, int row, int col, float (&v)[32]) {
@@ -90,6 +97,13 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, int row
     if (p.relu == 1) x = fmaxf(x, 0.f);
     else if (p.relu == 2) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
     v[i] = x;
+  }
+  if (p.out_nchw > 0) {
+    const int img = row / p.out_nchw, pix = row - img * p.out_nchw;
+    float* o = reinterpret_cast<float*>(p.out) + ((size_t)img * p.n_out + col) * p.out_nchw + pix;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[(size_t)i * p.out_nchw] = v[i];
+    return;
   }
   int orow = pass_to_canonical(row, p.map_mode, p.dims);
   if (p.out_bf16) {
@@ -245,6 +259,49 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
         } else {
           rowp[i] = nullptr;
         }
+      }
+      if (p.a_diag >= 3) {
+        // fp32 sources.  Mode 3 (NCHW): thread = pixel row ptid, i = 16-byte chunk (8 channels); mode 4: q = i * PT + ptid as below.
+        const int r3 = mt * GEMM_BM + ptid;
+        const int img = (p.a_diag == 3 && r3 < p.M) ? r3 / p.a_n : 0;
+        const float* base3 = p.A32 + ((size_t)img * p.K) * p.a_n + (r3 - img * p.a_n);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          uint4 v[ITERS];
+#pragma unroll
+          for (int i = 0; i < ITERS; ++i) {
+            float f[8];
+            if (p.a_diag == 3) {
+              const float* s = base3 + (size_t)(kb * GEMM_BK + i * 8) * p.a_n;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = r3 < p.M ? __ldg(s + (size_t)j * p.a_n) : 0.f;
+            } else {
+              const int q = i * PT + ptid;
+              const int r = mt * GEMM_BM + (q >> 3);
+              if (r < p.M) {
+                const float4* s = reinterpret_cast<const float4*>(p.A32 + (size_t)r * p.lda + kb * GEMM_BK + (q & 7) * 8);
+                const float4 a = __ldg(s), b = __ldg(s + 1);
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = 0.f;
+              }
+            }
+            v[i] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* dst = smem + stage * GEMM_STAGE_BYTES;
+#pragma unroll
+          for (int i = 0; i < ITERS; ++i) {
+            const int q = i * PT + ptid;
+            const uint32_t off = (p.a_diag == 3) ? sw128_offset(ptid, i) : sw128_offset(q >> 3, q & 7);
+            *reinterpret_cast<uint4*>(dst + off) = v[i];
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[stage]);
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        continue;
       }
       for (int kb = 0; kb < num_kb; ++kb) {
         uint4 v[ITERS];

@@ -1,0 +1,102 @@
+// Within-clip input / output projections: Conv2d 1x1 + GroupNorm(32) on either side of the
+// transformer encoder -- WC/msdeformattn.py:355-375 (definition), :413-416 (input side), :432-434 (output side).
+// The 1x1 convolutions run on the generic tcgen05 GEMM (gemm.cuh): the input side reads the NCHW backbone feature directly
+// (transposing fp32 -> bf16 producers, a_diag = 3) and writes token-major rows [image, pixel, 256] -- the layout the
+// temporal layers consume, so the reference's flatten(2).transpose(1,2) copy disappears; the output side reads token rows
+// (a_diag = 4) and writes NCHW.  GroupNorm is applied in place by the kernels below (deterministic: fixed-order reductions).
+#pragma once
+#include "simt.cuh"
+
+namespace axvs {
+
+constexpr int GN_GROUPS = 32;
+constexpr int GN_CHUNKS = 8;          // pixel chunks per image in the token-major statistics pass
+
+// ---- token-major [images, HW, 256]: group g = channels 8g..8g+7 of every pixel --------------------------------------------
+// pass 1: partial (sum, sumsq) per (image, chunk, group); thread t: channel quad t & 63, pixel slot t >> 6 (4 pixels per sweep)
+__global__ void __launch_bounds__(256) gn_tokens_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, int HW) {
+  __shared__ float2 red[4][64];
+  const int img = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = (int)(((long long)HW * chunk) / GN_CHUNKS), p1 = (int)(((long long)HW * (chunk + 1)) / GN_CHUNKS);
+  const int cq = threadIdx.x & 63, slot = threadIdx.x >> 6;
+  const float* base = x + (size_t)img * HW * C256 + cq * 4;
+  float s = 0.f, q = 0.f;
+  for (int p = p0 + slot; p < p1; p += 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * C256));
+    s += v.x + v.y + v.z + v.w;
+    q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  red[slot][cq] = make_float2(s, q);
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS) {                  // group = channel quads 2g, 2g+1; slots in fixed order
+    const int g = threadIdx.x;
+    float ts = 0.f, tq = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) {
+      ts += red[sl][2 * g].x + red[sl][2 * g + 1].x;
+      tq += red[sl][2 * g].y + red[sl][2 * g + 1].y;
+    }
+    partial[((size_t)img * GN_CHUNKS + chunk) * GN_GROUPS + g] = make_float2(ts, tq);
+  }
+}
+// pass 2: y = (x - mean_g) * rstd_g * gamma_c + beta_c in place
+__global__ void __launch_bounds__(256) gn_tokens_apply_kernel(float* __restrict__ x, const float2* __restrict__ partial, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int HW, float eps) {
+  __shared__ float2 stat[GN_GROUPS];               // (mean, rstd)
+  const int img = blockIdx.y, chunk = blockIdx.x;
+  if (threadIdx.x < GN_GROUPS) {
+    float ts = 0.f, tq = 0.f;
+    for (int c = 0; c < GN_CHUNKS; ++c) {
+      const float2 v = partial[((size_t)img * GN_CHUNKS + c) * GN_GROUPS + threadIdx.x];
+      ts += v.x; tq += v.y;
+    }
+    const float cnt = 8.f * (float)HW;
+    const float mean = ts / cnt;
+    const float var = fmaxf(tq / cnt - mean * mean, 0.f);
+    stat[threadIdx.x] = make_float2(mean, rsqrtf(var + eps));
+  }
+  __syncthreads();
+  const int p0 = (int)(((long long)HW * chunk) / GN_CHUNKS), p1 = (int)(((long long)HW * (chunk + 1)) / GN_CHUNKS);
+  const int cq = threadIdx.x & 63, slot = threadIdx.x >> 6;
+  const float2 st = stat[cq >> 1];
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cq), be = __ldg(reinterpret_cast<const float4*>(beta) + cq);
+  float* base = x + (size_t)img * HW * C256 + cq * 4;
+  for (int p = p0 + slot; p < p1; p += 4) {
+    float4 v = *reinterpret_cast<float4*>(base + (size_t)p * C256);
+    v.x = (v.x - st.x) * st.y * ga.x + be.x; v.y = (v.y - st.x) * st.y * ga.y + be.y;
+    v.z = (v.z - st.x) * st.y * ga.z + be.z; v.w = (v.w - st.x) * st.y * ga.w + be.w;
+    *reinterpret_cast<float4*>(base + (size_t)p * C256) = v;
+  }
+}
+
+// ---- NCHW [images, C, HW]: group g = the contiguous block of (C/32) * HW floats; one CTA per (image, group), two passes --------
+__global__ void __launch_bounds__(256) gn_nchw_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      int C, int HW, float eps) {
+  __shared__ float2 red[8];
+  __shared__ float2 stat;
+  const int img = blockIdx.y, g = blockIdx.x, cpg = C / GN_GROUPS;
+  const size_t n = (size_t)cpg * HW;
+  float* base = x + ((size_t)img * C + (size_t)g * cpg) * HW;
+  float s = 0.f, q = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += 256) {
+    const float v = base[i];
+    s += v; q += v * v;
+  }
+  s = warp_sum(s); q = warp_sum(q);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_float2(s, q);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ts = 0.f, tq = 0.f;
+    for (int w = 0; w < 8; ++w) { ts += red[w].x; tq += red[w].y; }
+    const float mean = ts / (float)n;
+    stat = make_float2(mean, rsqrtf(fmaxf(tq / (float)n - mean * mean, 0.f) + eps));
+  }
+  __syncthreads();
+  const float2 st = stat;
+  for (size_t i = threadIdx.x; i < n; i += 256) {
+    const int c = g * cpg + (int)(i / HW);
+    base[i] = (base[i] - st.x) * st.y * __ldg(gamma + c) + __ldg(beta + c);
+  }
+}
+
+}  // namespace axvs

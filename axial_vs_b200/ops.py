@@ -457,6 +457,43 @@ def cc_class_pool(ce: torch.Tensor, w_act: torch.Tensor, b_act: float, T: int, Q
     return out
 
 
+def input_proj_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, gn_w: torch.Tensor, gn_b: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """x fp32 NCHW [images, c_in, H, W] -> GroupNorm(32)(Conv1x1(x)) as token-major fp32 [images, H*W, 256]."""
+    _check(x, "x", torch.float32)
+    if x.dim() != 4:
+        raise RuntimeError("input_proj_fwd: expected an NCHW feature map")
+    images, c_in, H, W = x.shape
+    for t, nm in ((bias, "bias"), (gn_w, "GroupNorm weight"), (gn_b, "GroupNorm bias")):
+        _check(t, nm, torch.float32, (C,))
+    out = torch.empty(images, H * W, C, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    nbytes = lib.axvs_proj_workspace_bytes(images)
+    with torch.cuda.device(x.device):
+        ws = workspace(nbytes, x.device)
+        rc = lib.axvs_input_proj_fwd(x.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), gn_w.data_ptr(), gn_b.data_ptr(), out.data_ptr(),
+                                     images, c_in, H * W, float(eps), ws.data_ptr(), ws.numel(), _stream(x.device))
+    _lib.check(rc, "axvs_input_proj_fwd")
+    return out
+
+
+def output_proj_fwd(tokens: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, gn_w: torch.Tensor, gn_b: torch.Tensor,
+                    H: int, W: int, eps: float = 1e-5) -> torch.Tensor:
+    """tokens fp32 [images, H*W, 256] -> GroupNorm(32)(Conv1x1(tokens^T)) as fp32 NCHW [images, c_out, H, W]."""
+    _check(tokens, "tokens", torch.float32)
+    if tokens.dim() != 3 or tokens.shape[1] != H * W or tokens.shape[2] != C:
+        raise RuntimeError("output_proj_fwd: expected tokens [images, H*W, 256]")
+    images, c_out = tokens.shape[0], bias.numel()
+    for t, nm in ((bias, "bias"), (gn_w, "GroupNorm weight"), (gn_b, "GroupNorm bias")):
+        _check(t, nm, torch.float32, (c_out,))
+    out = torch.empty(images, c_out, H, W, dtype=torch.float32, device=tokens.device)
+    lib = _lib.load()
+    with torch.cuda.device(tokens.device):
+        rc = lib.axvs_output_proj_fwd(tokens.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), gn_w.data_ptr(), gn_b.data_ptr(), out.data_ptr(),
+                                      images, c_out, H * W, float(eps), _stream(tokens.device))
+    _lib.check(rc, "axvs_output_proj_fwd")
+    return out
+
+
 def query_self_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, sim_affine: torch.Tensor, val_affine: torch.Tensor) -> torch.Tensor:
     """AttentionOperation core: q, k fp32 [N, heads, 16, L], v fp32 [N, heads, 32, L] -> GELU(BN(softmax(BN(q.k)) v)) fp32 [N, heads*32, L]."""
     for t, nm in ((q, "query"), (k, "key"), (v, "value"), (sim_affine, "sim_affine"), (val_affine, "val_affine")):

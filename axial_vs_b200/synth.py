@@ -131,3 +131,13 @@ def checksum(p: Params) -> float:
         t = p[k].double()
         tot += float((t * torch.arange(1, t.numel() + 1, dtype=torch.float64).reshape(t.shape).remainder(7.0)).sum())
     return tot
+
+
+def proj_params(seed: int, c: int):
+    """State dicts of an input projection (c -> 256) and an output projection (256 -> 2c): Conv2d 1x1 + GroupNorm(32)."""
+    g = torch.Generator().manual_seed(seed)
+    pin = {"0.weight": _xavier(g, 256, c, 1, 1), "0.bias": 0.1 * torch.randn(256, generator=g),
+           "1.weight": 1.0 + 0.2 * torch.randn(256, generator=g), "1.bias": 0.1 * torch.randn(256, generator=g)}
+    pout = {"0.weight": _xavier(g, 2 * c, 256, 1, 1), "0.bias": 0.1 * torch.randn(2 * c, generator=g),
+            "1.weight": 1.0 + 0.2 * torch.randn(2 * c, generator=g), "1.bias": 0.1 * torch.randn(2 * c, generator=g)}
+    return pin, pout

@@ -196,6 +196,19 @@ size_t axvs_kmeans_update_workspace_bytes(int N, int L, int M);
 int axvs_kmeans_update(const float* mask_logits, const float* pixel_value, float* out, int* assign, int N, int L, int M, int advanced,
                        void* workspace, size_t workspace_bytes, axvs_stream_t stream);
 
+/* ---- within-clip input / output projections ---------------------------------------------
+ * input side  (WC/msdeformattn.py:355-358, 413-416): tokens[i, p, :] = GroupNorm(32, 256)(Conv2d(c_in, 256, 1)(x))[i, :, p]
+ *   x fp32 NCHW [images, c_in, hw] (c_in % 64 == 0); w_packed = axvs_pack_weight of the conv weight [256, c_in];
+ *   out fp32 token-major [images, hw, 256] -- the layout of the temporal layers (the reference's flatten + transpose is folded in).
+ * output side (WC/msdeformattn.py:359-362, 432-434): y[i, :, p] = GroupNorm(32, c_out)(Conv2d(256, c_out, 1))(tokens[i, p, :])
+ *   tokens fp32 [images, hw, 256]; w_packed of the conv weight [c_out, 256] (c_out % 256 == 0); out fp32 NCHW [images, c_out, hw].
+ * GroupNorm statistics are per image and per group (eps as given, nn.GroupNorm default 1e-5), reductions in a fixed order. */
+size_t axvs_proj_workspace_bytes(int images);
+int axvs_input_proj_fwd(const float* x_nchw, const void* w_packed, const float* bias, const float* gn_w, const float* gn_b, float* out_tokens,
+                        int images, int c_in, int hw, float eps, void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+int axvs_output_proj_fwd(const float* tokens, const void* w_packed, const float* bias, const float* gn_w, const float* gn_b, float* out_nchw,
+                         int images, int c_out, int hw, float eps, axvs_stream_t stream);
+
 /* PositionEmbeddingSine3D(num_pos_feats=128, normalize=True) + level_embed_3d[lvl], channels-last
  * (WC/pos_embeddings.py:86-130, WC/msdeformattn.py:112-115).  out fp32 [B,T,H,W,256]; level_embed may be NULL. */
 int axvs_pos3d(float* out, const float* level_embed, int B, int T, int H, int W, axvs_stream_t stream);

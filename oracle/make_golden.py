@@ -144,6 +144,25 @@ def main():
              **{"bn." + k: v for k, v in bn.items()})
 
 
+    # ---- 6. within-clip input / output projections (row f1): the reference instantiates stock modules,
+    #         nn.Sequential(nn.Conv2d(c_in, 256, 1), nn.GroupNorm(32, 256)) and the reverse (WC/msdeformattn.py:355-362)
+    for tag, (n, c, H, W, seed) in {"a": (3, 128, 7, 5, 81), "b": (2, 512, 9, 11, 82)}.items():
+        g = torch.Generator().manual_seed(seed)
+        pin = {"0.weight": synth._xavier(g, 256, c, 1, 1), "0.bias": 0.1 * torch.randn(256, generator=g),
+               "1.weight": 1.0 + 0.2 * torch.randn(256, generator=g), "1.bias": 0.1 * torch.randn(256, generator=g)}
+        pout = {"0.weight": synth._xavier(g, 2 * c, 256, 1, 1), "0.bias": 0.1 * torch.randn(2 * c, generator=g),
+                "1.weight": 1.0 + 0.2 * torch.randn(2 * c, generator=g), "1.bias": 0.1 * torch.randn(2 * c, generator=g)}
+        mi = torch.nn.Sequential(torch.nn.Conv2d(c, 256, kernel_size=1), torch.nn.GroupNorm(32, 256)).eval()
+        mo = torch.nn.Sequential(torch.nn.Conv2d(256, 2 * c, kernel_size=1), torch.nn.GroupNorm(32, 2 * c)).eval()
+        mi.load_state_dict(pin, strict=True)
+        mo.load_state_dict(pout, strict=True)
+        x = synth.randn(seed + 100, n, c, H, W)
+        tok = mi(x).flatten(2).transpose(1, 2).contiguous()                                       # :100-106
+        y = mo(tok.transpose(1, 2).contiguous().view(n, -1, H, W))                                # :432-434
+        save(f"proj_{tag}", n=n, c=c, H=H, W=W, seed=seed, tokens=tok, y=y, wsum=synth.checksum({**{"i." + k: v for k, v in pin.items()},
+                                                                                                **{"o." + k: v for k, v in pout.items()}}))
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found; golden fixtures can only be generated where it is mounted")

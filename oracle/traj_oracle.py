@@ -414,6 +414,34 @@ def kmeans_update(mask_logits: Tensor, pixel_value: Tensor, advanced: bool = Fal
     return upd, index[:, 0]
 
 
+# ------------------------------------------------------------------------------------------------ within-clip projections (row f1)
+def group_norm(x: Tensor, num_groups: int, w: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
+    """nn.GroupNorm on [images, C, ...]: statistics per image over (C/groups channels x all positions), biased variance."""
+    n, C = x.shape[0], x.shape[1]
+    xg = x.reshape(n, num_groups, -1)
+    mu = xg.mean(-1, keepdim=True)
+    var = ((xg - mu) ** 2).mean(-1, keepdim=True)
+    y = ((xg - mu) / torch.sqrt(var + eps)).reshape(x.shape)
+    shape = [1, C] + [1] * (x.dim() - 2)
+    return y * w.to(x.dtype).reshape(shape) + b.to(x.dtype).reshape(shape)
+
+
+def input_proj(x: Tensor, p: Params) -> Tensor:
+    """input_proj[idx](x) then flatten(2).transpose(1, 2) -- WC/msdeformattn.py:355-358, 413-416 and :100-106.
+    x [images, c_in, H, W] -> tokens [images, H*W, 256]."""
+    y = torch.einsum("oc,nchw->nohw", p["0.weight"][:, :, 0, 0].to(x.dtype), x) + p["0.bias"].to(x.dtype)[None, :, None, None]
+    y = group_norm(y, 32, p["1.weight"], p["1.bias"])
+    return y.flatten(2).transpose(1, 2)
+
+
+def output_proj(tokens: Tensor, p: Params, H: int, W: int) -> Tensor:
+    """output_proj[i](z.transpose(1, 2).view(bs, -1, H, W)) -- WC/msdeformattn.py:359-362, 432-434.
+    tokens [images, H*W, 256] -> [images, c_out, H, W]."""
+    z = tokens.transpose(1, 2).reshape(tokens.shape[0], tokens.shape[2], H, W)
+    y = torch.einsum("oc,nchw->nohw", p["0.weight"][:, :, 0, 0].to(z.dtype), z) + p["0.bias"].to(z.dtype)[None, :, None, None]
+    return group_norm(y, 32, p["1.weight"], p["1.bias"])
+
+
 def flops_trajectory_attention(Bp: int, N: int, F: int, C: int = 256) -> int:
     return Bp * N * C * (10 * C + 4 * F * C + 4 * N + 4 * F)
 

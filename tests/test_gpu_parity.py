@@ -587,3 +587,45 @@ def test_query_self_attention_oracle(ops, O, N, L):
     out = ops.query_self_attn(q.cuda(), k.cuda(), v.cuda(), fold("_batch_norm_similarity").contiguous().cuda(),
                               fold("_batch_norm_retrieved_value").contiguous().cuda())
     assert nerr(out, ref) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------- within-clip projections (f1)
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_projections_golden(golden, tag):
+    from axial_vs_b200.projections import InputProjection, OutputProjection
+    gz = golden(f"proj_{tag}")
+    n, c, H, W, seed = (int(gz[k]) for k in "n c H W seed".split())
+    pin, pout = synth.proj_params(seed, c)
+    mi, mo = InputProjection(c).eval(), OutputProjection(2 * c).eval()
+    mi.load_state_dict(pin, strict=True)
+    mo.load_state_dict(pout, strict=True)
+    x = synth.randn(seed + 100, n, c, H, W).cuda()
+    with torch.no_grad():
+        tok = mi.cuda()(x)
+        y = mo.cuda()(torch.as_tensor(gz["tokens"]).cuda(), H, W)
+    assert nerr(tok, torch.as_tensor(gz["tokens"])) < TOL
+    assert nerr(y, torch.as_tensor(gz["y"])) < TOL
+
+
+@pytest.mark.parametrize("n,c,H,W", [(4, 2048, 21, 21), (2, 1024, 41, 41), (2, 512, 81, 81), (3, 64, 5, 3)])
+def test_projections_oracle_config_sizes(O, n, c, H, W):
+    """R50 pyramid of BASELINE configs[1]: res5 2048 x 21^2, res4 1024 x 41^2, res3 512 x 81^2 (and a ragged tiny case)."""
+    from axial_vs_b200.projections import InputProjection, OutputProjection
+    seed = 700 + n + c + H
+    pin, pout = synth.proj_params(seed, c)
+    if (2 * c) % 256:
+        pout = None
+    x = synth.randn(seed + 1, n, c, H, W)
+    ref_tok = O.input_proj(x, pin)
+    mi = InputProjection(c).eval()
+    mi.load_state_dict(pin, strict=True)
+    with torch.no_grad():
+        tok = mi.cuda()(x.cuda())
+    assert nerr(tok, ref_tok) < TOL
+    assert torch.equal(tok, mi(x.cuda()))                       # deterministic (fixed-order GroupNorm reductions)
+    if pout is not None:
+        mo = OutputProjection(2 * c).eval()
+        mo.load_state_dict(pout, strict=True)
+        with torch.no_grad():
+            y = mo.cuda()(ref_tok.contiguous().cuda(), H, W)
+        assert nerr(y, O.output_proj(ref_tok, pout, H, W)) < TOL

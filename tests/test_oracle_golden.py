@@ -121,3 +121,16 @@ def test_decoder_attention(golden, tag):
     upd, idx = O.kmeans_update(t("mask_logits"), t("pixel_value"))
     _close(upd, gz["kmeans_update"])
     assert torch.equal(idx, t("mask_logits").argmax(1))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_projections(golden, tag):
+    """Row f1: Conv2d 1x1 + GroupNorm(32) input / output projections against the stock torch modules the reference instantiates."""
+    gz = golden(f"proj_{tag}")
+    n, c, H, W, seed = (int(gz[k]) for k in "n c H W seed".split())
+    pin, pout = synth.proj_params(seed, c)
+    assert synth.checksum({**{"i." + k: v for k, v in pin.items()}, **{"o." + k: v for k, v in pout.items()}}) == pytest.approx(float(gz["wsum"]), rel=1e-12)
+    x = synth.randn(seed + 100, n, c, H, W)
+    tok = O.input_proj(x, pin)
+    _close(tok, gz["tokens"])
+    _close(O.output_proj(tok, pout, H, W), gz["y"], atol=5e-5)
