@@ -953,7 +953,7 @@ int axvs_output_proj_fwd(const float* tokens, const void* w_packed, const float*
   if (int rc = launch_gemm(p, (cudaStream_t)stream)) return rc;
   {
     ProfScope ps(KC_GN, 0, (double)M * c_out * 12.0, (cudaStream_t)stream);
-    gn_nchw_kernel<<<dim3(GN_GROUPS, images), 256, 0, (cudaStream_t)stream>>>(out_nchw, gn_w, gn_b, c_out, hw, eps);
+    gn_nchw_kernel<<<dim3(GN_GROUPS, images), 512, 0, (cudaStream_t)stream>>>(out_nchw, gn_w, gn_b, c_out, hw, eps);
   }
   AXVS_CHECK_LAUNCH("gn_nchw_kernel");
   return AXVS_OK;

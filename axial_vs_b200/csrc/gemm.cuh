@@ -20,7 +20,7 @@ constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KiB
 constexpr int GEMM_W_BYTES = GEMM_BN * GEMM_BK * 2;   // 32 KiB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_W_BYTES;
 constexpr int GEMM_EPI_WARPS = 4;
-constexpr int GEMM_APROD_WARPS = 4;
+constexpr int GEMM_APROD_WARPS = 8;
 constexpr int GEMM_THREADS = (GEMM_EPI_WARPS + 2 + GEMM_APROD_WARPS) * 32;   // 320
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
@@ -261,45 +261,61 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
         }
       }
       if (p.a_diag >= 3) {
-        // fp32 sources.  Mode 3 (NCHW): thread = pixel row ptid, i = 16-byte chunk (8 channels); mode 4: q = i * PT + ptid as below.
-        const int r3 = mt * GEMM_BM + ptid;
-        const int img = (p.a_diag == 3 && r3 < p.M) ? r3 / p.a_n : 0;
-        const float* base3 = p.A32 + ((size_t)img * p.K) * p.a_n + (r3 - img * p.a_n);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          uint4 v[ITERS];
+        // fp32 sources, loads software-pipelined over two register sets (K-block kb+1 in flight while kb is converted and stored).
+        // Mode 3 (NCHW): q = i * PT + ptid -> pixel row q & 127, 16-byte chunk (8 channels) q >> 7: a warp's 32 lanes read 32
+        // consecutive pixels of one channel per instruction.  Mode 4: row q >> 3, chunk q & 7 as for bf16 sources.
+        float fa[ITERS][8], fb[ITERS][8];
+        auto load = [&](int kb, float (&f)[ITERS][8]) {
 #pragma unroll
           for (int i = 0; i < ITERS; ++i) {
-            float f[8];
+            const int q = i * PT + ptid;
             if (p.a_diag == 3) {
-              const float* s = base3 + (size_t)(kb * GEMM_BK + i * 8) * p.a_n;
+              const int r = mt * GEMM_BM + (q & 127);
+              if (r < p.M) {
+                const int img = r / p.a_n;
+                const float* s = p.A32 + ((size_t)img * p.K + kb * GEMM_BK + (q >> 7) * 8) * p.a_n + (r - img * p.a_n);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = r3 < p.M ? __ldg(s + (size_t)j * p.a_n) : 0.f;
+                for (int j = 0; j < 8; ++j) f[i][j] = __ldg(s + (size_t)j * p.a_n);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
+              }
             } else {
-              const int q = i * PT + ptid;
               const int r = mt * GEMM_BM + (q >> 3);
               if (r < p.M) {
                 const float4* s = reinterpret_cast<const float4*>(p.A32 + (size_t)r * p.lda + kb * GEMM_BK + (q & 7) * 8);
                 const float4 a = __ldg(s), b = __ldg(s + 1);
-                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+                f[i][0] = a.x; f[i][1] = a.y; f[i][2] = a.z; f[i][3] = a.w; f[i][4] = b.x; f[i][5] = b.y; f[i][6] = b.z; f[i][7] = b.w;
               } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = 0.f;
+                for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
               }
             }
-            v[i] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
           }
+        };
+        auto store = [&](const float (&f)[ITERS][8]) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* dst = smem + stage * GEMM_STAGE_BYTES;
 #pragma unroll
           for (int i = 0; i < ITERS; ++i) {
             const int q = i * PT + ptid;
-            const uint32_t off = (p.a_diag == 3) ? sw128_offset(ptid, i) : sw128_offset(q >> 3, q & 7);
-            *reinterpret_cast<uint4*>(dst + off) = v[i];
+            const uint32_t off = (p.a_diag == 3) ? sw128_offset(q & 127, q >> 7) : sw128_offset(q >> 3, q & 7);
+            *reinterpret_cast<uint4*>(dst + off) = make_uint4(pack_bf16x2(f[i][0], f[i][1]), pack_bf16x2(f[i][2], f[i][3]),
+                                                              pack_bf16x2(f[i][4], f[i][5]), pack_bf16x2(f[i][6], f[i][7]));
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_bar[stage]);
           if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        };
+        load(0, fa);
+        for (int kb = 0; kb < num_kb; kb += 2) {                 // K is a multiple of 64; an odd K-block count ends in the first half
+          if (kb + 1 < num_kb) load(kb + 1, fb);
+          store(fa);
+          if (kb + 1 < num_kb) {
+            if (kb + 2 < num_kb) load(kb + 2, fa);
+            store(fb);
+          }
         }
         continue;
       }

@@ -70,32 +70,53 @@ __global__ void __launch_bounds__(256) gn_tokens_apply_kernel(float* __restrict_
 }
 
 // ---- NCHW [images, C, HW]: group g = the contiguous block of (C/32) * HW floats; one CTA per (image, group), two passes --------
-__global__ void __launch_bounds__(256) gn_nchw_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+// (the second pass re-reads what the first just streamed: with ~8 CTAs per SM the block is usually still in L2)
+__global__ void __launch_bounds__(512) gn_nchw_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       int C, int HW, float eps) {
-  __shared__ float2 red[8];
+  __shared__ float2 red[16];
   __shared__ float2 stat;
   const int img = blockIdx.y, g = blockIdx.x, cpg = C / GN_GROUPS;
   const size_t n = (size_t)cpg * HW;
   float* base = x + ((size_t)img * C + (size_t)g * cpg) * HW;
+  const bool vec = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (n % 4 == 0) && (HW % 4 == 0);
   float s = 0.f, q = 0.f;
-  for (size_t i = threadIdx.x; i < n; i += 256) {
-    const float v = base[i];
-    s += v; q += v * v;
+  if (vec) {
+    const float4* b4 = reinterpret_cast<const float4*>(base);
+    for (size_t i = threadIdx.x; i < n / 4; i += 512) {
+      const float4 v = b4[i];
+      s += v.x + v.y + v.z + v.w;
+      q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  } else {
+    for (size_t i = threadIdx.x; i < n; i += 512) {
+      const float v = base[i];
+      s += v; q += v * v;
+    }
   }
   s = warp_sum(s); q = warp_sum(q);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_float2(s, q);
   __syncthreads();
   if (threadIdx.x == 0) {
     float ts = 0.f, tq = 0.f;
-    for (int w = 0; w < 8; ++w) { ts += red[w].x; tq += red[w].y; }
+    for (int w = 0; w < 16; ++w) { ts += red[w].x; tq += red[w].y; }
     const float mean = ts / (float)n;
     stat = make_float2(mean, rsqrtf(fmaxf(tq / (float)n - mean * mean, 0.f) + eps));
   }
   __syncthreads();
   const float2 st = stat;
-  for (size_t i = threadIdx.x; i < n; i += 256) {
-    const int c = g * cpg + (int)(i / HW);
-    base[i] = (base[i] - st.x) * st.y * __ldg(gamma + c) + __ldg(beta + c);
+  for (int c = 0; c < cpg; ++c) {                   // per channel: one (scale, shift) pair, no index divisions
+    const float sc = st.y * __ldg(gamma + g * cpg + c), sh = __ldg(beta + g * cpg + c) - st.x * sc;
+    float* row = base + (size_t)c * HW;
+    if (vec) {
+      float4* r4 = reinterpret_cast<float4*>(row);
+      for (int i = threadIdx.x; i < HW / 4; i += 512) {
+        float4 v = r4[i];
+        v.x = v.x * sc + sh; v.y = v.y * sc + sh; v.z = v.z * sc + sh; v.w = v.w * sc + sh;
+        r4[i] = v;
+      }
+    } else {
+      for (int i = threadIdx.x; i < HW; i += 512) row[i] = row[i] * sc + sh;
+    }
   }
 }
 
