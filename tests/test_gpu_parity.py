@@ -469,6 +469,19 @@ def test_cross_clip_module_oracle_cfg3_shard(O):
     assert nerr(o["pred_logits"], ref["pred_logits"]) < TOL
     assert nerr(o["pred_masks"], ref["pred_masks"]) < 2e-2
     assert nerr(m.last_clip_query, ref["clip_query"]) < TOL
+    # north_star: per-pixel agreement of the final argmax labels (query index per pixel, class per query).  With RANDOM-INIT heads
+    # the 128 queries' logits of a pixel are nearly tied, so bf16 rounding flips about 1 % of them; the
+    # checkable statement is that labels differ only where the reference's top-2 margin is inside the numerical error.
+    got, want = o["pred_masks"].float().cpu(), ref["pred_masks"].float()
+    agree = (got.argmax(1) == want.argmax(1)).float().mean().item()
+    assert agree >= 0.98, f"per-pixel mask argmax agreement {agree:.5f}"
+    top2 = want.topk(2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    err = (got - want).abs().max().item()
+    decided = margin > 2.0 * err
+    assert decided.float().mean().item() > 0.5
+    assert torch.equal(got.argmax(1)[decided], want.argmax(1)[decided])
+    assert torch.equal(o["pred_logits"].argmax(-1).cpu(), ref["pred_logits"].argmax(-1))
 
 
 def test_cross_clip_forward_sharded_equals_unsharded():
