@@ -29,7 +29,7 @@ class AsppWeights(Structure):
 class LayerWeights(Structure):
     _fields_ = [("attn_h", TaWeights), ("attn_w", TaWeights), ("ln1_g", c_void_p), ("ln1_b", c_void_p),
                 ("w_ffn1", c_void_p), ("b_ffn1", c_void_p), ("w_ffn2", c_void_p), ("b_ffn2", c_void_p),
-                ("w_ffn1_u", c_void_p), ("w_ffn2_u", c_void_p), ("ln2_g", c_void_p), ("ln2_b", c_void_p), ("d_ffn", c_int)]
+                ("w_ffn1_u", c_void_p), ("w_ffn2_u", c_void_p), ("ln2_g", c_void_p), ("ln2_b", c_void_p), ("d_ffn", c_int), ("w_ffn1_n", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/axvs.h declares

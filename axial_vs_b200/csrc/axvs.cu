@@ -12,6 +12,7 @@
 #include "traj_fused.cuh"
 #include "traj_ts.cuh"
 #include "ffn_fused.cuh"
+#include "ffn_n256.cuh"
 #include "qkv_fused.cuh"
 #include "qkv_direct.cuh"
 #include "qkv_attn.cuh"
@@ -35,12 +36,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel"};
 int g_fusion = 4;   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
 int g_pair = 0;   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
@@ -151,7 +152,8 @@ int device_info(DeviceInfo** out) {
     d.dec_attr = true;
   }
   if (!d.ffn_attr) {
-    if (cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(ffn_n256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(ffn_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.ffn_attr = true;
   }
@@ -304,6 +306,7 @@ int axvs_pack_weight(const float* w, int n_out, int k, void* packed, axvs_stream
 int axvs_pack_weight_units(const float* w, int n_out, int k, int k_major, void* packed, axvs_stream_t stream) {
   if (!w || !packed) return fail(AXVS_E_INVALID, "pack_weight_units: null pointer");
   if (n_out <= 0 || n_out % 128 || k <= 0 || k % 128) return fail(AXVS_E_UNSUPPORTED, "pack_weight_units: need n_out %% 128 == 0 and k %% 128 == 0 (got %d, %d)", n_out, k);
+  if (k_major < 0 || k_major > 2 || (k_major == 2 && n_out % 256)) return fail(AXVS_E_UNSUPPORTED, "pack_weight_units: bad unit order %d for n_out %d", k_major, n_out);
   const int total = n_out * (k / 8);
   {
     ProfScope ps(KC_PACKW, 0, (double)n_out * k * 6, (cudaStream_t)stream);
@@ -615,10 +618,14 @@ int ffn_fused_launch(const uint8_t* s_img, const float* s32, float* out, const a
   fp.b1 = w->b_ffn1; fp.b2 = w->b_ffn2;
   fp.rows = rows; fp.tiles = (rows + 127) / 128; fp.d_ffn = w->d_ffn; fp.eps = 1e-5f;
   {
-    ProfScope ps(KC_FFN, 4.0 * rows * 256.0 * w->d_ffn, (double)rows * 256 * 10.0, st);
+    const bool n256 = !g_pair && g_fusion >= 4 && w->w_ffn1_n && w->d_ffn % 256 == 0;
+    ProfScope ps(n256 ? KC_FFN256 : KC_FFN, 4.0 * rows * 256.0 * w->d_ffn, (double)rows * 256 * 10.0, st);
     if (g_pair) {
       const int pair_tiles = (fp.tiles + 1) / 2, max_pairs = d->sms / 2;
       ffn_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), FF_THREADS, FP_SMEM_BYTES, st>>>(fp);
+    } else if (g_fusion >= 4 && w->w_ffn1_n && w->d_ffn % 256 == 0) {
+      fp.w1 = reinterpret_cast<const uint8_t*>(w->w_ffn1_n);       // N = 256 units
+      ffn_n256_kernel<<<fp.tiles < d->sms ? fp.tiles : d->sms, FF_THREADS, FF_SMEM_BYTES, st>>>(fp);
     } else {
       ffn_fused_kernel<<<fp.tiles < d->sms ? fp.tiles : d->sms, FF_THREADS, FF_SMEM_BYTES, st>>>(fp);
     }

@@ -374,7 +374,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int n_out, int K
 
 // fp32 [n_out, K] -> bf16 "unit" image for the fused kernels: 32 KiB units = [2 K-blocks][128 rows x 128 B, SWIZZLE_128B],
 // i.e. one TMA bulk copy brings the operand of 8 UMMAs (N = 128, K = 128).  Unit order: k_major == 0 -> unit(rt, kg) =
-// rt * (K/128) + kg (all K of a 128-row tile contiguous); k_major == 1 -> unit = kg * (n_out/128) + rt.
+// rt * (K/128) + kg (all K of a 128-row tile contiguous); k_major == 1 -> unit = kg * (n_out/128) + rt;
+// k_major == 2 -> units of 256 rows x ONE K-block (the B operand of an N = 256 UMMA), unit = (r / 256) * (K / 64) + kb.
 __global__ void pack_weight_units_kernel(const float* __restrict__ w, int n_out, int K, int k_major, uint8_t* __restrict__ packed) {
   const int total = n_out * (K / 8);
   const int KG = K / 128, RT = n_out / 128;
@@ -391,6 +392,10 @@ __global__ void pack_weight_units_kernel(const float* __restrict__ w, int n_out,
     u.y = pack_bf16x2(a.z, a.w);
     u.z = pack_bf16x2(b.x, b.y);
     u.w = pack_bf16x2(b.z, b.w);
+    if (k_major == 2) {   // N = 256 units: [256 rows x 128 B] of ONE K-block, unit = (row tile of 256) * (K / 64) + K-block
+      *reinterpret_cast<uint4*>(packed + ((size_t)(r >> 8) * (K / 64) + kb) * 32768 + sw128_offset(r & 255, ch)) = u;
+      continue;
+    }
     *reinterpret_cast<uint4*>(packed + unit * 32768 + (size_t)kb2 * 16384 + sw128_offset(rl, ch)) = u;
   }
 }

@@ -68,7 +68,7 @@ def pack_weight(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def pack_weight_units(w: torch.Tensor, k_major: bool = False) -> torch.Tensor:
+def pack_weight_units(w: torch.Tensor, k_major: int = 0) -> torch.Tensor:
     """fp32 weight [n_out, k] -> 32 KiB-unit image of the fused kernels (see include/axvs.h)."""
     _check(w, "weight", torch.float32)
     n_out, k = w.shape
@@ -143,21 +143,24 @@ class PackedLayer:
     ln2_g: torch.Tensor
     ln2_b: torch.Tensor
     d_ffn: int
+    w_ffn1_n: Optional[torch.Tensor] = None      # linear1 as N = 256 units (pack_weight_units mode 2)
 
     def tensors(self) -> List[torch.Tensor]:
         aw = self.attn_w if self.attn_w is not None else self.attn_h
         return self.attn_h.tensors() + aw.tensors() + [self.ln1_g, self.ln1_b, self.w_ffn1, self.b_ffn1, self.w_ffn2,
-                                                       self.b_ffn2, self.w_ffn1_u, self.w_ffn2_u, self.ln2_g, self.ln2_b]
+                                                       self.b_ffn2, self.w_ffn1_u, self.w_ffn2_u, self.ln2_g, self.ln2_b, self.w_ffn1_n]
 
     def struct(self) -> LayerWeights:
         aw = self.attn_w if self.attn_w is not None else self.attn_h
         return LayerWeights(self.attn_h.struct(), aw.struct(), self.ln1_g.data_ptr(), self.ln1_b.data_ptr(),
                             self.w_ffn1.data_ptr(), self.b_ffn1.data_ptr(), self.w_ffn2.data_ptr(), self.b_ffn2.data_ptr(),
-                            self.w_ffn1_u.data_ptr(), self.w_ffn2_u.data_ptr(), self.ln2_g.data_ptr(), self.ln2_b.data_ptr(), self.d_ffn)
+                            self.w_ffn1_u.data_ptr(), self.w_ffn2_u.data_ptr(), self.ln2_g.data_ptr(), self.ln2_b.data_ptr(), self.d_ffn,
+                            self.w_ffn1_n.data_ptr() if self.w_ffn1_n is not None else None)
 
     @staticmethod
     def from_tensors(ts: Sequence[torch.Tensor], d_ffn: int) -> "PackedLayer":
-        return PackedLayer(PackedTA.from_tensors(ts[0:12]), PackedTA.from_tensors(ts[12:24]), *ts[24:34], d_ffn=d_ffn)
+        return PackedLayer(PackedTA.from_tensors(ts[0:12]), PackedTA.from_tensors(ts[12:24]), *ts[24:34], d_ffn=d_ffn,
+                           w_ffn1_n=ts[34] if len(ts) > 34 else None)
 
 
 def pack_layer(p: Dict[str, torch.Tensor], axial: bool = True) -> PackedLayer:
@@ -169,8 +172,8 @@ def pack_layer(p: Dict[str, torch.Tensor], axial: bool = True) -> PackedLayer:
     aw = pack_ta(p, "width_attn.") if axial else None
     return PackedLayer(ah, aw, g("norm1.weight"), g("norm1.bias"), pack_weight(g("linear1.weight")), g("linear1.bias"),
                        pack_weight(g("linear2.weight")), g("linear2.bias"), pack_weight_units(g("linear1.weight")),
-                       pack_weight_units(g("linear2.weight"), k_major=True), g("norm2.weight"), g("norm2.bias"),
-                       d_ffn=p["linear1.weight"].shape[0])
+                       pack_weight_units(g("linear2.weight"), k_major=1), g("norm2.weight"), g("norm2.bias"),
+                       d_ffn=p["linear1.weight"].shape[0], w_ffn1_n=pack_weight_units(g("linear1.weight"), k_major=2))
 
 
 # ------------------------------------------------------------------------------------------------ operators

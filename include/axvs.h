@@ -66,8 +66,9 @@ int axvs_set_pair_mode(int on);
 size_t axvs_packed_weight_bytes(int n_out, int k);
 int axvs_pack_weight(const float* w, int n_out, int k, void* packed, axvs_stream_t stream);
 /* "Unit" format of the fused kernels: 32 KiB units = [2 K-blocks][128 rows x 128 B swizzled] so one TMA bulk copy feeds
- * eight tensor-core instructions.  k_major = 0: units ordered (row tile, K group); 1: (K group, row tile).
- * n_out % 128 == 0, k % 128 == 0.  Same size as axvs_packed_weight_bytes. */
+ * eight tensor-core instructions.  k_major = 0: units ordered (row tile, K group); 1: (K group, row tile);
+ * 2: units of [256 rows x 128 B swizzled] of ONE K-block (B operand of an N = 256 instruction), ordered (row tile of 256, K-block).
+ * n_out % 128 == 0 (256 for mode 2), k % 128 == 0.  Same size as axvs_packed_weight_bytes. */
 int axvs_pack_weight_units(const float* w, int n_out, int k, int k_major, void* packed, axvs_stream_t stream);
 
 /* One TrajectoryAttention's parameters (WC/temporal_attention.py:27-33; CC:85-89; TL .../msdeformattn_pixel_decoder.py:659-665).
@@ -96,6 +97,7 @@ typedef struct axvs_layer_weights {
   const void* w_ffn2_u;                      /* linear2, unit format, k_major = 1 (fused kernel) */
   const float* ln2_g; const float* ln2_b;    /* norm2 */
   int d_ffn;                                 /* 1024 */
+  const void* w_ffn1_n;                      /* linear1, unit format mode 2 (N = 256 units; may be NULL: falls back to w_ffn1_u) */
 } axvs_layer_weights;
 
 /* ---- building blocks (each is also a test surface) ------------------------------------------------------------ */
