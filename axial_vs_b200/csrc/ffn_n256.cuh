@@ -85,12 +85,16 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_n256_kernel(const FfnParams
           tmem_ld_wait();
           const float4* b4 = reinterpret_cast<const float4*>(sb1 + j * 256 + 128 * g + 64 * c);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 8; ++i) {                         // packed fp32 adds, ReLU folded into the bf16x2 conversion
             const float4 bb = b4[i], bc = b4[8 + i];
-            hpk[32 * c + 2 * i] = pack_bf16x2(fmaxf(v0[4 * i] + bb.x, 0.f), fmaxf(v0[4 * i + 1] + bb.y, 0.f));
-            hpk[32 * c + 2 * i + 1] = pack_bf16x2(fmaxf(v0[4 * i + 2] + bb.z, 0.f), fmaxf(v0[4 * i + 3] + bb.w, 0.f));
-            hpk[32 * c + 16 + 2 * i] = pack_bf16x2(fmaxf(v1[4 * i] + bc.x, 0.f), fmaxf(v1[4 * i + 1] + bc.y, 0.f));
-            hpk[32 * c + 16 + 2 * i + 1] = pack_bf16x2(fmaxf(v1[4 * i + 2] + bc.z, 0.f), fmaxf(v1[4 * i + 3] + bc.w, 0.f));
+            const float2 a0 = add_f32x2(make_float2(v0[4 * i], v0[4 * i + 1]), make_float2(bb.x, bb.y));
+            const float2 a1 = add_f32x2(make_float2(v0[4 * i + 2], v0[4 * i + 3]), make_float2(bb.z, bb.w));
+            const float2 c0 = add_f32x2(make_float2(v1[4 * i], v1[4 * i + 1]), make_float2(bc.x, bc.y));
+            const float2 c1 = add_f32x2(make_float2(v1[4 * i + 2], v1[4 * i + 3]), make_float2(bc.z, bc.w));
+            hpk[32 * c + 2 * i] = pack_bf16x2_relu(a0.x, a0.y);
+            hpk[32 * c + 2 * i + 1] = pack_bf16x2_relu(a1.x, a1.y);
+            hpk[32 * c + 16 + 2 * i] = pack_bf16x2_relu(c0.x, c0.y);
+            hpk[32 * c + 16 + 2 * i + 1] = pack_bf16x2_relu(c1.x, c1.y);
           }
         }
         tmem_st32u(t_s, *reinterpret_cast<const uint32_t(*)[32]>(&hpk[0]));

@@ -102,10 +102,14 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
             for (int q = 0; q < 4; ++q) {
               const float4 b0 = b4[2 * q], b1 = b4[2 * q + 1];
               uint4 u;
-              u.x = pack_bf16x2(v[8 * q] + b0.x, v[8 * q + 1] + b0.y);
-              u.y = pack_bf16x2(v[8 * q + 2] + b0.z, v[8 * q + 3] + b0.w);
-              u.z = pack_bf16x2(v[8 * q + 4] + b1.x, v[8 * q + 5] + b1.y);
-              u.w = pack_bf16x2(v[8 * q + 6] + b1.z, v[8 * q + 7] + b1.w);
+              const float2 t0 = add_f32x2(make_float2(v[8 * q], v[8 * q + 1]), make_float2(b0.x, b0.y));
+              const float2 t1 = add_f32x2(make_float2(v[8 * q + 2], v[8 * q + 3]), make_float2(b0.z, b0.w));
+              const float2 t2 = add_f32x2(make_float2(v[8 * q + 4], v[8 * q + 5]), make_float2(b1.x, b1.y));
+              const float2 t3 = add_f32x2(make_float2(v[8 * q + 6], v[8 * q + 7]), make_float2(b1.z, b1.w));
+              u.x = pack_bf16x2(t0.x, t0.y);
+              u.y = pack_bf16x2(t1.x, t1.y);
+              u.z = pack_bf16x2(t2.x, t2.y);
+              u.w = pack_bf16x2(t3.x, t3.y);
               *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = u;
             }
           }

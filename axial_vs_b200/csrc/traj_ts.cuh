@@ -128,14 +128,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
             tmem_ld16(t_qp + 16 * lh, q2f);
             tmem_ld_wait();
             tmem_ld32(t_s + 64 + 32 * hh, v2);
-            float s0 = 0.f, s1 = 0.f;
+            float2 sacc = make_float2(0.f, 0.f);                // packed fp32 FMAs: two channels per instruction
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const uint32_t u = __float_as_uint(q2f[i]);
-              s0 = fmaf(bf16lo_to_f32(u), k2[2 * i], s0);
-              s1 = fmaf(bf16hi_to_f32(u), k2[2 * i + 1], s1);
+              sacc = fma_f32x2(make_float2(bf16lo_to_f32(u), bf16hi_to_f32(u)), make_float2(k2[2 * i], k2[2 * i + 1]), sacc);
             }
-            const float s = s0 + s1;
+            const float s = sacc.x + sacc.y;
             const float mn = fmaxf(m_run[lh], s);
             const float corr = exp2f(m_run[lh] - mn);
             const float pe = exp2f(s - mn);
@@ -147,8 +146,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
               __syncwarp();
               if (lane == 0) mbar_arrive(&s_empty[g]);
             }
+            const float2 pe2 = make_float2(pe, pe), corr2 = make_float2(corr, corr);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[lh][i] = fmaf(pe, v2[i], o[lh][i] * corr);
+            for (int i = 0; i < 16; ++i) {
+              const float2 r = fma_f32x2(pe2, make_float2(v2[2 * i], v2[2 * i + 1]), mul_f32x2(make_float2(o[lh][2 * i], o[lh][2 * i + 1]), corr2));
+              o[lh][2 * i] = r.x;
+              o[lh][2 * i + 1] = r.y;
+            }
           }
         }
       }
