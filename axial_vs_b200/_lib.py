@@ -21,6 +21,14 @@ class TaWeights(Structure):
                 ("w_pkv", c_void_p), ("b_pkv", c_void_p), ("w_qkv_u", c_void_p), ("w_pq_u", c_void_p), ("w_pkv_u", c_void_p), ("w_proj_u", c_void_p), ("w_proj", c_void_p), ("b_proj", c_void_p)]
 
 
+class MsdaWeights(Structure):
+    """struct axvs_msda_weights."""
+    _fields_ = [("w_value", c_void_p), ("b_value", c_void_p), ("w_oa", c_void_p), ("b_oa", c_void_p), ("w_out", c_void_p), ("b_out", c_void_p),
+                ("ln1_g", c_void_p), ("ln1_b", c_void_p), ("w_ffn1", c_void_p), ("b_ffn1", c_void_p), ("w_ffn2", c_void_p), ("b_ffn2", c_void_p),
+                ("w_ffn1_u", c_void_p), ("w_ffn2_u", c_void_p), ("w_ffn1_n", c_void_p), ("ln2_g", c_void_p), ("ln2_b", c_void_p),
+                ("d_ffn", c_int), ("n_levels", c_int), ("n_points", c_int)]
+
+
 class AsppWeights(Structure):
     _fields_ = [("w_conv", c_void_p * 3), ("b_conv", c_void_p * 3), ("dilation", c_int * 3), ("w_proj", c_void_p),
                 ("lncf_g", c_void_p), ("lncf_b", c_void_p), ("ln_g", c_void_p), ("ln_b", c_void_p)]
@@ -65,6 +73,8 @@ SIGNATURES = {
     "axvs_proj_workspace_bytes": (c_size_t, [c_int]),
     "axvs_input_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "axvs_output_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    "axvs_msda_layer_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "axvs_msda_layer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int), c_void_p, POINTER(MsdaWeights), c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "axvs_mask_einsum": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "axvs_pos3d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "axvs_profile_enable": (c_int, [c_int]),

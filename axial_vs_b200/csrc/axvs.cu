@@ -19,6 +19,7 @@
 #include "cc_tail.cuh"
 #include "decoder_attn.cuh"
 #include "proj.cuh"
+#include "msda.cuh"
 #include "ffn_pair.cuh"
 
 using namespace axvs;
@@ -36,12 +37,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel"};
 int g_fusion = 4;   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
 int g_pair = 0;   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
@@ -964,6 +965,66 @@ int axvs_output_proj_fwd(const float* tokens, const void* w_packed, const float*
   }
   AXVS_CHECK_LAUNCH("gn_nchw_kernel");
   return AXVS_OK;
+}
+
+size_t axvs_msda_layer_workspace_bytes(int rows, int d_ffn) {
+  if (rows <= 0 || d_ffn <= 0) return 0;
+  // value bf16 [rows,256] | offsets+logits fp32 [rows,512] | sampled bf16 [rows,256] | y fp32 [rows,256] | FFN workspace
+  return (size_t)rows * (512 + 2048 + 512 + 1024) + 1024 + carve_ffn(nullptr, (size_t)rows, d_ffn).bytes;
+}
+
+int axvs_msda_layer_fwd(const float* src, const float* pos, const float* ref_points, const int* shapes_hw, float* out,
+                        const axvs_msda_weights* w, int images, int len, void* workspace, size_t workspace_bytes, axvs_stream_t stream) {
+  if (!src || !ref_points || !shapes_hw || !out || !w || !workspace) return fail(AXVS_E_INVALID, "msda_layer: null pointer");
+  if (!w->w_value || !w->w_oa || !w->w_out || !w->b_value || !w->b_oa || !w->b_out) return fail(AXVS_E_INVALID, "msda_layer: null weight pointer");
+  if (images <= 0 || len <= 0) return fail(AXVS_E_INVALID, "msda_layer: sizes must be positive");
+  if (w->n_levels <= 0 || w->n_levels > MSDA_MAX_LEVELS || w->n_points <= 0 || w->n_levels * w->n_points > MSDA_MAX_LP)
+    return fail(AXVS_E_UNSUPPORTED, "msda_layer: at most %d levels and %d level*point samples per head (got %d x %d)", MSDA_MAX_LEVELS, MSDA_MAX_LP,
+                w->n_levels, w->n_points);
+  if ((long long)images * len > 0x7fffffffLL) return fail(AXVS_E_UNSUPPORTED, "msda_layer: too many tokens");
+  MsdaDims d;
+  memset(&d, 0, sizeof(d));
+  d.L = w->n_levels; d.P = w->n_points; d.len = len;
+  int acc = 0;
+  for (int l = 0; l < d.L; ++l) {
+    d.H[l] = shapes_hw[2 * l]; d.W[l] = shapes_hw[2 * l + 1]; d.start[l] = acc;
+    if (d.H[l] <= 0 || d.W[l] <= 0) return fail(AXVS_E_INVALID, "msda_layer: bad level shape");
+    acc += d.H[l] * d.W[l];
+  }
+  if (acc != len) return fail(AXVS_E_INVALID, "msda_layer: level shapes sum to %d tokens, len is %d", acc, len);
+  const int rows = images * len;
+  const size_t need = axvs_msda_layer_workspace_bytes(rows, w->d_ffn);
+  if (workspace_bytes < need) return fail(AXVS_E_WORKSPACE, "msda_layer: workspace %zu < required %zu", workspace_bytes, need);
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* value = reinterpret_cast<__nv_bfloat16*>(base);
+  float* oa = reinterpret_cast<float*>(base + (size_t)rows * 512);
+  __nv_bfloat16* samp = reinterpret_cast<__nv_bfloat16*>(base + (size_t)rows * (512 + 2048));
+  float* y = reinterpret_cast<float*>(base + (size_t)rows * (512 + 2048 + 512));
+  uint8_t* ffn_ws = base + (((size_t)rows * (512 + 2048 + 512 + 1024) + 1023) & ~(size_t)1023);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  // value = value_proj(src)                                                                         MSDA:98
+  GemmParams p = gemm_params(nullptr, 256, rows, 256, w->w_value, 256, 0, w->b_value, 256, 1.f, 0, value, 256, 0, 1, nullptr);
+  p.a_diag = 4; p.A32 = src;
+  if ((rc = launch_gemm(p, st))) return rc;
+  // [sampling offsets | attention logits] = Linear(src + pos)                                       MSDA:102-103 (query = src + pos, ENC:207)
+  p = gemm_params(nullptr, 256, rows, 256, w->w_oa, 512, 0, w->b_oa, 512, 1.f, 0, oa, 512, 0, 0, nullptr);
+  p.a_diag = 4; p.A32 = src; p.A32b = pos;
+  if ((rc = launch_gemm(p, st))) return rc;
+  {
+    ProfScope ps(KC_MSDA, 0, (double)rows * (8.0 * d.L * d.P * 4 * 64 + 2048 + 512), st);
+    msda_sample_kernel<<<(rows + 3) / 4, 256, 0, st>>>(value, oa, 512, ref_points, samp, rows, d);
+  }
+  AXVS_CHECK_LAUNCH("msda_sample_kernel");
+  // y = src + output_proj(sampled)                                                                   MSDA:124, ENC:208
+  p = gemm_params(samp, 256, rows, 256, w->w_out, 256, 0, w->b_out, 256, 1.f, 0, y, 256, 0, 0, src);
+  if ((rc = launch_gemm(p, st))) return rc;
+  // out = LN2(s + FFN(s)), s = LN1(y)                                                                ENC:209-213
+  axvs_layer_weights lw;
+  memset(&lw, 0, sizeof(lw));
+  lw.ln1_g = w->ln1_g; lw.ln1_b = w->ln1_b; lw.w_ffn1 = w->w_ffn1; lw.b_ffn1 = w->b_ffn1; lw.w_ffn2 = w->w_ffn2; lw.b_ffn2 = w->b_ffn2;
+  lw.w_ffn1_u = w->w_ffn1_u; lw.w_ffn2_u = w->w_ffn2_u; lw.w_ffn1_n = w->w_ffn1_n; lw.ln2_g = w->ln2_g; lw.ln2_b = w->ln2_b; lw.d_ffn = w->d_ffn;
+  return axvs_ln_ffn_fwd(y, out, &lw, rows, ffn_ws, workspace_bytes - (size_t)(ffn_ws - base), stream);
 }
 
 int axvs_pos3d(float* out, const float* level_embed, int B, int T, int H, int W, axvs_stream_t stream) {

@@ -68,6 +68,7 @@ struct GemmParams {
                 // 4: A32 is an fp32 row-major matrix [M, lda] (token rows), converted to bf16 on the fly
   int a_N, a_n, a_F;
   const float* A32;
+  const float* A32b;    // mode 4 only: optional second fp32 matrix added element-wise (e.g. src + pos), same layout as A32
   // W operand (packed) and bias
   const uint8_t* Wp;
   int w_rows_total;   // rows of the packed image (K-block stride = w_rows_total * 128 B)
@@ -283,8 +284,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
             } else {
               const int r = mt * GEMM_BM + (q >> 3);
               if (r < p.M) {
-                const float4* s = reinterpret_cast<const float4*>(p.A32 + (size_t)r * p.lda + kb * GEMM_BK + (q & 7) * 8);
-                const float4 a = __ldg(s), b = __ldg(s + 1);
+                const size_t o = (size_t)r * p.lda + kb * GEMM_BK + (q & 7) * 8;
+                const float4* s = reinterpret_cast<const float4*>(p.A32 + o);
+                float4 a = __ldg(s), b = __ldg(s + 1);
+                if (p.A32b) {
+                  const float4* s2 = reinterpret_cast<const float4*>(p.A32b + o);
+                  const float4 a2 = __ldg(s2), b2 = __ldg(s2 + 1);
+                  a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w; b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+                }
                 f[i][0] = a.x; f[i][1] = a.y; f[i][2] = a.z; f[i][3] = a.w; f[i][4] = b.x; f[i][5] = b.y; f[i][6] = b.z; f[i][7] = b.w;
               } else {
 #pragma unroll

@@ -497,6 +497,63 @@ def output_proj_fwd(tokens: torch.Tensor, w_packed: torch.Tensor, bias: torch.Te
     return out
 
 
+@dataclass
+class PackedMsda:
+    """struct axvs_msda_weights (+ the tensors that keep the pointers alive)."""
+    tensors: List[torch.Tensor]
+    d_ffn: int
+    n_levels: int
+    n_points: int
+
+    def struct(self) -> "_lib.MsdaWeights":
+        return _lib.MsdaWeights(*[t.data_ptr() for t in self.tensors], self.d_ffn, self.n_levels, self.n_points)
+
+
+def pack_msda_layer(p: Dict[str, torch.Tensor], n_levels: int, n_points: int) -> PackedMsda:
+    """Pack the state dict of MSDeformAttnTransformerEncoderLayer (WC/msdeformattn.py:177-203)."""
+    def g(name):
+        return p[name].detach().float().contiguous()
+
+    no = HEADS * n_levels * n_points
+    w_oa = torch.zeros(512, C, device=g("self_attn.value_proj.weight").device)
+    b_oa = torch.zeros(512, device=w_oa.device)
+    w_oa[: 2 * no] = g("self_attn.sampling_offsets.weight")
+    w_oa[2 * no: 3 * no] = g("self_attn.attention_weights.weight")
+    b_oa[: 2 * no] = g("self_attn.sampling_offsets.bias")
+    b_oa[2 * no: 3 * no] = g("self_attn.attention_weights.bias")
+    ts = [pack_weight(g("self_attn.value_proj.weight")), g("self_attn.value_proj.bias"), pack_weight(w_oa), b_oa,
+          pack_weight(g("self_attn.output_proj.weight")), g("self_attn.output_proj.bias"), g("norm1.weight"), g("norm1.bias"),
+          pack_weight(g("linear1.weight")), g("linear1.bias"), pack_weight(g("linear2.weight")), g("linear2.bias"),
+          pack_weight_units(g("linear1.weight")), pack_weight_units(g("linear2.weight"), k_major=1),
+          pack_weight_units(g("linear1.weight"), k_major=2), g("norm2.weight"), g("norm2.bias")]
+    return PackedMsda(ts, p["linear1.weight"].shape[0], n_levels, n_points)
+
+
+def msda_layer_fwd(src: torch.Tensor, pos: Optional[torch.Tensor], ref_points: torch.Tensor, shapes: Sequence[Tuple[int, int]],
+                   w: PackedMsda) -> torch.Tensor:
+    """MSDeformAttn spatial encoder layer: src, pos fp32 [images, len, 256]; ref_points fp32 [images, len, n_levels, 2]."""
+    _check(src, "src", torch.float32)
+    images, length, c = src.shape
+    if c != C:
+        raise RuntimeError("msda_layer_fwd: 256 channels expected")
+    if pos is not None:
+        _check(pos, "pos", torch.float32, src.shape)
+    _check(ref_points, "reference_points", torch.float32, (images, length, w.n_levels, 2))
+    if len(shapes) != w.n_levels or sum(int(h) * int(v) for h, v in shapes) != length:
+        raise RuntimeError("msda_layer_fwd: spatial shapes do not match the token count")
+    out = torch.empty_like(src)
+    lib = _lib.load()
+    hw = (ctypes.c_int * (2 * w.n_levels))(*[int(v) for s_ in shapes for v in s_])
+    nbytes = lib.axvs_msda_layer_workspace_bytes(images * length, w.d_ffn)
+    with torch.cuda.device(src.device):
+        ws = workspace(nbytes, src.device)
+        st = w.struct()
+        rc = lib.axvs_msda_layer_fwd(src.data_ptr(), pos.data_ptr() if pos is not None else None, ref_points.data_ptr(), hw, out.data_ptr(),
+                                     ctypes.byref(st), images, length, ws.data_ptr(), ws.numel(), _stream(src.device))
+    _lib.check(rc, "axvs_msda_layer_fwd")
+    return out
+
+
 def query_self_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, sim_affine: torch.Tensor, val_affine: torch.Tensor) -> torch.Tensor:
     """AttentionOperation core: q, k fp32 [N, heads, 16, L], v fp32 [N, heads, 32, L] -> GELU(BN(softmax(BN(q.k)) v)) fp32 [N, heads*32, L]."""
     for t, nm in ((q, "query"), (k, "key"), (v, "value"), (sim_affine, "sim_affine"), (val_affine, "val_affine")):

@@ -141,3 +141,22 @@ def proj_params(seed: int, c: int):
     pout = {"0.weight": _xavier(g, 2 * c, 256, 1, 1), "0.bias": 0.1 * torch.randn(2 * c, generator=g),
             "1.weight": 1.0 + 0.2 * torch.randn(2 * c, generator=g), "1.bias": 0.1 * torch.randn(2 * c, generator=g)}
     return pin, pout
+
+
+def msda_layer_params(seed: int, n_levels: int = 3, n_heads: int = 8, n_points: int = 4, C: int = 256, d_ffn: int = 1024) -> Params:
+    """State dict of MSDeformAttnTransformerEncoderLayer (WC/msdeformattn.py:177-203) with NON-degenerate sampling heads
+    (the reference's init zeroes the offset / attention weights, which would hide layout mistakes)."""
+    g = torch.Generator().manual_seed(seed)
+    p: Params = {}
+    no = n_heads * n_levels * n_points
+    p["self_attn.sampling_offsets.weight"] = 0.05 * torch.randn(2 * no, C, generator=g)
+    p["self_attn.sampling_offsets.bias"] = 1.5 * torch.randn(2 * no, generator=g)
+    p["self_attn.attention_weights.weight"] = 0.05 * torch.randn(no, C, generator=g)
+    p["self_attn.attention_weights.bias"] = 0.1 * torch.randn(no, generator=g)
+    _linear(g, "self_attn.value_proj", C, C, p)
+    _linear(g, "self_attn.output_proj", C, C, p)
+    _ln(g, C, "norm1", p)
+    _linear(g, "linear1", d_ffn, C, p)
+    _linear(g, "linear2", C, d_ffn, p)
+    _ln(g, C, "norm2", p)
+    return p

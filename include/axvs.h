@@ -211,6 +211,29 @@ int axvs_input_proj_fwd(const float* x_nchw, const void* w_packed, const float* 
 int axvs_output_proj_fwd(const float* tokens, const void* w_packed, const float* bias, const float* gn_w, const float* gn_b, float* out_nchw,
                          int images, int c_out, int hw, float eps, axvs_stream_t stream);
 
+/* ---- MSDeformAttn spatial encoder layer ------------------------------------------------------
+ * MSDeformAttnTransformerEncoderLayer.forward in eval mode without padding (WC/msdeformattn.py:205-215 with
+ * WC/ops/modules/ms_deform_attn.py:92-125; the module builds all-False masks, WC/msdeformattn.py:92):
+ *   y = src + output_proj(sample(value_proj(src), softmax(attention_weights(src+pos)), ref + sampling_offsets(src+pos)/(W,H)))
+ *   out = LN2(s + FFN(s)), s = LN1(y)
+ * src, pos, out fp32 [images, len, 256] (levels concatenated along len, low resolution first); ref_points fp32
+ * [images, len, n_levels, 2] normalised (x, y); shapes_hw = HOST array [n_levels][2] of (H, W).  8 heads of 32 channels.
+ * w_oa packs [sampling_offsets.weight (8*L*P*2 rows, order head, level, point, xy) ; attention_weights.weight (8*L*P rows) ;
+ * zero rows up to 512] with b_oa likewise (512 floats). */
+typedef struct axvs_msda_weights {
+  const void* w_value; const float* b_value;     /* value_proj  packed [256,256] */
+  const void* w_oa;    const float* b_oa;        /* offsets | logits packed [512,256], bias [512] */
+  const void* w_out;   const float* b_out;       /* output_proj packed [256,256] */
+  const float* ln1_g; const float* ln1_b;
+  const void* w_ffn1; const float* b_ffn1; const void* w_ffn2; const float* b_ffn2;   /* as in axvs_layer_weights */
+  const void* w_ffn1_u; const void* w_ffn2_u; const void* w_ffn1_n;
+  const float* ln2_g; const float* ln2_b;
+  int d_ffn, n_levels, n_points;
+} axvs_msda_weights;
+size_t axvs_msda_layer_workspace_bytes(int rows, int d_ffn);
+int axvs_msda_layer_fwd(const float* src, const float* pos, const float* ref_points, const int* shapes_hw, float* out,
+                        const axvs_msda_weights* w, int images, int len, void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+
 /* PositionEmbeddingSine3D(num_pos_feats=128, normalize=True) + level_embed_3d[lvl], channels-last
  * (WC/pos_embeddings.py:86-130, WC/msdeformattn.py:112-115).  out fp32 [B,T,H,W,256]; level_embed may be NULL. */
 int axvs_pos3d(float* out, const float* level_embed, int B, int T, int H, int W, axvs_stream_t stream);

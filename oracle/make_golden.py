@@ -163,6 +163,22 @@ def main():
                                                                                                 **{"o." + k: v for k, v in pout.items()}}))
 
 
+    # ---- 7. MSDeformAttn spatial encoder layer (row f2): the reference module on CPU (its pure-PyTorch sampling branch)
+    WCM = ref_loader.within_clip_module()
+    for tag, (n, shapes, seed) in {"a": (2, [(3, 4), (5, 6), (7, 9)], 91), "b": (1, [(4, 4), (9, 7), (17, 13)], 92)}.items():
+        p = synth.msda_layer_params(seed)
+        m = WCM.MSDeformAttnTransformerEncoderLayer(256, 1024, 0.0, "relu", 3, 8, 4).eval()
+        m.load_state_dict(p, strict=True)
+        Len = sum(h * w for h, w in shapes)
+        src = synth.randn(seed + 100, n, Len, 256)
+        pos = synth.randn(seed + 200, n, Len, 256)
+        ss = torch.tensor(shapes)
+        lsi = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+        ref = WCM.MSDeformAttnTransformerEncoder.get_reference_points(ss, torch.ones(n, 3, 2), "cpu")
+        out = m(src, pos, ref, ss, lsi, None)
+        save(f"msda_layer_{tag}", n=n, shapes=ss, seed=seed, out=out, ref_points=ref, wsum=synth.checksum(p))
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found; golden fixtures can only be generated where it is mounted")

@@ -138,3 +138,28 @@ def cross_clip():
     _cache["cc"] = _load("_axvs_ref_cross_clip",
                          os.path.join(CC, "maxtron_cross_clip_tracking_module.py"))
     return _cache["cc"]
+
+
+def within_clip_module():
+    """`WC/msdeformattn.py` (MSDeformAttn spatial layer, encoder, pixel-decoder plumbing) as a synthetic package so that its
+    relative imports (`.ops.modules`, `.pos_embeddings`, `.temporal_attention`) resolve.  The compiled
+    `MultiScaleDeformableAttention` extension is replaced by an empty module: `MSDeformAttn.forward` then falls into its own
+    pure-PyTorch `ms_deform_attn_core_pytorch` branch (WC/ops/modules/ms_deform_attn.py:116-121) -- the CPU path of the reference."""
+    if "wcm" in _cache:
+        return _cache["wcm"]
+    _install_stubs()
+    if "MultiScaleDeformableAttention" not in sys.modules:
+        sys.modules["MultiScaleDeformableAttention"] = types.ModuleType("MultiScaleDeformableAttention")
+    pkg = "_axvs_ref_wcm"
+    _pkg(pkg, WC)
+    _pkg(pkg + ".ops", os.path.join(WC, "ops"))
+    for sub in ("functions", "modules"):
+        d = os.path.join(WC, "ops", sub)
+        spec = importlib.util.spec_from_file_location(f"{pkg}.ops.{sub}", os.path.join(d, "__init__.py"), submodule_search_locations=[d])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[f"{pkg}.ops.{sub}"] = mod
+        spec.loader.exec_module(mod)
+    for name in ("pos_embeddings", "temporal_attention", "msdeformattn"):
+        _load(f"{pkg}.{name}", os.path.join(WC, name + ".py"))
+    _cache["wcm"] = sys.modules[pkg + ".msdeformattn"]
+    return _cache["wcm"]

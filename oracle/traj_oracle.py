@@ -442,6 +442,66 @@ def output_proj(tokens: Tensor, p: Params, H: int, W: int) -> Tensor:
     return group_norm(y, 32, p["1.weight"], p["1.bias"])
 
 
+# ------------------------------------------------------------------------------------------------ MSDeformAttn spatial layer (row f2)
+# MSDA = WC/ops/modules/ms_deform_attn.py, CORE = WC/ops/functions/ms_deform_attn_func.py, ENC = WC/msdeformattn.py
+def msda_reference_points(spatial_shapes, n_images: int) -> Tensor:
+    """ENC:231-245 with valid_ratios == 1 (the module builds all-False masks, ENC:92): the centre of every token's own cell,
+    normalised to [0,1], repeated for every level.  -> [n_images, sum(H*W), n_levels, 2] as (x, y)."""
+    pts = []
+    for (H, W) in spatial_shapes:
+        ys, xs = torch.meshgrid(torch.linspace(0.5, H - 0.5, H), torch.linspace(0.5, W - 0.5, W), indexing="ij")
+        pts.append(torch.stack((xs.reshape(-1) / W, ys.reshape(-1) / H), -1))
+    ref = torch.cat(pts, 0)                                                     # [Len, 2]
+    return ref[None, :, None, :].expand(n_images, -1, len(spatial_shapes), -1).contiguous()
+
+
+def ms_deform_attn(query: Tensor, reference_points: Tensor, src: Tensor, spatial_shapes, p: Params,
+                   n_heads: int = 8, n_points: int = 4) -> Tensor:
+    """MSDeformAttn.forward without padding mask -- MSDA:92-125 and the bilinear sampling of CORE:51-72
+    (grid_sample, align_corners=False, zero padding), written as explicit gathers."""
+    N, Lq, C = query.shape
+    L = len(spatial_shapes)
+    d = C // n_heads
+    value = linear(src, p["value_proj.weight"], p["value_proj.bias"]).reshape(N, -1, n_heads, d)          # :98-101
+    off = linear(query, p["sampling_offsets.weight"], p["sampling_offsets.bias"]).reshape(N, Lq, n_heads, L, n_points, 2)
+    aw = linear(query, p["attention_weights.weight"], p["attention_weights.bias"]).reshape(N, Lq, n_heads, L * n_points)
+    aw = torch.softmax(aw, -1).reshape(N, Lq, n_heads, L, n_points)                                       # :104
+    out = query.new_zeros(N, Lq, n_heads, d)
+    start = 0
+    for l, (H, W) in enumerate(spatial_shapes):
+        v = value[:, start:start + H * W]                                                                 # [N, H*W, h, d]
+        start += H * W
+        norm = torch.tensor([W, H], dtype=query.dtype)
+        loc = reference_points[:, :, None, l, None, :] + off[:, :, :, l] / norm                           # :107-109  [N,Lq,h,P,2]
+        x = loc[..., 0] * W - 0.5                                                                         # align_corners=False
+        y = loc[..., 1] * H - 0.5
+        x0, y0 = torch.floor(x), torch.floor(y)
+        fx, fy = x - x0, y - y0
+        for dy, wy in ((0, 1 - fy), (1, fy)):
+            for dx, wx in ((0, 1 - fx), (1, fx)):
+                xi, yi = (x0 + dx).long(), (y0 + dy).long()
+                ok = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)                                          # zero padding
+                idx = (yi.clamp(0, H - 1) * W + xi.clamp(0, W - 1))                                       # [N,Lq,h,P]
+                g = torch.gather(v.permute(0, 2, 1, 3), 2,                                                # [N,h,HW,d] gathered at [N,h,Lq*P]
+                                 idx.permute(0, 2, 1, 3).reshape(N, n_heads, -1, 1).expand(-1, -1, -1, d))
+                g = g.reshape(N, n_heads, Lq, n_points, d).permute(0, 2, 1, 3, 4)                         # [N,Lq,h,P,d]
+                wgt = (wx * wy * ok.to(query.dtype) * aw[:, :, :, l])[..., None]
+                out = out + (g * wgt).sum(3)
+    return linear(out.reshape(N, Lq, C), p["output_proj.weight"], p["output_proj.bias"])                  # :124
+
+
+def msda_encoder_layer(src: Tensor, pos: Tensor, reference_points: Tensor, spatial_shapes, p: Params) -> Tensor:
+    """MSDeformAttnTransformerEncoderLayer.forward (eval) -- ENC:205-215: src = LN1(src + MSDA(src+pos, ref, src)); LN2(src + FFN(src))."""
+    src2 = ms_deform_attn(src + pos, reference_points, src, spatial_shapes, _sub(p, "self_attn"))
+    src = layer_norm(src + src2, p["norm1.weight"], p["norm1.bias"])
+    return _ffn_tail_only(src, p)
+
+
+def _ffn_tail_only(src: Tensor, p: Params) -> Tensor:
+    h = torch.relu(linear(src, p["linear1.weight"], p["linear1.bias"]))
+    return layer_norm(src + linear(h, p["linear2.weight"], p["linear2.bias"]), p["norm2.weight"], p["norm2.bias"])
+
+
 def flops_trajectory_attention(Bp: int, N: int, F: int, C: int = 256) -> int:
     return Bp * N * C * (10 * C + 4 * F * C + 4 * N + 4 * F)
 

@@ -642,3 +642,44 @@ def test_projections_oracle_config_sizes(O, n, c, H, W):
         with torch.no_grad():
             y = mo.cuda()(ref_tok.contiguous().cuda(), H, W)
         assert nerr(y, O.output_proj(ref_tok, pout, H, W)) < TOL
+
+
+# --------------------------------------------------------------------------------------------- MSDeformAttn spatial layer (f2)
+def _msda_layer(p):
+    from axial_vs_b200.msda import MSDeformAttnTransformerEncoderLayer
+    m = MSDeformAttnTransformerEncoderLayer(256, 1024, 0.0, "relu", 3, 8, 4).eval()
+    m.load_state_dict(p, strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_msda_layer_golden(golden, tag):
+    from axial_vs_b200 import msda
+    gz = golden(f"msda_layer_{tag}")
+    n, seed = int(gz["n"]), int(gz["seed"])
+    shapes = [tuple(int(v) for v in r) for r in gz["shapes"]]
+    p = synth.msda_layer_params(seed)
+    Len = sum(h * w for h, w in shapes)
+    src, pos = synth.randn(seed + 100, n, Len, 256).cuda(), synth.randn(seed + 200, n, Len, 256).cuda()
+    ref = msda.reference_points(shapes, n, "cuda")
+    assert torch.allclose(ref.cpu(), torch.as_tensor(gz["ref_points"]), atol=1e-6)
+    with torch.no_grad():
+        out = _msda_layer(p)(src, pos, ref, torch.tensor(shapes), None, None)
+    assert nerr(out, torch.as_tensor(gz["out"])) < TOL
+
+
+@pytest.mark.parametrize("n,shapes", [(2, [(21, 21), (41, 41), (81, 81)]), (3, [(5, 7), (10, 13), (20, 27)])])
+def test_msda_layer_oracle_config_sizes(O, n, shapes):
+    """The R50 641x641 pyramid of BASELINE configs[1] (441 + 1681 + 6561 tokens per frame) and a ragged small pyramid."""
+    from axial_vs_b200 import msda
+    seed = 800 + n + shapes[0][0]
+    p = synth.msda_layer_params(seed)
+    Len = sum(h * w for h, w in shapes)
+    src, pos = synth.randn(seed + 1, n, Len, 256), synth.randn(seed + 2, n, Len, 256)
+    ref = O.msda_reference_points(shapes, n)
+    want = O.msda_encoder_layer(src, pos, ref, shapes, p)
+    with torch.no_grad():
+        out = _msda_layer(p)(src.cuda(), pos.cuda(), msda.reference_points(shapes, n, "cuda"), shapes)
+    e = nerr(out, want)
+    cos = torch.nn.functional.cosine_similarity(out.cpu().flatten(), want.flatten(), dim=0).item()
+    assert e < TOL and cos > 0.9999, (e, cos)

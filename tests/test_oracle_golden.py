@@ -134,3 +134,18 @@ def test_projections(golden, tag):
     tok = O.input_proj(x, pin)
     _close(tok, gz["tokens"])
     _close(O.output_proj(tok, pout, H, W), gz["y"], atol=5e-5)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_msda_layer(golden, tag):
+    """Row f2: MSDeformAttn spatial encoder layer against the reference module run on CPU (its pure-PyTorch sampling branch)."""
+    gz = golden(f"msda_layer_{tag}")
+    n, seed = int(gz["n"]), int(gz["seed"])
+    shapes = [tuple(int(v) for v in r) for r in gz["shapes"]]
+    p = synth.msda_layer_params(seed)
+    assert synth.checksum(p) == pytest.approx(float(gz["wsum"]), rel=1e-12)
+    Len = sum(h * w for h, w in shapes)
+    src, pos = synth.randn(seed + 100, n, Len, 256), synth.randn(seed + 200, n, Len, 256)
+    ref = O.msda_reference_points(shapes, n)
+    _close(ref, gz["ref_points"])
+    _close(O.msda_encoder_layer(src, pos, ref, shapes, p), gz["out"])
