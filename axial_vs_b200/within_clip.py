@@ -91,3 +91,42 @@ def run_temporal_levels(temporal_layer, memory: Tensor, spatial_shapes: Sequence
     for i in range(min(num_temporal_levels, len(parts))):
         parts[i], h_attn, w_attn = temporal_layer(src=parts[i].contiguous(), pos=pos_3d[i])
     return torch.cat(parts, dim=1), h_attn, w_attn
+
+
+class WithinClipEncoder(torch.nn.Module):
+    """Drop-in for `MSDeformAttnTransformerEncoder` (WC/msdeformattn.py:217-273): `num_stages` x [MSDeformAttn spatial layer on all
+    levels, then the SAME-stage TemporalEncoder on the first `num_temporal_levels` levels].  Same sub-module names
+    (`spatial_layers.{i}`, `temporal_layers.{i}`), forward signature and return tuple; unpadded feature maps only."""
+
+    def __init__(self, spatial_layer, num_stages, transformer_num_spatial_feature_levels, transformer_num_temporal_feature_levels=0,
+                 temporal_layer=None):
+        super().__init__()
+        import copy
+        self.spatial_layers = torch.nn.ModuleList([copy.deepcopy(spatial_layer) for _ in range(num_stages)])
+        self.transformer_num_spatial_feature_levels = transformer_num_spatial_feature_levels
+        self.transformer_num_temporal_feature_levels = transformer_num_temporal_feature_levels
+        if transformer_num_temporal_feature_levels > 0:
+            self.temporal_layers = torch.nn.ModuleList([copy.deepcopy(temporal_layer) for _ in range(num_stages)])
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device):
+        from . import msda
+        if valid_ratios is not None and not bool((valid_ratios == 1).all()):
+            raise NotImplementedError("axial_vs_b200: padded feature maps (valid_ratios != 1) are not supported")
+        shapes = [(int(h), int(w)) for h, w in (spatial_shapes.tolist() if torch.is_tensor(spatial_shapes) else spatial_shapes)]
+        n = valid_ratios.shape[0] if valid_ratios is not None else 1
+        return msda.reference_points(shapes, n, device)
+
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos, padding_mask, pos_3d=None):
+        output = src
+        shapes = [(int(h), int(w)) for h, w in (spatial_shapes.tolist() if torch.is_tensor(spatial_shapes) else spatial_shapes)]
+        reference_points = self.get_reference_points(shapes, valid_ratios, src.device)
+        if reference_points.shape[0] != src.shape[0]:
+            reference_points = reference_points[:1].expand(src.shape[0], -1, -1, -1).contiguous()
+        h_attn = w_attn = None
+        for i, spatial_layer in enumerate(self.spatial_layers):
+            output = spatial_layer(output, pos, reference_points, shapes, level_start_index, padding_mask)
+            if self.transformer_num_temporal_feature_levels > 0:
+                output, h_attn, w_attn = run_temporal_levels(self.temporal_layers[i], output, shapes, pos_3d,
+                                                             self.transformer_num_temporal_feature_levels)
+        return output, h_attn, w_attn

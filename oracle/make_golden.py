@@ -179,6 +179,28 @@ def main():
         save(f"msda_layer_{tag}", n=n, shapes=ss, seed=seed, out=out, ref_points=ref, wsum=synth.checksum(p))
 
 
+    # ---- 8. the whole within-clip transformer encoder (rows A6 + f2): reference MSDeformAttnTransformerEncoder on CPU,
+    #         2 stages x [spatial layer on 3 levels, TemporalEncoder(1 axial layer) on the first 2 levels]
+    B, T, shapes, seed = 1, 2, [(3, 4), (5, 6), (7, 9)], 95
+    sp = WCM.MSDeformAttnTransformerEncoderLayer(256, 1024, 0.0, "relu", 3, 8, 4)
+    tp = WCM.TemporalEncoder(256, 1024, 0.0, 0.0, "relu", 8, "axial-trajectory", 1)
+    enc = WCM.MSDeformAttnTransformerEncoder(sp, 2, 3, 2, tp).eval()
+    state = {}
+    for i in range(2):
+        state.update({f"spatial_layers.{i}.{k}": v for k, v in synth.msda_layer_params(seed + i).items()})
+        state.update({f"temporal_layers.{i}.{k}": v for k, v in synth.encoder_params(seed + 10 + i, 1).items()})
+    enc.load_state_dict(state, strict=True)
+    Len = sum(h * w for h, w in shapes)
+    src = synth.randn(seed + 100, B * T, Len, 256)
+    pos = synth.randn(seed + 200, B * T, Len, 256)
+    le = synth.level_embed(seed + 300)
+    pos3d = [O.level_pos3d(B, T, h, w, le[i]) for i, (h, w) in enumerate(shapes[:2])]
+    ss = torch.tensor(shapes)
+    lsi = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+    out, _, _ = enc(src, ss, lsi, torch.ones(B * T, 3, 2), pos, torch.zeros(B * T, Len, dtype=torch.bool), pos3d)
+    save("wc_encoder", B=B, T=T, shapes=ss, seed=seed, out=out, wsum=synth.checksum(state))
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found; golden fixtures can only be generated where it is mounted")

@@ -502,6 +502,22 @@ def _ffn_tail_only(src: Tensor, p: Params) -> Tensor:
     return layer_norm(src + linear(h, p["linear2.weight"], p["linear2.bias"]), p["norm2.weight"], p["norm2.bias"])
 
 
+def within_clip_encoder(src: Tensor, spatial_shapes, pos: Tensor, pos_3d: List[Tensor], spatial: List[Params],
+                        temporal: List[List[Params]], num_temporal_levels: int) -> Tensor:
+    """MSDeformAttnTransformerEncoder.forward (unpadded) -- ENC:247-273: per stage the spatial layer on every level, then the
+    stage's TemporalEncoder on the first `num_temporal_levels` levels (split / concat along the token axis, ENC:251-266)."""
+    ref = msda_reference_points(spatial_shapes, src.shape[0])
+    sizes = [h * w for h, w in spatial_shapes]
+    out = src
+    for sp, tl in zip(spatial, temporal):
+        out = msda_encoder_layer(out, pos, ref, spatial_shapes, sp)
+        parts = list(torch.split(out, sizes, dim=1))
+        for i in range(num_temporal_levels):
+            parts[i], _, _ = temporal_encoder(parts[i], pos_3d[i], tl, "axial-trajectory")
+        out = torch.cat(parts, dim=1)
+    return out
+
+
 def flops_trajectory_attention(Bp: int, N: int, F: int, C: int = 256) -> int:
     return Bp * N * C * (10 * C + 4 * F * C + 4 * N + 4 * F)
 

@@ -683,3 +683,24 @@ def test_msda_layer_oracle_config_sizes(O, n, shapes):
     e = nerr(out, want)
     cos = torch.nn.functional.cosine_similarity(out.cpu().flatten(), want.flatten(), dim=0).item()
     assert e < TOL and cos > 0.9999, (e, cos)
+
+
+def test_within_clip_encoder_golden(golden):
+    """The whole within-clip transformer encoder (drop-in for MSDeformAttnTransformerEncoder): 2 stages x [MSDeformAttn spatial
+    layer on 3 levels, TemporalEncoder on the first 2], same state-dict keys as the reference, against its CPU output."""
+    from axial_vs_b200 import msda, modules, within_clip
+    from _cases import wc_encoder_case as _wc_encoder_case
+    gz = golden("wc_encoder")
+    B, T, shapes, spatial, temporal_states, state, src, pos, pos3d = _wc_encoder_case(gz)
+    enc = within_clip.WithinClipEncoder(msda.MSDeformAttnTransformerEncoderLayer(256, 1024, 0.0, "relu", 3, 8, 4), 2, 3, 2,
+                                        modules.TemporalEncoder(256, 1024, 0.0, 0.0, "relu", 8, "axial-trajectory", 1)).eval()
+    enc.load_state_dict(state, strict=True)
+    enc.cuda()
+    Len = src.shape[1]
+    ss = torch.tensor(shapes)
+    lsi = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+    with torch.no_grad():
+        out, h, w = enc(src.cuda(), ss, lsi, torch.ones(B * T, 3, 2, device="cuda"), pos.cuda(),
+                        torch.zeros(B * T, Len, dtype=torch.bool, device="cuda"), [p.cuda() for p in pos3d])
+    assert h is None and w is None
+    assert nerr(out, torch.as_tensor(gz["out"])) < 1.5e-2        # four chained bf16 layers

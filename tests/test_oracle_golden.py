@@ -149,3 +149,17 @@ def test_msda_layer(golden, tag):
     ref = O.msda_reference_points(shapes, n)
     _close(ref, gz["ref_points"])
     _close(O.msda_encoder_layer(src, pos, ref, shapes, p), gz["out"])
+
+
+from _cases import wc_encoder_case as _wc_encoder_case  # noqa: E402
+
+
+def test_within_clip_encoder(golden):
+    """Rows A6 + f2 together: the reference MSDeformAttnTransformerEncoder (2 stages, spatial layer on 3 levels + temporal layer
+    on 2) against the oracle's composition of its spatial and temporal restatements."""
+    gz = golden("wc_encoder")
+    B, T, shapes, spatial, temporal_states, state, src, pos, pos3d = _wc_encoder_case(gz)
+    assert synth.checksum(state) == pytest.approx(float(gz["wsum"]), rel=1e-12)
+    temporal = [O.split_encoder_params(ts) for ts in temporal_states]
+    out = O.within_clip_encoder(src, shapes, pos, pos3d, spatial, temporal, 2)
+    _close(out, gz["out"], atol=5e-5)
