@@ -19,7 +19,7 @@ constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KiB
 constexpr int GEMM_W_BYTES = GEMM_BN * GEMM_BK * 2;   // 32 KiB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_W_BYTES;
-constexpr int GEMM_EPI_WARPS = 4;
+constexpr int GEMM_EPI_WARPS = 8;   // two groups of four (TMEM lane quarter = warp & 3), each draining 128 of the 256 accumulator columns
 constexpr int GEMM_APROD_WARPS = 8;
 constexpr int GEMM_THREADS = (GEMM_EPI_WARPS + 2 + GEMM_APROD_WARPS) * 32;   // 320
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -179,10 +179,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
       const int mt = tile / n_chunks, nc = tile % n_chunks;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = mt * GEMM_BM + warp * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * GEMM_BN;
+      const int row = mt * GEMM_BM + (warp & 3) * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * GEMM_BN;
+      const int c_begin = (warp >> 2) * (GEMM_BN / 2);
 #pragma unroll 1
-      for (int c = 0; c < GEMM_BN; c += 32) {
+      for (int c = c_begin; c < c_begin + GEMM_BN / 2; c += 32) {
         float v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
