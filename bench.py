@@ -134,7 +134,7 @@ def cpu_baseline_sample(budget_s: float = 12.0):
         el = time.perf_counter() - t0
         if el >= budget_s or n >= 200:
             break
-    return {"value": n / el, "unit": METRIC, "cores": cores, "kind": "port",
+    return {"value": n / el, "unit": "clips/s", "cores": cores, "kind": "port",
             "sample": f"{n} clips (T=2, res5 21x21 + res4 41x41, 2 stages x 2 layers) in {el:.1f} s, fp32 torch-CPU oracle port"}
 
 
@@ -153,9 +153,10 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(1),
+            "config": workload_config(args.clips),
             "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
-                             "sample": "1 clip per step; the oracle port of the reference modules (oracle/traj_oracle.py), all host threads"},
+                             "sample": "bounded sample of the workload: 1 clip per timed step (the CPU port is batch-size independent: clips run "
+                                       "one after the other); the oracle port of the reference modules (oracle/traj_oracle.py), all host threads"},
             "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
