@@ -274,7 +274,7 @@ int blocks_for(long long work_items, int per_block, int sms) {
 
 extern "C" {
 
-int axvs_version(void) { return 106; }
+int axvs_version(void) { return 110; }
 int axvs_set_pair_mode(int on) {
   const int prev = g_pair;
   g_pair = on ? 1 : 0;

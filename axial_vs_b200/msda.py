@@ -34,21 +34,22 @@ class MSDeformAttn(nn.Module):
         self.output_proj = nn.Linear(d_model, d_model)
         self._reset_parameters()
 
-    def _reset_parameters(self):                                   # WC/ops/modules/ms_deform_attn.py:67-83
-        nn.init.constant_(self.sampling_offsets.weight.data, 0.)
-        thetas = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
-        grid = torch.stack([thetas.cos(), thetas.sin()], -1)
-        grid = (grid / grid.abs().max(-1, keepdim=True)[0]).view(self.n_heads, 1, 1, 2).repeat(1, self.n_levels, self.n_points, 1)
-        for i in range(self.n_points):
-            grid[:, :, i, :] *= i + 1
+    def _reset_parameters(self):
+        """Same initial values as the reference (WC/ops/modules/ms_deform_attn.py:67-83): zero offset / attention weights, offset
+        biases pointing in 8 compass directions (one per head, unit max-norm) scaled by the point index 1..P, Xavier projections."""
+        ang = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
+        dirs = torch.stack([ang.cos(), ang.sin()], dim=-1)
+        dirs = dirs / dirs.abs().amax(dim=-1, keepdim=True)                                  # [heads, 2]
+        steps = torch.arange(1, self.n_points + 1, dtype=torch.float32).view(1, 1, self.n_points, 1)
+        bias = (dirs.view(self.n_heads, 1, 1, 2) * steps).expand(-1, self.n_levels, -1, -1)  # [heads, levels, points, 2]
         with torch.no_grad():
-            self.sampling_offsets.bias = nn.Parameter(grid.view(-1))
-        nn.init.constant_(self.attention_weights.weight.data, 0.)
-        nn.init.constant_(self.attention_weights.bias.data, 0.)
-        nn.init.xavier_uniform_(self.value_proj.weight.data)
-        nn.init.constant_(self.value_proj.bias.data, 0.)
-        nn.init.xavier_uniform_(self.output_proj.weight.data)
-        nn.init.constant_(self.output_proj.bias.data, 0.)
+            self.sampling_offsets.weight.zero_()
+            self.sampling_offsets.bias.copy_(bias.reshape(-1))
+            self.attention_weights.weight.zero_()
+            self.attention_weights.bias.zero_()
+            for lin in (self.value_proj, self.output_proj):
+                nn.init.xavier_uniform_(lin.weight)
+                lin.bias.zero_()
 
 
 class MSDeformAttnTransformerEncoderLayer(nn.Module):
