@@ -347,9 +347,15 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = sum(v["launches"] for v in ops.profile_read().values())
     if args.graph:                                  # capture outside the warm-up / timed regions (both input sets, both e2e slots)
-        for k in range(2):
-            step_resident_graph(k)
-        torch.cuda.synchronize()
+        try:
+            for k in range(2):
+                step_resident_graph(k)
+            torch.cuda.synchronize()
+        except Exception as e:                      # capture is an optimisation of the launch path, never a requirement
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); falling back to eager launches", file=sys.stderr)
+            graphs.clear()
+            args.graph = 0
+            torch.cuda.synchronize()
     resident = step_resident_graph if args.graph else step_resident
     for k in range(args.warmup):
         resident(k)
