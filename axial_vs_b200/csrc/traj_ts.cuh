@@ -302,8 +302,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
               }
             }
           }
-          // the partner must have read my statistics before my next tile's transposes overwrite them
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          // (no second barrier: my next write to this staging area is the next tile's projection transpose, which cannot start before
+          //  the partner warp has arrived on o_ready for that tile -- i.e. long after it has read these statistics)
         }
       }
     }
