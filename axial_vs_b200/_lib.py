@@ -74,7 +74,8 @@ SIGNATURES = {
     "axvs_input_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "axvs_output_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "axvs_msda_layer_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "axvs_msda_layer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int), c_void_p, POINTER(MsdaWeights), c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "axvs_msda_layer_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, POINTER(c_int), c_void_p, POINTER(MsdaWeights), c_int, c_int, c_void_p, c_size_t,
+                                    c_void_p]),
     "axvs_mask_einsum": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "axvs_pos3d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "axvs_profile_enable": (c_int, [c_int]),

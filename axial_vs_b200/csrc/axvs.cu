@@ -973,11 +973,14 @@ size_t axvs_msda_layer_workspace_bytes(int rows, int d_ffn) {
   return (size_t)rows * (512 + 2048 + 512 + 1024) + 1024 + carve_ffn(nullptr, (size_t)rows, d_ffn).bytes;
 }
 
-int axvs_msda_layer_fwd(const float* src, const float* pos, const float* ref_points, const int* shapes_hw, float* out,
-                        const axvs_msda_weights* w, int images, int len, void* workspace, size_t workspace_bytes, axvs_stream_t stream) {
+int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, const float* ref_points, int ref_images, const int* shapes_hw,
+                        float* out, const axvs_msda_weights* w, int images, int len, void* workspace, size_t workspace_bytes,
+                        axvs_stream_t stream) {
   if (!src || !ref_points || !shapes_hw || !out || !w || !workspace) return fail(AXVS_E_INVALID, "msda_layer: null pointer");
   if (!w->w_value || !w->w_oa || !w->w_out || !w->b_value || !w->b_oa || !w->b_out) return fail(AXVS_E_INVALID, "msda_layer: null weight pointer");
   if (images <= 0 || len <= 0) return fail(AXVS_E_INVALID, "msda_layer: sizes must be positive");
+  if ((pos && pos_images != images && pos_images != 1) || (ref_images != images && ref_images != 1))
+    return fail(AXVS_E_INVALID, "msda_layer: pos / reference points must cover every image or exactly one (broadcast)");
   if (w->n_levels <= 0 || w->n_levels > MSDA_MAX_LEVELS || w->n_points <= 0 || w->n_levels * w->n_points > MSDA_MAX_LP)
     return fail(AXVS_E_UNSUPPORTED, "msda_layer: at most %d levels and %d level*point samples per head (got %d x %d)", MSDA_MAX_LEVELS, MSDA_MAX_LP,
                 w->n_levels, w->n_points);
@@ -1009,11 +1012,11 @@ int axvs_msda_layer_fwd(const float* src, const float* pos, const float* ref_poi
   if ((rc = launch_gemm(p, st))) return rc;
   // [sampling offsets | attention logits] = Linear(src + pos)                                       MSDA:102-103 (query = src + pos, ENC:207)
   p = gemm_params(nullptr, 256, rows, 256, w->w_oa, 512, 0, w->b_oa, 512, 1.f, 0, oa, 512, 0, 0, nullptr);
-  p.a_diag = 4; p.A32 = src; p.A32b = pos;
+  p.a_diag = 4; p.A32 = src; p.A32b = pos; p.a32b_rows = (pos && pos_images == 1 && images > 1) ? len : 0;
   if ((rc = launch_gemm(p, st))) return rc;
   {
     ProfScope ps(KC_MSDA, 0, (double)rows * (8.0 * d.L * d.P * 4 * 64 + 2048 + 512), st);
-    msda_sample_kernel<<<(rows + 3) / 4, 256, 0, st>>>(value, oa, 512, ref_points, samp, rows, d);
+    msda_sample_kernel<<<(rows + 3) / 4, 256, 0, st>>>(value, oa, 512, ref_points, (ref_images == 1 && images > 1) ? len : 0, samp, rows, d);
   }
   AXVS_CHECK_LAUNCH("msda_sample_kernel");
   // y = src + output_proj(sampled)                                                                   MSDA:124, ENC:208

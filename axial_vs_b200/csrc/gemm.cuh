@@ -69,6 +69,7 @@ struct GemmParams {
   int a_N, a_n, a_F;
   const float* A32;
   const float* A32b;    // mode 4 only: optional second fp32 matrix added element-wise (e.g. src + pos), same layout as A32
+  int a32b_rows;        // > 0: A32b has only this many rows and is broadcast (row r reads A32b row r % a32b_rows)
   // W operand (packed) and bias
   const uint8_t* Wp;
   int w_rows_total;   // rows of the packed image (K-block stride = w_rows_total * 128 B)
@@ -289,7 +290,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
                 const float4* s = reinterpret_cast<const float4*>(p.A32 + o);
                 float4 a = __ldg(s), b = __ldg(s + 1);
                 if (p.A32b) {
-                  const float4* s2 = reinterpret_cast<const float4*>(p.A32b + o);
+                  const size_t o2 = p.a32b_rows > 0 ? (size_t)(r % p.a32b_rows) * p.lda + kb * GEMM_BK + (q & 7) * 8 : o;
+                  const float4* s2 = reinterpret_cast<const float4*>(p.A32b + o2);
                   const float4 a2 = __ldg(s2), b2 = __ldg(s2 + 1);
                   a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w; b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
                 }

@@ -18,10 +18,11 @@ struct MsdaDims {
 
 // value bf16 [images*len, 256] (value_proj output, channel = head*32 + j); oa fp32 [images*len, ld_oa]:
 // columns [0, 8*L*P*2) = sampling offsets ordered (head, level, point, xy), then 8*L*P attention logits (head, level, point);
-// ref fp32 [images*len, L, 2] normalised (x, y) reference points; out bf16 [images*len, 256].
+// ref fp32 [images*len, L, 2] normalised (x, y) reference points (ref_rows > 0: only that many rows, shared by every image);
+// out bf16 [images*len, 256].
 // 256 threads = 4 tokens x (8 heads x 8 four-channel groups): each thread gathers 4 channels with 8-byte loads.
 __global__ void __launch_bounds__(256) msda_sample_kernel(const __nv_bfloat16* __restrict__ value, const float* __restrict__ oa, int ld_oa,
-                                                          const float* __restrict__ ref, __nv_bfloat16* __restrict__ out, int rows, MsdaDims d) {
+                                                          const float* __restrict__ ref, int ref_rows, __nv_bfloat16* __restrict__ out, int rows, MsdaDims d) {
   const int token = blockIdx.x * 4 + (threadIdx.x >> 6);
   if (token >= rows) return;
   const int lane64 = threadIdx.x & 63, head = lane64 >> 3, cg = lane64 & 7;
@@ -49,7 +50,8 @@ __global__ void __launch_bounds__(256) msda_sample_kernel(const __nv_bfloat16* _
   for (int l = 0; l < MSDA_MAX_LEVELS; ++l) {
     if (l >= d.L) break;
     const int H = d.H[l], W = d.W[l];
-    const float rx = __ldg(ref + ((size_t)token * d.L + l) * 2), ry = __ldg(ref + ((size_t)token * d.L + l) * 2 + 1);
+    const size_t rrow = ref_rows > 0 ? (size_t)(token % ref_rows) : (size_t)token;
+    const float rx = __ldg(ref + (rrow * d.L + l) * 2), ry = __ldg(ref + (rrow * d.L + l) * 2 + 1);
     const __nv_bfloat16* vl = vbase + (size_t)d.start[l] * C256;
     for (int pt = 0; pt < d.P; ++pt) {
       const float2 off = __ldg(reinterpret_cast<const float2*>(o_row + ((head * d.L + l) * d.P + pt) * 2));

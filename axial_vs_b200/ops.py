@@ -531,14 +531,19 @@ def pack_msda_layer(p: Dict[str, torch.Tensor], n_levels: int, n_points: int) ->
 
 def msda_layer_fwd(src: torch.Tensor, pos: Optional[torch.Tensor], ref_points: torch.Tensor, shapes: Sequence[Tuple[int, int]],
                    w: PackedMsda) -> torch.Tensor:
-    """MSDeformAttn spatial encoder layer: src, pos fp32 [images, len, 256]; ref_points fp32 [images, len, n_levels, 2]."""
+    """MSDeformAttn spatial encoder layer: src fp32 [images, len, 256]; pos fp32 [images or 1, len, 256]; ref_points fp32
+    [images or 1, len, n_levels, 2] (a leading dimension of 1 is broadcast over the images inside the kernels)."""
     _check(src, "src", torch.float32)
     images, length, c = src.shape
     if c != C:
         raise RuntimeError("msda_layer_fwd: 256 channels expected")
     if pos is not None:
-        _check(pos, "pos", torch.float32, src.shape)
-    _check(ref_points, "reference_points", torch.float32, (images, length, w.n_levels, 2))
+        _check(pos, "pos", torch.float32)
+        if pos.dim() != 3 or pos.shape[0] not in (1, images) or tuple(pos.shape[1:]) != (length, C):
+            raise RuntimeError(f"msda_layer_fwd: pos must be [{images} or 1, {length}, {C}], got {tuple(pos.shape)}")
+    _check(ref_points, "reference_points", torch.float32)
+    if ref_points.dim() != 4 or ref_points.shape[0] not in (1, images) or tuple(ref_points.shape[1:]) != (length, w.n_levels, 2):
+        raise RuntimeError(f"msda_layer_fwd: reference_points must be [{images} or 1, {length}, {w.n_levels}, 2]")
     if len(shapes) != w.n_levels or sum(int(h) * int(v) for h, v in shapes) != length:
         raise RuntimeError("msda_layer_fwd: spatial shapes do not match the token count")
     out = torch.empty_like(src)
@@ -548,8 +553,9 @@ def msda_layer_fwd(src: torch.Tensor, pos: Optional[torch.Tensor], ref_points: t
     with torch.cuda.device(src.device):
         ws = workspace(nbytes, src.device)
         st = w.struct()
-        rc = lib.axvs_msda_layer_fwd(src.data_ptr(), pos.data_ptr() if pos is not None else None, ref_points.data_ptr(), hw, out.data_ptr(),
-                                     ctypes.byref(st), images, length, ws.data_ptr(), ws.numel(), _stream(src.device))
+        rc = lib.axvs_msda_layer_fwd(src.data_ptr(), pos.data_ptr() if pos is not None else None, pos.shape[0] if pos is not None else 0,
+                                     ref_points.data_ptr(), ref_points.shape[0], hw, out.data_ptr(), ctypes.byref(st), images, length,
+                                     ws.data_ptr(), ws.numel(), _stream(src.device))
     _lib.check(rc, "axvs_msda_layer_fwd")
     return out
 

@@ -160,3 +160,26 @@ def msda_layer_params(seed: int, n_levels: int = 3, n_heads: int = 8, n_points: 
     _linear(g, "linear2", C, d_ffn, p)
     _ln(g, C, "norm2", p)
     return p
+
+
+def within_clip_module_params(seed: int, channels, num_stages: int = 2, temporal_layers_per_stage: int = 1) -> Params:
+    """State dict of the whole within-clip tracking module (MSDeformAttnPixelDecoder, WC/msdeformattn.py:293-402) for feature
+    levels given top-down (`channels` = [res5, res4, res3] widths): projections, level embeddings, spatial and temporal layers."""
+    p: Params = {}
+    g = torch.Generator().manual_seed(seed)
+    for i, c in enumerate(channels):
+        p[f"input_proj.{i}.0.weight"] = _xavier(g, 256, c, 1, 1)
+        p[f"input_proj.{i}.0.bias"] = 0.1 * torch.randn(256, generator=g)
+        p[f"input_proj.{i}.1.weight"] = 1.0 + 0.2 * torch.randn(256, generator=g)
+        p[f"input_proj.{i}.1.bias"] = 0.1 * torch.randn(256, generator=g)
+        p[f"output_proj.{i}.0.weight"] = _xavier(g, c, 256, 1, 1)
+        p[f"output_proj.{i}.0.bias"] = 0.1 * torch.randn(c, generator=g)
+        p[f"output_proj.{i}.1.weight"] = 1.0 + 0.2 * torch.randn(c, generator=g)
+        p[f"output_proj.{i}.1.bias"] = 0.1 * torch.randn(c, generator=g)
+    p["transformer.level_embed_2d"] = torch.randn(len(channels), 256, generator=g)
+    p["transformer.level_embed_3d"] = torch.randn(2, 256, generator=g)
+    for i in range(num_stages):
+        p.update({f"transformer.encoder.spatial_layers.{i}.{k}": v for k, v in msda_layer_params(seed + 1 + i, len(channels)).items()})
+        p.update({f"transformer.encoder.temporal_layers.{i}.{k}": v
+                  for k, v in encoder_params(seed + 11 + i, temporal_layers_per_stage).items()})
+    return p

@@ -120,9 +120,7 @@ class WithinClipEncoder(torch.nn.Module):
     def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos, padding_mask, pos_3d=None):
         output = src
         shapes = [(int(h), int(w)) for h, w in (spatial_shapes.tolist() if torch.is_tensor(spatial_shapes) else spatial_shapes)]
-        reference_points = self.get_reference_points(shapes, valid_ratios, src.device)
-        if reference_points.shape[0] != src.shape[0]:
-            reference_points = reference_points[:1].expand(src.shape[0], -1, -1, -1).contiguous()
+        reference_points = self.get_reference_points(shapes, valid_ratios, src.device)[:1].contiguous()   # identical for every image: broadcast
         h_attn = w_attn = None
         for i, spatial_layer in enumerate(self.spatial_layers):
             output = spatial_layer(output, pos, reference_points, shapes, level_start_index, padding_mask)
@@ -130,3 +128,78 @@ class WithinClipEncoder(torch.nn.Module):
                 output, h_attn, w_attn = run_temporal_levels(self.temporal_layers[i], output, shapes, pos_3d,
                                                              self.transformer_num_temporal_feature_levels)
         return output, h_attn, w_attn
+
+
+class _EncoderOnly(torch.nn.Module):
+    """Parameter layout of `MSDeformAttnTransformerEncoderOnly` (WC/msdeformattn.py:30-80): level embeddings + `encoder`."""
+
+    def __init__(self, d_model, nhead, num_stages, num_spatial_layers, num_temporal_layers, temporal_attn_type, dim_feedforward, dropout,
+                 attn_drop, num_spatial_feature_levels, num_temporal_feature_levels):
+        super().__init__()
+        from . import modules, msda
+        if not (num_spatial_layers > 0 and num_temporal_layers > 0 and num_spatial_layers == num_stages):
+            raise NotImplementedError("axial_vs_b200.WithinClipTrackingModule: spatial + temporal layers per stage (every shipped config)")
+        spatial = msda.MSDeformAttnTransformerEncoderLayer(d_model, dim_feedforward, dropout, "relu", num_spatial_feature_levels, nhead, 4)
+        temporal = modules.TemporalEncoder(d_model, dim_feedforward, dropout, attn_drop, "relu", nhead, temporal_attn_type,
+                                           num_temporal_layers // num_stages)
+        self.encoder = WithinClipEncoder(spatial, num_spatial_layers, num_spatial_feature_levels, num_temporal_feature_levels, temporal)
+        self.level_embed_2d = torch.nn.Parameter(torch.randn(num_spatial_feature_levels, d_model))
+        self.level_embed_3d = torch.nn.Parameter(torch.randn(num_temporal_feature_levels, d_model))
+
+
+class WithinClipTrackingModule(torch.nn.Module):
+    """Drop-in for `MSDeformAttnPixelDecoder` (WC/msdeformattn.py:293-435), the within-clip tracking module: input projections,
+    2-D / 3-D positional terms, `num_stages` x [MSDeformAttn spatial layer + trajectory-attention temporal layers], output
+    projections.  Same constructor keywords (`input_shape` maps a feature name to an object with `.channels` / `.stride`), same
+    state-dict keys (`input_proj.{i}.{0,1}.*`, `output_proj.{i}.{0,1}.*`, `transformer.level_embed_{2d,3d}`,
+    `transformer.encoder.{spatial,temporal}_layers.*`) and the same `forward_features(features) -> (out, h_attn, w_attn)`.
+    Differences inside: the positional tables are built once per shape and shared by all frames, tokens stay token-major between
+    the projections and the encoder, and no NCHW <-> token copies are made."""
+
+    def __init__(self, input_shape, *, transformer_dropout, transformer_attn_drop, transformer_nheads, transformer_dim_feedforward,
+                 transformer_num_stages, transformer_spatial_layers, transformer_temporal_layers, transformer_temporal_attn_type, conv_dims,
+                 transformer_spatial_in_features, transformer_temporal_in_features, num_clip_frames, cross_clip_training):
+        super().__init__()
+        from .pos import PositionEmbeddingSine
+        from .projections import InputProjection, OutputProjection
+        self.transformer_temporal_layers, self.num_clip_frames, self.cross_clip_training = transformer_temporal_layers, num_clip_frames, cross_clip_training
+        spatial = sorted(((k, v) for k, v in input_shape.items() if k in transformer_spatial_in_features), key=lambda kv: kv[1].stride)
+        temporal = sorted(((k, v) for k, v in input_shape.items() if k in transformer_temporal_in_features), key=lambda kv: kv[1].stride)
+        self.transformer_spatial_in_features = [k for k, _ in spatial]           # "res3" .. "res5"
+        self.transformer_temporal_in_features = [k for k, _ in temporal]
+        chans = [v.channels for _, v in spatial]
+        self.transformer_num_spatial_feature_levels = len(spatial)
+        self.transformer_num_temporal_feature_levels = len(temporal)
+        self.input_proj = torch.nn.ModuleList([InputProjection(c, conv_dims) for c in chans[::-1]])      # low resolution first
+        self.output_proj = torch.nn.ModuleList([OutputProjection(c, conv_dims) for c in chans[::-1]])
+        self.transformer = _EncoderOnly(conv_dims, transformer_nheads, transformer_num_stages, transformer_spatial_layers,
+                                        transformer_temporal_layers, transformer_temporal_attn_type, transformer_dim_feedforward,
+                                        transformer_dropout, transformer_attn_drop, len(spatial), len(temporal))
+        self.pe_layer = PositionEmbeddingSine(conv_dims // 2, normalize=True)
+        self.pe_layer_3d = PositionEmbeddingSine3D(conv_dims // 2, normalize=True)
+
+    @torch.no_grad()
+    def forward_features(self, features):
+        names = self.transformer_spatial_in_features[::-1]                        # top-down: res5, res4, res3
+        BT = features[names[0]].shape[0]
+        B = BT // self.num_clip_frames if (self.training or self.cross_clip_training) else 1
+        T = BT // B
+        tokens, pos2d, shapes, pos3d = [], [], [], []
+        for i, f in enumerate(names):
+            x = features[f]
+            H, W = int(x.shape[2]), int(x.shape[3])
+            shapes.append((H, W))
+            tokens.append(self.input_proj[i](x))                                  # [BT, H*W, 256]
+            pos2d.append(self.pe_layer.table(H, W, x.device) + self.transformer.level_embed_2d[i].detach().float())
+            if f in self.transformer_temporal_in_features:
+                pos3d.append(self.pe_layer_3d.table(B, T, H, W, x.device, self.transformer.level_embed_3d[len(pos3d)]))
+        src = torch.cat(tokens, dim=1)
+        pos = torch.cat(pos2d, dim=0)[None].contiguous()                          # [1, Len, 256], broadcast over the frames
+        y, h_attn, w_attn = self.transformer.encoder(src, shapes, None, None, pos, None, pos3d)
+        out = {}
+        start = 0
+        for i, (H, W) in enumerate(shapes):
+            z = y[:, start:start + H * W].contiguous()
+            start += H * W
+            out[names[i]] = self.output_proj[i](z, H, W)
+        return out, h_attn, w_attn

@@ -218,6 +218,8 @@ int axvs_output_proj_fwd(const float* tokens, const void* w_packed, const float*
  *   out = LN2(s + FFN(s)), s = LN1(y)
  * src, pos, out fp32 [images, len, 256] (levels concatenated along len, low resolution first); ref_points fp32
  * [images, len, n_levels, 2] normalised (x, y); shapes_hw = HOST array [n_levels][2] of (H, W).  8 heads of 32 channels.
+ * pos_images / ref_images = number of images pos / ref_points cover: `images`, or 1 when the (input-independent) tensor is shared
+ * by every image and broadcast inside the kernels.
  * w_oa packs [sampling_offsets.weight (8*L*P*2 rows, order head, level, point, xy) ; attention_weights.weight (8*L*P rows) ;
  * zero rows up to 512] with b_oa likewise (512 floats). */
 typedef struct axvs_msda_weights {
@@ -231,8 +233,9 @@ typedef struct axvs_msda_weights {
   int d_ffn, n_levels, n_points;
 } axvs_msda_weights;
 size_t axvs_msda_layer_workspace_bytes(int rows, int d_ffn);
-int axvs_msda_layer_fwd(const float* src, const float* pos, const float* ref_points, const int* shapes_hw, float* out,
-                        const axvs_msda_weights* w, int images, int len, void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, const float* ref_points, int ref_images, const int* shapes_hw,
+                        float* out, const axvs_msda_weights* w, int images, int len, void* workspace, size_t workspace_bytes,
+                        axvs_stream_t stream);
 
 /* PositionEmbeddingSine3D(num_pos_feats=128, normalize=True) + level_embed_3d[lvl], channels-last
  * (WC/pos_embeddings.py:86-130, WC/msdeformattn.py:112-115).  out fp32 [B,T,H,W,256]; level_embed may be NULL. */

@@ -201,6 +201,24 @@ def main():
     save("wc_encoder", B=B, T=T, shapes=ss, seed=seed, out=out, wsum=synth.checksum(state))
 
 
+    # ---- 9. the whole within-clip tracking module (MSDeformAttnPixelDecoder.forward_features): projections, positional terms,
+    #         2 stages x [spatial layer, temporal layer], output projections; B=1, T=2, three small levels
+    D2L = sys.modules["detectron2.layers"]
+    chans, sizes, seed = [512, 256, 256], [(3, 4), (5, 6), (7, 9)], 97            # res5, res4, res3
+    shape = {"res2": D2L.ShapeSpec(channels=64, stride=4), "res3": D2L.ShapeSpec(channels=chans[2], stride=8),
+             "res4": D2L.ShapeSpec(channels=chans[1], stride=16), "res5": D2L.ShapeSpec(channels=chans[0], stride=32)}
+    mod = WCM.MSDeformAttnPixelDecoder(shape, transformer_dropout=0.0, transformer_attn_drop=0.0, transformer_nheads=8,
+                                       transformer_dim_feedforward=1024, transformer_num_stages=2, transformer_spatial_layers=2,
+                                       transformer_temporal_layers=2, transformer_temporal_attn_type="axial-trajectory", conv_dims=256,
+                                       transformer_spatial_in_features=["res3", "res4", "res5"],
+                                       transformer_temporal_in_features=["res4", "res5"], num_clip_frames=2, cross_clip_training=False).eval()
+    p = synth.within_clip_module_params(seed, chans)
+    mod.load_state_dict(p, strict=True)
+    feats = {f"res{5 - i}": synth.randn(seed + 100 + i, 2, chans[i], *sizes[i]) for i in range(3)}
+    out, _, _ = mod.forward_features(feats)
+    save("wc_module", seed=seed, chans=chans, sizes=torch.tensor(sizes), res5=out["res5"], res4=out["res4"], res3=out["res3"], wsum=synth.checksum(p))
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found; golden fixtures can only be generated where it is mounted")

@@ -518,6 +518,41 @@ def within_clip_encoder(src: Tensor, spatial_shapes, pos: Tensor, pos_3d: List[T
     return out
 
 
+def pos2d_table(H: int, W: int, num_pos_feats: int = 128, temperature: float = 10000.0) -> Tensor:
+    """PositionEmbeddingSine(normalize=True) without mask -- WC/pos_embeddings.py:30-53 -> [H*W, 2*num_pos_feats] (pos_y | pos_x)."""
+    scale = 2 * math.pi
+    y = torch.arange(1, H + 1, dtype=torch.float32) / (H + 1e-6) * scale
+    x = torch.arange(1, W + 1, dtype=torch.float32) / (W + 1e-6) * scale
+    i = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(i, 2, rounding_mode="trunc") / num_pos_feats)
+
+    def enc(v):
+        a = v[:, None] / dim_t
+        return torch.stack((a[:, 0::2].sin(), a[:, 1::2].cos()), dim=2).flatten(1)
+
+    py, px = enc(y), enc(x)
+    return torch.cat((py[:, None, :].expand(H, W, -1), px[None, :, :].expand(H, W, -1)), -1).reshape(H * W, 2 * num_pos_feats)
+
+
+def within_clip_module(features: List[Tensor], p: Params, B: int, T: int, num_stages: int = 2, num_temporal_levels: int = 2) -> List[Tensor]:
+    """MSDeformAttnPixelDecoder.forward_features -- ENC:404-435 with MSDeformAttnTransformerEncoderOnly.forward ENC:91-125.
+    `features` top-down (res5, res4, res3), each [B*T, C_l, H_l, W_l]; returns the output-projected maps in the same order."""
+    shapes = [(int(f.shape[2]), int(f.shape[3])) for f in features]
+    toks = [input_proj(f, _sub(p, f"input_proj.{i}")) for i, f in enumerate(features)]
+    pos = torch.cat([pos2d_table(h, w) + p["transformer.level_embed_2d"][i] for i, (h, w) in enumerate(shapes)], 0)
+    pos = pos[None].expand(B * T, -1, -1)
+    pos3d = [level_pos3d(B, T, h, w, p["transformer.level_embed_3d"][i]) for i, (h, w) in enumerate(shapes[:num_temporal_levels])]
+    enc = _sub(p, "transformer.encoder")
+    spatial = [_sub(enc, f"spatial_layers.{i}") for i in range(num_stages)]
+    temporal = [split_encoder_params(_sub(enc, f"temporal_layers.{i}")) for i in range(num_stages)]
+    y = within_clip_encoder(torch.cat(toks, 1), shapes, pos, pos3d, spatial, temporal, num_temporal_levels)
+    outs, start = [], 0
+    for i, (h, w) in enumerate(shapes):
+        outs.append(output_proj(y[:, start:start + h * w], _sub(p, f"output_proj.{i}"), h, w))
+        start += h * w
+    return outs
+
+
 def flops_trajectory_attention(Bp: int, N: int, F: int, C: int = 256) -> int:
     return Bp * N * C * (10 * C + 4 * F * C + 4 * N + 4 * F)
 

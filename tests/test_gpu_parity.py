@@ -704,3 +704,52 @@ def test_within_clip_encoder_golden(golden):
                         torch.zeros(B * T, Len, dtype=torch.bool, device="cuda"), [p.cuda() for p in pos3d])
     assert h is None and w is None
     assert nerr(out, torch.as_tensor(gz["out"])) < 1.5e-2        # four chained bf16 layers
+
+
+class _Shape:
+    def __init__(self, channels, stride):
+        self.channels, self.stride = channels, stride
+
+
+def _wc_module(chans):
+    from axial_vs_b200 import within_clip
+    shape = {"res2": _Shape(64, 4), "res3": _Shape(chans[2], 8), "res4": _Shape(chans[1], 16), "res5": _Shape(chans[0], 32)}
+    return within_clip.WithinClipTrackingModule(
+        shape, transformer_dropout=0.0, transformer_attn_drop=0.0, transformer_nheads=8, transformer_dim_feedforward=1024,
+        transformer_num_stages=2, transformer_spatial_layers=2, transformer_temporal_layers=2,
+        transformer_temporal_attn_type="axial-trajectory", conv_dims=256, transformer_spatial_in_features=["res3", "res4", "res5"],
+        transformer_temporal_in_features=["res4", "res5"], num_clip_frames=2, cross_clip_training=False).eval()
+
+
+def test_within_clip_module_golden(golden):
+    """The whole within-clip tracking module as a drop-in for MSDeformAttnPixelDecoder: the reference's state dict loads with
+    strict=True and forward_features reproduces its CPU output (projections, positional terms, 2 x [spatial + temporal layers])."""
+    gz = golden("wc_module")
+    seed, chans = int(gz["seed"]), [int(c) for c in gz["chans"]]
+    sizes = [tuple(int(v) for v in r) for r in gz["sizes"]]
+    m = _wc_module(chans)
+    m.load_state_dict(synth.within_clip_module_params(seed, chans), strict=True)
+    m.cuda()
+    feats = {f"res{5 - i}": synth.randn(seed + 100 + i, 2, chans[i], *sizes[i]).cuda() for i in range(3)}
+    out, h, w = m.forward_features(feats)
+    assert h is None and w is None
+    for name in ("res5", "res4", "res3"):
+        want = torch.as_tensor(gz[name])
+        assert out[name].shape == want.shape
+        assert nerr(out[name], want) < 2e-2, name           # six chained bf16 stages, GroupNorm-normalised output
+
+
+def test_within_clip_module_r50_shapes(O):
+    """BASELINE configs[1] pyramid for one clip (T=2): res5 2048 x 21^2, res4 1024 x 41^2, res3 512 x 81^2, against the oracle."""
+    chans, sizes, seed = [2048, 1024, 512], [(21, 21), (41, 41), (81, 81)], 123
+    p = synth.within_clip_module_params(seed, chans)
+    m = _wc_module(chans)
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    feats = [synth.randn(seed + 1 + i, 2, chans[i], *sizes[i]) for i in range(3)]
+    want = O.within_clip_module(feats, p, 1, 2)
+    out, _, _ = m.forward_features({f"res{5 - i}": feats[i].cuda() for i in range(3)})
+    for i, name in enumerate(("res5", "res4", "res3")):
+        e = nerr(out[name], want[i])
+        cos = torch.nn.functional.cosine_similarity(out[name].cpu().flatten(), want[i].flatten(), dim=0).item()
+        assert e < 3e-2 and cos > 0.999, (name, e, cos)

@@ -163,3 +163,17 @@ def test_within_clip_encoder(golden):
     temporal = [O.split_encoder_params(ts) for ts in temporal_states]
     out = O.within_clip_encoder(src, shapes, pos, pos3d, spatial, temporal, 2)
     _close(out, gz["out"], atol=5e-5)
+
+
+def test_within_clip_module(golden):
+    """The whole within-clip tracking module (MSDeformAttnPixelDecoder.forward_features of the reference, CPU): projections, 2-D and
+    3-D positional terms, two stages of spatial + temporal layers, output projections."""
+    gz = golden("wc_module")
+    seed, chans = int(gz["seed"]), [int(c) for c in gz["chans"]]
+    sizes = [tuple(int(v) for v in r) for r in gz["sizes"]]
+    p = synth.within_clip_module_params(seed, chans)
+    assert synth.checksum(p) == pytest.approx(float(gz["wsum"]), rel=1e-12)
+    feats = [synth.randn(seed + 100 + i, 2, chans[i], *sizes[i]) for i in range(3)]
+    outs = O.within_clip_module(feats, p, 1, 2)
+    for o, name in zip(outs, ("res5", "res4", "res3")):
+        _close(o, gz[name], atol=2e-4)
