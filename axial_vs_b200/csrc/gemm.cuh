@@ -245,6 +245,77 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
     constexpr int PT = GEMM_APROD_WARPS * 32;
     constexpr int ITERS = GEMM_BM * 8 / PT;                     // 16-byte chunks per thread per K-block
     uint32_t stage = 0, phase = 0;
+    if (p.a_diag >= 3) {
+      // fp32 sources, loads software-pipelined over two register sets ACROSS K-blocks and tiles: work item it = (this CTA's tile
+      // it / num_kb, K-block it % num_kb); item it+1 is in flight while item it is converted and stored, so the short K loops of
+      // the 256-channel projections never drain the pipeline at a tile boundary.
+      // Mode 3 (NCHW): q = i * PT + ptid -> pixel row q & 127, 16-byte chunk (8 channels) q >> 7: a warp's 32 lanes read 32
+      // consecutive pixels of one channel per instruction.  Mode 4: row q >> 3, chunk q & 7 as for bf16 sources.
+      float fa[ITERS][8], fb[ITERS][8];
+      auto load = [&](int it, float (&f)[ITERS][8]) {
+        const int tile = blockIdx.x + (it / num_kb) * gridDim.x, kb = it % num_kb;
+        const int mt = tile / n_chunks;
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i) {
+          const int q = i * PT + ptid;
+          if (p.a_diag == 3) {
+            const int r = mt * GEMM_BM + (q & 127);
+            if (r < p.M) {
+              const int img = r / p.a_n;
+              const float* s = p.A32 + ((size_t)img * p.K + kb * GEMM_BK + (q >> 7) * 8) * p.a_n + (r - img * p.a_n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[i][j] = __ldg(s + (size_t)j * p.a_n);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
+            }
+          } else {
+            const int r = mt * GEMM_BM + (q >> 3);
+            if (r < p.M) {
+              const size_t o = (size_t)r * p.lda + kb * GEMM_BK + (q & 7) * 8;
+              const float4* s = reinterpret_cast<const float4*>(p.A32 + o);
+              float4 a = __ldg(s), b = __ldg(s + 1);
+              if (p.A32b) {
+                const size_t o2 = p.a32b_rows > 0 ? (size_t)(r % p.a32b_rows) * p.lda + kb * GEMM_BK + (q & 7) * 8 : o;
+                const float4* s2 = reinterpret_cast<const float4*>(p.A32b + o2);
+                const float4 a2 = __ldg(s2), b2 = __ldg(s2 + 1);
+                a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w; b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+              }
+              f[i][0] = a.x; f[i][1] = a.y; f[i][2] = a.z; f[i][3] = a.w; f[i][4] = b.x; f[i][5] = b.y; f[i][6] = b.z; f[i][7] = b.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
+            }
+          }
+        }
+      };
+      auto store = [&](const float (&f)[ITERS][8]) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* dst = smem + stage * GEMM_STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i) {
+          const int q = i * PT + ptid;
+          const uint32_t off = (p.a_diag == 3) ? sw128_offset(q & 127, q >> 7) : sw128_offset(q >> 3, q & 7);
+          *reinterpret_cast<uint4*>(dst + off) = make_uint4(pack_bf16x2(f[i][0], f[i][1]), pack_bf16x2(f[i][2], f[i][3]),
+                                                            pack_bf16x2(f[i][4], f[i][5]), pack_bf16x2(f[i][6], f[i][7]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[stage]);
+        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+      };
+      const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const int n_items = my_tiles * num_kb;
+      if (n_items > 0) load(0, fa);
+      for (int it = 0; it < n_items; it += 2) {
+        if (it + 1 < n_items) load(it + 1, fb);
+        store(fa);
+        if (it + 1 < n_items) {
+          if (it + 2 < n_items) load(it + 2, fa);
+          store(fb);
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / n_chunks;
       // source row pointers are K-block independent
@@ -262,72 +333,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
         } else {
           rowp[i] = nullptr;
         }
-      }
-      if (p.a_diag >= 3) {
-        // fp32 sources, loads software-pipelined over two register sets (K-block kb+1 in flight while kb is converted and stored).
-        // Mode 3 (NCHW): q = i * PT + ptid -> pixel row q & 127, 16-byte chunk (8 channels) q >> 7: a warp's 32 lanes read 32
-        // consecutive pixels of one channel per instruction.  Mode 4: row q >> 3, chunk q & 7 as for bf16 sources.
-        float fa[ITERS][8], fb[ITERS][8];
-        auto load = [&](int kb, float (&f)[ITERS][8]) {
-#pragma unroll
-          for (int i = 0; i < ITERS; ++i) {
-            const int q = i * PT + ptid;
-            if (p.a_diag == 3) {
-              const int r = mt * GEMM_BM + (q & 127);
-              if (r < p.M) {
-                const int img = r / p.a_n;
-                const float* s = p.A32 + ((size_t)img * p.K + kb * GEMM_BK + (q >> 7) * 8) * p.a_n + (r - img * p.a_n);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[i][j] = __ldg(s + (size_t)j * p.a_n);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
-              }
-            } else {
-              const int r = mt * GEMM_BM + (q >> 3);
-              if (r < p.M) {
-                const size_t o = (size_t)r * p.lda + kb * GEMM_BK + (q & 7) * 8;
-                const float4* s = reinterpret_cast<const float4*>(p.A32 + o);
-                float4 a = __ldg(s), b = __ldg(s + 1);
-                if (p.A32b) {
-                  const size_t o2 = p.a32b_rows > 0 ? (size_t)(r % p.a32b_rows) * p.lda + kb * GEMM_BK + (q & 7) * 8 : o;
-                  const float4* s2 = reinterpret_cast<const float4*>(p.A32b + o2);
-                  const float4 a2 = __ldg(s2), b2 = __ldg(s2 + 1);
-                  a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w; b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
-                }
-                f[i][0] = a.x; f[i][1] = a.y; f[i][2] = a.z; f[i][3] = a.w; f[i][4] = b.x; f[i][5] = b.y; f[i][6] = b.z; f[i][7] = b.w;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
-              }
-            }
-          }
-        };
-        auto store = [&](const float (&f)[ITERS][8]) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* dst = smem + stage * GEMM_STAGE_BYTES;
-#pragma unroll
-          for (int i = 0; i < ITERS; ++i) {
-            const int q = i * PT + ptid;
-            const uint32_t off = (p.a_diag == 3) ? sw128_offset(q & 127, q >> 7) : sw128_offset(q >> 3, q & 7);
-            *reinterpret_cast<uint4*>(dst + off) = make_uint4(pack_bf16x2(f[i][0], f[i][1]), pack_bf16x2(f[i][2], f[i][3]),
-                                                              pack_bf16x2(f[i][4], f[i][5]), pack_bf16x2(f[i][6], f[i][7]));
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full_bar[stage]);
-          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
-        };
-        load(0, fa);
-        for (int kb = 0; kb < num_kb; kb += 2) {                 // K is a multiple of 64; an odd K-block count ends in the first half
-          if (kb + 1 < num_kb) load(kb + 1, fb);
-          store(fa);
-          if (kb + 1 < num_kb) {
-            if (kb + 2 < num_kb) load(kb + 2, fa);
-            store(fb);
-          }
-        }
-        continue;
       }
       for (int kb = 0; kb < num_kb; ++kb) {
         uint4 v[ITERS];
