@@ -20,12 +20,12 @@ struct MsdaDims {
 // columns [0, 8*L*P*2) = sampling offsets ordered (head, level, point, xy), then 8*L*P attention logits (head, level, point);
 // ref fp32 [images*len, L, 2] normalised (x, y) reference points (ref_rows > 0: only that many rows, shared by every image);
 // out bf16 [images*len, 256].
-// 256 threads = 4 tokens x (8 heads x 8 four-channel groups): each thread gathers 4 channels with 8-byte loads.
+// 256 threads = 8 tokens x (8 heads x 4 eight-channel groups): one warp per token, each thread gathers 8 channels with 16-byte loads.
 __global__ void __launch_bounds__(256) msda_sample_kernel(const __nv_bfloat16* __restrict__ value, const float* __restrict__ oa, int ld_oa,
                                                           const float* __restrict__ ref, int ref_rows, __nv_bfloat16* __restrict__ out, int rows, MsdaDims d) {
-  const int token = blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int token = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (token >= rows) return;
-  const int lane64 = threadIdx.x & 63, head = lane64 >> 3, cg = lane64 & 7;
+  const int lane = threadIdx.x & 31, head = lane >> 2, cg = lane & 3;
   const int LP = d.L * d.P;
   const float* o_row = oa + (size_t)token * ld_oa;
   const float* lg = o_row + 8 * LP * 2 + head * LP;
@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(256) msda_sample_kernel(const __nv_bfloat16* _
   }
   const float inv = 1.f / den;
   const size_t img_row0 = (size_t)(token / d.len) * d.len;
-  const __nv_bfloat16* vbase = value + img_row0 * C256 + head * 32 + cg * 4;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const __nv_bfloat16* vbase = value + img_row0 * C256 + head * 32 + cg * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int l = 0; l < MSDA_MAX_LEVELS; ++l) {
     if (l >= d.L) break;
@@ -66,18 +66,22 @@ __global__ void __launch_bounds__(256) msda_sample_kernel(const __nv_bfloat16* _
         const int xi = x0 + (t & 1), yi = y0 + (t >> 1);
         if (xi >= 0 && xi < W && yi >= 0 && yi < H) {                      // zero padding outside the map
           const float wgt = a * ((t & 1) ? fx : 1.f - fx) * ((t >> 1) ? fy : 1.f - fy);
-          const uint2 u = __ldg(reinterpret_cast<const uint2*>(vl + (size_t)(yi * W + xi) * C256));
-          const float2 v0 = unpack_bf16x2(u.x), v1 = unpack_bf16x2(u.y);
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(vl + (size_t)(yi * W + xi) * C256));
+          const float2 v0 = unpack_bf16x2(u.x), v1 = unpack_bf16x2(u.y), v2 = unpack_bf16x2(u.z), v3 = unpack_bf16x2(u.w);
           acc[0] = fmaf(wgt, v0.x, acc[0]); acc[1] = fmaf(wgt, v0.y, acc[1]);
           acc[2] = fmaf(wgt, v1.x, acc[2]); acc[3] = fmaf(wgt, v1.y, acc[3]);
+          acc[4] = fmaf(wgt, v2.x, acc[4]); acc[5] = fmaf(wgt, v2.y, acc[5]);
+          acc[6] = fmaf(wgt, v3.x, acc[6]); acc[7] = fmaf(wgt, v3.y, acc[7]);
         }
       }
     }
   }
-  uint2 o;
+  uint4 o;
   o.x = pack_bf16x2(acc[0], acc[1]);
   o.y = pack_bf16x2(acc[2], acc[3]);
-  *reinterpret_cast<uint2*>(out + (size_t)token * C256 + head * 32 + cg * 4) = o;
+  o.z = pack_bf16x2(acc[4], acc[5]);
+  o.w = pack_bf16x2(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(out + (size_t)token * C256 + head * 32 + cg * 8) = o;
 }
 
 }  // namespace axvs
