@@ -53,7 +53,7 @@ SIGNATURES = {
                             c_int, c_int, c_void_p, c_void_p]),
     "axvs_spatial_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "axvs_traj_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "axvs_traj_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(TaWeights), c_int, c_int, c_int,
+    "axvs_traj_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, POINTER(TaWeights), c_int, c_int, c_int,
                                    c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "axvs_traj_attn_maps": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(TaWeights), c_int, c_int, c_int, c_int, c_int,
                                     c_void_p, c_size_t, c_void_p]),
@@ -61,7 +61,7 @@ SIGNATURES = {
     "axvs_ffn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "axvs_ln_ffn_fwd": (c_int, [c_void_p, c_void_p, POINTER(LayerWeights), c_int, c_void_p, c_size_t, c_void_p]),
     "axvs_layer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
-    "axvs_axial_layer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(LayerWeights), c_int, c_int, c_int, c_int,
+    "axvs_axial_layer_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, POINTER(LayerWeights), c_int, c_int, c_int, c_int,
                                      c_int, c_void_p, c_size_t, c_void_p]),
     "axvs_cast_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "axvs_cc_aspp_workspace_bytes": (c_size_t, [c_int]),

@@ -204,7 +204,7 @@ GemmParams gemm_params(const void* A, int lda, int M, int K, const void* Wp, int
   p.out = out; p.ldo = ldo; p.out_col0 = out_col0; p.out_bf16 = out_bf16;
   p.resid = resid;
   p.map_mode = MAP_NONE;
-  p.dims = AxialDims{1, 1, 1, 1};
+  p.dims = make_dims(1, 1, 1, 1);
   return p;
 }
 
@@ -274,7 +274,7 @@ int blocks_for(long long work_items, int per_block, int sms) {
 
 extern "C" {
 
-int axvs_version(void) { return 110; }
+int axvs_version(void) { return 111; }
 int axvs_set_pair_mode(int on) {
   const int prev = g_pair;
   g_pair = on ? 1 : 0;
@@ -353,7 +353,7 @@ size_t axvs_traj_attn_workspace_bytes(int B, int T, int H, int W) {
 namespace {
 // ln_g/ln_b/ln_img != null: the output epilogue additionally applies LayerNorm (norm1 of the layer) and emits the FFN's
 // bf16 tile image; only available on the fully fused path (returns AXVS_E_UNSUPPORTED otherwise).
-int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, const float* pos, const float* resid, float* out,
+int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, const float* pos, int pos_clips, const float* resid, float* out,
                    const axvs_ta_weights* w, int B, int T, int H, int W, int axis, void* workspace, size_t workspace_bytes,
                    axvs_stream_t stream, const float* ln_g, const float* ln_b, uint8_t* ln_img) {
   if (!q_in || !k_in || !v_in || !out || !w || !workspace) return fail(AXVS_E_INVALID, "traj_attn: null pointer");
@@ -374,7 +374,8 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
   rc = device_info(&d);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const AxialDims dims{B, T, H, W};
+  if (pos && pos_clips != B && pos_clips != 1) return fail(AXVS_E_INVALID, "traj_attn: pos must cover every clip or exactly one (pos_clips = %d, B = %d)", pos_clips, B);
+  const AxialDims dims = make_dims(B, T, H, W, pos && pos_clips == 1 && B > 1);
   const int map = axis;   // AXVS_AXIS_* == RowMap values
   const int pk_blocks = blocks_for((long long)rows, 8, d->sms);
 
@@ -411,7 +412,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       qp.w = reinterpret_cast<const uint8_t*>(w->w_qkv_u); qp.bias = w->b_qkv;
       qp.qkv = ws.qkv; qp.rows = (int)rows; qp.tiles = tiles; qp.map_mode = map; qp.dims = dims;
       {
-        ProfScope ps(KC_QKVD, 2.0 * rows * 256.0 * 768.0, (double)rows * ((pos ? 2048.0 : 1024.0) + 1536.0), st);
+        ProfScope ps(KC_QKVD, 2.0 * rows * 256.0 * 768.0, (double)rows * ((pos ? (dims.pos_mod ? 1024.0 + 1024.0 / B : 2048.0) : 1024.0) + 1536.0), st);
         qkv_direct_kernel<<<tiles < d->sms ? tiles : d->sms, QD_THREADS, QD_SMEM_BYTES, st>>>(qp);
       }
       AXVS_CHECK_LAUNCH("qkv_direct_kernel");
@@ -638,10 +639,10 @@ int ffn_fused_launch(const uint8_t* s_img, const float* s32, float* out, const a
 
 extern "C" {
 
-int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, const float* pos, const float* resid, float* out,
+int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, const float* pos, int pos_clips, const float* resid, float* out,
                        const axvs_ta_weights* w, int B, int T, int H, int W, int axis, void* workspace, size_t workspace_bytes,
                        axvs_stream_t stream) {
-  return traj_attn_impl(q_in, k_in, v_in, pos, resid, out, w, B, T, H, W, axis, workspace, workspace_bytes, stream, nullptr, nullptr, nullptr);
+  return traj_attn_impl(q_in, k_in, v_in, pos, pos_clips, resid, out, w, B, T, H, W, axis, workspace, workspace_bytes, stream, nullptr, nullptr, nullptr);
 }
 
 int axvs_traj_attn_maps(const float* q_in, const float* k_in, const float* pos, float* maps, const axvs_ta_weights* w, int B, int T, int H,
@@ -664,7 +665,7 @@ int axvs_traj_attn_maps(const float* q_in, const float* k_in, const float* pos, 
   DeviceInfo* d;
   if ((rc = device_info(&d))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const AxialDims dims{B, T, H, W};
+  const AxialDims dims = make_dims(B, T, H, W);
   const int tiles = (int)((rows + 127) / 128);
   pack_image_kernel<<<blocks_for((long long)rows, 8, d->sms), 256, 0, st>>>(q_in, pos, ws.a1_img, nullptr, (int)rows, axis, dims);
   AXVS_CHECK_LAUNCH("pack_image_kernel");
@@ -736,7 +737,7 @@ size_t axvs_layer_workspace_bytes(int B, int T, int H, int W, int d_ffn) {
   return 2 * align256(rows * 256 * 4) + align256(((rows + 127) / 128) * 4 * (size_t)TF_KB) + (ta > ffn ? ta : ffn);
 }
 
-int axvs_axial_layer_fwd(const float* src, const float* pos, float* out, const axvs_layer_weights* w, int B, int T, int H, int W,
+int axvs_axial_layer_fwd(const float* src, const float* pos, int pos_clips, float* out, const axvs_layer_weights* w, int B, int T, int H, int W,
                          int axial, void* workspace, size_t workspace_bytes, axvs_stream_t stream) {
   if (!src || !pos || !out || !w || !workspace) return fail(AXVS_E_INVALID, "axial_layer: null pointer");
   int rc = check_dims(B, T, H, W);
@@ -760,11 +761,11 @@ int axvs_axial_layer_fwd(const float* src, const float* pos, float* out, const a
   uint8_t* li = fuse_ln ? ln_img : nullptr;
   if (axial) {
     // S1 = S0 + TA_h(S0 + P, S0 + P, S0);  S2 = S1 + TA_w(S1 + P, S1 + P, S1)      WC/temporal_attention.py:197-213
-    if ((rc = traj_attn_impl(src, src, src, pos, src, s1, &w->attn_h, B, T, H, W, AXVS_AXIS_H, sub, sub_bytes, stream, nullptr, nullptr, nullptr))) return rc;
-    if ((rc = traj_attn_impl(s1, s1, s1, pos, s1, s2, &w->attn_w, B, T, H, W, AXVS_AXIS_W, sub, sub_bytes, stream, lg, lb, li))) return rc;
+    if ((rc = traj_attn_impl(src, src, src, pos, pos_clips, src, s1, &w->attn_h, B, T, H, W, AXVS_AXIS_H, sub, sub_bytes, stream, nullptr, nullptr, nullptr))) return rc;
+    if ((rc = traj_attn_impl(s1, s1, s1, pos, pos_clips, s1, s2, &w->attn_w, B, T, H, W, AXVS_AXIS_W, sub, sub_bytes, stream, lg, lb, li))) return rc;
   } else {
     // non-axial: one attention over all T*H*W tokens of a clip                       WC/temporal_attention.py:141-150
-    if ((rc = traj_attn_impl(src, src, src, pos, src, s2, &w->attn_h, B, T, H, W, AXVS_AXIS_NONE, sub, sub_bytes, stream, lg, lb, li))) return rc;
+    if ((rc = traj_attn_impl(src, src, src, pos, pos_clips, src, s2, &w->attn_h, B, T, H, W, AXVS_AXIS_NONE, sub, sub_bytes, stream, lg, lb, li))) return rc;
   }
   if (fuse_ln) return ffn_fused_launch(ln_img, s2, out, w, (int)rows, (cudaStream_t)stream);   // s2 already holds LN1(S2)
   return axvs_ln_ffn_fwd(s2, out, w, (int)rows, sub, sub_bytes, stream);
@@ -779,7 +780,7 @@ int axvs_cast_bf16(const float* x, void* out_bf16, int rows, axvs_stream_t strea
   {
     ProfScope ps(KC_PACK, 0, (double)rows * 256 * 6.0, (cudaStream_t)stream);
     pack_kq_kernel<<<blocks_for(rows, 8, d->sms), 256, 0, (cudaStream_t)stream>>>(x, nullptr, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, rows, MAP_NONE,
-                                                                                 AxialDims{1, 1, 1, 1});
+                                                                                 make_dims(1, 1, 1, 1));
   }
   AXVS_CHECK_LAUNCH("pack_kq_kernel(cast)");
   return AXVS_OK;

@@ -28,7 +28,25 @@ enum RowMap : int { MAP_NONE = 0, MAP_HPASS = 1, MAP_WPASS = 2 };
 
 struct AxialDims {
   int B, T, H, W;
+  uint32_t pos_mod;     // != 0: the positional table covers ONE clip ([T, H, W, 256], pos_mod = T*H*W rows) and is shared by all B clips
+  uint32_t pos_magic;   // floor(2^32 / pos_mod)
 };
+
+__host__ __forceinline__ AxialDims make_dims(int B, int T, int H, int W, bool shared_pos = false) {
+  AxialDims d{B, T, H, W, 0u, 0u};
+  if (shared_pos) {
+    d.pos_mod = (uint32_t)T * H * W;
+    d.pos_magic = (uint32_t)(0x100000000ull / d.pos_mod);
+  }
+  return d;
+}
+
+// canonical token -> row of the positional table (c mod pos_mod by a reciprocal multiply: the estimate is low by at most one)
+__device__ __forceinline__ uint32_t pos_row(uint32_t c, const AxialDims& d) {
+  if (!d.pos_mod) return c;
+  const uint32_t r = c - __umulhi(c, d.pos_magic) * d.pos_mod;
+  return r >= d.pos_mod ? r - d.pos_mod : r;
+}
 
 // pass-order row index -> canonical token index ((b*T + t)*H + h)*W + w
 __device__ __forceinline__ int pass_to_canonical(int p, int mode, const AxialDims& d) {

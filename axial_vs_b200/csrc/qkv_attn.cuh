@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(QA_THREADS, 1) qkv_attn_kernel(const QkvAttnPa
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t c = cr[4 * hf + j];
-          q[j] = c != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)c * C256 + kb * 64) + c16) : z;
+          q[j] = c != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)pos_row(c, p.dims) * C256 + kb * 64) + c16) : z;
         }
       } else {
 #pragma unroll

@@ -24,7 +24,7 @@ __global__ void pack_kq_kernel(const float* __restrict__ src, const float* __res
       reinterpret_cast<uint4*>(a2 + (size_t)p * C256)[lane] = u;
     }
     if (pos) {
-      const float4* p4 = reinterpret_cast<const float4*>(pos + c * C256) + lane * 2;
+      const float4* p4 = reinterpret_cast<const float4*>(pos + (size_t)pos_row((uint32_t)c, d) * C256) + lane * 2;
       float4 q0 = __ldg(p4), q1 = __ldg(p4 + 1);
       s0.x += q0.x; s0.y += q0.y; s0.z += q0.z; s0.w += q0.w;
       s1.x += q1.x; s1.y += q1.y; s1.z += q1.z; s1.w += q1.w;

@@ -121,7 +121,7 @@ class _LayerBase(nn.Module):
         _require_inference(self, src, pos)
         if src.numel() == 0:                      # empty batch of clips: nothing to launch (the reference returns an empty tensor too)
             return src.clone()
-        out = ops.axial_layer_fwd(src.contiguous().float(), pos.contiguous().float(), self.packed(src.device), self.axial)
+        out = ops.axial_layer_fwd(src.contiguous().float(), ops.shared_pos(pos).contiguous().float(), self.packed(src.device), self.axial)
         return out.to(src.dtype)
 
 

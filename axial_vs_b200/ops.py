@@ -212,9 +212,14 @@ def traj_attn_fwd(q_in: torch.Tensor, k_in: torch.Tensor, v_in: torch.Tensor, po
         _check(t, nm, torch.float32)
         if t.numel() != rows * C:
             raise RuntimeError(f"{nm} has {t.numel()} elements, expected {rows}x{C}")
+    pos_clips = 0
     if pos is not None:
         _check(pos, "pos", torch.float32)
-        if pos.numel() != rows * C:
+        if pos.numel() == rows * C:
+            pos_clips = B
+        elif pos.numel() == T * H * W * C:
+            pos_clips = 1                         # one table shared by all clips
+        else:
             raise RuntimeError("pos size mismatch")
     if resid is not None:
         _check(resid, "resid", torch.float32)
@@ -224,7 +229,7 @@ def traj_attn_fwd(q_in: torch.Tensor, k_in: torch.Tensor, v_in: torch.Tensor, po
     with torch.cuda.device(q_in.device):
         ws = workspace(nbytes, q_in.device)
         st = w.struct()
-        rc = lib.axvs_traj_attn_fwd(q_in.data_ptr(), k_in.data_ptr(), v_in.data_ptr(), _ptr(pos), _ptr(resid), out.data_ptr(),
+        rc = lib.axvs_traj_attn_fwd(q_in.data_ptr(), k_in.data_ptr(), v_in.data_ptr(), _ptr(pos), pos_clips, _ptr(resid), out.data_ptr(),
                                     ctypes.byref(st), B, T, H, W, axis, ws.data_ptr(), ws.numel(), _stream(q_in.device))
     _lib.check(rc, "axvs_traj_attn_fwd")
     return out
@@ -261,13 +266,29 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return y
 
 
+def shared_pos(pos: torch.Tensor) -> torch.Tensor:
+    """A positional tensor that is a stride-0 broadcast over the clip dim (`table.expand(B, ...)`) -> its single [1, ...] table."""
+    if pos.dim() >= 2 and pos.shape[0] > 1 and pos.stride(0) == 0:
+        return pos[:1]
+    return pos
+
+
 def axial_layer_fwd(src: torch.Tensor, pos: torch.Tensor, w: PackedLayer, axial: bool = True) -> torch.Tensor:
-    """Temporal(Axial)TrajectoryAttentionLayer.forward: src [(B T), (H W), 256], pos [B, T, H, W, 256] (fp32)."""
+    """Temporal(Axial)TrajectoryAttentionLayer.forward: src [(B T), (H W), 256], pos [B, T, H, W, 256] (fp32).
+
+    pos may also be [1, T, H, W, 256] (or a stride-0 `expand` of it, see `shared_pos`): the reference's 3-D sine table does not depend
+    on the clip index (WC/pos_embeddings.py:86-130), and the kernels then read the one table instead of B copies."""
     _check(src, "src", torch.float32)
+    pos = shared_pos(pos)
     _check(pos, "pos", torch.float32)
     if pos.dim() != 5 or pos.shape[-1] != C:
         raise RuntimeError(f"pos must be [B, T, H, W, {C}], got {tuple(pos.shape)}")
-    B, T, H, W, _ = pos.shape
+    pos_clips, T, H, W, _ = pos.shape
+    if T <= 0 or src.dim() != 3 or src.shape[0] % T:
+        raise RuntimeError(f"src must be [(B T), (H W), {C}] with T={T}, got {tuple(src.shape)}")
+    B = src.shape[0] // T
+    if pos_clips not in (1, B):
+        raise RuntimeError(f"pos covers {pos_clips} clips, expected {B} or 1 (shared table)")
     if tuple(src.shape) != (B * T, H * W, C):
         raise RuntimeError(f"src must be [(B T)={B * T}, (H W)={H * W}, {C}], got {tuple(src.shape)}")
     if src.device != pos.device:
@@ -278,7 +299,7 @@ def axial_layer_fwd(src: torch.Tensor, pos: torch.Tensor, w: PackedLayer, axial:
     with torch.cuda.device(src.device):
         ws = workspace(nbytes, src.device)
         st = w.struct()
-        rc = lib.axvs_axial_layer_fwd(src.data_ptr(), pos.data_ptr(), out.data_ptr(), ctypes.byref(st), B, T, H, W, int(axial),
+        rc = lib.axvs_axial_layer_fwd(src.data_ptr(), pos.data_ptr(), pos_clips, out.data_ptr(), ctypes.byref(st), B, T, H, W, int(axial),
                                       ws.data_ptr(), ws.numel(), _stream(src.device))
     _lib.check(rc, "axvs_axial_layer_fwd")
     return out

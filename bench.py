@@ -166,6 +166,7 @@ def workload_config(clips):
     return {"workload": "Video-kMaX R50 + MaXTron within-clip tracking hot path (BASELINE configs[1]): T=2, 641x641 -> "
                         "res5 21x21 + res4 41x41, C=256, 2 stages x TemporalEncoder(2 axial-trajectory layers)",
             "clips_per_gpu_per_step": clips, "gflop_per_clip": round(flops_per_clip() / 1e9, 2),
+            "pos": "one PositionEmbeddingSine3D table per level shared by all clips (the reference's table is clip-independent)",
             "l2": "per-step activations exceed the 126 MB L2 and two input sets alternate"}
 
 
@@ -180,6 +181,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="1 (default): replay each step's kernels from a CUDA graph (launch overhead removed); 0: eager launches")
     ap.add_argument("--clip-chunks", type=int, default=1, help="split each level's clips into this many groups, one CUDA stream per (level, group)")
+    ap.add_argument("--full-pos", type=int, default=0, help="1: materialise the positional table for every clip ([B,T,H,W,C], as the reference passes it) instead of sharing one table")
     ap.add_argument("--level-streams", type=int, default=1, help="1: run the two pyramid levels on two CUDA streams (default), 0: serially")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -209,7 +211,9 @@ def main():
         enc.load_state_dict(synth.encoder_params(s, LAYERS_PER_STAGE), strict=True)
         encoders.append(enc.to(dev))
     le = synth.level_embed(99).to(dev)
-    pos = [ops.pos3d(clips, T_FRAMES, H, W, le[i].contiguous(), dev) for i, (H, W) in enumerate(LEVELS)]
+    pos = [ops.pos3d(1, T_FRAMES, H, W, le[i].contiguous(), dev).expand(clips, -1, -1, -1, -1) for i, (H, W) in enumerate(LEVELS)]   # one table per level, shared by the clips (as PositionEmbeddingSine3D.table)
+    if args.full_pos:
+        pos = [p.contiguous() for p in pos]
     # two alternating input sets (device-resident for `value`, pinned host copies for `e2e`)
     host_in = [[torch.randn(clips * T_FRAMES, H * W, 256, generator=torch.Generator().manual_seed(1000 * k + 10 * rank + i)).pin_memory()
                 for i, (H, W) in enumerate(LEVELS)] for k in range(2)]

@@ -120,9 +120,12 @@ int axvs_spatial_attention(const void* qkv_bf16, void* x_bf16, int num_seq, int 
  * q_in = k_in = v_in = src (:200-202).  `axis` selects how canonical tokens form sequences:
  *   AXVS_AXIS_H: B*W sequences of T*H tokens, AXVS_AXIS_W: B*H sequences of T*W tokens,
  *   AXVS_AXIS_NONE: B sequences of T*(H*W) tokens in storage order (frames of n = H*W tokens).
- * pos and resid may be NULL (resid NULL = the bare nn.Module `TrajectoryAttention.forward`). */
+ * pos and resid may be NULL (resid NULL = the bare nn.Module `TrajectoryAttention.forward`).
+ * pos_clips = number of clips the pos tensor covers: B, or 1 when one [T, H, W, 256] table is shared by all clips (the reference's
+ * PositionEmbeddingSine3D output does not depend on the batch index, WC/pos_embeddings.py:86-130; the kernels then re-read the
+ * one table, which stays L2-resident, instead of streaming B copies from HBM). */
 size_t axvs_traj_attn_workspace_bytes(int B, int T, int H, int W);
-int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, const float* pos, const float* resid,
+int axvs_traj_attn_fwd(const float* q_in, const float* k_in, const float* v_in, const float* pos, int pos_clips, const float* resid,
                        float* out, const axvs_ta_weights* w, int B, int T, int H, int W, int axis,
                        void* workspace, size_t workspace_bytes, axvs_stream_t stream);
 
@@ -144,10 +147,10 @@ int axvs_ln_ffn_fwd(const float* x, float* out, const axvs_layer_weights* w, int
 /* ---- layers --------------------------------------------------------------------------------------------------- */
 
 /* TemporalAxialTrajectoryAttentionLayer.forward (WC/temporal_attention.py:187-220; TL copy :753-791):
- * src [(B T), (H W), 256], pos [B, T, H, W, 256] -> out (same shape as src).  axial = 0 runs the non-axial
+ * src [(B T), (H W), 256], pos [pos_clips, T, H, W, 256] (pos_clips = B or 1, see axvs_traj_attn_fwd) -> out (same shape as src).  axial = 0 runs the non-axial
  * TemporalTrajectoryAttentionLayer (:131-155) using attn_h only. */
 size_t axvs_layer_workspace_bytes(int B, int T, int H, int W, int d_ffn);
-int axvs_axial_layer_fwd(const float* src, const float* pos, float* out, const axvs_layer_weights* w,
+int axvs_axial_layer_fwd(const float* src, const float* pos, int pos_clips, float* out, const axvs_layer_weights* w,
                          int B, int T, int H, int W, int axial,
                          void* workspace, size_t workspace_bytes, axvs_stream_t stream);
 

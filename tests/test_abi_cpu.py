@@ -37,7 +37,7 @@ def test_argument_validation_without_gpu(lib):
     one = ctypes.c_void_p(16)
     assert lib.axvs_pack_weight(one, 7, 64, one, None) == -2           # n_out % 8
     assert lib.axvs_linear(one, 256, 10, 100, one, None, 256, 1.0, 0, one, 256, 1, None, None) == -2   # K % 64
-    assert lib.axvs_traj_attn_fwd(one, one, one, None, None, one, None, 1, 2, 3, 4, 1, one, 0, None) == -1
+    assert lib.axvs_traj_attn_fwd(one, one, one, None, 0, None, one, None, 1, 2, 3, 4, 1, one, 0, None) == -1
     assert lib.axvs_layer_workspace_bytes(1, 2, 41, 41, 1024) > 0
     assert lib.axvs_layer_workspace_bytes(0, 2, 41, 41, 1024) == 0
 

@@ -214,6 +214,31 @@ def test_direct_qkv_matches_packed_front_end(ops, B, T, H, W):
     assert torch.equal(outs[2], outs[1])
 
 
+@pytest.mark.parametrize("B,T,H,W", [(3, 2, 13, 29), (5, 2, 21, 21), (2, 3, 7, 40)])
+def test_shared_pos_table_is_bit_identical(ops, B, T, H, W):
+    """One [1,T,H,W,C] positional table shared by the clips (or its stride-0 expand, what PositionEmbeddingSine3D.table returns)
+    must give exactly the result of the materialised [B,T,H,W,C] tensor, at every fusion level."""
+    seed = 1300 + B + T + H + W
+    p = synth.axial_layer_params(seed)
+    src = synth.randn(seed + 1, B * T, H * W, 256).cuda()
+    one = synth.randn(seed + 2, 1, T, H, W, 256).cuda()
+    full = one.expand(B, -1, -1, -1, -1).contiguous()
+    layer = _layer(p)
+    try:
+        for level in (0, 2, 3, 4, 5):
+            ops.set_fusion(level)
+            with torch.no_grad():
+                ref = layer(src, full)[0]
+                a = layer(src, one)[0]
+                b = layer(src, one.expand(B, -1, -1, -1, -1))[0]
+            torch.cuda.synchronize()
+            assert torch.equal(a, ref) and torch.equal(b, ref), f"fusion level {level}"
+    finally:
+        ops.set_fusion(ops.DEFAULT_FUSION)
+    with pytest.raises(RuntimeError):
+        layer(src, full[:2].contiguous()) if B > 2 else layer(src, torch.cat([full, full]).contiguous())
+
+
 def test_encoder_config1_two_layers(O):
     """BASELINE config 1: TemporalEncoder(axial-trajectory, 2 layers) on T=2, 41x41x256."""
     from axial_vs_b200 import modules
