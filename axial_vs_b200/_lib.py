@@ -76,6 +76,9 @@ SIGNATURES = {
     "axvs_msda_layer_workspace_bytes": (c_size_t, [c_int, c_int]),
     "axvs_msda_layer_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, POINTER(c_int), c_void_p, POINTER(MsdaWeights), c_int, c_int, c_void_p, c_size_t,
                                     c_void_p]),
+    "axvs_panoptic_workspace_bytes": (c_size_t, [c_int, ctypes.c_longlong]),
+    "axvs_panoptic_inference": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_float, c_float, c_float,
+                                        c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "axvs_mask_einsum": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "axvs_pos3d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "axvs_profile_enable": (c_int, [c_int]),

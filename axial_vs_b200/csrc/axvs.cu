@@ -20,6 +20,7 @@
 #include "decoder_attn.cuh"
 #include "proj.cuh"
 #include "msda.cuh"
+#include "panoptic.cuh"
 #include "ffn_pair.cuh"
 
 using namespace axvs;
@@ -37,12 +38,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels"};
 int g_fusion = 4;   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
 int g_pair = 0;   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
@@ -274,7 +275,7 @@ int blocks_for(long long work_items, int per_block, int sms) {
 
 extern "C" {
 
-int axvs_version(void) { return 111; }
+int axvs_version(void) { return 112; }
 int axvs_set_pair_mode(int on) {
   const int prev = g_pair;
   g_pair = on ? 1 : 0;
@@ -1029,6 +1030,86 @@ int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, cons
   lw.ln1_g = w->ln1_g; lw.ln1_b = w->ln1_b; lw.w_ffn1 = w->w_ffn1; lw.b_ffn1 = w->b_ffn1; lw.w_ffn2 = w->w_ffn2; lw.b_ffn2 = w->b_ffn2;
   lw.w_ffn1_u = w->w_ffn1_u; lw.w_ffn2_u = w->w_ffn2_u; lw.w_ffn1_n = w->w_ffn1_n; lw.ln2_g = w->ln2_g; lw.ln2_b = w->ln2_b; lw.d_ffn = w->d_ffn;
   return axvs_ln_ffn_fwd(y, out, &lw, rows, ffn_ws, workspace_bytes - (size_t)(ffn_ws - base), stream);
+}
+
+// ---------------------------------------------------------------------------------------------- panoptic post-processing (row f4)
+namespace {
+struct PanoWs { size_t cand, set_key, set_cnt, set_pos, set_dkey, set_dcnt, sum, ints, bytes; uint32_t cap; };
+PanoWs carve_pano(int N, long long P) {
+  PanoWs w;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += align256(n); return r; };
+  w.cap = 1024;
+  while ((long long)w.cap < 2 * P) w.cap <<= 1;          // open addressing never fills up: at most P distinct candidate sets
+  w.cand = take((size_t)P * 4);
+  w.set_key = take((size_t)w.cap * 4);
+  w.set_cnt = take((size_t)w.cap * 4);
+  w.set_pos = take((size_t)w.cap * 2);                    // at most P <= cap / 2 occupied entries
+  w.set_dkey = take((size_t)w.cap * 2);                   // at most P <= cap / 2 occupied entries
+  w.set_dcnt = take((size_t)w.cap * 2);
+  w.sum = take((size_t)N * 8);
+  w.ints = take((size_t)(8 * N + 8) * 4);                 // n_sets, count, single, order, rank, label, confident, final_id
+  w.bytes = o;
+  return w;
+}
+}  // namespace
+
+size_t axvs_panoptic_workspace_bytes(int N, long long P) {
+  if (N <= 0 || P <= 0) return 0;
+  return carve_pano(N, P).bytes;
+}
+
+int axvs_panoptic_inference(const float* mask_cls, const float* mask_pred, int N, int num_classes, long long P, const int* cat_ids,
+                            const int* is_thing, int label_divisor, float pixel_thr, float thing_thr, float stuff_thr, float overlap_thr,
+                            float w_cls, float w_mask, int* panoptic, int* segments, void* workspace, size_t workspace_bytes,
+                            axvs_stream_t stream) {
+  if (!mask_cls || !mask_pred || !cat_ids || !is_thing || !panoptic || !segments || !workspace) return fail(AXVS_E_INVALID, "panoptic: null pointer");
+  if (N <= 0 || num_classes <= 0 || P <= 0) return fail(AXVS_E_INVALID, "panoptic: sizes must be positive");
+  if (N > PANO_MAX_SLOTS) return fail(AXVS_E_UNSUPPORTED, "panoptic: at most %d mask slots (got %d)", PANO_MAX_SLOTS, N);
+  if (P > (1ll << 29)) return fail(AXVS_E_UNSUPPORTED, "panoptic: too many pixels (%lld)", P);
+  if (!(pixel_thr >= 1.0f / (PANO_CAND + 1))) return fail(AXVS_E_UNSUPPORTED, "panoptic: pixel_confidence_threshold must be >= %.2f (at most %d slots per pixel)", 1.0 / (PANO_CAND + 1), PANO_CAND);
+  const PanoWs w = carve_pano(N, P);
+  if (w.bytes > workspace_bytes) return fail(AXVS_E_WORKSPACE, "panoptic: workspace %zu < required %zu", workspace_bytes, w.bytes);
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  PanoParams p;
+  p.mask_cls = mask_cls; p.mask_pred = mask_pred; p.N = N; p.C1 = num_classes + 1; p.P = P;
+  p.cat_ids = cat_ids; p.is_thing = is_thing; p.label_divisor = label_divisor;
+  p.pixel_thr = pixel_thr; p.thing_thr = thing_thr; p.stuff_thr = stuff_thr; p.overlap_thr = overlap_thr; p.w_cls = w_cls; p.w_mask = w_mask;
+  p.out = panoptic; p.segments = segments;
+  p.cand = reinterpret_cast<uint32_t*>(base + w.cand);
+  p.set_key = reinterpret_cast<uint32_t*>(base + w.set_key);
+  p.set_cnt = reinterpret_cast<uint32_t*>(base + w.set_cnt);
+  p.set_pos = reinterpret_cast<uint32_t*>(base + w.set_pos);
+  p.set_dkey = reinterpret_cast<uint32_t*>(base + w.set_dkey);
+  p.set_dcnt = reinterpret_cast<uint32_t*>(base + w.set_dcnt);
+  p.set_cap = w.cap;
+  p.sum = reinterpret_cast<unsigned long long*>(base + w.sum);
+  int* ints = reinterpret_cast<int*>(base + w.ints);
+  p.n_sets = ints;
+  p.count = ints + 8;
+  p.single = p.count + N;
+  p.order = p.single + N;
+  p.rank = p.order + N;
+  p.label = p.rank + N;
+  p.confident = p.label + N;
+  p.final_id = p.confident + N;
+  const unsigned blocks = (unsigned)((P + 255) / 256);
+  {
+    ProfScope ps(KC_PANOPTIC, 0, (double)P * (N * 4.0 + 4 + 4 + 4), st);
+    cudaMemsetAsync(p.set_key, 0xFF, (size_t)w.cap * 4, st);
+    cudaMemsetAsync(p.set_cnt, 0, (size_t)w.cap * 4, st);
+    pano_zero_kernel<<<1, 256, 0, st>>>(p);
+    pano_pixel_kernel<<<blocks, 256, 0, st>>>(p);
+    pano_rank_kernel<<<1, 1024, 0, st>>>(p);
+    pano_greedy_kernel<<<1, PANO_GREEDY_THREADS, 0, st>>>(p);
+    pano_paint_kernel<<<blocks, 256, 0, st>>>(p);
+  }
+  AXVS_CHECK_LAUNCH("panoptic kernels");
+  return AXVS_OK;
 }
 
 int axvs_pos3d(float* out, const float* level_embed, int B, int T, int H, int W, axvs_stream_t stream) {

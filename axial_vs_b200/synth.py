@@ -183,3 +183,25 @@ def within_clip_module_params(seed: int, channels, num_stages: int = 2, temporal
         p.update({f"transformer.encoder.temporal_layers.{i}.{k}": v
                   for k, v in encoder_params(seed + 11 + i, temporal_layers_per_stage).items()})
     return p
+
+
+def panoptic_case(seed: int, N: int, C: int, T: int, H: int, W: int, cell: int = 4, emb: int = 128):
+    """Inputs of `panoptic_mask_inference` (Vk/maxtron_deeplab/maxtron_wc_model.py:439): class logits [N, C+1], mask logits
+    [N, T, H, W] made of piecewise-constant cells (so slots own coherent regions that overlap at their borders) plus pixel noise,
+    and mask embeddings [N, emb]."""
+    g = torch.Generator().manual_seed(seed)
+    mask_cls = torch.randn(N, C + 1, generator=g) * 3.0
+    mask_cls[:, -1] -= 2.0                                            # keep the void class from winning everywhere
+    hc, wc = (H + cell - 1) // cell, (W + cell - 1) // cell
+    coarse = torch.randn(N, T, hc, wc, generator=g) * 2.5
+    fine = coarse.repeat_interleave(cell, dim=2).repeat_interleave(cell, dim=3)[:, :, :H, :W]
+    mask_pred = (fine + torch.randn(N, T, H, W, generator=g) * 0.7).contiguous()
+    mask_embedding = torch.randn(N, emb, generator=g)
+    return mask_cls, mask_pred, mask_embedding
+
+
+def panoptic_metadata(C: int, label_divisor: int = 1000):
+    """A VIPSeg-like split: contiguous ids 0..C-1, every third class is a thing; dataset ids are the contiguous ids + 1."""
+    thing = {c + 1: c for c in range(C) if c % 3 == 0}
+    stuff = {c + 1: c for c in range(C) if c % 3 != 0}
+    return thing, stuff, label_divisor

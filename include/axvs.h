@@ -240,6 +240,23 @@ int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, cons
                         float* out, const axvs_msda_weights* w, int images, int len, void* workspace, size_t workspace_bytes,
                         axvs_stream_t stream);
 
+/* ---- post-path tail ------------------------------------------------------------------------------ */
+
+/* MaXTronWCDeepLab.panoptic_mask_inference (Vk/maxtron_deeplab/maxtron_wc_model.py:439-553; identical copy in maxtron_cc_model.py:460-574),
+ * the mask-wise panoptic merge, without the reference's per-slot host round trips:
+ *   mask_cls  fp32 [N, num_classes + 1] class logits (void class last), mask_pred fp32 [N, P] mask logits (P = T*H*W pixels),
+ *   cat_ids   int32 [num_classes]: label -> category id (the reference's id_cont_to_ids_dic, :469-473),
+ *   is_thing  int32 [num_classes]: label in thing ids (:489),
+ *   panoptic  int32 [P]: panoptic_seg_mask (category * label_divisor + instance for things, category for stuff, -1 unassigned),
+ *   segments  int32 [1 + 4 N]: number of opened segments, then (slot, label, is_thing, id) per segment in acceptance order
+ *             (segments_info / dic_tmp of the reference; the caller gathers the thing slots' embeddings from it).
+ * All device pointers.  N <= 255, pixel_thr >= 0.2 (at most four slots can exceed it at one pixel). */
+size_t axvs_panoptic_workspace_bytes(int N, long long P);
+int axvs_panoptic_inference(const float* mask_cls, const float* mask_pred, int N, int num_classes, long long P,
+                            const int* cat_ids, const int* is_thing, int label_divisor,
+                            float pixel_thr, float thing_thr, float stuff_thr, float overlap_thr, float w_cls, float w_mask,
+                            int* panoptic, int* segments, void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+
 /* PositionEmbeddingSine3D(num_pos_feats=128, normalize=True) + level_embed_3d[lvl], channels-last
  * (WC/pos_embeddings.py:86-130, WC/msdeformattn.py:112-115).  out fp32 [B,T,H,W,256]; level_embed may be NULL. */
 int axvs_pos3d(float* out, const float* level_embed, int B, int T, int H, int W, axvs_stream_t stream);

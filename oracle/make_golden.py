@@ -217,9 +217,35 @@ def main():
     feats = {f"res{5 - i}": synth.randn(seed + 100 + i, 2, chans[i], *sizes[i]) for i in range(3)}
     out, _, _ = mod.forward_features(feats)
     save("wc_module", seed=seed, chans=chans, sizes=torch.tensor(sizes), res5=out["res5"], res4=out["res4"], res3=out["res3"], wsum=synth.checksum(p))
+    panoptic_goldens()
+
+
+@torch.no_grad()
+def panoptic_goldens():
+    # ---- 10. mask-wise panoptic post-processing (row f4): the unmodified MaXTronWCDeepLab.panoptic_mask_inference
+    import types
+    from oracle import panoptic_oracle as PO
+    WCMODEL = ref_loader.wc_model().MaXTronWCDeepLab
+    for tag, (seed, N, C, T, H, W, thr) in {"a": (11, 16, 6, 2, 12, 10, 0.3), "b": (12, 128, 124, 2, 33, 41, 0.3), "c": (13, 32, 19, 3, 20, 17, 0.4)}.items():
+        thing, stuff, div = synth.panoptic_metadata(C)
+        md = types.SimpleNamespace(thing_dataset_id_to_contiguous_id=thing, stuff_dataset_id_to_contiguous_id=stuff, label_divisor=div)
+        ns = types.SimpleNamespace(class_threshold_thing=0.1, class_threshold_stuff=0.3, pixel_confidence_threshold=thr, overlap_threshold=0.8,
+                                   reorder_class_weight=1.0, reorder_mask_weight=1.0, metadata=md)
+        mc, mp, me = synth.panoptic_case(seed, N, C, T, H, W)
+        seg, dic = WCMODEL.panoptic_mask_inference(ns, mc, mp, me)
+        cats = sorted(dic.keys())
+        embs = torch.cat([torch.stack(dic[c]) for c in cats]) if cats else torch.zeros(0, me.shape[1])
+        mg = PO.margins(mc.numpy(), mp.numpy(), PO.Metadata(thing, stuff, div), thr, 0.1, 0.3)
+        print(f"  panoptic_{tag}: {len(seg.unique())} ids, margins {mg}")
+        save(f"panoptic_{tag}", seed=seed, N=N, C=C, T=T, H=H, W=W, thr=thr, seg=seg, cats=torch.tensor(cats, dtype=torch.int64),
+             counts=torch.tensor([len(dic[c]) for c in cats], dtype=torch.int64), embs=embs)
+
 
 
 if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found; golden fixtures can only be generated where it is mounted")
-    main()
+    if sys.argv[1:] == ["panoptic"]:          # only the post-processing fixtures
+        panoptic_goldens()
+    else:
+        main()

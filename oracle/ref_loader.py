@@ -163,3 +163,36 @@ def within_clip_module():
         _load(f"{pkg}.{name}", os.path.join(WC, name + ".py"))
     _cache["wcm"] = sys.modules[pkg + ".msdeformattn"]
     return _cache["wcm"]
+
+
+def wc_model():
+    """`Vk/maxtron_deeplab/maxtron_wc_model.py` (MaXTronWCDeepLab: `panoptic_mask_inference`, the post-path tail).
+    detectron2 is needed only for registries / type names at import time, and the two sibling modules (criterion, matcher: training
+    only) are replaced by empty stand-ins."""
+    if "wcmodel" in _cache:
+        return _cache["wcmodel"]
+    _install_stubs()
+    import torch
+    d2 = sys.modules["detectron2"]
+    data = _pkg("detectron2.data")
+    data.MetadataCatalog = types.SimpleNamespace(get=lambda name: types.SimpleNamespace())
+    modeling = sys.modules["detectron2.modeling"]
+    if not hasattr(modeling, "META_ARCH_REGISTRY"):
+        modeling.META_ARCH_REGISTRY = type(modeling.SEM_SEG_HEADS_REGISTRY)("META_ARCH")
+        modeling.build_backbone = modeling.build_sem_seg_head = lambda *a, **k: None
+    bb = _pkg("detectron2.modeling.backbone")
+    bb.Backbone = torch.nn.Module
+    st = _pkg("detectron2.structures")
+    st.ImageList = object
+    mem = _pkg("detectron2.utils.memory")
+    mem.retry_if_cuda_oom = lambda f: f
+    d2.data, d2.structures = data, st
+    pkg = "_axvs_ref_maxtron"
+    _pkg(pkg, os.path.join(VK, "maxtron_deeplab"))
+    _pkg(pkg + ".modeling", os.path.join(VK, "maxtron_deeplab/modeling"))
+    crit = _pkg(pkg + ".modeling.wc_criterion")
+    crit.MaXTronWCSetCriterion = object
+    mat = _pkg(pkg + ".modeling.matcher")
+    mat.VideoHungarianMatcher = object
+    _cache["wcmodel"] = _load(pkg + ".maxtron_wc_model", os.path.join(VK, "maxtron_deeplab/maxtron_wc_model.py"))
+    return _cache["wcmodel"]

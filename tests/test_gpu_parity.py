@@ -778,3 +778,72 @@ def test_within_clip_module_r50_shapes(O):
         e = nerr(out[name], want[i])
         cos = torch.nn.functional.cosine_similarity(out[name].cpu().flatten(), want[i].flatten(), dim=0).item()
         assert e < 3e-2 and cos > 0.999, (name, e, cos)
+
+
+# --------------------------------------------------------------------------------------------- post-path tail (row f4)
+def _pano(C, thr=0.3):
+    from types import SimpleNamespace
+    from axial_vs_b200.postprocess import PanopticPostProcessor
+    thing, stuff, div = synth.panoptic_metadata(C)
+    md = SimpleNamespace(thing_dataset_id_to_contiguous_id=thing, stuff_dataset_id_to_contiguous_id=stuff, label_divisor=div)
+    return PanopticPostProcessor(md, pixel_confidence_threshold=thr)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_panoptic_golden(golden, tag):
+    """Bit-exact panoptic ids against the unmodified reference method (fixtures made by oracle/make_golden.py)."""
+    gz = golden(f"panoptic_{tag}")
+    N, C, T, H, W, seed = (int(gz[k]) for k in "N C T H W seed".split())
+    mc, mp, me = synth.panoptic_case(seed, N, C, T, H, W)
+    seg, dic = _pano(C, float(gz["thr"])).panoptic_mask_inference(mc.cuda(), mp.cuda(), me.cuda())
+    assert seg.dtype == torch.int32 and tuple(seg.shape) == (T, H, W)
+    assert np.array_equal(seg.cpu().numpy(), gz["seg"])
+    cats = sorted(dic.keys())
+    assert cats == list(gz["cats"]) and [len(dic[c]) for c in cats] == list(gz["counts"])
+    if cats:
+        got = torch.cat([torch.stack(dic[c]) for c in cats]).cpu()
+        assert (got - torch.from_numpy(gz["embs"])).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("N,C,T,H,W,thr,cell", [(128, 124, 2, 161, 161, 0.3, 13), (128, 124, 2, 641, 641, 0.3, 53), (100, 19, 5, 97, 131, 0.4, 8),
+                                                 (255, 50, 1, 64, 48, 0.2, 5), (1, 3, 1, 5, 7, 0.3, 4),
+                                                 (120, 10, 2, 200, 160, 0.2, 1)])      # pure noise: thousands of distinct candidate sets (more than the greedy kernel keeps in registers)
+def test_panoptic_oracle_sizes(N, C, T, H, W, thr, cell):
+    """Config-sized inputs (128 slots, VIPSeg's 124 classes, up to the full 2 x 641 x 641 frame pair) against the numpy oracle.  Every
+    decision is a comparison of fp32 scores, so the result is exact unless a score sits within rounding distance of its threshold:
+    the test measures those margins on the oracle side and asserts exact equality when they are clear."""
+    from oracle import panoptic_oracle as PO
+    seed = 3000 + N + C + T + H + W
+    mc, mp, me = synth.panoptic_case(seed, N, C, T, H, W, cell=cell)
+    pp = _pano(C, thr)
+    seg, segments = pp.panoptic_segments(mc.cuda(), mp.cuda())
+    seg2, segments2 = pp.panoptic_segments(mc.cuda(), mp.cuda())
+    assert torch.equal(seg, seg2) and torch.equal(segments, segments2), "not reproducible"
+    meta = PO.Metadata(*synth.panoptic_metadata(C))
+    ref, _, ref_segments = PO.panoptic_mask_inference(mc.numpy(), mp.numpy(), None, meta, pixel_thr=thr)
+    px_m, cls_m, gap, top2 = PO.margins(mc.numpy(), mp.numpy(), meta, thr, 0.1, 0.3)
+    got = seg.cpu().numpy()
+    n = int(segments[0])
+    got_segments = [tuple(r) for r in segments[1:1 + 4 * n].view(n, 4).tolist()]
+    if cls_m > 1e-5 and gap > 1e-5 and top2 > 1e-5:
+        mism = int((got != ref).sum())
+        if px_m > 2e-6:
+            assert mism == 0 and got_segments == ref_segments
+        else:   # a handful of pixels within rounding distance of the pixel threshold may flip; the segment table must still agree
+            assert mism <= max(2, got.size // 100000), mism
+            assert [s[0] for s in got_segments] == [s[0] for s in ref_segments]
+    else:
+        pytest.skip(f"degenerate synthetic case (margins {cls_m:.2e} {gap:.2e} {top2:.2e})")
+
+
+def test_panoptic_rejects_bad_arguments():
+    mc, mp, me = synth.panoptic_case(1, 8, 6, 1, 8, 8)
+    with pytest.raises(RuntimeError):
+        _pano(6).panoptic_mask_inference(mc, mp, me)                                   # CPU tensors
+    with pytest.raises(RuntimeError):
+        _pano(6, thr=0.1).panoptic_mask_inference(mc.cuda(), mp.cuda(), me.cuda())      # more than four candidates per pixel possible
+    with pytest.raises(KeyError):
+        _pano(3).panoptic_mask_inference(mc.cuda(), mp.cuda(), me.cuda())               # more classes than the metadata names
+    big = torch.zeros(256, 7, device="cuda")
+    with pytest.raises(RuntimeError):
+        _pano(6).panoptic_mask_inference(big, torch.zeros(256, 1, 4, 4, device="cuda"), torch.zeros(256, 4, device="cuda"))

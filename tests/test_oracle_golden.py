@@ -177,3 +177,23 @@ def test_within_clip_module(golden):
     outs = O.within_clip_module(feats, p, 1, 2)
     for o, name in zip(outs, ("res5", "res4", "res3")):
         _close(o, gz[name], atol=2e-4)
+
+
+# --------------------------------------------------------------------------------------------- post-path tail (row f4)
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_panoptic_mask_inference(golden, tag):
+    """The numpy restatement against outputs of the unmodified `MaXTronWCDeepLab.panoptic_mask_inference` (integer ids: exact)."""
+    from oracle import panoptic_oracle as PO
+    gz = golden(f"panoptic_{tag}")
+    N, C, T, H, W, seed = (int(gz[k]) for k in "N C T H W seed".split())
+    mc, mp, me = synth.panoptic_case(seed, N, C, T, H, W)
+    meta = PO.Metadata(*synth.panoptic_metadata(C))
+    seg, dic, segments = PO.panoptic_mask_inference(mc.numpy(), mp.numpy(), me.numpy(), meta, pixel_thr=float(gz["thr"]))
+    assert np.array_equal(seg, gz["seg"])
+    cats = sorted(dic.keys())
+    assert cats == list(gz["cats"]) and [len(dic[c]) for c in cats] == list(gz["counts"])
+    if cats:
+        _close(np.concatenate([np.stack(dic[c]) for c in cats]), gz["embs"], atol=1e-6)
+    # every id in the map is -1, a stuff category or category * divisor + instance index of an opened thing segment
+    ids = {s[3] for s in segments}
+    assert set(np.unique(seg).tolist()) <= ids | {-1}
