@@ -22,7 +22,8 @@ constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_W_BYTES;
 constexpr int GEMM_EPI_WARPS = 8;   // two groups of four (TMEM lane quarter = warp & 3), each draining 128 of the 256 accumulator columns
 constexpr int GEMM_APROD_WARPS = 8;
 constexpr int GEMM_THREADS = (GEMM_EPI_WARPS + 2 + GEMM_APROD_WARPS) * 32;   // 320
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_STG_BYTES = GEMM_EPI_WARPS * 4096;   // per-warp 32 rows x 128 B transpose staging of the epilogue
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 enum RowMap : int { MAP_NONE = 0, MAP_HPASS = 1, MAP_WPASS = 2 };
 
@@ -108,27 +109,37 @@ struct GemmParams {
                         //      pixel r % out_nchw; every column is one coalesced 4-byte store per lane (lanes = consecutive pixels)
 };
 
-__device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, int row, int col, float (&v)[32]) {
-  // v holds acc for columns col..col+31 of logical row `row`
+// v holds the accumulator for columns col..col+31 of logical row `row` (= row0 + lane; rows >= M are not stored).
+// Token-major outputs go through a per-warp 4 KiB shared-memory transpose so that one store instruction writes whole rows pieces:
+// 4 rows x 128 contiguous bytes (fp32) or 8 rows x 64 bytes (bf16) instead of 32 scattered 16-byte pieces; the residual is read the
+// same way.  NCHW outputs are already coalesced (lanes = consecutive pixels of one channel).
+__device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, int row, int row0, int col, float (&v)[32], const float4 (&b)[8],
+                                                    uint8_t* stg, int lane) {
+  // bias (loaded by the caller before it waits for the accumulator), scale, activation: one uniform branch per group, so the GELU
+  // body (erff, 32 x unrolled) is not fetched by the projections that do not use it
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float x = v[i] + (p.bias ? __ldg(p.bias + col + i) : 0.f);
-    x *= p.scale;
-    if (p.relu == 1) x = fmaxf(x, 0.f);
-    else if (p.relu == 2) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
-    v[i] = x;
+  for (int i = 0; i < 8; ++i) { v[4 * i] += b[i].x; v[4 * i + 1] += b[i].y; v[4 * i + 2] += b[i].z; v[4 * i + 3] += b[i].w; }
+  if (p.scale != 1.f) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+  }
+  if (p.relu == 1) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (p.relu == 2) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
   }
   if (p.out_nchw > 0) {
+    if (row >= p.M) return;
     const int img = row / p.out_nchw, pix = row - img * p.out_nchw;
     float* o = reinterpret_cast<float*>(p.out) + ((size_t)img * p.n_out + col) * p.out_nchw + pix;
 #pragma unroll
     for (int i = 0; i < 32; ++i) o[(size_t)i * p.out_nchw] = v[i];
     return;
   }
-  int orow = pass_to_canonical(row, p.map_mode, p.dims);
   if (p.out_bf16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)orow * p.ldo + p.out_col0 + col;
-    uint4* o4 = reinterpret_cast<uint4*>(o);
+    // staging row = 64 B (4 pieces of 16 B), piece index XOR-swizzled with (row >> 1) & 3
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint4 u;
@@ -136,30 +147,57 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, int row
       u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
       u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
       u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      o4[i] = u;
+      *reinterpret_cast<uint4*>(stg + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = u;
     }
-  } else {
-    float* o = reinterpret_cast<float*>(p.out) + (size_t)orow * p.ldo + p.out_col0 + col;
-    float4* o4 = reinterpret_cast<float4*>(o);
-    if (p.resid) {
-      const float4* r4 = reinterpret_cast<const float4*>(p.resid + (size_t)orow * p.ldo + p.out_col0 + col);
+    __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 r = __ldg(r4 + i);
-        o4[i] = make_float4(v[4 * i] + r.x, v[4 * i + 1] + r.y, v[4 * i + 2] + r.z, v[4 * i + 3] + r.w);
+    for (int i = 0; i < 4; ++i) {
+      const int rl = 8 * i + (lane >> 2), piece = lane & 3;
+      const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((piece ^ ((rl >> 1) & 3)) << 4));
+      if (row0 + rl < p.M) {
+        const int orow = pass_to_canonical(row0 + rl, p.map_mode, p.dims);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)orow * p.ldo + p.out_col0 + col + piece * 8) = u;
       }
-    } else {
+    }
+    __syncwarp();
+    return;
+  }
+  // fp32: staging row = 128 B (8 pieces), piece index XOR-swizzled with row & 7
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  __syncwarp();
+  float4 r[8];
+  if (p.resid) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = 4 * i + (lane >> 3), piece = lane & 7;
+      r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + rl < p.M) {
+        const int orow = pass_to_canonical(row0 + rl, p.map_mode, p.dims);
+        r[i] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)orow * p.ldo + p.out_col0 + col) + piece);
+      }
     }
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = 4 * i + (lane >> 3), piece = lane & 7;
+    float4 u = *reinterpret_cast<const float4*>(stg + rl * 128 + ((piece ^ (rl & 7)) << 4));
+    if (p.resid) { u.x += r[i].x; u.y += r[i].y; u.z += r[i].z; u.w += r[i].w; }
+    if (row0 + rl < p.M) {
+      const int orow = pass_to_canonical(row0 + rl, p.map_mode, p.dims);
+      *(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)orow * p.ldo + p.out_col0 + col) + piece) = u;
+    }
+  }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+  uint8_t* stg_base = smem + GEMM_STAGES * GEMM_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + GEMM_STG_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + GEMM_STAGES;        // [STAGES]
   uint64_t* tfull_bar = bars + 2 * GEMM_STAGES;    // [2]
@@ -194,6 +232,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
   if (warp < GEMM_EPI_WARPS) {
     // ===================== epilogue: TMEM -> registers -> global =====================
     uint32_t acc = 0, acc_phase = 0;
+    uint8_t* stg = stg_base + warp * 4096;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / n_chunks, nc = tile % n_chunks;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -204,9 +243,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
 #pragma unroll 1
       for (int c = c_begin; c < c_begin + GEMM_BN / 2; c += 32) {
         float v[32];
+        float4 b[8];
         tmem_ld32(taddr + c, v);
+        if (p.bias) {                              // eight independent 16-byte loads, in flight while the accumulator is read
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc * GEMM_BN + c);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) b[i] = __ldg(b4 + i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         tmem_ld_wait();
-        if (row < p.M) gemm_epilogue_store(p, row, nc * GEMM_BN + c, v);
+        gemm_epilogue_store(p, row, mt * GEMM_BM + (warp & 3) * 32, nc * GEMM_BN + c, v, b, stg, lane);
       }
       tc_fence_before();
       __syncwarp();
