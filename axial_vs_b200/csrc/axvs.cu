@@ -1015,6 +1015,7 @@ int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, cons
   // [sampling offsets | attention logits] = Linear(src + pos)                                       MSDA:102-103 (query = src + pos, ENC:207)
   p = gemm_params(nullptr, 256, rows, 256, w->w_oa, 512, 0, w->b_oa, 512, 1.f, 0, oa, 512, 0, 0, nullptr);
   p.a_diag = 4; p.A32 = src; p.A32b = pos; p.a32b_rows = (pos && pos_images == 1 && images > 1) ? len : 0;
+  p.n_valid = (8 * d.L * d.P * 3 + 31) / 32 * 32;          // 8 heads x L levels x P points x (2 offsets + 1 logit) = 288 of the 512 padded columns
   if ((rc = launch_gemm(p, st))) return rc;
   {
     ProfScope ps(KC_MSDA, 0, (double)rows * (8.0 * d.L * d.P * 4 * 64 + 2048 + 512), st);

@@ -94,6 +94,7 @@ struct GemmParams {
   int w_rows_total;   // rows of the packed image (K-block stride = w_rows_total * 128 B)
   int w_row0;         // first weight row used by this GEMM (multiple of 8)
   int n_out;    // multiple of 256
+  int n_valid;  // > 0: only columns < n_valid (a multiple of 32) are stored; the rest of n_out is zero-weight padding
   const float* bias;
   // epilogue
   float scale;  // applied after bias
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
       const int c_begin = (warp >> 2) * (GEMM_BN / 2);
 #pragma unroll 1
       for (int c = c_begin; c < c_begin + GEMM_BN / 2; c += 32) {
+        if (p.n_valid > 0 && nc * GEMM_BN + c >= p.n_valid) break;      // padding columns
         float v[32];
         float4 b[8];
         tmem_ld32(taddr + c, v);
