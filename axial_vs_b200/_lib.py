@@ -29,6 +29,12 @@ class MsdaWeights(Structure):
                 ("d_ffn", c_int), ("n_levels", c_int), ("n_points", c_int)]
 
 
+class KmaxAxialWeights(Structure):
+    """struct axvs_kmax_axial_weights."""
+    _fields_ = [("w_qkv", c_void_p), ("b_qkv", c_void_p), ("emb_q", c_void_p), ("emb_k", c_void_p), ("emb_v", c_void_p),
+                ("sim_s", c_void_p), ("sim_t", c_void_p), ("out_s", c_void_p), ("out_t", c_void_p), ("heads", c_int), ("dk", c_int), ("dv", c_int)]
+
+
 class AsppWeights(Structure):
     _fields_ = [("w_conv", c_void_p * 3), ("b_conv", c_void_p * 3), ("dilation", c_int * 3), ("w_proj", c_void_p),
                 ("lncf_g", c_void_p), ("lncf_b", c_void_p), ("ln_g", c_void_p), ("ln_b", c_void_p)]
@@ -75,6 +81,9 @@ SIGNATURES = {
     "axvs_output_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "axvs_msda_layer_workspace_bytes": (c_size_t, [c_int, c_int]),
     "axvs_msda_layer_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, POINTER(c_int), c_void_p, POINTER(MsdaWeights), c_int, c_int, c_void_p, c_size_t,
+                                    c_void_p]),
+    "axvs_kmax_axial_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "axvs_kmax_axial_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(KmaxAxialWeights), c_void_p, c_int, c_void_p, c_size_t,
                                     c_void_p]),
     "axvs_panoptic_workspace_bytes": (c_size_t, [c_int, ctypes.c_longlong]),
     "axvs_panoptic_inference": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_float, c_float, c_float,

@@ -21,6 +21,7 @@
 #include "proj.cuh"
 #include "msda.cuh"
 #include "panoptic.cuh"
+#include "kmax_axial.cuh"
 #include "ffn_pair.cuh"
 
 using namespace axvs;
@@ -38,12 +39,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel"};
 int g_fusion = 4;   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
 int g_pair = 0;   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
@@ -275,7 +276,7 @@ int blocks_for(long long work_items, int per_block, int sms) {
 
 extern "C" {
 
-int axvs_version(void) { return 112; }
+int axvs_version(void) { return 113; }
 int axvs_set_pair_mode(int on) {
   const int prev = g_pair;
   g_pair = on ? 1 : 0;
@@ -1110,6 +1111,74 @@ int axvs_panoptic_inference(const float* mask_cls, const float* mask_pred, int N
     pano_paint_kernel<<<blocks, 256, 0, st>>>(p);
   }
   AXVS_CHECK_LAUNCH("panoptic kernels");
+  return AXVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- kMaX axial attention (row f3)
+size_t axvs_kmax_axial_workspace_bytes(int images, int H, int W, int heads, int dk, int dv) {
+  if (images <= 0 || H <= 0 || W <= 0 || heads <= 0 || dk <= 0 || dv <= 0) return 0;
+  return align256((size_t)images * H * W * (size_t)(2 * heads * dk + heads * dv) * 4);
+}
+
+int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int H, int W, int axis, const axvs_kmax_axial_weights* w,
+                        float* out, int out_layout, void* workspace, size_t workspace_bytes, axvs_stream_t stream) {
+  if (!x || !w || !out || !workspace) return fail(AXVS_E_INVALID, "kmax_axial: null pointer");
+  if (!w->w_qkv || !w->b_qkv || !w->emb_q || !w->emb_k || !w->emb_v || !w->sim_s || !w->sim_t || !w->out_s || !w->out_t)
+    return fail(AXVS_E_INVALID, "kmax_axial: null weight pointer");
+  if (images <= 0 || c_in <= 0 || H <= 0 || W <= 0) return fail(AXVS_E_INVALID, "kmax_axial: sizes must be positive");
+  if (axis != 1 && axis != 2) return fail(AXVS_E_INVALID, "kmax_axial: axis must be 1 (height) or 2 (width)");
+  if ((x_layout != 0 && x_layout != 1) || (out_layout != 0 && out_layout != 1)) return fail(AXVS_E_INVALID, "kmax_axial: bad layout code");
+  const int heads = w->heads, dk = w->dk, dv = w->dv;
+  const int n_qkv = 2 * heads * dk + heads * dv, Vd = heads * dv;
+  if (heads <= 0 || dk <= 0 || dv <= 0) return fail(AXVS_E_INVALID, "kmax_axial: bad head sizes");
+  if (c_in % 64 || n_qkv % GEMM_BN) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: c_in must be a multiple of 64 and 2*key_depth + value_depth of 256");
+  const int L = axis == 1 ? H : W;
+  if (L > KA_MAX_L) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: axis length %d exceeds %d", L, KA_MAX_L);
+  const size_t smem = kmax_axial_smem_bytes(L, dk, dv);
+  if (smem > 227 * 1024) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: %zu bytes of shared memory needed (L=%d, dk=%d, dv=%d)", smem, L, dk, dv);
+  const long long rows = (long long)images * H * W;
+  if (rows > 0x7fffffffLL) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: too many pixels");
+  const size_t need = axvs_kmax_axial_workspace_bytes(images, H, W, heads, dk, dv);
+  if (workspace_bytes < need) return fail(AXVS_E_WORKSPACE, "kmax_axial: workspace %zu < required %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* qkv = reinterpret_cast<float*>(workspace);
+  // qkv = BN(conv1x1(x)): the batch norm is folded into the packed weight rows and the bias      kmax_pixel_decoder.py:130
+  // Split precision (a_split): the packed weight is [W_hi | W_hi | W_lo] over 3 c_in columns; a softmax over sums of 64 products of these
+  // outputs follows, and plain bf16 operands left 1.5e-2 of error after the two chained passes of AxialAttention2D.
+  GemmParams g = gemm_params(nullptr, c_in, (int)rows, 3 * c_in, w->w_qkv, n_qkv, 0, w->b_qkv, n_qkv, 1.f, 0, qkv, n_qkv, 0, 0, nullptr);
+  g.a_split = 1;
+  if (x_layout == 0) { g.a_diag = 3; g.A32 = x; g.a_n = H * W; }
+  else { g.a_diag = 4; g.A32 = x; }
+  if (int rc = launch_gemm(g, st)) return rc;
+  KmaxAxialParams p;
+  p.qkv = qkv; p.ld = n_qkv; p.L = L; p.heads = heads; p.dk = dk; p.dv = dv;
+  const long long HW = (long long)H * W;
+  p.row_outer = HW;
+  if (axis == 1) { p.seq_inner = W; p.row_inner = 1; p.row_pos = W; }
+  else { p.seq_inner = H; p.row_inner = W; p.row_pos = 1; }
+  if (out_layout == 0) {          // NCHW [images, Vd, H, W]
+    p.out_outer = Vd * HW; p.out_chan = HW;
+    if (axis == 1) { p.out_inner = 1; p.out_pos = W; } else { p.out_inner = W; p.out_pos = 1; }
+  } else {                        // token rows [images * H * W, Vd]
+    p.out_outer = HW * Vd; p.out_chan = 1;
+    if (axis == 1) { p.out_inner = Vd; p.out_pos = (long long)W * Vd; } else { p.out_inner = (long long)W * Vd; p.out_pos = Vd; }
+  }
+  p.emb_q = w->emb_q; p.emb_k = w->emb_k; p.emb_v = w->emb_v;
+  p.sim_s = w->sim_s; p.sim_t = w->sim_t; p.out_s = w->out_s; p.out_t = w->out_t;
+  p.out = out;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kmax_axial_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "kmax_axial: cannot raise the shared-memory limit");
+    attr_set = true;
+  }
+  const int n_seq = images * (axis == 1 ? W : H);
+  if (n_seq > 65535) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: at most 65535 sequences per call (got %d)", n_seq);
+  {
+    ProfScope ps(KC_KMAXAX, (double)n_seq * heads * ((double)L * L * (6.0 * dk + 4.0 * dv)), (double)rows * (n_qkv + Vd) * 4.0, st);
+    kmax_axial_attn_kernel<<<dim3(heads, n_seq), KA_THREADS, smem, st>>>(p);
+  }
+  AXVS_CHECK_LAUNCH("kmax_axial_attn_kernel");
   return AXVS_OK;
 }
 

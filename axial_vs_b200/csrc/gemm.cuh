@@ -86,6 +86,9 @@ struct GemmParams {
                 //    eight 4-byte loads at a stride of a_n floats -> one 16-byte chunk of the K-major image)
                 // 4: A32 is an fp32 row-major matrix [M, lda] (token rows), converted to bf16 on the fly
   int a_N, a_n, a_F;
+  int a_split;  // modes 3 / 4 only: 1 = split-precision product.  K counts 3 x the source channels: K-blocks [0, K/3) and [2K/3, K) carry
+                //   hi = bf16(a), K-blocks [K/3, 2K/3) carry lo = bf16(a - hi); with weights packed as [hi | hi | lo] the accumulator
+                //   holds a_hi w_hi + a_lo w_hi + a_hi w_lo, i.e. the fp32 product to ~2^-17 (kmax_axial: a softmax sits behind this GEMM)
   const float* A32;
   const float* A32b;    // mode 4 only: optional second fp32 matrix added element-wise (e.g. src + pos), same layout as A32
   int a32b_rows;        // > 0: A32b has only this many rows and is broadcast (row r reads A32b row r % a32b_rows)
@@ -321,7 +324,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
       // consecutive pixels of one channel per instruction.  Mode 4: row q >> 3, chunk q & 7 as for bf16 sources.
       float fa[ITERS][8], fb[ITERS][8];
       auto load = [&](int it, float (&f)[ITERS][8]) {
-        const int tile = blockIdx.x + (it / num_kb) * gridDim.x, kb = it % num_kb;
+        const int tile = blockIdx.x + (it / num_kb) * gridDim.x;
+        const int kb = p.a_split ? (it % num_kb) % (num_kb / 3) : it % num_kb;      // source K-block
         const int mt = tile / n_chunks;
 #pragma unroll
         for (int i = 0; i < ITERS; ++i) {
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
             const int r = mt * GEMM_BM + (q & 127);
             if (r < p.M) {
               const int img = r / p.a_n;
-              const float* s = p.A32 + ((size_t)img * p.K + kb * GEMM_BK + (q >> 7) * 8) * p.a_n + (r - img * p.a_n);
+              const float* s = p.A32 + ((size_t)img * (p.a_split ? p.K / 3 : p.K) + kb * GEMM_BK + (q >> 7) * 8) * p.a_n + (r - img * p.a_n);
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[i][j] = __ldg(s + (size_t)j * p.a_n);
             } else {
@@ -357,15 +361,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
           }
         }
       };
-      auto store = [&](const float (&f)[ITERS][8]) {
+      auto store = [&](const float (&f)[ITERS][8], int it) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* dst = smem + stage * GEMM_STAGE_BYTES;
+        const bool lo_part = p.a_split && ((it % num_kb) / (num_kb / 3)) == 1;
 #pragma unroll
         for (int i = 0; i < ITERS; ++i) {
           const int q = i * PT + ptid;
           const uint32_t off = (p.a_diag == 3) ? sw128_offset(q & 127, q >> 7) : sw128_offset(q >> 3, q & 7);
-          *reinterpret_cast<uint4*>(dst + off) = make_uint4(pack_bf16x2(f[i][0], f[i][1]), pack_bf16x2(f[i][2], f[i][3]),
-                                                            pack_bf16x2(f[i][4], f[i][5]), pack_bf16x2(f[i][6], f[i][7]));
+          float g[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = lo_part ? f[i][j] - __bfloat162float(__float2bfloat16_rn(f[i][j])) : f[i][j];
+          *reinterpret_cast<uint4*>(dst + off) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
+                                                            pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -377,10 +385,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
       if (n_items > 0) load(0, fa);
       for (int it = 0; it < n_items; it += 2) {
         if (it + 1 < n_items) load(it + 1, fb);
-        store(fa);
+        store(fa, it);
         if (it + 1 < n_items) {
           if (it + 2 < n_items) load(it + 2, fa);
-          store(fb);
+          store(fb, it + 1);
         }
       }
     } else

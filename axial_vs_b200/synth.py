@@ -205,3 +205,22 @@ def panoptic_metadata(C: int, label_divisor: int = 1000):
     thing = {c + 1: c for c in range(C) if c % 3 == 0}
     stuff = {c + 1: c for c in range(C) if c % 3 != 0}
     return thing, stuff, label_divisor
+
+
+def kmax_axial_params(seed: int, in_planes: int, key_depth: int = 512, value_depth: int = 1024, heads: int = 8) -> Params:
+    """State dict of the kMaX `AxialAttention` (Vk/kmax_deeplab/modeling/pixel_decoder/kmax_pixel_decoder.py:105-126): 1x1 conv, three
+    relative-position embedding tables (trunc-normal-like, std 1), three batch norms with non-trivial running statistics."""
+    g = torch.Generator().manual_seed(seed)
+    n_qkv = 2 * key_depth + value_depth
+    p: Params = {"qkv_transform.conv.weight": torch.randn(n_qkv, in_planes, 1, generator=g) * in_planes ** -0.5}
+    for name, depth in (("query", key_depth // heads), ("key", key_depth // heads), ("value", value_depth // heads)):
+        p[f"_{name}_rpe._embeddings.weight"] = torch.randn(2 * 255 - 1, depth, generator=g).clamp_(-2, 2)
+    for name, ch in (("_batch_norm_qkv", n_qkv), ("_batch_norm_similarity", 3 * heads), ("_batch_norm_retrieved_output", 2 * value_depth)):
+        p[name + ".weight"] = 1.0 + 0.2 * torch.randn(ch, generator=g)
+        p[name + ".bias"] = 0.1 * torch.randn(ch, generator=g)
+        p[name + ".running_mean"] = 0.1 * torch.randn(ch, generator=g)
+        p[name + ".running_var"] = 0.5 + torch.rand(ch, generator=g)
+        p[name + ".num_batches_tracked"] = torch.tensor(1, dtype=torch.long)
+    # similarity logits are sums over 64 channels of unit-variance products: keep their batch-norm scale small so the softmax is not one-hot
+    p["_batch_norm_similarity.weight"] *= 0.15
+    return p

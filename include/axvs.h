@@ -240,6 +240,31 @@ int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, cons
                         float* out, const axvs_msda_weights* w, int images, int len, void* workspace, size_t workspace_bytes,
                         axvs_stream_t stream);
 
+/* ---- kMaX pixel-decoder axial attention ------------------------------------------------------------- */
+
+/* One AxialAttention pass (Vk/kmax_deeplab/modeling/pixel_decoder/kmax_pixel_decoder.py:105-157, eval mode) over an image batch:
+ * qkv = BN(conv1x1(x)) as a tcgen05 GEMM (the batch norm folded into w_qkv / b_qkv by the caller), then per (sequence, head) in fp32:
+ * logits = BN(q.k) + BN(q.rpe_q) + BN(k.rpe_k), softmax, BN(w v) + BN(w rpe_v).
+ *   w_qkv   packed (axvs_pack_weight) split-precision image [2*heads*dk + heads*dv, 3*c_in] = [W | W | W - bf16(W)] of the conv weight with
+ *           the qkv batch-norm scale folded into its rows (the GEMM multiplies hi / lo bf16 halves: fp32-grade logits); b_qkv the shift
+ *   emb_*   fp32 relative-position embedding tables [2*255 - 1, depth] (_query_rpe / _key_rpe / _value_rpe ._embeddings.weight)
+ *   sim_s/t fp32 [3*heads]      folded _batch_norm_similarity (y = x*s + t; channels: content, query-rpe, key-rpe heads)
+ *   out_s/t fp32 [2*heads*dv]   folded _batch_norm_retrieved_output (content channels, then rpe channels) */
+typedef struct axvs_kmax_axial_weights {
+  const void* w_qkv; const float* b_qkv;
+  const float* emb_q; const float* emb_k; const float* emb_v;
+  const float* sim_s; const float* sim_t; const float* out_s; const float* out_t;
+  int heads, dk, dv;
+} axvs_kmax_axial_weights;
+
+/* x: x_layout 0 = fp32 NCHW [images, c_in, H, W], 1 = fp32 token rows [images*H*W, c_in].  axis 1: one sequence per (image, w) running
+ * along H (the `_height_axis` of AxialAttention2D, :179-182; also the 1-D module on [N, C, L] with H = L, W = 1); axis 2: one per
+ * (image, h) along W (:184-187).  out: out_layout 0 = NCHW [images, heads*dv, H, W], 1 = token rows [images*H*W, heads*dv] (what the
+ * next axis consumes: the reference's permutes at :183 and :188 are folded into these layouts).  Axis length <= 64. */
+size_t axvs_kmax_axial_workspace_bytes(int images, int H, int W, int heads, int dk, int dv);
+int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int H, int W, int axis, const axvs_kmax_axial_weights* w,
+                        float* out, int out_layout, void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+
 /* ---- post-path tail ------------------------------------------------------------------------------ */
 
 /* MaXTronWCDeepLab.panoptic_mask_inference (Vk/maxtron_deeplab/maxtron_wc_model.py:439-553; identical copy in maxtron_cc_model.py:460-574),

@@ -218,6 +218,7 @@ def main():
     out, _, _ = mod.forward_features(feats)
     save("wc_module", seed=seed, chans=chans, sizes=torch.tensor(sizes), res5=out["res5"], res4=out["res4"], res3=out["res3"], wsum=synth.checksum(p))
     panoptic_goldens()
+    kmax_goldens()
 
 
 @torch.no_grad()
@@ -242,10 +243,32 @@ def panoptic_goldens():
 
 
 
+@torch.no_grad()
+def kmax_goldens():
+    # ---- 11. kMaX pixel-decoder axial attention (row f3): the unmodified AxialAttention / AxialAttention2D in eval mode
+    ref_loader.cross_clip()                                   # loads kmax_pixel_decoder.py
+    KP = sys.modules["kmax_deeplab.modeling.pixel_decoder.kmax_pixel_decoder"]
+    for tag, (N, C, L, seed) in {"a": (3, 128, 9, 31), "b": (2, 512, 41, 32)}.items():
+        m = KP.AxialAttention(C, query_shape=L, total_key_depth=512, total_value_depth=1024, num_heads=8).eval()
+        p = synth.kmax_axial_params(seed, C)
+        m.load_state_dict(p, strict=True)
+        y = m(synth.randn(seed + 100, N, C, L))
+        save(f"kmax_axial_{tag}", N=N, C=C, L=L, seed=seed, y=y, wsum=synth.checksum(p))
+    N, C, H, W, seed = 2, 256, 11, 14, 33
+    m2 = KP.AxialAttention2D(C, query_shape=[H, W], filters=512, key_expansion=1, value_expansion=2, num_heads=8).eval()
+    ph, pw = synth.kmax_axial_params(seed, C), synth.kmax_axial_params(seed + 1, 1024)
+    m2._height_axis.load_state_dict(ph, strict=True)
+    m2._width_axis.load_state_dict(pw, strict=True)
+    y = m2(synth.randn(seed + 100, N, C, H, W))
+    save("kmax_axial_2d", N=N, C=C, H=H, W=W, seed=seed, y=y, wsum=synth.checksum(ph) + synth.checksum(pw))
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found; golden fixtures can only be generated where it is mounted")
     if sys.argv[1:] == ["panoptic"]:          # only the post-processing fixtures
         panoptic_goldens()
+    elif sys.argv[1:] == ["kmax"]:
+        kmax_goldens()
     else:
         main()

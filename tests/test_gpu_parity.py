@@ -847,3 +847,72 @@ def test_panoptic_rejects_bad_arguments():
     big = torch.zeros(256, 7, device="cuda")
     with pytest.raises(RuntimeError):
         _pano(6).panoptic_mask_inference(big, torch.zeros(256, 1, 4, 4, device="cuda"), torch.zeros(256, 4, device="cuda"))
+
+
+# --------------------------------------------------------------------------------------------- kMaX axial attention (row f3)
+def _kmax_1d(C, L, p):
+    from axial_vs_b200.kmax_axial import AxialAttention
+    m = AxialAttention(C, query_shape=L, total_key_depth=512, total_value_depth=1024, num_heads=8).eval()
+    m.load_state_dict(p, strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_kmax_axial_golden(golden, tag):
+    gz = golden(f"kmax_axial_{tag}")
+    N, C, L, seed = (int(gz[k]) for k in "N C L seed".split())
+    p = synth.kmax_axial_params(seed, C)
+    with torch.no_grad():
+        y = _kmax_1d(C, L, p)(synth.randn(seed + 100, N, C, L).cuda())
+    assert tuple(y.shape) == (N, 1024, L)
+    assert nerr(y, torch.from_numpy(gz["y"])) < TOL
+
+
+def test_kmax_axial_2d_golden(golden):
+    from axial_vs_b200.kmax_axial import AxialAttention2D
+    gz = golden("kmax_axial_2d")
+    N, C, H, W, seed = (int(gz[k]) for k in "N C H W seed".split())
+    m = AxialAttention2D(C, query_shape=[H, W], filters=512, key_expansion=1, value_expansion=2, num_heads=8).eval()
+    m._height_axis.load_state_dict(synth.kmax_axial_params(seed, C), strict=True)
+    m._width_axis.load_state_dict(synth.kmax_axial_params(seed + 1, 1024), strict=True)
+    m.cuda()
+    with torch.no_grad():
+        y = m(synth.randn(seed + 100, N, C, H, W).cuda())
+    assert tuple(y.shape) == (N, 1024, H, W)
+    assert nerr(y, torch.from_numpy(gz["y"])) < TOL
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 512, 21, 21), (1, 512, 41, 41), (3, 64, 64, 5), (2, 128, 1, 33)])
+def test_kmax_axial_2d_oracle_config_sizes(N, C, H, W):
+    """kMaX R50 at 641x641: the axial blocks run at stride 32 (21x21) and stride 16 (41x41) on 512 channels; plus the longest supported
+    axis and a degenerate one."""
+    from axial_vs_b200.kmax_axial import AxialAttention2D
+    from oracle import kmax_oracle as KO
+    seed = 4000 + N + C + H + W
+    ph, pw = synth.kmax_axial_params(seed, C), synth.kmax_axial_params(seed + 1, 1024)
+    m = AxialAttention2D(C, query_shape=[H, W]).eval()
+    m._height_axis.load_state_dict(ph, strict=True)
+    m._width_axis.load_state_dict(pw, strict=True)
+    m.cuda()
+    x = synth.randn(seed + 2, N, C, H, W)
+    ref = KO.axial_attention_2d(x, ph, pw)
+    with torch.no_grad():
+        y = m(x.cuda())
+    e = nerr(y, ref)
+    cos = torch.nn.functional.cosine_similarity(y.cpu().flatten(), ref.flatten(), dim=0).item()
+    assert e < TOL and cos > 0.9999, (e, cos)
+
+
+def test_kmax_axial_rejects_bad_arguments():
+    p = synth.kmax_axial_params(1, 64)
+    m = _kmax_1d(64, 9, p)
+    with torch.no_grad():
+        with pytest.raises(RuntimeError):
+            m(torch.zeros(1, 64, 9))                      # CPU tensor
+        with pytest.raises(RuntimeError):
+            m(torch.zeros(1, 64, 65, device="cuda"))      # axis longer than the kernel's shared-memory budget allows
+        with pytest.raises(RuntimeError):
+            m(torch.zeros(1, 32, 9, device="cuda"))       # wrong channel count
+    m.train()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 64, 9, device="cuda"))

@@ -197,3 +197,22 @@ def test_panoptic_mask_inference(golden, tag):
     # every id in the map is -1, a stuff category or category * divisor + instance index of an opened thing segment
     ids = {s[3] for s in segments}
     assert set(np.unique(seg).tolist()) <= ids | {-1}
+
+
+# --------------------------------------------------------------------------------------------- kMaX axial attention (row f3)
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_kmax_axial_attention(golden, tag):
+    from oracle import kmax_oracle as KO
+    gz = golden(f"kmax_axial_{tag}")
+    N, C, L, seed = (int(gz[k]) for k in "N C L seed".split())
+    p = synth.kmax_axial_params(seed, C)
+    assert synth.checksum(p) == pytest.approx(float(gz["wsum"]), rel=1e-12)
+    _close(KO.axial_attention(synth.randn(seed + 100, N, C, L), p), gz["y"])
+
+
+def test_kmax_axial_attention_2d(golden):
+    from oracle import kmax_oracle as KO
+    gz = golden("kmax_axial_2d")
+    N, C, H, W, seed = (int(gz[k]) for k in "N C H W seed".split())
+    ph, pw = synth.kmax_axial_params(seed, C), synth.kmax_axial_params(seed + 1, 1024)
+    _close(KO.axial_attention_2d(synth.randn(seed + 100, N, C, H, W), ph, pw), gz["y"])
