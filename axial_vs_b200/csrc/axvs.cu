@@ -1132,6 +1132,7 @@ int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int 
   const int n_qkv = 2 * heads * dk + heads * dv, Vd = heads * dv;
   if (heads <= 0 || dk <= 0 || dv <= 0) return fail(AXVS_E_INVALID, "kmax_axial: bad head sizes");
   if (c_in % 64 || n_qkv % GEMM_BN) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: c_in must be a multiple of 64 and 2*key_depth + value_depth of 256");
+  if (dk % 4 || dv % 4) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: per-head depths must be multiples of 4 (got %d, %d)", dk, dv);
   const int L = axis == 1 ? H : W;
   if (L > KA_MAX_L) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: axis length %d exceeds %d", L, KA_MAX_L);
   const size_t smem = kmax_axial_smem_bytes(L, dk, dv);
@@ -1173,10 +1174,15 @@ int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int 
     attr_set = true;
   }
   const int n_seq = images * (axis == 1 ? W : H);
-  if (n_seq > 65535) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: at most 65535 sequences per call (got %d)", n_seq);
+  p.n_items = n_seq * heads;
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
   {
     ProfScope ps(KC_KMAXAX, (double)n_seq * heads * ((double)L * L * (6.0 * dk + 4.0 * dv)), (double)rows * (n_qkv + Vd) * 4.0, st);
-    kmax_axial_attn_kernel<<<dim3(heads, n_seq), KA_THREADS, smem, st>>>(p);
+    int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));          // resident CTAs per SM by shared memory (256 threads each)
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    const int grid = p.n_items < d->sms * per_sm ? p.n_items : d->sms * per_sm;
+    kmax_axial_attn_kernel<<<grid, KA_THREADS, smem, st>>>(p);
   }
   AXVS_CHECK_LAUNCH("kmax_axial_attn_kernel");
   return AXVS_OK;

@@ -4,8 +4,10 @@
 //   w = softmax_m(logits)                                                              (fp32, :147-148)
 //   y[c, l] = BNa(sum_m w[l, m] v_m[c]) + BNb(sum_m w[l, m] rv[l, m][c])
 // The 1x1 qkv convolution with its folded batch norm is the tcgen05 GEMM (gemm.cuh, fp32 token rows [q | k | v] out); this kernel is
-// everything after it, in fp32.  One CTA per (head, sequence): q, k, v of the head and the 2L-1 rows of each embedding table that a
-// length-L axis can address live in shared memory (rows padded to an odd word count: conflict-free column walks), the L x L weights too.
+// everything after it, in fp32.  Persistent CTAs walk the (sequence, head) items: q, k, v of the head and the 2L-1 rows of each embedding table that a
+// length-L axis can address live in shared memory (rows padded by 4 words: 16-byte row alignment, and 8 consecutive rows tile the 32 banks,
+// so float4 reads of consecutive rows are conflict-free), the L x L weights too.  Both contraction phases are register-tiled over four
+// positions so that a shared-memory wavefront feeds 40-55 FMAs instead of 20-24.
 // Sequences are addressed by strides so the same kernel serves the 1-D module ([N, C, L]) and both passes of AxialAttention2D
 // (height axis: token rows at stride W, token-major output feeding the width-axis GEMM; width axis: NCHW output).
 #pragma once
@@ -22,6 +24,7 @@ struct KmaxAxialParams {
   const float* qkv;            // fp32 token rows [rows, 2 * H * dk + H * dv]
   int ld;                      // row length
   int L, heads, dk, dv;
+  int n_items;                 // heads x sequences, item = s * heads + h
   int seq_inner;               // sequence s -> first row (s / seq_inner) * row_outer + (s % seq_inner) * row_inner; position l adds l * row_pos
   long long row_outer, row_inner, row_pos;
   const float* emb_q;          // [2 * 255 - 1, dk]
@@ -36,65 +39,89 @@ struct KmaxAxialParams {
 };
 
 __host__ __device__ inline size_t kmax_axial_smem_bytes(int L, int dk, int dv) {
-  const int pk = dk + 1, pv = dv + 1, R = 2 * L - 1;
+  const int pk = dk + 4, pv = dv + 4, R = 2 * L - 1;
   return sizeof(float) * ((size_t)2 * L * pk + (size_t)L * pv + (size_t)2 * R * pk + (size_t)R * pv + (size_t)L * (L + 1));
 }
 
 __global__ void __launch_bounds__(KA_THREADS) kmax_axial_attn_kernel(const KmaxAxialParams p) {
   extern __shared__ float ka_smem[];
-  const int L = p.L, dk = p.dk, dv = p.dv, pk = dk + 1, pv = dv + 1, R = 2 * L - 1;
+  const int L = p.L, dk = p.dk, dv = p.dv, pk = dk + 4, pv = dv + 4, R = 2 * L - 1;
   float* sq = ka_smem;                    // [L][pk]
   float* sk = sq + L * pk;                // [L][pk]
   float* sv = sk + L * pk;                // [L][pv]
-  float* rq = sv + L * pv;                // [R][pk]   row r = relative distance m - l + (L - 1); rq | rk double as the output staging
+  float* rq = sv + L * pv;                // [R][pk]   row r = relative distance m - l + (L - 1)
   float* rk = rq + R * pk;                // [R][pk]
   float* rv = rk + R * pk;                // [R][pv]
   float* sw = rv + R * pv;                // [L][L + 1] logits -> weights
-  const int h = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const int Kd = p.heads * dk;
+
+  // ---- the addressable rows of the three embedding tables: shared by every head and sequence, staged once per (persistent) CTA
+  const int e0 = KA_MAX_SPAN - 1 - (L - 1);                        // embedding row of relative distance -(L - 1)
+  for (int e = tid; e < R * (dk / 4); e += KA_THREADS) {
+    const int r = e / (dk / 4), d4 = e - r * (dk / 4);
+    reinterpret_cast<float4*>(rq + r * pk)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_q + (size_t)(e0 + r) * dk) + d4);
+    reinterpret_cast<float4*>(rk + r * pk)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_k + (size_t)(e0 + r) * dk) + d4);
+  }
+  for (int e = tid; e < R * (dv / 4); e += KA_THREADS) {
+    const int r = e / (dv / 4), d4 = e - r * (dv / 4);
+    reinterpret_cast<float4*>(rv + r * pv)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_v + (size_t)(e0 + r) * dv) + d4);
+  }
+
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+  const int h = item % p.heads, s = item / p.heads;
   const long long row0 = (long long)(s / p.seq_inner) * p.row_outer + (long long)(s % p.seq_inner) * p.row_inner;
 
-  // ---- stage q, k, v of this head and the addressable embedding rows
-  for (int e = tid; e < L * dk; e += KA_THREADS) {
-    const int l = e / dk, d = e - l * dk;
+  // ---- stage q, k, v of this head (16-byte loads: a head's slice of a token row is contiguous)
+  for (int e = tid; e < L * (dk / 4); e += KA_THREADS) {
+    const int l = e / (dk / 4), d4 = e - l * (dk / 4);
     const float* row = p.qkv + (size_t)(row0 + l * p.row_pos) * p.ld;
-    sq[l * pk + d] = __ldg(row + h * dk + d);
-    sk[l * pk + d] = __ldg(row + Kd + h * dk + d);
+    reinterpret_cast<float4*>(sq + l * pk)[d4] = __ldg(reinterpret_cast<const float4*>(row + h * dk) + d4);
+    reinterpret_cast<float4*>(sk + l * pk)[d4] = __ldg(reinterpret_cast<const float4*>(row + Kd + h * dk) + d4);
   }
-  for (int e = tid; e < L * dv; e += KA_THREADS) {
-    const int l = e / dv, d = e - l * dv;
-    sv[l * pv + d] = __ldg(p.qkv + (size_t)(row0 + l * p.row_pos) * p.ld + 2 * Kd + h * dv + d);
-  }
-  const int e0 = KA_MAX_SPAN - 1 - (L - 1);                        // embedding row of relative distance -(L - 1)
-  for (int e = tid; e < R * dk; e += KA_THREADS) {
-    const int r = e / dk, d = e - r * dk;
-    rq[r * pk + d] = __ldg(p.emb_q + (size_t)(e0 + r) * dk + d);
-    rk[r * pk + d] = __ldg(p.emb_k + (size_t)(e0 + r) * dk + d);
-  }
-  for (int e = tid; e < R * dv; e += KA_THREADS) {
-    const int r = e / dv, d = e - r * dv;
-    rv[r * pv + d] = __ldg(p.emb_v + (size_t)(e0 + r) * dv + d);
+  for (int e = tid; e < L * (dv / 4); e += KA_THREADS) {
+    const int l = e / (dv / 4), d4 = e - l * (dv / 4);
+    reinterpret_cast<float4*>(sv + l * pv)[d4] =
+        __ldg(reinterpret_cast<const float4*>(p.qkv + (size_t)(row0 + l * p.row_pos) * p.ld + 2 * Kd + h * dv) + d4);
   }
   __syncthreads();
 
   // ---- similarity logits: three dot products per (l, m), each through its own batch-norm affine        (:137-145)
   const float s0 = p.sim_s[h], t0 = p.sim_t[h], s1 = p.sim_s[p.heads + h], t1 = p.sim_t[p.heads + h];
   const float s2 = p.sim_s[2 * p.heads + h], t2 = p.sim_t[2 * p.heads + h];
-  for (int e = tid; e < L * L; e += KA_THREADS) {
-    const int l = e / L, m = e - l * L;
-    const float* q = sq + l * pk;
-    const float* k = sk + m * pk;
-    const float* a = rq + (m - l + L - 1) * pk;
-    const float* b = rk + (m - l + L - 1) * pk;
-    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#pragma unroll 8
-    for (int d = 0; d < dk; ++d) {
-      const float qd = q[d], kd = k[d];
-      c0 = fmaf(qd, kd, c0);
-      c1 = fmaf(qd, a[d], c1);
-      c2 = fmaf(kd, b[d], c2);
+  // item = (relative distance r, block of four query positions): the four entries (l0 + j, l0 + j + r - (L - 1)) share the rows rq[r] and
+  // rk[r]; lanes take consecutive r, so the k / rq / rk rows of a warp are consecutive (conflict-free float4 reads) and q is a broadcast
+  const int LB = (L + 3) / 4;
+  for (int e = tid; e < R * LB; e += KA_THREADS) {
+    const int lb = e / R, r = e - lb * R;
+    const int l0 = lb * 4, m0 = l0 + r - (L - 1);
+    if (m0 + 3 < 0 || m0 >= L) continue;                          // the whole strip lies outside the L x L square
+    const float4* a4 = reinterpret_cast<const float4*>(rq + r * pk);
+    const float4* b4 = reinterpret_cast<const float4*>(rk + r * pk);
+    const float4* q4[4];
+    const float4* k4[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = l0 + j, m = m0 + j;
+      ok[j] = l < L && m >= 0 && m < L;
+      q4[j] = reinterpret_cast<const float4*>(sq + (ok[j] ? l : 0) * pk);
+      k4[j] = reinterpret_cast<const float4*>(sk + (ok[j] ? m : 0) * pk);
     }
-    sw[l * (L + 1) + m] = fmaf(c0, s0, t0) + fmaf(c1, s1, t1) + fmaf(c2, s2, t2);
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int d = 0; d < dk / 4; ++d) {
+      const float4 A = a4[d], B = b4[d];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 Q = q4[j][d], K = k4[j][d];
+        c0[j] = fmaf(Q.x, K.x, fmaf(Q.y, K.y, fmaf(Q.z, K.z, fmaf(Q.w, K.w, c0[j]))));
+        c1[j] = fmaf(Q.x, A.x, fmaf(Q.y, A.y, fmaf(Q.z, A.z, fmaf(Q.w, A.w, c1[j]))));
+        c2[j] = fmaf(K.x, B.x, fmaf(K.y, B.y, fmaf(K.z, B.z, fmaf(K.w, B.w, c2[j]))));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (ok[j]) sw[(l0 + j) * (L + 1) + m0 + j] = fmaf(c0[j], s0, t0) + fmaf(c1[j], s1, t1) + fmaf(c2[j], s2, t2);
   }
   __syncthreads();
 
@@ -121,29 +148,38 @@ __global__ void __launch_bounds__(KA_THREADS) kmax_axial_attn_kernel(const KmaxA
   const float* ot = p.out_t;
   const int Vd = p.heads * dv;
   const long long out0 = (long long)(s / p.seq_inner) * p.out_outer + (long long)(s % p.seq_inner) * p.out_inner;
-  // channels-first outputs: stage [dv][L + 1] in the (now dead) rq | rk area and store along l
-  const bool pos_fast = p.out_pos == 1 && dv * (L + 1) <= 2 * R * pk;
-  float* stg = rq;
-  for (int e = tid; e < L * dv; e += KA_THREADS) {
-    const int l = e / dv, d = e - l * dv;
-    const float* wrow = sw + l * (L + 1);
-    float yc = 0.f, yr = 0.f;
+  // item = (block of four channels, 32 positions): lanes take consecutive l, so w[l][m] is one conflict-free read, v_m a 16-byte
+  // broadcast and the rv rows of a warp are consecutive; channels-first outputs are stored directly (lanes = consecutive positions)
+  const int LC = (L + 31) / 32, DB = dv / 4;
+  for (int item = tid >> 5; item < DB * LC; item += KA_THREADS / 32) {
+    const int db = item / LC, l = (item - db * LC) * 32 + (tid & 31);
+    const bool ok = l < L;
+    const int lc = ok ? l : L - 1;
+    const float* wrow = sw + lc * (L + 1);
+    const float4* v4 = reinterpret_cast<const float4*>(sv) + db;
+    const float4* r4 = reinterpret_cast<const float4*>(rv + (L - 1 - lc) * pv) + db;        // row m - l + L - 1 at m = 0
+    float4 yc = make_float4(0.f, 0.f, 0.f, 0.f), yr = yc;
     for (int m = 0; m < L; ++m) {
       const float wm = wrow[m];
-      yc = fmaf(wm, sv[m * pv + d], yc);
-      yr = fmaf(wm, rv[(m - l + L - 1) * pv + d], yr);
+      const float4 V = v4[m * (pv / 4)], Rr = r4[m * (pv / 4)];
+      yc.x = fmaf(wm, V.x, yc.x); yc.y = fmaf(wm, V.y, yc.y); yc.z = fmaf(wm, V.z, yc.z); yc.w = fmaf(wm, V.w, yc.w);
+      yr.x = fmaf(wm, Rr.x, yr.x); yr.y = fmaf(wm, Rr.y, yr.y); yr.z = fmaf(wm, Rr.z, yr.z); yr.w = fmaf(wm, Rr.w, yr.w);
     }
-    const int c = h * dv + d;
-    const float y = fmaf(yc, os[c], ot[c]) + fmaf(yr, os[Vd + c], ot[Vd + c]);
-    if (pos_fast) stg[d * (L + 1) + l] = y;
-    else p.out[out0 + (long long)c * p.out_chan + (long long)l * p.out_pos] = y;
+    if (!ok) continue;
+    const int c = h * dv + db * 4;
+    float4 y;
+    y.x = fmaf(yc.x, os[c], ot[c]) + fmaf(yr.x, os[Vd + c], ot[Vd + c]);
+    y.y = fmaf(yc.y, os[c + 1], ot[c + 1]) + fmaf(yr.y, os[Vd + c + 1], ot[Vd + c + 1]);
+    y.z = fmaf(yc.z, os[c + 2], ot[c + 2]) + fmaf(yr.z, os[Vd + c + 2], ot[Vd + c + 2]);
+    y.w = fmaf(yc.w, os[c + 3], ot[c + 3]) + fmaf(yr.w, os[Vd + c + 3], ot[Vd + c + 3]);
+    float* o = p.out + out0 + (long long)c * p.out_chan + (long long)l * p.out_pos;
+    if (p.out_chan == 1) {
+      *reinterpret_cast<float4*>(o) = y;                           // token rows: four consecutive channels
+    } else {
+      o[0] = y.x; o[p.out_chan] = y.y; o[2 * p.out_chan] = y.z; o[3 * p.out_chan] = y.w;
+    }
   }
-  if (pos_fast) {
-    __syncthreads();
-    for (int e = tid; e < L * dv; e += KA_THREADS) {
-      const int d = e / L, l = e - d * L;
-      p.out[out0 + (long long)(h * dv + d) * p.out_chan + l] = stg[d * (L + 1) + l];
-    }
+  __syncthreads();                                                 // q / k / v / weights are overwritten by the next item
   }
 }
 
