@@ -70,15 +70,18 @@ __global__ void __launch_bounds__(256) gn_tokens_apply_kernel(float* __restrict_
 }
 
 // ---- NCHW [images, C, HW]: group g = the contiguous block of (C/32) * HW floats; one CTA per (image, group), two passes --------
-// (the second pass re-reads what the first just streamed: with ~8 CTAs per SM the block is usually still in L2)
+// (the second pass re-reads what the first just streamed: with ~8 CTAs per SM the block is usually still in L2).  HW is odd at every
+// pyramid level, so channel rows are not 16-byte aligned, but the GROUP block is (C/32 is a multiple of 4): both passes walk it with
+// float4 accesses, and the second one picks the (scale, shift) pair per element (a float4 can straddle two channels).
 __global__ void __launch_bounds__(512) gn_nchw_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       int C, int HW, float eps) {
   __shared__ float2 red[16];
   __shared__ float2 stat;
+  __shared__ float s_sc[64], s_sh[64];
   const int img = blockIdx.y, g = blockIdx.x, cpg = C / GN_GROUPS;
   const size_t n = (size_t)cpg * HW;
   float* base = x + ((size_t)img * C + (size_t)g * cpg) * HW;
-  const bool vec = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (n % 4 == 0) && (HW % 4 == 0);
+  const bool vec = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (n % 4 == 0) && cpg <= 64 && HW >= 4;
   float s = 0.f, q = 0.f;
   if (vec) {
     const float4* b4 = reinterpret_cast<const float4*>(base);
@@ -104,19 +107,31 @@ __global__ void __launch_bounds__(512) gn_nchw_kernel(float* __restrict__ x, con
   }
   __syncthreads();
   const float2 st = stat;
-  for (int c = 0; c < cpg; ++c) {                   // per channel: one (scale, shift) pair, no index divisions
+  if (vec) {
+    if (threadIdx.x < cpg) {                          // per channel: one (scale, shift) pair
+      const float sc = st.y * __ldg(gamma + g * cpg + threadIdx.x);
+      s_sc[threadIdx.x] = sc;
+      s_sh[threadIdx.x] = __ldg(beta + g * cpg + threadIdx.x) - st.x * sc;
+    }
+    __syncthreads();
+    float4* b4 = reinterpret_cast<float4*>(base);
+    for (size_t i = threadIdx.x; i < n / 4; i += 512) {
+      const int e = (int)(4 * i), c = e / HW, left = (c + 1) * HW - e;      // elements of this float4 still in channel c (>= 1)
+      const float sc0 = s_sc[c], sh0 = s_sh[c];
+      const float sc1 = left < 4 ? s_sc[c + 1] : sc0, sh1 = left < 4 ? s_sh[c + 1] : sh0;
+      float4 v = b4[i];
+      v.x = v.x * sc0 + sh0;
+      v.y = left > 1 ? v.y * sc0 + sh0 : v.y * sc1 + sh1;
+      v.z = left > 2 ? v.z * sc0 + sh0 : v.z * sc1 + sh1;
+      v.w = left > 3 ? v.w * sc0 + sh0 : v.w * sc1 + sh1;
+      b4[i] = v;
+    }
+    return;
+  }
+  for (int c = 0; c < cpg; ++c) {
     const float sc = st.y * __ldg(gamma + g * cpg + c), sh = __ldg(beta + g * cpg + c) - st.x * sc;
     float* row = base + (size_t)c * HW;
-    if (vec) {
-      float4* r4 = reinterpret_cast<float4*>(row);
-      for (int i = threadIdx.x; i < HW / 4; i += 512) {
-        float4 v = r4[i];
-        v.x = v.x * sc + sh; v.y = v.y * sc + sh; v.z = v.z * sc + sh; v.w = v.w * sc + sh;
-        r4[i] = v;
-      }
-    } else {
-      for (int i = threadIdx.x; i < HW; i += 512) row[i] = row[i] * sc + sh;
-    }
+    for (int i = threadIdx.x; i < HW; i += 512) row[i] = row[i] * sc + sh;
   }
 }
 
