@@ -88,6 +88,7 @@ struct DeviceInfo {
   bool mask_attr = false;
   bool pair_attr = false;
   bool dec_attr = false;
+  bool kmax_attr = false;
 };
 DeviceInfo g_dev[64];
 
@@ -1115,6 +1116,9 @@ int axvs_panoptic_inference(const float* mask_cls, const float* mask_pred, int N
 }
 
 // ---------------------------------------------------------------------------------------------- kMaX axial attention (row f3)
+static int g_kmax_tc = 0;   // measured: the split conversions per fragment make the mma.sync variant no faster than the SIMT kernel yet
+int axvs_set_kmax_tensor_cores(int on) { const int prev = g_kmax_tc; g_kmax_tc = on ? 1 : 0; return prev; }
+
 size_t axvs_kmax_axial_workspace_bytes(int images, int H, int W, int heads, int dk, int dv) {
   if (images <= 0 || H <= 0 || W <= 0 || heads <= 0 || dk <= 0 || dv <= 0) return 0;
   return align256((size_t)images * H * W * (size_t)(2 * heads * dk + heads * dv) * 4);
@@ -1135,7 +1139,10 @@ int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int 
   if (dk % 4 || dv % 4) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: per-head depths must be multiples of 4 (got %d, %d)", dk, dv);
   const int L = axis == 1 ? H : W;
   if (L > KA_MAX_L) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: axis length %d exceeds %d", L, KA_MAX_L);
-  const size_t smem = kmax_axial_smem_bytes(L, dk, dv);
+  // tensor-core variant (split-bf16 mma.sync) when its operand tiles fit; the fp32 SIMT kernel otherwise (axis lengths 49..64)
+  const size_t smem_tc = kmax_axial_tc_layout(L, dk, dv).floats * sizeof(float);
+  const bool use_tc = g_kmax_tc && L <= 48 && dk % 16 == 0 && dv % 8 == 0 && smem_tc <= 227 * 1024;
+  const size_t smem = use_tc ? smem_tc : kmax_axial_smem_bytes(L, dk, dv);
   if (smem > 227 * 1024) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: %zu bytes of shared memory needed (L=%d, dk=%d, dv=%d)", smem, L, dk, dv);
   const long long rows = (long long)images * H * W;
   if (rows > 0x7fffffffLL) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: too many pixels");
@@ -1167,22 +1174,23 @@ int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int 
   p.emb_q = w->emb_q; p.emb_k = w->emb_k; p.emb_v = w->emb_v;
   p.sim_s = w->sim_s; p.sim_t = w->sim_t; p.out_s = w->out_s; p.out_t = w->out_t;
   p.out = out;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kmax_axial_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return fail(AXVS_E_CUDA, "kmax_axial: cannot raise the shared-memory limit");
-    attr_set = true;
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (!d->kmax_attr) {                                  // per device, like the other kernels' opt-in shared-memory sizes
+    if (cudaFuncSetAttribute(kmax_axial_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(kmax_axial_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "kmax_axial: cannot raise the shared-memory limit: %s", cudaGetErrorString(cudaGetLastError()));
+    d->kmax_attr = true;
   }
   const int n_seq = images * (axis == 1 ? W : H);
   p.n_items = n_seq * heads;
-  DeviceInfo* d;
-  if (int rc = device_info(&d)) return rc;
   {
     ProfScope ps(KC_KMAXAX, (double)n_seq * heads * ((double)L * L * (6.0 * dk + 4.0 * dv)), (double)rows * (n_qkv + Vd) * 4.0, st);
     int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));          // resident CTAs per SM by shared memory (256 threads each)
     per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
     const int grid = p.n_items < d->sms * per_sm ? p.n_items : d->sms * per_sm;
-    kmax_axial_attn_kernel<<<grid, KA_THREADS, smem, st>>>(p);
+    if (use_tc) kmax_axial_tc_kernel<<<grid, KA_THREADS, smem, st>>>(p);
+    else kmax_axial_attn_kernel<<<grid, KA_THREADS, smem, st>>>(p);
   }
   AXVS_CHECK_LAUNCH("kmax_axial_attn_kernel");
   return AXVS_OK;

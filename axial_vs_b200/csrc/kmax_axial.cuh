@@ -14,6 +14,9 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "attn.cuh"   // mma_bf16_16816
+#include "ptx.cuh"    // pack_bf16x2 / unpack_bf16x2
+
 namespace axvs {
 
 constexpr int KA_MAX_L = 64;
@@ -180,6 +183,185 @@ __global__ void __launch_bounds__(KA_THREADS) kmax_axial_attn_kernel(const KmaxA
     }
   }
   __syncthreads();                                                 // q / k / v / weights are overwritten by the next item
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// Tensor-core variant (axis length <= 48): the five small contractions of one (sequence, head) item as mma.sync m16n8k16 tiles with
+// SPLIT bf16 operands (x = hi + lo, three MMAs per product: hi.hi + lo.hi + hi.lo), i.e. fp32-grade results from the bf16 tensor cores:
+//   S0 = Q K^T [L x L],  QR = Q Rq^T [L x R],  KR = K Rk^T [L x R]       (R = 2L - 1 relative distances)
+//   logits[l, m] = BN0(S0[l, m]) + BN1(QR[l, m - l + L - 1]) + BN2(KR[m, m - l + L - 1]),  w = softmax_m
+//   yc = W V [L x dv],  yr = W' RV [L x dv]  with  W'[l, r] = w[l, r + l - (L - 1)]  (zero outside the square), gathered by the A loads
+// Row strides are chosen so that the fragment loads are conflict-free: 8 floats modulo 32 banks for the K-contiguous operands (q, k, rq,
+// rk, w: 8-byte loads), 4 modulo 32 for v / rv (n-contiguous, two 4-byte loads per register).
+__host__ __device__ inline int ka_pad8(int n) { return n + ((8 - n % 32) + 32) % 32; }        // smallest m >= n with m % 32 == 8
+
+struct KaTcLayout { int ML, RT, pk, pv, LW, RW; size_t floats; };
+__host__ __device__ inline KaTcLayout kmax_axial_tc_layout(int L, int dk, int dv) {
+  KaTcLayout y;
+  y.ML = (L + 15) / 16 * 16;
+  y.RT = (2 * L - 1 + 15) / 16 * 16;
+  y.pk = ka_pad8(dk); y.pv = dv + 4; y.LW = ka_pad8(y.ML); y.RW = ka_pad8(y.RT);
+  y.floats = (size_t)2 * y.ML * y.pk + (size_t)y.ML * y.pv + (size_t)2 * y.RT * y.pk + (size_t)y.RT * y.pv + (size_t)y.ML * y.LW +
+             (size_t)2 * y.ML * y.RW;
+  return y;
+}
+
+__device__ __forceinline__ void ka_split(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(x, y);
+  const float2 h = unpack_bf16x2(hi);
+  lo = pack_bf16x2(x - h.x, y - h.y);
+}
+__device__ __forceinline__ void ka_mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
+                                        uint32_t bl0, uint32_t bl1) {
+  mma_bf16_16816(c, ah, bh0, bh1);
+  mma_bf16_16816(c, al, bh0, bh1);
+  mma_bf16_16816(c, ah, bl0, bl1);
+}
+
+__global__ void __launch_bounds__(KA_THREADS) kmax_axial_tc_kernel(const KmaxAxialParams p) {
+  extern __shared__ float ka_smem[];
+  const int L = p.L, dk = p.dk, dv = p.dv, R = 2 * L - 1;
+  const KaTcLayout y = kmax_axial_tc_layout(L, dk, dv);
+  const int ML = y.ML, RT = y.RT, pk = y.pk, pv = y.pv, LW = y.LW, RW = y.RW;
+  float* sq = ka_smem;                  // [ML][pk]   rows >= L stay zero
+  float* sk = sq + ML * pk;             // [ML][pk]
+  float* sv = sk + ML * pk;             // [ML][pv]
+  float* rq = sv + ML * pv;             // [RT][pk]   rows >= R stay zero
+  float* rk = rq + RT * pk;             // [RT][pk]
+  float* rv = rk + RT * pk;             // [RT][pv]
+  float* sw = rv + RT * pv;             // [ML][LW]   raw content scores, then the softmax weights; pad rows / columns are zero
+  float* sQR = sw + ML * LW;            // [ML][RW]
+  float* sKR = sQR + ML * RW;           // [ML][RW]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int Kd = p.heads * dk, Vd = p.heads * dv;
+
+  for (size_t e = tid; e < y.floats; e += KA_THREADS) ka_smem[e] = 0.f;
+  __syncthreads();
+  const int e0 = KA_MAX_SPAN - 1 - (L - 1);
+  for (int e = tid; e < R * (dk / 4); e += KA_THREADS) {
+    const int r = e / (dk / 4), d4 = e - r * (dk / 4);
+    reinterpret_cast<float4*>(rq + r * pk)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_q + (size_t)(e0 + r) * dk) + d4);
+    reinterpret_cast<float4*>(rk + r * pk)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_k + (size_t)(e0 + r) * dk) + d4);
+  }
+  for (int e = tid; e < R * (dv / 4); e += KA_THREADS) {
+    const int r = e / (dv / 4), d4 = e - r * (dv / 4);
+    reinterpret_cast<float4*>(rv + r * pv)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_v + (size_t)(e0 + r) * dv) + d4);
+  }
+
+  const int MT = ML / 16, NLt = (L + 7) / 8, NRt = (R + 7) / 8, NDt = dv / 8;
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    const int h = item % p.heads, s = item / p.heads;
+    const long long row0 = (long long)(s / p.seq_inner) * p.row_outer + (long long)(s % p.seq_inner) * p.row_inner;
+    for (int e = tid; e < L * (dk / 4); e += KA_THREADS) {
+      const int l = e / (dk / 4), d4 = e - l * (dk / 4);
+      const float* row = p.qkv + (size_t)(row0 + l * p.row_pos) * p.ld;
+      reinterpret_cast<float4*>(sq + l * pk)[d4] = __ldg(reinterpret_cast<const float4*>(row + h * dk) + d4);
+      reinterpret_cast<float4*>(sk + l * pk)[d4] = __ldg(reinterpret_cast<const float4*>(row + Kd + h * dk) + d4);
+    }
+    for (int e = tid; e < L * (dv / 4); e += KA_THREADS) {
+      const int l = e / (dv / 4), d4 = e - l * (dv / 4);
+      reinterpret_cast<float4*>(sv + l * pv)[d4] =
+          __ldg(reinterpret_cast<const float4*>(p.qkv + (size_t)(row0 + l * p.row_pos) * p.ld + 2 * Kd + h * dv) + d4);
+    }
+    __syncthreads();
+
+    // ---- S0, QR, KR: one 16 x 8 output tile per job
+    const int T0 = MT * NLt, T1 = MT * NRt;
+    for (int job = warp; job < T0 + 2 * T1; job += KA_THREADS / 32) {
+      int sel, i, j;
+      if (job < T0) { sel = 0; i = job / NLt; j = job - i * NLt; }
+      else { const int q = job - T0; sel = 1 + q / T1; const int rem = q - (sel - 1) * T1; i = rem / NRt; j = rem - i * NRt; }
+      const float* A = (sel == 2 ? sk : sq) + (i * 16 + g) * pk + 2 * t;
+      const float* B = (sel == 0 ? sk : sel == 1 ? rq : rk) + (j * 8 + g) * pk + 2 * t;
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int ks = 0; ks < dk / 16; ++ks) {
+        uint32_t ah[4], al[4], bh0, bh1, bl0, bl1;
+        const float2 a0 = *reinterpret_cast<const float2*>(A + ks * 16), a1 = *reinterpret_cast<const float2*>(A + 8 * pk + ks * 16);
+        const float2 a2 = *reinterpret_cast<const float2*>(A + ks * 16 + 8), a3 = *reinterpret_cast<const float2*>(A + 8 * pk + ks * 16 + 8);
+        const float2 b0 = *reinterpret_cast<const float2*>(B + ks * 16), b1 = *reinterpret_cast<const float2*>(B + ks * 16 + 8);
+        ka_split(a0.x, a0.y, ah[0], al[0]); ka_split(a1.x, a1.y, ah[1], al[1]);
+        ka_split(a2.x, a2.y, ah[2], al[2]); ka_split(a3.x, a3.y, ah[3], al[3]);
+        ka_split(b0.x, b0.y, bh0, bl0); ka_split(b1.x, b1.y, bh1, bl1);
+        ka_mma3(c, ah, al, bh0, bh1, bl0, bl1);
+      }
+      const int r0 = i * 16 + g, c0 = j * 8 + 2 * t;
+      if (sel == 0) {                                             // only inside the L x L square: the pads of sw must stay zero
+        if (r0 < L && c0 < L) sw[r0 * LW + c0] = c[0];
+        if (r0 < L && c0 + 1 < L) sw[r0 * LW + c0 + 1] = c[1];
+        if (r0 + 8 < L && c0 < L) sw[(r0 + 8) * LW + c0] = c[2];
+        if (r0 + 8 < L && c0 + 1 < L) sw[(r0 + 8) * LW + c0 + 1] = c[3];
+      } else {
+        float* o = (sel == 1 ? sQR : sKR) + r0 * RW + c0;
+        *reinterpret_cast<float2*>(o) = make_float2(c[0], c[1]);
+        *reinterpret_cast<float2*>(o + 8 * RW) = make_float2(c[2], c[3]);
+      }
+    }
+    __syncthreads();
+
+    // ---- combine the three similarities (each through its batch-norm affine) and softmax over m, one warp per row
+    const float s0 = p.sim_s[h], t0 = p.sim_t[h], s1 = p.sim_s[p.heads + h], t1 = p.sim_t[p.heads + h];
+    const float s2 = p.sim_s[2 * p.heads + h], t2 = p.sim_t[2 * p.heads + h];
+    for (int l = warp; l < L; l += KA_THREADS / 32) {
+      float* row = sw + l * LW;
+      float x[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int m = lane + 32 * u;
+        x[u] = m < L ? fmaf(row[m], s0, t0) + fmaf(sQR[l * RW + m - l + L - 1], s1, t1) + fmaf(sKR[m * RW + m - l + L - 1], s2, t2) : -INFINITY;
+      }
+      float mx = fmaxf(x[0], x[1]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+      const float y0 = lane < L ? expf(x[0] - mx) : 0.f, y1 = lane + 32 < L ? expf(x[1] - mx) : 0.f;
+      float sum = y0 + y1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+      const float inv = 1.f / sum;
+      if (lane < L) row[lane] = y0 * inv;
+      if (lane + 32 < L) row[lane + 32] = y1 * inv;
+    }
+    __syncthreads();
+
+    // ---- retrieval: yc = W V and yr = W' RV, one 16 x 8 output tile per job
+    const long long out0 = (long long)(s / p.seq_inner) * p.out_outer + (long long)(s % p.seq_inner) * p.out_inner;
+    for (int job = warp; job < MT * NDt; job += KA_THREADS / 32) {
+      const int i = job / NDt, j = job - i * NDt;
+      const int la = i * 16 + g, lb = la + 8, n = j * 8 + g;
+      float yc[4] = {0.f, 0.f, 0.f, 0.f}, yr[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int ks = 0; ks < ML / 16; ++ks) {
+        uint32_t ah[4], al[4], bh0, bh1, bl0, bl1;
+        const int kc = ks * 16 + 2 * t;
+        const float2 a0 = *reinterpret_cast<const float2*>(sw + la * LW + kc), a1 = *reinterpret_cast<const float2*>(sw + lb * LW + kc);
+        const float2 a2 = *reinterpret_cast<const float2*>(sw + la * LW + kc + 8), a3 = *reinterpret_cast<const float2*>(sw + lb * LW + kc + 8);
+        ka_split(a0.x, a0.y, ah[0], al[0]); ka_split(a1.x, a1.y, ah[1], al[1]);
+        ka_split(a2.x, a2.y, ah[2], al[2]); ka_split(a3.x, a3.y, ah[3], al[3]);
+        ka_split(sv[kc * pv + n], sv[(kc + 1) * pv + n], bh0, bl0);
+        ka_split(sv[(kc + 8) * pv + n], sv[(kc + 9) * pv + n], bh1, bl1);
+        ka_mma3(yc, ah, al, bh0, bh1, bl0, bl1);
+      }
+      auto wsh = [&](int l, int r) -> float {                      // W'[l, r]
+        const int m = r + l - (L - 1);
+        return (l < L && m >= 0 && m < L) ? sw[l * LW + m] : 0.f;
+      };
+      for (int ks = 0; ks < RT / 16; ++ks) {
+        uint32_t ah[4], al[4], bh0, bh1, bl0, bl1;
+        const int kc = ks * 16 + 2 * t;
+        ka_split(wsh(la, kc), wsh(la, kc + 1), ah[0], al[0]); ka_split(wsh(lb, kc), wsh(lb, kc + 1), ah[1], al[1]);
+        ka_split(wsh(la, kc + 8), wsh(la, kc + 9), ah[2], al[2]); ka_split(wsh(lb, kc + 8), wsh(lb, kc + 9), ah[3], al[3]);
+        ka_split(rv[kc * pv + n], rv[(kc + 1) * pv + n], bh0, bl0);
+        ka_split(rv[(kc + 8) * pv + n], rv[(kc + 9) * pv + n], bh1, bl1);
+        ka_mma3(yr, ah, al, bh0, bh1, bl0, bl1);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int l = la + (u >> 1) * 8, c = h * dv + j * 8 + 2 * t + (u & 1);
+        if (l < L)
+          p.out[out0 + (long long)c * p.out_chan + (long long)l * p.out_pos] =
+              fmaf(yc[u], p.out_s[c], p.out_t[c]) + fmaf(yr[u], p.out_s[Vd + c], p.out_t[Vd + c]);
+      }
+    }
+    __syncthreads();                                               // operands and weights are overwritten by the next item
   }
 }
 

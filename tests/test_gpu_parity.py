@@ -916,3 +916,26 @@ def test_kmax_axial_rejects_bad_arguments():
     m.train()
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 64, 9, device="cuda"))
+
+
+def test_kmax_axial_tensor_core_and_simt_paths_agree():
+    """The split-bf16 mma.sync attention core against the fp32 SIMT kernel (same GEMM in front): both fp32-grade."""
+    from axial_vs_b200 import _lib
+    from axial_vs_b200.kmax_axial import AxialAttention2D
+    N, C, H, W = 2, 128, 41, 23
+    m = AxialAttention2D(C, query_shape=[H, W]).eval()
+    m._height_axis.load_state_dict(synth.kmax_axial_params(71, C), strict=True)
+    m._width_axis.load_state_dict(synth.kmax_axial_params(72, 1024), strict=True)
+    m.cuda()
+    x = synth.randn(73, N, C, H, W).cuda()
+    lib = _lib.load()
+    try:
+        with torch.no_grad():
+            lib.axvs_set_kmax_tensor_cores(0)
+            a = m(x)
+            lib.axvs_set_kmax_tensor_cores(1)
+            b = m(x)
+        torch.cuda.synchronize()
+    finally:
+        lib.axvs_set_kmax_tensor_cores(0)
+    assert nerr(b, a) < 1e-4
