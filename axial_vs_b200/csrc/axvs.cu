@@ -1116,7 +1116,7 @@ int axvs_panoptic_inference(const float* mask_cls, const float* mask_pred, int N
 }
 
 // ---------------------------------------------------------------------------------------------- kMaX axial attention (row f3)
-static int g_kmax_tc = 0;   // measured: the split conversions per fragment make the mma.sync variant no faster than the SIMT kernel yet
+static int g_kmax_tc = 1;
 int axvs_set_kmax_tensor_cores(int on) { const int prev = g_kmax_tc; g_kmax_tc = on ? 1 : 0; return prev; }
 
 size_t axvs_kmax_axial_workspace_bytes(int images, int H, int W, int heads, int dk, int dv) {
@@ -1140,8 +1140,10 @@ int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int 
   const int L = axis == 1 ? H : W;
   if (L > KA_MAX_L) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: axis length %d exceeds %d", L, KA_MAX_L);
   // tensor-core variant (split-bf16 mma.sync) when its operand tiles fit; the fp32 SIMT kernel otherwise (axis lengths 49..64)
-  const size_t smem_tc = kmax_axial_tc_layout(L, dk, dv).floats * sizeof(float);
-  const bool use_tc = g_kmax_tc && L <= 48 && dk % 16 == 0 && dv % 8 == 0 && smem_tc <= 227 * 1024;
+  const size_t smem_tc = kmax_axial_tc_layout(L, dk, dv).words * sizeof(uint32_t);
+  // (its staging keeps two 16-byte pieces of q, k and of each V row pair per thread in registers; below 33 positions three SIMT CTAs per SM win)
+  const bool use_tc = g_kmax_tc && L > 32 && L <= 48 && dk % 16 == 0 && dv % 8 == 0 && smem_tc <= 227 * 1024 &&
+                      L * (dk / 4) <= 2 * KA_TC_THREADS && ((L + 15) / 16 * 8) * (dv / 4) <= 2 * KA_TC_THREADS;
   const size_t smem = use_tc ? smem_tc : kmax_axial_smem_bytes(L, dk, dv);
   if (smem > 227 * 1024) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: %zu bytes of shared memory needed (L=%d, dk=%d, dv=%d)", smem, L, dk, dv);
   const long long rows = (long long)images * H * W;
@@ -1189,7 +1191,7 @@ int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int 
     int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));          // resident CTAs per SM by shared memory (256 threads each)
     per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
     const int grid = p.n_items < d->sms * per_sm ? p.n_items : d->sms * per_sm;
-    if (use_tc) kmax_axial_tc_kernel<<<grid, KA_THREADS, smem, st>>>(p);
+    if (use_tc) kmax_axial_tc_kernel<<<grid, KA_TC_THREADS, smem, st>>>(p);
     else kmax_axial_attn_kernel<<<grid, KA_THREADS, smem, st>>>(p);
   }
   AXVS_CHECK_LAUNCH("kmax_axial_attn_kernel");

@@ -22,6 +22,7 @@ namespace axvs {
 constexpr int KA_MAX_L = 64;
 constexpr int KA_MAX_SPAN = 255;
 constexpr int KA_THREADS = 256;
+constexpr int KA_TC_THREADS = 512;     // tensor-core variant: 16 warps hide the fragment-load / mma latencies of the small tiles
 
 struct KmaxAxialParams {
   const float* qkv;            // fp32 token rows [rows, 2 * H * dk + H * dv]
@@ -191,19 +192,25 @@ __global__ void __launch_bounds__(KA_THREADS) kmax_axial_attn_kernel(const KmaxA
 // SPLIT bf16 operands (x = hi + lo, three MMAs per product: hi.hi + lo.hi + hi.lo), i.e. fp32-grade results from the bf16 tensor cores:
 //   S0 = Q K^T [L x L],  QR = Q Rq^T [L x R],  KR = K Rk^T [L x R]       (R = 2L - 1 relative distances)
 //   logits[l, m] = BN0(S0[l, m]) + BN1(QR[l, m - l + L - 1]) + BN2(KR[m, m - l + L - 1]),  w = softmax_m
-//   yc = W V [L x dv],  yr = W' RV [L x dv]  with  W'[l, r] = w[l, r + l - (L - 1)]  (zero outside the square), gathered by the A loads
-// Row strides are chosen so that the fragment loads are conflict-free: 8 floats modulo 32 banks for the K-contiguous operands (q, k, rq,
-// rk, w: 8-byte loads), 4 modulo 32 for v / rv (n-contiguous, two 4-byte loads per register).
+//   yc = W V [L x dv],  yr = W' RV [L x dv]  with  W'[l, r] = w[l, r + l - (L - 1)]  (zero outside the square)
+// Every operand is split ONCE when it is staged (the embedding tables once per CTA) into hi / lo images of packed bf16 pairs along the
+// contraction index (V and RV transposed, W' materialised by the softmax pass), so a fragment register is one 32-bit shared-memory load.
+// Row strides are odd multiples of 4 words: the (row g, word t) fragment pattern then covers the 32 banks exactly once.
+__host__ __device__ inline int ka_pad4o(int n) { return n + ((4 - n % 8) + 8) % 8; }          // smallest m >= n with m % 8 == 4
 __host__ __device__ inline int ka_pad8(int n) { return n + ((8 - n % 32) + 32) % 32; }        // smallest m >= n with m % 32 == 8
 
-struct KaTcLayout { int ML, RT, pk, pv, LW, RW; size_t floats; };
+struct KaTcLayout { int ML, RT, RB, SK, SM, SR, LW, RW; size_t x_words, words; };
 __host__ __device__ inline KaTcLayout kmax_axial_tc_layout(int L, int dk, int dv) {
   KaTcLayout y;
   y.ML = (L + 15) / 16 * 16;
-  y.RT = (2 * L - 1 + 15) / 16 * 16;
-  y.pk = ka_pad8(dk); y.pv = dv + 4; y.LW = ka_pad8(y.ML); y.RW = ka_pad8(y.RT);
-  y.floats = (size_t)2 * y.ML * y.pk + (size_t)y.ML * y.pv + (size_t)2 * y.RT * y.pk + (size_t)y.RT * y.pv + (size_t)y.ML * y.LW +
-             (size_t)2 * y.ML * y.RW;
+  y.RT = (2 * L - 1 + 15) / 16 * 16;                   // contraction length of W' RV
+  y.RB = (2 * L - 1 + 7) / 8 * 8;                      // rows of the rq / rk images (n-tiles of QR / KR)
+  y.SK = ka_pad4o(dk / 2); y.SM = ka_pad4o(y.ML / 2); y.SR = ka_pad4o(y.RT / 2);
+  y.LW = ka_pad8(y.ML); y.RW = ka_pad8(y.RB);
+  const size_t qr = (size_t)2 * y.ML * y.RW, vt = (size_t)2 * dv * y.SM;
+  y.x_words = qr > vt ? qr : vt;                       // QR | KR (fp32) during the logits, then V^T hi | lo
+  y.words = (size_t)4 * y.ML * y.SK + (size_t)4 * y.RB * y.SK + (size_t)2 * dv * y.SR + y.x_words + (size_t)2 * y.ML * y.SM +
+            (size_t)2 * y.ML * y.SR + (size_t)y.ML * y.LW;
   return y;
 }
 
@@ -212,85 +219,133 @@ __device__ __forceinline__ void ka_split(float x, float y, uint32_t& hi, uint32_
   const float2 h = unpack_bf16x2(hi);
   lo = pack_bf16x2(x - h.x, y - h.y);
 }
-__device__ __forceinline__ void ka_mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
-                                        uint32_t bl0, uint32_t bl1) {
-  mma_bf16_16816(c, ah, bh0, bh1);
-  mma_bf16_16816(c, al, bh0, bh1);
-  mma_bf16_16816(c, ah, bl0, bl1);
+// c += A B^T for one 16 x 8 tile over `ksteps` 16-wide steps; A / B are hi (and lo = + *_lo words further) images with row stride S
+__device__ __forceinline__ void ka_tile(float (&c)[4], const uint32_t* Ah, size_t a_lo, const uint32_t* Bh, size_t b_lo, int SA, int SB, int ksteps) {
+  float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};      // three independent accumulation chains
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint32_t* a = Ah + ks * 8;
+    const uint32_t* b = Bh + ks * 8;
+    const uint32_t ah[4] = {a[0], a[8 * SA], a[4], a[8 * SA + 4]};
+    const uint32_t al[4] = {a[a_lo], a[a_lo + 8 * SA], a[a_lo + 4], a[a_lo + 8 * SA + 4]};
+    const uint32_t bh0 = b[0], bh1 = b[4], bl0 = b[b_lo], bl1 = b[b_lo + 4];
+    mma_bf16_16816(c, ah, bh0, bh1);
+    mma_bf16_16816(c1, al, bh0, bh1);
+    mma_bf16_16816(c2, ah, bl0, bl1);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) c[u] += c1[u] + c2[u];
 }
 
-__global__ void __launch_bounds__(KA_THREADS) kmax_axial_tc_kernel(const KmaxAxialParams p) {
-  extern __shared__ float ka_smem[];
+__global__ void __launch_bounds__(KA_TC_THREADS) kmax_axial_tc_kernel(const KmaxAxialParams p) {
+  extern __shared__ uint32_t ka_words[];
   const int L = p.L, dk = p.dk, dv = p.dv, R = 2 * L - 1;
   const KaTcLayout y = kmax_axial_tc_layout(L, dk, dv);
-  const int ML = y.ML, RT = y.RT, pk = y.pk, pv = y.pv, LW = y.LW, RW = y.RW;
-  float* sq = ka_smem;                  // [ML][pk]   rows >= L stay zero
-  float* sk = sq + ML * pk;             // [ML][pk]
-  float* sv = sk + ML * pk;             // [ML][pv]
-  float* rq = sv + ML * pv;             // [RT][pk]   rows >= R stay zero
-  float* rk = rq + RT * pk;             // [RT][pk]
-  float* rv = rk + RT * pk;             // [RT][pv]
-  float* sw = rv + RT * pv;             // [ML][LW]   raw content scores, then the softmax weights; pad rows / columns are zero
-  float* sQR = sw + ML * LW;            // [ML][RW]
-  float* sKR = sQR + ML * RW;           // [ML][RW]
+  const int ML = y.ML, RT = y.RT, RB = y.RB, SK = y.SK, SM = y.SM, SR = y.SR, LW = y.LW, RW = y.RW;
+  // hi image first, lo image right behind it (same shape)
+  uint32_t* qh = ka_words;                         const size_t q_lo = (size_t)ML * SK;     // [ML][SK] x 2
+  uint32_t* kh = qh + 2 * q_lo;                                                              // [ML][SK] x 2
+  uint32_t* rqh = kh + 2 * q_lo;                   const size_t r_lo = (size_t)RB * SK;     // [RB][SK] x 2
+  uint32_t* rkh = rqh + 2 * r_lo;
+  uint32_t* rvh = rkh + 2 * r_lo;                  const size_t rv_lo = (size_t)dv * SR;    // RV^T [dv][SR] x 2
+  uint32_t* xw = rvh + 2 * rv_lo;                                                            // QR | KR fp32, then V^T hi | lo
+  float* sQR = reinterpret_cast<float*>(xw);
+  float* sKR = sQR + (size_t)ML * RW;
+  uint32_t* vth = xw;                              const size_t vt_lo = (size_t)dv * SM;    // V^T [dv][SM] x 2
+  uint32_t* wh = xw + y.x_words;                   const size_t w_lo = (size_t)ML * SM;     // W [ML][SM] x 2
+  uint32_t* wph = wh + 2 * w_lo;                   const size_t wp_lo = (size_t)ML * SR;    // W' [ML][SR] x 2
+  float* sw = reinterpret_cast<float*>(wph + 2 * wp_lo);                                     // [ML][LW] fp32 scores / weights
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int Kd = p.heads * dk, Vd = p.heads * dv;
 
-  for (size_t e = tid; e < y.floats; e += KA_THREADS) ka_smem[e] = 0.f;
+  for (size_t e = tid; e < y.words; e += KA_TC_THREADS) ka_words[e] = 0u;
   __syncthreads();
+  // ---- embedding tables, once per CTA: rq / rk rows as pairs along d; RV transposed as pairs along r
   const int e0 = KA_MAX_SPAN - 1 - (L - 1);
-  for (int e = tid; e < R * (dk / 4); e += KA_THREADS) {
+  for (int e = tid; e < R * (dk / 4); e += KA_TC_THREADS) {
     const int r = e / (dk / 4), d4 = e - r * (dk / 4);
-    reinterpret_cast<float4*>(rq + r * pk)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_q + (size_t)(e0 + r) * dk) + d4);
-    reinterpret_cast<float4*>(rk + r * pk)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_k + (size_t)(e0 + r) * dk) + d4);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.emb_q + (size_t)(e0 + r) * dk) + d4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.emb_k + (size_t)(e0 + r) * dk) + d4);
+    uint2 h, l;
+    ka_split(a.x, a.y, h.x, l.x); ka_split(a.z, a.w, h.y, l.y);
+    *reinterpret_cast<uint2*>(rqh + r * SK + 2 * d4) = h; *reinterpret_cast<uint2*>(rqh + r_lo + r * SK + 2 * d4) = l;
+    ka_split(b.x, b.y, h.x, l.x); ka_split(b.z, b.w, h.y, l.y);
+    *reinterpret_cast<uint2*>(rkh + r * SK + 2 * d4) = h; *reinterpret_cast<uint2*>(rkh + r_lo + r * SK + 2 * d4) = l;
   }
-  for (int e = tid; e < R * (dv / 4); e += KA_THREADS) {
-    const int r = e / (dv / 4), d4 = e - r * (dv / 4);
-    reinterpret_cast<float4*>(rv + r * pv)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_v + (size_t)(e0 + r) * dv) + d4);
+  for (int e = tid; e < (RT / 2) * (dv / 4); e += KA_TC_THREADS) {          // lanes = consecutive r pairs: conflict-free transposed stores
+    const int d4 = e / (RT / 2), rp = e - d4 * (RT / 2);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a = 2 * rp < R ? __ldg(reinterpret_cast<const float4*>(p.emb_v + (size_t)(e0 + 2 * rp) * dv) + d4) : z;
+    const float4 b = 2 * rp + 1 < R ? __ldg(reinterpret_cast<const float4*>(p.emb_v + (size_t)(e0 + 2 * rp + 1) * dv) + d4) : z;
+    uint32_t h, l;
+    ka_split(a.x, b.x, h, l); rvh[(4 * d4 + 0) * SR + rp] = h; rvh[rv_lo + (4 * d4 + 0) * SR + rp] = l;
+    ka_split(a.y, b.y, h, l); rvh[(4 * d4 + 1) * SR + rp] = h; rvh[rv_lo + (4 * d4 + 1) * SR + rp] = l;
+    ka_split(a.z, b.z, h, l); rvh[(4 * d4 + 2) * SR + rp] = h; rvh[rv_lo + (4 * d4 + 2) * SR + rp] = l;
+    ka_split(a.w, b.w, h, l); rvh[(4 * d4 + 3) * SR + rp] = h; rvh[rv_lo + (4 * d4 + 3) * SR + rp] = l;
   }
 
-  const int MT = ML / 16, NLt = (L + 7) / 8, NRt = (R + 7) / 8, NDt = dv / 8;
+  const int MT = ML / 16, NLt = (L + 7) / 8, NRt = RB / 8, NDt = dv / 8, MP = ML / 2;
+  float4 pq[2], pk_[2];                                            // next item's q / k slices (two 16-byte pieces per thread)
+  auto prefetch_qk = [&](int it) {
+    const int hh = it % p.heads, ss = it / p.heads;
+    const long long r0 = (long long)(ss / p.seq_inner) * p.row_outer + (long long)(ss % p.seq_inner) * p.row_inner;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + u * KA_TC_THREADS;
+      if (e < L * (dk / 4)) {
+        const int l = e / (dk / 4), d4 = e - l * (dk / 4);
+        const float* row = p.qkv + (size_t)(r0 + l * p.row_pos) * p.ld;
+        pq[u] = __ldg(reinterpret_cast<const float4*>(row + hh * dk) + d4);
+        pk_[u] = __ldg(reinterpret_cast<const float4*>(row + Kd + hh * dk) + d4);
+      }
+    }
+  };
+  if ((int)blockIdx.x < p.n_items) prefetch_qk(blockIdx.x);
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
     const int h = item % p.heads, s = item / p.heads;
     const long long row0 = (long long)(s / p.seq_inner) * p.row_outer + (long long)(s % p.seq_inner) * p.row_inner;
-    for (int e = tid; e < L * (dk / 4); e += KA_THREADS) {
-      const int l = e / (dk / 4), d4 = e - l * (dk / 4);
-      const float* row = p.qkv + (size_t)(row0 + l * p.row_pos) * p.ld;
-      reinterpret_cast<float4*>(sq + l * pk)[d4] = __ldg(reinterpret_cast<const float4*>(row + h * dk) + d4);
-      reinterpret_cast<float4*>(sk + l * pk)[d4] = __ldg(reinterpret_cast<const float4*>(row + Kd + h * dk) + d4);
-    }
-    for (int e = tid; e < L * (dv / 4); e += KA_THREADS) {
-      const int l = e / (dv / 4), d4 = e - l * (dv / 4);
-      reinterpret_cast<float4*>(sv + l * pv)[d4] =
-          __ldg(reinterpret_cast<const float4*>(p.qkv + (size_t)(row0 + l * p.row_pos) * p.ld + 2 * Kd + h * dv) + d4);
+    // q / k of this item were prefetched into registers during the previous item's retrieval: split and store them now
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + u * KA_TC_THREADS;
+      if (e < L * (dk / 4)) {
+        const int l = e / (dk / 4), d4 = e - l * (dk / 4);
+        uint2 hh, ll;
+        ka_split(pq[u].x, pq[u].y, hh.x, ll.x); ka_split(pq[u].z, pq[u].w, hh.y, ll.y);
+        *reinterpret_cast<uint2*>(qh + l * SK + 2 * d4) = hh; *reinterpret_cast<uint2*>(qh + q_lo + l * SK + 2 * d4) = ll;
+        ka_split(pk_[u].x, pk_[u].y, hh.x, ll.x); ka_split(pk_[u].z, pk_[u].w, hh.y, ll.y);
+        *reinterpret_cast<uint2*>(kh + l * SK + 2 * d4) = hh; *reinterpret_cast<uint2*>(kh + q_lo + l * SK + 2 * d4) = ll;
+      }
     }
     __syncthreads();
+    // V of this item: issued now, consumed after the softmax (two rows of a pair per register set)
+    float4 va[2], vb[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + u * KA_TC_THREADS;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      va[u] = z; vb[u] = z;
+      if (e < MP * (dv / 4)) {
+        const int d4 = e / MP, mp = e - d4 * MP;
+        const float* base = p.qkv + 2 * Kd + h * dv;
+        if (2 * mp < L) va[u] = __ldg(reinterpret_cast<const float4*>(base + (size_t)(row0 + (2 * mp) * p.row_pos) * p.ld) + d4);
+        if (2 * mp + 1 < L) vb[u] = __ldg(reinterpret_cast<const float4*>(base + (size_t)(row0 + (2 * mp + 1) * p.row_pos) * p.ld) + d4);
+      }
+    }
 
     // ---- S0, QR, KR: one 16 x 8 output tile per job
     const int T0 = MT * NLt, T1 = MT * NRt;
-    for (int job = warp; job < T0 + 2 * T1; job += KA_THREADS / 32) {
+    for (int job = warp; job < T0 + 2 * T1; job += KA_TC_THREADS / 32) {
       int sel, i, j;
       if (job < T0) { sel = 0; i = job / NLt; j = job - i * NLt; }
       else { const int q = job - T0; sel = 1 + q / T1; const int rem = q - (sel - 1) * T1; i = rem / NRt; j = rem - i * NRt; }
-      const float* A = (sel == 2 ? sk : sq) + (i * 16 + g) * pk + 2 * t;
-      const float* B = (sel == 0 ? sk : sel == 1 ? rq : rk) + (j * 8 + g) * pk + 2 * t;
       float c[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int ks = 0; ks < dk / 16; ++ks) {
-        uint32_t ah[4], al[4], bh0, bh1, bl0, bl1;
-        const float2 a0 = *reinterpret_cast<const float2*>(A + ks * 16), a1 = *reinterpret_cast<const float2*>(A + 8 * pk + ks * 16);
-        const float2 a2 = *reinterpret_cast<const float2*>(A + ks * 16 + 8), a3 = *reinterpret_cast<const float2*>(A + 8 * pk + ks * 16 + 8);
-        const float2 b0 = *reinterpret_cast<const float2*>(B + ks * 16), b1 = *reinterpret_cast<const float2*>(B + ks * 16 + 8);
-        ka_split(a0.x, a0.y, ah[0], al[0]); ka_split(a1.x, a1.y, ah[1], al[1]);
-        ka_split(a2.x, a2.y, ah[2], al[2]); ka_split(a3.x, a3.y, ah[3], al[3]);
-        ka_split(b0.x, b0.y, bh0, bl0); ka_split(b1.x, b1.y, bh1, bl1);
-        ka_mma3(c, ah, al, bh0, bh1, bl0, bl1);
-      }
+      const uint32_t* A = (sel == 2 ? kh : qh) + (i * 16 + g) * SK + t;
+      if (sel == 0) ka_tile(c, A, q_lo, kh + (j * 8 + g) * SK + t, q_lo, SK, SK, dk / 16);
+      else ka_tile(c, A, q_lo, (sel == 1 ? rqh : rkh) + (j * 8 + g) * SK + t, r_lo, SK, SK, dk / 16);
       const int r0 = i * 16 + g, c0 = j * 8 + 2 * t;
-      if (sel == 0) {                                             // only inside the L x L square: the pads of sw must stay zero
-        if (r0 < L && c0 < L) sw[r0 * LW + c0] = c[0];
-        if (r0 < L && c0 + 1 < L) sw[r0 * LW + c0 + 1] = c[1];
-        if (r0 + 8 < L && c0 < L) sw[(r0 + 8) * LW + c0] = c[2];
-        if (r0 + 8 < L && c0 + 1 < L) sw[(r0 + 8) * LW + c0 + 1] = c[3];
+      if (sel == 0) {
+        *reinterpret_cast<float2*>(sw + r0 * LW + c0) = make_float2(c[0], c[1]);
+        *reinterpret_cast<float2*>(sw + (r0 + 8) * LW + c0) = make_float2(c[2], c[3]);
       } else {
         float* o = (sel == 1 ? sQR : sKR) + r0 * RW + c0;
         *reinterpret_cast<float2*>(o) = make_float2(c[0], c[1]);
@@ -299,10 +354,10 @@ __global__ void __launch_bounds__(KA_THREADS) kmax_axial_tc_kernel(const KmaxAxi
     }
     __syncthreads();
 
-    // ---- combine the three similarities (each through its batch-norm affine) and softmax over m, one warp per row
+    // ---- combine the three similarities (each through its batch-norm affine), softmax over m, and write W / W' as split pair images
     const float s0 = p.sim_s[h], t0 = p.sim_t[h], s1 = p.sim_s[p.heads + h], t1 = p.sim_t[p.heads + h];
     const float s2 = p.sim_s[2 * p.heads + h], t2 = p.sim_t[2 * p.heads + h];
-    for (int l = warp; l < L; l += KA_THREADS / 32) {
+    for (int l = warp; l < L; l += KA_TC_THREADS / 32) {
       float* row = sw + l * LW;
       float x[2];
 #pragma unroll
@@ -318,47 +373,58 @@ __global__ void __launch_bounds__(KA_THREADS) kmax_axial_tc_kernel(const KmaxAxi
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
       const float inv = 1.f / sum;
-      if (lane < L) row[lane] = y0 * inv;
-      if (lane + 32 < L) row[lane + 32] = y1 * inv;
+      __syncwarp();
+      row[lane] = y0 * inv;                                        // lanes >= L write zeros: LW >= 64 is not guaranteed, ML + 8 is
+      if (lane + 32 < LW) row[lane + 32] = y1 * inv;
+      __syncwarp();
+      auto wat = [&](int m) -> float { return (m >= 0 && m < L) ? row[m] : 0.f; };
+      for (int jp = lane; jp < MP; jp += 32) {                     // W pairs (2 jp, 2 jp + 1)
+        uint32_t hh, ll;
+        ka_split(wat(2 * jp), wat(2 * jp + 1), hh, ll);
+        wh[l * SM + jp] = hh; wh[w_lo + l * SM + jp] = ll;
+      }
+      for (int jp = lane; jp < RT / 2; jp += 32) {                 // W' pairs: r = 2 jp, m = r + l - (L - 1)
+        const int m = 2 * jp + l - (L - 1);
+        uint32_t hh, ll;
+        ka_split(wat(m), wat(m + 1), hh, ll);
+        wph[l * SR + jp] = hh; wph[wp_lo + l * SR + jp] = ll;
+      }
     }
+    __syncthreads();                                               // QR / KR are dead: their area becomes V^T
+
+    // ---- V^T hi | lo from the registers: lanes = consecutive m pairs (conflict-free transposed stores)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + u * KA_TC_THREADS;
+      if (e < MP * (dv / 4)) {
+        const int d4 = e / MP, mp = e - d4 * MP;
+        const float4 a = va[u], b = vb[u];
+        uint32_t hh, ll;
+        ka_split(a.x, b.x, hh, ll); vth[(4 * d4 + 0) * SM + mp] = hh; vth[vt_lo + (4 * d4 + 0) * SM + mp] = ll;
+        ka_split(a.y, b.y, hh, ll); vth[(4 * d4 + 1) * SM + mp] = hh; vth[vt_lo + (4 * d4 + 1) * SM + mp] = ll;
+        ka_split(a.z, b.z, hh, ll); vth[(4 * d4 + 2) * SM + mp] = hh; vth[vt_lo + (4 * d4 + 2) * SM + mp] = ll;
+        ka_split(a.w, b.w, hh, ll); vth[(4 * d4 + 3) * SM + mp] = hh; vth[vt_lo + (4 * d4 + 3) * SM + mp] = ll;
+      }
+    }
+    if (item + (int)gridDim.x < p.n_items) prefetch_qk(item + gridDim.x);      // lands while this item's retrieval runs
     __syncthreads();
 
     // ---- retrieval: yc = W V and yr = W' RV, one 16 x 8 output tile per job
     const long long out0 = (long long)(s / p.seq_inner) * p.out_outer + (long long)(s % p.seq_inner) * p.out_inner;
-    for (int job = warp; job < MT * NDt; job += KA_THREADS / 32) {
+    for (int job = warp; job < MT * NDt; job += KA_TC_THREADS / 32) {
       const int i = job / NDt, j = job - i * NDt;
-      const int la = i * 16 + g, lb = la + 8, n = j * 8 + g;
       float yc[4] = {0.f, 0.f, 0.f, 0.f}, yr[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int ks = 0; ks < ML / 16; ++ks) {
-        uint32_t ah[4], al[4], bh0, bh1, bl0, bl1;
-        const int kc = ks * 16 + 2 * t;
-        const float2 a0 = *reinterpret_cast<const float2*>(sw + la * LW + kc), a1 = *reinterpret_cast<const float2*>(sw + lb * LW + kc);
-        const float2 a2 = *reinterpret_cast<const float2*>(sw + la * LW + kc + 8), a3 = *reinterpret_cast<const float2*>(sw + lb * LW + kc + 8);
-        ka_split(a0.x, a0.y, ah[0], al[0]); ka_split(a1.x, a1.y, ah[1], al[1]);
-        ka_split(a2.x, a2.y, ah[2], al[2]); ka_split(a3.x, a3.y, ah[3], al[3]);
-        ka_split(sv[kc * pv + n], sv[(kc + 1) * pv + n], bh0, bl0);
-        ka_split(sv[(kc + 8) * pv + n], sv[(kc + 9) * pv + n], bh1, bl1);
-        ka_mma3(yc, ah, al, bh0, bh1, bl0, bl1);
-      }
-      auto wsh = [&](int l, int r) -> float {                      // W'[l, r]
-        const int m = r + l - (L - 1);
-        return (l < L && m >= 0 && m < L) ? sw[l * LW + m] : 0.f;
-      };
-      for (int ks = 0; ks < RT / 16; ++ks) {
-        uint32_t ah[4], al[4], bh0, bh1, bl0, bl1;
-        const int kc = ks * 16 + 2 * t;
-        ka_split(wsh(la, kc), wsh(la, kc + 1), ah[0], al[0]); ka_split(wsh(lb, kc), wsh(lb, kc + 1), ah[1], al[1]);
-        ka_split(wsh(la, kc + 8), wsh(la, kc + 9), ah[2], al[2]); ka_split(wsh(lb, kc + 8), wsh(lb, kc + 9), ah[3], al[3]);
-        ka_split(rv[kc * pv + n], rv[(kc + 1) * pv + n], bh0, bl0);
-        ka_split(rv[(kc + 8) * pv + n], rv[(kc + 9) * pv + n], bh1, bl1);
-        ka_mma3(yr, ah, al, bh0, bh1, bl0, bl1);
-      }
+      const int cb = h * dv + j * 8 + 2 * t;                       // this thread's two channels; their affines load under the MMAs
+      const float2 osc = *reinterpret_cast<const float2*>(p.out_s + cb), otc = *reinterpret_cast<const float2*>(p.out_t + cb);
+      const float2 osr = *reinterpret_cast<const float2*>(p.out_s + Vd + cb), otr = *reinterpret_cast<const float2*>(p.out_t + Vd + cb);
+      ka_tile(yc, wh + (i * 16 + g) * SM + t, w_lo, vth + (j * 8 + g) * SM + t, vt_lo, SM, SM, ML / 16);
+      ka_tile(yr, wph + (i * 16 + g) * SR + t, wp_lo, rvh + (j * 8 + g) * SR + t, rv_lo, SR, SR, RT / 16);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int l = la + (u >> 1) * 8, c = h * dv + j * 8 + 2 * t + (u & 1);
+        const int l = i * 16 + g + (u >> 1) * 8, c = h * dv + j * 8 + 2 * t + (u & 1);
         if (l < L)
           p.out[out0 + (long long)c * p.out_chan + (long long)l * p.out_pos] =
-              fmaf(yc[u], p.out_s[c], p.out_t[c]) + fmaf(yr[u], p.out_s[Vd + c], p.out_t[Vd + c]);
+              (u & 1) ? fmaf(yc[u], osc.y, otc.y) + fmaf(yr[u], osr.y, otr.y) : fmaf(yc[u], osc.x, otc.x) + fmaf(yr[u], osr.x, otr.x);
       }
     }
     __syncthreads();                                               // operands and weights are overwritten by the next item

@@ -261,8 +261,8 @@ typedef struct axvs_kmax_axial_weights {
  * along H (the `_height_axis` of AxialAttention2D, :179-182; also the 1-D module on [N, C, L] with H = L, W = 1); axis 2: one per
  * (image, h) along W (:184-187).  out: out_layout 0 = NCHW [images, heads*dv, H, W], 1 = token rows [images*H*W, heads*dv] (what the
  * next axis consumes: the reference's permutes at :183 and :188 are folded into these layouts).  Axis length <= 64. */
-/* 1: the attention core runs on the tensor cores (split-bf16 mma.sync, axis length <= 48; validated, same accuracy, not faster yet);
- * 0 (default): the fp32 SIMT kernel.  Returns the previous setting. */
+/* 1 (default): axes of 33..48 positions run their attention core on the tensor cores (split-bf16 mma.sync, same accuracy, 1.8x faster at
+ * 41 positions); 0: always the fp32 SIMT kernel (the validation baseline; also used for <= 32 and 49..64 positions).  Returns the previous setting. */
 int axvs_set_kmax_tensor_cores(int on);
 size_t axvs_kmax_axial_workspace_bytes(int images, int H, int W, int heads, int dk, int dv);
 int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int H, int W, int axis, const axvs_kmax_axial_weights* w,

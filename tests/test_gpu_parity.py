@@ -937,5 +937,5 @@ def test_kmax_axial_tensor_core_and_simt_paths_agree():
             b = m(x)
         torch.cuda.synchronize()
     finally:
-        lib.axvs_set_kmax_tensor_cores(0)
+        lib.axvs_set_kmax_tensor_cores(1)
     assert nerr(b, a) < 1e-4

@@ -1,10 +1,12 @@
 """Debug: parity error and time of the kMaX AxialAttention2D drop-in (row f3) at the R50 641x641 shapes (84 frames, 512 channels).
-usage: python tools/debug/bench_kmax.py"""
+usage: python tools/debug/bench_kmax.py [simt]    (simt: the fp32 SIMT attention core everywhere instead of mma.sync for 33..48 positions)"""
 import sys, torch
 sys.path.insert(0, ".")
 from axial_vs_b200 import synth, ops
 from axial_vs_b200.kmax_axial import AxialAttention2D
 from oracle import kmax_oracle as KO          # checker only (debug tool)
+from axial_vs_b200 import _lib
+_lib.load().axvs_set_kmax_tensor_cores(0 if 'simt' in sys.argv[1:] else 1)
 
 for N, C, H, W in [(84, 512, 21, 21), (84, 512, 41, 41)]:
     ph, pw = synth.kmax_axial_params(1, C), synth.kmax_axial_params(2, 1024)
