@@ -83,7 +83,7 @@ SIGNATURES = {
     "axvs_msda_layer_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, POINTER(c_int), c_void_p, POINTER(MsdaWeights), c_int, c_int, c_void_p, c_size_t,
                                     c_void_p]),
     "axvs_set_kmax_tensor_cores": (c_int, [c_int]),
-    "axvs_kmax_axial_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "axvs_kmax_axial_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "axvs_kmax_axial_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(KmaxAxialWeights), c_void_p, c_int, c_void_p, c_size_t,
                                     c_void_p]),
     "axvs_panoptic_workspace_bytes": (c_size_t, [c_int, ctypes.c_longlong]),

@@ -1119,9 +1119,10 @@ int axvs_panoptic_inference(const float* mask_cls, const float* mask_pred, int N
 static int g_kmax_tc = 1;
 int axvs_set_kmax_tensor_cores(int on) { const int prev = g_kmax_tc; g_kmax_tc = on ? 1 : 0; return prev; }
 
-size_t axvs_kmax_axial_workspace_bytes(int images, int H, int W, int heads, int dk, int dv) {
-  if (images <= 0 || H <= 0 || W <= 0 || heads <= 0 || dk <= 0 || dv <= 0) return 0;
-  return align256((size_t)images * H * W * (size_t)(2 * heads * dk + heads * dv) * 4);
+size_t axvs_kmax_axial_workspace_bytes(int images, int c_in, int H, int W, int heads, int dk, int dv) {
+  if (images <= 0 || c_in <= 0 || H <= 0 || W <= 0 || heads <= 0 || dk <= 0 || dv <= 0) return 0;
+  const size_t rows = (size_t)images * H * W;
+  return align256(rows * (size_t)(2 * heads * dk + heads * dv) * 4) + align256(rows * 2 * (size_t)c_in * 2);      // qkv fp32 | A bf16 [hi | lo]
 }
 
 int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int H, int W, int axis, const axvs_kmax_axial_weights* w,
@@ -1131,6 +1132,7 @@ int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int 
     return fail(AXVS_E_INVALID, "kmax_axial: null weight pointer");
   if (images <= 0 || c_in <= 0 || H <= 0 || W <= 0) return fail(AXVS_E_INVALID, "kmax_axial: sizes must be positive");
   if (axis != 1 && axis != 2) return fail(AXVS_E_INVALID, "kmax_axial: axis must be 1 (height) or 2 (width)");
+  if (images > 65535) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: at most 65535 images per call");
   if ((x_layout != 0 && x_layout != 1) || (out_layout != 0 && out_layout != 1)) return fail(AXVS_E_INVALID, "kmax_axial: bad layout code");
   const int heads = w->heads, dk = w->dk, dv = w->dv;
   const int n_qkv = 2 * heads * dk + heads * dv, Vd = heads * dv;
@@ -1148,17 +1150,23 @@ int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int 
   if (smem > 227 * 1024) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: %zu bytes of shared memory needed (L=%d, dk=%d, dv=%d)", smem, L, dk, dv);
   const long long rows = (long long)images * H * W;
   if (rows > 0x7fffffffLL) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: too many pixels");
-  const size_t need = axvs_kmax_axial_workspace_bytes(images, H, W, heads, dk, dv);
+  const size_t need = axvs_kmax_axial_workspace_bytes(images, c_in, H, W, heads, dk, dv);
   if (workspace_bytes < need) return fail(AXVS_E_WORKSPACE, "kmax_axial: workspace %zu < required %zu", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   float* qkv = reinterpret_cast<float*>(workspace);
   // qkv = BN(conv1x1(x)): the batch norm is folded into the packed weight rows and the bias      kmax_pixel_decoder.py:130
   // Split precision (a_split): the packed weight is [W_hi | W_hi | W_lo] over 3 c_in columns; a softmax over sums of 64 products of these
-  // outputs follows, and plain bf16 operands left 1.5e-2 of error after the two chained passes of AxialAttention2D.
-  GemmParams g = gemm_params(nullptr, c_in, (int)rows, 3 * c_in, w->w_qkv, n_qkv, 0, w->b_qkv, n_qkv, 1.f, 0, qkv, n_qkv, 0, 0, nullptr);
+  // outputs follows, and plain bf16 operands left 1.5e-2 of error after the two chained passes of AxialAttention2D.  The activations are
+  // split once into bf16 [hi | lo] token rows (the NCHW -> token-row transpose rides along), then a plain bf16-A GEMM reads them.
+  __nv_bfloat16* a_split = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + align256((size_t)rows * n_qkv * 4));
+  {
+    ProfScope ps(KC_KMAXAX, 0, (double)rows * c_in * 8.0, st);
+    if (x_layout == 0) kmax_split_nchw_kernel<<<dim3((H * W + 31) / 32, c_in / 64, images), 256, 0, st>>>(x, a_split, c_in, H * W);
+    else kmax_split_rows_kernel<<<(unsigned)((rows * (c_in / 4) + 255) / 256), 256, 0, st>>>(x, a_split, rows, c_in);
+  }
+  AXVS_CHECK_LAUNCH("kmax_split kernels");
+  GemmParams g = gemm_params(a_split, 2 * c_in, (int)rows, 3 * c_in, w->w_qkv, n_qkv, 0, w->b_qkv, n_qkv, 1.f, 0, qkv, n_qkv, 0, 0, nullptr);
   g.a_split = 1;
-  if (x_layout == 0) { g.a_diag = 3; g.A32 = x; g.a_n = H * W; }
-  else { g.a_diag = 4; g.A32 = x; }
   if (int rc = launch_gemm(g, st)) return rc;
   KmaxAxialParams p;
   p.qkv = qkv; p.ld = n_qkv; p.L = L; p.heads = heads; p.dk = dk; p.dv = dv;

@@ -86,7 +86,7 @@ struct GemmParams {
                 //    eight 4-byte loads at a stride of a_n floats -> one 16-byte chunk of the K-major image)
                 // 4: A32 is an fp32 row-major matrix [M, lda] (token rows), converted to bf16 on the fly
   int a_N, a_n, a_F;
-  int a_split;  // modes 3 / 4 only: 1 = split-precision product.  K counts 3 x the source channels: K-blocks [0, K/3) and [2K/3, K) carry
+  int a_split;  // 1 = split-precision product (modes 3 / 4: fp32 source split by the producers; mode 0: A = bf16 [hi | lo], see the producer).  K counts 3 x the source channels: K-blocks [0, K/3) and [2K/3, K) carry
                 //   hi = bf16(a), K-blocks [K/3, 2K/3) carry lo = bf16(a - hi); with weights packed as [hi | hi | lo] the accumulator
                 //   holds a_hi w_hi + a_lo w_hi + a_hi w_lo, i.e. the fp32 product to ~2^-17 (kmax_axial: a softmax sits behind this GEMM)
   const float* A32;
@@ -419,7 +419,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
             t2 = t2 < 0 ? 0 : (t2 >= p.a_N ? p.a_N - 1 : t2);
             v[i] = rowp[i] ? ldg_nc_v4(rowp[i] + (ptrdiff_t)(t2 - tstep[i]) * p.a_n * p.lda + (kb & 3) * GEMM_BK) : make_uint4(0, 0, 0, 0);
           } else {
-            v[i] = rowp[i] ? ldg_nc_v4(rowp[i] + kb * GEMM_BK) : make_uint4(0, 0, 0, 0);
+            // a_split with a bf16 source: A holds [hi | lo] (2 x K/3 columns); K-blocks of the middle third read the lo half
+            const int nk3 = num_kb / 3;
+            const int kcol = p.a_split ? ((kb / nk3 == 1 ? nk3 : 0) + kb % nk3) * GEMM_BK : kb * GEMM_BK;
+            v[i] = rowp[i] ? ldg_nc_v4(rowp[i] + kcol) : make_uint4(0, 0, 0, 0);
           }
         }
         mbar_wait(&empty_bar[stage], phase ^ 1);

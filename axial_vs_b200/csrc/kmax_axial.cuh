@@ -42,6 +42,41 @@ struct KmaxAxialParams {
   long long out_outer, out_inner, out_chan, out_pos;
 };
 
+// fp32 activations -> bf16 [rows][hi (K) | lo (K)] token rows: the A operand of the split-precision qkv GEMM, converted ONCE (the GEMM's
+// converting producers would redo it for each of the eight 256-column chunks of the 2048 outputs).
+// Token-row source: one thread per four channels.
+__global__ void __launch_bounds__(256) kmax_split_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int K) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= rows * (K / 4)) return;
+  const long long r = e / (K / 4);
+  const int c4 = (int)(e - r * (K / 4));
+  const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * K) + c4);
+  uint2 h, l;
+  h.x = pack_bf16x2(v.x, v.y); h.y = pack_bf16x2(v.z, v.w);
+  const float2 h0 = unpack_bf16x2(h.x), h1 = unpack_bf16x2(h.y);
+  l.x = pack_bf16x2(v.x - h0.x, v.y - h0.y); l.y = pack_bf16x2(v.z - h1.x, v.w - h1.y);
+  uint2* o = reinterpret_cast<uint2*>(out + r * 2 * K);
+  o[c4] = h;
+  o[K / 4 + c4] = l;
+}
+// NCHW source [images][K][HW]: a 64-channel x 32-pixel tile goes through shared memory (reads along pixels, writes along channels).
+__global__ void __launch_bounds__(256) kmax_split_nchw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int K, int HW) {
+  __shared__ float tile[64][33];
+  const int img = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int c = w; c < 64; c += 8) tile[c][lane] = p0 + lane < HW ? __ldg(x + ((size_t)img * K + c0 + c) * HW + p0 + lane) : 0.f;
+  __syncthreads();
+  for (int px = w; px < 32; px += 8) {
+    if (p0 + px >= HW) break;
+    const float a = tile[2 * lane][px], b = tile[2 * lane + 1][px];
+    const uint32_t h = pack_bf16x2(a, b);
+    const float2 hf = unpack_bf16x2(h);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + ((size_t)img * HW + p0 + px) * 2 * K);
+    o[c0 / 2 + lane] = h;
+    o[(K + c0) / 2 + lane] = pack_bf16x2(a - hf.x, b - hf.y);
+  }
+}
+
 __host__ __device__ inline size_t kmax_axial_smem_bytes(int L, int dk, int dv) {
   const int pk = dk + 4, pv = dv + 4, R = 2 * L - 1;
   return sizeof(float) * ((size_t)2 * L * pk + (size_t)L * pv + (size_t)2 * R * pk + (size_t)R * pv + (size_t)L * (L + 1));

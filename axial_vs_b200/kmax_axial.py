@@ -94,7 +94,7 @@ class AxialAttention(nn.Module):
         Vd, heads = self._total_value_depth, self._num_heads
         out = torch.empty((images, Vd, H, W) if out_layout == 0 else (images * H * W, Vd), dtype=torch.float32, device=x.device)
         lib = _lib.load()
-        nbytes = lib.axvs_kmax_axial_workspace_bytes(images, H, W, heads, self._key_depth_per_head, Vd // heads)
+        nbytes = lib.axvs_kmax_axial_workspace_bytes(images, self._in_planes, H, W, heads, self._key_depth_per_head, Vd // heads)
         with torch.cuda.device(x.device):
             ws = ops.workspace(nbytes, x.device)
             st = self._struct(pk)

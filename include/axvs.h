@@ -264,7 +264,7 @@ typedef struct axvs_kmax_axial_weights {
 /* 1 (default): axes of 33..48 positions run their attention core on the tensor cores (split-bf16 mma.sync, same accuracy, 1.8x faster at
  * 41 positions); 0: always the fp32 SIMT kernel (the validation baseline; also used for <= 32 and 49..64 positions).  Returns the previous setting. */
 int axvs_set_kmax_tensor_cores(int on);
-size_t axvs_kmax_axial_workspace_bytes(int images, int H, int W, int heads, int dk, int dv);
+size_t axvs_kmax_axial_workspace_bytes(int images, int c_in, int H, int W, int heads, int dk, int dv);
 int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int H, int W, int axis, const axvs_kmax_axial_weights* w,
                         float* out, int out_layout, void* workspace, size_t workspace_bytes, axvs_stream_t stream);
 
