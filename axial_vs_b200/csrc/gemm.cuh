@@ -410,8 +410,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
           rowp[i] = nullptr;
         }
       }
-      for (int kb = 0; kb < num_kb; ++kb) {
-        uint4 v[ITERS];
+      // two register sets: the loads of K-block kb + 1 are in flight while K-block kb waits for its stage and is stored
+      auto loadk = [&](int kb, uint4 (&v)[ITERS]) {
 #pragma unroll
         for (int i = 0; i < ITERS; ++i) {
           if (p.a_diag == 2) {
@@ -425,6 +425,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
             v[i] = rowp[i] ? ldg_nc_v4(rowp[i] + kcol) : make_uint4(0, 0, 0, 0);
           }
         }
+      };
+      auto storek = [&](const uint4 (&v)[ITERS]) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* dst = smem + stage * GEMM_STAGE_BYTES;
 #pragma unroll
@@ -436,6 +438,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);
         if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+      };
+      uint4 va[ITERS], vb[ITERS];
+      loadk(0, va);
+      for (int kb = 0; kb < num_kb; kb += 2) {
+        if (kb + 1 < num_kb) loadk(kb + 1, vb);
+        storek(va);
+        if (kb + 1 < num_kb) {
+          if (kb + 2 < num_kb) loadk(kb + 2, va);
+          storek(vb);
+        }
       }
     }
   }
