@@ -90,3 +90,46 @@ def test_unsupported_sizes_raise():
         modules.TrajectoryAttention(128, 4)
     with pytest.raises(NotImplementedError):
         modules.TemporalAxialTrajectoryAttentionLayer(activation="gelu")
+
+
+def test_kmax_axial_state_dict_keys_match_live_reference():
+    """Row f3 drop-ins: same constructor arguments and state-dict keys / shapes as the reference's AxialAttention2D."""
+    import sys
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not mounted")
+    from axial_vs_b200 import kmax_axial
+    ref_loader.cross_clip()                     # loads kmax_pixel_decoder.py
+    KP = sys.modules["kmax_deeplab.modeling.pixel_decoder.kmax_pixel_decoder"]
+    ref = KP.AxialAttention2D(512, query_shape=[21, 41], filters=512, key_expansion=1, value_expansion=2, num_heads=8)
+    ours = kmax_axial.AxialAttention2D(512, query_shape=[21, 41], filters=512, key_expansion=1, value_expansion=2, num_heads=8)
+    rs, os_ = ref.state_dict(), ours.state_dict()
+    assert list(rs) == list(os_)
+    assert all(tuple(rs[k].shape) == tuple(os_[k].shape) for k in rs)
+    ours.load_state_dict(rs, strict=True)
+
+
+def test_panoptic_oracle_invariants():
+    """Properties of the mask-wise merge that hold for any input (numpy oracle, CPU): ids come from the segment table, every
+    painted pixel had its slot above the pixel threshold, a stuff category appears under one id, thing ids of a category are consecutive."""
+    import numpy as np
+    from axial_vs_b200 import synth
+    from oracle import panoptic_oracle as PO
+    for seed in range(5):
+        N, C, T, H, W = 24, 9, 2, 17, 13
+        mc, mp, me = synth.panoptic_case(100 + seed, N, C, T, H, W, cell=3)
+        meta = PO.Metadata(*synth.panoptic_metadata(C, label_divisor=100))
+        seg, dic, segments = PO.panoptic_mask_inference(mc.numpy(), mp.numpy(), me.numpy(), meta, pixel_thr=0.3)
+        _, _, binary, _, _, _ = PO.scores(mc.numpy(), mp.numpy(), 0.3)
+        ids = {s[3] for s in segments}
+        assert set(np.unique(seg).tolist()) <= ids | {-1}
+        covered = binary.any(0).reshape(seg.shape)
+        assert not (seg[~covered] != -1).any()                       # a pixel no slot claims stays unassigned
+        stuff_ids = [s[3] for s in segments if not s[2]]
+        assert len(stuff_ids) == len(set(stuff_ids))
+        by_cat = {}
+        for slot, label, is_thing, fid in segments:
+            if is_thing:
+                by_cat.setdefault(fid // 100, []).append(fid % 100)
+        assert all(v == list(range(len(v))) for v in by_cat.values())
+        assert {k: len(v) for k, v in dic.items()} == {k: len(v) for k, v in by_cat.items()}
