@@ -254,7 +254,7 @@ def kmax_goldens():
         m.load_state_dict(p, strict=True)
         y = m(synth.randn(seed + 100, N, C, L))
         save(f"kmax_axial_{tag}", N=N, C=C, L=L, seed=seed, y=y, wsum=synth.checksum(p))
-    N, C, H, W, seed = 2, 256, 11, 14, 33
+    N, C, H, W, seed = 1, 256, 7, 10, 33
     m2 = KP.AxialAttention2D(C, query_shape=[H, W], filters=512, key_expansion=1, value_expansion=2, num_heads=8).eval()
     ph, pw = synth.kmax_axial_params(seed, C), synth.kmax_axial_params(seed + 1, 1024)
     m2._height_axis.load_state_dict(ph, strict=True)
