@@ -133,3 +133,15 @@ def test_panoptic_oracle_invariants():
                 by_cat.setdefault(fid // 100, []).append(fid % 100)
         assert all(v == list(range(len(v))) for v in by_cat.values())
         assert {k: len(v) for k, v in dic.items()} == {k: len(v) for k, v in by_cat.items()}
+
+
+def test_shared_pos_detection():
+    """`ops.shared_pos`: a stride-0 broadcast over the clip dim collapses to its single table; materialised tensors pass through."""
+    from axial_vs_b200 import ops
+    one = torch.randn(1, 2, 3, 4, 8)
+    ex = one.expand(5, -1, -1, -1, -1)
+    assert ops.shared_pos(ex).shape[0] == 1 and ops.shared_pos(ex).data_ptr() == one.data_ptr()
+    full = ex.contiguous()
+    assert ops.shared_pos(full) is full
+    assert ops.shared_pos(one) is one
+    assert ops.shared_pos(ex[1:4]).shape[0] == 1          # slices of a broadcast (clip chunks) stay broadcasts
