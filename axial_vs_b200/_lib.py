@@ -52,6 +52,7 @@ SIGNATURES = {
     "axvs_last_error": (c_char_p, []),
     "axvs_set_fusion": (c_int, [c_int]),
     "axvs_set_pair_mode": (c_int, [c_int]),
+    "axvs_set_attn_core": (c_int, [c_int]),
     "axvs_packed_weight_bytes": (c_size_t, [c_int, c_int]),
     "axvs_pack_weight": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "axvs_pack_weight_units": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "attn.cuh"
+#include "attn_tc.cuh"
 #include "gemm.cuh"
 #include "simt.cuh"
 #include "traj_fused.cuh"
@@ -39,13 +40,14 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel"};
 int g_fusion = 4;   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
+int g_attn_core = 1;   // 1 = tcgen05 attention core (attn_tc.cuh), 0 = the mma.sync kernels (validation baseline)
 int g_pair = 0;   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
@@ -89,6 +91,7 @@ struct DeviceInfo {
   bool pair_attr = false;
   bool dec_attr = false;
   bool kmax_attr = false;
+  bool attn_tc_attr = false;
 };
 DeviceInfo g_dev[64];
 
@@ -137,6 +140,17 @@ int device_info(DeviceInfo** out) {
         cudaFuncSetAttribute(spatial_attn_v3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(spatial_attn_v2) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.attn2_attr = true;
+  }
+  if (!d.attn_tc_attr) {
+    const int mx = 200 * 1024;
+    if (cudaFuncSetAttribute(spatial_attn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(spatial_attn_tc) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (const char* e = getenv("AXVS_ATTN_CORE")) g_attn_core = atoi(e) ? 1 : 0;   // A/B aid for bench.py runs
+    d.attn_tc_attr = true;
   }
   if (!d.pair_attr) {
     if (cudaFuncSetAttribute(ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_BYTES) != cudaSuccess)
@@ -283,6 +297,11 @@ int axvs_set_pair_mode(int on) {
   g_pair = on ? 1 : 0;
   return prev;
 }
+int axvs_set_attn_core(int core) {
+  const int prev = g_attn_core;
+  g_attn_core = core ? 1 : 0;
+  return prev;
+}
 int axvs_set_fusion(int level) {
   const int prev = g_fusion;
   g_fusion = level < 0 ? 0 : (level > 5 ? 5 : level);
@@ -387,6 +406,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
     // ---- fused front end: tile-image pack -> TMA-fed q|k|v GEMM (head-major) -> one-shot attention writing tile images
     const int tiles = (int)((rows + 127) / 128);
     const int nt16_f = (n + 15) / 16;
+    bool use_tc = false;                                         // tcgen05 attention core (needs the chunk-permuted q|k|v of qkv_direct)
     if (g_fusion >= 5 && v_in == q_in && N <= 128 && nt16_f <= 4) {
       // q|k|v projections and the per-frame attention in one kernel: q, k, v never leave the SM
       QkvAttnParams ap;
@@ -408,12 +428,14 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       AXVS_CHECK_LAUNCH("qkv_attn_kernel");
     } else {
     if (g_fusion >= 4 && v_in == q_in) {
+      use_tc = g_attn_core == 1 && (n + 15) / 16 * 16 <= 224;
       // the q|k|v GEMM reads the fp32 residual stream (+ pos) itself: no tile-image pack, no a1/a2 round trip
       QkvDirectParams qp;
       memset(&qp, 0, sizeof(qp));
       qp.src = q_in; qp.pos = pos;
       qp.w = reinterpret_cast<const uint8_t*>(w->w_qkv_u); qp.bias = w->b_qkv;
       qp.qkv = ws.qkv; qp.rows = (int)rows; qp.tiles = tiles; qp.map_mode = map; qp.dims = dims;
+      if (use_tc) { qp.swz_N = N; qp.swz_n = n; }
       {
         ProfScope ps(KC_QKVD, 2.0 * rows * 256.0 * 768.0, (double)rows * ((pos ? (dims.pos_mod ? 1024.0 + 1024.0 / B : 2048.0) : 1024.0) + 1536.0), st);
         qkv_direct_kernel<<<tiles < d->sms ? tiles : d->sms, QD_THREADS, QD_SMEM_BYTES, st>>>(qp);
@@ -443,6 +465,49 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
     }
     AXVS_CHECK_LAUNCH("qkv_fused_kernel");
     }
+    if (use_tc) {
+      // ---- tcgen05 attention: S = Q K_f^T and O_f = P_f V_f as UMMAs, softmax thread-per-row out of tensor memory
+      AttnTcParams ap;
+      memset(&ap, 0, sizeof(ap));
+      ap.qkv = ws.qkv; ap.rows_total = rows; ap.x_img = ws.x_img; ap.xd_img = ws.xd_img;
+      ap.tiles = tiles; ap.N = N; ap.n = n; ap.F = F; ap.NP = nt16_f * 16; ap.QB = (N + 127) / 128;
+      ap.scale_log2e = kScaleLog2e;
+      // softmax groups (= TMEM buffers) and frames per unit: the most groups that still take two frames per unit
+      int G = 2, FC = 1;
+      for (int g = AT_MAX_G; g >= 2; --g) {
+        const int cols = (512 / g) / 16 * 16;
+        int fc = cols / (ap.NP + 32);
+        if (fc > AT_MAX_FC) fc = AT_MAX_FC;
+        if (fc > F) fc = F;
+        if (fc >= (F < 2 ? F : 2) || (g == 2 && fc >= 1)) { G = g; FC = fc; break; }
+      }
+      if (G == 2 && FC < (F < 2 ? F : 2)) {                       // long frames: one frame per unit, as many groups as fit
+        for (int g = AT_MAX_G; g >= 2; --g)
+          if ((512 / g) / 16 * 16 >= ap.NP + 32) { G = g; FC = 1; break; }
+      }
+      ap.G = G; ap.FC = FC; ap.buf_cols = (512 / G) / 16 * 16; ap.NCH = (F + FC - 1) / FC;
+      const long long units = (long long)num_seq * 8 * ap.QB * ap.NCH;
+      if (units > 0x7fffffff) return fail(AXVS_E_UNSUPPORTED, "traj_attn: too many attention work units (%lld)", units);
+      ap.num_units = (int)units;
+      ap.slot_bytes = AT_Q_BYTES + FC * ap.NP * 128;
+      int slots = (184 * 1024) / ap.slot_bytes;
+      if (slots > AT_MAX_SLOTS) slots = AT_MAX_SLOTS;
+      ap.slots = slots;                                           // >= 5 (at most 36 KiB per slot); G + 1 are needed
+      const size_t smem_b = (size_t)slots * ap.slot_bytes + 512;
+      const int grid = ap.num_units < d->sms ? ap.num_units : d->sms;
+      {
+        ProfScope ps(KC_ATTNTC, 4.0 * num_seq * (double)N * N * 256, (double)rows * (1536.0 + (F + 1) * 512.0), st);
+        const int threads = 128 * G + 64;
+        switch (nt16_f <= 4 ? nt16_f : 0) {
+          case 1: spatial_attn_tc_kernel<1><<<grid, threads, smem_b, st>>>(ap); break;
+          case 2: spatial_attn_tc_kernel<2><<<grid, threads, smem_b, st>>>(ap); break;
+          case 3: spatial_attn_tc_kernel<3><<<grid, threads, smem_b, st>>>(ap); break;
+          case 4: spatial_attn_tc_kernel<4><<<grid, threads, smem_b, st>>>(ap); break;
+          default: spatial_attn_tc_kernel<0><<<grid, threads, smem_b, st>>>(ap); break;
+        }
+      }
+      AXVS_CHECK_LAUNCH("spatial_attn_tc_kernel");
+    } else {
     const int nt16 = (n + 15) / 16;
     const int np_sel = nt16 <= 2 ? 2 : nt16 <= 3 ? 3 : nt16 <= 4 ? 4 : nt16 <= 6 ? 6 : nt16 <= 8 ? 8 : 11;
     const size_t att_q = (size_t)((N + 15) / 16) * 16 * 64 + 4096;
@@ -490,6 +555,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       x_to_image_kernel<<<blocks_for((long long)rows * F * 32, 256, d->sms), 256, 0, st>>>(ws.x, ws.x_img, ws.xd_img, (int)rows, tiles, F, N, n);
     }
     AXVS_CHECK_LAUNCH("spatial attention");
+    }
     }
     TrajParams tp;
     memset(&tp, 0, sizeof(tp));

@@ -35,6 +35,8 @@ struct QkvDirectParams {
   __nv_bfloat16* qkv;      // head-major [3][8][rows][32]
   int rows, tiles, map_mode;
   AxialDims dims;
+  int swz_N, swz_n;        // > 0: permute the 16-byte chunks of every stored row for the tcgen05 attention kernel (attn_tc.cuh): chunk c
+                           // of a q row goes to position c ^ ((i >> 1) & 3), i = row % swz_N; of a k / v row to c ^ ((j >> 1) & 3), j = i % swz_n
 };
 
 __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDirectParams p) {
@@ -78,6 +80,12 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
     AXVS_PROF_DECL(1)
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
       const int row0 = tile * 128 + (warp & 3) * 32;           // first row of this warp
+      uint32_t key_q = 0, key_kv = 0;                          // chunk permutation keys of row (row0 + lane), see swz_N
+      if (p.swz_N > 0) {
+        const int i = (row0 + lane) % p.swz_N;
+        key_q = (uint32_t)(i >> 1) & 3u;
+        key_kv = (uint32_t)((i % p.swz_n) >> 1) & 3u;
+      }
 #pragma unroll 1
       for (int rt = 0; rt < 6; ++rt, ++cnt) {
         const int st = cnt & 1;                                // 6 chunks per tile: even, so st == rt & 1
@@ -117,11 +125,13 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
           {
             const int which = rt >> 1, head = (rt & 1) * 4 + c;
             uint8_t* dst = reinterpret_cast<uint8_t*>(p.qkv + ((size_t)(which * 8 + head) * p.rows + row0) * 32);
+            const uint32_t my_key = which == 0 ? key_q : key_kv;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int rl = 8 * i + (lane >> 2), piece = lane & 3;
               const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((piece ^ ((rl >> 1) & 3)) << 4));
-              if (row0 + rl < p.rows) *reinterpret_cast<uint4*>(dst + rl * 64 + piece * 16) = u;
+              const uint32_t key = __shfl_sync(0xffffffffu, my_key, rl);
+              if (row0 + rl < p.rows) *reinterpret_cast<uint4*>(dst + rl * 64 + ((piece ^ key) << 4)) = u;
             }
           }
           __syncwarp();

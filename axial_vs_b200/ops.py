@@ -369,6 +369,11 @@ def set_pair_mode(on: bool) -> int:
     return _lib.load().axvs_set_pair_mode(int(on))
 
 
+def set_attn_core(core: int) -> int:
+    """1 = tcgen05 attention core (default), 0 = the mma.sync kernels (validation baseline); returns the previous setting."""
+    return _lib.load().axvs_set_attn_core(int(core))
+
+
 # ------------------------------------------------------------------------------------------------ measurement hooks
 def profile_enable(on: bool) -> None:
     """Reset the library's launch counters; with on=True every launch is bracketed by CUDA events (bench.py)."""

@@ -58,6 +58,11 @@ int axvs_set_fusion(int level);
 /* CTA-pair FFN kernel (tcgen05 cta_group::2, two SMs per M = 256 instruction stream) on/off.  Default OFF: it is validated
  * and its UMMAs run at the full 64 clk rate, but the per-SM epilogue becomes the bottleneck (profiles/README.md).  Returns previous. */
 int axvs_set_pair_mode(int on);
+/* Attention core of the per-frame spatial attention (WC/temporal_attention.py:47-60) at fusion level >= 4.
+ *   1 (default): tcgen05 kernel -- Q K^T and P V as UMMAs (scores / probabilities / outputs in tensor memory, operands by TMA),
+ *                softmax thread-per-row in registers (csrc/attn_tc.cuh); frames of up to 224 tokens, any sequence length
+ *   0: the mma.sync kernels (csrc/attn.cuh; validation baseline, and the fallback for longer frames).  Returns previous. */
+int axvs_set_attn_core(int core);
 
 /* ---- weights ------------------------------------------------------------------------------------------------
  * nn.Linear weights [n_out, k] fp32 are converted once to bf16 and laid out as the shared-memory image the

@@ -201,17 +201,20 @@ def test_direct_qkv_matches_packed_front_end(ops, B, T, H, W):
     layer = _layer(p)
     outs = []
     try:
-        for level in (3, 4, 5):
+        for level, core in ((3, 1), (4, 1), (4, 0), (5, 0)):
             ops.set_fusion(level)
+            ops.set_attn_core(core)
             with torch.no_grad():
                 outs.append(layer(src, pos)[0])
             torch.cuda.synchronize()
     finally:
         ops.set_fusion(ops.DEFAULT_FUSION)
+        ops.set_attn_core(1)
     assert torch.isfinite(outs[1]).all()
     assert nerr(outs[1], outs[0]) < 4e-3
-    # level 5 runs the same attention arithmetic on the same bf16 q | k | v inside the projection kernel
-    assert torch.equal(outs[2], outs[1])
+    assert nerr(outs[2], outs[1]) < 4e-3      # mma.sync attention core against the tcgen05 core
+    # level 5 runs the mma.sync attention arithmetic on the same bf16 q | k | v inside the projection kernel
+    assert torch.equal(outs[3], outs[2])
 
 
 @pytest.mark.parametrize("B,T,H,W", [(3, 2, 13, 29), (5, 2, 21, 21), (2, 3, 7, 40)])
@@ -350,6 +353,28 @@ def test_fusion_levels_agree(ops, O, Bp, F, n):
         ops.set_fusion(ops.DEFAULT_FUSION)
     assert nerr(outs[1], outs[0]) < 5e-3 and nerr(outs[3], outs[0]) < 5e-3
     assert nerr(outs[4], outs[3]) < 4e-3      # level 4: tensor-memory operands, q2 rounded to bf16
+
+
+@pytest.mark.parametrize("Bp,F,n", [(5, 2, 41), (7, 2, 21), (3, 5, 30), (2, 5, 40), (1, 10, 33), (2, 2, 5), (1, 1, 50), (1, 2, 161), (1, 2, 200),
+                                    (1, 3, 224), (2, 2, 128), (1, 4, 64), (3, 1, 16), (1, 7, 17), (9, 2, 81)])
+def test_attention_core_tcgen05(ops, O, Bp, F, n):
+    """tcgen05 attention core (S = Q K^T and P V as UMMAs, softmax out of tensor memory) against the mma.sync core and
+    the oracle; query == key == value input so that the level-4 front end (qkv_direct) runs, sequences longer than one
+    128-query block included."""
+    p, q, _, pk = _ta_case(ops, O, Bp, F, n, 3000 + Bp + F + n)
+    ref, _ = O.trajectory_attention(q, q, q, p, F)
+    qc = q.reshape(-1, 256).cuda()
+    outs = []
+    try:
+        for core in (0, 1):
+            ops.set_attn_core(core)
+            out = ops.traj_attn_fwd(qc, qc, qc, None, None, pk, Bp, F, n, 1, ops.AXIS_NONE)
+            torch.cuda.synchronize()
+            assert nerr(out, ref.reshape(-1, 256)) < TOL, f"attention core {core}"
+            outs.append(out)
+    finally:
+        ops.set_attn_core(1)
+    assert nerr(outs[1], outs[0]) < 4e-3
 
 
 # --------------------------------------------------------------------------------------------- maps, pos module, TL, cross-clip
