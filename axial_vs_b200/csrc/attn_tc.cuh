@@ -11,16 +11,21 @@
 //                     (rows = keys, 32 contiguous channels per row: exactly how the q|k|v kernel stores v), N = 32
 //   epilogue          O_f / l_f -> bf16 -> the x_f (and, for the query's own frame, x_diag) rows of the SWIZZLE_128B
 //                     tile images traj_ts_kernel loads by TMA
-// q | k | v arrive head-major ([which][head][row][32] bf16) with the 16-byte chunks of every row pre-permuted by the
-// q|k|v kernel (chunk c of a row at position c ^ ((i >> 1) & 3), i = row index inside the sequence for q, inside the key
-// frame for k / v), so plain 1-D TMA bulk copies land ready-to-use SWIZZLE_64B tiles.  Operand forms validated in
-// tools/microbench/umma_sw64.cu (K-major and MN-major SWIZZLE_64B descriptors: SBO = 512 B, LBO unused).
 //
-// The per-unit tensor work is tiny (5-10 instructions), so every fixed cost is paid once per UNIT, not per frame: one
-// shared-memory slot = Q + the chunk's K_f | V_f, filled by ONE warp-wide cp.async.bulk (lane 0: Q, lanes 1 + 2f / 2 + 2f:
-// K_f / V_f) against one mbarrier; one commit per phase.  G softmax / epilogue groups of 4 warps (warps 0 .. 4G-1, TMEM
-// lane quarter = warp & 3) work on G units at once (unit k -> TMEM buffer and group k % G); the issuer runs the S phase up to
-// G - 1 units ahead of the P V phase.  Then one TMA producer warp and one MMA issuer warp.
+// Operand layout in HBM ("unit-major", written by qkv_direct_kernel when swz_N > 0): one contiguous region of 3 N rows of
+// 64 bytes per (sequence, head):  Q rows [0, N), then per key frame f its K rows at N + 2 f n and its V rows at N + (2 f + 1) n;
+// the 16-byte chunks of the row at position `pos` of the region are permuted by (pos >> 1) & 3.  The tensor core applies
+// the SWIZZLE_64B XOR to ABSOLUTE shared-memory address bits (tools/microbench/umma_sw64.cu: operand tiles may start at any
+// row of a 512-byte-aligned buffer, base_offset = 0), so ONE 1-D TMA bulk copy of the region lands Q and every K_f / V_f
+// ready to use, with no padding between the frames: an instruction that reads NP > n rows runs into the next tile's rows,
+// whose scores are never read and whose probabilities are zero.  Units that do not cover a whole (sequence, head) -- more
+// than 128 queries, or more frames than fit in tensor memory -- take two copies (the Q block, the K_f | V_f rows of the chunk).
+//
+// The per-unit tensor work is tiny (5-10 instructions), so every fixed cost is paid once per unit: one shared-memory slot and
+// one mbarrier per unit, one commit per phase, descriptors computed by the converged issuer warp outside the elected branch
+// (a lone diverged lane pays ~150 clk per instruction).  G softmax / epilogue groups of 4 warps (warps 0 .. 4G-1, TMEM lane
+// quarter = warp & 3) work on G units at once (unit k -> TMEM buffer and group k % G); the issuer runs the S phase up to G - 1
+// units ahead of the P V phase.  Then one TMA producer warp and one MMA issuer warp.
 #pragma once
 #include "attn.cuh"
 
@@ -31,7 +36,7 @@ constexpr int AT_MAX_SLOTS = 12;
 constexpr int AT_MAX_G = 4;
 
 struct AttnTcParams {
-  const __nv_bfloat16* qkv;   // head-major [3][8][rows_total][32], chunks pre-permuted (see above)
+  const __nv_bfloat16* qkv;   // unit-major: [(sequence, head)][3 N rows][32], chunks permuted (see above)
   size_t rows_total;
   uint8_t* x_img;             // [F][tiles][4][16 KiB]
   uint8_t* xd_img;            // [tiles][4][16 KiB]
@@ -40,6 +45,7 @@ struct AttnTcParams {
   int G, buf_cols;            // softmax groups = TMEM buffers, columns per buffer (>= FC * (NP + 32))
   int num_units;              // num_seq * 8 * QB * NCH
   int slots, slot_bytes;      // shared-memory ring
+  int single;                 // 1: a unit is a whole (sequence, head) region -> one bulk copy
   float scale_log2e;
 };
 
@@ -69,10 +75,17 @@ __device__ __forceinline__ void umma_ts_raw(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
+__device__ __forceinline__ float max3_f32(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 // unit index -> (item, chunk); item -> (sequence * 8 + head, query block)
 struct AtUnit { int sh, qb, f0, fc; };
 __device__ __forceinline__ AtUnit at_decode(int unit, const AttnTcParams& p) {
   AtUnit u;
+  if (p.single) { u.sh = unit; u.qb = 0; u.f0 = 0; u.fc = p.F; return u; }
   const int ch = unit % p.NCH;
   const int item = unit / p.NCH;
   u.qb = item % p.QB;
@@ -92,27 +105,33 @@ __device__ __forceinline__ float at_softmax_frame(uint32_t t_s, int NP, int n, f
 #pragma unroll
     for (int c = 0; c < NT16; ++c) tmem_ld16(t_s + 16 * c, v[c]);
     tmem_ld_wait();
+    {
+      // NP = n rounded up to 16, so only the LAST 16-column piece can reach past the end of the frame
+      const int tail = n - 16 * (NT16 - 1);                    // valid columns of the last piece, 1 .. 16
+#pragma unroll
+      for (int i = 1; i < 16; ++i) if (i >= tail) v[NT16 - 1][i] = -INFINITY;
+    }
     float mx = -INFINITY;
 #pragma unroll
     for (int c = 0; c < NT16; ++c) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (16 * c + i >= n) v[c][i] = -INFINITY;             // resolved per (c, i) at run time only for the straddling piece
-        mx = fmaxf(mx, v[c][i]);
-      }
+      for (int i = 0; i < 16; i += 2) mx = max3_f32(mx, v[c][i], v[c][i + 1]);
     }
-    const float mxs = -mx * sc;
+    const float2 sc2 = make_float2(sc, sc), mxs2 = make_float2(-mx * sc, -mx * sc);
+    float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < NT16; ++c) {
       uint32_t pk[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float e0 = ex2_approx(fmaf(v[c][2 * i], sc, mxs)), e1 = ex2_approx(fmaf(v[c][2 * i + 1], sc, mxs));   // 2^-inf = 0 past the frame
-        sum += e0 + e1;
-        pk[i] = pack_bf16x2(e0, e1);
+        const float2 a = fma_f32x2(make_float2(v[c][2 * i], v[c][2 * i + 1]), sc2, mxs2);   // 2^-inf = 0 past the frame
+        const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+        sum2 = add_f32x2(sum2, e);
+        pk[i] = pack_bf16x2(e.x, e.y);
       }
       tmem_st8u(t_s + 8 * c, pk);
     }
+    sum = sum2.x + sum2.y;
   } else {
     float mx = -INFINITY;
 #pragma unroll 1
@@ -151,11 +170,12 @@ __device__ __forceinline__ float at_softmax_frame(uint32_t t_s, int NP, int n, f
 constexpr int AT_MAX_FC = 4;   // frames per chunk the epilogue keeps row sums for
 
 template <int NT16>
-__global__ void __launch_bounds__(128 * AT_MAX_G + 64, 1) spatial_attn_tc_kernel(const AttnTcParams p) {
+__global__ void __launch_bounds__((NT16 == 1 || NT16 == 2) ? 128 * 4 + 96 : 128 * 3 + 96, 1) spatial_attn_tc_kernel(const AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* ring = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.slots * p.slot_bytes);
+  uint8_t* stg_all = ring + (size_t)p.slots * p.slot_bytes;   // [4 G warps][32 rows x 64 B] transpose staging of the epilogue
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + 4 * AT_MAX_G * 2048);
   uint64_t* full = bars;                            // [AT_MAX_SLOTS]
   uint64_t* empty = full + AT_MAX_SLOTS;
   uint64_t* s_full = empty + AT_MAX_SLOTS;          // [G] scores of the buffer's unit complete
@@ -168,8 +188,8 @@ __global__ void __launch_bounds__(128 * AT_MAX_G + 64, 1) spatial_attn_tc_kernel
   const int lane = threadIdx.x & 31;
   const int F = p.F, n = p.n, N = p.N, NP = p.NP, G = p.G;
 
-  // zero the ring once: the pad rows [n, NP) of every K_f | V_f tile and the rows of a Q tile past the end of a sequence are
-  // never written by the bulk copies and must stay finite (their products meet zero probabilities / are ignored)
+  // zero the ring once: rows an instruction reads beyond what the bulk copies wrote (past the last V_f, past a short Q block)
+  // must be finite -- their products meet zero probabilities or land in score rows / columns nobody reads
   {
     const int total16 = (p.slots * p.slot_bytes) >> 4;
     for (int i = threadIdx.x; i < total16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -189,19 +209,18 @@ __global__ void __launch_bounds__(128 * AT_MAX_G + 64, 1) spatial_attn_tc_kernel
   if (warp < 4 * G) {
     // =============================================================== softmax + epilogue groups
     const int g = warp >> 2;
-    const int row = (warp & 3) * 32 + lane;
+    uint8_t* stg = stg_all + warp * 2048;
     const uint32_t t_buf = tmem + ((uint32_t)((warp & 3) * 32) << 16) + g * p.buf_cols;
     const float sc = p.scale_log2e;
     uint32_t use = 0;                                         // units this group has processed
+    AXVS_PROF_DECL(2)
     for (int unit = blockIdx.x + g * gridDim.x; unit < p.num_units; unit += G * gridDim.x, ++use) {
       const AtUnit u = at_decode(unit, p);
       const int head = u.sh & 7;
       const size_t seq_row0 = (size_t)(u.sh >> 3) * N;
-      const int qi = u.qb * 128 + row;                        // query index inside the sequence
-      const bool valid = qi < N;
       const uint32_t par = use & 1;
       const uint32_t t_o = t_buf + u.fc * NP;
-      mbar_wait(&s_full[g], par);
+      AXVS_PROF_WAIT(0, mbar_wait(&s_full[g], par))
       tc_fence_after();
       float inv[AT_MAX_FC];
 #pragma unroll
@@ -211,12 +230,12 @@ __global__ void __launch_bounds__(128 * AT_MAX_G + 64, 1) spatial_attn_tc_kernel
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
-      // ---- epilogue: O_f / l_f -> bf16 -> tile images
+      // ---- epilogue: O_f / l_f -> bf16 -> tile images.  A thread holds one row (64 bytes per frame); a 2 KiB per-warp transpose
+      // lets every store instruction write whole 64-byte row segments (4 lanes per row) instead of 32 scattered 16-byte pieces
+      // (those cost one L1 wavefront each and bound the first version of this kernel).
       const int kb = head >> 1, ch0 = (head & 1) * 4;
-      const size_t r = seq_row0 + (valid ? qi : 0);
-      const size_t img_off = ((r >> 7) * 4 + kb) * (size_t)ATT2_KB;
-      const uint32_t rl = (uint32_t)(r & 127);
-      mbar_wait(&o_full[g], par);
+      const int q_w0 = u.qb * 128 + (warp & 3) * 32;          // query index of this warp's first row
+      AXVS_PROF_WAIT(1, mbar_wait(&o_full[g], par))
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < AT_MAX_FC; ++j) {
@@ -229,106 +248,141 @@ __global__ void __launch_bounds__(128 * AT_MAX_G + 64, 1) spatial_attn_tc_kernel
             __syncwarp();
             if (lane == 0) mbar_arrive(&buf_free[g]);
           }
-          if (valid) {
-            const int f = u.f0 + j;
-            const float il = __frcp_rn(inv[j]);
-            uint8_t* dst = p.x_img + (size_t)f * p.tiles * 4 * ATT2_KB + img_off;
-            const bool diag = (unsigned)(qi - f * n) < (unsigned)n;   // qi / n == f
+          const float il = __frcp_rn(inv[j]);
+          const float2 il2 = make_float2(il, il);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 w;
-              w.x = pack_bf16x2(o[8 * c] * il, o[8 * c + 1] * il);
-              w.y = pack_bf16x2(o[8 * c + 2] * il, o[8 * c + 3] * il);
-              w.z = pack_bf16x2(o[8 * c + 4] * il, o[8 * c + 5] * il);
-              w.w = pack_bf16x2(o[8 * c + 6] * il, o[8 * c + 7] * il);
-              const uint32_t off = sw128_offset(rl, ch0 + c);
+          for (int c = 0; c < 4; ++c) {
+            uint4 w;
+            const float2 m0 = mul_f32x2(make_float2(o[8 * c], o[8 * c + 1]), il2), m1 = mul_f32x2(make_float2(o[8 * c + 2], o[8 * c + 3]), il2);
+            const float2 m2 = mul_f32x2(make_float2(o[8 * c + 4], o[8 * c + 5]), il2), m3 = mul_f32x2(make_float2(o[8 * c + 6], o[8 * c + 7]), il2);
+            w.x = pack_bf16x2(m0.x, m0.y);
+            w.y = pack_bf16x2(m1.x, m1.y);
+            w.z = pack_bf16x2(m2.x, m2.y);
+            w.w = pack_bf16x2(m3.x, m3.y);
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = w;
+          }
+          __syncwarp();
+          const int f = u.f0 + j;
+          uint8_t* dst = p.x_img + (size_t)f * p.tiles * 4 * ATT2_KB;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + (lane >> 2), piece = lane & 3;
+            const uint4 w = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
+            const int qi = q_w0 + rr;                          // query index inside the sequence
+            if (qi < N) {
+              const size_t r = seq_row0 + qi;
+              const size_t off = ((r >> 7) * 4 + kb) * (size_t)ATT2_KB + sw128_offset((uint32_t)(r & 127), ch0 + piece);
               *reinterpret_cast<uint4*>(dst + off) = w;
-              if (diag) *reinterpret_cast<uint4*>(p.xd_img + img_off + off) = w;
+              if ((unsigned)(qi - f * n) < (unsigned)n) *reinterpret_cast<uint4*>(p.xd_img + off) = w;   // qi / n == f
             }
           }
+          __syncwarp();
         }
       }
     }
+    AXVS_PROF_FLUSH(52, 2, warp == 0 && lane == 0)
   } else if (warp == 4 * G) {
-    // =============================================================== TMA producer: one warp-wide bulk copy per unit
-    uint32_t cnt = 0;
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++cnt) {
-      const AtUnit u = at_decode(unit, p);
-      const int head = u.sh & 7;
-      const size_t seq_row0 = (size_t)(u.sh >> 3) * N;
-      const int rows_q = min(128, N - u.qb * 128);
-      const uint32_t slot = cnt % p.slots;
-      uint8_t* dst = ring + (size_t)slot * p.slot_bytes;
-      if (lane == 0) {
-        mbar_wait(&empty[slot], ((cnt / p.slots) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[slot], rows_q * 64 + u.fc * 2 * n * 64);
-      }
-      __syncwarp();
-      // lane 0: Q rows; lane 1 + 2j: K of frame f0 + j; lane 2 + 2j: V of frame f0 + j
-      if (lane < 1 + 2 * u.fc) {
-        const int j = (lane - 1) >> 1, isv = (lane - 1) & 1;
-        const void* src;
-        uint8_t* d;
-        uint32_t bytes;
-        if (lane == 0) {
-          src = p.qkv + ((size_t)head * p.rows_total + seq_row0 + (size_t)u.qb * 128) * 32;
-          d = dst;
-          bytes = rows_q * 64;
+    // =============================================================== TMA producer: one (or two) bulk copies per unit
+    if (lane == 0) {
+      uint32_t slot = 0, sphase = 0;                           // ring position and its phase bit (no divisions on this path)
+      AXVS_PROF_DECL(1)
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        const AtUnit u = at_decode(unit, p);
+        uint8_t* dst = ring + (size_t)slot * p.slot_bytes;
+        const __nv_bfloat16* region = p.qkv + (size_t)u.sh * 3 * N * 32;
+        AXVS_PROF_WAIT(0, mbar_wait(&empty[slot], sphase ^ 1))
+        if (p.single) {
+          mbar_arrive_expect_tx(&full[slot], 3 * N * 64);
+          tma_bulk_g2s(dst, region, 3 * N * 64, &full[slot]);
         } else {
-          src = p.qkv + ((size_t)((isv ? 16 : 8) + head) * p.rows_total + seq_row0 + (size_t)(u.f0 + j) * n) * 32;
-          d = dst + AT_Q_BYTES + (2 * j + isv) * NP * 64;
-          bytes = n * 64;
+          const int rows_q = min(128, N - u.qb * 128);
+          const int kpos = N + 2 * u.f0 * n;                  // region row of the chunk's first K row
+          mbar_arrive_expect_tx(&full[slot], rows_q * 64 + u.fc * 2 * n * 64);
+          tma_bulk_g2s(dst, region + (size_t)u.qb * 128 * 32, rows_q * 64, &full[slot]);
+          tma_bulk_g2s(dst + AT_Q_BYTES + (kpos & 7) * 64, region + (size_t)kpos * 32, u.fc * 2 * n * 64, &full[slot]);
         }
-        tma_bulk_g2s(d, src, bytes, &full[slot]);
+        if (++slot == (uint32_t)p.slots) { slot = 0; sphase ^= 1; }
       }
-      __syncwarp();
+      AXVS_PROF_FLUSH(60, 1, true)
     }
   } else {
-    // =============================================================== MMA issuer (converged warp, elected lane)
+    // =============================================================== MMA issuers (converged warps, elected lane): warp 4G + 1 issues
+    // the S phase of every unit, warp 4G + 2 the P V phase -- the per-instruction issue cost (~150 clk per elected block) is
+    // the bottleneck of this kernel, and the two phases are ordered by mbarriers only (S of unit k + G waits for buf_free, which
+    // follows o_full of unit k), so they can be issued from two warps in parallel
     const uint32_t idesc_s = umma_idesc_bf16(128, NP);
     const uint32_t idesc_o = umma_idesc_bf16(128, 32) | (1u << 16);        // B (= V) is MN-major
     const uint32_t ring_addr = smem_u32(ring);
-    uint32_t k = 0;                                            // units whose S phase has been issued
-    uint32_t pv_k = 0;                                         // units whose P V phase has been issued
-    int pv_unit = blockIdx.x;
-    auto issue_pv = [&]() {
-      const uint32_t b = pv_k % G, slot = pv_k % p.slots;
-      const int fc = at_decode(pv_unit, p).fc;
-      mbar_wait(&p_full[b], (pv_k / G) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t t_p = tmem + b * p.buf_cols;
-        for (int j = 0; j < fc; ++j) {
-          const uint32_t v_lo = (((ring_addr + slot * p.slot_bytes + AT_Q_BYTES + (2 * j + 1) * NP * 64) & 0x3FFFFu) >> 4) | (64u << 16);
-          for (int kk = 0; kk < (NP >> 4); ++kk)
-            umma_ts_raw(t_p + fc * NP + 32 * j, t_p + j * NP + 8 * kk, v_lo + kk * 64, AT_DESC_HI_SW64, idesc_o, kk ? 1u : 0u);
-        }
-        umma_commit(&o_full[b]);
-        umma_commit(&empty[slot]);
-      }
-      __syncwarp();
-      ++pv_k;
-      pv_unit += gridDim.x;
+    // shared-memory row of the unit's first K row inside its slot
+    auto k_row0 = [&](const AtUnit& u) { return p.single ? N : 128 + ((N + 2 * u.f0 * n) & 7); };
+    uint32_t slot = 0, sphase = 0, b = 0, bphase = 0;          // ring slot / TMEM buffer of the current unit and their phase bits
+    auto advance = [&]() {
+      if (++slot == (uint32_t)p.slots) { slot = 0; sphase ^= 1; }
+      if (++b == (uint32_t)G) { b = 0; bphase ^= 1; }
     };
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++k) {
-      const int fc = at_decode(unit, p).fc;
-      const uint32_t b = k % G, slot = k % p.slots;
-      mbar_wait(&full[slot], (k / p.slots) & 1);
-      mbar_wait(&buf_free[b], ((k / G) & 1) ^ 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t qa = (((ring_addr + slot * p.slot_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-        for (int j = 0; j < fc; ++j) {
-          const uint32_t ka = qa + ((AT_Q_BYTES + 2 * j * NP * 64) >> 4);
-          umma_ss_raw(tmem + b * p.buf_cols + j * NP, qa, AT_DESC_HI_SW64, ka, AT_DESC_HI_SW64, idesc_s, 0u);
-          umma_ss_raw(tmem + b * p.buf_cols + j * NP, qa + 2, AT_DESC_HI_SW64, ka + 2, AT_DESC_HI_SW64, idesc_s, 1u);
+    if (warp == 4 * G + 1) {
+      AXVS_PROF_DECL(3)
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        const AtUnit u = at_decode(unit, p);
+        const uint32_t base = ring_addr + slot * p.slot_bytes;
+        const uint32_t qa = ((base & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t k_base = base + k_row0(u) * 64;
+        AXVS_PROF_WAIT(0, mbar_wait(&full[slot], sphase))
+        AXVS_PROF_WAIT(1, mbar_wait(&buf_free[b], bphase ^ 1))
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < u.fc; ++j) {
+          const uint32_t ka = (((k_base + 2 * j * n * 64) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t t_d = tmem + b * p.buf_cols + j * NP;
+          const bool last = j == u.fc - 1;
+          if (elect_one()) {
+            umma_ss_raw(t_d, qa, AT_DESC_HI_SW64, ka, AT_DESC_HI_SW64, idesc_s, 0u);
+            umma_ss_raw(t_d, qa + 2, AT_DESC_HI_SW64, ka + 2, AT_DESC_HI_SW64, idesc_s, 1u);
+            if (last) umma_commit(&s_full[b]);
+          }
+          __syncwarp();
         }
-        umma_commit(&s_full[b]);
+        advance();
       }
-      __syncwarp();
-      if (k + 1 - pv_k >= (uint32_t)G) issue_pv();              // keep the S phase at most G - 1 units ahead of the P V phase
+      AXVS_PROF_FLUSH(56, 3, lane == 0)
+    } else {
+      AXVS_PROF_DECL(1)
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        const AtUnit u = at_decode(unit, p);
+        const uint32_t t_p = tmem + b * p.buf_cols;
+        const uint32_t v_base = ring_addr + slot * p.slot_bytes + (k_row0(u) + n) * 64;
+        AXVS_PROF_WAIT(0, mbar_wait(&p_full[b], bphase))
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < u.fc; ++j) {
+          const uint32_t v_lo = (((v_base + 2 * j * n * 64) & 0x3FFFFu) >> 4) | (64u << 16);
+          const uint32_t t_d = t_p + u.fc * NP + 32 * j, t_a = t_p + j * NP;
+          const bool last = j == u.fc - 1;
+          if constexpr (NT16 > 0) {
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < NT16; ++kk) umma_ts_raw(t_d, t_a + 8 * kk, v_lo + kk * 64, AT_DESC_HI_SW64, idesc_o, kk ? 1u : 0u);
+              if (last) { umma_commit(&o_full[b]); umma_commit(&empty[slot]); }
+            }
+            __syncwarp();
+          } else {
+#pragma unroll 1
+            for (int k0 = 0; k0 < (NP >> 4); k0 += 4) {
+              const int rem = (NP >> 4) - k0;
+              if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  if (kk < rem) umma_ts_raw(t_d, t_a + 8 * (k0 + kk), v_lo + (k0 + kk) * 64, AT_DESC_HI_SW64, idesc_o, (k0 + kk) ? 1u : 0u);
+                if (last && rem <= 4) { umma_commit(&o_full[b]); umma_commit(&empty[slot]); }
+              }
+              __syncwarp();
+            }
+          }
+        }
+        advance();
+      }
+      AXVS_PROF_FLUSH(36, 1, lane == 0)
     }
-    while (pv_k < k) issue_pv();
   }
 
   tc_fence_before();

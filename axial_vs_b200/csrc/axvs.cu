@@ -428,7 +428,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       AXVS_CHECK_LAUNCH("qkv_attn_kernel");
     } else {
     if (g_fusion >= 4 && v_in == q_in) {
-      use_tc = g_attn_core == 1 && (n + 15) / 16 * 16 <= 224;
+      use_tc = g_attn_core == 1 && (n + 15) / 16 * 16 <= 224 && rows * 24 < (size_t)0xffffffffu;
       // the q|k|v GEMM reads the fp32 residual stream (+ pos) itself: no tile-image pack, no a1/a2 round trip
       QkvDirectParams qp;
       memset(&qp, 0, sizeof(qp));
@@ -473,8 +473,9 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       ap.tiles = tiles; ap.N = N; ap.n = n; ap.F = F; ap.NP = nt16_f * 16; ap.QB = (N + 127) / 128;
       ap.scale_log2e = kScaleLog2e;
       // softmax groups (= TMEM buffers) and frames per unit: the most groups that still take two frames per unit
+      const int max_g = nt16_f <= 2 ? 4 : 3;                     // register budget of the softmax warps (launch bounds per NT16)
       int G = 2, FC = 1;
-      for (int g = AT_MAX_G; g >= 2; --g) {
+      for (int g = max_g; g >= 2; --g) {
         const int cols = (512 / g) / 16 * 16;
         int fc = cols / (ap.NP + 32);
         if (fc > AT_MAX_FC) fc = AT_MAX_FC;
@@ -482,22 +483,25 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
         if (fc >= (F < 2 ? F : 2) || (g == 2 && fc >= 1)) { G = g; FC = fc; break; }
       }
       if (G == 2 && FC < (F < 2 ? F : 2)) {                       // long frames: one frame per unit, as many groups as fit
-        for (int g = AT_MAX_G; g >= 2; --g)
+        for (int g = max_g; g >= 2; --g)
           if ((512 / g) / 16 * 16 >= ap.NP + 32) { G = g; FC = 1; break; }
       }
       ap.G = G; ap.FC = FC; ap.buf_cols = (512 / G) / 16 * 16; ap.NCH = (F + FC - 1) / FC;
+      ap.single = (ap.QB == 1 && ap.NCH == 1) ? 1 : 0;
       const long long units = (long long)num_seq * 8 * ap.QB * ap.NCH;
       if (units > 0x7fffffff) return fail(AXVS_E_UNSUPPORTED, "traj_attn: too many attention work units (%lld)", units);
       ap.num_units = (int)units;
-      ap.slot_bytes = AT_Q_BYTES + FC * ap.NP * 128;
-      int slots = (184 * 1024) / ap.slot_bytes;
+      // slot = the rows the bulk copies write + 16 rows the last P V instruction may read past them (>= 144 rows: the M = 128 Q tile)
+      const int slot_rows = ap.single ? (3 * N + 16 > 144 ? 3 * N + 16 : 144) : 128 + 8 + 2 * FC * n + 16;
+      ap.slot_bytes = (slot_rows * 64 + 1023) / 1024 * 1024;
+      int slots = (152 * 1024) / ap.slot_bytes;
       if (slots > AT_MAX_SLOTS) slots = AT_MAX_SLOTS;
-      ap.slots = slots;                                           // >= 5 (at most 36 KiB per slot); G + 1 are needed
-      const size_t smem_b = (size_t)slots * ap.slot_bytes + 512;
+      ap.slots = slots;                                           // >= 4 (at most 36 KiB per slot); G + 1 are needed
+      const size_t smem_b = (size_t)slots * ap.slot_bytes + 4 * AT_MAX_G * 2048 + 512;
       const int grid = ap.num_units < d->sms ? ap.num_units : d->sms;
       {
         ProfScope ps(KC_ATTNTC, 4.0 * num_seq * (double)N * N * 256, (double)rows * (1536.0 + (F + 1) * 512.0), st);
-        const int threads = 128 * G + 64;
+        const int threads = 128 * G + 96;
         switch (nt16_f <= 4 ? nt16_f : 0) {
           case 1: spatial_attn_tc_kernel<1><<<grid, threads, smem_b, st>>>(ap); break;
           case 2: spatial_attn_tc_kernel<2><<<grid, threads, smem_b, st>>>(ap); break;

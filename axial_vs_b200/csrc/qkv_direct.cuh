@@ -35,8 +35,9 @@ struct QkvDirectParams {
   __nv_bfloat16* qkv;      // head-major [3][8][rows][32]
   int rows, tiles, map_mode;
   AxialDims dims;
-  int swz_N, swz_n;        // > 0: permute the 16-byte chunks of every stored row for the tcgen05 attention kernel (attn_tc.cuh): chunk c
-                           // of a q row goes to position c ^ ((i >> 1) & 3), i = row % swz_N; of a k / v row to c ^ ((j >> 1) & 3), j = i % swz_n
+  int swz_N, swz_n;        // > 0: "unit-major" output for the tcgen05 attention kernel (attn_tc.cuh) instead of head-major: one region of
+                           // 3 N rows per (sequence, head) -- Q rows, then K_f | V_f per key frame (N = swz_N tokens per sequence, n = swz_n per
+                           // frame) -- with the 16-byte chunks of the row at region position pos permuted by (pos >> 1) & 3
 };
 
 __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDirectParams p) {
@@ -80,11 +81,15 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
     AXVS_PROF_DECL(1)
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
       const int row0 = tile * 128 + (warp & 3) * 32;           // first row of this warp
-      uint32_t key_q = 0, key_kv = 0;                          // chunk permutation keys of row (row0 + lane), see swz_N
+      uint32_t um_q = 0, um_k = 0, pos_q = 0, pos_k = 0;       // unit-major: rows of q / k of row (row0 + lane) for head 0 (v = k + n), positions inside the region
       if (p.swz_N > 0) {
-        const int i = (row0 + lane) % p.swz_N;
-        key_q = (uint32_t)(i >> 1) & 3u;
-        key_kv = (uint32_t)((i % p.swz_n) >> 1) & 3u;
+        const int r = row0 + lane;
+        const int seq = r / p.swz_N, i = r - seq * p.swz_N;
+        const int f = i / p.swz_n, j = i - f * p.swz_n;
+        pos_q = (uint32_t)i;
+        pos_k = (uint32_t)(p.swz_N + 2 * f * p.swz_n + j);
+        um_q = (uint32_t)seq * 24u * p.swz_N + pos_q;
+        um_k = (uint32_t)seq * 24u * p.swz_N + pos_k;
       }
 #pragma unroll 1
       for (int rt = 0; rt < 6; ++rt, ++cnt) {
@@ -124,14 +129,24 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
           __syncwarp();
           {
             const int which = rt >> 1, head = (rt & 1) * 4 + c;
+            if (p.swz_N > 0) {
+              const uint32_t my_row = (which == 0 ? um_q : um_k + (which == 2 ? p.swz_n : 0)) + (uint32_t)head * 3u * p.swz_N;
+              const uint32_t my_key = ((which == 0 ? pos_q : pos_k + (which == 2 ? p.swz_n : 0)) >> 1) & 3u;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rl = 8 * i + (lane >> 2), piece = lane & 3;
+                const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((piece ^ ((rl >> 1) & 3)) << 4));
+                const uint32_t drow = __shfl_sync(0xffffffffu, my_row, rl), key = __shfl_sync(0xffffffffu, my_key, rl);
+                if (row0 + rl < p.rows) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.qkv) + (size_t)drow * 64 + ((piece ^ key) << 4)) = u;
+              }
+            } else {
             uint8_t* dst = reinterpret_cast<uint8_t*>(p.qkv + ((size_t)(which * 8 + head) * p.rows + row0) * 32);
-            const uint32_t my_key = which == 0 ? key_q : key_kv;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int rl = 8 * i + (lane >> 2), piece = lane & 3;
               const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((piece ^ ((rl >> 1) & 3)) << 4));
-              const uint32_t key = __shfl_sync(0xffffffffu, my_key, rl);
-              if (row0 + rl < p.rows) *reinterpret_cast<uint4*>(dst + rl * 64 + ((piece ^ key) << 4)) = u;
+              if (row0 + rl < p.rows) *reinterpret_cast<uint4*>(dst + rl * 64 + piece * 16) = u;
+            }
             }
           }
           __syncwarp();

@@ -5,8 +5,9 @@ sys.path.insert(0, ".")
 from axial_vs_b200 import _lib, ops, synth
 which = sys.argv[1] if len(sys.argv) > 1 else "ffn"
 clips = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+hw = int(sys.argv[3]) if len(sys.argv) > 3 else 41
 lib = _lib.load()
-rows = clips * 2 * 41 * 41
+rows = clips * 2 * hw * hw
 p = {k: v.cuda() for k, v in synth.axial_layer_params(0).items()}
 pk = ops.pack_layer(p)
 x = torch.randn(rows, 256, device="cuda")
@@ -17,6 +18,9 @@ def run():
     if which == "qkvd":
         ops.set_fusion(4)
         return ops.traj_attn_fwd(x, x, x, x, x, pk.attn_h, clips, 2, 41, 41, ops.AXIS_H)
+    if which == "attn":
+        ops.set_fusion(4)
+        return ops.traj_attn_fwd(x, x, x, x, x, pk.attn_h, clips, 2, hw, hw, ops.AXIS_H)
     if which == "qkv":
         ops.set_fusion(3)
         return ops.traj_attn_fwd(x, x, x, None, x, pk.attn_h, clips, 2, 41, 41, ops.AXIS_H)
@@ -43,6 +47,13 @@ if which == "ffn":
     show("epilogue g0 warp0", 8, ["s_full", "-", "acc_full", "bar.sync", "final:chunks", "final:all", "st_wait"])
     show("epilogue g1 warp4", 16, ["s_full", "-", "acc_full", "bar.sync", "final:chunks", "final:all", "st_wait"])
     show("W producer", 32, ["w_empty"])
+elif which == "attn":
+    tiles = clips * hw * 8          # work units (sequence, head)
+    ctas = min(tiles, 148)
+    show("attn_tc softmax g0 warp0", 52, ["s_full", "o_full"])
+    show("attn_tc S issuer", 56, ["slot full", "buf_free", "-"])
+    show("attn_tc PV issuer", 36, ["p_full"])
+    show("attn_tc producer", 60, ["slot empty"])
 elif which == "qkvd":
     show("qkv_direct MMA warp", 40, ["w_full", "s_empty", "a_full"])
     show("qkv_direct epilogue g0", 44, ["s_full"])
