@@ -37,7 +37,7 @@ class KmaxAxialWeights(Structure):
 
 class AsppWeights(Structure):
     _fields_ = [("w_conv", c_void_p * 3), ("b_conv", c_void_p * 3), ("dilation", c_int * 3), ("w_proj", c_void_p),
-                ("lncf_g", c_void_p), ("lncf_b", c_void_p), ("ln_g", c_void_p), ("ln_b", c_void_p)]
+                ("lncf_g", c_void_p), ("lncf_b", c_void_p), ("ln_g", c_void_p), ("ln_b", c_void_p), ("split", c_int)]
 
 
 class LayerWeights(Structure):
@@ -91,6 +91,9 @@ SIGNATURES = {
     "axvs_panoptic_inference": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_float, c_float, c_float,
                                         c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "axvs_mask_einsum": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "axvs_mask_einsum_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "axvs_linear_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_int, c_int,
+                                c_void_p]),
     "axvs_pos3d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "axvs_profile_enable": (c_int, [c_int]),
     "axvs_profile_num_classes": (c_int, []),

@@ -103,6 +103,7 @@ class _ConvBN1d(nn.Module):
         self.act_code = {None: 0, "relu": 1, "gelu": 2}[act]
         self.cout = cout
         self._cache = _PackedCache()
+        self._cache32 = _PackedCache()
 
     def folded(self):
         w = self.conv.weight.detach().float()[:, :, 0]
@@ -124,6 +125,24 @@ class _ConvBN1d(nn.Module):
             return ops.pack_weight(wp.contiguous()), bp.contiguous(), n_pad
         key_mod = nn.ModuleList([self.conv, self.norm]) if isinstance(self.norm, nn.BatchNorm1d) else self.conv
         return self._cache.get(key_mod, device, build)
+
+    def packed_split(self, device):
+        """Split-precision image of the folded weight (see ops.pack_weight_split) for `run32`."""
+        def build():
+            w, b = self.folded()
+            n_pad = (self.cout + 255) // 256 * 256
+            wp = torch.zeros(n_pad, w.shape[1], device=w.device)
+            wp[: self.cout] = w
+            bp = torch.zeros(n_pad, device=w.device)
+            bp[: self.cout] = b
+            return ops.pack_weight_split(wp), bp.contiguous(), n_pad
+        key_mod = nn.ModuleList([self.conv, self.norm]) if isinstance(self.norm, nn.BatchNorm1d) else self.conv
+        return self._cache32.get(key_mod, device, build)
+
+    def run32(self, a_f32: Tensor, out_dtype=torch.float32) -> Tensor:
+        """fp32 rows in, fp32-grade GEMM (split precision), fp32 (or bf16) rows out."""
+        wp, bp, n_pad = self.packed_split(a_f32.device)
+        return ops.linear_f32(a_f32, wp, bp, n_pad, self.act_code, True, out_dtype)
 
     def run(self, a_bf16: Tensor, out_dtype=torch.bfloat16, extra_bias: Tensor = None) -> Tensor:
         wp, bp, n_pad = self.packed(a_bf16.device)
@@ -176,7 +195,9 @@ class MaXTronCCPredictor(nn.Module):
         return cls.unsqueeze(0)
 
     def mask_kernels(self, mask_embeddings):
-        """CC:53: bf16 [T*Q, 256] rows (t, q), 128 valid columns."""
+        """CC:53: [T*Q, 256] rows (t, q), 128 valid columns; fp32 embeddings -> fp32 kernels through the split-precision GEMM."""
+        if mask_embeddings.dtype == torch.float32:
+            return self._transformer_mask_head.run32(mask_embeddings)
         return self._transformer_mask_head.run(mask_embeddings)
 
     def mask_logits(self, mk, pixel_feature, num_clips):
@@ -190,7 +211,7 @@ class MaXTronCCPredictor(nn.Module):
         return ops.mask_einsum(pixel_feature.contiguous().float(), mk.contiguous(), T, Q, VH * Wd, sc, sh)
 
     def forward(self, mask_embeddings, class_embeddings, pixel_feature, num_clips, num_clip_frames):
-        """mask/class embeddings: bf16 [T*Q, 256] rows (t, q); pixel_feature fp32 [T, 128, V*H, W]."""
+        """mask embeddings fp32 (or bf16), class embeddings bf16: [T*Q, 256] rows (t, q); pixel_feature fp32 [T, 128, V*H, W]."""
         T = num_clips
         Q = class_embeddings.shape[0] // T
         cls = self.class_logits(class_embeddings, T)
@@ -242,8 +263,10 @@ class CrossClipTrackingModule(nn.Module):
             x = self.transformer_trajectory_self_attention_layers[i](x, seq_len=Q, num_frames=T)                 # LN(x + TA(x))
             x32, x16 = ops.cc_aspp_fwd(x.view(-1, C), self._packed_aspp(i, x.device), b, T, Q)                     # LN(ASPP(z) + z)
             x = x32.view(b, T * Q, C)
-            ce = self._class_embedding_projection.run(x16)
-            me = self._mask_embedding_projection.run(x16)
+            # the mask branch (embedding projection -> mask head -> query x pixel contraction) runs fp32-grade (split precision): it
+            # decides the per-pixel argmax labels, and its rows are few.  The class branch pools bf16 embeddings as before.
+            ce = self._class_embedding_projection.run32(x32, torch.bfloat16)
+            me = self._mask_embedding_projection.run32(x32)
             r = self._predictor(me, ce, pf, T, V)
             predictions_class.append(r["class_logits"])
             predictions_mask.append(r["mask_logits"])
@@ -277,8 +300,8 @@ class CrossClipTrackingModule(nn.Module):
                 x = self.transformer_trajectory_self_attention_layers[i](x, seq_len=Q, num_frames=T)
                 x32, x16 = ops.cc_aspp_fwd(x.view(-1, C), self._packed_aspp(i, x.device), 1, T, Q)
                 x = x32.view(1, T * Q, C)
-            ce = self._class_embedding_projection.run(x16)
-            me = self._mask_embedding_projection.run(x16)
+            ce = self._class_embedding_projection.run32(x32, torch.bfloat16)
+            me = self._mask_embedding_projection.run32(x32)
             return self._predictor.class_logits(ce, T), self._predictor.mask_kernels(me)
 
         def masks(mk_local, pf_local, t_local):

@@ -158,7 +158,8 @@ int device_info(DeviceInfo** out) {
     d.pair_attr = true;
   }
   if (!d.mask_attr) {
-    if (cudaFuncSetAttribute(mask_einsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 256) != cudaSuccess)
+    if (cudaFuncSetAttribute(mask_einsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 256) != cudaSuccess ||
+        cudaFuncSetAttribute(mask_einsum_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 128 * 256) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(mask_einsum) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.mask_attr = true;
   }
@@ -861,7 +862,8 @@ int axvs_cast_bf16(const float* x, void* out_bf16, int rows, axvs_stream_t strea
 
 size_t axvs_cc_aspp_workspace_bytes(int rows) {
   if (rows <= 0) return 0;
-  return align256((size_t)rows * 256 * 2) + align256((size_t)rows * 768 * 2) + align256((size_t)rows * 256 * 4);
+  // bf16 path: x (bf16) | cat (bf16) | y (fp32);  split-precision path: gathered taps (fp32) | cat (fp32) | y (fp32)
+  return align256((size_t)rows * 768 * 4) + align256((size_t)rows * 768 * 4) + align256((size_t)rows * 256 * 4);
 }
 
 int axvs_cc_aspp_fwd(const float* x, float* out, void* out_bf16, const axvs_aspp_weights* w, int b, int T, int Q, void* workspace,
@@ -881,6 +883,37 @@ int axvs_cc_aspp_fwd(const float* x, float* out, void* out_bf16, const axvs_aspp
   float* y = reinterpret_cast<float*>(base + align256((size_t)rows * 256 * 2) + align256((size_t)rows * 768 * 2));
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
+  if (w->split) {
+    // split-precision path (weights packed [W | W | W - bf16(W)]): fp32-grade products on the bf16 tensor cores.  The rows are few
+    // (clips x queries), so the 3x tensor work is free, and the query embeddings that decide the per-pixel labels keep fp32 accuracy.
+    DeviceInfo* dv;
+    if ((rc = device_info(&dv))) return rc;
+    float* z32 = reinterpret_cast<float*>(base);
+    float* cat32 = reinterpret_cast<float*>(base + align256((size_t)rows * 768 * 4));
+    float* y32 = reinterpret_cast<float*>(base + 2 * align256((size_t)rows * 768 * 4));
+    for (int i = 0; i < 3; ++i) {
+      {
+        ProfScope ps(KC_CCTAIL, 0, (double)rows * 768 * 8.0, st);
+        aspp_gather_kernel<<<blocks_for(rows, 8, dv->sms), 256, 0, st>>>(x, z32, rows, T, Q, w->dilation[i]);
+      }
+      AXVS_CHECK_LAUNCH("aspp_gather_kernel");
+      GemmParams p = gemm_params(nullptr, 768, rows, 3 * 768, w->w_conv[i], 256, 0, w->b_conv[i], 256, 1.f, 0, cat32, 768, 256 * i, 0, nullptr);
+      p.a_diag = 4; p.A32 = z32; p.a_split = 1;
+      if ((rc = launch_gemm(p, st))) return rc;
+    }
+    {
+      GemmParams p = gemm_params(nullptr, 768, rows, 3 * 768, w->w_proj, 256, 0, nullptr, 256, 1.f, 0, y32, 256, 0, 0, nullptr);
+      p.a_diag = 4; p.A32 = cat32; p.a_split = 1;
+      if ((rc = launch_gemm(p, st))) return rc;
+    }
+    {
+      ProfScope ps(KC_CCTAIL, 0, (double)rows * 256 * 14.0, st);
+      aspp_tail_kernel<<<blocks_for(rows, 8, dv->sms), 256, 0, st>>>(y32, x, w->lncf_g, w->lncf_b, w->ln_g, w->ln_b, out,
+                                                                   reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, 1e-6f, 1e-5f);
+    }
+    AXVS_CHECK_LAUNCH("aspp_tail_kernel");
+    return AXVS_OK;
+  }
   if ((rc = axvs_cast_bf16(x, xb, rows, stream))) return rc;
   for (int i = 0; i < 3; ++i) {       // three dilated k=3 convs over time = GEMMs with K = 3 x 256 on time-shifted rows
     GemmParams p = gemm_params(xb, 256, rows, 768, w->w_conv[i], 256, 0, w->b_conv[i], 256, 1.f, 0, cat, 768, 256 * i, 1, nullptr);
@@ -932,6 +965,36 @@ int axvs_mask_einsum(const float* pixel, const void* mk_bf16, int ld_mk, float* 
   }
   AXVS_CHECK_LAUNCH("mask_einsum_kernel");
   return AXVS_OK;
+}
+
+int axvs_mask_einsum_f32(const float* pixel, const float* mk, int ld_mk, float* out, int T, int Q, int P, float bn_scale, float bn_shift,
+                         axvs_stream_t stream) {
+  if (!pixel || !mk || !out) return fail(AXVS_E_INVALID, "mask_einsum_f32: null pointer");
+  if (T <= 0 || Q <= 0 || P <= 0) return fail(AXVS_E_INVALID, "mask_einsum_f32: sizes must be positive");
+  if (Q > 128) return fail(AXVS_E_UNSUPPORTED, "mask_einsum_f32: at most 128 queries per clip (got %d)", Q);
+  if (ld_mk < 128 || ld_mk % 4) return fail(AXVS_E_INVALID, "mask_einsum_f32: ld_mk must be >= 128 and a multiple of 4");
+  if (T > 65535) return fail(AXVS_E_UNSUPPORTED, "mask_einsum_f32: at most 65535 clips");
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  dim3 grid((P + ME_PT - 1) / ME_PT, T);
+  {
+    ProfScope ps(KC_MASK, 6.0 * T * (double)Q * P * 128, (double)T * P * (512.0 + 4.0 * Q), (cudaStream_t)stream);
+    mask_einsum_split_kernel<<<grid, 256, 4 * 128 * 256, (cudaStream_t)stream>>>(pixel, mk, ld_mk, out, T, Q, P, bn_scale, bn_shift);
+  }
+  AXVS_CHECK_LAUNCH("mask_einsum_split_kernel");
+  return AXVS_OK;
+}
+
+int axvs_linear_f32(const float* a, int lda, int M, int K, const void* w_packed, int split, const float* bias, int n_out, float scale, int act,
+                    void* out, int ldo, int out_bf16, axvs_stream_t stream) {
+  if (!a || !w_packed || !out) return fail(AXVS_E_INVALID, "linear_f32: null pointer");
+  if (lda < K || ldo < n_out) return fail(AXVS_E_INVALID, "linear_f32: leading dimension too small");
+  if ((lda % 4) || (ldo % 8)) return fail(AXVS_E_UNSUPPORTED, "linear_f32: lda must be a multiple of 4 and ldo of 8");
+  if (act < 0 || act > 2) return fail(AXVS_E_INVALID, "linear_f32: activation code must be 0 (none), 1 (ReLU) or 2 (GELU)");
+  GemmParams p = gemm_params(nullptr, lda, M, split ? 3 * K : K, w_packed, n_out, 0, bias, n_out, scale, act, out, ldo, 0, out_bf16, nullptr);
+  p.a_diag = 4; p.A32 = a; p.a_split = split ? 1 : 0;
+  return launch_gemm(p, (cudaStream_t)stream);
 }
 
 int axvs_query_self_attn(const float* q, const float* k, const float* v, const float* sim_affine, const float* val_affine, float* out, int N,

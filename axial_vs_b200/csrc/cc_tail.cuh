@@ -186,4 +186,126 @@ __global__ void __launch_bounds__(256) mask_einsum_kernel(const float* __restric
   }
 }
 
+
+// Split-precision variant of mask_einsum_kernel: both operands arrive in fp32 and are split into bf16 hi / lo = bf16(x - hi) halves in
+// shared memory; acc += A_hi B_hi + A_hi B_lo + A_lo B_hi reproduces the fp32 product to ~2^-17 on the bf16 tensor cores.  The kernel
+// stays HBM-bound (the pixel tile is read once), so the extra MMAs are free -- and the per-pixel argmax over the queries, which decides
+// the final panoptic label, no longer flips on near-ties because of operand rounding (tests/test_error_budget_cpu.py).
+__global__ void __launch_bounds__(256) mask_einsum_split_kernel(const float* __restrict__ pixel, const float* __restrict__ mk, int ld_mk,
+                                                                float* __restrict__ out, int T, int Q, int P, float bn_scale, float bn_shift) {
+  extern __shared__ __align__(128) uint8_t me_smem[];
+  uint8_t* sBh = me_smem;                    // [128 c][128 p] bf16 hi
+  uint8_t* sBl = me_smem + 128 * 256;        // lo
+  uint8_t* sAh = me_smem + 2 * 128 * 256;    // [128 q][128 c] bf16 hi
+  uint8_t* sAl = me_smem + 3 * 128 * 256;
+  const int t = blockIdx.y;
+  const int p0 = blockIdx.x * ME_PT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  auto off = [](int row, int chunk) { return row * 256 + ((chunk ^ (row & 7)) << 4); };
+  auto split8 = [](const float (&x)[8], uint4& hi, uint4& lo) {
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = x[i] - __bfloat162float(__float2bfloat16_rn(x[i]));
+    hi = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+    lo = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+  };
+  for (int c = tid; c < 128 * 16; c += 256) {
+    const int q = c >> 4, ch = c & 15;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = 0.f;
+    if (q < Q) {
+      const float4* s = reinterpret_cast<const float4*>(mk + ((size_t)t * Q + q) * ld_mk + ch * 8);
+      const float4 a = __ldg(s), b = __ldg(s + 1);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    *reinterpret_cast<uint4*>(sAh + off(q, ch)) = hi;
+    *reinterpret_cast<uint4*>(sAl + off(q, ch)) = lo;
+  }
+  const float* px = pixel + (size_t)t * 128 * P;
+  const bool vec_ok = (P % 4 == 0);
+  for (int c = tid; c < 128 * 16; c += 256) {
+    const int ch_row = c >> 4, chunk = c & 15;
+    const int p = p0 + chunk * 8;
+    float x[8];
+    const float* src = px + (size_t)ch_row * P + p;
+    if (vec_ok && p + 8 <= P) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = (p + i < P) ? __ldg(src + i) : 0.f;
+    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    *reinterpret_cast<uint4*>(sBh + off(ch_row, chunk)) = hi;
+    *reinterpret_cast<uint4*>(sBl + off(ch_row, chunk)) = lo;
+  }
+  __syncthreads();
+
+  float acc[16][4];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll 2
+  for (int ks = 0; ks < 8; ++ks) {                     // k = channel, 16 per step
+    uint32_t ah[4], al[4];
+    {
+      const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      ldmatrix_x4(ah, sAh + off(r, ks * 2 + (lane >> 4)));
+      ldmatrix_x4(al, sAl + off(r, ks * 2 + (lane >> 4)));
+    }
+#pragma unroll
+    for (int jn = 0; jn < 16; jn += 2) {               // n = pixel, 8 per tile
+      uint32_t bh[4], bl[4];
+      const int krow = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      ldmatrix_x4_trans(bh, sBh + off(krow, jn + (lane >> 4)));
+      ldmatrix_x4_trans(bl, sBl + off(krow, jn + (lane >> 4)));
+      mma_bf16_16816(acc[jn], al, bh[0], bh[1]);       // small terms first
+      mma_bf16_16816(acc[jn], ah, bl[0], bl[1]);
+      mma_bf16_16816(acc[jn], ah, bh[0], bh[1]);
+      mma_bf16_16816(acc[jn + 1], al, bh[2], bh[3]);
+      mma_bf16_16816(acc[jn + 1], ah, bl[2], bl[3]);
+      mma_bf16_16816(acc[jn + 1], ah, bh[2], bh[3]);
+    }
+  }
+  const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int q = warp * 16 + g + h * 8;
+    if (q >= Q) continue;
+    float* orow = out + ((size_t)q * T + t) * P + p0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int p = j * 8 + t4 * 2;
+      const float v0 = acc[j][h * 2] * bn_scale + bn_shift, v1 = acc[j][h * 2 + 1] * bn_scale + bn_shift;
+      if (p0 + p + 1 < P && ((P & 1) == 0)) *reinterpret_cast<float2*>(orow + p) = make_float2(v0, v1);
+      else {
+        if (p0 + p < P) orow[p] = v0;
+        if (p0 + p + 1 < P) orow[p + 1] = v1;
+      }
+    }
+  }
+}
+
+// z[r, tap*256 + c] = x[row of (b, clamp(t + (tap - 1) * dilation, 0, T-1), q), c]: the A operand of one dilated temporal convolution
+// (Conv1d k = 3, padding 'same', replicate; CC:180-182) as an fp32 matrix, for the split-precision GEMM.  One warp per row.
+__global__ void aspp_gather_kernel(const float* __restrict__ x, float* __restrict__ z, int rows, int T, int Q, int dilation) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const int t = (r / Q) % T;
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap) {
+      int t2 = t + (tap - 1) * dilation;
+      t2 = t2 < 0 ? 0 : (t2 >= T ? T - 1 : t2);
+      const float4* s = reinterpret_cast<const float4*>(x + ((size_t)r + (ptrdiff_t)(t2 - t) * Q) * C256) + lane * 2;
+      float4* d = reinterpret_cast<float4*>(z + (size_t)r * 768 + tap * C256) + lane * 2;
+      d[0] = __ldg(s);
+      d[1] = __ldg(s + 1);
+    }
+  }
+}
+
 }  // namespace axvs

@@ -414,6 +414,7 @@ class PackedAspp:
     lncf_b: torch.Tensor
     ln_g: torch.Tensor
     ln_b: torch.Tensor
+    split: bool = False
 
     def struct(self) -> "_lib.AsppWeights":
         s = _lib.AsppWeights()
@@ -423,24 +424,34 @@ class PackedAspp:
             s.dilation[i] = int(self.dilation[i])
         s.w_proj = self.w_proj.data_ptr()
         s.lncf_g, s.lncf_b, s.ln_g, s.ln_b = (t.data_ptr() for t in (self.lncf_g, self.lncf_b, self.ln_g, self.ln_b))
+        s.split = int(self.split)
         return s
 
 
-def pack_aspp(p: Dict[str, torch.Tensor], ln_w: torch.Tensor, ln_b: torch.Tensor, atrous_rates: Sequence[int]) -> PackedAspp:
-    """Pack an `ASPP` state dict (CC:176-201) + the following `conv_norms[i]` LayerNorm."""
+def pack_weight_split(w: torch.Tensor) -> torch.Tensor:
+    """Split-precision image of an fp32 weight [n_out, k]: [W | W | W - bf16(W)] packed as [n_out, 3k] (include/axvs.h, axvs_linear_f32)."""
+    w = w.detach().float()
+    return pack_weight(torch.cat((w, w, w - w.bfloat16().float()), dim=1).contiguous())
+
+
+def pack_aspp(p: Dict[str, torch.Tensor], ln_w: torch.Tensor, ln_b: torch.Tensor, atrous_rates: Sequence[int], split: bool = True) -> PackedAspp:
+    """Pack an `ASPP` state dict (CC:176-201) + the following `conv_norms[i]` LayerNorm.  split=True (default): split-precision
+    weight images, fp32-grade GEMMs (the rows are clips x queries: the 3x tensor work is negligible)."""
     def g(name):
         return p[name].detach().float().contiguous()
+
+    pw = pack_weight_split if split else pack_weight
 
     wc, bc = [], []
     for i in range(3):
         w = g(f"_aspp_conv{i}.weight")                                  # [256, 256, 3] (out, in, tap)
         if w.shape[-1] != 3:
             raise NotImplementedError("axial_vs_b200: ASPP kernel_size must be 3 (every shipped config)")
-        wc.append(pack_weight(w.permute(0, 2, 1).reshape(256, 768).contiguous()))   # K index = tap * 256 + c_in
+        wc.append(pw(w.permute(0, 2, 1).reshape(256, 768).contiguous()))   # K index = tap * 256 + c_in
         bc.append(g(f"_aspp_conv{i}.bias"))
-    wproj = pack_weight(g("_proj_conv_bn_act.conv.weight")[:, :, 0].contiguous())   # [256, 768]
+    wproj = pw(g("_proj_conv_bn_act.conv.weight")[:, :, 0].contiguous())   # [256, 768]
     return PackedAspp(wc, bc, [int(r) for r in atrous_rates], wproj, g("_proj_conv_bn_act.norm.weight"), g("_proj_conv_bn_act.norm.bias"),
-                      ln_w.detach().float().contiguous(), ln_b.detach().float().contiguous())
+                      ln_w.detach().float().contiguous(), ln_b.detach().float().contiguous(), bool(split))
 
 
 def cc_aspp_fwd(x: torch.Tensor, w: PackedAspp, b: int, T: int, Q: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -473,6 +484,20 @@ def linear_act(a: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Ten
         rc = lib.axvs_linear(a.data_ptr(), K, M, K, w_packed.data_ptr(), _ptr(bias), n_out, 1.0, int(act), out.data_ptr(), n_out,
                              int(out_dtype == torch.bfloat16), None, _stream(a.device))
     _lib.check(rc, "axvs_linear")
+    return out
+
+
+def linear_f32(a: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], n_out: int, act: int = 0, split: bool = True,
+               out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """act(a W^T + bias) on fp32 rows a [M, K]; split=True: w_packed from `pack_weight_split`, fp32-grade product (axvs_linear_f32)."""
+    _check(a, "a", torch.float32)
+    M, K = a.shape
+    out = torch.empty(M, n_out, dtype=out_dtype, device=a.device)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        rc = lib.axvs_linear_f32(a.data_ptr(), K, M, K, w_packed.data_ptr(), int(split), _ptr(bias), n_out, 1.0, int(act), out.data_ptr(), n_out,
+                                 int(out_dtype == torch.bfloat16), _stream(a.device))
+    _lib.check(rc, "axvs_linear_f32")
     return out
 
 
@@ -629,15 +654,18 @@ def kmeans_update(mask_logits: torch.Tensor, pixel_value: torch.Tensor, advanced
 
 
 def mask_einsum(pixel: torch.Tensor, mk: torch.Tensor, T: int, Q: int, P: int, bn_scale: float, bn_shift: float) -> torch.Tensor:
-    """out[q, t, p] = bn_scale * sum_c pixel[t, c, p] mk[t*Q + q, c] + bn_shift; pixel fp32 [T, 128, P], mk bf16 [T*Q, ld >= 128]."""
+    """out[q, t, p] = bn_scale * sum_c pixel[t, c, p] mk[t*Q + q, c] + bn_shift; pixel fp32 [T, 128, P], mk [T*Q, ld >= 128]:
+    bf16 (plain bf16 products) or fp32 (split-precision products, fp32-grade logits)."""
     _check(pixel, "pixel", torch.float32)
-    _check(mk, "mk", torch.bfloat16)
+    if mk.dtype not in (torch.bfloat16, torch.float32):
+        raise RuntimeError("mask_einsum: mk must be bf16 or fp32")
+    _check(mk, "mk", mk.dtype)
     if pixel.numel() != T * 128 * P or mk.shape[0] != T * Q:
         raise RuntimeError("mask_einsum: size mismatch")
     out = torch.empty(Q, T, P, dtype=torch.float32, device=pixel.device)
     lib = _lib.load()
+    fn = lib.axvs_mask_einsum_f32 if mk.dtype == torch.float32 else lib.axvs_mask_einsum
     with torch.cuda.device(pixel.device):
-        rc = lib.axvs_mask_einsum(pixel.data_ptr(), mk.data_ptr(), mk.shape[1], out.data_ptr(), T, Q, P, float(bn_scale), float(bn_shift),
-                                  _stream(pixel.device))
+        rc = fn(pixel.data_ptr(), mk.data_ptr(), mk.shape[1], out.data_ptr(), T, Q, P, float(bn_scale), float(bn_shift), _stream(pixel.device))
     _lib.check(rc, "axvs_mask_einsum")
     return out

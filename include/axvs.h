@@ -173,6 +173,9 @@ typedef struct axvs_aspp_weights {
   const void* w_proj;                              /* 1x1 conv [256, 768], no bias */
   const float* lncf_g; const float* lncf_b;        /* channels-first LayerNorm, eps 1e-6 */
   const float* ln_g;   const float* ln_b;          /* conv_norms[i], eps 1e-5 */
+  int split;                                       /* 1: w_conv / w_proj are split-precision images [W | W | W - bf16(W)] ([256, 3*768]) and the
+                                                    *    GEMMs run on fp32 rows split into bf16 hi / lo halves: fp32-grade results (default of the
+                                                    *    Python layer: the rows are few, and these embeddings decide the per-pixel labels) */
 } axvs_aspp_weights;
 size_t axvs_cc_aspp_workspace_bytes(int rows);
 int axvs_cc_aspp_fwd(const float* x, float* out, void* out_bf16, const axvs_aspp_weights* w, int b, int T, int Q,
@@ -187,6 +190,16 @@ int axvs_cc_class_pool(const void* ce_bf16, const float* w_act, float b_act, voi
  * out fp32 [Q, T, P] == the reference's final [1, Q, (T V), H, W]. */
 int axvs_mask_einsum(const float* pixel, const void* mk_bf16, int ld_mk, float* out, int T, int Q, int P, float bn_scale,
                      float bn_shift, axvs_stream_t stream);
+/* The same contraction with fp32 mask kernels and split-precision products (both operands split into bf16 hi / lo halves in shared
+ * memory, three tensor-core products per pair): fp32-grade logits at the same HBM-bound cost.  mk fp32 rows (t, q), ld_mk % 4 == 0. */
+int axvs_mask_einsum_f32(const float* pixel, const float* mk, int ld_mk, float* out, int T, int Q, int P, float bn_scale,
+                         float bn_shift, axvs_stream_t stream);
+/* out = act((a W^T + bias) * scale) on fp32 rows a [M, lda] (converted inside the GEMM's producers).  split = 1: w_packed is the
+ * split-precision image of [n_out, 3*K] = [W | W | W - bf16(W)] (axvs_pack_weight) and a is split into bf16 hi / lo halves:
+ * a_hi W_hi + a_lo W_hi + a_hi W_lo, the fp32 product to ~2^-17.  act: 0 none, 1 ReLU, 2 GELU (erf).  n_out % 256 == 0, K % 64 == 0.
+ * Replaces the eval-mode ConvBN 1x1 heads of CC:53, 266-270, 300-301 (batch norm folded into W / bias by the caller). */
+int axvs_linear_f32(const float* a, int lda, int M, int K, const void* w_packed, int split, const float* bias, int n_out, float scale, int act,
+                    void* out, int ldo, int out_bf16, axvs_stream_t stream);
 
 /* ---- clip-level kMaX decoder attention, query side ----------------------------------------
  * DEC = Vk/maxtron_deeplab/modeling/transformer_decoder/maxtron_transformer_decoder.py

@@ -41,8 +41,20 @@ def _sub(params: Params, prefix: str) -> Params:
     return {k[len(p):]: v for k, v in params.items() if k.startswith(p)}
 
 
+# Error-budget emulation (tests/test_error_budget_cpu.py only): stages named here round their matmul operands to bf16 (fp32 /
+# fp64 accumulation), which is what the CUDA path does; empty = the plain reference arithmetic.
+#   "ta"     q/k/v/proj_q/proj_kv/proj/FFN linears and the attention operands (q, k, v, P, x, q2, o)
+#   "aspp"   the temporal ASPP convolutions           "proj"   the ConvBN 1x1 projections / heads
+#   "einsum" the query x pixel mask contraction
+EMULATE_BF16: set = set()
+
+
+def _rb(x: Tensor, stage: str) -> Tensor:
+    return x.bfloat16().to(x.dtype) if stage in EMULATE_BF16 else x
+
+
 def linear(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
-    y = x @ w.to(x.dtype).t()
+    y = _rb(x, "ta") @ _rb(w.to(x.dtype), "ta").t()
     return y if b is None else y + b.to(x.dtype)
 
 
@@ -86,7 +98,7 @@ def trajectory_attention_core(q: Tensor, k: Tensor, v: Tensor, p: Params, num_fr
     def heads(t):                                            # 'b n (h d) -> b h n d'   :47-48
         return t.reshape(Bp, N, h, d).permute(0, 2, 1, 3)
 
-    qh, kh, vh = heads(q), heads(k), heads(v)                # [B', h, N, d]
+    qh, kh, vh = heads(_rb(q, "ta")), heads(_rb(k, "ta")), heads(_rb(v, "ta"))   # [B', h, N, d]
 
     # spatial attention, softmax taken independently inside every key frame      :51-60
     x = q.new_zeros(Bp, N, F, C)
@@ -98,23 +110,24 @@ def trajectory_attention_core(q: Tensor, k: Tensor, v: Tensor, p: Params, num_fr
         a = softmax_last(s)                                  # softmax over the n keys of frame f :54
         if return_maps:
             maps[:, :, :, f, :] = a
-        xf = a @ vf                                          # [B', h, N, d]           :56-57
+        xf = _rb(a, "ta") @ vf                               # [B', h, N, d]           :56-57
         x[:, :, f, :] = xf.permute(0, 2, 1, 3).reshape(Bp, N, C)   # merge heads, head-major   :60
 
     # x_diag: for query token t = g*n + i take the aggregation over its own frame g      :61-63
     frame_of_token = torch.arange(N, device=q.device) // n
+    x = _rb(x, "ta")
     x_diag = x[:, torch.arange(N, device=q.device), frame_of_token, :]        # [B', N, C]
 
     q2 = linear(x_diag, p["proj_q.weight"], p["proj_q.bias"]) * scale         # :64,67
     kv2 = linear(x, p["proj_kv.weight"], p["proj_kv.bias"])                   # [B', N, F, 2C]   :65
     k2, v2 = kv2[..., :C], kv2[..., C:]                                       # chunk(2): k2 first
-    q2h = q2.reshape(Bp, N, h, d)
+    q2h = _rb(q2, "ta").reshape(Bp, N, h, d)
     k2h = k2.reshape(Bp, N, F, h, d)
     v2h = v2.reshape(Bp, N, F, h, d)
     logits = (q2h[:, :, None, :, :] * k2h).sum(-1)                            # [B', N, F, h]   :70
     a2 = softmax_last(logits.permute(0, 1, 3, 2))                             # softmax over F  :71
     o = (a2.permute(0, 1, 3, 2)[..., None] * v2h).sum(2)                      # [B', N, h, d]   :72
-    o = o.reshape(Bp, N, C)                                                   # :73
+    o = _rb(o.reshape(Bp, N, C), "ta")                                        # :73
     y = linear(o, p["proj.weight"], p["proj.bias"])                           # :75
 
     if return_intermediates:
@@ -283,7 +296,7 @@ def conv1d_same_replicate(x: Tensor, w: Tensor, b: Optional[Tensor], dilation: i
     t_idx = torch.arange(T)
     for j in range(k):
         src_t = (t_idx - left + j * dilation).clamp(0, T - 1)
-        out += torch.einsum("oc,mct->mot", w[:, :, j].to(x.dtype), x[:, :, src_t])
+        out += torch.einsum("oc,mct->mot", _rb(w[:, :, j].to(x.dtype), "aspp"), _rb(x[:, :, src_t], "aspp"))
     if b is not None:
         out = out + b.to(x.dtype)[None, :, None]
     return out
@@ -310,7 +323,7 @@ def aspp(x: Tensor, p: Params, atrous_rates=(1, 2, 3), norm_fn: str = "ln") -> T
     r = [conv1d_same_replicate(x, p[f"_aspp_conv{i}.weight"], p[f"_aspp_conv{i}.bias"], atrous_rates[i])
          for i in range(3)]
     z = torch.cat(r, dim=1)                                                       # [M, 3C, T]
-    z = torch.einsum("oc,mct->mot", p["_proj_conv_bn_act.conv.weight"][:, :, 0].to(x.dtype), z)   # 1x1, no bias
+    z = torch.einsum("oc,mct->mot", _rb(p["_proj_conv_bn_act.conv.weight"][:, :, 0].to(x.dtype), "aspp"), _rb(z, "aspp"))   # 1x1, no bias
     if norm_fn == "ln":
         z = layer_norm_channels_first(z, p["_proj_conv_bn_act.norm.weight"], p["_proj_conv_bn_act.norm.bias"])
     elif norm_fn == "syncbn":
@@ -321,7 +334,7 @@ def aspp(x: Tensor, p: Params, atrous_rates=(1, 2, 3), norm_fn: str = "ln") -> T
 def conv_bn_1d(x: Tensor, p: Params, prefix: str, norm: Optional[str], act: Optional[str]) -> Tensor:
     """ConvBN(conv_type='1d', kernel_size=1) in eval -- Vk/kmax_deeplab/modeling/pixel_decoder/kmax_pixel_decoder.py:42-72."""
     w = p[prefix + ".conv.weight"][:, :, 0].to(x.dtype)
-    y = torch.einsum("oc,bcn->bon", w, x)
+    y = torch.einsum("oc,bcn->bon", _rb(w, "proj"), _rb(x, "proj"))
     if prefix + ".conv.bias" in p:
         y = y + p[prefix + ".conv.bias"].to(x.dtype)[None, :, None]
     if norm == "syncbn":
@@ -345,7 +358,7 @@ def cc_predictor(mask_emb: Tensor, class_emb: Tensor, pixel_feature: Tensor, p: 
     bias[-1] = math.log((cls.shape[-1] - 1) * 0.9 / (1 - 0.9))                             # add_bias_towards_void
     cls = cls + bias
     mk = conv_bn_1d(mask_emb, p, "_transformer_mask_head", "syncbn", None)                 # [T',128,Q] :53
-    logits = torch.einsum("bchw,bcn->bnhw", pixel_feature, mk)                             # :62-67
+    logits = torch.einsum("bchw,bcn->bnhw", _rb(pixel_feature, "einsum"), _rb(mk, "einsum"))   # :62-67
     logits = batch_norm_eval(logits.unsqueeze(1), p, "_pixel_space_mask_batch_norm").squeeze(1)   # :68
     Tp, Q, VH, Wd = logits.shape
     V = num_clip_frames

@@ -496,10 +496,11 @@ def test_cross_clip_module_golden(golden):
     ref_logits, ref_masks = torch.from_numpy(gz["pred_logits"]), torch.from_numpy(gz["pred_masks"])
     assert tuple(o["pred_logits"].shape) == tuple(ref_logits.shape) and tuple(o["pred_masks"].shape) == tuple(ref_masks.shape)
     assert nerr(o["pred_logits"], ref_logits) < TOL
-    assert nerr(o["pred_masks"], ref_masks) < 2e-2          # bf16 pixel features x bf16 mask kernels, K = 128
+    assert nerr(o["pred_masks"], ref_masks) < TOL           # the mask branch runs split-precision (fp32-grade) after the bf16 attention
     agree = (o["pred_masks"].cpu().argmax(1) == ref_masks.argmax(1)).float().mean().item()
-    assert agree >= 0.97, agree                            # tiny random-init logits: near-ties dominate the disagreements
-    assert nerr(o["aux_outputs"][0]["pred_masks"], torch.from_numpy(gz["aux_masks"])) < 2e-2
+    print(f"[cc_module golden] per-pixel argmax agreement {agree:.5f}")
+    assert agree >= 0.995, agree                           # tiny random-init logits: near-ties dominate the disagreements
+    assert nerr(o["aux_outputs"][0]["pred_masks"], torch.from_numpy(gz["aux_masks"])) < TOL
 
 
 def test_cross_clip_module_oracle_cfg3_shard(O):
@@ -517,14 +518,16 @@ def test_cross_clip_module_oracle_cfg3_shard(O):
     with torch.no_grad():
         o = m(cq.cuda(), pf.cuda())
     assert nerr(o["pred_logits"], ref["pred_logits"]) < TOL
-    assert nerr(o["pred_masks"], ref["pred_masks"]) < 2e-2
+    assert nerr(o["pred_masks"], ref["pred_masks"]) < TOL
     assert nerr(m.last_clip_query, ref["clip_query"]) < TOL
     # north_star: per-pixel agreement of the final argmax labels (query index per pixel, class per query).  With RANDOM-INIT heads
-    # the 128 queries' logits of a pixel are nearly tied, so bf16 rounding flips about 1 % of them; the
-    # checkable statement is that labels differ only where the reference's top-2 margin is inside the numerical error.
+    # the 128 queries' logits of a pixel are nearly tied (median top-2 margin ~ 4 % of the logit range), so the
+    # agreement measures operand rounding directly.  The stages after the bf16 trajectory attention run split-precision
+    # (tests/test_error_budget_cpu.py shows each of them cost more agreement in bf16 than the whole attention).
     got, want = o["pred_masks"].float().cpu(), ref["pred_masks"].float()
     agree = (got.argmax(1) == want.argmax(1)).float().mean().item()
-    assert agree >= 0.98, f"per-pixel mask argmax agreement {agree:.5f}"
+    print(f"[cfg3 shard] per-pixel argmax agreement {agree:.5f}, logit error {nerr(got, want):.2e}")
+    assert agree >= 0.998, f"per-pixel mask argmax agreement {agree:.5f}"     # measured 0.9988 = the bf16-attention bound of the error budget
     top2 = want.topk(2, dim=1).values
     margin = top2[:, 0] - top2[:, 1]
     err = (got - want).abs().max().item()
@@ -964,3 +967,51 @@ def test_kmax_axial_tensor_core_and_simt_paths_agree():
     finally:
         lib.axvs_set_kmax_tensor_cores(1)
     assert nerr(b, a) < 1e-4
+
+
+# --------------------------------------------------------------------------------------------- end-to-end labels (row N1)
+def test_label_agreement_end_to_end(O):
+    """GPU logits -> GPU panoptic merge against reference (oracle) logits -> the reference's merge (numpy restatement, pinned on the
+    unmodified method), class thresholds overridden to 0 as SURVEY.md 8c(ii) prescribes.  Random-init logits are nearly flat (every
+    softmax confidence ~ 1/128 < the 0.3 pixel threshold -> everything void), so both sides' mask logits are multiplied by the same
+    temperature, which makes the confidences decisive the way a trained head does without touching the comparison."""
+    from axial_vs_b200 import cross_clip
+    from oracle import panoptic_oracle as PO
+    Q, T, V, H, W, L, K, seed = 128, 4, 2, 48, 48, 4, 124, 4242
+    p = synth.cross_clip_params(seed, L, K)
+    m = cross_clip.CrossClipTrackingModule(num_layers=L, num_classes=K, attn_drop=0.0, aspp_drop=0.0, kernel_sizes=[3, 3, 3],
+                                           atrous_rates=[1, 2, 3], norm_fn="ln", num_clip_frames=V).eval()
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    cq = synth.randn(seed + 1, 1, Q, T, 256)
+    pf = synth.randn(seed + 2, 1, 128, T * V, H, W)
+    ref = O.cross_clip_module(cq, pf, p, L, V)
+    with torch.no_grad():
+        o = m(cq.cuda(), pf.cuda())
+    got_masks, want_masks = o["pred_masks"][0].float(), ref["pred_masks"][0].float()          # [Q, T*V, H, W]
+    agree_q = (got_masks.cpu().argmax(0) == want_masks.argmax(0)).float().mean().item()
+    temp = 60.0
+    pp = _pano(K, 0.3)
+    pp.class_threshold_thing = pp.class_threshold_stuff = 0.0
+    seg, segments = pp.panoptic_segments(o["pred_logits"][0], got_masks * temp)
+    meta = PO.Metadata(*synth.panoptic_metadata(K))
+    ref_seg, _, ref_segments = PO.panoptic_mask_inference(ref["pred_logits"][0].numpy(), (want_masks * temp).numpy(), None, meta, pixel_thr=0.3,
+                                                          thing_thr=0.0, stuff_thr=0.0)
+    seg = seg.cpu().numpy()
+    n = int(segments[0])
+    got_slots = {(r[0], r[1]) for r in segments[1:1 + 4 * n].view(n, 4).tolist()}              # (slot, label) of every accepted segment
+    ref_slots = {(r[0], r[1]) for r in ref_segments}
+    jacc = len(got_slots & ref_slots) / max(1, len(got_slots | ref_slots))
+    assigned = float((ref_seg >= 0).mean())
+    agree_p = float((seg == ref_seg).mean())
+    div = meta.label_divisor
+    agree_c = float(((seg // div) == (ref_seg // div)).mean())                                  # category of the pixel (instance ids ignored)
+    print(f"[labels end to end] query argmax agreement {agree_q:.5f}; panoptic: {assigned:.1%} of the pixels assigned, {len(ref_slots)} segments, "
+          f"segment-set Jaccard {jacc:.3f}, pixel agreement ids {agree_p:.5f} / categories {agree_c:.5f}")
+    assert assigned > 0.3, "the synthetic case must exercise the merge"
+    # The greedy merge is a cascade of discrete decisions (slot order by score, overlap test at 0.8): on these near-tied random-init logits
+    # one flipped accept / reject re-labels every pixel of a slot, so id agreement sits well below the per-pixel query agreement.
+    assert agree_q >= 0.998 and jacc >= 0.85 and agree_c >= 0.995      # measured 0.9985, 0.93, 0.9983 (instance ids renumber after one flipped slot: 0.966)
+    # the merge itself, on IDENTICAL (reference) logits, is exact: the panoptic kernels decide by comparisons of fp32 scores
+    seg_same, _ = pp.panoptic_segments(ref["pred_logits"][0].cuda(), (want_masks * temp).cuda())
+    assert float((seg_same.cpu().numpy() == ref_seg).mean()) >= 0.999
