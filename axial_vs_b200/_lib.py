@@ -50,6 +50,7 @@ class LayerWeights(Structure):
 SIGNATURES = {
     "axvs_version": (c_int, []),
     "axvs_last_error": (c_char_p, []),
+    "axvs_build_id": (c_char_p, []),
     "axvs_set_fusion": (c_int, [c_int]),
     "axvs_set_pair_mode": (c_int, [c_int]),
     "axvs_set_attn_core": (c_int, [c_int]),

@@ -16,7 +16,7 @@ import torch.nn as nn
 from torch import Tensor
 
 from . import ops
-from .modules import _PackedCache, _require_inference
+from .modules import _PackedCache, _invalidate_hook, _require_inference
 
 
 class TrajectoryAttention(nn.Module):
@@ -35,6 +35,7 @@ class TrajectoryAttention(nn.Module):
         self.attn_drop = nn.Dropout(attn_drop)
         self.proj = nn.Linear(d_model, d_model)
         self._cache = _PackedCache()
+        self.register_load_state_dict_post_hook(_invalidate_hook)
 
     def packed(self, device) -> ops.PackedTA:
         return self._cache.get(self, device, lambda: ops.pack_ta(dict(self.state_dict())))
@@ -103,6 +104,7 @@ class _ConvBN1d(nn.Module):
         self.act_code = {None: 0, "relu": 1, "gelu": 2}[act]
         self.cout = cout
         self._cache = _PackedCache()
+        self.register_load_state_dict_post_hook(_invalidate_hook)
         self._cache32 = _PackedCache()
 
     def folded(self):
@@ -181,6 +183,17 @@ class MaXTronCCPredictor(nn.Module):
         self._pixel_space_mask_batch_norm = nn.BatchNorm1d(1, eps=1e-3, momentum=0.01)
         nn.init.constant_(self._pixel_space_mask_batch_norm.weight, 0.1)
         self.num_classes = num_classes
+        self._scalars = _PackedCache()
+
+    def _host_scalars(self, device):
+        """(class-activation bias, folded pixel-space BN scale, shift) as Python floats: ONE host read per weight update, not one per call."""
+        def build():
+            act, bn = self._transformer_class_activation_head, self._pixel_space_mask_batch_norm
+            sc = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
+            sh = bn.bias.detach().float() - bn.running_mean.float() * sc
+            v = torch.stack((act.conv.bias.detach().float().reshape(()), sc.reshape(()), sh.reshape(()))).tolist()
+            return tuple(float(x) for x in v)
+        return self._scalars.get(nn.ModuleList([self._transformer_class_activation_head.conv, self._pixel_space_mask_batch_norm]), device, build)
 
     def class_logits(self, class_embeddings, num_clips):
         """CC:47-51: class activation softmax over the clips, pooled class embedding, class head + void bias -> [1, Q, K+1]."""
@@ -188,7 +201,7 @@ class MaXTronCCPredictor(nn.Module):
         Q = class_embeddings.shape[0] // T
         act = self._transformer_class_activation_head
         pooled = ops.cc_class_pool(class_embeddings, act.conv.weight.detach().float().reshape(-1).contiguous(),
-                                   float(act.conv.bias.detach()), T, Q)                                      # [Q, 256]
+                                   self._host_scalars(class_embeddings.device)[0], T, Q)                     # [Q, 256]
         void = torch.zeros(self.num_classes, device=pooled.device)
         void[-1] = math.log((self.num_classes - 1) * 0.9 / (1 - 0.9))                                         # add_bias_towards_void
         cls = self._transformer_class_head.run(pooled, torch.float32, extra_bias=void)[:, : self.num_classes]  # [Q, K+1]
@@ -204,9 +217,7 @@ class MaXTronCCPredictor(nn.Module):
         """CC:62-68 for `num_clips` clips: mk rows (t, q) of those clips, pixel_feature fp32 [T, 128, V*H, W] -> fp32 [Q, T, V*H*W]."""
         T = num_clips
         Q = mk.shape[0] // T
-        bn = self._pixel_space_mask_batch_norm
-        sc = float(bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps))
-        sh = float(bn.bias.detach() - bn.running_mean * sc)
+        _, sc, sh = self._host_scalars(mk.device)
         _, Cp, VH, Wd = pixel_feature.shape
         return ops.mask_einsum(pixel_feature.contiguous().float(), mk.contiguous(), T, Q, VH * Wd, sc, sh)
 
@@ -243,6 +254,10 @@ class CrossClipTrackingModule(nn.Module):
         self._mask_embedding_projection = _ConvBN1d(256, 256, bias=False, norm="syncbn", act="gelu")
         self._predictor = MaXTronCCPredictor(num_classes=num_classes + 1)
         self._aspp_cache = [_PackedCache() for _ in range(num_layers)]
+        # The reference's eval branch moves class / mask logits to the host (CC:57,71: `.cpu()`), because its post-processing runs there.
+        # This drop-in keeps them on the GPU by default (postprocess.PanopticPostProcessor consumes them in place); set
+        # `outputs_on_cpu = True` for callers that mix the outputs with host tensors.
+        self.outputs_on_cpu = False
 
     def _packed_aspp(self, i, device):
         mods = nn.ModuleList([self.conv_short_aggregate_layers[i], self.conv_norms[i]])
@@ -276,7 +291,11 @@ class CrossClipTrackingModule(nn.Module):
         align_corners = (target_size[-1] % 2 == 1)
         for a, m in zip(predictions_class[:-1], predictions_mask[:-1]):
             aux.append({"pred_logits": a, "pred_masks": torch.nn.functional.interpolate(m, size=target_size, mode="trilinear", align_corners=align_corners)})
-        return {"pred_logits": predictions_class[-1], "pred_masks": predictions_mask[-1], "aux_outputs": aux}
+        out = {"pred_logits": predictions_class[-1], "pred_masks": predictions_mask[-1], "aux_outputs": aux}
+        if self.outputs_on_cpu:
+            out = {"pred_logits": out["pred_logits"].cpu(), "pred_masks": out["pred_masks"].cpu(),
+                   "aux_outputs": [{k: v.cpu() for k, v in a.items()} for a in aux]}
+        return out
 
     def forward_sharded(self, clip_query_local, panoptic_local, n_clips, group=None, gather=None):
         """Clip-sharded video (one process per GPU): `clip_query_local` [1, Q, T_local, C] and

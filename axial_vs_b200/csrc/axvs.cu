@@ -2,7 +2,9 @@
 // no host synchronisation, no allocation: everything is enqueued on the caller's stream.
 #include "../../include/axvs.h"
 
+#include <atomic>
 #include <cstdarg>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 
@@ -46,25 +48,32 @@ const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel"
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
                                             "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel"};
-int g_fusion = 4;   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
-int g_attn_core = 1;   // 1 = tcgen05 attention core (attn_tc.cuh), 0 = the mma.sync kernels (validation baseline)
-int g_pair = 0;   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
+// Process-wide knobs are atomics (two host threads driving two devices may read / set them concurrently); the profiler's records and
+// the per-device attribute table are guarded by mutexes.  None of them is touched on the launch path beyond one relaxed load.
+std::atomic<int> g_fusion{4};   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
+std::atomic<int> g_attn_core{1};   // 1 = tcgen05 attention core (attn_tc.cuh), 0 = the mma.sync kernels (validation baseline)
+std::atomic<int> g_pair{0};   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
 struct Profiler {
-  bool on = false;
+  std::atomic<bool> on{false};
+  std::atomic<bool> count{false};     // launch counters are kept only between axvs_profile_enable(...) and the read (bench.py's gpu_launches)
+  std::mutex mu;                      // guards n / created / rec
   int n = 0;
   int created = 0;
   ProfRec rec[PROF_MAX];
-  long long launches[KC_COUNT] = {0};
+  std::atomic<long long> launches[KC_COUNT];
 } g_prof;
 
 struct ProfScope {
   int idx = -1;
   cudaStream_t st;
   ProfScope(int cls, double flops, double bytes, cudaStream_t s) : st(s) {
-    g_prof.launches[cls]++;
-    if (!g_prof.on || g_prof.n >= PROF_MAX) return;
+    if (!g_prof.count.load(std::memory_order_relaxed)) return;
+    g_prof.launches[cls].fetch_add(1, std::memory_order_relaxed);
+    if (!g_prof.on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    if (g_prof.n >= PROF_MAX) return;
     idx = g_prof.n++;
     ProfRec& r = g_prof.rec[idx];
     if (idx >= g_prof.created) { cudaEventCreate(&r.a); cudaEventCreate(&r.b); g_prof.created = idx + 1; }
@@ -92,13 +101,17 @@ struct DeviceInfo {
   bool dec_attr = false;
   bool kmax_attr = false;
   bool attn_tc_attr = false;
+  std::atomic<bool> ready{false};
 };
 DeviceInfo g_dev[64];
+std::mutex g_dev_mu;   // first use per device sets function attributes; later calls only read the flags
 
 int device_info(DeviceInfo** out) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(AXVS_E_CUDA, "cudaGetDevice failed");
   DeviceInfo& d = g_dev[dev];
+  if (d.ready.load(std::memory_order_acquire)) { *out = &d; return AXVS_OK; }
+  std::lock_guard<std::mutex> lk(g_dev_mu);
   if (d.sms == 0) {
     int major = 0;
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
@@ -176,6 +189,7 @@ int device_info(DeviceInfo** out) {
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(ffn_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.ffn_attr = true;
   }
+  d.ready.store(true, std::memory_order_release);
   *out = &d;
   return AXVS_OK;
 }
@@ -292,21 +306,21 @@ int blocks_for(long long work_items, int per_block, int sms) {
 
 extern "C" {
 
-int axvs_version(void) { return 113; }
+int axvs_version(void) { return 120; }
+#ifndef AXVS_BUILD_ID
+#define AXVS_BUILD_ID "unknown"
+#endif
+// hash of csrc/ + include/ at compile time (__graft_entry__.build passes it); the marker string lets build() read it from the file
+static const char k_build_marker[] = "AXVS_BUILD_ID=" AXVS_BUILD_ID;
+const char* axvs_build_id(void) { return k_build_marker + 14; }
 int axvs_set_pair_mode(int on) {
-  const int prev = g_pair;
-  g_pair = on ? 1 : 0;
-  return prev;
+  return g_pair.exchange(on ? 1 : 0);
 }
 int axvs_set_attn_core(int core) {
-  const int prev = g_attn_core;
-  g_attn_core = core ? 1 : 0;
-  return prev;
+  return g_attn_core.exchange(core ? 1 : 0);
 }
 int axvs_set_fusion(int level) {
-  const int prev = g_fusion;
-  g_fusion = level < 0 ? 0 : (level > 5 ? 5 : level);
-  return prev;
+  return g_fusion.exchange(level < 0 ? 0 : (level > 5 ? 5 : level));
 }
 const char* axvs_last_error(void) { return g_err; }
 
@@ -1090,11 +1104,13 @@ int axvs_output_proj_fwd(const float* tokens, const void* w_packed, const float*
                          int images, int c_out, int hw, float eps, axvs_stream_t stream) {
   if (!tokens || !w_packed || !gn_w || !gn_b || !out_nchw) return fail(AXVS_E_INVALID, "output_proj: null pointer");
   if (images <= 0 || c_out <= 0 || hw <= 0) return fail(AXVS_E_INVALID, "output_proj: sizes must be positive");
-  if (c_out % 256) return fail(AXVS_E_UNSUPPORTED, "output_proj: the channel count must be a multiple of 256 (got %d)", c_out);
+  if (c_out % 32) return fail(AXVS_E_UNSUPPORTED, "output_proj: the channel count must be a multiple of 32 (GroupNorm(32); got %d)", c_out);
   if ((long long)images * hw > 0x7fffffffLL || images > 65535) return fail(AXVS_E_UNSUPPORTED, "output_proj: too many pixels / images");
   const int M = images * hw;
-  GemmParams p = gemm_params(nullptr, 256, M, 256, w_packed, c_out, 0, bias, c_out, 1.f, 0, out_nchw, c_out, 0, 0, nullptr);
-  p.a_diag = 4; p.A32 = tokens; p.out_nchw = hw;
+  const int n_pad = (c_out + 255) / 256 * 256;          // the GEMM works on 256-column chunks: weight rows / bias are zero-padded by the caller
+  GemmParams p = gemm_params(nullptr, 256, M, 256, w_packed, n_pad, 0, bias, n_pad, 1.f, 0, out_nchw, n_pad, 0, 0, nullptr);
+  p.a_diag = 4; p.A32 = tokens; p.out_nchw = hw; p.out_ch = c_out;
+  if (n_pad != c_out) p.n_valid = c_out;
   if (int rc = launch_gemm(p, (cudaStream_t)stream)) return rc;
   {
     ProfScope ps(KC_GN, 0, (double)M * c_out * 12.0, (cudaStream_t)stream);
@@ -1249,8 +1265,8 @@ int axvs_panoptic_inference(const float* mask_cls, const float* mask_pred, int N
 }
 
 // ---------------------------------------------------------------------------------------------- kMaX axial attention (row f3)
-static int g_kmax_tc = 1;
-int axvs_set_kmax_tensor_cores(int on) { const int prev = g_kmax_tc; g_kmax_tc = on ? 1 : 0; return prev; }
+static std::atomic<int> g_kmax_tc{1};
+int axvs_set_kmax_tensor_cores(int on) { return g_kmax_tc.exchange(on ? 1 : 0); }
 
 size_t axvs_kmax_axial_workspace_bytes(int images, int c_in, int H, int W, int heads, int dk, int dv) {
   if (images <= 0 || c_in <= 0 || H <= 0 || W <= 0 || heads <= 0 || dk <= 0 || dv <= 0) return 0;
@@ -1355,7 +1371,9 @@ int axvs_pos3d(float* out, const float* level_embed, int B, int T, int H, int W,
 }
 
 int axvs_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   g_prof.on = on != 0;
+  g_prof.count = true;                 // launch counters run from the first call of this function on (off by default: no shared writes)
   g_prof.n = 0;
   for (int i = 0; i < KC_COUNT; ++i) g_prof.launches[i] = 0;
   return AXVS_OK;
@@ -1366,7 +1384,8 @@ const char* axvs_profile_class_name(int cls) { return (cls >= 0 && cls < KC_COUN
 
 int axvs_profile_read(double* ms, double* flops, double* bytes, long long* launches, long long* timed) {
   if (!ms || !flops || !bytes || !launches || !timed) return fail(AXVS_E_INVALID, "profile_read: null pointer");
-  for (int i = 0; i < KC_COUNT; ++i) { ms[i] = flops[i] = bytes[i] = 0; launches[i] = g_prof.launches[i]; timed[i] = 0; }
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  for (int i = 0; i < KC_COUNT; ++i) { ms[i] = flops[i] = bytes[i] = 0; launches[i] = g_prof.launches[i].load(); timed[i] = 0; }
   for (int i = 0; i < g_prof.n; ++i) {
     ProfRec& r = g_prof.rec[i];
     if (cudaEventSynchronize(r.b) != cudaSuccess) return fail(AXVS_E_CUDA, "profile_read: %s", cudaGetErrorString(cudaGetLastError()));

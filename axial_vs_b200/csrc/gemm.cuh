@@ -109,7 +109,8 @@ struct GemmParams {
   const float* resid;   // optional fp32 residual, same row map / ld as out (fp32 path only)
   int map_mode;         // RowMap applied to output (and residual) rows
   AxialDims dims;
-  int out_nchw;         // > 0: fp32 output is NCHW [images, n_out, out_nchw pixels] (Conv2d 1x1 output): row r = image r / out_nchw,
+  int out_ch;           // NCHW outputs: channels of the output tensor (0 = n_out); smaller than n_out when n_out is padded to 256 (n_valid)
+  int out_nchw;         // > 0: fp32 output is NCHW [images, out_ch, out_nchw pixels] (Conv2d 1x1 output): row r = image r / out_nchw,
                         //      pixel r % out_nchw; every column is one coalesced 4-byte store per lane (lanes = consecutive pixels)
 };
 
@@ -137,7 +138,7 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, int row
   if (p.out_nchw > 0) {
     if (row >= p.M) return;
     const int img = row / p.out_nchw, pix = row - img * p.out_nchw;
-    float* o = reinterpret_cast<float*>(p.out) + ((size_t)img * p.n_out + col) * p.out_nchw + pix;
+    float* o = reinterpret_cast<float*>(p.out) + ((size_t)img * (p.out_ch > 0 ? p.out_ch : p.n_out) + col) * p.out_nchw + pix;
 #pragma unroll
     for (int i = 0; i < 32; ++i) o[(size_t)i * p.out_nchw] = v[i];
     return;

@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import _lib, ops
-from .modules import _PackedCache, _require_inference
+from .modules import _PackedCache, _invalidate_hook, _require_inference
 
 MAX_SPAN = 255
 _BN_EPS = 1e-3            # get_norm('syncbn'): eps = 1e-3, momentum = 0.01 (kmax_pixel_decoder.py:37)
@@ -68,6 +68,7 @@ class AxialAttention(nn.Module):
         self._batch_norm_similarity = nn.BatchNorm1d(num_heads * 3, eps=_BN_EPS, momentum=0.01)
         self._batch_norm_retrieved_output = nn.BatchNorm1d(total_value_depth * 2, eps=_BN_EPS, momentum=0.01)
         self._cache = _PackedCache()
+        self.register_load_state_dict_post_hook(_invalidate_hook)
 
     def _packed(self, device):
         def build():

@@ -33,18 +33,58 @@ def _require_inference(mod: nn.Module, *tensors: Tensor) -> None:
 
 
 class _PackedCache:
-    """Packed bf16 weights derived from the fp32 nn.Parameters; rebuilt when any parameter changes."""
+    """Packed bf16 weights derived from the fp32 nn.Parameters AND buffers (BatchNorm running statistics are folded into some
+    images); rebuilt when any of them is replaced or modified in place through autograd-visible ops (`_version`).  Writes that
+    bypass the version counter (`p.data.fill_()`, which the reference's init code uses) need an explicit `invalidate()` --
+    `invalidate_packed(module)` does that for a whole module tree and is registered as a load_state_dict post-hook by the drop-ins.
+
+    The pack kernels run on the stream that is current when the cache is (re)built; a CUDA event recorded behind them makes any OTHER
+    stream that later fetches the images wait for the build (the per-level / per-chunk side streams of within_clip.py fetch them
+    while the first level may still be packing)."""
 
     def __init__(self):
         self._key = None
         self._val = None
+        self._event = None
+        self._stream = None
+
+    def invalidate(self) -> None:
+        self._key = None
 
     def get(self, module: nn.Module, device: torch.device, build):
-        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in module.parameters())
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in module.parameters()) + \
+            tuple((b.data_ptr(), b._version) for b in module.buffers())
+        dev = torch.device(device)
         if key != self._key:
             self._val = build()
             self._key = key
+            if dev.type == "cuda":
+                self._stream = torch.cuda.current_stream(dev)
+                self._event = torch.cuda.Event()
+                self._event.record(self._stream)
+        elif self._event is not None:
+            cur = torch.cuda.current_stream(dev)
+            if cur != self._stream and not self._event.query():
+                cur.wait_event(self._event)
+            elif self._event.query():
+                self._event = None                             # build finished: nothing to order against any more
         return self._val
+
+
+def _invalidate_hook(module: nn.Module, incompatible_keys=None) -> None:
+    invalidate_packed(module)
+
+
+def invalidate_packed(module: nn.Module) -> None:
+    """Drop every packed-weight image under `module` (call after writing parameters through `.data`)."""
+    for m in module.modules():
+        for v in vars(m).values():
+            if isinstance(v, _PackedCache):
+                v.invalidate()
+            elif isinstance(v, (list, tuple)):
+                for c in v:
+                    if isinstance(c, _PackedCache):
+                        c.invalidate()
 
 
 class TrajectoryAttention(nn.Module):
@@ -66,6 +106,7 @@ class TrajectoryAttention(nn.Module):
         self.proj = nn.Linear(dim, dim)
         self.return_attn_maps = False
         self._cache = _PackedCache()
+        self.register_load_state_dict_post_hook(_invalidate_hook)
 
     def packed(self, device) -> ops.PackedTA:
         return self._cache.get(self, device, lambda: ops.pack_ta({k: v for k, v in self.state_dict().items()}))
@@ -109,6 +150,7 @@ class _LayerBase(nn.Module):
         self.dropout3 = nn.Dropout(dropout)
         self.norm2 = nn.LayerNorm(d_model)
         self._cache = _PackedCache()
+        self.register_load_state_dict_post_hook(_invalidate_hook)
 
     @staticmethod
     def with_pos_embed(tensor, pos):

@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .modules import _PackedCache, _require_inference
+from .modules import _PackedCache, _invalidate_hook, _require_inference
 
 
 class MSDeformAttn(nn.Module):
@@ -69,6 +69,7 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         self.dropout3 = nn.Dropout(dropout)
         self.norm2 = nn.LayerNorm(d_model)
         self._cache = _PackedCache()
+        self.register_load_state_dict_post_hook(_invalidate_hook)
 
     def packed(self, device) -> ops.PackedMsda:
         return self._cache.get(self, device, lambda: ops.pack_msda_layer(dict(self.state_dict()), self.self_attn.n_levels, self.self_attn.n_points))

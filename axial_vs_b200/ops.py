@@ -43,17 +43,28 @@ def _check(t: torch.Tensor, name: str, dtype: torch.dtype, shape: Optional[Seque
         raise RuntimeError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
 
 
-_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+_workspaces: "Dict[Tuple[int, int], torch.Tensor]" = {}     # insertion-ordered: least recently used first
+MAX_WORKSPACES = 8                                           # per process; callers cycling through many streams evict the oldest
 
 
 def workspace(nbytes: int, dev: torch.device) -> torch.Tensor:
-    """Per-(device, stream) scratch buffer, grown on demand; reuse is ordered by the stream itself."""
+    """Per-(device, stream) scratch buffer, grown on demand; reuse is ordered by the stream itself.  At most MAX_WORKSPACES buffers
+    are kept (least recently used evicted; an evicted buffer's memory returns to the caching allocator once its stream's work is
+    done, which `record_stream` guarantees)."""
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(dev))
-    buf = _workspaces.get(key)
+    buf = _workspaces.pop(key, None)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
-        _workspaces[key] = buf
+        buf.record_stream(torch.cuda.current_stream(dev))
+    _workspaces[key] = buf                                   # most recently used last
+    while len(_workspaces) > MAX_WORKSPACES:
+        _workspaces.pop(next(iter(_workspaces)))
     return buf
+
+
+def release_workspaces() -> None:
+    """Drop every cached scratch buffer (e.g. between a benchmark's configurations)."""
+    _workspaces.clear()
 
 
 # ------------------------------------------------------------------------------------------------ weights
@@ -239,8 +250,14 @@ def traj_attn_maps(q_in: torch.Tensor, pos: Optional[torch.Tensor], w: PackedTA,
     """The reference's `space_attn` maps: fp32 [(num_seq*8), N, F, n] (slow path for the attention visualiser)."""
     rows = B * T * H * W
     _check(q_in, "q_in", torch.float32)
+    if q_in.numel() != rows * C:
+        raise RuntimeError(f"q_in has {q_in.numel()} elements, expected {rows}x{C}")
     if pos is not None:
         _check(pos, "pos", torch.float32)
+        if pos.numel() != rows * C:                   # this slow path reads one positional row per token: materialise a shared table
+            if pos.numel() != T * H * W * C:
+                raise RuntimeError("pos size mismatch")
+            pos = pos.reshape(1, T * H * W, C).expand(B, -1, -1).contiguous()
     num_seq, n = {AXIS_H: (B * W, H), AXIS_W: (B * H, W), AXIS_NONE: (B, H * W)}[axis]
     N = T * n
     maps = torch.empty(num_seq * HEADS, N, T, n, dtype=torch.float32, device=q_in.device)
@@ -536,8 +553,9 @@ def output_proj_fwd(tokens: torch.Tensor, w_packed: torch.Tensor, bias: torch.Te
     _check(tokens, "tokens", torch.float32)
     if tokens.dim() != 3 or tokens.shape[1] != H * W or tokens.shape[2] != C:
         raise RuntimeError("output_proj_fwd: expected tokens [images, H*W, 256]")
-    images, c_out = tokens.shape[0], bias.numel()
-    for t, nm in ((bias, "bias"), (gn_w, "GroupNorm weight"), (gn_b, "GroupNorm bias")):
+    images, c_out = tokens.shape[0], gn_w.numel()
+    _check(bias, "bias", torch.float32, ((c_out + 255) // 256 * 256,))          # zero-padded to the GEMM's 256-column chunks
+    for t, nm in ((gn_w, "GroupNorm weight"), (gn_b, "GroupNorm bias")):
         _check(t, nm, torch.float32, (c_out,))
     out = torch.empty(images, c_out, H, W, dtype=torch.float32, device=tokens.device)
     lib = _lib.load()

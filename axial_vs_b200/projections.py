@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .modules import _PackedCache, _require_inference
+from .modules import _PackedCache, _invalidate_hook, _require_inference
 
 
 class _Proj(nn.Sequential):
@@ -22,13 +22,23 @@ class _Proj(nn.Sequential):
         nn.init.xavier_uniform_(self[0].weight, gain=1)      # WC/msdeformattn.py:377-382
         nn.init.constant_(self[0].bias, 0)
         self._cache = _PackedCache()
+        self.register_load_state_dict_post_hook(_invalidate_hook)
 
     def _packed(self, device):
-        return self._cache.get(self, device, lambda: ops.pack_weight(self[0].weight.detach().float().flatten(1).contiguous()))
+        def build():
+            w = self[0].weight.detach().float().flatten(1)
+            n_pad = (w.shape[0] + 255) // 256 * 256                 # output side: the GEMM stores 256-column chunks (padding never stored)
+            if n_pad != w.shape[0]:
+                w = torch.cat((w, w.new_zeros(n_pad - w.shape[0], w.shape[1])), 0)
+            return ops.pack_weight(w.contiguous())
+        return self._cache.get(self, device, build)
 
     def _params(self):
-        return (self[0].bias.detach().float().contiguous(), self[1].weight.detach().float().contiguous(),
-                self[1].bias.detach().float().contiguous())
+        b = self[0].bias.detach().float()
+        n_pad = (b.numel() + 255) // 256 * 256
+        if n_pad != b.numel():
+            b = torch.cat((b, b.new_zeros(n_pad - b.numel())))
+        return (b.contiguous(), self[1].weight.detach().float().contiguous(), self[1].bias.detach().float().contiguous())
 
 
 class InputProjection(_Proj):
@@ -46,7 +56,7 @@ class InputProjection(_Proj):
 
 
 class OutputProjection(_Proj):
-    """forward(tokens [images, H*W, 256], H, W) -> y [images, c_out, H, W] (c_out a multiple of 256)."""
+    """forward(tokens [images, H*W, 256], H, W) -> y [images, c_out, H, W] (c_out a multiple of 32, e.g. 384 / 768 / 1536 for ConvNeXt-L)."""
 
     def __init__(self, out_channels: int, conv_dims: int = 256):
         if conv_dims != 256:

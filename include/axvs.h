@@ -43,6 +43,9 @@ typedef void* axvs_stream_t;
 
 int axvs_version(void);
 const char* axvs_last_error(void);
+/* Hash of the sources this library was compiled from (-DAXVS_BUILD_ID, set by __graft_entry__.build); "unknown" for ad-hoc builds.
+ * smoke() compares it with the hash of the tree it runs in, so a stale prebuilt binary is detected. */
+const char* axvs_build_id(void);
 
 /* Fusion level of the composite entry points (process-wide; default = 4, the fastest measured).
  *   0: one kernel per reference op group (tcgen05 GEMMs + attention + SIMT helpers; validation baseline)
@@ -224,7 +227,9 @@ int axvs_kmeans_update(const float* mask_logits, const float* pixel_value, float
  *   x fp32 NCHW [images, c_in, hw] (c_in % 64 == 0); w_packed = axvs_pack_weight of the conv weight [256, c_in];
  *   out fp32 token-major [images, hw, 256] -- the layout of the temporal layers (the reference's flatten + transpose is folded in).
  * output side (WC/msdeformattn.py:359-362, 432-434): y[i, :, p] = GroupNorm(32, c_out)(Conv2d(256, c_out, 1))(tokens[i, p, :])
- *   tokens fp32 [images, hw, 256]; w_packed of the conv weight [c_out, 256] (c_out % 256 == 0); out fp32 NCHW [images, c_out, hw].
+ *   tokens fp32 [images, hw, 256]; c_out % 32 == 0 (GroupNorm(32); e.g. 384 for res3 of the ConvNeXt-L configs); w_packed of the conv
+ *   weight zero-padded to [ceil256(c_out), 256] rows and bias zero-padded to ceil256(c_out) entries (the GEMM works on 256-column
+ *   chunks; padding columns are never stored); out fp32 NCHW [images, c_out, hw].
  * GroupNorm statistics are per image and per group (eps as given, nn.GroupNorm default 1e-5), reductions in a fixed order. */
 size_t axvs_proj_workspace_bytes(int images);
 int axvs_input_proj_fwd(const float* x_nchw, const void* w_packed, const float* bias, const float* gn_w, const float* gn_b, float* out_tokens,

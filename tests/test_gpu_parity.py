@@ -673,13 +673,15 @@ def test_projections_golden(golden, tag):
     assert nerr(y, torch.as_tensor(gz["y"])) < TOL
 
 
-@pytest.mark.parametrize("n,c,H,W", [(4, 2048, 21, 21), (2, 1024, 41, 41), (2, 512, 81, 81), (3, 64, 5, 3)])
+@pytest.mark.parametrize("n,c,H,W", [(4, 2048, 21, 21), (2, 1024, 41, 41), (2, 512, 81, 81), (3, 64, 5, 3),
+                                     (2, 192, 33, 29), (2, 768, 21, 21), (3, 320, 11, 13)])
 def test_projections_oracle_config_sizes(O, n, c, H, W):
-    """R50 pyramid of BASELINE configs[1]: res5 2048 x 21^2, res4 1024 x 41^2, res3 512 x 81^2 (and a ragged tiny case)."""
+    """R50 pyramid of BASELINE configs[1]: res5 2048 x 21^2, res4 1024 x 41^2, res3 512 x 81^2, a ragged tiny case, and channel counts
+    that are not multiples of 256 on the output side (ConvNeXt-L / V2-L: res3 has 384 channels = 2 x 192; 1536 = 2 x 768)."""
     from axial_vs_b200.projections import InputProjection, OutputProjection
     seed = 700 + n + c + H
     pin, pout = synth.proj_params(seed, c)
-    if (2 * c) % 256:
+    if (2 * c) % 32:
         pout = None
     x = synth.randn(seed + 1, n, c, H, W)
     ref_tok = O.input_proj(x, pin)
