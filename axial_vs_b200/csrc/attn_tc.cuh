@@ -96,7 +96,7 @@ __device__ __forceinline__ AtUnit at_decode(int unit, const AttnTcParams& p) {
 }
 
 // One frame's softmax for this thread's query row.  NT16 > 0: the score row (NP = 16 * NT16 <= 64 columns) is held in registers
-// (one TMEM round trip); NT16 == 0: two passes over 16-column pieces (any NP).  Returns the row sum of the probabilities.
+// (one TMEM round trip; NP <= 96); NT16 == 0: two passes over 32-column pieces with prefetch (any NP).  Returns the row sum of the probabilities.
 template <int NT16>
 __device__ __forceinline__ float at_softmax_frame(uint32_t t_s, int NP, int n, float sc) {
   float sum = 0.f;
@@ -133,36 +133,91 @@ __device__ __forceinline__ float at_softmax_frame(uint32_t t_s, int NP, int n, f
     }
     sum = sum2.x + sum2.y;
   } else {
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c0 = 0; c0 < NP; c0 += 16) {
-      float v[16];
-      tmem_ld16(t_s + c0, v);
-      tmem_ld_wait();
-      if (c0 + 16 <= n) {
+    // long frames (NP > 96): two passes over 32-column pieces, the next piece's tcgen05.ld in flight while the current one is
+    // processed (tcgen05.wait::ld covers every load issued before it, so the prefetch is issued right after the wait)
+    const int NP32 = NP & ~31;
+    float va[32], vb[32];
+    auto max32 = [&](const float (&v)[32], int c0, float m) {
+      if (c0 + 32 <= n) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+        for (int i = 0; i < 32; i += 2) m = max3_f32(m, v[i], v[i + 1]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (c0 + i < n) mx = fmaxf(mx, v[i]);
+        for (int i = 0; i < 32; ++i) if (c0 + i < n) m = fmaxf(m, v[i]);
+      }
+      return m;
+    };
+    float mx = -INFINITY;
+    if (NP32 > 0) tmem_ld32(t_s, va);
+#pragma unroll 1
+    for (int c0 = 0; c0 < NP32; c0 += 64) {
+      tmem_ld_wait();
+      if (c0 + 32 < NP32) tmem_ld32(t_s + c0 + 32, vb);
+      mx = max32(va, c0, mx);
+      if (c0 + 32 < NP32) {
+        tmem_ld_wait();
+        if (c0 + 64 < NP32) tmem_ld32(t_s + c0 + 64, va);
+        mx = max32(vb, c0 + 32, mx);
       }
     }
-    const float mxs = -mx * sc;
-#pragma unroll 1
-    for (int c0 = 0; c0 < NP; c0 += 16) {                     // writes columns [c0/2, c0/2 + 8): always behind the reads
+    if (NP & 16) {
       float v[16];
-      tmem_ld16(t_s + c0, v);
+      tmem_ld16(t_s + NP32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (NP32 + i < n) mx = fmaxf(mx, v[i]);
+    }
+    const float mxs = -mx * sc;
+    const float2 sc2 = make_float2(sc, sc), mxs2 = make_float2(mxs, mxs);
+    float2 sum2 = make_float2(0.f, 0.f);
+    auto exp32 = [&](const float (&v)[32], int c0) {           // probabilities of columns [c0, c0 + 32) -> packed columns [c0/2, c0/2 + 16)
+      uint32_t pk[16];
+      if (c0 + 32 <= n) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 a = fma_f32x2(make_float2(v[2 * i], v[2 * i + 1]), sc2, mxs2);
+          const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+          sum2 = add_f32x2(sum2, e);
+          pk[i] = pack_bf16x2(e.x, e.y);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float e0 = (c0 + 2 * i < n) ? ex2_approx(fmaf(v[2 * i], sc, mxs)) : 0.f;
+          const float e1 = (c0 + 2 * i + 1 < n) ? ex2_approx(fmaf(v[2 * i + 1], sc, mxs)) : 0.f;
+          sum2 = add_f32x2(sum2, make_float2(e0, e1));
+          pk[i] = pack_bf16x2(e0, e1);
+        }
+      }
+      tmem_st16u(t_s + (c0 >> 1), pk);                         // always behind the columns still to be read
+    };
+    if (NP32 > 0) tmem_ld32(t_s, va);
+#pragma unroll 1
+    for (int c0 = 0; c0 < NP32; c0 += 64) {
+      tmem_ld_wait();
+      if (c0 + 32 < NP32) tmem_ld32(t_s + c0 + 32, vb);
+      exp32(va, c0);
+      if (c0 + 32 < NP32) {
+        tmem_ld_wait();
+        if (c0 + 64 < NP32) tmem_ld32(t_s + c0 + 64, va);
+        exp32(vb, c0 + 32);
+      }
+    }
+    if (NP & 16) {
+      float v[16];
+      tmem_ld16(t_s + NP32, v);
       tmem_ld_wait();
       uint32_t pk[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float e0 = (c0 + 2 * i < n) ? ex2_approx(fmaf(v[2 * i], sc, mxs)) : 0.f;
-        const float e1 = (c0 + 2 * i + 1 < n) ? ex2_approx(fmaf(v[2 * i + 1], sc, mxs)) : 0.f;
-        sum += e0 + e1;
+        const float e0 = (NP32 + 2 * i < n) ? ex2_approx(fmaf(v[2 * i], sc, mxs)) : 0.f;
+        const float e1 = (NP32 + 2 * i + 1 < n) ? ex2_approx(fmaf(v[2 * i + 1], sc, mxs)) : 0.f;
+        sum2 = add_f32x2(sum2, make_float2(e0, e1));
         pk[i] = pack_bf16x2(e0, e1);
       }
-      tmem_st8u(t_s + (c0 >> 1), pk);
+      tmem_st8u(t_s + (NP32 >> 1), pk);
     }
+    sum = sum2.x + sum2.y;
   }
   return sum;
 }
@@ -170,7 +225,7 @@ __device__ __forceinline__ float at_softmax_frame(uint32_t t_s, int NP, int n, f
 constexpr int AT_MAX_FC = 4;   // frames per chunk the epilogue keeps row sums for
 
 template <int NT16>
-__global__ void __launch_bounds__((NT16 == 1 || NT16 == 2) ? 128 * 4 + 96 : 128 * 3 + 96, 1) spatial_attn_tc_kernel(const AttnTcParams p) {
+__global__ void __launch_bounds__((NT16 == 1 || NT16 == 2) ? 128 * 4 + 96 : (NT16 == 5 || NT16 == 6) ? 128 * 2 + 96 : 128 * 3 + 96, 1) spatial_attn_tc_kernel(const AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* ring = smem;

@@ -160,7 +160,9 @@ int device_info(DeviceInfo** out) {
         cudaFuncSetAttribute(spatial_attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
         cudaFuncSetAttribute(spatial_attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
         cudaFuncSetAttribute(spatial_attn_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
-        cudaFuncSetAttribute(spatial_attn_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
+        cudaFuncSetAttribute(spatial_attn_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_attn_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(spatial_attn_tc) failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (const char* e = getenv("AXVS_ATTN_CORE")) g_attn_core = atoi(e) ? 1 : 0;   // A/B aid for bench.py runs
     d.attn_tc_attr = true;
@@ -488,7 +490,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       ap.tiles = tiles; ap.N = N; ap.n = n; ap.F = F; ap.NP = nt16_f * 16; ap.QB = (N + 127) / 128;
       ap.scale_log2e = kScaleLog2e;
       // softmax groups (= TMEM buffers) and frames per unit: the most groups that still take two frames per unit
-      const int max_g = nt16_f <= 2 ? 4 : 3;                     // register budget of the softmax warps (launch bounds per NT16)
+      const int max_g = nt16_f <= 2 ? 4 : (nt16_f == 5 || nt16_f == 6) ? 2 : 3;   // register budget of the softmax warps (launch bounds per NT16)
       int G = 2, FC = 1;
       for (int g = max_g; g >= 2; --g) {
         const int cols = (512 / g) / 16 * 16;
@@ -517,11 +519,13 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       {
         ProfScope ps(KC_ATTNTC, 4.0 * num_seq * (double)N * N * 256, (double)rows * (1536.0 + (F + 1) * 512.0), st);
         const int threads = 128 * G + 96;
-        switch (nt16_f <= 4 ? nt16_f : 0) {
+        switch (nt16_f <= 6 ? nt16_f : 0) {
           case 1: spatial_attn_tc_kernel<1><<<grid, threads, smem_b, st>>>(ap); break;
           case 2: spatial_attn_tc_kernel<2><<<grid, threads, smem_b, st>>>(ap); break;
           case 3: spatial_attn_tc_kernel<3><<<grid, threads, smem_b, st>>>(ap); break;
           case 4: spatial_attn_tc_kernel<4><<<grid, threads, smem_b, st>>>(ap); break;
+          case 5: spatial_attn_tc_kernel<5><<<grid, threads, smem_b, st>>>(ap); break;
+          case 6: spatial_attn_tc_kernel<6><<<grid, threads, smem_b, st>>>(ap); break;
           default: spatial_attn_tc_kernel<0><<<grid, threads, smem_b, st>>>(ap); break;
         }
       }

@@ -458,6 +458,40 @@ def test_cross_clip_layer_oracle(O):
     assert nerr(y, ref) < TOL
 
 
+def test_cross_clip_layer_oracle_64_clips(O):
+    """BASELINE configs[2] at its FULL length: one video of 64 clips x 128 queries = 8192 tokens, F = 64 frames of n = 128 tokens
+    (the tcgen05 attention core with 64 query blocks per sequence and one frame per unit; x [8192, 64, 256] never leaves bf16 images)."""
+    from axial_vs_b200 import cross_clip
+    b, Q, T, seed = 1, 128, 64, 655
+    p = {}
+    g = torch.Generator().manual_seed(seed)
+    synth.traj_attn_params(g, "self_attn.", 256, p, fused_qkv=True)
+    p["norm.weight"] = 1 + 0.1 * torch.randn(256, generator=g)
+    p["norm.bias"] = 0.1 * torch.randn(256, generator=g)
+    m = cross_clip.TrajectoryAttentionLayer(256, 8).eval()
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    x = synth.randn(seed + 1, b, T * Q, 256)
+    ref = O.cc_attention_layer(x, p, Q, T)
+    with torch.no_grad():
+        y = m(x.cuda(), Q, T)
+    assert nerr(y, ref) < TOL
+
+
+@pytest.mark.parametrize("B,T,H,W", [(1, 5, 30, 40), (1, 2, 81, 81)])
+def test_axial_layer_oracle_large_shapes(O, B, T, H, W):
+    """BASELINE configs[3] at its larger temporal level (T = 5, 30x40: sequences of 150 / 200 tokens, two query blocks each) and the
+    sweep's 81x81 point (sequences of 162 tokens), whole layer against the oracle."""
+    seed = 5000 + T + H + W
+    p = synth.axial_layer_params(seed)
+    src = synth.randn(seed + 1, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 2)[0])
+    ref, _, _ = O.axial_layer(src, pos, p)
+    with torch.no_grad():
+        out, _, _ = _layer(p)(src.cuda(), pos.cuda())
+    assert nerr(out, ref) < TOL
+
+
 def test_level_plumbing(O):
     from axial_vs_b200 import modules, within_clip
     from axial_vs_b200.pos import PositionEmbeddingSine3D
