@@ -235,6 +235,25 @@ def workload_config(clips):
             "l2": "per-step activations exceed the 126 MB L2 and two input sets alternate"}
 
 
+def bind_to_gpu_numa(gpu_index: int):
+    """Pin this process to the CPUs NVML reports as affine to its GPU, so the pinned staging buffers are first-touched on the GPU's NUMA
+    node.  Returns the CPU list as a short string (or why it was skipped): the bench line records it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{cpus[0]}-{cpus[-1]} ({len(cpus)} cpus)"
+        return "no affine cpus reported"
+    except Exception as e:
+        return f"unchanged ({type(e).__name__})"
+
+
 def pcie_probe(dev, world, dist, mb: int = 256, reps: int = 4):
     """Host<->device ceilings of THIS box at THIS rank count: every rank moves `mb` MiB of pinned memory at the same time (H2D alone,
     D2H alone, both directions at once on two streams); aggregate GB/s over all ranks, max-over-ranks time.  The e2e leg is bounded by
@@ -350,6 +369,7 @@ def main():
         raise SystemExit("bench.py: a CUDA device is required (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
@@ -598,7 +618,7 @@ def main():
             moved = (in_bytes + out_bytes) * n_gpus * args.steps / (ms_e2e * 1e-3) / 1e9
             line["e2e"]["roofline"] = {"h2d_gbs": pcie["h2d_gbs"], "d2h_gbs": pcie["d2h_gbs"], "box_ceiling_gbs": pcie["bidir_gbs"],
                                        "achieved_gbs": round(moved, 1), "frac": round(moved / pcie["bidir_gbs"], 3), "how": pcie["how"],
-                                       "host_dtype": args.host_dtype, "d2h": args.d2h}
+                                       "host_dtype": args.host_dtype, "d2h": args.d2h, "cpu_affinity_rank0": affinity}
         if n_gpus == 1 and not args.no_extras:
             line["module"] = module_figure(dev)
             line["gpu_eager_baseline"] = gpu_eager_baseline(clips, dev)

@@ -128,6 +128,24 @@ def run_cfg3(args):
                                            norm_fn="ln", num_clip_frames=V).eval()
     m.load_state_dict(synth.cross_clip_params(11, L, K), strict=True)
     m.to(dev)
+    # within-clip stage of the same video: the temporal hot path (bench.py's workload) over THIS rank's clips
+    from axial_vs_b200 import modules, within_clip
+    encoders = []
+    for s_ in range(B.STAGES):
+        enc = modules.TemporalEncoder(256, 1024, 0.0, 0.0, "relu", 8, "axial-trajectory", B.LAYERS_PER_STAGE).eval()
+        enc.load_state_dict(synth.encoder_params(s_, B.LAYERS_PER_STAGE), strict=True)
+        encoders.append(enc.to(dev))
+    le = synth.level_embed(99).to(dev)
+    wc_pos = [ops.pos3d(1, V, H, W, le[i].contiguous(), dev).expand(Tl, -1, -1, -1, -1) for i, (H, W) in enumerate(B.LEVELS)]
+    wc_in = [torch.randn(Tl * V, H * W, 256, device=dev) for (H, W) in B.LEVELS]
+
+    @torch.no_grad()
+    def within_clip_stage():
+        cur = list(wc_in)
+        for enc in encoders:
+            cur = [o[0] for o in within_clip.run_levels_concurrent(enc, cur, wc_pos, 1)]
+        return cur
+
     g = torch.Generator().manual_seed(100 + rank)
     h_cq = torch.randn(1, Q, Tl, 256, generator=g).pin_memory()                     # this rank's clips (cluster centres of the clip segmenter)
     h_pf = torch.randn(1, 128, Tl * V, Hm, Wm, generator=g).pin_memory()            # and their pixel features
@@ -137,6 +155,7 @@ def run_cfg3(args):
     @torch.no_grad()
     def step(k, cq=None, pf=None):
         cq, pf = (d_cq, d_pf) if cq is None else (cq, pf)
+        within_clip_stage()                                            # clips are independent: no collective
         return m.forward_sharded(cq, pf, T)                            # final-layer predictions only (N = 1: no collective is issued)
 
     @torch.no_grad()
@@ -160,15 +179,17 @@ def run_cfg3(args):
     prof_steps = min(args.steps, 3)
     prof = _profile(step, prof_steps, ops)
     step_flops = L * flops_cc_layer(T, Q) + 2.0 * T * Q * (V * Hm * Wm) * 128     # layers (run redundantly per rank, counted once) + the mask contraction
+    step_flops += B.flops_per_clip() * T                                          # + the within-clip hot path of the 64 clips
     peaks = B.load_peaks()
     roof = _roofline(prof, prof_steps, peaks, step_flops, ms_total / args.steps) if rank == 0 else None
     e2e = {"value": round(T * args.steps / (ms_e2e * 1e-3), 2), "unit": "clips/s", "h2d_bytes_per_step": h_cq.numel() * 4 + h_pf.numel() * 4,
            "d2h_bytes_per_step": h_out.numel() * 4, "ms_per_step": round(ms_e2e / args.steps, 4),
            "how": "CrossClipTrackingModule API; per step every rank copies its clips' queries and pixel features from pinned host memory and reads "
                   "its clips' mask logits back (bytes are per rank)"}
-    cfg = {"workload": "Video-kMaX cross-clip tracking module on one synthetic video (BASELINE configs[2]): 64 clips x 2 frames, Q = 128, 4 layers, "
-                       "mask features 128 x 161 x 161 per frame, clip-sharded over the GPUs (forward_sharded: all-gather of clip queries, redundant "
-                       "layers, per-rank mask logits, all-gather of the logits)",
+    cfg = {"workload": "within-clip + cross-clip tracking on one long synthetic video (BASELINE configs[2]): 64 clips x 2 frames clip-sharded over the "
+                       "GPUs; per step every rank runs the within-clip temporal hot path on its clips (res5 21x21 + res4 41x41, no collective), then "
+                       "the cross-clip module (Q = 128, 4 layers, mask features 128 x 161 x 161 per frame) through forward_sharded: all-gather of the "
+                       "clip queries, layers run redundantly, per-rank mask logits, all-gather of the logits",
            "clips_per_video": T, "clips_per_gpu": Tl, "gflop_per_step": round(step_flops / 1e9, 1),
            "l2": "per-step pixel features and mask logits (1.7 GB each) exceed the 126 MB L2"}
     _emit(args, rank, world, sampler, "clips/s", T * args.steps / (ms_total * 1e-3), ms_total, e2e, launches * args.steps, roof, cfg, "strong")
