@@ -25,6 +25,7 @@
 #include "msda.cuh"
 #include "panoptic.cuh"
 #include "kmax_axial.cuh"
+#include "matching.cuh"
 #include "ffn_pair.cuh"
 
 using namespace axvs;
@@ -42,12 +43,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_MATCH, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel", "matching_kernels"};
 // Process-wide knobs are atomics (two host threads driving two devices may read / set them concurrently); the profiler's records and
 // the per-device attribute table are guarded by mutexes.  None of them is touched on the launch path beyond one relaxed load.
 std::atomic<int> g_fusion{4};   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
@@ -982,6 +983,48 @@ int axvs_mask_einsum(const float* pixel, const void* mk_bf16, int ld_mk, float* 
                                                                           bn_shift);
   }
   AXVS_CHECK_LAUNCH("mask_einsum_kernel");
+  return AXVS_OK;
+}
+
+int axvs_lsap(const float* cost, int batch, int n, int* col4row, axvs_stream_t stream) {
+  if (!cost || !col4row) return fail(AXVS_E_INVALID, "lsap: null pointer");
+  if (batch <= 0 || n <= 0) return fail(AXVS_E_INVALID, "lsap: sizes must be positive");
+  if (n > LS_MAX_N) return fail(AXVS_E_UNSUPPORTED, "lsap: at most %d rows / columns (got %d)", LS_MAX_N, n);
+  {
+    ProfScope ps(KC_MATCH, 0, (double)batch * n * n * 4.0, (cudaStream_t)stream);
+    const size_t cs = (size_t)n * n * sizeof(float);
+    const int in_smem = cs <= 170 * 1024 ? 1 : 0;
+    if (in_smem && cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(lsap) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    lsap_kernel<<<batch, LS_THREADS, in_smem ? cs : 0, (cudaStream_t)stream>>>(cost, n, col4row, in_smem);
+  }
+  AXVS_CHECK_LAUNCH("lsap_kernel");
+  return AXVS_OK;
+}
+
+size_t axvs_match_chain_workspace_bytes(int videos, int n, int e) {
+  if (videos <= 0 || n <= 0 || e <= 0) return 0;
+  return (size_t)videos * ((2 * (size_t)n * e + (size_t)n * n + 3) & ~(size_t)3) * sizeof(float);
+}
+
+int axvs_match_chain(const float* emb, int videos, int clips, int n, int e, int* indices, void* workspace, size_t workspace_bytes,
+                     axvs_stream_t stream) {
+  if (!emb || !indices || !workspace) return fail(AXVS_E_INVALID, "match_chain: null pointer");
+  if (videos <= 0 || clips <= 0 || n <= 0 || e <= 0) return fail(AXVS_E_INVALID, "match_chain: sizes must be positive");
+  if (n > LS_MAX_N) return fail(AXVS_E_UNSUPPORTED, "match_chain: at most %d queries per clip (got %d)", LS_MAX_N, n);
+  if (e % 4) return fail(AXVS_E_UNSUPPORTED, "match_chain: the embedding width must be a multiple of 4 (got %d)", e);
+  if (videos > 65535) return fail(AXVS_E_UNSUPPORTED, "match_chain: at most 65535 videos per call");
+  const size_t need = axvs_match_chain_workspace_bytes(videos, n, e);
+  if (workspace_bytes < need) return fail(AXVS_E_WORKSPACE, "match_chain: workspace %zu < required %zu", workspace_bytes, need);
+  {
+    ProfScope ps(KC_MATCH, 2.0 * videos * (double)(clips - 1) * n * n * e, (double)videos * clips * n * e * 4.0, (cudaStream_t)stream);
+    const size_t cs = (size_t)n * n * sizeof(float);
+    const int in_smem = cs <= 170 * 1024 ? 1 : 0;
+    if (in_smem && cudaFuncSetAttribute(match_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(match_chain) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    match_chain_kernel<<<videos, LS_THREADS, in_smem ? cs : 0, (cudaStream_t)stream>>>(emb, clips, n, e, indices, reinterpret_cast<float*>(workspace), in_smem);
+  }
+  AXVS_CHECK_LAUNCH("match_chain_kernel");
   return AXVS_OK;
 }
 

@@ -263,6 +263,23 @@ int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, cons
                         float* out, const axvs_msda_weights* w, int images, int len, void* workspace, size_t workspace_bytes,
                         axvs_stream_t stream);
 
+/* ---- clip-to-clip query matching ----------------------------------------------------------------------
+ * MaXTronWCDeepLab.match_from_embds (Vk/maxtron_deeplab/maxtron_wc_model.py:391-400; copy in maxtron_cc_model.py) and its chains
+ * (maxtron_wc_model.py:342-346, maxtron_cc_model.py:292-295).  The reference builds the cosine cost on the device, moves it to the host and
+ * calls scipy.optimize.linear_sum_assignment once per adjacent clip pair; these entry points keep everything on the device.
+ *
+ * axvs_lsap: exact linear sum assignment of `batch` square cost matrices [n, n] fp32 (row = target, column = current), n <= 256;
+ *   col4row[b, i] = column assigned to row i == linear_sum_assignment(cost[b])[1].  The algorithm, its float64 arithmetic and its tie
+ *   rules are scipy's (rectangular_lsap.cpp), so the permutation equals scipy's on the same matrix, ties included; a matrix without a
+ *   finite assignment yields -1 everywhere.
+ * axvs_match_chain: emb [videos, clips, n, e] fp32 (mask embeddings of the clips of each video).  indices[v, 0] = identity;
+ *   indices[v, i] = match_from_embds(aligned clip i-1, clip i): emb[v, i][indices[v, i]] is clip i aligned to the first clip.  One
+ *   launch for the whole chain of every video. */
+int axvs_lsap(const float* cost, int batch, int n, int* col4row, axvs_stream_t stream);
+size_t axvs_match_chain_workspace_bytes(int videos, int n, int e);
+int axvs_match_chain(const float* emb, int videos, int clips, int n, int e, int* indices, void* workspace, size_t workspace_bytes,
+                     axvs_stream_t stream);
+
 /* ---- kMaX pixel-decoder axial attention ------------------------------------------------------------- */
 
 /* One AxialAttention pass (Vk/kmax_deeplab/modeling/pixel_decoder/kmax_pixel_decoder.py:105-157, eval mode) over an image batch:

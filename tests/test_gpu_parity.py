@@ -1051,3 +1051,75 @@ def test_label_agreement_end_to_end(O):
     # the merge itself, on IDENTICAL (reference) logits, is exact: the panoptic kernels decide by comparisons of fp32 scores
     seg_same, _ = pp.panoptic_segments(ref["pred_logits"][0].cuda(), (want_masks * temp).cuda())
     assert float((seg_same.cpu().numpy() == ref_seg).mean()) >= 0.999
+
+
+# --------------------------------------------------------------------------------------------- clip-to-clip matching (row f4)
+def _lsap_cases():
+    rng = np.random.default_rng(7)
+    cases = []
+    for k in range(18):
+        for n in (4, 31, 64, 100, 128):
+            kind = k % 6
+            if kind == 0:
+                c = rng.random((n, n))
+            elif kind == 1:
+                c = rng.integers(0, 3, (n, n))                       # heavy ties
+            elif kind == 2:
+                c = rng.integers(0, 20, (n, n))
+            elif kind == 3:
+                c = np.full((n, n), 0.5)                             # constant: scipy returns the identity
+            elif kind == 4:
+                e = rng.standard_normal((n, 32))
+                e[n // 2] = e[0]                                     # duplicated embedding: exact cosine ties
+                en = e / np.linalg.norm(e, axis=1, keepdims=True)
+                c = 1 - en @ en[rng.permutation(n)].T
+            else:
+                c = rng.random((n, n)) - 0.5
+            cases.append(np.asarray(c, dtype=np.float32))
+    cases.append(rng.random((256, 256)).astype(np.float32))
+    cases.append(rng.integers(0, 4, (256, 256)).astype(np.float32))
+    return cases
+
+
+def test_lsap_matches_scipy_including_ties():
+    """axvs_lsap against scipy.optimize.linear_sum_assignment (the reference's call, maxtron_wc_model.py:398) on 92 seeded matrices:
+    random, integer-valued (heavily tied), constant, tied cosine costs, n up to 256.  Same algorithm, arithmetic and tie rules -> the
+    permutations are identical, not merely equally good."""
+    from scipy.optimize import linear_sum_assignment
+    from axial_vs_b200 import matching
+    cases = _lsap_cases()
+    by_n = {}
+    for c in cases:
+        by_n.setdefault(c.shape[0], []).append(c)
+    n_checked = 0
+    for n, cs in by_n.items():
+        got = matching.linear_sum_assignment(torch.from_numpy(np.stack(cs)).cuda()).cpu().numpy()      # one launch per size, one CTA per matrix
+        for c, g_ in zip(cs, got):
+            want = linear_sum_assignment(c)[1]
+            assert np.array_equal(g_, want), f"n={n}"
+            n_checked += 1
+    assert n_checked >= 90
+
+
+@pytest.mark.parametrize("videos,clips,n,e", [(1, 6, 128, 128), (3, 9, 100, 256), (2, 2, 17, 40)])
+def test_match_chain_against_reference_loop(videos, clips, n, e):
+    """The whole chain (normalise, cosine cost, assignment, permute, next clip) in ONE launch per call against the reference's loop
+    restated with torch + scipy (oracle/matching_oracle.py), without a host synchronisation inside the call."""
+    from axial_vs_b200 import matching
+    from oracle import matching_oracle as MO
+    g = torch.Generator().manual_seed(videos * 100 + clips)
+    emb = torch.randn(videos, clips, n, e, generator=g)
+    emb[:, 1:] = 0.7 * emb[:, 1:] + 0.3 * emb[:, :1][:, :, torch.randperm(n, generator=g)]      # clips share structure, shuffled
+    x = emb.cuda()
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        idx = matching.match_chain(x)                                   # must not synchronise with the host
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    idx = idx.cpu().numpy()
+    for v in range(videos):
+        assert np.array_equal(idx[v], MO.match_chain(emb[v]))
+    # reference-signature wrapper
+    one = matching.match_from_embds(x[0, 0], x[0, 1]).cpu().numpy()
+    assert np.array_equal(one, MO.match_from_embds(emb[0, 0], emb[0, 1]))
