@@ -92,10 +92,13 @@ SIGNATURES = {
     "axvs_panoptic_inference": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_float, c_float, c_float,
                                         c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "axvs_mask_einsum": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "axvs_msda_sample_workspace_bytes": (c_size_t, [c_int]),
+    "axvs_msda_sample_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                     c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "axvs_lsap": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "axvs_match_chain_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "axvs_match_chain": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "axvs_mask_einsum_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "axvs_mask_einsum_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "axvs_linear_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_int, c_int,
                                 c_void_p]),
     "axvs_pos3d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

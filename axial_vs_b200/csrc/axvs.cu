@@ -1028,20 +1028,21 @@ int axvs_match_chain(const float* emb, int videos, int clips, int n, int e, int*
   return AXVS_OK;
 }
 
-int axvs_mask_einsum_f32(const float* pixel, const float* mk, int ld_mk, float* out, int T, int Q, int P, float bn_scale, float bn_shift,
-                         axvs_stream_t stream) {
+int axvs_mask_einsum_f32(const float* pixel, const float* mk, int ld_mk, float* out, int T, int Q, int P, int channels, float bn_scale,
+                         float bn_shift, axvs_stream_t stream) {
   if (!pixel || !mk || !out) return fail(AXVS_E_INVALID, "mask_einsum_f32: null pointer");
   if (T <= 0 || Q <= 0 || P <= 0) return fail(AXVS_E_INVALID, "mask_einsum_f32: sizes must be positive");
   if (Q > 128) return fail(AXVS_E_UNSUPPORTED, "mask_einsum_f32: at most 128 queries per clip (got %d)", Q);
-  if (ld_mk < 128 || ld_mk % 4) return fail(AXVS_E_INVALID, "mask_einsum_f32: ld_mk must be >= 128 and a multiple of 4");
+  if (channels <= 0 || channels % 128) return fail(AXVS_E_UNSUPPORTED, "mask_einsum_f32: the channel count must be a multiple of 128 (got %d)", channels);
+  if (ld_mk < channels || ld_mk % 4) return fail(AXVS_E_INVALID, "mask_einsum_f32: ld_mk must be >= channels and a multiple of 4");
   if (T > 65535) return fail(AXVS_E_UNSUPPORTED, "mask_einsum_f32: at most 65535 clips");
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
   dim3 grid((P + ME_PT - 1) / ME_PT, T);
   {
-    ProfScope ps(KC_MASK, 6.0 * T * (double)Q * P * 128, (double)T * P * (512.0 + 4.0 * Q), (cudaStream_t)stream);
-    mask_einsum_split_kernel<<<grid, 256, 4 * 128 * 256, (cudaStream_t)stream>>>(pixel, mk, ld_mk, out, T, Q, P, bn_scale, bn_shift);
+    ProfScope ps(KC_MASK, 6.0 * T * (double)Q * P * channels, (double)T * P * (4.0 * channels + 4.0 * Q), (cudaStream_t)stream);
+    mask_einsum_split_kernel<<<grid, 256, 4 * 128 * 256, (cudaStream_t)stream>>>(pixel, mk, ld_mk, out, T, Q, P, bn_scale, bn_shift, channels);
   }
   AXVS_CHECK_LAUNCH("mask_einsum_split_kernel");
   return AXVS_OK;
@@ -1229,6 +1230,53 @@ int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, cons
   lw.ln1_g = w->ln1_g; lw.ln1_b = w->ln1_b; lw.w_ffn1 = w->w_ffn1; lw.b_ffn1 = w->b_ffn1; lw.w_ffn2 = w->w_ffn2; lw.b_ffn2 = w->b_ffn2;
   lw.w_ffn1_u = w->w_ffn1_u; lw.w_ffn2_u = w->w_ffn2_u; lw.w_ffn1_n = w->w_ffn1_n; lw.ln2_g = w->ln2_g; lw.ln2_b = w->ln2_b; lw.d_ffn = w->d_ffn;
   return axvs_ln_ffn_fwd(y, out, &lw, rows, ffn_ws, workspace_bytes - (size_t)(ffn_ws - base), stream);
+}
+
+size_t axvs_msda_sample_workspace_bytes(int rows) { return rows <= 0 ? 0 : (size_t)rows * (512 + 2048) + 256; }
+
+int axvs_msda_sample_fwd(const float* value_in, const float* query_in, const float* pos, int pos_images, const float* ref_points, int ref_images,
+                         const int* shapes_hw, const void* w_value, const float* b_value, const void* w_oa, const float* b_oa, int n_levels,
+                         int n_points, void* sampled_bf16, int images, int len, void* workspace, size_t workspace_bytes, axvs_stream_t stream) {
+  if (!value_in || !query_in || !ref_points || !shapes_hw || !w_value || !b_value || !w_oa || !b_oa || !sampled_bf16 || !workspace)
+    return fail(AXVS_E_INVALID, "msda_sample: null pointer");
+  if (images <= 0 || len <= 0) return fail(AXVS_E_INVALID, "msda_sample: sizes must be positive");
+  if ((pos && pos_images != images && pos_images != 1) || (ref_images != images && ref_images != 1))
+    return fail(AXVS_E_INVALID, "msda_sample: pos / reference points must cover every image or exactly one (broadcast)");
+  if (n_levels <= 0 || n_levels > MSDA_MAX_LEVELS || n_points <= 0 || n_levels * n_points > MSDA_MAX_LP)
+    return fail(AXVS_E_UNSUPPORTED, "msda_sample: at most %d levels and %d level*point samples per head (got %d x %d)", MSDA_MAX_LEVELS, MSDA_MAX_LP,
+                n_levels, n_points);
+  if ((long long)images * len > 0x7fffffffLL) return fail(AXVS_E_UNSUPPORTED, "msda_sample: too many tokens");
+  MsdaDims d;
+  memset(&d, 0, sizeof(d));
+  d.L = n_levels; d.P = n_points; d.len = len;
+  int acc = 0;
+  for (int l = 0; l < d.L; ++l) {
+    d.H[l] = shapes_hw[2 * l]; d.W[l] = shapes_hw[2 * l + 1]; d.start[l] = acc;
+    if (d.H[l] <= 0 || d.W[l] <= 0) return fail(AXVS_E_INVALID, "msda_sample: bad level shape");
+    acc += d.H[l] * d.W[l];
+  }
+  if (acc != len) return fail(AXVS_E_INVALID, "msda_sample: level shapes sum to %d tokens, len is %d", acc, len);
+  const int rows = images * len;
+  if (workspace_bytes < axvs_msda_sample_workspace_bytes(rows)) return fail(AXVS_E_WORKSPACE, "msda_sample: workspace too small");
+  uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* value = reinterpret_cast<__nv_bfloat16*>(base);
+  float* oa = reinterpret_cast<float*>(base + (size_t)rows * 512);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  GemmParams p = gemm_params(nullptr, 256, rows, 256, w_value, 256, 0, b_value, 256, 1.f, 0, value, 256, 0, 1, nullptr);
+  p.a_diag = 4; p.A32 = value_in;
+  if ((rc = launch_gemm(p, st))) return rc;
+  p = gemm_params(nullptr, 256, rows, 256, w_oa, 512, 0, b_oa, 512, 1.f, 0, oa, 512, 0, 0, nullptr);
+  p.a_diag = 4; p.A32 = query_in; p.A32b = pos; p.a32b_rows = (pos && pos_images == 1 && images > 1) ? len : 0;
+  p.n_valid = (8 * d.L * d.P * 3 + 31) / 32 * 32;
+  if ((rc = launch_gemm(p, st))) return rc;
+  {
+    ProfScope ps(KC_MSDA, 0, (double)rows * (8.0 * d.L * d.P * 4 * 64 + 2048 + 512), st);
+    msda_sample_kernel<<<(rows + 7) / 8, 256, 0, st>>>(value, oa, 512, ref_points, (ref_images == 1 && images > 1) ? len : 0,
+                                                     reinterpret_cast<__nv_bfloat16*>(sampled_bf16), rows, d);
+  }
+  AXVS_CHECK_LAUNCH("msda_sample_kernel");
+  return AXVS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- panoptic post-processing (row f4)

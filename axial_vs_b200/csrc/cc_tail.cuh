@@ -191,8 +191,10 @@ __global__ void __launch_bounds__(256) mask_einsum_kernel(const float* __restric
 // shared memory; acc += A_hi B_hi + A_hi B_lo + A_lo B_hi reproduces the fp32 product to ~2^-17 on the bf16 tensor cores.  The kernel
 // stays HBM-bound (the pixel tile is read once), so the extra MMAs are free -- and the per-pixel argmax over the queries, which decides
 // the final panoptic label, no longer flips on near-ties because of operand rounding (tests/test_error_budget_cpu.py).
+// `channels` (a multiple of 128) may exceed one shared-memory tile: the contraction then walks 128-channel slabs (Tube-Link mask features
+// have 256 channels, the Video-kMaX ones 128).
 __global__ void __launch_bounds__(256) mask_einsum_split_kernel(const float* __restrict__ pixel, const float* __restrict__ mk, int ld_mk,
-                                                                float* __restrict__ out, int T, int Q, int P, float bn_scale, float bn_shift) {
+                                                                float* __restrict__ out, int T, int Q, int P, float bn_scale, float bn_shift, int channels) {
   extern __shared__ __align__(128) uint8_t me_smem[];
   uint8_t* sBh = me_smem;                    // [128 c][128 p] bf16 hi
   uint8_t* sBl = me_smem + 128 * 256;        // lo
@@ -209,13 +211,18 @@ __global__ void __launch_bounds__(256) mask_einsum_split_kernel(const float* __r
     hi = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
     lo = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
   };
+  float acc[16][4];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  for (int k0 = 0; k0 < channels; k0 += 128) {
+  if (k0) __syncthreads();                             // every warp is done with the previous slab's tiles
   for (int c = tid; c < 128 * 16; c += 256) {
     const int q = c >> 4, ch = c & 15;
     float x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = 0.f;
     if (q < Q) {
-      const float4* s = reinterpret_cast<const float4*>(mk + ((size_t)t * Q + q) * ld_mk + ch * 8);
+      const float4* s = reinterpret_cast<const float4*>(mk + ((size_t)t * Q + q) * ld_mk + k0 + ch * 8);
       const float4 a = __ldg(s), b = __ldg(s + 1);
       x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
     }
@@ -224,7 +231,7 @@ __global__ void __launch_bounds__(256) mask_einsum_split_kernel(const float* __r
     *reinterpret_cast<uint4*>(sAh + off(q, ch)) = hi;
     *reinterpret_cast<uint4*>(sAl + off(q, ch)) = lo;
   }
-  const float* px = pixel + (size_t)t * 128 * P;
+  const float* px = pixel + ((size_t)t * channels + k0) * P;
   const bool vec_ok = (P % 4 == 0);
   for (int c = tid; c < 128 * 16; c += 256) {
     const int ch_row = c >> 4, chunk = c & 15;
@@ -245,9 +252,6 @@ __global__ void __launch_bounds__(256) mask_einsum_split_kernel(const float* __r
   }
   __syncthreads();
 
-  float acc[16][4];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 #pragma unroll 2
   for (int ks = 0; ks < 8; ++ks) {                     // k = channel, 16 per step
     uint32_t ah[4], al[4];
@@ -270,6 +274,7 @@ __global__ void __launch_bounds__(256) mask_einsum_split_kernel(const float* __r
       mma_bf16_16816(acc[jn + 1], ah, bh[2], bh[3]);
     }
   }
+  }                                                    // 128-channel slabs
   const int g = lane >> 2, t4 = lane & 3;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {

@@ -598,6 +598,50 @@ def pack_msda_layer(p: Dict[str, torch.Tensor], n_levels: int, n_points: int) ->
     return PackedMsda(ts, p["linear1.weight"].shape[0], n_levels, n_points)
 
 
+def pack_msda_sampler(sampling_offsets_w, sampling_offsets_b, attention_weights_w, attention_weights_b, value_w, value_b, n_levels: int, n_points: int):
+    """(w_value, b_value, w_oa, b_oa) images for `msda_sample_fwd` from the four Linear layers of a deformable attention."""
+    no = HEADS * n_levels * n_points
+    w_oa = torch.zeros(512, C, device=value_w.device)
+    b_oa = torch.zeros(512, device=value_w.device)
+    w_oa[: 2 * no] = sampling_offsets_w.detach().float()
+    w_oa[2 * no: 3 * no] = attention_weights_w.detach().float()
+    b_oa[: 2 * no] = sampling_offsets_b.detach().float()
+    b_oa[2 * no: 3 * no] = attention_weights_b.detach().float()
+    return pack_weight(value_w.detach().float().contiguous()), value_b.detach().float().contiguous(), pack_weight(w_oa), b_oa
+
+
+def msda_sample_fwd(value_in: torch.Tensor, query_in: torch.Tensor, pos: Optional[torch.Tensor], ref_points: torch.Tensor,
+                    shapes: Sequence[Tuple[int, int]], packed, n_levels: int, n_points: int) -> torch.Tensor:
+    """Sampling half of a deformable attention: value_in / query_in fp32 [images, len, 256], pos [images or 1, len, 256] or None,
+    ref_points [images or 1, len, n_levels, 2] -> sampled bf16 [images, len, 256]."""
+    _check(value_in, "value", torch.float32)
+    _check(query_in, "query", torch.float32)
+    images, length, c = value_in.shape
+    if c != C or tuple(query_in.shape) != (images, length, C):
+        raise RuntimeError("msda_sample_fwd: value and query must be [images, len, 256]")
+    if pos is not None:
+        _check(pos, "pos", torch.float32)
+        if pos.dim() != 3 or pos.shape[0] not in (1, images) or tuple(pos.shape[1:]) != (length, C):
+            raise RuntimeError("msda_sample_fwd: pos must be [images or 1, len, 256]")
+    _check(ref_points, "reference_points", torch.float32)
+    if ref_points.dim() != 4 or ref_points.shape[0] not in (1, images) or tuple(ref_points.shape[1:]) != (length, n_levels, 2):
+        raise RuntimeError(f"msda_sample_fwd: reference_points must be [{images} or 1, {length}, {n_levels}, 2]")
+    if len(shapes) != n_levels or sum(int(h) * int(v) for h, v in shapes) != length:
+        raise RuntimeError("msda_sample_fwd: spatial shapes do not match the token count")
+    out = torch.empty(images, length, C, dtype=torch.bfloat16, device=value_in.device)
+    lib = _lib.load()
+    hw = (ctypes.c_int * (2 * n_levels))(*[int(v) for s_ in shapes for v in s_])
+    wv, bv, woa, boa = packed
+    nbytes = lib.axvs_msda_sample_workspace_bytes(images * length)
+    with torch.cuda.device(value_in.device):
+        ws = workspace(nbytes, value_in.device)
+        rc = lib.axvs_msda_sample_fwd(value_in.data_ptr(), query_in.data_ptr(), _ptr(pos), pos.shape[0] if pos is not None else 0, ref_points.data_ptr(),
+                                      ref_points.shape[0], hw, wv.data_ptr(), bv.data_ptr(), woa.data_ptr(), boa.data_ptr(), n_levels, n_points,
+                                      out.data_ptr(), images, length, ws.data_ptr(), ws.numel(), _stream(value_in.device))
+    _lib.check(rc, "axvs_msda_sample_fwd")
+    return out
+
+
 def msda_layer_fwd(src: torch.Tensor, pos: Optional[torch.Tensor], ref_points: torch.Tensor, shapes: Sequence[Tuple[int, int]],
                    w: PackedMsda) -> torch.Tensor:
     """MSDeformAttn spatial encoder layer: src fp32 [images, len, 256]; pos fp32 [images or 1, len, 256]; ref_points fp32
@@ -678,12 +722,17 @@ def mask_einsum(pixel: torch.Tensor, mk: torch.Tensor, T: int, Q: int, P: int, b
     if mk.dtype not in (torch.bfloat16, torch.float32):
         raise RuntimeError("mask_einsum: mk must be bf16 or fp32")
     _check(mk, "mk", mk.dtype)
-    if pixel.numel() != T * 128 * P or mk.shape[0] != T * Q:
+    channels = pixel.numel() // (T * P)
+    if pixel.numel() != T * channels * P or mk.shape[0] != T * Q or (mk.dtype == torch.bfloat16 and channels != 128):
         raise RuntimeError("mask_einsum: size mismatch")
     out = torch.empty(Q, T, P, dtype=torch.float32, device=pixel.device)
     lib = _lib.load()
-    fn = lib.axvs_mask_einsum_f32 if mk.dtype == torch.float32 else lib.axvs_mask_einsum
     with torch.cuda.device(pixel.device):
-        rc = fn(pixel.data_ptr(), mk.data_ptr(), mk.shape[1], out.data_ptr(), T, Q, P, float(bn_scale), float(bn_shift), _stream(pixel.device))
+        if mk.dtype == torch.float32:
+            rc = lib.axvs_mask_einsum_f32(pixel.data_ptr(), mk.data_ptr(), mk.shape[1], out.data_ptr(), T, Q, P, channels, float(bn_scale),
+                                          float(bn_shift), _stream(pixel.device))
+        else:
+            rc = lib.axvs_mask_einsum(pixel.data_ptr(), mk.data_ptr(), mk.shape[1], out.data_ptr(), T, Q, P, float(bn_scale), float(bn_shift),
+                                      _stream(pixel.device))
     _lib.check(rc, "axvs_mask_einsum")
     return out

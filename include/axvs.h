@@ -194,8 +194,9 @@ int axvs_cc_class_pool(const void* ce_bf16, const float* w_act, float b_act, voi
 int axvs_mask_einsum(const float* pixel, const void* mk_bf16, int ld_mk, float* out, int T, int Q, int P, float bn_scale,
                      float bn_shift, axvs_stream_t stream);
 /* The same contraction with fp32 mask kernels and split-precision products (both operands split into bf16 hi / lo halves in shared
- * memory, three tensor-core products per pair): fp32-grade logits at the same HBM-bound cost.  mk fp32 rows (t, q), ld_mk % 4 == 0. */
-int axvs_mask_einsum_f32(const float* pixel, const float* mk, int ld_mk, float* out, int T, int Q, int P, float bn_scale,
+ * memory, three tensor-core products per pair): fp32-grade logits at the same HBM-bound cost.  pixel fp32 [T, channels, P] with
+ * channels % 128 == 0 (128 for Video-kMaX, 256 for the Tube-Link mask features: TL cc head :776); mk fp32 rows (t, q), ld_mk % 4 == 0. */
+int axvs_mask_einsum_f32(const float* pixel, const float* mk, int ld_mk, float* out, int T, int Q, int P, int channels, float bn_scale,
                          float bn_shift, axvs_stream_t stream);
 /* out = act((a W^T + bias) * scale) on fp32 rows a [M, lda] (converted inside the GEMM's producers).  split = 1: w_packed is the
  * split-precision image of [n_out, 3*K] = [W | W | W - bf16(W)] (axvs_pack_weight) and a is split into bf16 hi / lo halves:
@@ -262,6 +263,15 @@ size_t axvs_msda_layer_workspace_bytes(int rows, int d_ffn);
 int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, const float* ref_points, int ref_images, const int* shapes_hw,
                         float* out, const axvs_msda_weights* w, int images, int len, void* workspace, size_t workspace_bytes,
                         axvs_stream_t stream);
+
+/* The sampling half of a multi-scale deformable attention on its own (value projection, offsets / weights projection of query + pos,
+ * softmax, bilinear gather; WC/ops/modules/ms_deform_attn.py:98-123 == TL/mmdet/models/plugins/msdeformattn_pixel_decoder.py:573-614):
+ * sampled bf16 [images*len, 256].  The Tube-Link attention module inserts its temporal branch between this and the output projection
+ * (TL:616-632).  w_oa / b_oa: [sampling_offsets | attention_weights] stacked and zero-padded to 512 rows (as in axvs_msda_weights). */
+size_t axvs_msda_sample_workspace_bytes(int rows);
+int axvs_msda_sample_fwd(const float* value_in, const float* query_in, const float* pos, int pos_images, const float* ref_points, int ref_images,
+                         const int* shapes_hw, const void* w_value, const float* b_value, const void* w_oa, const float* b_oa, int n_levels,
+                         int n_points, void* sampled_bf16, int images, int len, void* workspace, size_t workspace_bytes, axvs_stream_t stream);
 
 /* ---- clip-to-clip query matching ----------------------------------------------------------------------
  * MaXTronWCDeepLab.match_from_embds (Vk/maxtron_deeplab/maxtron_wc_model.py:391-400; copy in maxtron_cc_model.py) and its chains

@@ -196,3 +196,45 @@ def wc_model():
     mat.VideoHungarianMatcher = object
     _cache["wcmodel"] = _load(pkg + ".maxtron_wc_model", os.path.join(VK, "maxtron_deeplab/maxtron_wc_model.py"))
     return _cache["wcmodel"]
+
+
+# ------------------------------------------------------------------------------------------------ Tube-Link source slices
+# The Tube-Link files import mmcv / mmdet / mmengine at module level (absent here), but the classes on the hot path are pure
+# torch + einops.  They are taken as LINE SLICES of the unmodified files and exec'd in a namespace that provides only the names the
+# slice uses: nothing is copied into the repository.
+TL = os.path.join(REF_ROOT, "MaXTron_Tube-Link")
+TL_PIXEL_DECODER = os.path.join(TL, "mmdet/models/plugins/msdeformattn_pixel_decoder.py")
+TL_CC_HEAD = os.path.join(TL, "models/video/tube_link_vis/mask2former_video_cc_head.py")
+
+
+def tl_available() -> bool:
+    return os.path.isfile(TL_PIXEL_DECODER) and os.path.isfile(TL_CC_HEAD)
+
+
+def _exec_slice(path: str, first: int, last: int, extra: dict | None = None) -> dict:
+    """Execute lines [first, last] (1-based, inclusive) of `path` in a fresh namespace with torch / einops names."""
+    import math
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from einops import rearrange
+    with open(path) as fh:
+        lines = fh.readlines()
+    src = "".join(lines[first - 1:last])
+    ns = {"math": math, "torch": torch, "nn": nn, "F": F, "Tensor": torch.Tensor, "rearrange": rearrange, "__name__": "tl_slice"}
+    ns.update(extra or {})
+    exec(compile(src, f"{path}:{first}-{last}", "exec"), ns)
+    return ns
+
+
+def tl_temporal_classes():
+    """TrajectoryAttention, TemporalEncoder, TemporalAxialTrajectoryAttentionLayer of the Tube-Link pixel decoder (TL :640-791)."""
+    ns = _exec_slice(TL_PIXEL_DECODER, 640, 791)
+    return ns["TrajectoryAttention"], ns["TemporalEncoder"], ns["TemporalAxialTrajectoryAttentionLayer"]
+
+
+def tl_cc_classes():
+    """TrajectoryAttentionLayer and TrajectoryAttention of the Tube-Link cross-clip head (TL cc head :152-247)."""
+    helper = _exec_slice(TL_CC_HEAD, 62, 71)                       # _get_activation_fn
+    ns = _exec_slice(TL_CC_HEAD, 152, 247, {"_get_activation_fn": helper["_get_activation_fn"]})
+    return ns["TrajectoryAttentionLayer"], ns["TrajectoryAttention"]

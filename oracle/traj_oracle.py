@@ -469,7 +469,7 @@ def msda_reference_points(spatial_shapes, n_images: int) -> Tensor:
 
 
 def ms_deform_attn(query: Tensor, reference_points: Tensor, src: Tensor, spatial_shapes, p: Params,
-                   n_heads: int = 8, n_points: int = 4) -> Tensor:
+                   n_heads: int = 8, n_points: int = 4, sample_only: bool = False) -> Tensor:
     """MSDeformAttn.forward without padding mask -- MSDA:92-125 and the bilinear sampling of CORE:51-72
     (grid_sample, align_corners=False, zero padding), written as explicit gathers."""
     N, Lq, C = query.shape
@@ -500,7 +500,46 @@ def ms_deform_attn(query: Tensor, reference_points: Tensor, src: Tensor, spatial
                 g = g.reshape(N, n_heads, Lq, n_points, d).permute(0, 2, 1, 3, 4)                         # [N,Lq,h,P,d]
                 wgt = (wx * wy * ok.to(query.dtype) * aw[:, :, :, l])[..., None]
                 out = out + (g * wgt).sum(3)
+    if sample_only:                                                                                       # the Tube-Link module works on this
+        return out.reshape(N, Lq, C)
     return linear(out.reshape(N, Lq, C), p["output_proj.weight"], p["output_proj.bias"])                  # :124
+
+
+def tl_axial_trajectory_msda(query: Tensor, query_pos: Tensor, query_pos3d: List[Tensor], reference_points: Tensor, spatial_shapes,
+                             p: Params, num_temporal_levels: int = 2, n_points: int = 4, identity: Optional[Tensor] = None) -> Tensor:
+    """MultiScaleDeformableAxialTrajectoryAttention.forward (batch_first, skip_connect, eval) --
+    TL/mmdet/models/plugins/msdeformattn_pixel_decoder.py:556-638.  query [bs, num_query, C] over all levels; query_pos3d[i] [B, T, H_i, W_i, C]
+    with bs = B*T.  `p`: sampling_offsets / attention_weights / value_proj / output_proj, `temporal_layer.temporal_layers.{k}.*`, `gamma`."""
+    identity = query if identity is None else identity                                                    # :558-561
+    sampled = ms_deform_attn(query + query_pos, reference_points, query, spatial_shapes, p, n_points=n_points, sample_only=True)   # :563-614
+    sizes = [h * w for h, w in spatial_shapes]
+    outs = list(torch.split(sampled, sizes, dim=1))                                                       # :618-620
+    layers = split_encoder_params(_sub(p, "temporal_layer"))
+    for i in range(num_temporal_levels):                                                                  # :622-627
+        f = outs[i]
+        t = f
+        for lp in layers:                                                                                 # TL TemporalEncoder :724-727 (features only)
+            t = axial_layer(t, query_pos3d[i], lp)[0]
+        outs[i] = f + p["gamma"].to(f.dtype) * t
+    out = linear(torch.cat(outs, dim=1), p["output_proj.weight"], p["output_proj.bias"])                  # :630-632
+    return out + identity                                                                                 # :638 (dropout = identity in eval)
+
+
+def tl_forward_head_clips(decoder_out: Tensor, mask_feature: Tensor, p: Params):
+    """Mask2FormerVideoCCHeadTube.forward_head_clips + pred_class -- TL/models/video/tube_link_vis/mask2former_video_cc_head.py:761-797.
+    decoder_out [t, l, q, b, c] (clips, layers, queries, batch, channels); mask_feature [b, T_frames, c_m, h, w].
+    `p`: post_norm.{weight,bias}, activation_proj, cls_embed, mask_embed.{0,2,4} (Linear-ReLU-Linear-ReLU-Linear).
+    Returns (class logits [l, b, q, K+1], mask logits [l, b, T_frames, q, h, w])."""
+    num_clips = decoder_out.shape[0]
+    fpc = mask_feature.shape[1] // num_clips
+    x = layer_norm(decoder_out, p["post_norm.weight"], p["post_norm.bias"])                               # :768
+    x = x.permute(1, 3, 0, 2, 4)                                                                          # (l, b, t, q, c)  :769
+    act = torch.softmax(linear(x, p["activation_proj.weight"], p["activation_proj.bias"]), dim=2)        # :790
+    cls = linear((x * act).sum(dim=2), p["cls_embed.weight"], p["cls_embed.bias"])                        # :791-796
+    me = linear(torch.relu(linear(torch.relu(linear(x, p["mask_embed.0.weight"], p["mask_embed.0.bias"])),
+                                  p["mask_embed.2.weight"], p["mask_embed.2.bias"])), p["mask_embed.4.weight"], p["mask_embed.4.bias"])   # :772
+    masks = [torch.einsum("lbqc,btchw->lbtqhw", me[:, :, k], mask_feature[:, fpc * k:fpc * (k + 1)]) for k in range(num_clips)]   # :774-777
+    return cls, torch.cat(masks, dim=2)
 
 
 def msda_encoder_layer(src: Tensor, pos: Tensor, reference_points: Tensor, spatial_shapes, p: Params) -> Tensor:

@@ -1123,3 +1123,99 @@ def test_match_chain_against_reference_loop(videos, clips, n, e):
     # reference-signature wrapper
     one = matching.match_from_embds(x[0, 0], x[0, 1]).cpu().numpy()
     assert np.array_equal(one, MO.match_from_embds(emb[0, 0], emb[0, 1]))
+
+
+# --------------------------------------------------------------------------------------------- Tube-Link rows (A7, A10)
+def test_tube_link_temporal_encoder_golden(golden):
+    """Tube-Link TemporalEncoder drop-in against the output of the UNMODIFIED Tube-Link classes (tests/golden/tl_temporal.npz)."""
+    from axial_vs_b200 import tube_link
+    gz = golden("tl_temporal")
+    B, T, H, W, seed = (int(gz[k]) for k in "B T H W seed".split())
+    enc = tube_link.TemporalEncoder(256, 1024, attn_drop=0.0, num_temporal_layer=1).eval()
+    enc.load_state_dict(synth.encoder_params(seed, 1), strict=True)
+    enc.cuda()
+    src = synth.randn(seed + 1, B * T, H * W, 256)
+    from oracle import traj_oracle as O_
+    pos = O_.level_pos3d(B, T, H, W, synth.level_embed(seed + 2)[0])
+    with torch.no_grad():
+        y = enc(src=src.cuda(), pos=pos.cuda())
+    assert nerr(y, torch.from_numpy(gz["y"])) < TOL
+
+
+def test_tube_link_cc_layer_golden(golden):
+    from axial_vs_b200 import cross_clip
+    gz = golden("tl_cc_layer")
+    b, Q, T, seed = (int(gz[k]) for k in "b Q T seed".split())
+    p = {}
+    g = torch.Generator().manual_seed(seed)
+    synth.traj_attn_params(g, "self_attn.", 256, p, fused_qkv=True)
+    p["norm.weight"] = 1 + 0.1 * torch.randn(256, generator=g)
+    p["norm.bias"] = 0.1 * torch.randn(256, generator=g)
+    m = cross_clip.TrajectoryAttentionLayer(256, 8).eval()
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    with torch.no_grad():
+        y = m(synth.randn(seed + 1, b, T * Q, 256).cuda(), seq_len=Q, num_frames=T)
+    assert nerr(y, torch.from_numpy(gz["y"])) < TOL
+
+
+def _tl_attention_params(seed, n_levels, n_temporal_layers=1):
+    g = torch.Generator().manual_seed(seed)
+    p = {k[len("self_attn."):]: v for k, v in synth.msda_layer_params(seed, n_levels).items() if k.startswith("self_attn.")}
+    p.update({f"temporal_layer.{k}": v for k, v in synth.encoder_params(seed + 1, n_temporal_layers).items()})
+    p["gamma"] = 0.5 + torch.rand(256, generator=g)
+    return p
+
+
+@pytest.mark.parametrize("batch_first", [True, False])
+def test_tube_link_axial_trajectory_msda(O, batch_first):
+    """MultiScaleDeformableAxialTrajectoryAttention (TL plugin :393-638): sampling -> gamma-skip temporal branch on the two
+    low-resolution levels -> shared output_proj -> identity residual, against the oracle composition (whose temporal classes are
+    pinned on the Tube-Link sources by tl_temporal.npz)."""
+    from axial_vs_b200 import tube_link, msda
+    B, T, seed = 2, 3, 6100
+    shapes = [(5, 6), (9, 11), (17, 21)]
+    p = _tl_attention_params(seed, len(shapes))
+    m = tube_link.MultiScaleDeformableAxialTrajectoryAttention(256, 8, num_levels=3, num_temporal_levels=2, num_temporal_layers=1, num_temporal_dim=1024,
+                                                               num_points=4, dropout=0.0, batch_first=batch_first).eval()
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    n = sum(h * w for h, w in shapes)
+    query = synth.randn(seed + 2, B * T, n, 256)
+    qpos = synth.randn(seed + 3, B * T, n, 256)
+    le = synth.level_embed(seed + 4)
+    pos3d = [O.level_pos3d(B, T, h, w, le[i]) for i, (h, w) in enumerate(shapes[:2])]
+    ref = O.msda_reference_points(shapes, B * T)
+    want = O.tl_axial_trajectory_msda(query, qpos, pos3d, ref, shapes, p, 2)
+    ss = torch.tensor(shapes)
+    if batch_first:
+        got = m(query.cuda(), query_pos=qpos.cuda(), query_pos3d=[x.cuda() for x in pos3d], reference_points=ref.cuda(), spatial_shapes=ss)
+    else:
+        got = m(query.permute(1, 0, 2).cuda(), query_pos=qpos.permute(1, 0, 2).cuda(), query_pos3d=[x.cuda() for x in pos3d],
+                reference_points=ref.cuda(), spatial_shapes=ss).permute(1, 0, 2)
+    assert nerr(got, want) < TOL
+
+
+def test_tube_link_forward_head_clips(O):
+    """forward_head_clips + pred_class of the Tube-Link cross-clip head (TL cc head :761-797): 100 queries, 256-channel mask features."""
+    from axial_vs_b200 import tube_link
+    t, l, q, c, K, fpc, h, w, seed = 4, 3, 100, 256, 40, 2, 24, 20, 6200
+    g = torch.Generator().manual_seed(seed)
+    head = tube_link.CCHeadPredictor(256, 256, K).eval()
+    with torch.no_grad():
+        for prm in head.parameters():
+            prm.copy_(torch.randn(prm.shape, generator=g) * (0.06 if prm.dim() > 1 else 0.1))
+        head.post_norm.weight.add_(1.0)
+    p = {k: v.detach().clone() for k, v in head.state_dict().items()}
+    head.cuda()
+    dec = synth.randn(seed + 1, t, l, q, 1, c)
+    mf = synth.randn(seed + 2, 1, t * fpc, c, h, w)
+    want_cls, want_masks = O.tl_forward_head_clips(dec, mf, p)
+    with torch.no_grad():
+        cls, masks = head.forward_head_clips(dec.cuda(), mf.cuda())
+    assert len(cls) == l and len(masks) == l
+    for i in range(l):
+        assert nerr(cls[i], want_cls[i]) < TOL
+        assert nerr(masks[i], want_masks[i]) < TOL
+        agree = (masks[i].cpu().argmax(2) == want_masks[i].argmax(2)).float().mean().item()
+        assert agree >= 0.998, agree

@@ -216,3 +216,31 @@ def test_kmax_axial_attention_2d(golden):
     N, C, H, W, seed = (int(gz[k]) for k in "N C H W seed".split())
     ph, pw = synth.kmax_axial_params(seed, C), synth.kmax_axial_params(seed + 1, 1024)
     _close(KO.axial_attention_2d(synth.randn(seed + 100, N, C, H, W), ph, pw), gz["y"])
+
+
+# ------------------------------------------------------------------------------------------------ Tube-Link (goldens from the TL sources)
+def test_tube_link_temporal_encoder(golden):
+    """Oracle against the UNMODIFIED Tube-Link TemporalEncoder (source slice exec'd by oracle/make_golden_tl.py): pins rows A1/A2/A7 on TL."""
+    gz = golden("tl_temporal")
+    B, T, H, W, seed = (int(gz[k]) for k in "B T H W seed".split())
+    p = synth.encoder_params(seed, 1)
+    assert synth.checksum(p) == pytest.approx(float(gz["wsum"]), rel=1e-12)
+    src = synth.randn(seed + 1, B * T, H * W, 256)
+    pos = O.level_pos3d(B, T, H, W, synth.level_embed(seed + 2)[0])
+    y, _, _ = O.temporal_encoder(src, pos, O.split_encoder_params(p))
+    assert (y - torch.from_numpy(gz["y"])).abs().max().item() < 2e-5
+
+
+def test_tube_link_cc_layer(golden):
+    """Oracle against the unmodified Tube-Link cross-clip TrajectoryAttentionLayer (TL cc head :152-247)."""
+    gz = golden("tl_cc_layer")
+    b, Q, T, seed = (int(gz[k]) for k in "b Q T seed".split())
+    p = {}
+    g = torch.Generator().manual_seed(seed)
+    synth.traj_attn_params(g, "self_attn.", 256, p, fused_qkv=True)
+    p["norm.weight"] = 1 + 0.1 * torch.randn(256, generator=g)
+    p["norm.bias"] = 0.1 * torch.randn(256, generator=g)
+    assert synth.checksum(p) == pytest.approx(float(gz["wsum"]), rel=1e-12)
+    x = synth.randn(seed + 1, b, T * Q, 256)
+    y = O.cc_attention_layer(x, p, Q, T)
+    assert (y - torch.from_numpy(gz["y"])).abs().max().item() < 2e-5
