@@ -145,3 +145,22 @@ def test_shared_pos_detection():
     assert ops.shared_pos(full) is full
     assert ops.shared_pos(one) is one
     assert ops.shared_pos(ex[1:4]).shape[0] == 1          # slices of a broadcast (clip chunks) stay broadcasts
+
+
+def test_registry_surface_without_frameworks():
+    """`from_config` maps the reference's cfg keys one for one (WC/maxtron_within_clip_tracking_module.py:44-63) and `register()`
+    degrades gracefully when detectron2 / mmcv are absent (they are, in this image)."""
+    from types import SimpleNamespace as NS
+    from axial_vs_b200 import registry
+    wc = NS(DROPOUT=0.0, ATTN_DROP=0.0, NHEADS=8, DIM_FEEDFORWARD=1024, NUM_STAGES=2, SPATIAL_LAYERS=2, TEMPORAL_LAYERS=4,
+            TEMPORAL_ATTN_TYPE="axial-trajectory", CONV_DIMS=256, SPATIAL_IN_FEATURES=["res3", "res4", "res5"], TEMPORAL_IN_FEATURES=["res4", "res5"])
+    cfg = NS(MODEL=NS(MAXTRON=NS(WITHIN_CLIP_TRACKING_MODULE=wc, CROSS_CLIP_TRACKING_MODULE=NS(ENABLE=False))), INPUT=NS(NUM_CLIP_FRAMES=2))
+    shape = {f"res{i}": NS(channels=c, stride=s) for i, c, s in ((2, 256, 4), (3, 512, 8), (4, 1024, 16), (5, 2048, 32))}
+    kw = registry.B200WithinClipTrackingModule.from_config(cfg, shape)
+    assert sorted(kw["input_shape"]) == ["res3", "res4", "res5"] and kw["transformer_temporal_layers"] == 4 and kw["num_clip_frames"] == 2
+    m = registry.B200WithinClipTrackingModule(**kw)
+    keys = list(m.state_dict().keys())
+    assert all(k.startswith("within_clip_tracking_module.") for k in keys)                    # the reference's checkpoint prefix
+    assert any("transformer.encoder.temporal_layers.1.temporal_layers.1.width_attn.proj_kv.weight" in k for k in keys)
+    out = registry.register()
+    assert set(out) == {"detectron2", "mmcv"}
