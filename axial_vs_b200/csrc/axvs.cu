@@ -14,6 +14,7 @@
 #include "simt.cuh"
 #include "traj_fused.cuh"
 #include "traj_ts.cuh"
+#include "traj_pair.cuh"
 #include "ffn_fused.cuh"
 #include "ffn_n256.cuh"
 #include "qkv_fused.cuh"
@@ -53,7 +54,7 @@ const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel"
 // the per-device attribute table are guarded by mutexes.  None of them is touched on the launch path beyond one relaxed load.
 std::atomic<int> g_fusion{4};   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
 std::atomic<int> g_attn_core{1};   // 1 = tcgen05 attention core (attn_tc.cuh), 0 = the mma.sync kernels (validation baseline)
-std::atomic<int> g_pair{0};   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
+std::atomic<int> g_pair{getenv("AXVS_PAIR") ? atoi(getenv("AXVS_PAIR")) : 0};   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
 struct Profiler {
@@ -118,6 +119,9 @@ int device_info(DeviceInfo** out) {
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     if (major != 10) return fail(AXVS_E_UNSUPPORTED, "libaxvs is built for sm_100a only (device major %d)", major);
     cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+#ifdef AXVS_WAIT_PROFILE
+    if (const char* e = getenv("AXVS_DEBUG_SMS")) d.sms = atoi(e);      // debug builds: persistent grids of fewer CTAs (is a kernel bound by a chip-wide resource?)
+#endif
   }
   if (!d.gemm_attr) {
     if (cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess)
@@ -126,7 +130,8 @@ int device_info(DeviceInfo** out) {
   }
   if (!d.traj_attr) {
     if (cudaFuncSetAttribute(traj_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(traj_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM_BYTES) != cudaSuccess)
+        cudaFuncSetAttribute(traj_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(traj_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM_BYTES) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(traj_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.traj_attr = true;
   }
@@ -317,7 +322,7 @@ int axvs_version(void) { return 120; }
 static const char k_build_marker[] = "AXVS_BUILD_ID=" AXVS_BUILD_ID;
 const char* axvs_build_id(void) { return k_build_marker + 14; }
 int axvs_set_pair_mode(int on) {
-  return g_pair.exchange(on ? 1 : 0);
+  return g_pair.exchange(on);
 }
 int axvs_set_attn_core(int core) {
   return g_attn_core.exchange(core ? 1 : 0);
@@ -596,7 +601,10 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
     {
       ProfScope ps(g_fusion >= 4 ? KC_TRAJTS : KC_TRAJ, 2.0 * rows * 256.0 * 256.0 * (2.0 + 2.0 * F) + 4.0 * rows * F * 256.0,
                    (double)rows * (512.0 * (F + 1) + 1024.0 + (resid ? 1024.0 : 0.0) + (ln_img ? 1536.0 : 0.0)), st);
-      if (g_fusion >= 4) traj_ts_kernel<<<tiles < d->sms ? tiles : d->sms, TF_THREADS, TT_SMEM_BYTES, st>>>(tp);
+      if (g_fusion >= 4 && (g_pair & 2) && tiles >= 2) {
+        const int pair_tiles = (tiles + 1) / 2, max_pairs = d->sms / 2;
+        traj_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), TF_THREADS, TP_SMEM_BYTES, st>>>(tp);
+      } else if (g_fusion >= 4) traj_ts_kernel<<<tiles < d->sms ? tiles : d->sms, TF_THREADS, TT_SMEM_BYTES, st>>>(tp);
       else traj_fused_kernel<<<tiles < d->sms ? tiles : d->sms, TF_THREADS, TF_SMEM_BYTES, st>>>(tp);
     }
     AXVS_CHECK_LAUNCH("traj_ts_kernel / traj_fused_kernel");
@@ -713,9 +721,9 @@ int ffn_fused_launch(const uint8_t* s_img, const float* s32, float* out, const a
   fp.b1 = w->b_ffn1; fp.b2 = w->b_ffn2;
   fp.rows = rows; fp.tiles = (rows + 127) / 128; fp.d_ffn = w->d_ffn; fp.eps = 1e-5f;
   {
-    const bool n256 = !g_pair && g_fusion >= 4 && w->w_ffn1_n && w->d_ffn % 256 == 0;
+    const bool n256 = !(g_pair & 1) && g_fusion >= 4 && w->w_ffn1_n && w->d_ffn % 256 == 0;
     ProfScope ps(n256 ? KC_FFN256 : KC_FFN, 4.0 * rows * 256.0 * w->d_ffn, (double)rows * 256 * 10.0, st);
-    if (g_pair) {
+    if (g_pair & 1) {
       const int pair_tiles = (fp.tiles + 1) / 2, max_pairs = d->sms / 2;
       ffn_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), FF_THREADS, FP_SMEM_BYTES, st>>>(fp);
     } else if (g_fusion >= 4 && w->w_ffn1_n && w->d_ffn % 256 == 0) {
@@ -1498,6 +1506,14 @@ int axvs_debug_read_waits(unsigned long long* out64) {
   cudaMemcpyFromSymbol(out64, g_wait_prof, sizeof(unsigned long long) * 64);
   unsigned long long z[64] = {0};
   cudaMemcpyToSymbol(g_wait_prof, z, sizeof(z));
+  return AXVS_OK;
+}
+// debug builds only: the timeline stamps of the traced tile (512 slots, 0 = not written)
+int axvs_debug_read_trace(unsigned long long* out512) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out512, g_trace, sizeof(unsigned long long) * 512);
+  static unsigned long long z[512];
+  cudaMemcpyToSymbol(g_trace, z, sizeof(z));
   return AXVS_OK;
 }
 #endif

@@ -13,11 +13,19 @@ namespace axvs {
 __device__ unsigned long long g_wait_prof[64];
 #define AXVS_PROF_DECL(n) long long prof_acc_[n] = {}; const long long prof_t0_ = clock64();
 #define AXVS_PROF_WAIT(i, stmt) { const long long t_ = clock64(); stmt; prof_acc_[i] += clock64() - t_; }
+__device__ unsigned long long g_trace[512];
+// timeline trace of ONE tile iteration of CTA 0 (clock64 is an SM-wide counter, so the roles' stamps are comparable)
+#define AXVS_TRACE(cond, slot) if ((cond) && blockIdx.x == 0) g_trace[slot] = (unsigned long long)clock64();
+#define AXVS_PROF_MARK(v) const long long v = clock64();
+#define AXVS_PROF_SPAN(i, since) prof_acc_[i] += clock64() - (since);
 #define AXVS_PROF_FLUSH(base, n, cond) if (cond) { for (int i_ = 0; i_ < (n); ++i_) atomicAdd(&g_wait_prof[(base) + i_], (unsigned long long)prof_acc_[i_]); \
                                                    atomicAdd(&g_wait_prof[(base) + (n)], (unsigned long long)(clock64() - prof_t0_)); }
 #else
 #define AXVS_PROF_DECL(n)
 #define AXVS_PROF_WAIT(i, stmt) stmt;
+#define AXVS_PROF_MARK(v)
+#define AXVS_TRACE(cond, slot)
+#define AXVS_PROF_SPAN(i, since)
 #define AXVS_PROF_FLUSH(base, n, cond)
 #endif
 

@@ -1,92 +1,112 @@
-// Fused "temporal half" of TrajectoryAttention, tensor-memory-operand version (fusion level 4).  Same math and interface
-// as traj_fused_kernel (traj_fused.cuh; reference WC/temporal_attention.py:61-75 + residual :204/:213 + norm1 :217), but
-// every UMMA reads its A operand from TENSOR MEMORY, which lets the N = 128 instructions run at the full 64 clk rate
-// (A in shared memory: ~90 clk, the operand reads saturate the shared-memory port) and removes every shared-memory
-// hand-off between the epilogue and the tensor pipe:
+// CTA-pair (cta_group::2) version of traj_ts_kernel: the two CTAs of a cluster process two adjacent 128-row tiles with ONE stream of
+// M = 256 tensor-core instructions issued by the leader CTA.  Same math, TMEM plan and epilogue as traj_ts_kernel (traj_ts.cuh; reference
+// WC/temporal_attention.py:61-75 + residual :204/:213 + norm1 :217).
 //
-//   TMEM columns [  0,128)  Q2P : q2 = (x_diag Wpq^T + bpq) * scale as bf16 pairs, later overwritten IN PLACE by o (A of GEMM 3)
-//                [128,256)  XA  : the current A tile (x_diag, then x_f per frame), copied from the TMA-landed K-block
-//                                 images with tcgen05.cp; the shared-memory slot is released as soon as the copy retires
-//                [256,512)  two 128-column accumulator stages (stage g <-> epilogue group g <-> heads 4g..4g+3)
+// Why: a single CTA that streams every weight unit through shared memory ONCE per 128-row tile is bound by the shared-memory port, not by
+// the tensor pipe: each N = 128 instruction reads 4 KiB of B and the TMA refills 4 KiB behind it = 128 B/clk at the 64 clk rate.  Measured
+// (tools/microbench/gemm_core_rate.cu): 670 clk per 32 KiB unit instead of 512, 889 with the per-frame tcgen05.cp of the A tile.  With
+// cta_group::2 each CTA stages only HALF of every unit (64 of its 128 rows; the tensor core reads the other half from the peer), so the
+// port load halves: 512 clk per unit, 616 with the A copies (tools/microbench/gemm_core_rate_pair.cu) -- and the weight ring shrinks to
+// 16 KiB slots, which pays for an A ring of 6 K-blocks.
 //
-//   GEMM 1: q2 halves -> stages, finalised (bias, scale, bf16) into Q2P by the epilogue
-//   GEMM 2: per frame four [k2 | v2] chunks of two heads; online softmax over frames and o accumulation in registers
-//           (a variant in which both groups drain every chunk, one head each, removed the issuer's stage waits but cost
-//            more in epilogue hand-shakes than it saved: 150 us vs 132 us per res4 launch)
-//   GEMM 3: out = resid + o Wproj^T + bproj (+ fused LayerNorm), A = o from Q2P, accumulators = both stages
-//
-// Hazards between copies / UMMAs on the same TMEM columns are resolved by the tensor pipe executing in issue order.
-// q2 is held as bf16 (the same rounding every other GEMM operand of the path gets); measured effect on the layer output
-// < 2e-5 of its max-abs (oracle emulation), inside the 1e-2 parity tolerance.
-//
-// Warp roles (384 threads): warps 0-3 / 4-7 = epilogue groups, warp 8 = A-tile TMA producer, warp 9 = weight TMA producer,
-// warp 10 = tcgen05.cp + MMA issuer (converged warp, elected lane).
+// Protocol (identical barrier offsets in both CTAs):
+//   * A-tile and weight TMA producers run in BOTH CTAs (own tile / own half of the unit) and signal their local full barriers; the
+//     non-leader's warp 10 ("relay") forwards each completed local full barrier to the leader's (count 2 there) with a remote arrive;
+//   * the leader's warp 10 waits its full barriers, issues tcgen05.cp.cta_group::2 / tcgen05.mma.cta_group::2 (both CTAs' shared
+//     memory -> both CTAs' tensor memory at the same addresses) and commits with a cluster multicast, so a_empty / w_empty / s_full
+//     fire in both CTAs;
+//   * epilogue -> issuer hand-offs (stage drained, o ready) are remote arrives on the LEADER's barriers (count 8 / 16).
 #pragma once
-#include "traj_fused.cuh"
+#include "traj_ts.cuh"
 
 namespace axvs {
 
-#ifndef TT_HOIST
-#define TT_HOIST 0
-#endif
-#ifndef TT_OWAIT
-#define TT_OWAIT 0
-#endif
-#ifndef TT_PREFETCH
-#define TT_PREFETCH 0
-#endif
-constexpr int TT_A_SLOTS = 4;
-constexpr int TT_W_SLOTS = 4;
-constexpr int TT_STG_BYTES = 8 * 4096;             // per-warp transpose staging of the output epilogue (+ LayerNorm statistics exchange)
-constexpr int TT_SMEM_BYTES = TT_STG_BYTES + TT_A_SLOTS * TF_KB + TT_W_SLOTS * TF_WU + TF_BIAS_BYTES + 512;
-static_assert(TT_SMEM_BYTES <= 232448, "traj_ts_kernel exceeds the 227 KiB shared-memory limit");
+constexpr int TP_A_SLOTS = 6;
+constexpr int TP_W_SLOTS = 5;                   // half units
+constexpr int TP_WH = 16384;                    // half a weight unit: [2 K-blocks][64 rows x 128 B]
+constexpr int TP_SMEM_BYTES = TT_STG_BYTES + TP_A_SLOTS * TF_KB + TP_W_SLOTS * TP_WH + TF_BIAS_BYTES + 512;
+static_assert(TP_SMEM_BYTES <= 232448, "traj_pair_kernel exceeds the 227 KiB shared-memory limit");
 
-__device__ __forceinline__ float bf16lo_to_f32(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16hi_to_f32(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ void umma_bf16_ts_lo_pair(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(UMMA_DESC_HI), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One weight unit for a CTA pair with A in tensor memory (each CTA's own, same address): each CTA holds half of the unit's rows as
+// [2 K-blocks][64 rows x 128 B] (K-blocks 8 KiB apart); 8 UMMAs with M = 256, N = 128.  Elected lane of a converged warp in the leader.
+__device__ __forceinline__ void umma_unit_elect_ts_pair(uint32_t tmem_d, uint32_t ta0, uint32_t ta1, uint32_t w, uint32_t idesc, bool accumulate,
+                                                        uint64_t* c0, uint64_t* c1) {
+  const uint32_t w_lo = umma_desc_lo(w);
+  if (elect_one()) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_ts_lo_pair(tmem_d, ta0 + 8 * k, w_lo + 2 * k, idesc, (accumulate || k) ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_ts_lo_pair(tmem_d, ta1 + 8 * k, w_lo + (8192 >> 4) + 2 * k, idesc, 1u);
+    if (c0) umma_commit_pair(c0);
+    if (c1) umma_commit_pair(c1);
+  }
+  __syncwarp();
+}
+// One K-block image (128 rows x 64 bf16) of EACH CTA's shared memory (same offset) -> 32 columns of each CTA's tensor memory.
+__device__ __forceinline__ void tmem_cp_kblock_pair(uint32_t taddr, uint32_t smem_addr) {
+  const uint32_t lo = umma_desc_lo(smem_addr);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    asm volatile(
+        "{\n\t.reg .b64 d;\n\tmov.b64 d, {%1, %2};\n\t"
+        "tcgen05.cp.cta_group::2.128x256b [%0], d;\n\t}" ::"r"(taddr + 8 * k), "r"(lo + 2 * k), "r"(UMMA_DESC_HI)
+        : "memory");
+}
 
-__global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_pair_kernel(const TrajParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* stg_all = smem;
   uint8_t* a_ring = smem + TT_STG_BYTES;
-  uint8_t* w_ring = a_ring + TT_A_SLOTS * TF_KB;
-  float* sb_pq = reinterpret_cast<float*>(w_ring + TT_W_SLOTS * TF_WU);
+  uint8_t* w_ring = a_ring + TP_A_SLOTS * TF_KB;
+  float* sb_pq = reinterpret_cast<float*>(w_ring + TP_W_SLOTS * TP_WH);
   float* sb_v2 = sb_pq + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb_v2 + 256);
-  uint64_t* a_full = bars;                       // [TT_A_SLOTS]
-  uint64_t* a_empty = a_full + TT_A_SLOTS;       // [TT_A_SLOTS]
-  uint64_t* w_full = a_empty + TT_A_SLOTS;       // [TT_W_SLOTS]
-  uint64_t* w_empty = w_full + TT_W_SLOTS;       // [TT_W_SLOTS]
-  uint64_t* s_full = w_empty + TT_W_SLOTS;       // [2]
-  uint64_t* s_empty = s_full + 2;                // [2]
-  uint64_t* o_ready = s_empty + 2;
+  uint64_t* a_full = bars;                       // [TP_A_SLOTS]
+  uint64_t* a_empty = a_full + TP_A_SLOTS;       // [TP_A_SLOTS]
+  uint64_t* w_full = a_empty + TP_A_SLOTS;       // [TP_W_SLOTS]
+  uint64_t* w_empty = w_full + TP_W_SLOTS;       // [TP_W_SLOTS]
+  uint64_t* s_full = w_empty + TP_W_SLOTS;       // [2]
+  uint64_t* s_empty = s_full + 2;                // [2]  (the leader's copy is the live one)
+  uint64_t* o_ready = s_empty + 2;               //      (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 1);
-  volatile uint32_t* tile_flag = tmem_slot + 2;     // tiles started by the issuer (paces the residual prefetcher, warp 11)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-#ifdef AXVS_WAIT_PROFILE
-  if (threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_trace[500] = gt; g_trace[501] = clock64(); }
-#endif
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int pair_tiles = (p.tiles + 1) >> 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TT_A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < TT_W_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
-    mbar_init(o_ready, 8);
-    *tile_flag = 0;
+    const uint32_t fullc = rank == 0 ? 2 : 1;                // leader: own producer + the peer's relay
+    for (int i = 0; i < TP_A_SLOTS; ++i) { mbar_init(&a_full[i], fullc); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < TP_W_SLOTS; ++i) { mbar_init(&w_full[i], fullc); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
+    mbar_init(o_ready, 16);
     fence_barrier_init();
   }
-  if (warp == 10) tmem_alloc(tmem_slot, 512);
   for (int i = threadIdx.x; i < 256; i += TF_THREADS) { sb_pq[i] = p.b_pq[i]; sb_v2[i] = p.b_v2[i]; }
+  __syncthreads();
+  cluster_sync_all();                                          // both CTAs' barriers are initialised before any remote arrive
+  if (warp == 10) tmem_alloc_pair(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  cluster_sync_all();
   const uint32_t tmem = *tmem_slot;
   const int F = p.F;
 
   if (warp < 8) {
-    // =============================================================== epilogue groups
+    // =============================================================== epilogue groups (both CTAs, own 128 rows)
     setmaxnreg_inc<224>();   // 256*224 + 128*56 = 64512 = the CTA register pool at launch (384 x 168)
     const int g = warp >> 2;                                     // group = TMEM stage = head quad
     const int row_in_tile = (warp & 3) * 32 + lane;
@@ -96,17 +116,12 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
     uint8_t* stg = stg_all + warp * 4096;
     uint32_t s_cnt = 0;                                          // items consumed on my stage
     uint32_t it = 0;                                             // tile iteration
-    AXVS_PROF_DECL(7)
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+    for (int pt = pair; pt < pair_tiles; pt += npairs, ++it) {
+      const int tile = 2 * pt + (int)rank;                       // may be == p.tiles (odd tile count): every row masked
       // ---- q2 of my 4 heads: (acc + bias) * scale*log2e -> bf16 pairs in Q2P; the stage is then free for the frame chunks
-      const bool trc_ = it == 3 && lane == 0 && (warp & 3) == 0;
-      const int tb_ = 100 + 100 * g;
-      AXVS_TRACE(trc_, tb_ + 0)
-      AXVS_PROF_WAIT(0, mbar_wait(&s_full[g], s_cnt & 1))
-      AXVS_TRACE(trc_, tb_ + 1)
+      mbar_wait_cluster(&s_full[g], s_cnt & 1);
       ++s_cnt;
       tc_fence_after();
-      AXVS_PROF_MARK(tq2_)
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         float v[32];
@@ -121,9 +136,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[g]);
-      AXVS_TRACE(trc_, tb_ + 2)
-      AXVS_PROF_SPAN(3, tq2_)
+      if (lane == 0) mbar_arrive_cluster_relaxed(&s_empty[g], 0);
 
       float m_run[4], l_run[4], o[4][32];
 #pragma unroll
@@ -137,12 +150,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
       for (int f = 0; f < F; ++f) {
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
-          AXVS_TRACE(trc_, tb_ + 10 + 4 * (2 * f + cc))
-          AXVS_PROF_WAIT(1, mbar_wait(&s_full[g], s_cnt & 1))
-          AXVS_TRACE(trc_, tb_ + 11 + 4 * (2 * f + cc))
+          mbar_wait_cluster(&s_full[g], s_cnt & 1);
           ++s_cnt;
           tc_fence_after();
-          AXVS_PROF_MARK(tch_)
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             // two TMEM round trips per head: (k2, q2) then v2, the v2 load issued before the logit arithmetic
@@ -168,9 +178,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
             if (hh == 1) {                                       // both heads of the chunk are in registers
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&s_empty[g]);
-              AXVS_PROF_SPAN(4, tch_)
-              AXVS_TRACE(trc_, tb_ + 12 + 4 * (2 * f + cc))
+              if (lane == 0) mbar_arrive_cluster_relaxed(&s_empty[g], 0);
             }
             const float2 pe2 = make_float2(pe, pe), corr2 = make_float2(corr, corr);
 #pragma unroll
@@ -180,12 +188,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
               o[lh][2 * i + 1] = r.y;
             }
           }
-          AXVS_TRACE(trc_, tb_ + 13 + 4 * (2 * f + cc))
         }
       }
       // ---- o = o / l + bv2 -> bf16 pairs over my (now dead) q2 columns: the tensor-memory A operand of the output projection
-      AXVS_PROF_MARK(to_)
-      AXVS_TRACE(trc_, tb_ + 40)
 #pragma unroll
       for (int lh = 0; lh < 4; ++lh) {
         const float inv = 1.f / l_run[lh];
@@ -196,20 +201,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
           pk[i] = pack_bf16x2(fmaf(o[lh][2 * i], inv, sb_v2[col0 + 2 * i]), fmaf(o[lh][2 * i + 1], inv, sb_v2[col0 + 2 * i + 1]));
         tmem_st16u(t_qp + 16 * lh, pk);
       }
-      AXVS_PROF_SPAN(6, to_)
-      AXVS_PROF_MARK(to2_)
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(o_ready);
-      AXVS_TRACE(trc_, tb_ + 41)
+      if (lane == 0) mbar_arrive_cluster_relaxed(o_ready, 0);
       // The residual loads below fill the load/store queue for ~2k clk; issued while the OTHER group still reads its bias from shared
       // memory for o (same queue) they delayed its o_ready arrive -- the start of GEMM 3 -- by that much.  So: wait until both groups
       // have handed o over (the loads then overlap GEMM 3 instead of the hand-off).
-#if TT_OWAIT
-      mbar_wait(o_ready, it & 1);
-#endif
-      AXVS_PROF_SPAN(5, to2_)
       // ---- output projection item on my stage: out = resid + acc + bproj (my 128 output columns).
       // TMEM rows are one-per-thread; a 4 KiB per-warp transpose through shared memory turns the global accesses into full
       // 128-byte row segments.  resid + bias are fetched BEFORE waiting for the accumulator (latency hides behind GEMM 3).
@@ -232,9 +230,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
             rr[j][i] = make_float4(x.x + bb.x, x.y + bb.y, x.z + bb.z, x.w + bb.w);
           }
         }
-        AXVS_TRACE(trc_, tb_ + 42)
-        AXVS_PROF_WAIT(2, mbar_wait(&s_full[g], s_cnt & 1))
-        AXVS_TRACE(trc_, tb_ + 43)
+        mbar_wait_cluster(&s_full[g], s_cnt & 1);
         ++s_cnt;
         tc_fence_after();
         if (p.ln_g == nullptr) {
@@ -247,8 +243,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
               if (j == 3) {                                        // accumulator fully read: the stage is free for the next tile
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[g]);
-                AXVS_TRACE(trc_, tb_ + 44)
+                if (lane == 0) mbar_arrive_cluster_relaxed(&s_empty[g], 0);
               }
 #pragma unroll
               for (int c = 0; c < 8; ++c)
@@ -281,8 +276,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
               if (j == 3) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[g]);
-                AXVS_TRACE(trc_, tb_ + 44)
+                if (lane == 0) mbar_arrive_cluster_relaxed(&s_empty[g], 0);
               }
 #pragma unroll
               for (int c = 0; c < 8; ++c)
@@ -348,37 +342,38 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
           // (no second barrier: my next write to this staging area is the next tile's projection transpose, which cannot start before
           //  the partner warp has arrived on o_ready for that tile -- i.e. long after it has read these statistics)
         }
-        AXVS_TRACE(trc_, tb_ + 45)
       }
     }
-    AXVS_PROF_FLUSH(8 + 8 * g, 7, (warp & 3) == 0 && lane == 0)
   } else {
     setmaxnreg_dec<56>();
     if (warp == 8 && lane == 0) {
-      // =============================================================== A-tile producer (x_diag, x_0 .. x_{F-1})
-      uint32_t cnt = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      // =============================================================== A-tile producer (own tile: x_diag, x_0 .. x_{F-1})
+      uint32_t slot = 0, phase = 0;
+      for (int pt = pair; pt < pair_tiles; pt += npairs) {
+        int tile = 2 * pt + (int)rank;
+        if (tile >= p.tiles) tile = p.tiles - 1;                 // dummy tile of an odd count: load something valid
 #pragma unroll 1
-        for (int item = 0; item < 4 * (F + 1); ++item, ++cnt) {
-          const uint32_t slot = cnt % TT_A_SLOTS, phase = (cnt / TT_A_SLOTS) & 1;
+        for (int item = 0; item < 4 * (F + 1); ++item) {
           const uint8_t* src = (item < 4) ? p.xd_img + ((size_t)tile * 4 + item) * TF_KB
                                           : p.x_img + (((size_t)((item >> 2) - 1) * p.tiles + tile) * 4 + (item & 3)) * TF_KB;
-          mbar_wait(&a_empty[slot], phase ^ 1);
+          mbar_wait_cluster(&a_empty[slot], phase ^ 1);
           mbar_arrive_expect_tx(&a_full[slot], TF_KB);
           tma_bulk_g2s(a_ring + slot * TF_KB, src, TF_KB, &a_full[slot]);
+          if (++slot == TP_A_SLOTS) { slot = 0; phase ^= 1; }
         }
       }
     } else if (warp == 9 && lane == 0) {
-      // =============================================================== weight producer (32 KiB units)
+      // =============================================================== weight producer: my half (64 rows) of every unit
       uint32_t slot = 0, phase = 0;
-      AXVS_PROF_DECL(1)
       auto push = [&](const uint8_t* img, int unit) {
-        AXVS_PROF_WAIT(0, mbar_wait(&w_empty[slot], phase ^ 1))
-        mbar_arrive_expect_tx(&w_full[slot], TF_WU);
-        tma_bulk_g2s(w_ring + slot * TF_WU, img + (size_t)unit * TF_WU, TF_WU, &w_full[slot]);
-        if (++slot == TT_W_SLOTS) { slot = 0; phase ^= 1; }
+        mbar_wait_cluster(&w_empty[slot], phase ^ 1);
+        mbar_arrive_expect_tx(&w_full[slot], TP_WH);
+        const uint8_t* src = img + (size_t)unit * TF_WU + rank * 64 * 128;
+        tma_bulk_g2s(w_ring + slot * TP_WH, src, 8192, &w_full[slot]);
+        tma_bulk_g2s(w_ring + slot * TP_WH + 8192, src + TF_KB, 8192, &w_full[slot]);
+        if (++slot == TP_W_SLOTS) { slot = 0; phase ^= 1; }
       };
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      for (int pt = pair; pt < pair_tiles; pt += npairs) {
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) push(p.w_pq, u);               // (half, kg) = (u >> 1, u & 1)
 #pragma unroll 1
@@ -390,145 +385,119 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) push(p.w_proj, u);
       }
-      AXVS_PROF_FLUSH(32, 1, true)
+    } else if (warp == 10 && rank != 0) {
+      // =============================================================== relay (non-leader): forward my full barriers to the leader,
+      // in the order the leader consumes them
+      if (lane == 0) {
+        uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0;
+        auto fwd_a = [&]() {
+#pragma unroll 1
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait_cluster(&a_full[a_slot], a_phase);
+            mbar_arrive_cluster_relaxed(&a_full[a_slot], 0);
+            if (++a_slot == TP_A_SLOTS) { a_slot = 0; a_phase ^= 1; }
+          }
+        };
+        auto fwd_w = [&](int n) {
+#pragma unroll 1
+          for (int i = 0; i < n; ++i) {
+            mbar_wait_cluster(&w_full[w_slot], w_phase);
+            mbar_arrive_cluster_relaxed(&w_full[w_slot], 0);
+            if (++w_slot == TP_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
+          }
+        };
+        for (int pt = pair; pt < pair_tiles; pt += npairs) {
+          fwd_a();
+          fwd_w(4);
+#pragma unroll 1
+          for (int f = 0; f < F; ++f) { fwd_a(); fwd_w(8); }
+          fwd_w(4);
+        }
+      }
     } else if (warp == 10) {
-      // =============================================================== tcgen05.cp + MMA issuer
-      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      // =============================================================== tcgen05.cp + MMA issuer (leader CTA; converged warp, elected lane)
+      const uint32_t idesc = umma_idesc_bf16(256, 128);
       const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring);
       const uint32_t t_xa = tmem + 128, t_qp = tmem;
-      uint32_t a_cnt = 0, w_slot = 0, w_phase = 0, s_cnt0 = 0, s_cnt1 = 0, it = 0;
-      AXVS_PROF_DECL(7)
+      uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0, s_cnt0 = 0, s_cnt1 = 0, it = 0;
       auto w_wait = [&]() -> uint32_t {
-        AXVS_PROF_WAIT(0, mbar_wait(&w_full[w_slot], w_phase))
+        mbar_wait_cluster(&w_full[w_slot], w_phase);
         tc_fence_after();
         const uint32_t ws = w_slot;
-        if (++w_slot == TT_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
+        if (++w_slot == TP_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
         return ws;
       };
       auto stage_wait = [&](int g) {
         const uint32_t sc = g ? s_cnt1 : s_cnt0;
-        AXVS_PROF_WAIT(1, mbar_wait(&s_empty[g], (sc & 1) ^ 1))
+        mbar_wait_cluster(&s_empty[g], (sc & 1) ^ 1);
         if (g) ++s_cnt1; else ++s_cnt0;
       };
-      // the next A tile (4 K-block images) -> XA; ordered by the tensor pipe behind the UMMAs still reading the old tile
+      // the next A tile of BOTH CTAs (4 K-block images each) -> XA; ordered by the tensor pipe behind the UMMAs still reading the old tile
       auto copy_tile = [&]() {
 #pragma unroll 1
-        for (int kb = 0; kb < 4; ++kb, ++a_cnt) {
-          const uint32_t slot = a_cnt % TT_A_SLOTS;
-          AXVS_PROF_WAIT(2, mbar_wait(&a_full[slot], (a_cnt / TT_A_SLOTS) & 1))
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait_cluster(&a_full[a_slot], a_phase);
           tc_fence_after();
           if (elect_one()) {
-            tmem_cp_kblock(t_xa + 32 * kb, a_ring_addr + slot * TF_KB);
-            umma_commit(&a_empty[slot]);
+            tmem_cp_kblock_pair(t_xa + 32 * kb, a_ring_addr + a_slot * TF_KB);
+            umma_commit_pair(&a_empty[a_slot]);
           }
           __syncwarp();
+          if (++a_slot == TP_A_SLOTS) { a_slot = 0; a_phase ^= 1; }
         }
       };
-#if TT_HOIST
-      if ((int)blockIdx.x < p.tiles) copy_tile();               // x_diag of the first tile
-#endif
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        // ---- GEMM 1: q2 halves -> the two stages (free once the previous tile's projection has been drained); x_diag is already in XA
-        const bool trc_ = it == 3 && lane == 0;
-        AXVS_PROF_MARK(tg1_)
-        AXVS_TRACE(trc_, 0)
-#if TT_PREFETCH
-        if (lane == 0) *tile_flag = it + 1;
-#endif
-#if !TT_HOIST
+      for (int pt = pair; pt < pair_tiles; pt += npairs, ++it) {
+        // ---- GEMM 1: q2 halves -> the two stages (free once the previous tile's projection has been drained in both CTAs)
         copy_tile();
-#endif
         stage_wait(0);
         stage_wait(1);
         tc_fence_after();
-        AXVS_TRACE(trc_, 1)
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) {
           const int half = u >> 1, kg = u & 1;
           const uint32_t ws = w_wait();
-          umma_unit_elect_ts(tmem + 256 + half * 128, t_xa + 64 * kg, t_xa + 64 * kg + 32, w_ring_addr + ws * TF_WU, idesc, kg != 0,
-                             &w_empty[ws], kg == 1 ? &s_full[half] : nullptr, nullptr);
+          umma_unit_elect_ts_pair(tmem + 256 + half * 128, t_xa + 64 * kg, t_xa + 64 * kg + 32, w_ring_addr + ws * TP_WH, idesc, kg != 0,
+                                  &w_empty[ws], kg == 1 ? &s_full[half] : nullptr);
         }
-        AXVS_PROF_SPAN(6, tg1_)
-        AXVS_TRACE(trc_, 2)
-        AXVS_PROF_MARK(tfr_)
         // ---- GEMM 2: per frame, four 128-column chunks alternating between the two TMEM stages
 #pragma unroll 1
         for (int f = 0; f < F; ++f) {
-          AXVS_TRACE(trc_, 60 + 2 * f)
           copy_tile();
-          AXVS_TRACE(trc_, 61 + 2 * f)
 #pragma unroll 1
           for (int ci = 0; ci < 4; ++ci) {
             const int g = ci & 1;                               // chunk order 0,2,1,3 -> stage 0,1,0,1
-            AXVS_TRACE(trc_, 10 + 4 * (4 * f + ci))
             stage_wait(g);
             tc_fence_after();
-            AXVS_TRACE(trc_, 11 + 4 * (4 * f + ci))
 #pragma unroll 1
             for (int kg = 0; kg < 2; ++kg) {
               const uint32_t ws = w_wait();
-              umma_unit_elect_ts(tmem + 256 + g * 128, t_xa + 64 * kg, t_xa + 64 * kg + 32, w_ring_addr + ws * TF_WU, idesc, kg != 0,
-                                 &w_empty[ws], kg == 1 ? &s_full[g] : nullptr, nullptr);
-              AXVS_TRACE(trc_, 12 + kg + 4 * (4 * f + ci))
+              umma_unit_elect_ts_pair(tmem + 256 + g * 128, t_xa + 64 * kg, t_xa + 64 * kg + 32, w_ring_addr + ws * TP_WH, idesc, kg != 0,
+                                      &w_empty[ws], kg == 1 ? &s_full[g] : nullptr);
             }
           }
         }
-        AXVS_PROF_SPAN(5, tfr_)
-        // XA is dead once the last frame's UMMAs have run (tensor pipe order): the NEXT tile's x_diag goes in now, under the o hand-off
-#if TT_HOIST
-        if (tile + (int)gridDim.x < p.tiles) copy_tile();
-#endif
-        AXVS_TRACE(trc_, 3)
-        // ---- GEMM 3: output projection, A = o (bf16 pairs written over q2 by the epilogue), accumulators = both stages
-        AXVS_TRACE(trc_, 50)
-        AXVS_PROF_WAIT(3, mbar_wait(o_ready, it & 1))
-        AXVS_TRACE(trc_, 51)
+        // ---- GEMM 3: output projection, A = o (bf16 pairs written over q2 by both CTAs' epilogues), accumulators = both stages
+        mbar_wait_cluster(o_ready, it & 1);
         stage_wait(0);
         stage_wait(1);
         tc_fence_after();
-        AXVS_TRACE(trc_, 52)
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) {
           const int half = u >> 1, kg = u & 1;
           const uint32_t ws = w_wait();
-          umma_unit_elect_ts(tmem + 256 + half * 128, t_qp + 64 * kg, t_qp + 64 * kg + 32, w_ring_addr + ws * TF_WU, idesc, kg != 0,
-                             &w_empty[ws], kg == 1 ? &s_full[half] : nullptr, nullptr);
-        }
-        AXVS_TRACE(trc_, 53)
-      }
-      AXVS_PROF_FLUSH(0, 7, lane == 0)
-    }
-#if TT_PREFETCH
-    else if (warp == 11 && p.resid != nullptr) {
-      // =============================================================== residual prefetcher: the epilogue reads 128 fp32 rows (128 KiB) per tile
-      // right before GEMM 3 and then waits for them; pulling the lines into L2 while the tile's frames are still being computed turns a
-      // DRAM round trip on the tile's critical path into an L2 hit (no registers or shared memory needed)
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        while (*tile_flag < it + 1) __nanosleep(200);
-#pragma unroll 1
-        for (int rr = lane; rr < 128; rr += 32) {
-          const int r = tile * 128 + rr;
-          if (r < p.rows) {
-            const char* src = reinterpret_cast<const char*>(p.resid + (size_t)pass_to_canonical(r, p.map_mode, p.dims) * 256);
-#pragma unroll
-            for (int l = 0; l < 8; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128 * l));
-          }
+          umma_unit_elect_ts_pair(tmem + 256 + half * 128, t_qp + 64 * kg, t_qp + 64 * kg + 32, w_ring_addr + ws * TP_WH, idesc, kg != 0,
+                                  &w_empty[ws], kg == 1 ? &s_full[half] : nullptr);
         }
       }
     }
-#endif
   }
 
   tc_fence_before();
   __syncthreads();
-#ifdef AXVS_WAIT_PROFILE
-  if (threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_trace[502] = gt; g_trace[503] = clock64(); }
-#endif
+  cluster_sync_all();
   if (warp == 10) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc_pair(tmem, 512);
   }
 }
 

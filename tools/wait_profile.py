@@ -1,6 +1,6 @@
 """Debug: run one fused kernel on a libaxvs build with -DAXVS_WAIT_PROFILE and print the wait-cycle breakdown.
 usage: AXVS_LIB=axial_vs_b200/libaxvs_prof.so python tools/wait_profile.py [ffn|traj] [clips]"""
-import ctypes, sys, torch
+import ctypes, os, sys, torch
 sys.path.insert(0, ".")
 from axial_vs_b200 import _lib, ops, synth
 which = sys.argv[1] if len(sys.argv) > 1 else "ffn"
@@ -32,7 +32,7 @@ e0.record(); run(); e1.record(); torch.cuda.synchronize()
 lib.axvs_debug_read_waits(buf)
 v = list(buf)
 tiles = (rows + 127) // 128
-ctas = min(tiles, 148)
+ctas = min(tiles, int(os.environ.get('AXVS_DEBUG_SMS', 148)))
 if "--pair-ctas" in sys.argv:      # pair kernels: counters are flushed by the leader CTA of each pair only
     ctas = min((tiles + 1) // 2, 74)
     tiles = (tiles + 1) // 2
@@ -64,7 +64,7 @@ elif which == "qkv":
     show("qkv epilogue g0", 44, ["s_full"])
     show("qkv epilogue g1", 46, ["s_full"])
 else:
-    show("MMA warp", 0, ["w_full", "s_empty", "a_full", "o_ready", "pj_free"])
-    show("epilogue g0 warp0", 8, ["q2_full", "s_full(fr)", "s_full(pj)"])
-    show("epilogue g1 warp4", 16, ["q2_full", "s_full(fr)", "s_full(pj)"])
+    show("MMA warp", 0, ["w_full", "s_empty", "a_full", "o_ready", "pj_free", "[frames span]", "[gemm1 span]"])
+    show("epilogue g0 warp0", 8, ["q2_full", "s_full(fr)", "s_full(pj)", "[q2 drain]", "[chunk hold]", "[o st_wait]", "[o pack]"])
+    show("epilogue g1 warp4", 16, ["q2_full", "s_full(fr)", "s_full(pj)", "[q2 drain]", "[chunk hold]", "[o st_wait]", "[o pack]"])
     show("W producer", 32, ["w_empty"])
