@@ -15,6 +15,7 @@
 #include "traj_fused.cuh"
 #include "traj_ts.cuh"
 #include "traj_pair.cuh"
+#include "qkv_pair.cuh"
 #include "ffn_fused.cuh"
 #include "ffn_n256.cuh"
 #include "qkv_fused.cuh"
@@ -28,6 +29,7 @@
 #include "kmax_axial.cuh"
 #include "matching.cuh"
 #include "ffn_pair.cuh"
+#include "ffn_n256_pair.cuh"
 
 using namespace axvs;
 
@@ -54,7 +56,10 @@ const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel"
 // the per-device attribute table are guarded by mutexes.  None of them is touched on the launch path beyond one relaxed load.
 std::atomic<int> g_fusion{4};   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
 std::atomic<int> g_attn_core{1};   // 1 = tcgen05 attention core (attn_tc.cuh), 0 = the mma.sync kernels (validation baseline)
-std::atomic<int> g_pair{getenv("AXVS_PAIR") ? atoi(getenv("AXVS_PAIR")) : 0};   // CTA-pair (cta_group::2) FFN kernel: validated, but epilogue-bound and ~15 % slower end to end -> opt-in
+// CTA-pair (cta_group::2) kernels, bit mask: 2 = traj_pair_kernel, 4 = qkv_pair_kernel, 8 = ffn_n256_pair_kernel (default: all three; each is
+// bit-identical to its single-CTA kernel and 4-8 % faster because every CTA stages only half of each weight unit), 1 = the older
+// ffn_pair_kernel (128-column chunk schedule, slower than ffn_n256: validation only).  AXVS_PAIR overrides the default for A/B runs.
+std::atomic<int> g_pair{getenv("AXVS_PAIR") ? atoi(getenv("AXVS_PAIR")) : 14};
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
 struct Profiler {
@@ -138,6 +143,7 @@ int device_info(DeviceInfo** out) {
   if (!d.qkv_attr) {
     if (cudaFuncSetAttribute(qkv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QK_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QD_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(qkv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_attn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES) != cudaSuccess)
@@ -174,7 +180,8 @@ int device_info(DeviceInfo** out) {
     d.attn_tc_attr = true;
   }
   if (!d.pair_attr) {
-    if (cudaFuncSetAttribute(ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(ffn_n256_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SMEM_BYTES) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(ffn_pair) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.pair_attr = true;
   }
@@ -461,6 +468,10 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       if (use_tc) { qp.swz_N = N; qp.swz_n = n; }
       {
         ProfScope ps(KC_QKVD, 2.0 * rows * 256.0 * 768.0, (double)rows * ((pos ? (dims.pos_mod ? 1024.0 + 1024.0 / B : 2048.0) : 1024.0) + 1536.0), st);
+        if ((g_pair & 4) && tiles >= 2) {
+          const int pair_tiles = (tiles + 1) / 2, max_pairs = d->sms / 2;
+          qkv_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), QD_THREADS, QP_SMEM_BYTES, st>>>(qp);
+        } else
         qkv_direct_kernel<<<tiles < d->sms ? tiles : d->sms, QD_THREADS, QD_SMEM_BYTES, st>>>(qp);
       }
       AXVS_CHECK_LAUNCH("qkv_direct_kernel");
@@ -728,6 +739,10 @@ int ffn_fused_launch(const uint8_t* s_img, const float* s32, float* out, const a
       ffn_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), FF_THREADS, FP_SMEM_BYTES, st>>>(fp);
     } else if (g_fusion >= 4 && w->w_ffn1_n && w->d_ffn % 256 == 0) {
       fp.w1 = reinterpret_cast<const uint8_t*>(w->w_ffn1_n);       // N = 256 units
+      if ((g_pair & 8) && fp.tiles >= 2) {
+        const int pair_tiles = (fp.tiles + 1) / 2, max_pairs = d->sms / 2;
+        ffn_n256_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), FF_THREADS, FQ_SMEM_BYTES, st>>>(fp);
+      } else
       ffn_n256_kernel<<<fp.tiles < d->sms ? fp.tiles : d->sms, FF_THREADS, FF_SMEM_BYTES, st>>>(fp);
     } else {
       ffn_fused_kernel<<<fp.tiles < d->sms ? fp.tiles : d->sms, FF_THREADS, FF_SMEM_BYTES, st>>>(fp);

@@ -1,75 +1,58 @@
-// q | k | v projections reading the fp32 residual stream directly (fusion level 4): the tile-image pack kernel and its
-// 2 KiB/token round trip through HBM disappear.
-//
-//   A1 = bf16(src[c(row)] + pos[c(row)]),  A2 = bf16(src[c(row)])        c(row) = canonical token of pass-order row `row`
-//   [q | k] = A1 [Wq; Wk]^T + b,   v = A2 Wv^T + b                        (the reference's axis permutes, WC/temporal_attention.py:197,206,
-//                                                                          exist only as this index map)
-//
-// Eight converting producer warps read 256-byte row segments (half a warp per segment, one K-block of the lane's 8 rows per burst of
-// 16 loads), and write BOTH images of a K-block from the one src load into a 32 KiB "pair slot" (SWIZZLE_128B K-major).  The MMA
-// warp moves each image into TENSOR MEMORY with tcgen05.cp (columns [0,128) = A1, [128,256) = A2) and frees the slot at once,
-// so the shared-memory ring only decouples producers and tensor pipe -- the whole tile's A operand lives in TMEM, and the
-// N = 128 UMMAs read it from there at the full 64 clk rate (A in shared memory: ~90 clk, operand reads saturate the smem port).
-// Six 128-column chunks (q heads 0-3, 4-7, k, k, v, v) alternate between two TMEM accumulator stages; BOTH epilogue groups
-// drain every chunk (two heads each), which halves the time a stage stays occupied -- the issuer's stage waits would otherwise
-// delay the next tile's tcgen05.cp and stall the producers.  The epilogue adds the bias and writes bf16 HEAD-MAJOR
-// qkv[which][head][row][32]  through a per-warp transpose.
-//
-// Warp roles (576 threads, no setmaxnreg): warps 0-7 epilogue, 8-15 A producers, 16 weight TMA, 17 MMA / tcgen05.cp issuer.
+// CTA-pair (cta_group::2) version of qkv_direct_kernel (same math, layouts and epilogue; reference WC/temporal_attention.py:42-44 with the
+// layer's `src + pos` :200 and axis permutes :197,206 folded into the loads).  The leader CTA issues ONE stream of M = 256 instructions for
+// two adjacent 128-row tiles; each CTA stages half of every weight unit, which halves the shared-memory traffic of the GEMM core -- in the
+// single-CTA kernel that traffic (B reads + TMA refills = 128 B/clk) saturates the shared-memory port, and the converting producers' and
+// the epilogue's shared-memory accesses queue behind it (epilogue busy 85 % of the tile, issuer waiting 43 % for drained stages).
+// Protocol as in traj_pair.cuh: local full barriers forwarded to the leader by the non-leader's warp 17, multicast commits, remote
+// arrives for "stage drained".
 #pragma once
-#include "qkv_fused.cuh"
+#include "qkv_direct.cuh"
+#include "traj_pair.cuh"
 
 namespace axvs {
 
-constexpr int QD_THREADS = 576;
-constexpr int QD_PRODUCER_WARPS = 8;
-constexpr int QD_A_SLOTS = 3;                 // pair slots: [A1 K-block image | A2 K-block image] = 32 KiB
-constexpr int QD_SMEM_BYTES = QD_A_SLOTS * 2 * TF_KB + QK_W_SLOTS * TF_WU + QK_STAGE_BYTES + QK_BIAS_BYTES + 512;
-static_assert(QD_SMEM_BYTES <= 232448, "qkv_direct_kernel exceeds the 227 KiB shared-memory limit");
+constexpr int QP_W_SLOTS = 5;                   // half units
+constexpr int QP_WH = 16384;
+constexpr int QP_SMEM_BYTES = QD_A_SLOTS * 2 * TF_KB + QP_W_SLOTS * QP_WH + QK_STAGE_BYTES + QK_BIAS_BYTES + 512;
+static_assert(QP_SMEM_BYTES <= 232448, "qkv_pair_kernel exceeds the 227 KiB shared-memory limit");
 
-struct QkvDirectParams {
-  const float* src;        // fp32 [tokens, 256] canonical order: q = k input (before the positional term) and v input
-  const float* pos;        // fp32 [tokens, 256] or null
-  const uint8_t* w;        // unit format of [Wq; Wk; Wv]
-  const float* bias;       // [768]
-  __nv_bfloat16* qkv;      // head-major [3][8][rows][32]
-  int rows, tiles, map_mode;
-  AxialDims dims;
-  int swz_N, swz_n;        // > 0: "unit-major" output for the tcgen05 attention kernel (attn_tc.cuh) instead of head-major: one region of
-                           // 3 N rows per (sequence, head) -- Q rows, then K_f | V_f per key frame (N = swz_N tokens per sequence, n = swz_n per
-                           // frame) -- with the 16-byte chunks of the row at region position pos permuted by (pos >> 1) & 3
-};
-
-__global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDirectParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_pair_kernel(const QkvDirectParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* a_ring = smem;
   uint8_t* w_ring = a_ring + QD_A_SLOTS * 2 * TF_KB;
-  uint8_t* stage_all = w_ring + QK_W_SLOTS * TF_WU;
+  uint8_t* stage_all = w_ring + QP_W_SLOTS * QP_WH;
   float* sbias = reinterpret_cast<float*>(stage_all + QK_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 768);
   uint64_t* a_full = bars;                      // [QD_A_SLOTS], one arrive per producer warp
   uint64_t* a_empty = a_full + QD_A_SLOTS;      // tcgen05.commit after the slot's copies
-  uint64_t* w_full = a_empty + QD_A_SLOTS;      // [QK_W_SLOTS]
-  uint64_t* w_empty = w_full + QK_W_SLOTS;
-  uint64_t* s_full = w_empty + QK_W_SLOTS;      // [2] accumulator stage of group g complete
+  uint64_t* w_full = a_empty + QD_A_SLOTS;      // [QP_W_SLOTS]
+  uint64_t* w_empty = w_full + QP_W_SLOTS;
+  uint64_t* s_full = w_empty + QP_W_SLOTS;      // [2] accumulator stage of group g complete
   uint64_t* s_empty = s_full + 2;               // [2] drained by the 4 warps of group g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int pair_tiles = (p.tiles + 1) >> 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < QD_A_SLOTS; ++i) { mbar_init(&a_full[i], QD_PRODUCER_WARPS); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < QK_W_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
+    const uint32_t extra = rank == 0 ? 1 : 0;                 // leader: + the peer's relay
+    for (int i = 0; i < QD_A_SLOTS; ++i) { mbar_init(&a_full[i], QD_PRODUCER_WARPS + extra); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < QP_W_SLOTS; ++i) { mbar_init(&w_full[i], 1 + extra); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 16); }   // s_empty: the leader's copy is live (8 warps x 2 CTAs)
     fence_barrier_init();
   }
-  if (warp == 17) tmem_alloc(tmem_slot, 512);
   for (int i = threadIdx.x; i < 768; i += QD_THREADS) sbias[i] = p.bias[i];
+  __syncthreads();
+  cluster_sync_all();                                          // both CTAs' barriers are initialised before any remote arrive
+  if (warp == 17) tmem_alloc_pair(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  cluster_sync_all();
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 8) {
@@ -78,8 +61,8 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint8_t* stg = stage_all + warp * 2048;
     uint32_t cnt = 0;                                          // chunks consumed (stage = cnt & 1)
-    AXVS_PROF_DECL(1)
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    for (int pt = pair; pt < pair_tiles; pt += npairs) {
+      const int tile = 2 * pt + (int)rank;                     // may be == p.tiles (odd tile count): every row masked
       const int row0 = tile * 128 + (warp & 3) * 32;           // first row of this warp
       uint32_t um_q = 0, um_k = 0, pos_q = 0, pos_k = 0;       // unit-major: rows of q / k of row (row0 + lane) for head 0 (v = k + n), positions inside the region
       if (p.swz_N > 0) {
@@ -94,7 +77,7 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
 #pragma unroll 1
       for (int rt = 0; rt < 6; ++rt, ++cnt) {
         const int st = cnt & 1;                                // 6 chunks per tile: even, so st == rt & 1
-        AXVS_PROF_WAIT(0, mbar_wait(&s_full[st], (cnt >> 1) & 1))
+        mbar_wait_cluster(&s_full[st], (cnt >> 1) & 1);
         tc_fence_after();
         const uint32_t t_s = tmem + lane_base + 256 + st * 128;
 #pragma unroll
@@ -106,7 +89,7 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
           if (cc == 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[st]);
+            if (lane == 0) mbar_arrive_cluster_relaxed(&s_empty[st], 0);
           }
           // bias + bf16, then a 2 KiB per-warp transpose so every store instruction writes 512 contiguous bytes
           {
@@ -153,7 +136,6 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
         }
       }
     }
-    AXVS_PROF_FLUSH(44 + 2 * g, 1, (warp & 3) == 0 && lane == 0)
   } else if (warp < 8 + QD_PRODUCER_WARPS) {
     // =============================================================== converting A producers
     // Work unit = one K-block of the lane's 8 rows: a BURST of 8 src + 8 pos loads, then convert + store all of them.  (The first version
@@ -164,10 +146,10 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
     const int pw = warp - 8;
     const int half = lane >> 4, c16 = lane & 15;               // row of the pair, 16-byte piece (4 channels) of the 256-byte segment
     uint32_t cnt = 0;
-    AXVS_PROF_DECL(2)
     float4 sv[8], qv[8];
     uint32_t crow[8];                                          // canonical token of this lane's 8 rows (0xFFFFFFFF = past the end)
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    for (int pt = pair; pt < pair_tiles; pt += npairs) {
+      const int tile = 2 * pt + (int)rank;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int pr = tile * 128 + pw * 16 + 2 * j + half;
@@ -192,7 +174,7 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
           for (int j = 0; j < 8; ++j) qv[j] = z;
         }
         const uint32_t slot = cnt % QD_A_SLOTS, phase = (cnt / QD_A_SLOTS) & 1;
-        AXVS_PROF_WAIT(0, mbar_wait(&a_empty[slot], phase ^ 1))
+        mbar_wait_cluster(&a_empty[slot], phase ^ 1);
         uint8_t* dst = a_ring + slot * 2 * TF_KB;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -211,38 +193,58 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
         if (lane == 0) mbar_arrive(&a_full[slot]);
       }
     }
-    AXVS_PROF_FLUSH(48, 2, pw == 0 && lane == 0)
   } else if (warp == 16 && lane == 0) {
-    // =============================================================== weight producer (12 units per tile)
+    // =============================================================== weight producer: my half (64 rows) of each of the 12 units per tile
     uint32_t slot = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    for (int pt = pair; pt < pair_tiles; pt += npairs) {
 #pragma unroll 1
       for (int u = 0; u < 12; ++u) {
-        mbar_wait(&w_empty[slot], phase ^ 1);
-        mbar_arrive_expect_tx(&w_full[slot], TF_WU);
-        tma_bulk_g2s(w_ring + slot * TF_WU, p.w + (size_t)u * TF_WU, TF_WU, &w_full[slot]);
-        if (++slot == QK_W_SLOTS) { slot = 0; phase ^= 1; }
+        mbar_wait_cluster(&w_empty[slot], phase ^ 1);
+        mbar_arrive_expect_tx(&w_full[slot], QP_WH);
+        const uint8_t* src = p.w + (size_t)u * TF_WU + rank * 64 * 128;
+        tma_bulk_g2s(w_ring + slot * QP_WH, src, 8192, &w_full[slot]);
+        tma_bulk_g2s(w_ring + slot * QP_WH + 8192, src + TF_KB, 8192, &w_full[slot]);
+        if (++slot == QP_W_SLOTS) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 17 && rank != 0) {
+    // =============================================================== relay (non-leader): forward my full barriers to the leader in
+    // the order the leader consumes them
+    if (lane == 0) {
+      uint32_t a_cnt = 0, w_slot = 0, w_phase = 0;
+      for (int pt = pair; pt < pair_tiles; pt += npairs) {
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb, ++a_cnt) {
+          const uint32_t slot = a_cnt % QD_A_SLOTS;
+          mbar_wait_cluster(&a_full[slot], (a_cnt / QD_A_SLOTS) & 1);
+          mbar_arrive_cluster(&a_full[slot], 0);               // release: my producers' generic-proxy writes were fenced before their arrive
+        }
+#pragma unroll 1
+        for (int u = 0; u < 12; ++u) {
+          mbar_wait_cluster(&w_full[w_slot], w_phase);
+          mbar_arrive_cluster_relaxed(&w_full[w_slot], 0);
+          if (++w_slot == QP_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
+        }
       }
     }
   } else if (warp == 17) {
-    // =============================================================== tcgen05.cp + MMA issuer (converged warp, elected lane)
-    const uint32_t idesc = umma_idesc_bf16(128, 128);
+    // =============================================================== tcgen05.cp + MMA issuer (leader CTA; converged warp, elected lane)
+    const uint32_t idesc = umma_idesc_bf16(256, 128);
     const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring);
     uint32_t a_cnt = 0, w_slot = 0, w_phase = 0, ccnt = 0;     // ccnt: chunks issued
-    AXVS_PROF_DECL(3)
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-      // the tile's A operand: four pair slots -> TMEM.  These copies are ordered by the tensor pipe behind every UMMA of the
+    for (int pt = pair; pt < pair_tiles; pt += npairs) {
+      // both CTAs' A operands: four pair slots each -> TMEM.  These copies are ordered by the tensor pipe behind every UMMA of the
       // previous tile (issued earlier by this thread), which still reads the old contents.
 #pragma unroll 1
       for (int kb = 0; kb < 4; ++kb, ++a_cnt) {
         const uint32_t slot = a_cnt % QD_A_SLOTS;
-        AXVS_PROF_WAIT(2, mbar_wait(&a_full[slot], (a_cnt / QD_A_SLOTS) & 1))
+        mbar_wait_cluster(&a_full[slot], (a_cnt / QD_A_SLOTS) & 1);
         tc_fence_after();
         const uint32_t sa = a_ring_addr + slot * 2 * TF_KB;
         if (elect_one()) {
-          tmem_cp_kblock(tmem + 32 * kb, sa);
-          tmem_cp_kblock(tmem + 128 + 32 * kb, sa + TF_KB);
-          umma_commit(&a_empty[slot]);
+          tmem_cp_kblock_pair(tmem + 32 * kb, sa);
+          tmem_cp_kblock_pair(tmem + 128 + 32 * kb, sa + TF_KB);
+          umma_commit_pair(&a_empty[slot]);
         }
         __syncwarp();
       }
@@ -250,28 +252,28 @@ __global__ void __launch_bounds__(QD_THREADS, 1) qkv_direct_kernel(const QkvDire
       for (int rt = 0; rt < 6; ++rt, ++ccnt) {
         const int g = rt & 1;
         const uint32_t gc = ccnt >> 1;                         // chunks already issued to group g (6 per tile: even count)
-        AXVS_PROF_WAIT(1, mbar_wait(&s_empty[g], (gc & 1) ^ 1))
+        mbar_wait_cluster(&s_empty[g], (gc & 1) ^ 1);
         tc_fence_after();
         const uint32_t t_a = tmem + (rt < 4 ? 0 : 128);        // A1 for the q / k chunks, A2 for the v chunks
 #pragma unroll 1
         for (int kg = 0; kg < 2; ++kg) {
-          AXVS_PROF_WAIT(0, mbar_wait(&w_full[w_slot], w_phase))
+          mbar_wait_cluster(&w_full[w_slot], w_phase);
           tc_fence_after();
           const uint32_t ws = w_slot;
-          if (++w_slot == QK_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
-          umma_unit_elect_ts(tmem + 256 + g * 128, t_a + 64 * kg, t_a + 64 * kg + 32, w_ring_addr + ws * TF_WU, idesc, kg != 0,
-                             &w_empty[ws], kg == 1 ? &s_full[g] : nullptr, nullptr);
+          if (++w_slot == QP_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
+          umma_unit_elect_ts_pair(tmem + 256 + g * 128, t_a + 64 * kg, t_a + 64 * kg + 32, w_ring_addr + ws * QP_WH, idesc, kg != 0,
+                                  &w_empty[ws], kg == 1 ? &s_full[g] : nullptr);
         }
       }
     }
-    AXVS_PROF_FLUSH(40, 3, lane == 0)
   }
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   if (warp == 17) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc_pair(tmem, 512);
   }
 }
 

@@ -118,8 +118,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
     uint32_t it = 0;                                             // tile iteration
     for (int pt = pair; pt < pair_tiles; pt += npairs, ++it) {
       const int tile = 2 * pt + (int)rank;                       // may be == p.tiles (odd tile count): every row masked
+      const bool trc_ = it == 3 && lane == 0 && (warp & 3) == 0 && pair == 0;
+      const int tb_ = 100 + 100 * g + 200 * (int)rank;
+      AXVS_TRACE(trc_, tb_ + 0)
       // ---- q2 of my 4 heads: (acc + bias) * scale*log2e -> bf16 pairs in Q2P; the stage is then free for the frame chunks
       mbar_wait_cluster(&s_full[g], s_cnt & 1);
+      AXVS_TRACE(trc_, tb_ + 1)
       ++s_cnt;
       tc_fence_after();
 #pragma unroll 1
@@ -137,6 +141,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&s_empty[g], 0);
+      AXVS_TRACE(trc_, tb_ + 2)
 
       float m_run[4], l_run[4], o[4][32];
 #pragma unroll
@@ -150,7 +155,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
       for (int f = 0; f < F; ++f) {
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
+          AXVS_TRACE(trc_, tb_ + 10 + 4 * (2 * f + cc))
           mbar_wait_cluster(&s_full[g], s_cnt & 1);
+          AXVS_TRACE(trc_, tb_ + 11 + 4 * (2 * f + cc))
           ++s_cnt;
           tc_fence_after();
 #pragma unroll
@@ -179,6 +186,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive_cluster_relaxed(&s_empty[g], 0);
+              AXVS_TRACE(trc_, tb_ + 12 + 4 * (2 * f + cc))
             }
             const float2 pe2 = make_float2(pe, pe), corr2 = make_float2(corr, corr);
 #pragma unroll
@@ -205,6 +213,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(o_ready, 0);
+      AXVS_TRACE(trc_, tb_ + 41)
       // The residual loads below fill the load/store queue for ~2k clk; issued while the OTHER group still reads its bias from shared
       // memory for o (same queue) they delayed its o_ready arrive -- the start of GEMM 3 -- by that much.  So: wait until both groups
       // have handed o over (the loads then overlap GEMM 3 instead of the hand-off).
@@ -230,7 +239,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
             rr[j][i] = make_float4(x.x + bb.x, x.y + bb.y, x.z + bb.z, x.w + bb.w);
           }
         }
+        AXVS_TRACE(trc_, tb_ + 42)
         mbar_wait_cluster(&s_full[g], s_cnt & 1);
+        AXVS_TRACE(trc_, tb_ + 43)
         ++s_cnt;
         tc_fence_after();
         if (p.ln_g == nullptr) {
@@ -244,6 +255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster_relaxed(&s_empty[g], 0);
+                AXVS_TRACE(trc_, tb_ + 44)
               }
 #pragma unroll
               for (int c = 0; c < 8; ++c)
@@ -277,6 +289,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster_relaxed(&s_empty[g], 0);
+                AXVS_TRACE(trc_, tb_ + 44)
               }
 #pragma unroll
               for (int c = 0; c < 8; ++c)
@@ -342,6 +355,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
           // (no second barrier: my next write to this staging area is the next tile's projection transpose, which cannot start before
           //  the partner warp has arrived on o_ready for that tile -- i.e. long after it has read these statistics)
         }
+        AXVS_TRACE(trc_, tb_ + 45)
       }
     }
   } else {
@@ -448,10 +462,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
       };
       for (int pt = pair; pt < pair_tiles; pt += npairs, ++it) {
         // ---- GEMM 1: q2 halves -> the two stages (free once the previous tile's projection has been drained in both CTAs)
+        const bool trc_ = it == 3 && lane == 0 && pair == 0;
+        AXVS_TRACE(trc_, 0)
         copy_tile();
+        AXVS_TRACE(trc_, 3)
         stage_wait(0);
         stage_wait(1);
         tc_fence_after();
+        AXVS_TRACE(trc_, 1)
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) {
           const int half = u >> 1, kg = u & 1;
@@ -459,28 +477,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
           umma_unit_elect_ts_pair(tmem + 256 + half * 128, t_xa + 64 * kg, t_xa + 64 * kg + 32, w_ring_addr + ws * TP_WH, idesc, kg != 0,
                                   &w_empty[ws], kg == 1 ? &s_full[half] : nullptr);
         }
+        AXVS_TRACE(trc_, 2)
         // ---- GEMM 2: per frame, four 128-column chunks alternating between the two TMEM stages
 #pragma unroll 1
         for (int f = 0; f < F; ++f) {
+          AXVS_TRACE(trc_, 60 + 2 * f)
           copy_tile();
+          AXVS_TRACE(trc_, 61 + 2 * f)
 #pragma unroll 1
           for (int ci = 0; ci < 4; ++ci) {
             const int g = ci & 1;                               // chunk order 0,2,1,3 -> stage 0,1,0,1
+            AXVS_TRACE(trc_, 10 + 4 * (4 * f + ci))
             stage_wait(g);
             tc_fence_after();
+            AXVS_TRACE(trc_, 11 + 4 * (4 * f + ci))
 #pragma unroll 1
             for (int kg = 0; kg < 2; ++kg) {
               const uint32_t ws = w_wait();
               umma_unit_elect_ts_pair(tmem + 256 + g * 128, t_xa + 64 * kg, t_xa + 64 * kg + 32, w_ring_addr + ws * TP_WH, idesc, kg != 0,
                                       &w_empty[ws], kg == 1 ? &s_full[g] : nullptr);
+              AXVS_TRACE(trc_, 12 + kg + 4 * (4 * f + ci))
             }
           }
         }
         // ---- GEMM 3: output projection, A = o (bf16 pairs written over q2 by both CTAs' epilogues), accumulators = both stages
+        AXVS_TRACE(trc_, 50)
         mbar_wait_cluster(o_ready, it & 1);
+        AXVS_TRACE(trc_, 51)
         stage_wait(0);
         stage_wait(1);
         tc_fence_after();
+        AXVS_TRACE(trc_, 52)
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) {
           const int half = u >> 1, kg = u & 1;
@@ -488,6 +515,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
           umma_unit_elect_ts_pair(tmem + 256 + half * 128, t_qp + 64 * kg, t_qp + 64 * kg + 32, w_ring_addr + ws * TP_WH, idesc, kg != 0,
                                   &w_empty[ws], kg == 1 ? &s_full[half] : nullptr);
         }
+        AXVS_TRACE(trc_, 53)
       }
     }
   }

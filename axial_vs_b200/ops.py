@@ -381,9 +381,10 @@ def set_fusion(level: int) -> int:
     return _lib.load().axvs_set_fusion(int(level))
 
 
-def set_pair_mode(on: bool) -> int:
-    """Enable / disable the CTA-pair (cta_group::2) FFN kernel (default off); returns the previous setting."""
-    return _lib.load().axvs_set_pair_mode(int(on))
+def set_pair_mode(mask: int) -> int:
+    """CTA-pair (cta_group::2) kernels, bit mask: 2 = temporal kernel, 4 = q|k|v projection, 8 = FFN (default 14), 1 = the first pair FFN
+    (validation only); 0 = single-CTA kernels everywhere.  Returns the previous mask."""
+    return _lib.load().axvs_set_pair_mode(int(mask))
 
 
 def set_attn_core(core: int) -> int:

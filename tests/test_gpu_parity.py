@@ -612,8 +612,12 @@ def _forward_sharded_as_rank(m, cq_local, pf_local, n_clips, rank, world, gather
         dist.get_world_size, dist.get_rank, dist.is_initialized = orig_ws, orig_rk, orig_init
 
 
+PAIR_DEFAULT = 14      # traj_pair | qkv_pair | ffn_n256_pair (csrc/axvs.cu g_pair)
+
+
 def test_pair_mode_ffn_matches(ops, O):
-    """The cta_group::2 (CTA-pair) FFN kernel is opt-in; it must give the same result as the single-CTA kernel."""
+    """Both cta_group::2 (CTA-pair) FFN kernels -- the default 256-column-chunk one (bit 8) and the first, 128-column-chunk one (bit 1) --
+    against the single-CTA kernel (mask 0): same results, bit for bit."""
     p = synth.axial_layer_params(3)
     pk = ops.pack_layer({k: v.cuda() for k, v in p.items()})
     for rows in (100, 129, 5000):
@@ -621,14 +625,39 @@ def test_pair_mode_ffn_matches(ops, O):
         ref = O._ffn_tail(x, p)
         outs = []
         try:
-            for pair in (0, 1):
+            for pair in (0, 1, 8):
                 ops.set_pair_mode(pair)
                 outs.append(ops.ln_ffn_fwd(x.cuda(), pk))
                 torch.cuda.synchronize()
         finally:
-            ops.set_pair_mode(0)
-        assert nerr(outs[0], ref) < TOL and nerr(outs[1], ref) < TOL
-        assert torch.equal(outs[0], outs[1])
+            ops.set_pair_mode(PAIR_DEFAULT)
+        assert all(nerr(o_, ref) < TOL for o_ in outs)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("clips,T,H,W", [(1, 2, 41, 41), (3, 2, 21, 21), (2, 5, 15, 20), (1, 2, 5, 5), (9, 2, 21, 21)])
+def test_pair_kernels_bit_identical_to_single_cta(ops, clips, T, H, W):
+    """traj_pair_kernel, qkv_pair_kernel and ffn_n256_pair_kernel (tcgen05 cta_group::2, one M = 256 instruction stream per two tiles) run
+    the arithmetic of their single-CTA counterparts in the same order: a whole axial layer must agree bit for bit, for even and odd tile
+    counts (the odd tile's partner CTA works on a masked dummy tile), a single tile (falls back) and T = 5."""
+    from axial_vs_b200.modules import TemporalAxialTrajectoryAttentionLayer
+    layer = TemporalAxialTrajectoryAttentionLayer(256, 1024, 0.0, 0.0, "relu", 8).eval()
+    layer.load_state_dict(synth.axial_layer_params(11))
+    layer.cuda()
+    src = synth.randn(clips * 100 + H, clips * T, H * W, 256).cuda()
+    pos = synth.randn(clips * 100 + W + 1, clips, T, H, W, 256).cuda()
+    outs = {}
+    try:
+        with torch.no_grad():
+            for mask in (0, 2, 4, 8, PAIR_DEFAULT):
+                ops.set_pair_mode(mask)
+                outs[mask] = layer(src, pos)[0].clone()
+                torch.cuda.synchronize()
+    finally:
+        ops.set_pair_mode(PAIR_DEFAULT)
+    assert torch.isfinite(outs[0]).all()
+    for mask, y in outs.items():
+        assert torch.equal(y, outs[0]), f"pair mask {mask}"
 
 
 # --------------------------------------------------------------------------------------------- clip-level decoder attention (A11)

@@ -3,6 +3,8 @@ import ctypes, sys, torch
 sys.path.insert(0, ".")
 from axial_vs_b200 import _lib, ops, synth
 clips = int(sys.argv[1]) if len(sys.argv) > 1 else 42
+import os
+if os.environ.get('AXVS_PAIR'): print('pair mode', os.environ['AXVS_PAIR'], '(E0/E1 = leader CTA groups 0/1, E2/E3 = peer CTA)')
 ln = len(sys.argv) > 2 and sys.argv[2] == "w"
 lib = _lib.load()
 rows = clips * 2 * 41 * 41
@@ -23,7 +25,7 @@ for f in range(2):
         k = 4 * f + ci
         names[10 + 4 * k] = f"I chunk {k} (stage {ci & 1}) wait stage"; names[11 + 4 * k] = f"I chunk {k} stage free"
         names[12 + 4 * k] = f"I chunk {k} unit0 issued"; names[13 + 4 * k] = f"I chunk {k} unit1 issued"
-for g in range(2):
+for g in range(4):
     b = 100 + 100 * g
     names[b] = f"E{g} wait q2"; names[b + 1] = f"E{g} q2 full"; names[b + 2] = f"E{g} q2 drained/released"
     for j in range(4):
