@@ -30,6 +30,7 @@
 #include "matching.cuh"
 #include "ffn_pair.cuh"
 #include "ffn_n256_pair.cuh"
+#include "masked_mha.cuh"
 
 using namespace axvs;
 
@@ -46,12 +47,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_MATCH, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_MATCH, KC_MMHA, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel", "matching_kernels"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel", "matching_kernels", "masked_mha_kernels"};
 // Process-wide knobs are atomics (two host threads driving two devices may read / set them concurrently); the profiler's records and
 // the per-device attribute table are guarded by mutexes.  None of them is touched on the launch path beyond one relaxed load.
 std::atomic<int> g_fusion{4};   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
@@ -1096,6 +1097,50 @@ int axvs_query_self_attn(const float* q, const float* k, const float* v, const f
     query_self_attn_kernel<<<dim3(heads, N), 128, smem, (cudaStream_t)stream>>>(q, k, v, sim_affine, val_affine, out, heads, L);
   }
   AXVS_CHECK_LAUNCH("query_self_attn_kernel");
+  return AXVS_OK;
+}
+
+// ---- masked multi-head attention (Tube-Link decoder layer)
+static void masked_mha_plan(int B, int heads, int Nq, int L, int* splits, int* keys_per_cta, int* qblocks) {
+  *qblocks = (Nq + MM_THREADS - 1) / MM_THREADS;
+  const long long base = (long long)B * heads * *qblocks;
+  long long want = (4 * 148 + base - 1) / base;                   // about four waves of CTAs over the SMs
+  const int stages = (L + MM_KC - 1) / MM_KC;
+  if (want < 1) want = 1;
+  if (want > stages) want = stages;
+  const int per = (int)((stages + want - 1) / want) * MM_KC;
+  *keys_per_cta = per;
+  *splits = (L + per - 1) / per;
+}
+
+size_t axvs_masked_mha_workspace_bytes(int B, int heads, int Nq, int L) {
+  if (B <= 0 || heads <= 0 || Nq <= 0 || L <= 0) return 0;
+  int splits, per, qb;
+  masked_mha_plan(B, heads, Nq, L, &splits, &per, &qb);
+  return (size_t)splits * B * heads * Nq * MM_REC * sizeof(float) + 256;
+}
+
+int axvs_masked_mha_fwd(const float* q, const float* k, const float* v, const unsigned char* mask, float* out32, void* out16_bf16, int B, int heads,
+                        int Nq, int L, int seq_first, void* workspace, size_t workspace_bytes, axvs_stream_t stream) {
+  if (!q || !k || !v || (!out32 && !out16_bf16) || !workspace) return fail(AXVS_E_INVALID, "masked_mha: null pointer");
+  if (B <= 0 || heads <= 0 || Nq <= 0 || L <= 0) return fail(AXVS_E_INVALID, "masked_mha: sizes must be positive");
+  int splits, per, qb;
+  masked_mha_plan(B, heads, Nq, L, &splits, &per, &qb);
+  if (heads > 65535 || (long long)B * qb > 65535) return fail(AXVS_E_UNSUPPORTED, "masked_mha: grid limits (heads, batch x query blocks <= 65535)");
+  if (workspace_bytes < axvs_masked_mha_workspace_bytes(B, heads, Nq, L)) return fail(AXVS_E_INVALID, "masked_mha: workspace too small");
+  MaskedMhaParams mp;
+  mp.q = q; mp.k = k; mp.v = v; mp.mask = mask;
+  mp.partial = reinterpret_cast<float*>(workspace);
+  mp.B = B; mp.H = heads; mp.Nq = Nq; mp.L = L; mp.keys_per_cta = per; mp.qblocks = qb; mp.seq_first = seq_first ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    ProfScope ps(KC_MMHA, 4.0 * B * heads * (double)Nq * L * MM_D, (double)B * heads * ((double)Nq * L + 2.0 * L * MM_D * 4.0), st);
+    masked_mha_partial_kernel<<<dim3(splits, heads, B * qb), MM_THREADS, 0, st>>>(mp);
+    const long long total = (long long)B * heads * Nq * MM_D;
+    masked_mha_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mp.partial, out32, reinterpret_cast<__nv_bfloat16*>(out16_bf16), splits, B, heads, Nq,
+                                                                              mp.seq_first);
+  }
+  AXVS_CHECK_LAUNCH("masked_mha kernels");
   return AXVS_OK;
 }
 

@@ -694,6 +694,35 @@ def query_self_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, sim_affin
     return out
 
 
+def masked_mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: Optional[torch.Tensor], heads: int = 8, seq_first: bool = True,
+               out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """softmax(q k^T + mask) v per head (axvs_masked_mha_fwd).  q [Nq, B, C] / k, v [L, B, C] fp32 (seq_first) or [B, N, C]; q already carries
+    head_dim^-0.5 * log2(e); mask bool / uint8 [B*heads, Nq, L] (True = blocked) or None.  Returns the heads' outputs in q's layout."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _check(t, nm, torch.float32)
+    if q.dim() != 3 or k.shape != v.shape or k.dim() != 3 or q.shape[2] != k.shape[2] or q.shape[2] != heads * 32:
+        raise RuntimeError("masked_mha: expected q [Nq, B, heads*32] and k, v [L, B, heads*32] (or batch-first)")
+    (Nq, B), L = (q.shape[:2], k.shape[0]) if seq_first else ((q.shape[1], q.shape[0]), k.shape[1])
+    if (k.shape[1] if seq_first else k.shape[0]) != B:
+        raise RuntimeError("masked_mha: batch sizes of q and k differ")
+    mptr = None
+    if mask is not None:
+        if mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
+        _check(mask, "mask", torch.uint8, (B * heads, Nq, L))
+        mptr = mask.data_ptr()
+    out = torch.empty_like(q, dtype=out_dtype)
+    lib = _lib.load()
+    nbytes = lib.axvs_masked_mha_workspace_bytes(B, heads, Nq, L)
+    ws = workspace(nbytes, q.device)
+    with torch.cuda.device(q.device):
+        rc = lib.axvs_masked_mha_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), mptr, out.data_ptr() if out_dtype == torch.float32 else None,
+                                     out.data_ptr() if out_dtype == torch.bfloat16 else None, B, heads, Nq, L, int(seq_first), ws.data_ptr(), nbytes,
+                                     _stream(q.device))
+    _lib.check(rc, "axvs_masked_mha_fwd")
+    return out
+
+
 def kmeans_update(mask_logits: torch.Tensor, pixel_value: torch.Tensor, advanced: bool = False,
                   return_assignment: bool = False):
     """k-means cluster update: mask_logits fp32 [N, L, M], pixel_value fp32 [N, 256, M] -> fp32 [N, 256, L] (and int32 [N, M])."""

@@ -224,3 +224,33 @@ def kmax_axial_params(seed: int, in_planes: int, key_depth: int = 512, value_dep
     # similarity logits are sums over 64 channels of unit-variance products: keep their batch-norm scale small so the softmax is not one-hot
     p["_batch_norm_similarity.weight"] *= 0.15
     return p
+
+
+def tl_decoder_layer_params(seed: int, C: int = 256, d_ffn: int = 2048) -> Params:
+    """State dict of the Tube-Link `DetrTransformerDecoderLayer` (mmcv key names): two MultiheadAttention blocks, FFN, three LayerNorms."""
+    g = torch.Generator().manual_seed(seed)
+    p: Params = {}
+    for i in range(2):
+        p[f"attentions.{i}.attn.in_proj_weight"] = _xavier(g, 3 * C, C)
+        p[f"attentions.{i}.attn.in_proj_bias"] = 0.1 * torch.randn(3 * C, generator=g)
+        _linear(g, f"attentions.{i}.attn.out_proj", C, C, p)
+    _linear(g, "ffns.0.layers.0.0", d_ffn, C, p)
+    _linear(g, "ffns.0.layers.1", C, d_ffn, p)
+    for i in range(3):
+        _ln(g, C, f"norms.{i}", p)
+    return p
+
+
+def tl_decoder_case(seed: int, Nq: int, B: int, L: int, heads: int = 8, C: int = 256, blocked: float = 0.6):
+    """query / key / positions / boolean attention mask of one decoder step; no query row is fully blocked (the head un-blocks such rows,
+    TL cc head :877-879)."""
+    g = torch.Generator().manual_seed(seed)
+    query, qpos = torch.randn(Nq, B, C, generator=g), torch.randn(Nq, B, C, generator=g)
+    key, kpos = torch.randn(L, B, C, generator=g), torch.randn(L, B, C, generator=g)
+    mask = torch.rand(B, 1, Nq, L, generator=g).expand(B, heads, Nq, L) < blocked          # the head repeats one mask over the heads
+    mask = mask.reshape(B * heads, Nq, L).clone()
+    mask[mask.all(-1)] = False
+    if Nq > 1:
+        mask[0, 1] = True                                                                    # one row with a single visible key
+        mask[0, 1, L // 2] = False
+    return query, qpos, key, kpos, mask

@@ -205,3 +205,142 @@ class CCHeadPredictor(nn.Module):
             ml = ops.mask_einsum(pix, me[i].reshape(t * q, n4).contiguous(), t, q, pix.shape[-1], 1.0, 0.0)    # [q, t, fpc*h*w]
             masks.append(ml.view(q, t * fpc, *mask_feature.shape[3:]).permute(1, 0, 2, 3).unsqueeze(0))       # [b, T_frames, q, h, w]
         return tuple(cls.unbind(0)), tuple(masks)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Tube-Link mask decoder layer (row A11, TL half): DetrTransformerDecoderLayer with operation_order
+# ('cross_attn', 'norm', 'self_attn', 'norm', 'ffn', 'norm'), TL/mmdet/models/utils/transformer.py:408-451, configured at
+# TL/configs/video/**: MultiheadAttention(embed_dims=256, num_heads=8, batch_first=False), FFN(256 -> 2048 -> 256, ReLU, add_identity),
+# post-norm; called once per decoder step at TL/models/video/tube_link_vis/mask2former_video_cc_head.py:883-894 with
+# attn_masks = [attn_mask, None].
+#
+# mmcv-full 1.6.1 (MultiheadAttention, BaseTransformerLayer, FFN) is NOT vendored in the reference tree and not installed here, so its
+# wrapper semantics are RESTATED, not pinned -- "parity unpinned" for the wrapper:
+#   MultiheadAttention.forward(query, key, value, identity, query_pos, key_pos, attn_mask):
+#       q = query + query_pos; k = key + key_pos; v = value; out = torch.nn.MultiheadAttention(q, k, v, attn_mask)[0]; return identity + out
+#   BaseTransformerLayer (post-norm): 'cross_attn' uses (key, value, key_pos, attn_masks[0]); 'self_attn' uses key = value = query,
+#       key_pos = query_pos, attn_masks[1]; 'norm' = LayerNorm; 'ffn' = x + Linear(ReLU(Linear(x))).
+# The arithmetic core IS pinned: the oracle restatement is checked against torch.nn.MultiheadAttention / nn.LayerNorm / nn.Linear themselves
+# (tests/test_oracle_golden.py::test_tl_decoder_layer_oracle_against_torch_mha).
+# State-dict keys follow mmcv: attentions.{0,1}.attn.{in_proj_weight,in_proj_bias,out_proj.weight,out_proj.bias},
+# ffns.0.layers.0.0.{weight,bias}, ffns.0.layers.1.{weight,bias}, norms.{0,1,2}.{weight,bias}.
+# ------------------------------------------------------------------------------------------------------------------
+class _TorchMHAParams(nn.Module):
+    """Parameter holder with torch.nn.MultiheadAttention's names (mmcv keeps the torch module as `.attn`)."""
+
+    def __init__(self, embed_dims: int):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dims, embed_dims))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dims))
+        self.out_proj = nn.Linear(embed_dims, embed_dims)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+
+
+class MultiheadAttention(nn.Module):
+    """mmcv.cnn.bricks.transformer.MultiheadAttention (batch_first=False, no dropout) on the library's masked attention kernel."""
+
+    def __init__(self, embed_dims: int = 256, num_heads: int = 8, attn_drop: float = 0.0, proj_drop: float = 0.0, dropout_layer=None,
+                 batch_first: bool = False, **kwargs):
+        super().__init__()
+        if embed_dims != num_heads * 32:
+            raise NotImplementedError("MultiheadAttention: built for 32 channels per head (embed_dims = 32 * num_heads)")
+        if batch_first:
+            raise NotImplementedError("MultiheadAttention: the Tube-Link decoder uses batch_first=False")
+        self.embed_dims, self.num_heads = embed_dims, num_heads
+        self.attn = _TorchMHAParams(embed_dims)
+        self._cache = _PackedCache()
+        self.register_load_state_dict_post_hook(_invalidate_hook)
+
+    def _packed(self, dev):
+        def build():
+            E = self.embed_dims
+            w, b = self.attn.in_proj_weight.detach().float(), self.attn.in_proj_bias.detach().float()
+            return {"wq": ops.pack_weight(w[:E].contiguous()), "wk": ops.pack_weight(w[E:2 * E].contiguous()), "wv": ops.pack_weight(w[2 * E:].contiguous()),
+                    "bq": b[:E].contiguous(), "bk": b[E:2 * E].contiguous(), "bv": b[2 * E:].contiguous(),
+                    "wo": ops.pack_weight(self.attn.out_proj.weight.detach().float().contiguous()), "bo": self.attn.out_proj.bias.detach().float().contiguous()}
+        return self._cache.get(self, dev, build)
+
+    def project_kv(self, key: Tensor, value: Tensor, key_pos):
+        """k = (key + key_pos) Wk^T + bk and v = value Wv^T + bv as fp32 rows (the decoder re-uses a level's memory in three layers, but every
+        layer has its own weights).  The positional term goes through the GEMM's residual input: (key + key_pos) W^T = key W^T + key_pos W^T."""
+        pk = self._packed(key.device)
+        E = self.embed_dims
+        rows = key.reshape(-1, E)
+        kp = ops.linear(ops.cast_bf16(key_pos.reshape(-1, E)), pk["wk"], None, E, out_dtype=torch.float32) if key_pos is not None else None
+        k = ops.linear(ops.cast_bf16(rows), pk["wk"], pk["bk"], E, out_dtype=torch.float32, resid=kp)
+        v = ops.linear(ops.cast_bf16(value.reshape(-1, E)), pk["wv"], pk["bv"], E, out_dtype=torch.float32)
+        return k.view(key.shape), v.view(value.shape)
+
+    def forward(self, query: Tensor, key: Tensor = None, value: Tensor = None, identity: Tensor = None, query_pos: Tensor = None,
+                key_pos: Tensor = None, attn_mask: Tensor = None, key_padding_mask: Tensor = None, **kwargs) -> Tensor:
+        _require_inference(self, query)
+        if key_padding_mask is not None:
+            raise NotImplementedError("MultiheadAttention: key_padding_mask is None at both call sites of the Tube-Link decoder")
+        key = query if key is None else key
+        value = key if value is None else value
+        identity = query if identity is None else identity
+        if key_pos is None and query_pos is not None and query_pos.shape == key.shape:
+            key_pos = query_pos
+        pk = self._packed(query.device)
+        E = self.embed_dims
+        query, identity = query.float().contiguous(), identity.float().contiguous()
+        scale = (E // self.num_heads) ** -0.5 * 1.4426950408889634           # softmax scale and log2(e): the kernel works in the exp2 domain
+        # axvs_linear computes (a W^T + bias) * scale + resid: the positional term enters pre-scaled
+        qp = ops.linear(ops.cast_bf16(query_pos.float().reshape(-1, E)), pk["wq"], None, E, scale=scale, out_dtype=torch.float32) if query_pos is not None else None
+        q = ops.linear(ops.cast_bf16(query.reshape(-1, E)), pk["wq"], pk["bq"], E, scale=scale, out_dtype=torch.float32, resid=qp).view(query.shape)
+        k, v = self.project_kv(key.float().contiguous(), value.float().contiguous(), None if key_pos is None else key_pos.float().contiguous())
+        if attn_mask is not None and attn_mask.dtype != torch.bool:
+            raise NotImplementedError("MultiheadAttention: boolean attn_mask only (True = blocked), as the Tube-Link head builds it")
+        o = ops.masked_mha(q, k, v, None if attn_mask is None else attn_mask.contiguous(), heads=self.num_heads, seq_first=True)
+        return ops.linear(o.reshape(-1, E), pk["wo"], pk["bo"], E, out_dtype=torch.float32, resid=identity.reshape(-1, E)).view(query.shape)
+
+
+class _FFN(nn.Module):
+    """mmcv FFN: layers = Sequential(Sequential(Linear, ReLU, Dropout), Linear, Dropout), add_identity."""
+
+    def __init__(self, embed_dims: int, feedforward_channels: int):
+        super().__init__()
+        self.layers = nn.Sequential(nn.Sequential(nn.Linear(embed_dims, feedforward_channels), nn.ReLU(inplace=True), nn.Dropout(0.0)),
+                                    nn.Linear(feedforward_channels, embed_dims), nn.Dropout(0.0))
+
+
+class DetrTransformerDecoderLayer(nn.Module):
+    """Drop-in for the Tube-Link decoder layer (see the block comment above): forward(query, key, value, query_pos, key_pos, attn_masks)."""
+
+    def __init__(self, embed_dims: int = 256, num_heads: int = 8, feedforward_channels: int = 2048,
+                 operation_order=("cross_attn", "norm", "self_attn", "norm", "ffn", "norm"), **kwargs):
+        super().__init__()
+        if tuple(operation_order) != ("cross_attn", "norm", "self_attn", "norm", "ffn", "norm"):
+            raise NotImplementedError("DetrTransformerDecoderLayer: the operation order of the shipped Tube-Link configs only")
+        self.embed_dims, self.pre_norm = embed_dims, False
+        self.attentions = nn.ModuleList([MultiheadAttention(embed_dims, num_heads), MultiheadAttention(embed_dims, num_heads)])
+        self.ffns = nn.ModuleList([_FFN(embed_dims, feedforward_channels)])
+        self.norms = nn.ModuleList([nn.LayerNorm(embed_dims) for _ in range(3)])
+        self._cache = _PackedCache()
+        self.register_load_state_dict_post_hook(_invalidate_hook)
+
+    def _packed_ffn(self, dev):
+        def build():
+            l0, l1 = self.ffns[0].layers[0][0], self.ffns[0].layers[1]
+            return {"w1": ops.pack_weight(l0.weight.detach().float().contiguous()), "b1": l0.bias.detach().float().contiguous(),
+                    "w2": ops.pack_weight(l1.weight.detach().float().contiguous()), "b2": l1.bias.detach().float().contiguous()}
+        return self._cache.get(self.ffns[0], dev, build)
+
+    def _norm(self, i: int, x: Tensor) -> Tensor:
+        n = self.norms[i]
+        return ops.layernorm(x.reshape(-1, self.embed_dims), n.weight.detach().float(), n.bias.detach().float(), n.eps).view(x.shape)
+
+    def forward(self, query: Tensor, key: Tensor = None, value: Tensor = None, query_pos: Tensor = None, key_pos: Tensor = None,
+                attn_masks=None, query_key_padding_mask=None, key_padding_mask=None, **kwargs) -> Tensor:
+        _require_inference(self, query)
+        if query_key_padding_mask is not None or key_padding_mask is not None:
+            raise NotImplementedError("DetrTransformerDecoderLayer: padding masks are None in the Tube-Link head")
+        masks = [None, None] if attn_masks is None else list(attn_masks)
+        E = self.embed_dims
+        x = self._norm(0, self.attentions[0](query, key, value, None, query_pos=query_pos, key_pos=key_pos, attn_mask=masks[0]))
+        x = self._norm(1, self.attentions[1](x, x, x, None, query_pos=query_pos, key_pos=query_pos, attn_mask=masks[1]))
+        pk = self._packed_ffn(x.device)
+        F_ = self.ffns[0].layers[0][0].out_features
+        h = ops.linear(ops.cast_bf16(x.reshape(-1, E)), pk["w1"], pk["b1"], F_, relu=True)
+        y = ops.linear(h, pk["w2"], pk["b2"], E, out_dtype=torch.float32, resid=x.reshape(-1, E)).view(x.shape)
+        return self._norm(2, y)

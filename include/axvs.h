@@ -218,6 +218,18 @@ int axvs_linear_f32(const float* a, int lda, int M, int K, const void* w_packed,
 int axvs_query_self_attn(const float* q, const float* k, const float* v, const float* sim_affine, const float* val_affine, float* out,
                          int N, int heads, int L, axvs_stream_t stream);
 
+/* Masked multi-head attention core of the Tube-Link mask decoder: mmcv `MultiheadAttention` (a wrapper of torch.nn.MultiheadAttention;
+ * mmcv-full 1.6.1 is not vendored, its wrapper semantics are restated, see axial_vs_b200/tube_link.py) inside `DetrTransformerDecoderLayer`,
+ * TL/mmdet/models/utils/transformer.py:408-451, called at TL/models/video/tube_link_vis/mask2former_video_cc_head.py:883-894.
+ *   out[b, i, h*32 + :] = softmax_j( q[b, i, h] . k[b, j, h] + (mask[b*heads + h, i, j] ? -inf : 0) ) @ v[b, j, h]
+ * q, k, v fp32, ALREADY projected (in_proj) with 32 channels per head; q must carry head_dim^-0.5 * log2(e) (the kernel works in the
+ * exp2 domain).  Layout [B, N, heads*32], or [N, B, heads*32] when seq_first != 0 (mmcv batch_first = False).  mask: bytes
+ * [B*heads, Nq, L], non-zero = blocked, or NULL.  out32 (fp32) and / or out16 (bf16, the A operand of the output projection), same layout
+ * as q.  A row with every key blocked yields NaN like the reference op. */
+size_t axvs_masked_mha_workspace_bytes(int B, int heads, int Nq, int L);
+int axvs_masked_mha_fwd(const float* q, const float* k, const float* v, const unsigned char* mask, float* out32, void* out16_bf16, int B, int heads,
+                        int Nq, int L, int seq_first, void* workspace, size_t workspace_bytes, axvs_stream_t stream);
+
 /* k-means cross-attention update (DEC:196-208): assign[n, m] = argmax_l mask_logits[n, l, m] (first maximum),
  * out[n, d, l] = sum over the pixels assigned to l of pixel_value[n, d, m]; divided by max(count, 1) when advanced != 0
  * (advanced_kmax, DEC:206-208).  mask_logits fp32 [N, L, M], pixel_value fp32 [N, 256, M], out fp32 [N, 256, L], L <= 128;

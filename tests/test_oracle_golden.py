@@ -244,3 +244,21 @@ def test_tube_link_cc_layer(golden):
     x = synth.randn(seed + 1, b, T * Q, 256)
     y = O.cc_attention_layer(x, p, Q, T)
     assert (y - torch.from_numpy(gz["y"])).abs().max().item() < 2e-5
+
+
+def test_tl_decoder_layer_oracle_against_torch_mha(golden):
+    """Row A11 (Tube-Link half): the restated decoder layer against the same layer composed from torch.nn.MultiheadAttention / LayerNorm /
+    Linear (the modules mmcv's MultiheadAttention / BaseTransformerLayer / FFN wrap; mmcv itself is not installed: wrapper semantics
+    unpinned), on the golden inputs and on a second case with an un-masked self-attention only."""
+    from axial_vs_b200 import synth
+    from oracle import tl_decoder_oracle as TO
+    gz = golden("tl_decoder_layer")
+    seed, Nq, B, L = (int(gz[k]) for k in "seed Nq B L".split())
+    p = synth.tl_decoder_layer_params(seed)
+    q, qp, k, kp, m = synth.tl_decoder_case(seed + 1, Nq, B, L)
+    y = TO.decoder_layer(q, k, k, qp, kp, [m, None], p)
+    assert float((y - torch.from_numpy(gz["y"])).abs().max()) < 2e-5
+    q, qp, k, kp, m = synth.tl_decoder_case(seed + 9, 7, 3, 33)
+    a = TO.decoder_layer(q, k, k, qp, kp, None, p)
+    b = TO.torch_module_composition(q, k, k, qp, kp, None, p)
+    assert float((a - b).abs().max()) < 2e-5
