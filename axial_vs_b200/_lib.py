@@ -76,6 +76,10 @@ SIGNATURES = {
     "axvs_cc_aspp_fwd": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(AsppWeights), c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "axvs_cc_class_pool": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p]),
     "axvs_query_self_attn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "axvs_cm_to_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "axvs_rows_to_cm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "axvs_dwconv5": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "axvs_add_act": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
     "axvs_masked_mha_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "axvs_masked_mha_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "axvs_kmeans_update_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -31,6 +31,7 @@
 #include "ffn_pair.cuh"
 #include "ffn_n256_pair.cuh"
 #include "masked_mha.cuh"
+#include "kmax_layer.cuh"
 
 using namespace axvs;
 
@@ -47,12 +48,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_MATCH, KC_MMHA, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_MATCH, KC_MMHA, KC_KMAXLAYER, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel", "matching_kernels", "masked_mha_kernels"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel", "matching_kernels", "masked_mha_kernels", "kmax_layer_kernels"};
 // Process-wide knobs are atomics (two host threads driving two devices may read / set them concurrently); the profiler's records and
 // the per-device attribute table are guarded by mutexes.  None of them is touched on the launch path beyond one relaxed load.
 std::atomic<int> g_fusion{4};   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
@@ -1097,6 +1098,51 @@ int axvs_query_self_attn(const float* q, const float* k, const float* v, const f
     query_self_attn_kernel<<<dim3(heads, N), 128, smem, (cudaStream_t)stream>>>(q, k, v, sim_affine, val_affine, out, heads, L);
   }
   AXVS_CHECK_LAUNCH("query_self_attn_kernel");
+  return AXVS_OK;
+}
+
+// ---- layout / elementwise helpers of the kMaX transformer decoder layer (csrc/kmax_layer.cuh)
+int axvs_cm_to_rows(const float* x, float* rows, int N, int C, int M, int act, axvs_stream_t stream) {
+  if (!x || !rows) return fail(AXVS_E_INVALID, "cm_to_rows: null pointer");
+  if (N <= 0 || C <= 0 || M <= 0 || N > 65535 || (C + 31) / 32 > 65535) return fail(AXVS_E_INVALID, "cm_to_rows: bad sizes");
+  if (act != 0 && act != 2) return fail(AXVS_E_UNSUPPORTED, "cm_to_rows: act must be 0 (none) or 2 (GELU)");
+  {
+    ProfScope ps(KC_KMAXLAYER, 0, 8.0 * N * C * M, (cudaStream_t)stream);
+    cm_to_rows_kernel<<<dim3((M + 31) / 32, (C + 31) / 32, N), 256, 0, (cudaStream_t)stream>>>(x, rows, C, M, act);
+  }
+  AXVS_CHECK_LAUNCH("cm_to_rows_kernel");
+  return AXVS_OK;
+}
+
+int axvs_rows_to_cm(const float* rows, int ld, float* out, int N, int C, int M, int normalize, axvs_stream_t stream) {
+  if (!rows || !out) return fail(AXVS_E_INVALID, "rows_to_cm: null pointer");
+  if (N <= 0 || C <= 0 || M <= 0 || ld < C || N > 65535) return fail(AXVS_E_INVALID, "rows_to_cm: bad sizes");
+  if (C > 256) return fail(AXVS_E_UNSUPPORTED, "rows_to_cm: at most 256 channels (got %d)", C);
+  {
+    ProfScope ps(KC_KMAXLAYER, 0, 8.0 * N * C * M, (cudaStream_t)stream);
+    rows_to_cm_kernel<<<dim3((M + 31) / 32, N), 256, 0, (cudaStream_t)stream>>>(rows, ld, out, C, M, normalize ? 1 : 0);
+  }
+  AXVS_CHECK_LAUNCH("rows_to_cm_kernel");
+  return AXVS_OK;
+}
+
+int axvs_dwconv5(const float* x, const float* w, const float* affine, float* y, int N, int H, int W, int C, int act, axvs_stream_t stream) {
+  if (!x || !w || !affine || !y) return fail(AXVS_E_INVALID, "dwconv5: null pointer");
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return fail(AXVS_E_INVALID, "dwconv5: sizes must be positive and C a multiple of 4");
+  const long long total = (long long)N * H * W * (C / 4);
+  {
+    ProfScope ps(KC_KMAXLAYER, 50.0 * N * H * W * C, 8.0 * N * H * W * C, (cudaStream_t)stream);
+    dwconv5_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, w, affine, y, N, H, W, C, act);
+  }
+  AXVS_CHECK_LAUNCH("dwconv5_kernel");
+  return AXVS_OK;
+}
+
+int axvs_add_act(const float* a, const float* b, float* y, long long n, int act, axvs_stream_t stream) {
+  if (!a || !y) return fail(AXVS_E_INVALID, "add_act: null pointer");
+  if (n <= 0) return fail(AXVS_E_INVALID, "add_act: n must be positive");
+  add_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, y, n, act);
+  AXVS_CHECK_LAUNCH("add_act_kernel");
   return AXVS_OK;
 }
 

@@ -694,6 +694,54 @@ def query_self_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, sim_affin
     return out
 
 
+def cm_to_rows(x: torch.Tensor, gelu: bool = False) -> torch.Tensor:
+    """fp32 [N, C, M] (channel-major, the reference's layout) -> token rows [N*M, C]; optional GELU on the way (axvs_cm_to_rows)."""
+    _check(x, "x", torch.float32)
+    N, Cc, M = x.shape
+    rows = torch.empty(N * M, Cc, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.axvs_cm_to_rows(x.data_ptr(), rows.data_ptr(), N, Cc, M, 2 if gelu else 0, _stream(x.device)), "axvs_cm_to_rows")
+    return rows
+
+
+def rows_to_cm(rows: torch.Tensor, N: int, channels: int, normalize: bool = False) -> torch.Tensor:
+    """token rows fp32 [N*M, ld] -> [N, channels, M] (first `channels` columns); normalize: L2 over the channels (axvs_rows_to_cm)."""
+    _check(rows, "rows", torch.float32)
+    M = rows.shape[0] // N
+    out = torch.empty(N, channels, M, dtype=torch.float32, device=rows.device)
+    lib = _lib.load()
+    with torch.cuda.device(rows.device):
+        _lib.check(lib.axvs_rows_to_cm(rows.data_ptr(), rows.shape[1], out.data_ptr(), N, channels, M, int(normalize), _stream(rows.device)), "axvs_rows_to_cm")
+    return out
+
+
+def dwconv5(x_rows: torch.Tensor, w: torch.Tensor, affine: torch.Tensor, N: int, H: int, W: int, act: int = 2) -> torch.Tensor:
+    """Depthwise 5x5 convolution (padding 2) + folded batch norm + activation on channels-last rows [N*H*W, C] (axvs_dwconv5)."""
+    for t, nm in ((x_rows, "x"), (w, "w"), (affine, "affine")):
+        _check(t, nm, torch.float32)
+    Cc = x_rows.shape[1]
+    if x_rows.shape[0] != N * H * W or w.numel() != Cc * 25 or affine.numel() != 2 * Cc:
+        raise RuntimeError("dwconv5: size mismatch")
+    y = torch.empty_like(x_rows)
+    lib = _lib.load()
+    with torch.cuda.device(x_rows.device):
+        _lib.check(lib.axvs_dwconv5(x_rows.data_ptr(), w.data_ptr(), affine.data_ptr(), y.data_ptr(), N, H, W, Cc, act, _stream(x_rows.device)), "axvs_dwconv5")
+    return y
+
+
+def add_act(a: torch.Tensor, b: Optional[torch.Tensor], act: int = 0) -> torch.Tensor:
+    """act(a + b) elementwise on fp32 tensors of equal shape (axvs_add_act); act 0 none, 1 ReLU, 2 GELU."""
+    _check(a, "a", torch.float32)
+    if b is not None:
+        _check(b, "b", torch.float32, tuple(a.shape))
+    y = torch.empty_like(a)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        _lib.check(lib.axvs_add_act(a.data_ptr(), _ptr(b), y.data_ptr(), a.numel(), act, _stream(a.device)), "axvs_add_act")
+    return y
+
+
 def masked_mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: Optional[torch.Tensor], heads: int = 8, seq_first: bool = True,
                out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
     """softmax(q k^T + mask) v per head (axvs_masked_mha_fwd).  q [Nq, B, C] / k, v [L, B, C] fp32 (seq_first) or [B, N, C]; q already carries
@@ -745,7 +793,8 @@ def kmeans_update(mask_logits: torch.Tensor, pixel_value: torch.Tensor, advanced
     return (out, assign) if return_assignment else out
 
 
-def mask_einsum(pixel: torch.Tensor, mk: torch.Tensor, T: int, Q: int, P: int, bn_scale: float, bn_shift: float) -> torch.Tensor:
+def mask_einsum(pixel: torch.Tensor, mk: torch.Tensor, T: int, Q: int, P: int, bn_scale: float, bn_shift: float,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[q, t, p] = bn_scale * sum_c pixel[t, c, p] mk[t*Q + q, c] + bn_shift; pixel fp32 [T, 128, P], mk [T*Q, ld >= 128]:
     bf16 (plain bf16 products) or fp32 (split-precision products, fp32-grade logits)."""
     _check(pixel, "pixel", torch.float32)
@@ -755,7 +804,12 @@ def mask_einsum(pixel: torch.Tensor, mk: torch.Tensor, T: int, Q: int, P: int, b
     channels = pixel.numel() // (T * P)
     if pixel.numel() != T * channels * P or mk.shape[0] != T * Q or (mk.dtype == torch.bfloat16 and channels != 128):
         raise RuntimeError("mask_einsum: size mismatch")
-    out = torch.empty(Q, T, P, dtype=torch.float32, device=pixel.device)
+    if out is None:
+        out = torch.empty(Q, T, P, dtype=torch.float32, device=pixel.device)
+    else:
+        _check(out, "out", torch.float32)
+        if out.numel() != Q * T * P:
+            raise RuntimeError("mask_einsum: out has the wrong size")
     lib = _lib.load()
     with torch.cuda.device(pixel.device):
         if mk.dtype == torch.float32:

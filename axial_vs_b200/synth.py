@@ -254,3 +254,46 @@ def tl_decoder_case(seed: int, Nq: int, B: int, L: int, heads: int = 8, C: int =
         mask[0, 1] = True                                                                    # one row with a single visible key
         mask[0, 1, L // 2] = False
     return query, qpos, key, kpos, mask
+
+
+def kmax_layer_params(seed: int, in_channel_pixel: int, num_classes: int) -> Params:
+    """State dict of the clip-level `kMaXTransformerLayer` (reference key names; bottleneck 256, key depth 128, value depth 256, 8 heads) with
+    non-trivial eval-mode batch-norm statistics and affines (the reference's norm_init = 0 would zero the residual updates)."""
+    g = torch.Generator().manual_seed(seed)
+    p: Params = {}
+
+    def conv(name, o, c, k=1, groups=1, two_d=False, bias=False, std=None):
+        shape = (o, c // groups, k, k) if two_d else (o, c // groups, k)
+        std = math.sqrt(2.0 / c) if std is None else std
+        p[name + ".conv.weight"] = std * torch.randn(*shape, generator=g)
+        if bias:
+            p[name + ".conv.bias"] = 0.1 * torch.randn(o, generator=g)
+
+    def bn(name, c):
+        p[name + ".weight"] = 1.0 + 0.2 * torch.randn(c, generator=g)
+        p[name + ".bias"] = 0.1 * torch.randn(c, generator=g)
+        p[name + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
+        p[name + ".running_var"] = 1.0 + 0.3 * torch.rand(c, generator=g)
+
+    def conv_bn(name, o, c, **kw):
+        conv(name, o, c, **kw)
+        bn(name + ".norm", o)
+
+    conv_bn("_query_conv1_bn_act", 256, 256)
+    conv_bn("_pixel_conv1_bn_act", 256, in_channel_pixel, two_d=True)
+    conv_bn("_query_qkv_conv_bn", 512, 256, std=256 ** -0.5)
+    conv_bn("_pixel_v_conv_bn", 256, 256, two_d=True, std=256 ** -0.5)
+    bn("_query_self_attention._batch_norm_similarity", 8)
+    bn("_query_self_attention._batch_norm_retrieved_value", 256)
+    conv_bn("_query_conv3_bn", 256, 256)
+    conv_bn("_query_ffn_conv1_bn_act", 2048, 256)
+    conv_bn("_query_ffn_conv2_bn", 256, 2048)
+    conv_bn("_predictor._pixel_space_head_conv0bnact", 256, 256, k=5, groups=256, two_d=True, std=0.2)
+    conv_bn("_predictor._pixel_space_head_conv1bnact", 256, 256, two_d=True)
+    conv_bn("_predictor._pixel_space_head_last_convbn", 128, 256, two_d=True, bias=True, std=0.2)
+    conv_bn("_predictor._transformer_mask_head", 128, 256)
+    conv("_predictor._transformer_class_head", num_classes, 256, bias=True, std=0.05)
+    bn("_predictor._pixel_space_mask_batch_norm", 1)
+    bn("_kmeans_query_batch_norm_retrieved_value", 256)
+    conv_bn("_kmeans_query_conv3_bn", 256, 256)
+    return p

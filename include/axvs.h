@@ -218,6 +218,18 @@ int axvs_linear_f32(const float* a, int lda, int M, int K, const void* w_packed,
 int axvs_query_self_attn(const float* q, const float* k, const float* v, const float* sim_affine, const float* val_affine, float* out,
                          int N, int heads, int L, axvs_stream_t stream);
 
+/* Layout / elementwise helpers of the kMaX transformer decoder layer's pixel side (Vk/maxtron_deeplab/modeling/transformer_decoder/
+ * maxtron_transformer_decoder.py:75-124, 184-232; the 1x1 convolutions with their folded batch norms run on axvs_linear_f32 over token rows):
+ *   axvs_cm_to_rows : x fp32 [N, C, M] (the reference's channel-major tensors) -> rows [N*M, C]; act = 2 applies GELU on the way (:186)
+ *   axvs_rows_to_cm : rows [N*M, ld] -> out [N, C, M] (first C <= 256 channels); normalize != 0: F.normalize(p=2, dim=channel), eps 1e-12 (:102)
+ *   axvs_dwconv5    : depthwise 5x5 convolution, padding 2, on channels-last rows [N, H, W, C] + folded batch norm [C][2] + act (:78-79);
+ *                     w is the Conv2d weight [C, 1, 5, 5] flattened
+ *   axvs_add_act    : y = act(a + b), act 0 / 1 (ReLU) / 2 (GELU erf) (:212-213, 219-220); b may be NULL */
+int axvs_cm_to_rows(const float* x, float* rows, int N, int C, int M, int act, axvs_stream_t stream);
+int axvs_rows_to_cm(const float* rows, int ld, float* out, int N, int C, int M, int normalize, axvs_stream_t stream);
+int axvs_dwconv5(const float* x, const float* w, const float* affine, float* y, int N, int H, int W, int C, int act, axvs_stream_t stream);
+int axvs_add_act(const float* a, const float* b, float* y, long long n, int act, axvs_stream_t stream);
+
 /* Masked multi-head attention core of the Tube-Link mask decoder: mmcv `MultiheadAttention` (a wrapper of torch.nn.MultiheadAttention;
  * mmcv-full 1.6.1 is not vendored, its wrapper semantics are restated, see axial_vs_b200/tube_link.py) inside `DetrTransformerDecoderLayer`,
  * TL/mmdet/models/utils/transformer.py:408-451, called at TL/models/video/tube_link_vis/mask2former_video_cc_head.py:883-894.

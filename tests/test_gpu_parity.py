@@ -1291,3 +1291,48 @@ def test_masked_mha_core_fp32():
     want = (torch.softmax(s, -1) @ vh).permute(2, 0, 1, 3).reshape(Nq, B, 256).float()
     got = ops.masked_mha((q * (scale * 1.4426950408889634)).cuda(), k.cuda(), v.cuda(), mask.cuda(), heads=H, seq_first=True, out_dtype=torch.float32)
     assert float((got.cpu() - want).abs().max()) < 2e-5
+
+
+# --------------------------------------------------------------------------------------------- clip-level kMaX decoder layer, whole (row A11)
+def _kmax_layer_check(got_q, got_pred, want_q, want_pred, tol_q=2e-3):
+    # split-precision GEMMs: fp32-grade, so the tolerances sit far below the path's 1e-2; the k-means step is an argmax over the mask
+    # logits, so a pixel whose two best clusters are closer than the logit error may move: bounded through the assignment agreement
+    for name in ("class_logits", "mask_logits", "mask_embeddings", "pixel_feature"):
+        assert got_pred[name].shape == want_pred[name].shape, name
+        assert nerr(got_pred[name], want_pred[name]) < 2e-4, (name, nerr(got_pred[name], want_pred[name]))
+    agree = (got_pred["mask_logits"].cpu().argmax(1) == want_pred["mask_logits"].argmax(1)).float().mean().item()
+    assert agree >= 0.999, agree
+    assert got_q.shape == want_q.shape and nerr(got_q, want_q) < tol_q, nerr(got_q, want_q)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_kmax_transformer_layer_golden(golden, tag):
+    """kMaXTransformerLayer drop-in (pixel side: GELU -> 1x1 ConvBN -> value / depthwise 5x5 + two 1x1 ConvBN + L2 normalise; query x pixel
+    contraction + BN; k-means update; query self-attention; FFN) against the output of the unmodified reference layer."""
+    from axial_vs_b200 import decoder_attn
+    gz = golden(f"kmax_layer_{tag}")
+    N, L, Cp, TH, W, K, seed = (int(gz[k]) for k in "N L Cp TH W K seed".split())
+    layer = decoder_attn.kMaXTransformerLayer(num_classes=K, in_channel_pixel=Cp).eval()
+    layer.load_state_dict(synth.kmax_layer_params(seed, Cp, K), strict=True)
+    layer.cuda()
+    with torch.no_grad():
+        q, pred = layer(synth.randn(seed + 100, N, Cp, TH, W).cuda(), synth.randn(seed + 200, N, 256, L).cuda())
+    want = {k: torch.from_numpy(gz[k]) for k in ("class_logits", "mask_logits", "mask_embeddings", "pixel_feature")}
+    _kmax_layer_check(q, pred, torch.from_numpy(gz["query"]), want)
+
+
+def test_kmax_transformer_layer_oracle_r50_stage():
+    """The same at a BASELINE-sized stage: 3 clips of T = 2 frames at output stride 16 (2 x 41 x 41 pixels stacked along H), 1024 pixel channels,
+    128 queries, VIPSeg's 124 + 1 classes, against the oracle (pinned on the reference by the goldens)."""
+    from axial_vs_b200 import decoder_attn
+    from oracle import kmax_layer_oracle as KO
+    N, L, Cp, TH, W, K, seed = 3, 128, 1024, 82, 41, 125, 8200
+    p = synth.kmax_layer_params(seed, Cp, K)
+    layer = decoder_attn.kMaXTransformerLayer(num_classes=K, in_channel_pixel=Cp).eval()
+    layer.load_state_dict(p, strict=True)
+    layer.cuda()
+    pf, qf = synth.randn(seed + 100, N, Cp, TH, W), synth.randn(seed + 200, N, 256, L)
+    want_q, want_pred = KO.transformer_layer(pf, qf, p)
+    with torch.no_grad():
+        q, pred = layer(pf.cuda(), qf.cuda())
+    _kmax_layer_check(q, pred, want_q, want_pred)

@@ -262,3 +262,19 @@ def test_tl_decoder_layer_oracle_against_torch_mha(golden):
     a = TO.decoder_layer(q, k, k, qp, kp, None, p)
     b = TO.torch_module_composition(q, k, k, qp, kp, None, p)
     assert float((a - b).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_kmax_layer_oracle_golden(golden, tag):
+    """Row A11 (Video-kMaX half): the restated kMaXTransformerLayer + kMaXPredictor against the output of the UNMODIFIED reference layer
+    (tests/golden/kmax_layer_*.npz from oracle/make_golden_kmax_layer.py; parameters regenerated from the seed)."""
+    from oracle import kmax_layer_oracle as KO
+    gz = golden(f"kmax_layer_{tag}")
+    N, L, Cp, TH, W, K, seed = (int(gz[k]) for k in "N L Cp TH W K seed".split())
+    p = synth.kmax_layer_params(seed, Cp, K)
+    q, pred = KO.transformer_layer(synth.randn(seed + 100, N, Cp, TH, W), synth.randn(seed + 200, N, 256, L), p)
+    for name, got in (("query", q), ("class_logits", pred["class_logits"]), ("mask_logits", pred["mask_logits"]),
+                      ("mask_embeddings", pred["mask_embeddings"]), ("pixel_feature", pred["pixel_feature"])):
+        want = torch.from_numpy(gz[name])
+        assert got.shape == want.shape, name
+        assert float((got - want).abs().max() / want.abs().max()) < 2e-5, name
