@@ -91,60 +91,72 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FF_THREADS, 1) ffn_n
     uint32_t it = 0;
     for (int pt = pair; pt < pair_tiles; pt += npairs, ++it) {
       const int tile = 2 * pt + (int)rank;                     // may be == p.tiles (odd tile count): every row masked
+      const bool trc_ = it == 3 && lane == 0 && wq == 0;
+      const int tb_ = 100 + 100 * g;
+      // ---- the residual rows (128 KiB per tile = ~6 k clk of this SM's HBM share, and about as long to ISSUE: the load/store unit takes
+      // them at the memory system's pace) are requested in four 32-column batches, one after each hidden chunk's drain, so that both the
+      // issue time and the latency hide behind the next chunk's UMMAs; they wait in registers until the final epilogue (the drains work
+      // on 32 columns at a time to leave room).  The single-CTA kernel issues all of them after the last chunk, in front of the epilogue.
+      const int row0 = tile * 128 + wq * 32;
+      float4 t[4][8];
+      auto load_resid = [&](int c) {
+        const int col = 128 * g + 32 * c + piece * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                              // no arithmetic on the loaded values here: it would wait for them
+          const int r = row0 + i * 4 + sub;
+          t[c][i] = (r < p.rows) ? __ldg(reinterpret_cast<const float4*>(p.s32 + (size_t)r * 256 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
       // ---- hidden chunks of 256 columns on ONE 256-column stage: group g drains its 128 columns (bias + ReLU -> bf16 pairs)
       // and writes them back in place over the first 64 columns of its region: the tensor-memory A operand of GEMM 2
 #pragma unroll 1
       for (int j = 0; j < NJ; ++j) {
         const uint32_t hc = it * NJ + j;                         // global chunk counter
+        AXVS_TRACE(trc_, tb_ + 4 * j)
         mbar_wait_cluster(&s_full[0], hc & 1);
+        AXVS_TRACE(trc_, tb_ + 4 * j + 1)
         tc_fence_after();
         const uint32_t t_s = tmem + lane_base + 256 + 128 * g;
-        uint32_t hpk[64];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float v0[32], v1[32];
-          tmem_ld32(t_s + 64 * c, v0);
-          tmem_ld32(t_s + 64 * c + 32, v1);
+        for (int c = 0; c < 4; ++c) {                              // 32 columns at a time: 16 packed words back over the stage's head
+          float v[32];
+          tmem_ld32(t_s + 32 * c, v);
           tmem_ld_wait();
-          const float4* b4 = reinterpret_cast<const float4*>(sb1 + j * 256 + 128 * g + 64 * c);
+          const float4* b4 = reinterpret_cast<const float4*>(sb1 + j * 256 + 128 * g + 32 * c);
+          uint32_t hpk[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {                         // packed fp32 adds, ReLU folded into the bf16x2 conversion
-            const float4 bb = b4[i], bc = b4[8 + i];
-            const float2 a0 = add_f32x2(make_float2(v0[4 * i], v0[4 * i + 1]), make_float2(bb.x, bb.y));
-            const float2 a1 = add_f32x2(make_float2(v0[4 * i + 2], v0[4 * i + 3]), make_float2(bb.z, bb.w));
-            const float2 c0 = add_f32x2(make_float2(v1[4 * i], v1[4 * i + 1]), make_float2(bc.x, bc.y));
-            const float2 c1 = add_f32x2(make_float2(v1[4 * i + 2], v1[4 * i + 3]), make_float2(bc.z, bc.w));
-            hpk[32 * c + 2 * i] = pack_bf16x2_relu(a0.x, a0.y);
-            hpk[32 * c + 2 * i + 1] = pack_bf16x2_relu(a1.x, a1.y);
-            hpk[32 * c + 16 + 2 * i] = pack_bf16x2_relu(c0.x, c0.y);
-            hpk[32 * c + 16 + 2 * i + 1] = pack_bf16x2_relu(c1.x, c1.y);
+          for (int i = 0; i < 8; ++i) {                           // packed fp32 adds, ReLU folded into the bf16x2 conversion
+            const float4 bb = b4[i];
+            const float2 a0 = add_f32x2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(bb.x, bb.y));
+            const float2 a1 = add_f32x2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(bb.z, bb.w));
+            hpk[2 * i] = pack_bf16x2_relu(a0.x, a0.y);
+            hpk[2 * i + 1] = pack_bf16x2_relu(a1.x, a1.y);
           }
+          tmem_st16u(t_s + 16 * c, hpk);                           // columns [16c, 16c + 16) <= the columns already read
         }
-        tmem_st32u(t_s, *reinterpret_cast<const uint32_t(*)[32]>(&hpk[0]));
-        tmem_st32u(t_s + 32, *reinterpret_cast<const uint32_t(*)[32]>(&hpk[32]));
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(&h_ready[0], 0);
+        AXVS_TRACE(trc_, tb_ + 4 * j + 2)
+        // NJ is a runtime value: spell the four batches out so that t[][] keeps compile-time indices (registers, not local memory)
+        if (j == NJ - 4) load_resid(0);
+        else if (j == NJ - 3) load_resid(1);
+        else if (j == NJ - 2) load_resid(2);
+        else if (j == NJ - 1) load_resid(3);
+      }
+      if (NJ < 4) {                                                // fewer chunks than batches: the rest now
+        if (NJ < 2) load_resid(2);
+        if (NJ < 3) load_resid(1);
+        if (NJ < 4) load_resid(0);
       }
       // ---- final: t = acc2 + b2 + s, LayerNorm2, store.  Rows are one-per-thread in TMEM; a per-warp transpose through
       // shared memory (h_buf is idle: every GEMM 2 of this tile has retired) makes the global traffic row-segment
       // coalesced.  In the transposed domain lane (sub, piece) owns 4 columns of rows {4*i + sub}.
       // The residual (s + b2) is fetched BEFORE waiting for the accumulator so its latency hides behind the last GEMMs.
-      const int row0 = tile * 128 + wq * 32;
-      float4 t[4][8];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int col = 128 * g + 32 * c + piece * 4;
-        const float4 bb = *reinterpret_cast<const float4*>(sb2 + col);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = row0 + i * 4 + sub;
-          float4 sres = (r < p.rows) ? __ldg(reinterpret_cast<const float4*>(p.s32 + (size_t)r * 256 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          t[c][i] = make_float4(sres.x + bb.x, sres.y + bb.y, sres.z + bb.z, sres.w + bb.w);
-        }
-      }
+      AXVS_TRACE(trc_, tb_ + 40)
       mbar_wait_cluster(acc_full, it & 1);
+      AXVS_TRACE(trc_, tb_ + 41)
       tc_fence_after();
       float ps[8], pq[8];
 #pragma unroll
@@ -159,18 +171,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FF_THREADS, 1) ffn_n
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster_relaxed(acc_free, 0);
+            AXVS_TRACE(trc_, tb_ + 42)
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
         }
         __syncwarp();
+        const float4 bb2 = *reinterpret_cast<const float4*>(sb2 + 128 * g + 32 * c + piece * 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + sub;
           const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((piece ^ (rl & 7)) << 4));
           float4 tv = t[c][i];
-          tv.x += a.x; tv.y += a.y; tv.z += a.z; tv.w += a.w;
+          tv.x = (tv.x + bb2.x) + a.x; tv.y = (tv.y + bb2.y) + a.y; tv.z = (tv.z + bb2.z) + a.z; tv.w = (tv.w + bb2.w) + a.w;
           t[c][i] = tv;
           ps[i] += tv.x + tv.y + tv.z + tv.w;
           pq[i] += tv.x * tv.x + tv.y * tv.y + tv.z * tv.z + tv.w * tv.w;
@@ -212,6 +226,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FF_THREADS, 1) ffn_n
           }
         }
       }
+      AXVS_TRACE(trc_, tb_ + 43)
     }
   } else {
     setmaxnreg_dec<56>();
@@ -315,13 +330,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FF_THREADS, 1) ffn_n
         __syncwarp();
       };
       for (int pt = pair; pt < pair_tiles; pt += npairs, ++it) {
+        const bool trc_ = it == 3 && lane == 0;
+        AXVS_TRACE(trc_, 0)
         gemm1(0);
+        AXVS_TRACE(trc_, 1)
 #pragma unroll 1
         for (int j = 0; j < NJ; ++j) {
           // GEMM 2, K-chunk j: acc2 += h (128 x 256, bf16 pairs in TMEM) * W2[:, 256 j : 256 (j + 1)]^T
           const uint32_t hc = it * NJ + j;
+          AXVS_TRACE(trc_, 10 + 4 * j)
           if (j == 0) mbar_wait_cluster(acc_free, (it & 1) ^ 1);   // previous tile's final epilogue has drained acc2
           mbar_wait_cluster(&h_ready[0], hc & 1);
+          AXVS_TRACE(trc_, 11 + 4 * j)
           tc_fence_after();
 #pragma unroll 1
           for (int u = 0; u < 4; ++u) {
@@ -332,7 +352,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FF_THREADS, 1) ffn_n
                                     &w_empty[ws], (u == 3 && j == NJ - 1) ? acc_full : nullptr);
           }
           // the stage is overwritten only after GEMM 2 (j) above: the tensor pipe executes in issue order
+          AXVS_TRACE(trc_, 12 + 4 * j)
           if (j + 1 < NJ) gemm1(j + 1);
+          AXVS_TRACE(trc_, 13 + 4 * j)
         }
         a_cnt += 4;
       }
