@@ -21,6 +21,9 @@
 
 namespace axvs {
 
+#ifndef TP_PREFETCH
+#define TP_PREFETCH 1
+#endif
 constexpr int TP_A_SLOTS = 6;
 constexpr int TP_W_SLOTS = 5;                   // half units
 constexpr int TP_WH = 16384;                    // half a weight unit: [2 K-blocks][64 rows x 128 B]
@@ -79,6 +82,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
   uint64_t* s_empty = s_full + 2;                // [2]  (the leader's copy is the live one)
   uint64_t* o_ready = s_empty + 2;               //      (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 1);
+  volatile uint32_t* tile_flag = tmem_slot + 2;     // tiles whose frames phase has started (paces the residual prefetcher, warp 11)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,6 +96,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
     for (int i = 0; i < TP_W_SLOTS; ++i) { mbar_init(&w_full[i], fullc); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
     mbar_init(o_ready, 16);
+    *tile_flag = 0;
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 256; i += TF_THREADS) { sb_pq[i] = p.b_pq[i]; sb_v2[i] = p.b_v2[i]; }
@@ -142,6 +147,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&s_empty[g], 0);
       AXVS_TRACE(trc_, tb_ + 2)
+#if TP_PREFETCH
+      if (warp == 0 && lane == 0) *tile_flag = it + 1;          // the frames phase of this tile starts: ~10 k clk until the residual is needed
+#endif
 
       float m_run[4], l_run[4], o[4][32];
 #pragma unroll
@@ -399,6 +407,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) push(p.w_proj, u);
       }
+#if TP_PREFETCH
+    } else if (warp == 11 && p.resid != nullptr) {
+      // =============================================================== residual prefetcher: pulls the tile's 128 fp32 rows into L2 while the
+      // frames are computed, so that the epilogue's loads in front of GEMM 3 are L2 hits (no registers or shared memory needed)
+      uint32_t it = 0;
+      for (int pt = pair; pt < pair_tiles; pt += npairs, ++it) {
+        const int tile = 2 * pt + (int)rank;
+        while (*tile_flag < it + 1) __nanosleep(200);
+#pragma unroll 1
+        for (int rr = lane; rr < 128; rr += 32) {
+          const int r = tile * 128 + rr;
+          if (r < p.rows) {
+            const char* src = reinterpret_cast<const char*>(p.resid + (size_t)pass_to_canonical(r, p.map_mode, p.dims) * 256);
+#pragma unroll
+            for (int l = 0; l < 8; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128 * l));
+          }
+        }
+      }
+#endif
     } else if (warp == 10 && rank != 0) {
       // =============================================================== relay (non-leader): forward my full barriers to the leader,
       // in the order the leader consumes them
