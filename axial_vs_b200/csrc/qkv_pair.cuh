@@ -64,15 +64,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
     for (int pt = pair; pt < pair_tiles; pt += npairs) {
       const int tile = 2 * pt + (int)rank;                     // may be == p.tiles (odd tile count): every row masked
       const int row0 = tile * 128 + (warp & 3) * 32;           // first row of this warp
-      uint32_t um_q = 0, um_k = 0, pos_q = 0, pos_k = 0;       // unit-major: rows of q / k of row (row0 + lane) for head 0 (v = k + n), positions inside the region
+      // unit-major destinations of the FOUR rows this lane stores after the transpose (rows 8 i + lane / 4 of the warp's 32), for head 0:
+      // region row of q and of k (v = k + n).  Computed once per tile; the single-CTA kernel fetches them from the owner lane with two
+      // shuffles per store, which made the epilogue (the bottleneck of this kernel) 8 shared-memory-pipe instructions per head longer.
+      uint32_t seq4[4], pos_q4[4], pos_k4[4];                  // first region row of the sequence (head 0), position of the q / k row inside the region
       if (p.swz_N > 0) {
-        const int r = row0 + lane;
-        const int seq = r / p.swz_N, i = r - seq * p.swz_N;
-        const int f = i / p.swz_n, j = i - f * p.swz_n;
-        pos_q = (uint32_t)i;
-        pos_k = (uint32_t)(p.swz_N + 2 * f * p.swz_n + j);
-        um_q = (uint32_t)seq * 24u * p.swz_N + pos_q;
-        um_k = (uint32_t)seq * 24u * p.swz_N + pos_k;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = row0 + 8 * i + (lane >> 2);
+          const int seq = r / p.swz_N, ii = r - seq * p.swz_N;
+          const int f = ii / p.swz_n, j = ii - f * p.swz_n;
+          seq4[i] = (uint32_t)seq * 24u * p.swz_N;
+          pos_q4[i] = (uint32_t)ii;
+          pos_k4[i] = (uint32_t)(p.swz_N + 2 * f * p.swz_n + j);
+        }
       }
 #pragma unroll 1
       for (int rt = 0; rt < 6; ++rt, ++cnt) {
@@ -113,14 +118,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
           {
             const int which = rt >> 1, head = (rt & 1) * 4 + c;
             if (p.swz_N > 0) {
-              const uint32_t my_row = (which == 0 ? um_q : um_k + (which == 2 ? p.swz_n : 0)) + (uint32_t)head * 3u * p.swz_N;
-              const uint32_t my_key = ((which == 0 ? pos_q : pos_k + (which == 2 ? p.swz_n : 0)) >> 1) & 3u;
+              const uint32_t head_off = (uint32_t)head * 3u * p.swz_N;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int rl = 8 * i + (lane >> 2), piece = lane & 3;
                 const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((piece ^ ((rl >> 1) & 3)) << 4));
-                const uint32_t drow = __shfl_sync(0xffffffffu, my_row, rl), key = __shfl_sync(0xffffffffu, my_key, rl);
-                if (row0 + rl < p.rows) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.qkv) + (size_t)drow * 64 + ((piece ^ key) << 4)) = u;
+                const uint32_t pos = which == 0 ? pos_q4[i] : pos_k4[i] + (which == 2 ? (uint32_t)p.swz_n : 0u);
+                const uint32_t key = (pos >> 1) & 3u;
+                if (row0 + rl < p.rows)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.qkv) + (size_t)(seq4[i] + pos + head_off) * 64 + ((piece ^ key) << 4)) = u;
               }
             } else {
             uint8_t* dst = reinterpret_cast<uint8_t*>(p.qkv + ((size_t)(which * 8 + head) * p.rows + row0) * 32);
