@@ -42,7 +42,10 @@ struct AttnTcParams {
   uint8_t* xd_img;            // [tiles][4][16 KiB]
   int tiles, N, n, F, NP, QB; // QB = query blocks per sequence
   int FC, NCH;                // frames per chunk, chunks per item (NCH = ceil(F / FC))
-  int G, buf_cols;            // softmax groups = TMEM buffers, columns per buffer (>= FC * (NP + 32))
+  int G, buf_cols;            // softmax groups = TMEM buffers, columns per buffer
+  int p_stride, o_off;        // buffer layout: S_j at j NP (fp32 scores); P_j (bf16 pairs) at j p_stride; O_j at o_off + 32 j.  Plain: p_stride = NP
+                              // (P_j in place over S_j), o_off = FC NP.  Compact: p_stride = NP / 2, o_off = FC NP / 2 rounded up to 32 -- the
+                              // outputs land on score columns that are dead by then, 128 columns hold two frames of 48 keys (4 groups, not 3)
   int num_units;              // num_seq * 8 * QB * NCH
   int slots, slot_bytes;      // shared-memory ring
   int single;                 // 1: a unit is a whole (sequence, head) region -> one bulk copy
@@ -98,7 +101,7 @@ __device__ __forceinline__ AtUnit at_decode(int unit, const AttnTcParams& p) {
 // One frame's softmax for this thread's query row.  NT16 > 0: the score row (NP = 16 * NT16 <= 64 columns) is held in registers
 // (one TMEM round trip; NP <= 96); NT16 == 0: two passes over 32-column pieces with prefetch (any NP).  Returns the row sum of the probabilities.
 template <int NT16>
-__device__ __forceinline__ float at_softmax_frame(uint32_t t_s, int NP, int n, float sc) {
+__device__ __forceinline__ float at_softmax_frame(uint32_t t_s, uint32_t t_p, int NP, int n, float sc) {
   float sum = 0.f;
   if constexpr (NT16 > 0) {
     float v[NT16][16];
@@ -129,7 +132,7 @@ __device__ __forceinline__ float at_softmax_frame(uint32_t t_s, int NP, int n, f
         sum2 = add_f32x2(sum2, e);
         pk[i] = pack_bf16x2(e.x, e.y);
       }
-      tmem_st8u(t_s + 8 * c, pk);
+      tmem_st8u(t_p + 8 * c, pk);                              // every score of the frame is in registers: any column at or below t_s + NP is free
     }
     sum = sum2.x + sum2.y;
   } else {
@@ -225,7 +228,7 @@ __device__ __forceinline__ float at_softmax_frame(uint32_t t_s, int NP, int n, f
 constexpr int AT_MAX_FC = 4;   // frames per chunk the epilogue keeps row sums for
 
 template <int NT16>
-__global__ void __launch_bounds__((NT16 == 1 || NT16 == 2) ? 128 * 4 + 96 : (NT16 == 5 || NT16 == 6) ? 128 * 2 + 96 : 128 * 3 + 96, 1) spatial_attn_tc_kernel(const AttnTcParams p) {
+__global__ void __launch_bounds__((NT16 >= 1 && NT16 <= 3) ? 128 * 4 + 96 : (NT16 == 5 || NT16 == 6) ? 128 * 2 + 96 : 128 * 3 + 96, 1) spatial_attn_tc_kernel(const AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* ring = smem;
@@ -274,13 +277,13 @@ __global__ void __launch_bounds__((NT16 == 1 || NT16 == 2) ? 128 * 4 + 96 : (NT1
       const int head = u.sh & 7;
       const size_t seq_row0 = (size_t)(u.sh >> 3) * N;
       const uint32_t par = use & 1;
-      const uint32_t t_o = t_buf + u.fc * NP;
+      const uint32_t t_o = t_buf + p.o_off;
       AXVS_PROF_WAIT(0, mbar_wait(&s_full[g], par))
       tc_fence_after();
       float inv[AT_MAX_FC];
 #pragma unroll
       for (int j = 0; j < AT_MAX_FC; ++j)
-        if (j < u.fc) inv[j] = at_softmax_frame<NT16>(t_buf + j * NP, NP, n, sc);
+        if (j < u.fc) inv[j] = at_softmax_frame<NT16>(t_buf + j * NP, t_buf + j * p.p_stride, NP, n, sc);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__((NT16 == 1 || NT16 == 2) ? 128 * 4 + 96 : (NT1
 #pragma unroll 1
         for (int j = 0; j < u.fc; ++j) {
           const uint32_t v_lo = (((v_base + 2 * j * n * 64) & 0x3FFFFu) >> 4) | (64u << 16);
-          const uint32_t t_d = t_p + u.fc * NP + 32 * j, t_a = t_p + j * NP;
+          const uint32_t t_d = t_p + p.o_off + 32 * j, t_a = t_p + j * p.p_stride;
           const bool last = j == u.fc - 1;
           if constexpr (NT16 > 0) {
             if (elect_one()) {

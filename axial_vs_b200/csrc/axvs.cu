@@ -509,20 +509,25 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       ap.tiles = tiles; ap.N = N; ap.n = n; ap.F = F; ap.NP = nt16_f * 16; ap.QB = (N + 127) / 128;
       ap.scale_log2e = kScaleLog2e;
       // softmax groups (= TMEM buffers) and frames per unit: the most groups that still take two frames per unit
-      const int max_g = nt16_f <= 2 ? 4 : (nt16_f == 5 || nt16_f == 6) ? 2 : 3;   // register budget of the softmax warps (launch bounds per NT16)
+      const int max_g = nt16_f <= 3 ? 4 : (nt16_f == 5 || nt16_f == 6) ? 2 : 3;   // register budget of the softmax warps (launch bounds per NT16)
+      // columns one unit of fc frames needs in its TMEM buffer.  Single-pass softmax (1 <= nt16 <= 6: the frame's scores are all in registers
+      // before the probabilities are written) allows the compact layout: P_j packed at j NP / 2, O behind them on dead score columns.
+      const bool compact = nt16_f >= 1 && nt16_f <= 6;
+      auto o_off_of = [&](int fc) { return compact ? (fc * ap.NP / 2 + 31) / 32 * 32 : fc * ap.NP; };
+      auto cols_of = [&](int fc) { const int a = fc * ap.NP, b = o_off_of(fc) + 32 * fc; return a > b ? a : b; };
+      auto fc_fit = [&](int cols) { int fc = 0; while (fc < AT_MAX_FC && fc < F && cols_of(fc + 1) <= cols) ++fc; return fc; };
       int G = 2, FC = 1;
       for (int g = max_g; g >= 2; --g) {
-        const int cols = (512 / g) / 16 * 16;
-        int fc = cols / (ap.NP + 32);
-        if (fc > AT_MAX_FC) fc = AT_MAX_FC;
-        if (fc > F) fc = F;
+        const int cols = (512 / g) / 32 * 32;
+        const int fc = fc_fit(cols);
         if (fc >= (F < 2 ? F : 2) || (g == 2 && fc >= 1)) { G = g; FC = fc; break; }
       }
       if (G == 2 && FC < (F < 2 ? F : 2)) {                       // long frames: one frame per unit, as many groups as fit
         for (int g = max_g; g >= 2; --g)
-          if ((512 / g) / 16 * 16 >= ap.NP + 32) { G = g; FC = 1; break; }
+          if (fc_fit((512 / g) / 32 * 32) >= 1) { G = g; FC = 1; break; }
       }
-      ap.G = G; ap.FC = FC; ap.buf_cols = (512 / G) / 16 * 16; ap.NCH = (F + FC - 1) / FC;
+      ap.G = G; ap.FC = FC; ap.buf_cols = (512 / G) / 32 * 32; ap.NCH = (F + FC - 1) / FC;
+      ap.p_stride = compact ? ap.NP / 2 : ap.NP; ap.o_off = o_off_of(FC);
       ap.single = (ap.QB == 1 && ap.NCH == 1) ? 1 : 0;
       const long long units = (long long)num_seq * 8 * ap.QB * ap.NCH;
       if (units > 0x7fffffff) return fail(AXVS_E_UNSUPPORTED, "traj_attn: too many attention work units (%lld)", units);
