@@ -48,12 +48,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_MATCH, KC_MMHA, KC_KMAXLAYER, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_MATCH, KC_MMHA, KC_KMAXLAYER, KC_TRAJPAIR, KC_QKVPAIR, KC_FFNPAIR, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel", "matching_kernels", "masked_mha_kernels", "kmax_layer_kernels"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel", "matching_kernels", "masked_mha_kernels", "kmax_layer_kernels", "traj_pair_kernel", "qkv_pair_kernel", "ffn_n256_pair_kernel"};
 // Process-wide knobs are atomics (two host threads driving two devices may read / set them concurrently); the profiler's records and
 // the per-device attribute table are guarded by mutexes.  None of them is touched on the launch path beyond one relaxed load.
 std::atomic<int> g_fusion{4};   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
@@ -469,7 +469,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       qp.qkv = ws.qkv; qp.rows = (int)rows; qp.tiles = tiles; qp.map_mode = map; qp.dims = dims;
       if (use_tc) { qp.swz_N = N; qp.swz_n = n; }
       {
-        ProfScope ps(KC_QKVD, 2.0 * rows * 256.0 * 768.0, (double)rows * ((pos ? (dims.pos_mod ? 1024.0 + 1024.0 / B : 2048.0) : 1024.0) + 1536.0), st);
+        ProfScope ps(((g_pair & 4) && tiles >= 2) ? KC_QKVPAIR : KC_QKVD, 2.0 * rows * 256.0 * 768.0, (double)rows * ((pos ? (dims.pos_mod ? 1024.0 + 1024.0 / B : 2048.0) : 1024.0) + 1536.0), st);
         if ((g_pair & 4) && tiles >= 2) {
           const int pair_tiles = (tiles + 1) / 2, max_pairs = d->sms / 2;
           qkv_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), QD_THREADS, QP_SMEM_BYTES, st>>>(qp);
@@ -617,9 +617,10 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
     tp.scale_log2e = kScaleLog2e;
     tp.ln_g = ln_g; tp.ln_b = ln_b; tp.ln_img = ln_img; tp.ln_eps = 1e-5f;
     {
-      ProfScope ps(g_fusion >= 4 ? KC_TRAJTS : KC_TRAJ, 2.0 * rows * 256.0 * 256.0 * (2.0 + 2.0 * F) + 4.0 * rows * F * 256.0,
+      const bool traj_pair = g_fusion >= 4 && (g_pair & 2) && tiles >= 2;
+      ProfScope ps(traj_pair ? KC_TRAJPAIR : g_fusion >= 4 ? KC_TRAJTS : KC_TRAJ, 2.0 * rows * 256.0 * 256.0 * (2.0 + 2.0 * F) + 4.0 * rows * F * 256.0,
                    (double)rows * (512.0 * (F + 1) + 1024.0 + (resid ? 1024.0 : 0.0) + (ln_img ? 1536.0 : 0.0)), st);
-      if (g_fusion >= 4 && (g_pair & 2) && tiles >= 2) {
+      if (traj_pair) {
         const int pair_tiles = (tiles + 1) / 2, max_pairs = d->sms / 2;
         traj_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), TF_THREADS, TP_SMEM_BYTES, st>>>(tp);
       } else if (g_fusion >= 4) traj_ts_kernel<<<tiles < d->sms ? tiles : d->sms, TF_THREADS, TT_SMEM_BYTES, st>>>(tp);
@@ -740,7 +741,7 @@ int ffn_fused_launch(const uint8_t* s_img, const float* s32, float* out, const a
   fp.rows = rows; fp.tiles = (rows + 127) / 128; fp.d_ffn = w->d_ffn; fp.eps = 1e-5f;
   {
     const bool n256 = !(g_pair & 1) && g_fusion >= 4 && w->w_ffn1_n && w->d_ffn % 256 == 0;
-    ProfScope ps(n256 ? KC_FFN256 : KC_FFN, 4.0 * rows * 256.0 * w->d_ffn, (double)rows * 256 * 10.0, st);
+    ProfScope ps(n256 ? (((g_pair & 8) && fp.tiles >= 2) ? KC_FFNPAIR : KC_FFN256) : KC_FFN, 4.0 * rows * 256.0 * w->d_ffn, (double)rows * 256 * 10.0, st);
     if (g_pair & 1) {
       const int pair_tiles = (fp.tiles + 1) / 2, max_pairs = d->sms / 2;
       ffn_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), FF_THREADS, FP_SMEM_BYTES, st>>>(fp);

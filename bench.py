@@ -582,7 +582,7 @@ def main():
                    for k, v in prof.items() if v["timed"]}
         achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["flops"] > 0 else dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
         tensor_bound = dom["flops"] > 0 and dom_name in ("gemm_bf16_kernel", "spatial_attn_kernel", "spatial_attn_v2_kernel", "traj_fused_kernel",
-                                                          "traj_ts_kernel", "ffn_fused_kernel", "ffn_n256_kernel", "qkv_fused_kernel", "qkv_direct_kernel")
+                                                          "traj_ts_kernel", "ffn_fused_kernel", "ffn_n256_kernel", "qkv_fused_kernel", "qkv_direct_kernel", "traj_pair_kernel", "qkv_pair_kernel", "ffn_n256_pair_kernel")
         # the dominant kernel is event-timed launch by launch in a short pass at full clocks -> the BURST figure is its peak; the whole
         # step runs for seconds under the power cap -> its fraction is quoted against both
         peak = peaks["tf_burst"] if tensor_bound else peaks["hbm"]

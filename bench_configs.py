@@ -75,7 +75,7 @@ def _roofline(prof, prof_steps, peaks, step_flops, ms_per_step):
                    "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 and v["flops"] > 0 else None,
                    "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None} for k, v in timed.items()}
     tensor_bound = dom["flops"] > 0 and dom_name in ("gemm_bf16_kernel", "traj_ts_kernel", "traj_fused_kernel", "ffn_fused_kernel", "ffn_n256_kernel",
-                                                      "qkv_fused_kernel", "qkv_direct_kernel")
+                                                      "qkv_fused_kernel", "qkv_direct_kernel", "traj_pair_kernel", "qkv_pair_kernel", "ffn_n256_pair_kernel")
     achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if tensor_bound else dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
     peak = peaks["tf_burst"] if tensor_bound else peaks["hbm"]
     step_tf = step_flops / (ms_per_step * 1e-3) / 1e12
