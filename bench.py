@@ -431,11 +431,13 @@ def main():
         return graphs[("out", k & 1)]
 
     # e2e: the same step through the public nn.Module API with HOST buffers.  Three streams pipeline it the way a serving
-    # loop would: H2D of step k+1 and D2H of step k-1 overlap the kernels of step k (double-buffered pinned host + device
-    # staging); every step still moves its own inputs in and its own outputs out inside the timed region.
+    # loop would: H2D of step k+1 and D2H of step k-1 overlap the kernels of step k (NSLOT-deep pinned host + device staging: with
+    # two slots the kernels of step k+2 had to wait for the D2H of step k, which takes about as long as a step -- any slip stalled the
+    # GPU; three slots decouple them); every step still moves its own inputs in and its own outputs out inside the timed region.
+    NSLOT = 3
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    stage_in = [[torch.empty_like(t, device=dev) for t in host_in[0]] for _ in range(2)]
-    host_out2 = [[torch.empty(sh, dtype=hdt).pin_memory() for sh in out_shapes] for _ in range(2)]
+    stage_in = [[torch.empty_like(t, device=dev) for t in host_in[0]] for _ in range(NSLOT)]
+    host_out2 = [[torch.empty(sh, dtype=hdt).pin_memory() for sh in out_shapes] for _ in range(NSLOT)]
 
     def e2e_compute(staged):
         """staged host-dtype inputs -> outputs in the host dtype / read-back shape (conversions and pooling run on the device)."""
@@ -443,16 +445,16 @@ def main():
         if args.d2h == "summary":
             outs = [o.view(clips, -1, 256).mean(1) for o in outs]
         return [o.to(hdt) for o in outs] if hdt != torch.float32 else outs
-    ev_in = [torch.cuda.Event() for _ in range(2)]        # H2D of slot finished
-    ev_used = [torch.cuda.Event() for _ in range(2)]      # compute finished reading slot's staging inputs
-    ev_comp = [torch.cuda.Event() for _ in range(2)]      # compute of slot finished
-    ev_out = [torch.cuda.Event() for _ in range(2)]       # D2H of slot finished
-    e2e_state = {"n": 0, "keep": [None, None]}
+    ev_in = [torch.cuda.Event() for _ in range(NSLOT)]        # H2D of slot finished
+    ev_used = [torch.cuda.Event() for _ in range(NSLOT)]      # compute finished reading slot's staging inputs
+    ev_comp = [torch.cuda.Event() for _ in range(NSLOT)]      # compute of slot finished
+    ev_out = [torch.cuda.Event() for _ in range(NSLOT)]       # D2H of slot finished
+    e2e_state = {"n": 0, "keep": [None] * NSLOT}
     e2e_graphs = {}
 
     def step_e2e(k):
-        slot = e2e_state["n"] & 1
-        first = e2e_state["n"] < 2
+        slot = e2e_state["n"] % NSLOT
+        first = e2e_state["n"] < NSLOT
         e2e_state["n"] += 1
         cur = torch.cuda.current_stream(dev)
         with torch.cuda.stream(s_in):
@@ -464,7 +466,7 @@ def main():
         cur.wait_event(ev_in[slot])
         if args.graph:
             # the kernels of the step replay from a CUDA graph captured on this slot's staging buffers; its output buffers are
-            # rewritten two steps later, after the D2H of this slot has been waited for
+            # rewritten NSLOT steps later, after the D2H of this slot has been waited for
             if not first:
                 cur.wait_event(ev_out[slot])
             g = e2e_graphs.get(slot)
@@ -486,7 +488,7 @@ def main():
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_comp[slot])
             if not first:
-                pass                                   # host_out2[slot] was drained two steps ago (same stream, in order)
+                pass                                   # host_out2[slot] was drained NSLOT steps ago (same stream, in order)
             for o, h in zip(outs, host_out2[slot]):
                 h.copy_(o, non_blocking=True)
                 if not args.graph:
@@ -544,8 +546,9 @@ def main():
             torch.cuda.synchronize()
     pcie = None if args.no_extras else pcie_probe(dev, world, dist)
     resident = step_resident_graph if args.graph else step_resident
-    for k in range(args.warmup):
-        resident(k)
+    for k in range(max(args.warmup, NSLOT)):            # at least one e2e step per slot before the timed region: each slot captures its graph on first use
+        if k < args.warmup:
+            resident(k)
         step_e2e(k)
     e2e_drain()
     torch.cuda.synchronize()
@@ -612,7 +615,7 @@ def main():
                 "dtype": "bf16", "data": "synthetic", "config": workload_config(clips),
                 "e2e": {"value": round(e2e_value, 2), "unit": "clips/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                         "ms_per_step": round(ms_e2e / args.steps, 4),
-                        "how": "nn.Module API, pinned host fp32 in/out every step, H2D / kernels / D2H pipelined on 3 streams" + (", kernels replayed from a CUDA graph" if args.graph else "")},
+                        "how": "nn.Module API, pinned host fp32 in/out every step, H2D / kernels / D2H pipelined on 3 streams over 3 staging slots" + (", kernels replayed from a CUDA graph" if args.graph else "")},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
         if pcie is not None:
             moved = (in_bytes + out_bytes) * n_gpus * args.steps / (ms_e2e * 1e-3) / 1e9
