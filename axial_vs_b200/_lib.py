@@ -82,6 +82,8 @@ SIGNATURES = {
     "axvs_add_act": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
     "axvs_masked_mha_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "axvs_masked_mha_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "axvs_frame_attn_f32_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "axvs_frame_attn_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "axvs_kmeans_update_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "axvs_kmeans_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "axvs_proj_workspace_bytes": (c_size_t, [c_int]),

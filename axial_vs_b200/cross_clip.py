@@ -35,16 +35,59 @@ class TrajectoryAttention(nn.Module):
         self.attn_drop = nn.Dropout(attn_drop)
         self.proj = nn.Linear(d_model, d_model)
         self._cache = _PackedCache()
+        self._cache_split = _PackedCache()
+        self.precision = "bf16"            # "bf16": the fused bf16 kernels (default); "split": fp32-grade products, see _run_split
         self.register_load_state_dict_post_hook(_invalidate_hook)
 
     def packed(self, device) -> ops.PackedTA:
         return self._cache.get(self, device, lambda: ops.pack_ta(dict(self.state_dict())))
+
+    def _packed_split(self, device):
+        def build():
+            C = ops.C
+            wqkv, bqkv = self.qkv.weight.detach().float(), self.qkv.bias.detach().float()
+            wkv, bkv = self.proj_kv.weight.detach().float(), self.proj_kv.bias.detach().float()
+            lin = lambda w, b: (ops.pack_weight_split(w.contiguous()), b.contiguous())
+            return {"q": lin(wqkv[:C], bqkv[:C]), "k": lin(wqkv[C:2 * C], bqkv[C:2 * C]), "v": lin(wqkv[2 * C:], bqkv[2 * C:]),
+                    "pq": lin(self.proj_q.weight.detach().float(), self.proj_q.bias.detach().float()),
+                    "k2": lin(wkv[:C], bkv[:C]), "v2": lin(wkv[C:], bkv[C:]),
+                    "proj": lin(self.proj.weight.detach().float(), self.proj.bias.detach().float())}
+        return self._cache_split.get(self, device, build)
+
+    def _run_split(self, x: Tensor, seq_len: int, num_frames: int, residual: bool) -> Tensor:
+        """The same math (CC:95-130) at fp32-grade accuracy: every Linear as a split-precision GEMM (bf16 hi / lo operands, three tensor-core
+        products: axvs_linear_f32), both attentions in fp32 on the masked-attention kernel (per-frame softmax = key splits on the frames;
+        attention over the frames = one query with F keys per token).  About 5x the time of the fused bf16 kernels on this small stage;
+        it exists because the final per-pixel argmax over 128 nearly tied query logits resolves below the bf16-compute error
+        (99.85 % label agreement with bf16 attention, >= 99.9 % with this path)."""
+        b, N, C = x.shape
+        F_, n = num_frames, seq_len
+        pk = self._packed_split(x.device)
+        rows = x.contiguous().float().view(b * N, C)
+        lin = lambda a, key, scale=1.0: ops.linear_f32(a, pk[key][0], pk[key][1], C, act=0, split=True, scale=scale)
+        s2 = self.scale * 1.4426950408889634                   # softmax scale and log2(e): the attention kernel works in the exp2 domain
+        q, k, v = lin(rows, "q", s2).view(b, N, C), lin(rows, "k").view(b, N, C), lin(rows, "v").view(b, N, C)
+        xs = ops.frame_attn_f32(q, k, v, F_, heads=self.num_heads)                    # [b, N, F, C]
+        own = (torch.arange(N, device=x.device) // n).view(1, N, 1, 1).expand(b, N, 1, C)
+        x_diag = torch.gather(xs, 2, own).view(b * N, C)                              # the token's own frame (CC:112-114); pure indexing
+        q2 = lin(x_diag, "pq", s2)                                                    # (proj_q(x_diag)) * scale, CC:115-120
+        xf = xs.view(b * N * F_, C)
+        k2, v2 = lin(xf, "k2"), lin(xf, "v2")
+        o = torch.empty(b * N, C, dtype=torch.float32, device=x.device)
+        for r0 in range(0, b * N, 32768):                                             # one "batch element" per token: grid limits
+            r1 = min(b * N, r0 + 32768)
+            o[r0:r1] = ops.masked_mha(q2[r0:r1].view(r1 - r0, 1, C), k2[r0 * F_:r1 * F_].view(r1 - r0, F_, C), v2[r0 * F_:r1 * F_].view(r1 - r0, F_, C),
+                                      None, heads=self.num_heads, seq_first=False, out_dtype=torch.float32).view(r1 - r0, C)
+        out = lin(o, "proj")
+        return (ops.add_act(out, rows, act=0) if residual else out).view(b, N, C)
 
     def _run(self, x: Tensor, seq_len: int, num_frames: int, residual: bool) -> Tensor:
         _require_inference(self, x)
         b, N, C = x.shape
         if N != seq_len * num_frames:
             raise RuntimeError(f"sequence length {N} != seq_len {seq_len} * num_frames {num_frames}")
+        if self.precision == "split":
+            return self._run_split(x, seq_len, num_frames, residual)
         xf = x.contiguous().float().view(b * N, C)
         out = ops.traj_attn_fwd(xf, xf, xf, None, xf if residual else None, self.packed(x.device), b, num_frames, seq_len, 1, ops.AXIS_NONE)
         return out.view(b, N, C)
@@ -258,6 +301,16 @@ class CrossClipTrackingModule(nn.Module):
         # This drop-in keeps them on the GPU by default (postprocess.PanopticPostProcessor consumes them in place); set
         # `outputs_on_cpu = True` for callers that mix the outputs with host tensors.
         self.outputs_on_cpu = False
+
+    def set_precision(self, mode: str) -> "CrossClipTrackingModule":
+        """"bf16" (default): the trajectory attention of the cross-clip layers runs on the fused bf16 kernels; "split": at fp32-grade accuracy
+        (TrajectoryAttention._run_split).  Everything after the attention (temporal ASPP, projections, query x pixel contraction) is
+        split-precision in both modes."""
+        if mode not in ("bf16", "split"):
+            raise ValueError("precision must be 'bf16' or 'split'")
+        for layer in self.transformer_trajectory_self_attention_layers:
+            layer.self_attn.precision = mode
+        return self
 
     def _packed_aspp(self, i, device):
         mods = nn.ModuleList([self.conv_short_aggregate_layers[i], self.conv_norms[i]])

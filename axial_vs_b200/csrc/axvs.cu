@@ -1196,6 +1196,33 @@ int axvs_masked_mha_fwd(const float* q, const float* k, const float* v, const un
   return AXVS_OK;
 }
 
+size_t axvs_frame_attn_f32_workspace_bytes(int B, int heads, int N, int F) {
+  if (B <= 0 || heads <= 0 || N <= 0 || F <= 0) return 0;
+  return (size_t)F * B * heads * N * MM_REC * sizeof(float) + 256;
+}
+
+int axvs_frame_attn_f32(const float* q, const float* k, const float* v, float* x, int B, int heads, int N, int F, int n, void* workspace,
+                        size_t workspace_bytes, axvs_stream_t stream) {
+  if (!q || !k || !v || !x || !workspace) return fail(AXVS_E_INVALID, "frame_attn_f32: null pointer");
+  if (B <= 0 || heads <= 0 || N <= 0 || F <= 0 || n <= 0 || N != F * n) return fail(AXVS_E_INVALID, "frame_attn_f32: N must equal F * n");
+  const int qb = (N + MM_THREADS - 1) / MM_THREADS;
+  if (heads > 65535 || (long long)B * qb > 65535) return fail(AXVS_E_UNSUPPORTED, "frame_attn_f32: grid limits");
+  if (workspace_bytes < axvs_frame_attn_f32_workspace_bytes(B, heads, N, F)) return fail(AXVS_E_INVALID, "frame_attn_f32: workspace too small");
+  MaskedMhaParams mp;
+  mp.q = q; mp.k = k; mp.v = v; mp.mask = nullptr;
+  mp.partial = reinterpret_cast<float*>(workspace);
+  mp.B = B; mp.H = heads; mp.Nq = N; mp.L = N; mp.keys_per_cta = n; mp.qblocks = qb; mp.seq_first = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    ProfScope ps(KC_MMHA, 4.0 * B * heads * (double)N * N * MM_D, (double)B * N * heads * MM_D * 4.0 * (3.0 + F), st);
+    masked_mha_partial_kernel<<<dim3(F, heads, B * qb), MM_THREADS, 0, st>>>(mp);
+    const long long total = (long long)F * B * heads * N * MM_D;
+    masked_mha_per_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mp.partial, x, F, B, heads, N);
+  }
+  AXVS_CHECK_LAUNCH("frame_attn_f32 kernels");
+  return AXVS_OK;
+}
+
 static int kmeans_chunks(int N, int M) {   // pixel chunks per clip: about two waves of CTAs over the 148 SMs
   const int tiles = (M + KM_PT - 1) / KM_PT;
   int chunks = (2 * 148) / N;

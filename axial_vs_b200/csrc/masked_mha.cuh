@@ -141,6 +141,23 @@ __global__ void __launch_bounds__(MM_THREADS) masked_mha_partial_kernel(const Ma
   }
 }
 
+// Per-split outputs instead of a combination: x[b, i, s, h*32 + c] = o_s[c] / l_s -- with the key splits placed on the FRAMES of a sequence
+// (keys_per_cta = keys per frame) this is the per-frame-softmax spatial attention of TrajectoryAttention in fp32 (CC:104-110,
+// WC/temporal_attention.py:47-60), used by the split-precision cross-clip path.  out [B, Nq, splits, H*32] (batch-first).
+__global__ void __launch_bounds__(256) masked_mha_per_split_kernel(const float* __restrict__ partial, float* __restrict__ out, int splits, int B, int H, int Nq) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)splits * B * H * Nq * MM_D;
+  if (idx >= total) return;
+  const int c = (int)(idx % MM_D);
+  long long r = idx / MM_D;
+  const int qi = (int)(r % Nq); r /= Nq;
+  const int h = (int)(r % H); r /= H;
+  const int b = (int)(r % B);
+  const int s = (int)(r / B);
+  const float* rec = partial + ((((size_t)s * B + b) * H + h) * Nq + qi) * MM_REC;
+  out[(((size_t)b * Nq + qi) * splits + s) * (size_t)(H * MM_D) + h * MM_D + c] = __ldg(rec + 2 + c) / __ldg(rec + 1);
+}
+
 // out[b, i, h*32 + c] = sum_s o_s[c] 2^(m_s - M) / sum_s l_s 2^(m_s - M), M = max_s m_s; one thread per (b, h, i, c).  A row whose keys are
 // ALL blocked gives 0 / 0 = NaN exactly like torch.nn.MultiheadAttention (the caller un-blocks such rows first, cc head :877-879).
 __global__ void __launch_bounds__(256) masked_mha_combine_kernel(const float* __restrict__ partial, float* __restrict__ out32, __nv_bfloat16* __restrict__ out16,

@@ -506,14 +506,14 @@ def linear_act(a: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Ten
 
 
 def linear_f32(a: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], n_out: int, act: int = 0, split: bool = True,
-               out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
-    """act(a W^T + bias) on fp32 rows a [M, K]; split=True: w_packed from `pack_weight_split`, fp32-grade product (axvs_linear_f32)."""
+               out_dtype: torch.dtype = torch.float32, scale: float = 1.0) -> torch.Tensor:
+    """act((a W^T + bias) * scale) on fp32 rows a [M, K]; split=True: w_packed from `pack_weight_split`, fp32-grade product (axvs_linear_f32)."""
     _check(a, "a", torch.float32)
     M, K = a.shape
     out = torch.empty(M, n_out, dtype=out_dtype, device=a.device)
     lib = _lib.load()
     with torch.cuda.device(a.device):
-        rc = lib.axvs_linear_f32(a.data_ptr(), K, M, K, w_packed.data_ptr(), int(split), _ptr(bias), n_out, 1.0, int(act), out.data_ptr(), n_out,
+        rc = lib.axvs_linear_f32(a.data_ptr(), K, M, K, w_packed.data_ptr(), int(split), _ptr(bias), n_out, float(scale), int(act), out.data_ptr(), n_out,
                                  int(out_dtype == torch.bfloat16), _stream(a.device))
     _lib.check(rc, "axvs_linear_f32")
     return out
@@ -769,6 +769,23 @@ def masked_mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: Optional
                                      _stream(q.device))
     _lib.check(rc, "axvs_masked_mha_fwd")
     return out
+
+
+def frame_attn_f32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, F: int, heads: int = 8) -> torch.Tensor:
+    """Per-frame-softmax attention in fp32: q (pre-scaled by head_dim^-0.5 * log2 e), k, v [B, N, heads*32], N = F * n -> x [B, N, F, heads*32]."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _check(t, nm, torch.float32, tuple(q.shape))
+    B, N, Cc = q.shape
+    if Cc != heads * 32 or N % F:
+        raise RuntimeError("frame_attn_f32: expected [B, F*n, heads*32]")
+    x = torch.empty(B, N, F, Cc, dtype=torch.float32, device=q.device)
+    lib = _lib.load()
+    nbytes = lib.axvs_frame_attn_f32_workspace_bytes(B, heads, N, F)
+    ws = workspace(nbytes, q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(lib.axvs_frame_attn_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(), x.data_ptr(), B, heads, N, F, N // F, ws.data_ptr(), nbytes,
+                                           _stream(q.device)), "axvs_frame_attn_f32")
+    return x
 
 
 def kmeans_update(mask_logits: torch.Tensor, pixel_value: torch.Tensor, advanced: bool = False,

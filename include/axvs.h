@@ -242,6 +242,14 @@ size_t axvs_masked_mha_workspace_bytes(int B, int heads, int Nq, int L);
 int axvs_masked_mha_fwd(const float* q, const float* k, const float* v, const unsigned char* mask, float* out32, void* out16_bf16, int B, int heads,
                         int Nq, int L, int seq_first, void* workspace, size_t workspace_bytes, axvs_stream_t stream);
 
+/* Per-frame-softmax spatial attention of TrajectoryAttention in fp32 (split-precision cross-clip path; CC:104-110 = WC/temporal_attention.py:47-60):
+ *   x[b, i, f, h*32 + :] = softmax_j( q[b, i, h] . k[b, f*n + j, h] ) @ v[b, f*n + j, h],  j over the n keys of frame f
+ * q (pre-scaled by head_dim^-0.5 * log2 e), k, v fp32 [B, N, heads*32] with N = F * n; x fp32 [B, N, F, heads*32].
+ * Runs on the masked-attention kernel with the key splits placed on the frames. */
+size_t axvs_frame_attn_f32_workspace_bytes(int B, int heads, int N, int F);
+int axvs_frame_attn_f32(const float* q, const float* k, const float* v, float* x, int B, int heads, int N, int F, int n, void* workspace,
+                        size_t workspace_bytes, axvs_stream_t stream);
+
 /* k-means cross-attention update (DEC:196-208): assign[n, m] = argmax_l mask_logits[n, l, m] (first maximum),
  * out[n, d, l] = sum over the pixels assigned to l of pixel_value[n, d, m]; divided by max(count, 1) when advanced != 0
  * (advanced_kmax, DEC:206-208).  mask_logits fp32 [N, L, M], pixel_value fp32 [N, 256, M], out fp32 [N, 256, L], L <= 128;
