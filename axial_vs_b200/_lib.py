@@ -87,8 +87,8 @@ SIGNATURES = {
     "axvs_kmeans_update_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "axvs_kmeans_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "axvs_proj_workspace_bytes": (c_size_t, [c_int]),
-    "axvs_input_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
-    "axvs_output_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    "axvs_input_proj_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    "axvs_output_proj_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "axvs_msda_layer_workspace_bytes": (c_size_t, [c_int, c_int]),
     "axvs_msda_layer_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, POINTER(c_int), c_void_p, POINTER(MsdaWeights), c_int, c_int, c_void_p, c_size_t,
                                     c_void_p]),

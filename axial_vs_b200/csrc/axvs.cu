@@ -1274,29 +1274,33 @@ size_t axvs_proj_workspace_bytes(int images) {
 }
 
 int axvs_input_proj_fwd(const float* x_nchw, const void* w_packed, const float* bias, const float* gn_w, const float* gn_b, float* out_tokens,
-                        int images, int c_in, int hw, float eps, void* workspace, size_t workspace_bytes, axvs_stream_t stream) {
+                        long long out_image_stride, int images, int c_in, int hw, float eps, void* workspace, size_t workspace_bytes,
+                        axvs_stream_t stream) {
   if (!x_nchw || !w_packed || !gn_w || !gn_b || !out_tokens) return fail(AXVS_E_INVALID, "input_proj: null pointer");
   if (images <= 0 || c_in <= 0 || hw <= 0) return fail(AXVS_E_INVALID, "input_proj: sizes must be positive");
   if (c_in % 64) return fail(AXVS_E_UNSUPPORTED, "input_proj: the channel count must be a multiple of 64 (got %d)", c_in);
   if ((long long)images * hw > 0x7fffffffLL) return fail(AXVS_E_UNSUPPORTED, "input_proj: too many pixels");
+  if (out_image_stride == 0) out_image_stride = (long long)hw * 256;
+  if (out_image_stride < (long long)hw * 256 || (out_image_stride & 3)) return fail(AXVS_E_INVALID, "input_proj: bad output image stride");
   const size_t need = axvs_proj_workspace_bytes(images);
   if (!workspace || workspace_bytes < need) return fail(AXVS_E_WORKSPACE, "input_proj: workspace of %zu bytes required (got %zu)", need, workspace_bytes);
   const int M = images * hw;
   GemmParams p = gemm_params(nullptr, c_in, M, c_in, w_packed, 256, 0, bias, 256, 1.f, 0, out_tokens, 256, 0, 0, nullptr);
   p.a_diag = 3; p.A32 = x_nchw; p.a_n = hw;
+  if (out_image_stride != (long long)hw * 256) { p.out_img_rows = hw; p.out_img_stride = out_image_stride; }
   if (int rc = launch_gemm(p, (cudaStream_t)stream)) return rc;
   float2* partial = reinterpret_cast<float2*>(workspace);
   {
     ProfScope ps(KC_GN, 0, (double)M * 256 * 12.0, (cudaStream_t)stream);
-    gn_tokens_stats_kernel<<<dim3(GN_CHUNKS, images), 256, 0, (cudaStream_t)stream>>>(out_tokens, partial, hw);
-    gn_tokens_apply_kernel<<<dim3(GN_CHUNKS, images), 256, 0, (cudaStream_t)stream>>>(out_tokens, partial, gn_w, gn_b, hw, eps);
+    gn_tokens_stats_kernel<<<dim3(GN_CHUNKS, images), 256, 0, (cudaStream_t)stream>>>(out_tokens, partial, hw, out_image_stride);
+    gn_tokens_apply_kernel<<<dim3(GN_CHUNKS, images), 256, 0, (cudaStream_t)stream>>>(out_tokens, partial, gn_w, gn_b, hw, eps, out_image_stride);
   }
   AXVS_CHECK_LAUNCH("gn_tokens kernels");
   return AXVS_OK;
 }
 
-int axvs_output_proj_fwd(const float* tokens, const void* w_packed, const float* bias, const float* gn_w, const float* gn_b, float* out_nchw,
-                         int images, int c_out, int hw, float eps, axvs_stream_t stream) {
+int axvs_output_proj_fwd(const float* tokens, long long tokens_image_stride, const void* w_packed, const float* bias, const float* gn_w,
+                         const float* gn_b, float* out_nchw, int images, int c_out, int hw, float eps, axvs_stream_t stream) {
   if (!tokens || !w_packed || !gn_w || !gn_b || !out_nchw) return fail(AXVS_E_INVALID, "output_proj: null pointer");
   if (images <= 0 || c_out <= 0 || hw <= 0) return fail(AXVS_E_INVALID, "output_proj: sizes must be positive");
   if (c_out % 32) return fail(AXVS_E_UNSUPPORTED, "output_proj: the channel count must be a multiple of 32 (GroupNorm(32); got %d)", c_out);
@@ -1305,6 +1309,10 @@ int axvs_output_proj_fwd(const float* tokens, const void* w_packed, const float*
   const int n_pad = (c_out + 255) / 256 * 256;          // the GEMM works on 256-column chunks: weight rows / bias are zero-padded by the caller
   GemmParams p = gemm_params(nullptr, 256, M, 256, w_packed, n_pad, 0, bias, n_pad, 1.f, 0, out_nchw, n_pad, 0, 0, nullptr);
   p.a_diag = 4; p.A32 = tokens; p.out_nchw = hw; p.out_ch = c_out;
+  if (tokens_image_stride != 0 && tokens_image_stride != (long long)hw * 256) {
+    if (tokens_image_stride < (long long)hw * 256 || (tokens_image_stride & 3)) return fail(AXVS_E_INVALID, "output_proj: bad token image stride");
+    p.a_img_rows = hw; p.a_img_stride = tokens_image_stride;
+  }
   if (n_pad != c_out) p.n_valid = c_out;
   if (int rc = launch_gemm(p, (cudaStream_t)stream)) return rc;
   {

@@ -110,6 +110,10 @@ struct GemmParams {
   int map_mode;         // RowMap applied to output (and residual) rows
   AxialDims dims;
   int out_ch;           // NCHW outputs: channels of the output tensor (0 = n_out); smaller than n_out when n_out is padded to 256 (n_valid)
+  int a_img_rows;       // mode 4, > 0: logical row r lives at A32 + (r / a_img_rows) * a_img_stride + (r % a_img_rows) * lda (one pyramid level
+  long long a_img_stride;   //   inside the multi-level token tensor [images, sum(H_l*W_l), 256]: a_img_rows = H_l*W_l, a_img_stride = len * 256)
+  int out_img_rows;     // token-major fp32 outputs, > 0: the same per-image addressing for the output (and residual) rows
+  long long out_img_stride;
   int out_nchw;         // > 0: fp32 output is NCHW [images, out_ch, out_nchw pixels] (Conv2d 1x1 output): row r = image r / out_nchw,
                         //      pixel r % out_nchw; every column is one coalesced 4-byte store per lane (lanes = consecutive pixels)
 };
@@ -173,6 +177,13 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, int row
     *reinterpret_cast<float4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   __syncwarp();
   float4 r[8];
+  auto out_off = [&](int orow) -> size_t {
+    if (p.out_img_rows > 0) {
+      const int img = orow / p.out_img_rows;
+      return (size_t)img * (size_t)p.out_img_stride + (size_t)(orow - img * p.out_img_rows) * p.ldo;
+    }
+    return (size_t)orow * p.ldo;
+  };
   if (p.resid) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -180,7 +191,7 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, int row
       r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row0 + rl < p.M) {
         const int orow = pass_to_canonical(row0 + rl, p.map_mode, p.dims);
-        r[i] = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)orow * p.ldo + p.out_col0 + col) + piece);
+        r[i] = __ldg(reinterpret_cast<const float4*>(p.resid + out_off(orow) + p.out_col0 + col) + piece);
       }
     }
   }
@@ -191,7 +202,7 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmParams& p, int row
     if (p.resid) { u.x += r[i].x; u.y += r[i].y; u.z += r[i].z; u.w += r[i].w; }
     if (row0 + rl < p.M) {
       const int orow = pass_to_canonical(row0 + rl, p.map_mode, p.dims);
-      *(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)orow * p.ldo + p.out_col0 + col) + piece) = u;
+      *(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off(orow) + p.out_col0 + col) + piece) = u;
     }
   }
   __syncwarp();
@@ -345,7 +356,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
           } else {
             const int r = mt * GEMM_BM + (q >> 3);
             if (r < p.M) {
-              const size_t o = (size_t)r * p.lda + kb * GEMM_BK + (q & 7) * 8;
+              size_t o = (size_t)r * p.lda;
+              if (p.a_img_rows > 0) {
+                const int img = r / p.a_img_rows;
+                o = (size_t)img * (size_t)p.a_img_stride + (size_t)(r - img * p.a_img_rows) * p.lda;
+              }
+              o += kb * GEMM_BK + (q & 7) * 8;
               const float4* s = reinterpret_cast<const float4*>(p.A32 + o);
               float4 a = __ldg(s), b = __ldg(s + 1);
               if (p.A32b) {

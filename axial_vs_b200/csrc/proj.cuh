@@ -12,14 +12,15 @@ namespace axvs {
 constexpr int GN_GROUPS = 32;
 constexpr int GN_CHUNKS = 8;          // pixel chunks per image in the token-major statistics pass
 
-// ---- token-major [images, HW, 256]: group g = channels 8g..8g+7 of every pixel --------------------------------------------
+// ---- token-major [images, HW, 256] (img_stride floats between images: HW * 256, or more when the level is a slice of the multi-level
+// token tensor): group g = channels 8g..8g+7 of every pixel --------------------------------------------
 // pass 1: partial (sum, sumsq) per (image, chunk, group); thread t: channel quad t & 63, pixel slot t >> 6 (4 pixels per sweep)
-__global__ void __launch_bounds__(256) gn_tokens_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, int HW) {
+__global__ void __launch_bounds__(256) gn_tokens_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, int HW, long long img_stride) {
   __shared__ float2 red[4][64];
   const int img = blockIdx.y, chunk = blockIdx.x;
   const int p0 = (int)(((long long)HW * chunk) / GN_CHUNKS), p1 = (int)(((long long)HW * (chunk + 1)) / GN_CHUNKS);
   const int cq = threadIdx.x & 63, slot = threadIdx.x >> 6;
-  const float* base = x + (size_t)img * HW * C256 + cq * 4;
+  const float* base = x + (size_t)img * (size_t)img_stride + cq * 4;
   float s = 0.f, q = 0.f;
   for (int p = p0 + slot; p < p1; p += 4) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * C256));
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(256) gn_tokens_stats_kernel(const float* __res
 }
 // pass 2: y = (x - mean_g) * rstd_g * gamma_c + beta_c in place
 __global__ void __launch_bounds__(256) gn_tokens_apply_kernel(float* __restrict__ x, const float2* __restrict__ partial, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, int HW, float eps) {
+                                                              const float* __restrict__ beta, int HW, float eps, long long img_stride) {
   __shared__ float2 stat[GN_GROUPS];               // (mean, rstd)
   const int img = blockIdx.y, chunk = blockIdx.x;
   if (threadIdx.x < GN_GROUPS) {
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) gn_tokens_apply_kernel(float* __restrict_
   const int cq = threadIdx.x & 63, slot = threadIdx.x >> 6;
   const float2 st = stat[cq >> 1];
   const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cq), be = __ldg(reinterpret_cast<const float4*>(beta) + cq);
-  float* base = x + (size_t)img * HW * C256 + cq * 4;
+  float* base = x + (size_t)img * (size_t)img_stride + cq * 4;
   for (int p = p0 + slot; p < p1; p += 4) {
     float4 v = *reinterpret_cast<float4*>(base + (size_t)p * C256);
     v.x = (v.x - st.x) * st.y * ga.x + be.x; v.y = (v.y - st.x) * st.y * ga.y + be.y;

@@ -529,20 +529,33 @@ def cc_class_pool(ce: torch.Tensor, w_act: torch.Tensor, b_act: float, T: int, Q
     return out
 
 
-def input_proj_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, gn_w: torch.Tensor, gn_b: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
-    """x fp32 NCHW [images, c_in, H, W] -> GroupNorm(32)(Conv1x1(x)) as token-major fp32 [images, H*W, 256]."""
+def _level_slice_stride(t: torch.Tensor, name: str, images: int, hw: int) -> int:
+    """t fp32 [images, hw, 256], dense, or one level's slice of a multi-level token tensor [images, len, 256] -> floats between images."""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and tuple(t.shape) == (images, hw, C)):
+        raise RuntimeError(f"{name} must be a CUDA fp32 tensor of shape {(images, hw, C)}")
+    if t.stride(2) != 1 or t.stride(1) != C or (images > 1 and (t.stride(0) < hw * C or t.stride(0) % 4)) or t.data_ptr() % 16:
+        raise RuntimeError(f"{name} must be dense or a level slice [:, a:b] of a contiguous [images, len, 256] tensor")
+    return t.stride(0) if images > 1 else hw * C
+
+
+def input_proj_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, gn_w: torch.Tensor, gn_b: torch.Tensor, eps: float = 1e-5,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x fp32 NCHW [images, c_in, H, W] -> GroupNorm(32)(Conv1x1(x)) as token-major fp32 [images, H*W, 256]; `out`: write into this
+    tensor instead (dense, or the level's slice of the multi-level token tensor [images, len, 256])."""
     _check(x, "x", torch.float32)
     if x.dim() != 4:
         raise RuntimeError("input_proj_fwd: expected an NCHW feature map")
     images, c_in, H, W = x.shape
     for t, nm in ((bias, "bias"), (gn_w, "GroupNorm weight"), (gn_b, "GroupNorm bias")):
         _check(t, nm, torch.float32, (C,))
-    out = torch.empty(images, H * W, C, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(images, H * W, C, dtype=torch.float32, device=x.device)
+    stride = _level_slice_stride(out, "out", images, H * W)
     lib = _lib.load()
     nbytes = lib.axvs_proj_workspace_bytes(images)
     with torch.cuda.device(x.device):
         ws = workspace(nbytes, x.device)
-        rc = lib.axvs_input_proj_fwd(x.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), gn_w.data_ptr(), gn_b.data_ptr(), out.data_ptr(),
+        rc = lib.axvs_input_proj_fwd(x.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), gn_w.data_ptr(), gn_b.data_ptr(), out.data_ptr(), stride,
                                      images, c_in, H * W, float(eps), ws.data_ptr(), ws.numel(), _stream(x.device))
     _lib.check(rc, "axvs_input_proj_fwd")
     return out
@@ -550,18 +563,19 @@ def input_proj_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, 
 
 def output_proj_fwd(tokens: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, gn_w: torch.Tensor, gn_b: torch.Tensor,
                     H: int, W: int, eps: float = 1e-5) -> torch.Tensor:
-    """tokens fp32 [images, H*W, 256] -> GroupNorm(32)(Conv1x1(tokens^T)) as fp32 NCHW [images, c_out, H, W]."""
-    _check(tokens, "tokens", torch.float32)
+    """tokens fp32 [images, H*W, 256] (dense, or a level slice of the multi-level token tensor) -> GroupNorm(32)(Conv1x1(tokens^T)) as fp32
+    NCHW [images, c_out, H, W]."""
     if tokens.dim() != 3 or tokens.shape[1] != H * W or tokens.shape[2] != C:
         raise RuntimeError("output_proj_fwd: expected tokens [images, H*W, 256]")
     images, c_out = tokens.shape[0], gn_w.numel()
+    stride = _level_slice_stride(tokens, "tokens", images, H * W)
     _check(bias, "bias", torch.float32, ((c_out + 255) // 256 * 256,))          # zero-padded to the GEMM's 256-column chunks
     for t, nm in ((gn_w, "GroupNorm weight"), (gn_b, "GroupNorm bias")):
         _check(t, nm, torch.float32, (c_out,))
     out = torch.empty(images, c_out, H, W, dtype=torch.float32, device=tokens.device)
     lib = _lib.load()
     with torch.cuda.device(tokens.device):
-        rc = lib.axvs_output_proj_fwd(tokens.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), gn_w.data_ptr(), gn_b.data_ptr(), out.data_ptr(),
+        rc = lib.axvs_output_proj_fwd(tokens.data_ptr(), stride, w_packed.data_ptr(), bias.data_ptr(), gn_w.data_ptr(), gn_b.data_ptr(), out.data_ptr(),
                                       images, c_out, H * W, float(eps), _stream(tokens.device))
     _lib.check(rc, "axvs_output_proj_fwd")
     return out

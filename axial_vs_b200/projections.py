@@ -49,10 +49,12 @@ class InputProjection(_Proj):
             raise NotImplementedError("axial_vs_b200: conv_dims must be 256 (every shipped config)")
         super().__init__(in_channels, conv_dims)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """`out` (optional, fp32): the level's slice of the multi-level token tensor; the projection writes into it (no torch.cat afterwards)."""
         _require_inference(self, x)
         b, gw, gb = self._params()
-        return ops.input_proj_fwd(x.contiguous().float(), self._packed(x.device), b, gw, gb, self[1].eps).to(x.dtype)
+        y = ops.input_proj_fwd(x.contiguous().float(), self._packed(x.device), b, gw, gb, self[1].eps, out=out)
+        return y if out is not None else y.to(x.dtype)
 
 
 class OutputProjection(_Proj):
@@ -66,4 +68,7 @@ class OutputProjection(_Proj):
     def forward(self, tokens: torch.Tensor, H: int, W: int) -> torch.Tensor:
         _require_inference(self, tokens)
         b, gw, gb = self._params()
-        return ops.output_proj_fwd(tokens.contiguous().float(), self._packed(tokens.device), b, gw, gb, H, W, self[1].eps).to(tokens.dtype)
+        t = tokens.float()
+        if not (t.stride(2) == 1 and t.stride(1) == ops.C and t.data_ptr() % 16 == 0):       # dense rows or a level slice are read in place
+            t = t.contiguous()
+        return ops.output_proj_fwd(t, self._packed(tokens.device), b, gw, gb, H, W, self[1].eps).to(tokens.dtype)

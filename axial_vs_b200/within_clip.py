@@ -83,13 +83,28 @@ def _run_levels(temporal_layer, feats: Sequence[Tensor], pos_3d: Sequence[Tensor
 
 
 def run_temporal_levels(temporal_layer, memory: Tensor, spatial_shapes: Sequence[Tuple[int, int]], pos_3d: Sequence[Tensor],
-                        num_temporal_levels: int):
-    """memory [B*T, sum(H_l*W_l), C] -> same shape; returns (memory, height_traj_attn, width_traj_attn) like the reference."""
+                        num_temporal_levels: int, inplace: bool = False):
+    """memory [B*T, sum(H_l*W_l), C] -> same shape; returns (memory, height_traj_attn, width_traj_attn) like the reference.
+
+    The temporal levels are independent (WC/msdeformattn.py:261-263) and run on one CUDA stream each.  `inplace=True` (the caller owns
+    `memory`, e.g. the fresh output of the spatial layer): the results are written back into the levels' slices of `memory` instead of
+    re-concatenating every level -- the levels without a temporal layer (res3 = 75 % of the tokens) are then never copied."""
     sizes = [int(h) * int(w) for h, w in spatial_shapes]
+    n = min(num_temporal_levels, len(sizes))
+    if n == 0:
+        return memory, None, None
     parts = list(torch.split(memory, sizes, dim=1))
-    h_attn = w_attn = None
-    for i in range(min(num_temporal_levels, len(parts))):
-        parts[i], h_attn, w_attn = temporal_layer(src=parts[i].contiguous(), pos=pos_3d[i])
+    if memory.is_cuda:
+        outs = run_levels_concurrent(temporal_layer, [parts[i].contiguous() for i in range(n)], list(pos_3d[:n]))
+    else:
+        outs = [temporal_layer(src=parts[i].contiguous(), pos=pos_3d[i]) for i in range(n)]
+    h_attn, w_attn = outs[-1][1], outs[-1][2]
+    if inplace and memory.is_contiguous() and not memory.requires_grad:
+        for i in range(n):
+            parts[i].copy_(outs[i][0])
+        return memory, h_attn, w_attn
+    for i in range(n):
+        parts[i] = outs[i][0]
     return torch.cat(parts, dim=1), h_attn, w_attn
 
 
@@ -107,6 +122,7 @@ class WithinClipEncoder(torch.nn.Module):
         self.transformer_num_temporal_feature_levels = transformer_num_temporal_feature_levels
         if transformer_num_temporal_feature_levels > 0:
             self.temporal_layers = torch.nn.ModuleList([copy.deepcopy(temporal_layer) for _ in range(num_stages)])
+        self._ref_cache = {}
 
     @staticmethod
     def get_reference_points(spatial_shapes, valid_ratios, device):
@@ -120,13 +136,18 @@ class WithinClipEncoder(torch.nn.Module):
     def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos, padding_mask, pos_3d=None):
         output = src
         shapes = [(int(h), int(w)) for h, w in (spatial_shapes.tolist() if torch.is_tensor(spatial_shapes) else spatial_shapes)]
-        reference_points = self.get_reference_points(shapes, valid_ratios, src.device)[:1].contiguous()   # identical for every image: broadcast
+        if valid_ratios is not None and not bool((valid_ratios == 1).all()):
+            raise NotImplementedError("axial_vs_b200: padded feature maps (valid_ratios != 1) are not supported")
+        key = (tuple(shapes), str(src.device))
+        if key not in self._ref_cache:                                              # identical for every image: one broadcast row set, built once per pyramid
+            self._ref_cache = {key: self.get_reference_points(shapes, None, src.device)[:1].contiguous()}
+        reference_points = self._ref_cache[key]
         h_attn = w_attn = None
         for i, spatial_layer in enumerate(self.spatial_layers):
             output = spatial_layer(output, pos, reference_points, shapes, level_start_index, padding_mask)
             if self.transformer_num_temporal_feature_levels > 0:
                 output, h_attn, w_attn = run_temporal_levels(self.temporal_layers[i], output, shapes, pos_3d,
-                                                             self.transformer_num_temporal_feature_levels)
+                                                             self.transformer_num_temporal_feature_levels, inplace=True)   # `output` is the spatial layer's own result
         return output, h_attn, w_attn
 
 
@@ -175,6 +196,7 @@ class WithinClipTrackingModule(torch.nn.Module):
         self.transformer = _EncoderOnly(conv_dims, transformer_nheads, transformer_num_stages, transformer_spatial_layers,
                                         transformer_temporal_layers, transformer_temporal_attn_type, transformer_dim_feedforward,
                                         transformer_dropout, transformer_attn_drop, len(spatial), len(temporal))
+        self._pos2d_cache = (None, None)
         self.pe_layer = PositionEmbeddingSine(conv_dims // 2, normalize=True)
         self.pe_layer_3d = PositionEmbeddingSine3D(conv_dims // 2, normalize=True)
 
@@ -184,22 +206,34 @@ class WithinClipTrackingModule(torch.nn.Module):
         BT = features[names[0]].shape[0]
         B = BT // self.num_clip_frames if (self.training or self.cross_clip_training) else 1
         T = BT // B
-        tokens, pos2d, shapes, pos3d = [], [], [], []
+        shapes = [(int(features[f].shape[2]), int(features[f].shape[3])) for f in names]
+        x0 = features[names[0]]
+        # the multi-level token tensor [BT, Len, 256] is allocated once and every input projection writes its level's slice
+        # (the reference concatenates the projected levels, WC/msdeformattn.py:106)
+        src = torch.empty(BT, sum(h * w for h, w in shapes), 256, dtype=torch.float32, device=x0.device)
+        pos3d, start = [], 0
         for i, f in enumerate(names):
-            x = features[f]
-            H, W = int(x.shape[2]), int(x.shape[3])
-            shapes.append((H, W))
-            tokens.append(self.input_proj[i](x))                                  # [BT, H*W, 256]
-            pos2d.append(self.pe_layer.table(H, W, x.device) + self.transformer.level_embed_2d[i].detach().float())
+            H, W = shapes[i]
+            self.input_proj[i](features[f], out=src[:, start:start + H * W])
+            start += H * W
             if f in self.transformer_temporal_in_features:
-                pos3d.append(self.pe_layer_3d.table(B, T, H, W, x.device, self.transformer.level_embed_3d[len(pos3d)]))
-        src = torch.cat(tokens, dim=1)
-        pos = torch.cat(pos2d, dim=0)[None].contiguous()                          # [1, Len, 256], broadcast over the frames
-        y, h_attn, w_attn = self.transformer.encoder(src, shapes, None, None, pos, None, pos3d)
+                pos3d.append(self.pe_layer_3d.table(B, T, H, W, x0.device, self.transformer.level_embed_3d[len(pos3d)]))
+        if x0.dtype != torch.float32:
+            src = src.to(x0.dtype)
+        y, h_attn, w_attn = self.transformer.encoder(src, shapes, None, None, self._pos2d(shapes, x0.device), None, pos3d)
         out = {}
         start = 0
         for i, (H, W) in enumerate(shapes):
-            z = y[:, start:start + H * W].contiguous()
+            out[names[i]] = self.output_proj[i](y[:, start:start + H * W], H, W)   # the level's slice is read in place
             start += H * W
-            out[names[i]] = self.output_proj[i](z, H, W)
         return out, h_attn, w_attn
+
+    def _pos2d(self, shapes, device) -> Tensor:
+        """[1, Len, 256] = per level PositionEmbeddingSine table + level_embed_2d (WC/msdeformattn.py:103-105), broadcast over the frames;
+        rebuilt only when the pyramid shape or the level embedding changes."""
+        le = self.transformer.level_embed_2d
+        key = (tuple(shapes), str(device), le.data_ptr(), le._version)
+        if self._pos2d_cache[0] != key:
+            pos = torch.cat([self.pe_layer.table(H, W, device) + le[i].detach().float() for i, (H, W) in enumerate(shapes)], dim=0)
+            self._pos2d_cache = (key, pos[None].contiguous())
+        return self._pos2d_cache[1]

@@ -261,17 +261,21 @@ int axvs_kmeans_update(const float* mask_logits, const float* pixel_value, float
 /* ---- within-clip input / output projections ---------------------------------------------
  * input side  (WC/msdeformattn.py:355-358, 413-416): tokens[i, p, :] = GroupNorm(32, 256)(Conv2d(c_in, 256, 1)(x))[i, :, p]
  *   x fp32 NCHW [images, c_in, hw] (c_in % 64 == 0); w_packed = axvs_pack_weight of the conv weight [256, c_in];
- *   out fp32 token-major [images, hw, 256] -- the layout of the temporal layers (the reference's flatten + transpose is folded in).
+ *   out fp32 token-major [images, hw, 256] -- the layout of the temporal layers (the reference's flatten + transpose is folded in);
+ *   out_image_stride = floats between consecutive images of `out` (0 = hw * 256): with the stride of the multi-level token tensor
+ *   [images, sum(H_l*W_l), 256] the level is written straight into its slice (the reference's torch.cat, WC/msdeformattn.py:106).
  * output side (WC/msdeformattn.py:359-362, 432-434): y[i, :, p] = GroupNorm(32, c_out)(Conv2d(256, c_out, 1))(tokens[i, p, :])
- *   tokens fp32 [images, hw, 256]; c_out % 32 == 0 (GroupNorm(32); e.g. 384 for res3 of the ConvNeXt-L configs); w_packed of the conv
+ *   tokens fp32 [images, hw, 256] (tokens_image_stride floats between images, 0 = hw * 256: a level slice of the multi-level token
+ *   tensor is read in place, WC/msdeformattn.py:428-434); c_out % 32 == 0 (GroupNorm(32); e.g. 384 for res3 of the ConvNeXt-L configs); w_packed of the conv
  *   weight zero-padded to [ceil256(c_out), 256] rows and bias zero-padded to ceil256(c_out) entries (the GEMM works on 256-column
  *   chunks; padding columns are never stored); out fp32 NCHW [images, c_out, hw].
  * GroupNorm statistics are per image and per group (eps as given, nn.GroupNorm default 1e-5), reductions in a fixed order. */
 size_t axvs_proj_workspace_bytes(int images);
 int axvs_input_proj_fwd(const float* x_nchw, const void* w_packed, const float* bias, const float* gn_w, const float* gn_b, float* out_tokens,
-                        int images, int c_in, int hw, float eps, void* workspace, size_t workspace_bytes, axvs_stream_t stream);
-int axvs_output_proj_fwd(const float* tokens, const void* w_packed, const float* bias, const float* gn_w, const float* gn_b, float* out_nchw,
-                         int images, int c_out, int hw, float eps, axvs_stream_t stream);
+                        long long out_image_stride, int images, int c_in, int hw, float eps, void* workspace, size_t workspace_bytes,
+                        axvs_stream_t stream);
+int axvs_output_proj_fwd(const float* tokens, long long tokens_image_stride, const void* w_packed, const float* bias, const float* gn_w,
+                         const float* gn_b, float* out_nchw, int images, int c_out, int hw, float eps, axvs_stream_t stream);
 
 /* ---- MSDeformAttn spatial encoder layer ------------------------------------------------------
  * MSDeformAttnTransformerEncoderLayer.forward in eval mode without padding (WC/msdeformattn.py:205-215 with

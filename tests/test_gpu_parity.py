@@ -762,6 +762,28 @@ def test_projections_oracle_config_sizes(O, n, c, H, W):
         assert nerr(y, O.output_proj(ref_tok, pout, H, W)) < TOL
 
 
+def test_projections_level_slices():
+    """The projections read / write one level's slice of the multi-level token tensor [images, Len, 256] in place (what forward_features
+    does instead of torch.cat / .contiguous()): bit-identical to the dense call, neighbouring levels untouched."""
+    from axial_vs_b200.projections import InputProjection, OutputProjection
+    n, c, shapes = 3, 128, [(5, 7), (9, 11), (6, 4)]
+    pin, pout = synth.proj_params(31, c)
+    mi, mo = InputProjection(c).eval().cuda(), OutputProjection(2 * c).eval().cuda()
+    mi.load_state_dict(pin, strict=True)
+    mo.load_state_dict(pout, strict=True)
+    Len = sum(h * w for h, w in shapes)
+    mem = torch.full((n, Len, 256), 7.0, device="cuda")
+    start = shapes[0][0] * shapes[0][1]
+    H, W = shapes[1]
+    x = synth.randn(32, n, c, H, W).cuda()
+    with torch.no_grad():
+        dense = mi(x)
+        mi(x, out=mem[:, start:start + H * W])
+        assert torch.equal(mem[:, start:start + H * W], dense)
+        assert bool((mem[:, :start] == 7.0).all()) and bool((mem[:, start + H * W:] == 7.0).all())
+        assert torch.equal(mo(mem[:, start:start + H * W], H, W), mo(dense, H, W))
+
+
 # --------------------------------------------------------------------------------------------- MSDeformAttn spatial layer (f2)
 def _msda_layer(p):
     from axial_vs_b200.msda import MSDeformAttnTransformerEncoderLayer
