@@ -1373,7 +1373,7 @@ int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, cons
   if ((rc = launch_gemm(p, st))) return rc;
   {
     ProfScope ps(KC_MSDA, 0, (double)rows * (8.0 * d.L * d.P * 4 * 64 + 2048 + 512), st);
-    msda_sample_kernel<<<(rows + 7) / 8, 256, 0, st>>>(value, oa, 512, ref_points, (ref_images == 1 && images > 1) ? len : 0, samp, rows, d);
+    launch_msda_sample(value, 0, oa, 512, ref_points, (ref_images == 1 && images > 1) ? len : 0, samp, rows, d, st);
   }
   AXVS_CHECK_LAUNCH("msda_sample_kernel");
   // y = src + output_proj(sampled)                                                                   MSDA:124, ENC:208
@@ -1427,8 +1427,7 @@ int axvs_msda_sample_fwd(const float* value_in, const float* query_in, const flo
   if ((rc = launch_gemm(p, st))) return rc;
   {
     ProfScope ps(KC_MSDA, 0, (double)rows * (8.0 * d.L * d.P * 4 * 64 + 2048 + 512), st);
-    msda_sample_kernel<<<(rows + 7) / 8, 256, 0, st>>>(value, oa, 512, ref_points, (ref_images == 1 && images > 1) ? len : 0,
-                                                     reinterpret_cast<__nv_bfloat16*>(sampled_bf16), rows, d);
+    launch_msda_sample(value, 0, oa, 512, ref_points, (ref_images == 1 && images > 1) ? len : 0, reinterpret_cast<__nv_bfloat16*>(sampled_bf16), rows, d, st);
   }
   AXVS_CHECK_LAUNCH("msda_sample_kernel");
   return AXVS_OK;
