@@ -25,6 +25,7 @@
 #include "decoder_attn.cuh"
 #include "proj.cuh"
 #include "msda.cuh"
+#include "msda_front.cuh"
 #include "panoptic.cuh"
 #include "kmax_axial.cuh"
 #include "matching.cuh"
@@ -48,12 +49,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_MATCH, KC_MMHA, KC_KMAXLAYER, KC_TRAJPAIR, KC_QKVPAIR, KC_FFNPAIR, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_MATCH, KC_MMHA, KC_KMAXLAYER, KC_TRAJPAIR, KC_QKVPAIR, KC_FFNPAIR, KC_MSDAFRONT, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel", "matching_kernels", "masked_mha_kernels", "kmax_layer_kernels", "traj_pair_kernel", "qkv_pair_kernel", "ffn_n256_pair_kernel"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel", "matching_kernels", "masked_mha_kernels", "kmax_layer_kernels", "traj_pair_kernel", "qkv_pair_kernel", "ffn_n256_pair_kernel", "msda_front_pair_kernel"};
 // Process-wide knobs are atomics (two host threads driving two devices may read / set them concurrently); the profiler's records and
 // the per-device attribute table are guarded by mutexes.  None of them is touched on the launch path beyond one relaxed load.
 std::atomic<int> g_fusion{4};   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
@@ -146,6 +147,7 @@ int device_info(DeviceInfo** out) {
     if (cudaFuncSetAttribute(qkv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QK_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QD_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(msda_front_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_attn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES) != cudaSuccess)
@@ -1362,8 +1364,31 @@ int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, cons
   uint8_t* ffn_ws = base + (((size_t)rows * (512 + 2048 + 512 + 1024) + 1023) & ~(size_t)1023);
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
+  const int tiles = (rows + 127) / 128;
+  GemmParams p;
+  if (w->w_front_u && w->b_front && d.P == 4 && (d.L == 3 || d.L == 4) && tiles >= 2 && (g_pair & 4) && (long long)rows * 8 < 0x7fffffffLL) {
+    // value = value_proj(src) and [sampling offsets | attention logits] = Linear(src + pos) in ONE pass over src / pos         MSDA:98-103, ENC:207
+    DeviceInfo* di;
+    if ((rc = device_info(&di))) return rc;
+    MsdaFrontParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.src = src; fp.pos = pos; fp.w = reinterpret_cast<const uint8_t*>(w->w_front_u); fp.bias = w->b_front;
+    fp.oa = oa; fp.value = value; fp.rows = rows; fp.tiles = tiles; fp.len = len; fp.n_oa = 8 * d.L * d.P * 3;
+    fp.dims = make_dims(1, 1, len, 1, pos && pos_images == 1 && images > 1);
+    {
+      ProfScope ps(KC_MSDAFRONT, 2.0 * rows * 256.0 * (256.0 + fp.n_oa), (double)rows * ((pos ? 2048.0 : 1024.0) + 512.0 + 4.0 * fp.n_oa), st);
+      const int pair_tiles = (tiles + 1) / 2, max_pairs = di->sms / 2;
+      msda_front_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), QD_THREADS, QP_SMEM_BYTES, st>>>(fp);
+    }
+    AXVS_CHECK_LAUNCH("msda_front_pair_kernel");
+    {
+      ProfScope ps(KC_MSDA, 0, (double)rows * (8.0 * d.L * d.P * 4 * 64 + 2048 + 512), st);
+      launch_msda_sample(value, 1, oa, fp.n_oa, ref_points, (ref_images == 1 && images > 1) ? len : 0, samp, rows, d, st);
+    }
+    AXVS_CHECK_LAUNCH("msda_sample_kernel");
+  } else {
   // value = value_proj(src)                                                                         MSDA:98
-  GemmParams p = gemm_params(nullptr, 256, rows, 256, w->w_value, 256, 0, w->b_value, 256, 1.f, 0, value, 256, 0, 1, nullptr);
+  p = gemm_params(nullptr, 256, rows, 256, w->w_value, 256, 0, w->b_value, 256, 1.f, 0, value, 256, 0, 1, nullptr);
   p.a_diag = 4; p.A32 = src;
   if ((rc = launch_gemm(p, st))) return rc;
   // [sampling offsets | attention logits] = Linear(src + pos)                                       MSDA:102-103 (query = src + pos, ENC:207)
@@ -1376,6 +1401,7 @@ int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, cons
     launch_msda_sample(value, 0, oa, 512, ref_points, (ref_images == 1 && images > 1) ? len : 0, samp, rows, d, st);
   }
   AXVS_CHECK_LAUNCH("msda_sample_kernel");
+  }
   // y = src + output_proj(sampled)                                                                   MSDA:124, ENC:208
   p = gemm_params(samp, 256, rows, 256, w->w_out, 256, 0, w->b_out, 256, 1.f, 0, y, 256, 0, 0, src);
   if ((rc = launch_gemm(p, st))) return rc;

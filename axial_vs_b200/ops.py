@@ -610,6 +610,10 @@ def pack_msda_layer(p: Dict[str, torch.Tensor], n_levels: int, n_points: int) ->
           pack_weight(g("linear1.weight")), g("linear1.bias"), pack_weight(g("linear2.weight")), g("linear2.bias"),
           pack_weight_units(g("linear1.weight")), pack_weight_units(g("linear2.weight"), k_major=1),
           pack_weight_units(g("linear1.weight"), k_major=2), g("norm2.weight"), g("norm2.bias")]
+    # fused front end (msda_front_pair_kernel): [offsets | logits rows zero-padded to 384 ; value_proj] as one unit image + bias
+    w_front = torch.cat((w_oa[:384], g("self_attn.value_proj.weight")), 0).contiguous()
+    b_front = torch.cat((b_oa[:384], g("self_attn.value_proj.bias"))).contiguous()
+    ts += [pack_weight_units(w_front), b_front]
     return PackedMsda(ts, p["linear1.weight"].shape[0], n_levels, n_points)
 
 

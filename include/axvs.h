@@ -296,6 +296,9 @@ typedef struct axvs_msda_weights {
   const void* w_ffn1; const float* b_ffn1; const void* w_ffn2; const float* b_ffn2;   /* as in axvs_layer_weights */
   const void* w_ffn1_u; const void* w_ffn2_u; const void* w_ffn1_n;
   const float* ln2_g; const float* ln2_b;
+  const void* w_front_u; const float* b_front;   /* optional (NULL: two generic GEMMs instead): axvs_pack_weight_units (k_major 0) of
+                                                    [w_oa rows zero-padded to 384 ; value_proj.weight] = [640, 256] and the matching bias [640]:
+                                                    value and offsets | logits projections in one pass over src / pos (4 points per level) */
   int d_ffn, n_levels, n_points;
 } axvs_msda_weights;
 size_t axvs_msda_layer_workspace_bytes(int rows, int d_ffn);

@@ -825,6 +825,29 @@ def test_msda_layer_oracle_config_sizes(O, n, shapes):
     assert e < TOL and cos > 0.9999, (e, cos)
 
 
+@pytest.mark.parametrize("n,shapes", [(2, [(21, 21), (41, 41), (81, 81)]), (3, [(5, 7), (10, 13), (20, 27)]), (1, [(4, 5), (7, 9), (9, 14)])])
+def test_msda_front_kernel_matches_generic_gemms(ops, n, shapes):
+    """The fused front end (msda_front_pair_kernel: value + offsets | logits projections in one pass, head-major value rows) against
+    the two generic GEMMs it replaces (pair-mode bit 4 off): same bf16 operands, same accumulation order -> the layer output agrees
+    to fp32 noise; even / odd / tiny tile counts, with the positional table broadcast over the images and materialised per image."""
+    from axial_vs_b200 import msda
+    p = synth.msda_layer_params(77)
+    Len = sum(h * w for h, w in shapes)
+    src = synth.randn(78, n, Len, 256).cuda()
+    pos1 = synth.randn(79, 1, Len, 256).cuda()
+    ref = msda.reference_points(shapes, n, "cuda")
+    layer = _msda_layer(p)
+    for pos in (pos1, pos1.expand(n, -1, -1).contiguous(), None):
+        with torch.no_grad():
+            fused = layer(src, pos, ref[:1].contiguous(), shapes)
+            prev = ops.set_pair_mode(ops.set_pair_mode(14) & ~4)
+            try:
+                generic = layer(src, pos, ref, shapes)
+            finally:
+                ops.set_pair_mode(prev)
+        assert nerr(fused, generic) < 1e-5
+
+
 def test_within_clip_encoder_golden(golden):
     """The whole within-clip transformer encoder (drop-in for MSDeformAttnTransformerEncoder): 2 stages x [MSDeformAttn spatial
     layer on 3 levels, TemporalEncoder on the first 2], same state-dict keys as the reference, against its CPU output."""
