@@ -20,7 +20,6 @@
 #include "ffn_n256.cuh"
 #include "qkv_fused.cuh"
 #include "qkv_direct.cuh"
-#include "qkv_attn.cuh"
 #include "cc_tail.cuh"
 #include "decoder_attn.cuh"
 #include "proj.cuh"
@@ -29,7 +28,6 @@
 #include "panoptic.cuh"
 #include "kmax_axial.cuh"
 #include "matching.cuh"
-#include "ffn_pair.cuh"
 #include "ffn_n256_pair.cuh"
 #include "masked_mha.cuh"
 #include "kmax_layer.cuh"
@@ -57,11 +55,12 @@ const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel"
                                             "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel", "matching_kernels", "masked_mha_kernels", "kmax_layer_kernels", "traj_pair_kernel", "qkv_pair_kernel", "ffn_n256_pair_kernel", "msda_front_pair_kernel"};
 // Process-wide knobs are atomics (two host threads driving two devices may read / set them concurrently); the profiler's records and
 // the per-device attribute table are guarded by mutexes.  None of them is touched on the launch path beyond one relaxed load.
-std::atomic<int> g_fusion{4};   // level 5 (attention inside the q|k|v kernel) is validated but 15-20 % slower today: see profiles/README.md
+std::atomic<int> g_fusion{4};   // 0-3: earlier kernel generations kept as validation baselines (an attention-inside-the-q|k|v-kernel level 5 was measured
+                                // 15-20 % slower and removed: profiles/README.md)
 std::atomic<int> g_attn_core{1};   // 1 = tcgen05 attention core (attn_tc.cuh), 0 = the mma.sync kernels (validation baseline)
 // CTA-pair (cta_group::2) kernels, bit mask: 2 = traj_pair_kernel, 4 = qkv_pair_kernel, 8 = ffn_n256_pair_kernel (default: all three; each is
-// bit-identical to its single-CTA kernel and 4-8 % faster because every CTA stages only half of each weight unit), 1 = the older
-// ffn_pair_kernel (128-column chunk schedule, slower than ffn_n256: validation only).  AXVS_PAIR overrides the default for A/B runs.
+// bit-identical to its single-CTA kernel and 4-8 % faster because every CTA stages only half of each weight unit; bit 4 also selects the
+// fused MSDeformAttn front end, msda_front_pair_kernel).  AXVS_PAIR overrides the default for A/B runs.
 std::atomic<int> g_pair{getenv("AXVS_PAIR") ? atoi(getenv("AXVS_PAIR")) : 14};
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
@@ -147,10 +146,7 @@ int device_info(DeviceInfo** out) {
     if (cudaFuncSetAttribute(qkv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QK_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QD_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(msda_front_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(qkv_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(qkv_attn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(qkv_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES) != cudaSuccess)
+        cudaFuncSetAttribute(msda_front_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(qkv_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.qkv_attr = true;
   }
@@ -184,9 +180,8 @@ int device_info(DeviceInfo** out) {
     d.attn_tc_attr = true;
   }
   if (!d.pair_attr) {
-    if (cudaFuncSetAttribute(ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(ffn_n256_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SMEM_BYTES) != cudaSuccess)
-      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(ffn_pair) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (cudaFuncSetAttribute(ffn_n256_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SMEM_BYTES) != cudaSuccess)
+      return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(ffn_n256_pair) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.pair_attr = true;
   }
   if (!d.mask_attr) {
@@ -339,7 +334,7 @@ int axvs_set_attn_core(int core) {
   return g_attn_core.exchange(core ? 1 : 0);
 }
 int axvs_set_fusion(int level) {
-  return g_fusion.exchange(level < 0 ? 0 : (level > 5 ? 5 : level));
+  return g_fusion.exchange(level < 0 ? 0 : (level > 4 ? 4 : level));
 }
 const char* axvs_last_error(void) { return g_err; }
 
@@ -441,26 +436,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
     const int tiles = (int)((rows + 127) / 128);
     const int nt16_f = (n + 15) / 16;
     bool use_tc = false;                                         // tcgen05 attention core (needs the chunk-permuted q|k|v of qkv_direct)
-    if (g_fusion >= 5 && v_in == q_in && N <= 128 && nt16_f <= 4) {
-      // q|k|v projections and the per-frame attention in one kernel: q, k, v never leave the SM
-      QkvAttnParams ap;
-      memset(&ap, 0, sizeof(ap));
-      ap.src = q_in; ap.pos = pos;
-      ap.w = reinterpret_cast<const uint8_t*>(w->w_qkv_u); ap.bias = w->b_qkv;
-      ap.x_img = ws.x_img; ap.xd_img = ws.xd_img;
-      ap.rows = (int)rows; ap.num_seq = num_seq; ap.N = N; ap.n = n; ap.F = F;
-      ap.S = 128 / N; ap.tiles = (num_seq + ap.S - 1) / ap.S; ap.img_tiles = tiles;
-      ap.map_mode = map; ap.dims = dims; ap.scale_log2e = kScaleLog2e;
-      {
-        ProfScope ps(KC_QKVA, 2.0 * rows * 256.0 * 768.0 + 4.0 * num_seq * (double)N * N * 256,
-                     (double)rows * ((pos ? 2048.0 : 1024.0) + (F + 1) * 512.0), st);
-        const int grid = ap.tiles < d->sms ? ap.tiles : d->sms;
-        if (nt16_f <= 2) qkv_attn_kernel<2><<<grid, QA_THREADS, QA_SMEM_BYTES, st>>>(ap);
-        else if (nt16_f == 3) qkv_attn_kernel<3><<<grid, QA_THREADS, QA_SMEM_BYTES, st>>>(ap);
-        else qkv_attn_kernel<4><<<grid, QA_THREADS, QA_SMEM_BYTES, st>>>(ap);
-      }
-      AXVS_CHECK_LAUNCH("qkv_attn_kernel");
-    } else {
+    {
     if (g_fusion >= 4 && v_in == q_in) {
       use_tc = g_attn_core == 1 && (n + 15) / 16 * 16 <= 224 && rows * 24 < (size_t)0xffffffffu;
       // the q|k|v GEMM reads the fp32 residual stream (+ pos) itself: no tile-image pack, no a1/a2 round trip
@@ -742,12 +718,9 @@ int ffn_fused_launch(const uint8_t* s_img, const float* s32, float* out, const a
   fp.b1 = w->b_ffn1; fp.b2 = w->b_ffn2;
   fp.rows = rows; fp.tiles = (rows + 127) / 128; fp.d_ffn = w->d_ffn; fp.eps = 1e-5f;
   {
-    const bool n256 = !(g_pair & 1) && g_fusion >= 4 && w->w_ffn1_n && w->d_ffn % 256 == 0;
+    const bool n256 = g_fusion >= 4 && w->w_ffn1_n && w->d_ffn % 256 == 0;
     ProfScope ps(n256 ? (((g_pair & 8) && fp.tiles >= 2) ? KC_FFNPAIR : KC_FFN256) : KC_FFN, 4.0 * rows * 256.0 * w->d_ffn, (double)rows * 256 * 10.0, st);
-    if (g_pair & 1) {
-      const int pair_tiles = (fp.tiles + 1) / 2, max_pairs = d->sms / 2;
-      ffn_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), FF_THREADS, FP_SMEM_BYTES, st>>>(fp);
-    } else if (g_fusion >= 4 && w->w_ffn1_n && w->d_ffn % 256 == 0) {
+    if (n256) {
       fp.w1 = reinterpret_cast<const uint8_t*>(w->w_ffn1_n);       // N = 256 units
       if ((g_pair & 8) && fp.tiles >= 2) {
         const int pair_tiles = (fp.tiles + 1) / 2, max_pairs = d->sms / 2;

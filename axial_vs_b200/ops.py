@@ -377,13 +377,13 @@ DEFAULT_FUSION = 4     # fastest measured level (include/axvs.h lists them); 5 =
 
 
 def set_fusion(level: int) -> int:
-    """Select the fusion level of the composite calls (0 = unfused validation baseline ... 5); returns the previous level."""
+    """Select the fusion level of the composite calls (0 = unfused validation baseline ... 4, the default); returns the previous level."""
     return _lib.load().axvs_set_fusion(int(level))
 
 
 def set_pair_mode(mask: int) -> int:
-    """CTA-pair (cta_group::2) kernels, bit mask: 2 = temporal kernel, 4 = q|k|v projection, 8 = FFN (default 14), 1 = the first pair FFN
-    (validation only); 0 = single-CTA kernels everywhere.  Returns the previous mask."""
+    """CTA-pair (cta_group::2) kernels, bit mask: 2 = temporal kernel, 4 = q|k|v projection, 8 = FFN (default 14); 0 = single-CTA
+    kernels everywhere.  Returns the previous mask."""
     return _lib.load().axvs_set_pair_mode(int(mask))
 
 

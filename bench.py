@@ -605,6 +605,16 @@ def main():
                     "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}); burst bf16 figure: the kernel is timed alone, launch by launch",
                     "frac_of_sustained_peak": round(achieved / peaks["tf_sustained"], 4) if tensor_bound else None,
                     "avg_launch_ms": round(dom["ms"] / max(dom["timed"], 1), 5),
+                    # the other roof of the same kernel: its algorithmic bytes over the same launches against the measured
+                    # copy bandwidth, and where its arithmetic intensity sits relative to the ridge of the two measured peaks
+                    "hbm_view": ({"achieved_gbs": round(dom["bytes"] / (dom["ms"] * 1e-3) / 1e9, 1), "peak_gbs": peaks["hbm"],
+                                  "frac": round(dom["bytes"] / (dom["ms"] * 1e-3) / 1e9 / peaks["hbm"], 4),
+                                  "intensity_flop_per_byte": round(dom["flops"] / dom["bytes"], 1),
+                                  "ridge_flop_per_byte": round(peaks["tf_burst"] * 1e12 / (peaks["hbm"] * 1e9), 1),
+                                  "note": "intensity below the ridge: by the roofline model this kernel's floor is its HBM time, not its tensor time"
+                                          if dom["flops"] / dom["bytes"] < peaks["tf_burst"] * 1e12 / (peaks["hbm"] * 1e9) else
+                                          "intensity above the ridge: the tensor roof binds"}
+                                 if tensor_bound and dom["bytes"] > 0 else None),
                     "step_tflops": round(step_tf, 2),
                     "step_frac_of_burst_peak": round(step_tf / peaks["tf_burst"], 4),
                     "step_frac_of_tensor_peak": round(step_tf / peaks["tf_sustained"], 4),

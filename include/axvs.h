@@ -54,15 +54,13 @@ const char* axvs_build_id(void);
  *   3: + TMA-fed q|k|v projection with head-major output, one-shot per-frame attention writing UMMA tile images
  *   4: + the q|k|v projection reads the fp32 residual stream (+ pos) itself (permute, add and cast inside its A producers);
  *        every UMMA A operand lives in tensor memory
- *   5: + the per-frame spatial attention runs inside the q|k|v kernel (sequences of at most 128 tokens, frames of at most 64);
- *        opt-in: bit-identical to level 4 but its 8 drain/attention warps are issue-bound (230 vs 192 us per res4 call)
  * Returns the previous level; values outside the range are clamped. */
 int axvs_set_fusion(int level);
 /* CTA-pair kernels (tcgen05 cta_group::2: two SMs of a cluster share one M = 256 instruction stream, each staging half of every
  * weight unit, which halves the shared-memory traffic of the GEMM core: 512 instead of 670 clk per 32 KiB unit).  Bit mask:
- *   2 = fused temporal kernel (traj_pair_kernel), 4 = q|k|v projection (qkv_pair_kernel), 8 = FFN (ffn_n256_pair_kernel),
- *   1 = the first CTA-pair FFN (128-column chunks; validation only).  Default 14; every pair kernel is bit-identical to its
- *   single-CTA counterpart (which `0` selects).  Returns the previous mask. */
+ *   2 = fused temporal kernel (traj_pair_kernel), 4 = q|k|v projection (qkv_pair_kernel) and the fused front end of the MSDeformAttn
+ *   layer (msda_front_pair_kernel), 8 = FFN (ffn_n256_pair_kernel).  Default 14; every pair kernel is bit-identical to its single-CTA
+ *   counterpart (which `0` selects; the MSDeformAttn front end falls back to two generic GEMMs).  Returns the previous mask. */
 int axvs_set_pair_mode(int on);
 /* Attention core of the per-frame spatial attention (WC/temporal_attention.py:47-60) at fusion level >= 4.
  *   1 (default): tcgen05 kernel -- Q K^T and P V as UMMAs (scores / probabilities / outputs in tensor memory, operands by TMA),

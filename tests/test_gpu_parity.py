@@ -201,7 +201,7 @@ def test_direct_qkv_matches_packed_front_end(ops, B, T, H, W):
     layer = _layer(p)
     outs = []
     try:
-        for level, core in ((3, 1), (4, 1), (4, 0), (5, 0)):
+        for level, core in ((3, 1), (4, 1), (4, 0)):
             ops.set_fusion(level)
             ops.set_attn_core(core)
             with torch.no_grad():
@@ -213,8 +213,6 @@ def test_direct_qkv_matches_packed_front_end(ops, B, T, H, W):
     assert torch.isfinite(outs[1]).all()
     assert nerr(outs[1], outs[0]) < 4e-3
     assert nerr(outs[2], outs[1]) < 4e-3      # mma.sync attention core against the tcgen05 core
-    # level 5 runs the mma.sync attention arithmetic on the same bf16 q | k | v inside the projection kernel
-    assert torch.equal(outs[3], outs[2])
 
 
 @pytest.mark.parametrize("B,T,H,W", [(3, 2, 13, 29), (5, 2, 21, 21), (2, 3, 7, 40)])
@@ -228,7 +226,7 @@ def test_shared_pos_table_is_bit_identical(ops, B, T, H, W):
     full = one.expand(B, -1, -1, -1, -1).contiguous()
     layer = _layer(p)
     try:
-        for level in (0, 2, 3, 4, 5):
+        for level in (0, 2, 3, 4):
             ops.set_fusion(level)
             with torch.no_grad():
                 ref = layer(src, full)[0]
@@ -616,8 +614,7 @@ PAIR_DEFAULT = 14      # traj_pair | qkv_pair | ffn_n256_pair (csrc/axvs.cu g_pa
 
 
 def test_pair_mode_ffn_matches(ops, O):
-    """Both cta_group::2 (CTA-pair) FFN kernels -- the default 256-column-chunk one (bit 8) and the first, 128-column-chunk one (bit 1) --
-    against the single-CTA kernel (mask 0): same results, bit for bit."""
+    """The cta_group::2 (CTA-pair) FFN kernel (bit 8, the default) against the single-CTA kernel (mask 0): same results, bit for bit."""
     p = synth.axial_layer_params(3)
     pk = ops.pack_layer({k: v.cuda() for k, v in p.items()})
     for rows in (100, 129, 5000):
@@ -625,14 +622,14 @@ def test_pair_mode_ffn_matches(ops, O):
         ref = O._ffn_tail(x, p)
         outs = []
         try:
-            for pair in (0, 1, 8):
+            for pair in (0, 8):
                 ops.set_pair_mode(pair)
                 outs.append(ops.ln_ffn_fwd(x.cuda(), pk))
                 torch.cuda.synchronize()
         finally:
             ops.set_pair_mode(PAIR_DEFAULT)
         assert all(nerr(o_, ref) < TOL for o_ in outs)
-        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+        assert torch.equal(outs[0], outs[1])
 
 
 @pytest.mark.parametrize("clips,T,H,W", [(1, 2, 41, 41), (3, 2, 21, 21), (2, 5, 15, 20), (1, 2, 5, 5), (9, 2, 21, 21)])
