@@ -64,7 +64,10 @@ class _PackedCache:
                 self._event.record(self._stream)
         elif self._event is not None:
             cur = torch.cuda.current_stream(dev)
-            if cur != self._stream and not self._event.query():
+            if torch.cuda.is_current_stream_capturing():
+                pass      # no event calls inside a CUDA-graph capture (cudaEventQuery invalidates it); `torch.cuda.graph` synchronises the
+                          # device when the capture begins, so a build that preceded the capture has completed
+            elif cur != self._stream and not self._event.query():
                 cur.wait_event(self._event)
             elif self._event.query():
                 self._event = None                             # build finished: nothing to order against any more

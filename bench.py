@@ -321,9 +321,27 @@ def module_figure(dev, clip_counts=(16, 42), steps: int = 5):
                 torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
             out[f"clips_{clips}"] = {"clips_per_s": round(clips / (ms * 1e-3), 1), "ms_per_forward": round(ms, 3)}
+            try:                                    # the same forward replayed from a CUDA graph (the module is allocation-free and never synchronises)
+                with torch.no_grad():
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        m.forward_features(feats)
+                    g.replay()
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(steps):
+                        g.replay()
+                    e1.record()
+                    torch.cuda.synchronize()
+                msg = e0.elapsed_time(e1) / steps
+                out[f"clips_{clips}"].update({"graph_clips_per_s": round(clips / (msg * 1e-3), 1), "graph_ms_per_forward": round(msg, 3)})
+                del g
+            except Exception as e:
+                out[f"clips_{clips}"]["graph_error"] = f"{type(e).__name__}: {str(e).splitlines()[0]}"
+                torch.cuda.synchronize()
             del feats
             torch.cuda.empty_cache()
-        out["what"] = "WithinClipTrackingModule.forward_features, R50 pyramid (res5 2048x21^2, res4 1024x41^2, res3 512x81^2), T=2, inputs resident, eager launches"
+        out["what"] = "WithinClipTrackingModule.forward_features, R50 pyramid (res5 2048x21^2, res4 1024x41^2, res3 512x81^2), T=2, inputs resident; eager launches, and (graph_*) the same forward replayed from a CUDA graph"
     except Exception as e:
         out["error"] = f"{type(e).__name__}: {e}"
     return out

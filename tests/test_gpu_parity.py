@@ -915,6 +915,35 @@ def test_within_clip_module_r50_shapes(O):
         assert e < 3e-2 and cos > 0.999, (name, e, cos)
 
 
+def test_within_clip_module_convnext_channels_multi_clip_and_graph(O):
+    """ConvNeXt-L channel counts (res5 1536, res4 768, res3 384: the output side is not a multiple of 256) on a small ragged pyramid with
+    TWO clips (cross-clip training layout: B = 2, T = 2): the level slices of the multi-level token tensor are written / read in place
+    across four frames; against the oracle, and a CUDA-graph replay of forward_features reproduces the eager result bit for bit."""
+    chans, sizes, seed = [1536, 768, 384], [(6, 7), (12, 13), (23, 26)], 321
+    p = synth.within_clip_module_params(seed, chans)
+    m = _wc_module(chans)
+    m.cross_clip_training = True
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    feats = [synth.randn(seed + 1 + i, 4, chans[i], *sizes[i]) for i in range(3)]
+    want = O.within_clip_module(feats, p, 2, 2)
+    dev = {f"res{5 - i}": feats[i].cuda() for i in range(3)}
+    out, _, _ = m.forward_features(dev)
+    for i, name in enumerate(("res5", "res4", "res3")):
+        e = nerr(out[name], want[i])
+        cos = torch.nn.functional.cosine_similarity(out[name].cpu().flatten(), want[i].flatten(), dim=0).item()
+        assert e < 3e-2 and cos > 0.999, (name, e, cos)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out_g, _, _ = m.forward_features(dev)
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    for name in ("res5", "res4", "res3"):
+        assert torch.equal(out_g[name], out[name]), name
+
+
 # --------------------------------------------------------------------------------------------- post-path tail (row f4)
 def _pano(C, thr=0.3):
     from types import SimpleNamespace
