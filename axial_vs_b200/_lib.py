@@ -26,7 +26,7 @@ class MsdaWeights(Structure):
     _fields_ = [("w_value", c_void_p), ("b_value", c_void_p), ("w_oa", c_void_p), ("b_oa", c_void_p), ("w_out", c_void_p), ("b_out", c_void_p),
                 ("ln1_g", c_void_p), ("ln1_b", c_void_p), ("w_ffn1", c_void_p), ("b_ffn1", c_void_p), ("w_ffn2", c_void_p), ("b_ffn2", c_void_p),
                 ("w_ffn1_u", c_void_p), ("w_ffn2_u", c_void_p), ("w_ffn1_n", c_void_p), ("ln2_g", c_void_p), ("ln2_b", c_void_p),
-                ("w_front_u", c_void_p), ("b_front", c_void_p), ("d_ffn", c_int), ("n_levels", c_int), ("n_points", c_int)]
+                ("w_front_u", c_void_p), ("b_front", c_void_p), ("w_out_u", c_void_p), ("d_ffn", c_int), ("n_levels", c_int), ("n_points", c_int)]
 
 
 class KmaxAxialWeights(Structure):

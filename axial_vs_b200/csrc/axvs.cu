@@ -25,6 +25,7 @@
 #include "proj.cuh"
 #include "msda.cuh"
 #include "msda_front.cuh"
+#include "msda_tail.cuh"
 #include "panoptic.cuh"
 #include "kmax_axial.cuh"
 #include "matching.cuh"
@@ -47,12 +48,12 @@ int fail(int code, const char* fmt, ...) {
 }
 
 // ---- optional per-kernel profiling (bench.py roofline leg): CUDA events around every launch on the launching stream
-enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_MATCH, KC_MMHA, KC_KMAXLAYER, KC_TRAJPAIR, KC_QKVPAIR, KC_FFNPAIR, KC_MSDAFRONT, KC_COUNT };
+enum KClass { KC_PACK = 0, KC_GEMM, KC_ATTN, KC_TEMPORAL, KC_LN, KC_POS, KC_PACKW, KC_TRAJ, KC_X2IMG, KC_FFN, KC_LNIMG, KC_QKV, KC_PACKIMG, KC_ATTN2, KC_CCTAIL, KC_MASK, KC_QSA, KC_KMEANS, KC_QKVD, KC_QKVA, KC_TRAJTS, KC_GN, KC_FFN256, KC_MSDA, KC_PANOPTIC, KC_KMAXAX, KC_ATTNTC, KC_MATCH, KC_MMHA, KC_KMAXLAYER, KC_TRAJPAIR, KC_QKVPAIR, KC_FFNPAIR, KC_MSDAFRONT, KC_MSDATAIL, KC_COUNT };
 const char* const kclass_names[KC_COUNT] = {"pack_kq_kernel", "gemm_bf16_kernel", "spatial_attn_kernel", "temporal_attn_kernel",
                                             "layernorm256_kernel", "pos3d_kernel", "pack_weight_kernel", "traj_fused_kernel",
                                             "x_to_image_kernel", "ffn_fused_kernel", "ln_image_kernel", "qkv_fused_kernel", "pack_image_kernel",
                                             "spatial_attn_v2_kernel", "cc_tail_kernels", "mask_einsum_kernel", "query_self_attn_kernel",
-                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel", "matching_kernels", "masked_mha_kernels", "kmax_layer_kernels", "traj_pair_kernel", "qkv_pair_kernel", "ffn_n256_pair_kernel", "msda_front_pair_kernel"};
+                                            "kmeans_update_kernels", "qkv_direct_kernel", "qkv_attn_kernel", "traj_ts_kernel", "groupnorm_kernels", "ffn_n256_kernel", "msda_sample_kernel", "panoptic_kernels", "kmax_axial_attn_kernel", "spatial_attn_tc_kernel", "matching_kernels", "masked_mha_kernels", "kmax_layer_kernels", "traj_pair_kernel", "qkv_pair_kernel", "ffn_n256_pair_kernel", "msda_front_pair_kernel", "msda_tail_pair_kernel"};
 // Process-wide knobs are atomics (two host threads driving two devices may read / set them concurrently); the profiler's records and
 // the per-device attribute table are guarded by mutexes.  None of them is touched on the launch path beyond one relaxed load.
 std::atomic<int> g_fusion{4};   // 0-3: earlier kernel generations kept as validation baselines (an attention-inside-the-q|k|v-kernel level 5 was measured
@@ -146,7 +147,8 @@ int device_info(DeviceInfo** out) {
     if (cudaFuncSetAttribute(qkv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QK_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QD_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(msda_front_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess)
+        cudaFuncSetAttribute(msda_front_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(msda_tail_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(qkv_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
     d.qkv_attr = true;
   }
@@ -1375,14 +1377,33 @@ int axvs_msda_layer_fwd(const float* src, const float* pos, int pos_images, cons
   }
   AXVS_CHECK_LAUNCH("msda_sample_kernel");
   }
-  // y = src + output_proj(sampled)                                                                   MSDA:124, ENC:208
-  p = gemm_params(samp, 256, rows, 256, w->w_out, 256, 0, w->b_out, 256, 1.f, 0, y, 256, 0, 0, src);
-  if ((rc = launch_gemm(p, st))) return rc;
-  // out = LN2(s + FFN(s)), s = LN1(y)                                                                ENC:209-213
   axvs_layer_weights lw;
   memset(&lw, 0, sizeof(lw));
   lw.ln1_g = w->ln1_g; lw.ln1_b = w->ln1_b; lw.w_ffn1 = w->w_ffn1; lw.b_ffn1 = w->b_ffn1; lw.w_ffn2 = w->w_ffn2; lw.b_ffn2 = w->b_ffn2;
   lw.w_ffn1_u = w->w_ffn1_u; lw.w_ffn2_u = w->w_ffn2_u; lw.w_ffn1_n = w->w_ffn1_n; lw.ln2_g = w->ln2_g; lw.ln2_b = w->ln2_b; lw.d_ffn = w->d_ffn;
+  if (w->w_out_u && tiles >= 2 && (g_pair & 4) && g_fusion >= 2 && w->d_ffn >= 512 && w->d_ffn <= FF_MAX_DFFN && w->d_ffn % 256 == 0 && w->w_ffn1_u &&
+      w->w_ffn2_u && w->ln1_g && w->ln1_b) {
+    // s = LN1(src + output_proj(sampled)) as fp32 rows + the FFN's bf16 tile image in ONE kernel, then the fused FFN      MSDA:124, ENC:208-213
+    DeviceInfo* di;
+    if ((rc = device_info(&di))) return rc;
+    FfnWorkspace fw = carve_ffn(ffn_ws, (size_t)rows, w->d_ffn);
+    if (fw.bytes > workspace_bytes - (size_t)(ffn_ws - base)) return fail(AXVS_E_WORKSPACE, "msda_layer: FFN workspace too small");
+    MsdaTailParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.samp = samp; tp.resid = src; tp.w = reinterpret_cast<const uint8_t*>(w->w_out_u); tp.bias = w->b_out; tp.ln_g = w->ln1_g; tp.ln_b = w->ln1_b;
+    tp.out = fw.s3; tp.img = fw.s_img; tp.rows = rows; tp.tiles = tiles; tp.eps = 1e-5f;
+    {
+      ProfScope ps(KC_MSDATAIL, 2.0 * rows * 256.0 * 256.0, (double)rows * (512.0 + 1024.0 + 1024.0 + 512.0), st);
+      const int pair_tiles = (tiles + 1) / 2, max_pairs = di->sms / 2;
+      msda_tail_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), QD_THREADS, QP_SMEM_BYTES, st>>>(tp);
+    }
+    AXVS_CHECK_LAUNCH("msda_tail_pair_kernel");
+    return ffn_fused_launch(fw.s_img, fw.s3, out, &lw, rows, st);
+  }
+  // y = src + output_proj(sampled)                                                                   MSDA:124, ENC:208
+  p = gemm_params(samp, 256, rows, 256, w->w_out, 256, 0, w->b_out, 256, 1.f, 0, y, 256, 0, 0, src);
+  if ((rc = launch_gemm(p, st))) return rc;
+  // out = LN2(s + FFN(s)), s = LN1(y)                                                                ENC:209-213
   return axvs_ln_ffn_fwd(y, out, &lw, rows, ffn_ws, workspace_bytes - (size_t)(ffn_ws - base), stream);
 }
 

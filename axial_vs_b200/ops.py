@@ -613,7 +613,7 @@ def pack_msda_layer(p: Dict[str, torch.Tensor], n_levels: int, n_points: int) ->
     # fused front end (msda_front_pair_kernel): [offsets | logits rows zero-padded to 384 ; value_proj] as one unit image + bias
     w_front = torch.cat((w_oa[:384], g("self_attn.value_proj.weight")), 0).contiguous()
     b_front = torch.cat((b_oa[:384], g("self_attn.value_proj.bias"))).contiguous()
-    ts += [pack_weight_units(w_front), b_front]
+    ts += [pack_weight_units(w_front), b_front, pack_weight_units(g("self_attn.output_proj.weight"))]
     return PackedMsda(ts, p["linear1.weight"].shape[0], n_levels, n_points)
 
 

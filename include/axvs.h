@@ -297,6 +297,8 @@ typedef struct axvs_msda_weights {
   const void* w_front_u; const float* b_front;   /* optional (NULL: two generic GEMMs instead): axvs_pack_weight_units (k_major 0) of
                                                     [w_oa rows zero-padded to 384 ; value_proj.weight] = [640, 256] and the matching bias [640]:
                                                     value and offsets | logits projections in one pass over src / pos (4 points per level) */
+  const void* w_out_u;                           /* optional (NULL: generic GEMM + LayerNorm kernel): axvs_pack_weight_units (k_major 0) of
+                                                    output_proj.weight: output projection + residual + norm1 in one kernel */
   int d_ffn, n_levels, n_points;
 } axvs_msda_weights;
 size_t axvs_msda_layer_workspace_bytes(int rows, int d_ffn);

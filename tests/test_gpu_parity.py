@@ -824,9 +824,12 @@ def test_msda_layer_oracle_config_sizes(O, n, shapes):
 
 @pytest.mark.parametrize("n,shapes", [(2, [(21, 21), (41, 41), (81, 81)]), (3, [(5, 7), (10, 13), (20, 27)]), (1, [(4, 5), (7, 9), (9, 14)])])
 def test_msda_front_kernel_matches_generic_gemms(ops, n, shapes):
-    """The fused front end (msda_front_pair_kernel: value + offsets | logits projections in one pass, head-major value rows) against
-    the two generic GEMMs it replaces (pair-mode bit 4 off): same bf16 operands, same accumulation order -> the layer output agrees
-    to fp32 noise; even / odd / tiny tile counts, with the positional table broadcast over the images and materialised per image."""
+    """The fused MSDeformAttn kernels (msda_front_pair_kernel: value + offsets | logits projections in one pass, head-major value rows;
+    msda_tail_pair_kernel: output projection + residual + LayerNorm1 -> fp32 rows + the FFN's tile image) against the generic GEMMs /
+    LayerNorm kernel they replace (pair-mode bit 4 off): same bf16 operands and accumulation order in the GEMMs; LayerNorm1 uses one-pass
+    statistics instead of two-pass ones, so a few elements of the FFN's bf16 input round the other way -> agreement at the level of single
+    bf16 flips (<= 2e-3 of the output range, measured 4e-4), far inside the 1e-2 parity tolerance.  Even / odd / tiny tile counts, with
+    the positional table broadcast over the images and materialised per image."""
     from axial_vs_b200 import msda
     p = synth.msda_layer_params(77)
     Len = sum(h * w for h, w in shapes)
@@ -842,7 +845,7 @@ def test_msda_front_kernel_matches_generic_gemms(ops, n, shapes):
                 generic = layer(src, pos, ref, shapes)
             finally:
                 ops.set_pair_mode(prev)
-        assert nerr(fused, generic) < 1e-5
+        assert nerr(fused, generic) < 2e-3
 
 
 def test_within_clip_encoder_golden(golden):
