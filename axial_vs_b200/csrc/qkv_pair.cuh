@@ -13,7 +13,8 @@ namespace axvs {
 
 constexpr int QP_W_SLOTS = 5;                   // half units
 constexpr int QP_WH = 16384;
-constexpr int QP_SMEM_BYTES = QD_A_SLOTS * 2 * TF_KB + QP_W_SLOTS * QP_WH + QK_STAGE_BYTES + QK_BIAS_BYTES + 512;
+constexpr int QP_STAGE_BYTES = 8 * 4096;        // per epilogue warp: two 32 rows x 64 B staging buffers (bulk stores read one while the next is written)
+constexpr int QP_SMEM_BYTES = QD_A_SLOTS * 2 * TF_KB + QP_W_SLOTS * QP_WH + QP_STAGE_BYTES + QK_BIAS_BYTES + 512;
 static_assert(QP_SMEM_BYTES <= 232448, "qkv_pair_kernel exceeds the 227 KiB shared-memory limit");
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_pair_kernel(const QkvDirectParams p) {
@@ -22,7 +23,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
   uint8_t* a_ring = smem;
   uint8_t* w_ring = a_ring + QD_A_SLOTS * 2 * TF_KB;
   uint8_t* stage_all = w_ring + QP_W_SLOTS * QP_WH;
-  float* sbias = reinterpret_cast<float*>(stage_all + QK_STAGE_BYTES);
+  float* sbias = reinterpret_cast<float*>(stage_all + QP_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 768);
   uint64_t* a_full = bars;                      // [QD_A_SLOTS], one arrive per producer warp
   uint64_t* a_empty = a_full + QD_A_SLOTS;      // tcgen05.commit after the slot's copies
@@ -59,34 +60,99 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
     // =============================================================== epilogue: group g drains heads 2g, 2g+1 of every chunk
     const int g = warp >> 2;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint8_t* stg = stage_all + warp * 2048;
+    uint8_t* stg = stage_all + warp * 4096;
     uint32_t cnt = 0;                                          // chunks consumed (stage = cnt & 1)
+    uint32_t rnd = 0;                                          // head rounds done (staging buffer = rnd & 1)
+    AXVS_PROF_DECL(6)
     for (int pt = pair; pt < pair_tiles; pt += npairs) {
       const int tile = 2 * pt + (int)rank;                     // may be == p.tiles (odd tile count): every row masked
       const int row0 = tile * 128 + (warp & 3) * 32;           // first row of this warp
-      // unit-major destinations of the FOUR rows this lane stores after the transpose (rows 8 i + lane / 4 of the warp's 32), for head 0:
-      // region row of q and of k (v = k + n).  Computed once per tile; the single-CTA kernel fetches them from the owner lane with two
-      // shuffles per store, which made the epilogue (the bottleneck of this kernel) 8 shared-memory-pipe instructions per head longer.
-      uint32_t seq4[4], pos_q4[4], pos_k4[4];                  // first region row of the sequence (head 0), position of the q / k row inside the region
       if (p.swz_N > 0) {
+        // Unit-major destination: lane = row.  The lane's 64-byte row goes to the staging buffer already permuted the way the attention
+        // kernel wants it in global memory ((pos >> 1) & 3), so a run of rows of one frame is one contiguous piece of the (sequence, head)
+        // region: the first lane of every run writes it with ONE bulk copy (shared -> global, async proxy).  The previous version read the
+        // staging tile back and issued 16-byte global stores: 8 more LSU instructions per round on a load/store pipe that the converting
+        // producers keep full (wait profile: 750 clk per round in that phase).
+        const int r = row0 + lane;
+        const int seq = r / p.swz_N, ii = r - seq * p.swz_N;
+        const int f = ii / p.swz_n, j = ii - f * p.swz_n;
+        const uint32_t seq_row = (uint32_t)seq * 24u * p.swz_N;                       // first region row of the sequence (head 0)
+        const uint32_t pos_q = (uint32_t)ii, pos_k = (uint32_t)(p.swz_N + 2 * f * p.swz_n + j);
+        int run = min(min(p.swz_n - j, 32 - lane), p.rows - r);                       // rows of my run if I am its first lane
+        if (lane != 0 && j != 0) run = 0;
+#pragma unroll 1
+        for (int rt = 0; rt < 6; ++rt, ++cnt) {
+          const int st = cnt & 1;                              // 6 chunks per tile: even, so st == rt & 1
+          AXVS_PROF_WAIT(0, mbar_wait_cluster(&s_full[st], (cnt >> 1) & 1))
+          tc_fence_after();
+          const uint32_t t_s = tmem + lane_base + 256 + st * 128;
+          const int which = rt >> 1;
+          const uint32_t pos = which == 0 ? pos_q : pos_k + (which == 2 ? (uint32_t)p.swz_n : 0u);
+          const uint32_t key = (pos >> 1) & 3u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = row0 + 8 * i + (lane >> 2);
-          const int seq = r / p.swz_N, ii = r - seq * p.swz_N;
-          const int f = ii / p.swz_n, j = ii - f * p.swz_n;
-          seq4[i] = (uint32_t)seq * 24u * p.swz_N;
-          pos_q4[i] = (uint32_t)ii;
-          pos_k4[i] = (uint32_t)(p.swz_N + 2 * f * p.swz_n + j);
+          for (int cc = 0; cc < 2; ++cc, ++rnd) {              // one head (32 columns) at a time
+            const int c = 2 * g + cc;
+            float v[32];
+            float4 bb[8];                                      // the round's 32 biases, requested before the accumulator load so that the
+            {                                                  // shared-memory latency (a busy load/store pipe) overlaps it
+              const float4* b4 = reinterpret_cast<const float4*>(sbias + rt * 128 + c * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) bb[q] = b4[q];
+            }
+            AXVS_PROF_MARK(t_ld_)
+            tmem_ld32(t_s + 32 * c, v);
+            tmem_ld_wait();
+            AXVS_PROF_SPAN(1, t_ld_)
+            if (cc == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster_relaxed(&s_empty[st], 0);
+            }
+            AXVS_PROF_MARK(t_cv_)
+            uint8_t* sb = stg + (rnd & 1) * 2048;
+            bulk_wait_group_read<1>();                         // the copies of round rnd - 2 have read this buffer
+            __syncwarp();
+            AXVS_PROF_SPAN(4, t_cv_)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b0 = bb[2 * q], b1 = bb[2 * q + 1];
+              uint4 u;
+              const float2 t0 = add_f32x2(make_float2(v[8 * q], v[8 * q + 1]), make_float2(b0.x, b0.y));
+              const float2 t1 = add_f32x2(make_float2(v[8 * q + 2], v[8 * q + 3]), make_float2(b0.z, b0.w));
+              const float2 t2 = add_f32x2(make_float2(v[8 * q + 4], v[8 * q + 5]), make_float2(b1.x, b1.y));
+              const float2 t3 = add_f32x2(make_float2(v[8 * q + 6], v[8 * q + 7]), make_float2(b1.z, b1.w));
+              u.x = pack_bf16x2(t0.x, t0.y);
+              u.y = pack_bf16x2(t1.x, t1.y);
+              u.z = pack_bf16x2(t2.x, t2.y);
+              u.w = pack_bf16x2(t3.x, t3.y);
+              *reinterpret_cast<uint4*>(sb + lane * 64 + (((uint32_t)q ^ key) << 4)) = u;
+            }
+            AXVS_PROF_MARK(t_fn_)
+            fence_proxy_async_smem();
+            __syncwarp();
+            AXVS_PROF_SPAN(5, t_fn_)
+            AXVS_PROF_SPAN(2, t_cv_)
+            AXVS_PROF_MARK(t_st_)
+            if (run > 0) {
+              const int head = (rt & 1) * 4 + c;
+              tma_bulk_s2g(reinterpret_cast<uint8_t*>(p.qkv) + (size_t)(seq_row + (uint32_t)head * 3u * p.swz_N + pos) * 64, sb + lane * 64,
+                           (uint32_t)run * 64u);
+            }
+            bulk_commit_group();
+            AXVS_PROF_SPAN(3, t_st_)
+          }
         }
+        continue;
       }
+      // head-major destination (mma.sync attention baseline): 2 KiB per-warp transpose so every store instruction writes 512 contiguous bytes
 #pragma unroll 1
       for (int rt = 0; rt < 6; ++rt, ++cnt) {
-        const int st = cnt & 1;                                // 6 chunks per tile: even, so st == rt & 1
+        const int st = cnt & 1;
         mbar_wait_cluster(&s_full[st], (cnt >> 1) & 1);
         tc_fence_after();
         const uint32_t t_s = tmem + lane_base + 256 + st * 128;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {                       // one head (32 columns) at a time
+        for (int cc = 0; cc < 2; ++cc) {
           const int c = 2 * g + cc;
           float v[32];
           tmem_ld32(t_s + 32 * c, v);
@@ -96,7 +162,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster_relaxed(&s_empty[st], 0);
           }
-          // bias + bf16, then a 2 KiB per-warp transpose so every store instruction writes 512 contiguous bytes
           {
             const float4* b4 = reinterpret_cast<const float4*>(sbias + rt * 128 + c * 32);
 #pragma unroll
@@ -117,18 +182,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
           __syncwarp();
           {
             const int which = rt >> 1, head = (rt & 1) * 4 + c;
-            if (p.swz_N > 0) {
-              const uint32_t head_off = (uint32_t)head * 3u * p.swz_N;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rl = 8 * i + (lane >> 2), piece = lane & 3;
-                const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((piece ^ ((rl >> 1) & 3)) << 4));
-                const uint32_t pos = which == 0 ? pos_q4[i] : pos_k4[i] + (which == 2 ? (uint32_t)p.swz_n : 0u);
-                const uint32_t key = (pos >> 1) & 3u;
-                if (row0 + rl < p.rows)
-                  *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.qkv) + (size_t)(seq4[i] + pos + head_off) * 64 + ((piece ^ key) << 4)) = u;
-              }
-            } else {
             uint8_t* dst = reinterpret_cast<uint8_t*>(p.qkv + ((size_t)(which * 8 + head) * p.rows + row0) * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -136,12 +189,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
               const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((piece ^ ((rl >> 1) & 3)) << 4));
               if (row0 + rl < p.rows) *reinterpret_cast<uint4*>(dst + rl * 64 + piece * 16) = u;
             }
-            }
           }
           __syncwarp();
         }
       }
     }
+    bulk_wait_group<0>();                                      // every bulk store of this thread has completed
+    AXVS_PROF_FLUSH(24, 6, rank == 0 && warp == 0 && lane == 0)
   } else if (warp < 8 + QD_PRODUCER_WARPS) {
     // =============================================================== converting A producers
     // Work unit = one K-block of the lane's 8 rows: a BURST of 8 src + 8 pos loads, then convert + store all of them.  (The first version
@@ -154,6 +208,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
     uint32_t cnt = 0;
     float4 sv[8], qv[8];
     uint32_t crow[8];                                          // canonical token of this lane's 8 rows (0xFFFFFFFF = past the end)
+    AXVS_PROF_DECL(2)
     for (int pt = pair; pt < pair_tiles; pt += npairs) {
       const int tile = 2 * pt + (int)rank;
 #pragma unroll
@@ -180,8 +235,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
           for (int j = 0; j < 8; ++j) qv[j] = z;
         }
         const uint32_t slot = cnt % QD_A_SLOTS, phase = (cnt / QD_A_SLOTS) & 1;
-        mbar_wait_cluster(&a_empty[slot], phase ^ 1);
+        AXVS_PROF_WAIT(0, mbar_wait_cluster(&a_empty[slot], phase ^ 1))
         uint8_t* dst = a_ring + slot * 2 * TF_KB;
+        AXVS_PROF_MARK(t_cv_)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int r = pw * 16 + 2 * j + half;
@@ -196,9 +252,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
         }
         fence_proxy_async_smem();
         __syncwarp();
+        AXVS_PROF_SPAN(1, t_cv_)
         if (lane == 0) mbar_arrive(&a_full[slot]);
       }
     }
+    AXVS_PROF_FLUSH(48, 2, rank == 0 && pw == 0 && lane == 0)
   } else if (warp == 16 && lane == 0) {
     // =============================================================== weight producer: my half (64 rows) of each of the 12 units per tile
     uint32_t slot = 0, phase = 0;
@@ -238,13 +296,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
     const uint32_t idesc = umma_idesc_bf16(256, 128);
     const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring);
     uint32_t a_cnt = 0, w_slot = 0, w_phase = 0, ccnt = 0;     // ccnt: chunks issued
+    AXVS_PROF_DECL(3)
     for (int pt = pair; pt < pair_tiles; pt += npairs) {
       // both CTAs' A operands: four pair slots each -> TMEM.  These copies are ordered by the tensor pipe behind every UMMA of the
       // previous tile (issued earlier by this thread), which still reads the old contents.
 #pragma unroll 1
       for (int kb = 0; kb < 4; ++kb, ++a_cnt) {
         const uint32_t slot = a_cnt % QD_A_SLOTS;
-        mbar_wait_cluster(&a_full[slot], (a_cnt / QD_A_SLOTS) & 1);
+        AXVS_PROF_WAIT(2, mbar_wait_cluster(&a_full[slot], (a_cnt / QD_A_SLOTS) & 1))
         tc_fence_after();
         const uint32_t sa = a_ring_addr + slot * 2 * TF_KB;
         if (elect_one()) {
@@ -258,12 +317,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
       for (int rt = 0; rt < 6; ++rt, ++ccnt) {
         const int g = rt & 1;
         const uint32_t gc = ccnt >> 1;                         // chunks already issued to group g (6 per tile: even count)
-        mbar_wait_cluster(&s_empty[g], (gc & 1) ^ 1);
+        AXVS_PROF_WAIT(1, mbar_wait_cluster(&s_empty[g], (gc & 1) ^ 1))
         tc_fence_after();
         const uint32_t t_a = tmem + (rt < 4 ? 0 : 128);        // A1 for the q / k chunks, A2 for the v chunks
 #pragma unroll 1
         for (int kg = 0; kg < 2; ++kg) {
-          mbar_wait_cluster(&w_full[w_slot], w_phase);
+          AXVS_PROF_WAIT(0, mbar_wait_cluster(&w_full[w_slot], w_phase))
           tc_fence_after();
           const uint32_t ws = w_slot;
           if (++w_slot == QP_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
@@ -272,6 +331,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
         }
       }
     }
+    AXVS_PROF_FLUSH(40, 3, lane == 0)
   }
 
   tc_fence_before();

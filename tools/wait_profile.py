@@ -56,9 +56,13 @@ elif which == "attn":
     show("attn_tc producer", 60, ["slot empty"])
 elif which == "qkvd":
     show("qkv_direct MMA warp", 40, ["w_full", "s_empty", "a_full"])
-    show("qkv_direct epilogue g0", 44, ["s_full"])
-    show("qkv_direct epilogue g1", 46, ["s_full"])
-    show("qkv_direct A producer warp 0", 48, ["a_empty", "-"])
+    if "--pair-ctas" in sys.argv:
+        show("qkv_pair epilogue warp 0", 24, ["s_full", "[tmem ld]", "[cvt + sts]", "[bulk issue]", "[bulk wait]", "[fence]"])
+        show("qkv_pair A producer warp 0", 48, ["a_empty", "[cvt + sts]"])
+    else:
+        show("qkv_direct epilogue g0", 44, ["s_full"])
+        show("qkv_direct epilogue g1", 46, ["s_full"])
+        show("qkv_direct A producer warp 0", 48, ["a_empty", "-"])
 elif which == "qkv":
     show("qkv MMA warp", 40, ["w_full", "s_empty", "a_full"])
     show("qkv epilogue g0", 44, ["s_full"])
