@@ -49,6 +49,8 @@ struct AttnTcParams {
   int num_units;              // num_seq * 8 * QB * NCH
   int slots, slot_bytes;      // shared-memory ring
   int single;                 // 1: a unit is a whole (sequence, head) region -> one bulk copy
+  int tm_rpad;                // > 0: frame-major output rows (row = t * tm_rpad + sequence * n + j, see TrajParams), no x_diag image
+  uint32_t n_magic;           // floor(2^32 / n) + 1: qi / n == umulhi(qi, n_magic) for qi < 2^16
   float scale_log2e;
 };
 
@@ -293,6 +295,14 @@ __global__ void __launch_bounds__((NT16 >= 1 && NT16 <= 3) ? 128 * 4 + 96 : (NT1
       // (those cost one L1 wavefront each and bound the first version of this kernel).
       const int kb = head >> 1, ch0 = (head & 1) * 4;
       const int q_w0 = u.qb * 128 + (warp & 3) * 32;          // query index of this warp's first row
+      uint32_t orow4[4];                                      // tile-order row of the four rows this lane stores (0xFFFFFFFF: past the sequence)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int qi = q_w0 + 8 * i + (lane >> 2);
+        if (qi >= N) orow4[i] = 0xFFFFFFFFu;
+        else if (p.tm_rpad) { const int t = (int)__umulhi((uint32_t)qi, p.n_magic); orow4[i] = (uint32_t)(t * p.tm_rpad + (u.sh >> 3) * n + (qi - t * n)); }
+        else orow4[i] = (uint32_t)(seq_row0 + qi);
+      }
       AXVS_PROF_WAIT(1, mbar_wait(&o_full[g], par))
       tc_fence_after();
 #pragma unroll
@@ -327,11 +337,11 @@ __global__ void __launch_bounds__((NT16 >= 1 && NT16 <= 3) ? 128 * 4 + 96 : (NT1
             const int rr = 8 * i + (lane >> 2), piece = lane & 3;
             const uint4 w = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
             const int qi = q_w0 + rr;                          // query index inside the sequence
-            if (qi < N) {
-              const size_t r = seq_row0 + qi;
+            if (orow4[i] != 0xFFFFFFFFu) {
+              const size_t r = orow4[i];
               const size_t off = ((r >> 7) * 4 + kb) * (size_t)ATT2_KB + sw128_offset((uint32_t)(r & 127), ch0 + piece);
               *reinterpret_cast<uint4*>(dst + off) = w;
-              if ((unsigned)(qi - f * n) < (unsigned)n) *reinterpret_cast<uint4*>(p.xd_img + off) = w;   // qi / n == f
+              if (!p.tm_rpad && (unsigned)(qi - f * n) < (unsigned)n) *reinterpret_cast<uint4*>(p.xd_img + off) = w;   // qi / n == f
             }
           }
           __syncwarp();

@@ -61,8 +61,9 @@ std::atomic<int> g_fusion{4};   // 0-3: earlier kernel generations kept as valid
 std::atomic<int> g_attn_core{1};   // 1 = tcgen05 attention core (attn_tc.cuh), 0 = the mma.sync kernels (validation baseline)
 // CTA-pair (cta_group::2) kernels, bit mask: 2 = traj_pair_kernel, 4 = qkv_pair_kernel, 8 = ffn_n256_pair_kernel (default: all three; each is
 // bit-identical to its single-CTA kernel and 4-8 % faster because every CTA stages only half of each weight unit; bit 4 also selects the
-// fused MSDeformAttn front end, msda_front_pair_kernel).  AXVS_PAIR overrides the default for A/B runs.
-std::atomic<int> g_pair{getenv("AXVS_PAIR") ? atoi(getenv("AXVS_PAIR")) : 14};
+// fused MSDeformAttn front end, msda_front_pair_kernel); 16 = frame-major row order of the temporal stage (TrajParams::tm_rpad: the attention
+// kernel writes no x_diag image, bit-identical results).  AXVS_PAIR overrides the default for A/B runs.
+std::atomic<int> g_pair{getenv("AXVS_PAIR") ? atoi(getenv("AXVS_PAIR")) : 30};
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 constexpr int PROF_MAX = 8192;
 struct Profiler {
@@ -276,7 +277,8 @@ TaWorkspace carve_ta(void* base, size_t rows, int F) {
   w.kv2 = take(rows * (size_t)F * 512 * 2);
   w.o = take(rows * 256 * 2);
   const size_t tiles = (rows + 127) / 128;
-  w.x_img = reinterpret_cast<uint8_t*>(take(tiles * (size_t)F * 4 * TF_KB));
+  const size_t tiles_tm = (size_t)F * ((rows / (size_t)F + 127) / 128);          // frame-major row order: every frame group padded to whole tiles
+  w.x_img = reinterpret_cast<uint8_t*>(take((tiles > tiles_tm ? tiles : tiles_tm) * (size_t)F * 4 * TF_KB));
   w.xd_img = reinterpret_cast<uint8_t*>(take(tiles * 4 * TF_KB));
   w.a1_img = reinterpret_cast<uint8_t*>(take(tiles * 4 * TF_KB));
   w.a2_img = reinterpret_cast<uint8_t*>(take(tiles * 4 * TF_KB));
@@ -322,7 +324,7 @@ int blocks_for(long long work_items, int per_block, int sms) {
 
 extern "C" {
 
-int axvs_version(void) { return 120; }
+int axvs_version(void) { return 121; }
 #ifndef AXVS_BUILD_ID
 #define AXVS_BUILD_ID "unknown"
 #endif
@@ -438,6 +440,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
     const int tiles = (int)((rows + 127) / 128);
     const int nt16_f = (n + 15) / 16;
     bool use_tc = false;                                         // tcgen05 attention core (needs the chunk-permuted q|k|v of qkv_direct)
+    int tm_rpad = 0, tm_tiles = tiles;                           // frame-major row order of the temporal stage (TrajParams::tm_rpad)
     {
     if (g_fusion >= 4 && v_in == q_in) {
       use_tc = g_attn_core == 1 && (n + 15) / 16 * 16 <= 224 && rows * 24 < (size_t)0xffffffffu;
@@ -486,7 +489,13 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       AttnTcParams ap;
       memset(&ap, 0, sizeof(ap));
       ap.qkv = ws.qkv; ap.rows_total = rows; ap.x_img = ws.x_img; ap.xd_img = ws.xd_img;
-      ap.tiles = tiles; ap.N = N; ap.n = n; ap.F = F; ap.NP = nt16_f * 16; ap.QB = (N + 127) / 128;
+      if ((g_pair & 16) && N < 65536 && (size_t)F * (((size_t)num_seq * n + 127) / 128 * 128) < (size_t)0x7fffffff) {
+        tm_rpad = (int)(((size_t)num_seq * n + 127) / 128 * 128);
+        tm_tiles = F * (tm_rpad / 128);
+      }
+      ap.tm_rpad = tm_rpad;
+      ap.n_magic = (uint32_t)(0x100000000ull / (unsigned)n) + 1u;
+      ap.tiles = tm_tiles; ap.N = N; ap.n = n; ap.F = F; ap.NP = nt16_f * 16; ap.QB = (N + 127) / 128;
       ap.scale_log2e = kScaleLog2e;
       // softmax groups (= TMEM buffers) and frames per unit: the most groups that still take two frames per unit
       const int max_g = nt16_f <= 3 ? 4 : (nt16_f == 5 || nt16_f == 6) ? 2 : 3;   // register budget of the softmax warps (launch bounds per NT16)
@@ -521,7 +530,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       const size_t smem_b = (size_t)slots * ap.slot_bytes + 4 * AT_MAX_G * 2048 + 512;
       const int grid = ap.num_units < d->sms ? ap.num_units : d->sms;
       {
-        ProfScope ps(KC_ATTNTC, 4.0 * num_seq * (double)N * N * 256, (double)rows * (1536.0 + (F + 1) * 512.0), st);
+        ProfScope ps(KC_ATTNTC, 4.0 * num_seq * (double)N * N * 256, (double)rows * (1536.0 + (F + (tm_rpad ? 0 : 1)) * 512.0), st);
         const int threads = 128 * G + 96;
         switch (nt16_f <= 6 ? nt16_f : 0) {
           case 1: spatial_attn_tc_kernel<1><<<grid, threads, smem_b, st>>>(ap); break;
@@ -596,10 +605,12 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
     tp.map_mode = map; tp.dims = dims;
     tp.scale_log2e = kScaleLog2e;
     tp.ln_g = ln_g; tp.ln_b = ln_b; tp.ln_img = ln_img; tp.ln_eps = 1e-5f;
+    if (tm_rpad) { tp.tm_rpad = tm_rpad; tp.tm_rt = num_seq * n; tp.tm_n = n; tp.rows = F * tm_rpad; tp.tiles = tm_tiles; }
     {
+      const int tiles = tp.tiles;
       const bool traj_pair = g_fusion >= 4 && (g_pair & 2) && tiles >= 2;
       ProfScope ps(traj_pair ? KC_TRAJPAIR : g_fusion >= 4 ? KC_TRAJTS : KC_TRAJ, 2.0 * rows * 256.0 * 256.0 * (2.0 + 2.0 * F) + 4.0 * rows * F * 256.0,
-                   (double)rows * (512.0 * (F + 1) + 1024.0 + (resid ? 1024.0 : 0.0) + (ln_img ? 1536.0 : 0.0)), st);
+                   (double)rows * (512.0 * (F + (tm_rpad ? 0 : 1)) + 1024.0 + (resid ? 1024.0 : 0.0) + (ln_img ? 1536.0 : 0.0)), st);
       if (traj_pair) {
         const int pair_tiles = (tiles + 1) / 2, max_pairs = d->sms / 2;
         traj_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), TF_THREADS, TP_SMEM_BYTES, st>>>(tp);

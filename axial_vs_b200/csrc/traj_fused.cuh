@@ -49,7 +49,29 @@ struct TrajParams {
   const float* ln_b;
   uint8_t* ln_img;         // [ceil(rows/128)][4][16 KiB], indexed by CANONICAL row
   float ln_eps;
+  // Frame-major row order (tm_rpad > 0; traj_ts / traj_pair only): tile-order row r = t * tm_rpad + seq * tm_n + j, i.e. all tokens of
+  // frame 0 first (padded to a multiple of 128 rows), then frame 1, ...  The temporal stage is row-wise, so any order is valid -- and in
+  // this one every tile has ONE frame index t, whose x_t tile IS the tile's x_diag: the attention kernel writes no x_diag image
+  // (0.5 KiB per token less to write and to read back), `xd_img` is unused, rows = F * tm_rpad, tiles = rows / 128.
+  int tm_rpad;             // rows per frame group, multiple of 128 (0 = pass order)
+  int tm_rt;               // valid rows per frame group = sequences * tm_n
+  int tm_n;                // tokens of one frame in a sequence
 };
+
+// canonical token of tile-order row r, -1 for a padding row / a row past the end
+__device__ __forceinline__ int traj_row_canonical(int r, const TrajParams& p) {
+  if (p.tm_rpad == 0) return r < p.rows ? pass_to_canonical(r, p.map_mode, p.dims) : -1;
+  const int t = r / p.tm_rpad, rem = r - t * p.tm_rpad;
+  if (t >= p.F || rem >= p.tm_rt) return -1;
+  const int seq = rem / p.tm_n, j = rem - seq * p.tm_n;
+  return pass_to_canonical((seq * p.F + t) * p.tm_n + j, p.map_mode, p.dims);
+}
+// the four K-block images of a tile's x_diag operand
+__device__ __forceinline__ const uint8_t* traj_xd_tile(int tile, const TrajParams& p) {
+  if (p.tm_rpad == 0) return p.xd_img + (size_t)tile * 4 * TF_KB;
+  const int t = tile / (p.tm_rpad >> 7);
+  return p.x_img + ((size_t)t * p.tiles + tile) * 4 * TF_KB;
+}
 
 __global__ void __launch_bounds__(TF_THREADS, 1) traj_fused_kernel(const TrajParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];

@@ -65,6 +65,9 @@ __device__ __forceinline__ void tmem_cp_kblock_pair(uint32_t taddr, uint32_t sme
         : "memory");
 }
 
+// Frame-major row order: both tiles of pair `pt` hold frame-0 tokens (the tile's x_diag image is its x_0 image) -> x_0 is neither loaded
+// nor copied a second time.  Evaluated identically by the producers, the relay and the issuer.
+#define TP_SKIP0(pt) (p.tm_rpad != 0 && 2 * (pt) + 1 < (p.tm_rpad >> 7))
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_pair_kernel(const TrajParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -231,7 +234,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
       // 128-byte row segments.  resid + bias are fetched BEFORE waiting for the accumulator (latency hides behind GEMM 3).
       {
         const int r = tile * 128 + row_in_tile;
-        const int my_orow = (r < p.rows) ? pass_to_canonical(r, p.map_mode, p.dims) : -1;
+        const int my_orow = traj_row_canonical(r, p);
         const int sub = lane >> 3, piece = lane & 7;
         int orow[8];
 #pragma unroll
@@ -375,9 +378,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
       for (int pt = pair; pt < pair_tiles; pt += npairs) {
         int tile = 2 * pt + (int)rank;
         if (tile >= p.tiles) tile = p.tiles - 1;                 // dummy tile of an odd count: load something valid
+        const bool skip0 = TP_SKIP0(pt);
 #pragma unroll 1
         for (int item = 0; item < 4 * (F + 1); ++item) {
-          const uint8_t* src = (item < 4) ? p.xd_img + ((size_t)tile * 4 + item) * TF_KB
+          if (skip0 && item >= 4 && item < 8) continue;          // x_0 of a frame-0 tile is its x_diag: already in tensor memory
+          const uint8_t* src = (item < 4) ? traj_xd_tile(tile, p) + (size_t)item * TF_KB
                                           : p.x_img + (((size_t)((item >> 2) - 1) * p.tiles + tile) * 4 + (item & 3)) * TF_KB;
           mbar_wait_cluster(&a_empty[slot], phase ^ 1);
           mbar_arrive_expect_tx(&a_full[slot], TF_KB);
@@ -419,8 +424,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
 #pragma unroll 1
         for (int rr = lane; rr < 128; rr += 32) {
           const int r = tile * 128 + rr;
-          if (r < p.rows) {
-            const char* src = reinterpret_cast<const char*>(p.resid + (size_t)pass_to_canonical(r, p.map_mode, p.dims) * 256);
+          const int cr = traj_row_canonical(r, p);
+          if (cr >= 0) {
+            const char* src = reinterpret_cast<const char*>(p.resid + (size_t)cr * 256);
 #pragma unroll
             for (int l = 0; l < 8; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128 * l));
           }
@@ -452,7 +458,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
           fwd_a();
           fwd_w(4);
 #pragma unroll 1
-          for (int f = 0; f < F; ++f) { fwd_a(); fwd_w(8); }
+          for (int f = 0; f < F; ++f) { if (!(f == 0 && TP_SKIP0(pt))) fwd_a(); fwd_w(8); }
           fwd_w(4);
         }
       }
@@ -510,7 +516,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
 #pragma unroll 1
         for (int f = 0; f < F; ++f) {
           AXVS_TRACE(trc_, 60 + 2 * f)
-          copy_tile();
+          if (!(f == 0 && TP_SKIP0(pt))) copy_tile();            // frame-0 tiles: XA still holds x_diag = x_0
           AXVS_TRACE(trc_, 61 + 2 * f)
 #pragma unroll 1
           for (int ci = 0; ci < 4; ++ci) {

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
       // 128-byte row segments.  resid + bias are fetched BEFORE waiting for the accumulator (latency hides behind GEMM 3).
       {
         const int r = tile * 128 + row_in_tile;
-        const int my_orow = (r < p.rows) ? pass_to_canonical(r, p.map_mode, p.dims) : -1;
+        const int my_orow = traj_row_canonical(r, p);
         const int sub = lane >> 3, piece = lane & 7;
         int orow[8];
 #pragma unroll
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
 #pragma unroll 1
         for (int item = 0; item < 4 * (F + 1); ++item, ++cnt) {
           const uint32_t slot = cnt % TT_A_SLOTS, phase = (cnt / TT_A_SLOTS) & 1;
-          const uint8_t* src = (item < 4) ? p.xd_img + ((size_t)tile * 4 + item) * TF_KB
+          const uint8_t* src = (item < 4) ? traj_xd_tile(tile, p) + (size_t)item * TF_KB
                                           : p.x_img + (((size_t)((item >> 2) - 1) * p.tiles + tile) * 4 + (item & 3)) * TF_KB;
           mbar_wait(&a_empty[slot], phase ^ 1);
           mbar_arrive_expect_tx(&a_full[slot], TF_KB);
@@ -510,8 +510,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) traj_ts_kernel(const TrajParams
 #pragma unroll 1
         for (int rr = lane; rr < 128; rr += 32) {
           const int r = tile * 128 + rr;
-          if (r < p.rows) {
-            const char* src = reinterpret_cast<const char*>(p.resid + (size_t)pass_to_canonical(r, p.map_mode, p.dims) * 256);
+          const int cr = traj_row_canonical(r, p);
+          if (cr >= 0) {
+            const char* src = reinterpret_cast<const char*>(p.resid + (size_t)cr * 256);
 #pragma unroll
             for (int l = 0; l < 8; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128 * l));
           }

@@ -382,8 +382,8 @@ def set_fusion(level: int) -> int:
 
 
 def set_pair_mode(mask: int) -> int:
-    """CTA-pair (cta_group::2) kernels, bit mask: 2 = temporal kernel, 4 = q|k|v projection, 8 = FFN (default 14); 0 = single-CTA
-    kernels everywhere.  Returns the previous mask."""
+    """CTA-pair (cta_group::2) kernels, bit mask: 2 = temporal kernel, 4 = q|k|v projection, 8 = FFN; 16 = frame-major row order between
+    the attention and the temporal kernel (no x_diag image); default 30; 0 = single-CTA kernels, pass-order rows.  Returns the previous mask."""
     return _lib.load().axvs_set_pair_mode(int(mask))
 
 

@@ -59,8 +59,13 @@ int axvs_set_fusion(int level);
 /* CTA-pair kernels (tcgen05 cta_group::2: two SMs of a cluster share one M = 256 instruction stream, each staging half of every
  * weight unit, which halves the shared-memory traffic of the GEMM core: 512 instead of 670 clk per 32 KiB unit).  Bit mask:
  *   2 = fused temporal kernel (traj_pair_kernel), 4 = q|k|v projection (qkv_pair_kernel) and the fused front end of the MSDeformAttn
- *   layer (msda_front_pair_kernel), 8 = FFN (ffn_n256_pair_kernel).  Default 14; every pair kernel is bit-identical to its single-CTA
- *   counterpart (which `0` selects; the MSDeformAttn front end falls back to two generic GEMMs).  Returns the previous mask. */
+ *   layer (msda_front_pair_kernel), 8 = FFN (ffn_n256_pair_kernel); every pair kernel is bit-identical to its single-CTA
+ *   counterpart (which `0` selects; the MSDeformAttn front end falls back to two generic GEMMs).
+ *   16 = frame-major row order between the attention kernel and the temporal kernel: the per-frame attention outputs x_f
+ *   (WC/temporal_attention.py:56) are stored with all tokens of frame 0 first, then frame 1, ... (each group padded to whole 128-row
+ *   tiles), so the x_t tile of a tile of frame-t tokens IS its x_diag (WC/temporal_attention.py:61-63) and no x_diag image is written
+ *   or read (0.5 KiB per token less each way); results are bit-identical to the pass-order layout.
+ *   Default 30.  Returns the previous mask. */
 int axvs_set_pair_mode(int on);
 /* Attention core of the per-frame spatial attention (WC/temporal_attention.py:47-60) at fusion level >= 4.
  *   1 (default): tcgen05 kernel -- Q K^T and P V as UMMAs (scores / probabilities / outputs in tensor memory, operands by TMA),

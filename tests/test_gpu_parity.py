@@ -610,7 +610,7 @@ def _forward_sharded_as_rank(m, cq_local, pf_local, n_clips, rank, world, gather
         dist.get_world_size, dist.get_rank, dist.is_initialized = orig_ws, orig_rk, orig_init
 
 
-PAIR_DEFAULT = 14      # traj_pair | qkv_pair | ffn_n256_pair (csrc/axvs.cu g_pair)
+PAIR_DEFAULT = 30      # traj_pair | qkv_pair | ffn_n256_pair | frame-major temporal rows (csrc/axvs.cu g_pair)
 
 
 def test_pair_mode_ffn_matches(ops, O):
@@ -646,7 +646,7 @@ def test_pair_kernels_bit_identical_to_single_cta(ops, clips, T, H, W):
     outs = {}
     try:
         with torch.no_grad():
-            for mask in (0, 2, 4, 8, PAIR_DEFAULT):
+            for mask in (0, 2, 4, 8, 14, 16, PAIR_DEFAULT):
                 ops.set_pair_mode(mask)
                 outs[mask] = layer(src, pos)[0].clone()
                 torch.cuda.synchronize()
@@ -840,7 +840,7 @@ def test_msda_front_kernel_matches_generic_gemms(ops, n, shapes):
     for pos in (pos1, pos1.expand(n, -1, -1).contiguous(), None):
         with torch.no_grad():
             fused = layer(src, pos, ref[:1].contiguous(), shapes)
-            prev = ops.set_pair_mode(ops.set_pair_mode(14) & ~4)
+            prev = ops.set_pair_mode(ops.set_pair_mode(PAIR_DEFAULT) & ~4)
             try:
                 generic = layer(src, pos, ref, shapes)
             finally:
