@@ -84,7 +84,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
   uint64_t* s_full = w_empty + TP_W_SLOTS;       // [2]
   uint64_t* s_empty = s_full + 2;                // [2]  (the leader's copy is the live one)
   uint64_t* o_ready = s_empty + 2;               //      (leader)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 2);   // o_ready[g]: group g's half of o (heads 4g .. 4g+3) is in tensor memory
   uint32_t* tile_flag = tmem_slot + 2;     // tiles whose frames phase has started (paces the residual prefetcher, warp 11)
 
   const int warp = threadIdx.x >> 5;
@@ -98,7 +98,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
     for (int i = 0; i < TP_A_SLOTS; ++i) { mbar_init(&a_full[i], fullc); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < TP_W_SLOTS; ++i) { mbar_init(&w_full[i], fullc); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
-    mbar_init(o_ready, 16);
+    mbar_init(&o_ready[0], 8);
+    mbar_init(&o_ready[1], 8);
     *tile_flag = 0;
     fence_barrier_init();
   }
@@ -224,7 +225,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_relaxed(o_ready, 0);
+      if (lane == 0) mbar_arrive_cluster_relaxed(&o_ready[g], 0);
       AXVS_TRACE(trc_, tb_ + 41)
       // The residual loads below fill the load/store queue for ~2k clk; issued while the OTHER group still reads its bias from shared
       // memory for o (same queue) they delayed its o_ready arrive -- the start of GEMM 3 -- by that much.  So: wait until both groups
@@ -411,7 +412,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
           push(p.w_pkv, c * 2 + (i & 1));
         }
 #pragma unroll 1
-        for (int u = 0; u < 4; ++u) push(p.w_proj, u);
+        for (int u = 0; u < 4; ++u) push(p.w_proj, ((u & 1) << 1) | (u >> 1));   // K group 0 of both row tiles first (see GEMM 3)
       }
 #if TP_PREFETCH
     } else if (warp == 11 && p.resid != nullptr) {
@@ -500,13 +501,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
         AXVS_TRACE(trc_, 0)
         copy_tile();
         AXVS_TRACE(trc_, 3)
-        stage_wait(0);
-        stage_wait(1);
-        tc_fence_after();
         AXVS_TRACE(trc_, 1)
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) {
           const int half = u >> 1, kg = u & 1;
+          if (kg == 0) { stage_wait(half); tc_fence_after(); }  // half 0 starts as soon as group 0 has drained ITS accumulator of the previous tile
           const uint32_t ws = w_wait();
           umma_unit_elect_ts_pair(tmem + 256 + half * 128, t_xa + 64 * kg, t_xa + 64 * kg + 32, w_ring_addr + ws * TP_WH, idesc, kg != 0,
                                   &w_empty[ws], kg == 1 ? &s_full[half] : nullptr);
@@ -536,15 +535,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) traj_
         }
         // ---- GEMM 3: output projection, A = o (bf16 pairs written over q2 by both CTAs' epilogues), accumulators = both stages
         AXVS_TRACE(trc_, 50)
-        mbar_wait_cluster(o_ready, it & 1);
+        // K group 0 (channels 0-127 = heads 0-3) is group 0's half of o, K group 1 group 1's: the first K group of both accumulators is issued
+        // as soon as group 0 has handed its half over, while group 1 (whose last chunk of the last frame completes later) still packs its
+        // own.  Per accumulator the order stays K group 0, then 1: bit-identical to the single-barrier schedule.
+        mbar_wait_cluster(&o_ready[0], it & 1);
         AXVS_TRACE(trc_, 51)
-        stage_wait(0);
-        stage_wait(1);
-        tc_fence_after();
-        AXVS_TRACE(trc_, 52)
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) {
-          const int half = u >> 1, kg = u & 1;
+          const int half = u & 1, kg = u >> 1;
+          if (kg == 0) { stage_wait(half); tc_fence_after(); }
+          else if (half == 0) { mbar_wait_cluster(&o_ready[1], it & 1); tc_fence_after(); AXVS_TRACE(trc_, 52) }
           const uint32_t ws = w_wait();
           umma_unit_elect_ts_pair(tmem + 256 + half * 128, t_qp + 64 * kg, t_qp + 64 * kg + 32, w_ring_addr + ws * TP_WH, idesc, kg != 0,
                                   &w_empty[ws], kg == 1 ? &s_full[half] : nullptr);
