@@ -610,7 +610,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
       const int tiles = tp.tiles;
       const bool traj_pair = g_fusion >= 4 && (g_pair & 2) && tiles >= 2;
       ProfScope ps(traj_pair ? KC_TRAJPAIR : g_fusion >= 4 ? KC_TRAJTS : KC_TRAJ, 2.0 * rows * 256.0 * 256.0 * (2.0 + 2.0 * F) + 4.0 * rows * F * 256.0,
-                   (double)rows * (512.0 * (F + (tm_rpad ? 0 : 1)) + 1024.0 + (resid ? 1024.0 : 0.0) + (ln_img ? 1536.0 : 0.0)), st);
+                   (double)rows * (512.0 * (F + (tm_rpad ? 0 : 1)) + (resid ? 1024.0 : 0.0) + (ln_img ? 1536.0 : 1024.0)), st);   // LN path: fp32 LN rows + bf16 image
       if (traj_pair) {
         const int pair_tiles = (tiles + 1) / 2, max_pairs = d->sms / 2;
         traj_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), TF_THREADS, TP_SMEM_BYTES, st>>>(tp);
