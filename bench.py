@@ -357,6 +357,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="1 (default): replay each step's kernels from a CUDA graph (launch overhead removed); 0: eager launches")
+    ap.add_argument("--per-step", type=int, default=0, help="debug: print per-step device times of the timed regions to stderr")
     ap.add_argument("--clip-chunks", type=int, default=1, help="split each level's clips into this many groups, one CUDA stream per (level, group)")
     ap.add_argument("--full-pos", type=int, default=0, help="1: materialise the positional table for every clip ([B,T,H,W,C], as the reference passes it) instead of sharing one table")
     ap.add_argument("--level-streams", type=int, default=1, help="1: run the two pyramid levels on two CUDA streams (default), 0: serially")
@@ -527,13 +528,20 @@ def main():
     def timed(fn, steps, drain=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = []
         e0.record()
         for k in range(steps):
             fn(k)
+            if args.per_step:                          # debug: per-step device times (stderr), e.g. to see a power cap set in
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
         if drain is not None:
             drain()                                    # the timed region ends when the last D2H has landed
         e1.record()
         barrier()
+        if marks and rank == 0:
+            ts = [e0.elapsed_time(m) for m in marks]
+            print("[bench] per-step ms: " + " ".join(f"{b - a_:.2f}" for a_, b in zip([0.0] + ts[:-1], ts)), file=sys.stderr)
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)

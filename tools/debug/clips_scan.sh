@@ -1,4 +1,4 @@
-for c in 42 45 63 84; do
+for c in ${CLIPS:-42 45 63 84}; do
   timeout 300 python bench.py --clips $c --steps 20 --warmup 5 --no-cpu-baseline --no-extras 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
