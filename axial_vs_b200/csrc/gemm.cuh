@@ -334,24 +334,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
       // the 256-channel projections never drain the pipeline at a tile boundary.
       // Mode 3 (NCHW): q = i * PT + ptid -> pixel row q & 127, 16-byte chunk (8 channels) q >> 7: a warp's 32 lanes read 32
       // consecutive pixels of one channel per instruction.  Mode 4: row q >> 3, chunk q & 7 as for bf16 sources.
-      float fa[ITERS][8], fb[ITERS][8];
-      auto load = [&](int it, float (&f)[ITERS][8]) {
-        const int tile = blockIdx.x + (it / num_kb) * gridDim.x;
-        const int kb = p.a_split ? (it % num_kb) % (num_kb / 3) : it % num_kb;      // source K-block
+      // Plain bursts: a thread requests its ITERS x 8 (mode 3) / ITERS x 2 (mode 4) loads of a K-block, then converts and stores them; the other
+      // seven producer warps cover the gap.  (The first version software-pipelined two register sets across K-blocks: the consumer of one set
+      // then waits on a scoreboard shared with the other set's loads issued just before it, so only one set was ever in flight per warp --
+      // the same effect as in the q|k|v producers, tools/microbench/ldg_rows.cu vs ldg_burst.cu.)  The row -> (image, pixel) division is
+      // done once per tile, not once per K-block.
+      float fa[ITERS][8];
+      const float* rowp[ITERS];                                   // first element of the thread's row / pixel for K-block 0 (null: past the end)
+      size_t row2[ITERS];                                         // mode 4: element offset into A32b
+      auto prepare = [&](int tile) {
         const int mt = tile / n_chunks;
 #pragma unroll
         for (int i = 0; i < ITERS; ++i) {
           const int q = i * PT + ptid;
+          rowp[i] = nullptr;
+          row2[i] = 0;
           if (p.a_diag == 3) {
             const int r = mt * GEMM_BM + (q & 127);
             if (r < p.M) {
               const int img = r / p.a_n;
-              const float* s = p.A32 + ((size_t)img * (p.a_split ? p.K / 3 : p.K) + kb * GEMM_BK + (q >> 7) * 8) * p.a_n + (r - img * p.a_n);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[i][j] = __ldg(s + (size_t)j * p.a_n);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
+              rowp[i] = p.A32 + ((size_t)img * (p.a_split ? p.K / 3 : p.K) + (q >> 7) * 8) * p.a_n + (r - img * p.a_n);
             }
           } else {
             const int r = mt * GEMM_BM + (q >> 3);
@@ -361,20 +363,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
                 const int img = r / p.a_img_rows;
                 o = (size_t)img * (size_t)p.a_img_stride + (size_t)(r - img * p.a_img_rows) * p.lda;
               }
-              o += kb * GEMM_BK + (q & 7) * 8;
-              const float4* s = reinterpret_cast<const float4*>(p.A32 + o);
-              float4 a = __ldg(s), b = __ldg(s + 1);
-              if (p.A32b) {
-                const size_t o2 = p.a32b_rows > 0 ? (size_t)(r % p.a32b_rows) * p.lda + kb * GEMM_BK + (q & 7) * 8 : o;
-                const float4* s2 = reinterpret_cast<const float4*>(p.A32b + o2);
-                const float4 a2 = __ldg(s2), b2 = __ldg(s2 + 1);
-                a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w; b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
-              }
-              f[i][0] = a.x; f[i][1] = a.y; f[i][2] = a.z; f[i][3] = a.w; f[i][4] = b.x; f[i][5] = b.y; f[i][6] = b.z; f[i][7] = b.w;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
+              rowp[i] = p.A32 + o + (q & 7) * 8;
+              if (p.A32b) row2[i] = p.a32b_rows > 0 ? (size_t)(r % p.a32b_rows) * p.lda + (q & 7) * 8 : o + (q & 7) * 8;
             }
+          }
+        }
+      };
+      auto load = [&](int kbi, float (&f)[ITERS][8]) {
+        const int kb = p.a_split ? kbi % (num_kb / 3) : kbi;      // source K-block
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i) {
+          if (rowp[i] == nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
+          } else if (p.a_diag == 3) {
+            const float* s = rowp[i] + (size_t)kb * GEMM_BK * p.a_n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[i][j] = __ldg(s + (size_t)j * p.a_n);
+          } else {
+            const float4* s = reinterpret_cast<const float4*>(rowp[i] + kb * GEMM_BK);
+            float4 a = __ldg(s), b = __ldg(s + 1);
+            if (p.A32b) {
+              const float4* s2 = reinterpret_cast<const float4*>(p.A32b + row2[i] + kb * GEMM_BK);
+              const float4 a2 = __ldg(s2), b2 = __ldg(s2 + 1);
+              a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w; b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+            }
+            f[i][0] = a.x; f[i][1] = a.y; f[i][2] = a.z; f[i][3] = a.w; f[i][4] = b.x; f[i][5] = b.y; f[i][6] = b.z; f[i][7] = b.w;
           }
         }
       };
@@ -397,15 +411,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const GemmPa
         if (lane == 0) mbar_arrive(&full_bar[stage]);
         if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
       };
-      const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-      const int n_items = my_tiles * num_kb;
-      if (n_items > 0) load(0, fa);
-      for (int it = 0; it < n_items; it += 2) {
-        if (it + 1 < n_items) load(it + 1, fb);
-        store(fa, it);
-        if (it + 1 < n_items) {
-          if (it + 2 < n_items) load(it + 2, fa);
-          store(fb, it + 1);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        prepare(tile);
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb) {
+          load(kb, fa);
+          store(fa, kb);
         }
       }
     } else
