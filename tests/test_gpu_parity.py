@@ -98,7 +98,8 @@ def test_trajectory_attention_golden(ops, golden, tag):
     assert nerr(out.reshape(Bp, F * n, 256), torch.from_numpy(gz["y"])) < TOL
 
 
-@pytest.mark.parametrize("Bp,F,n", [(5, 2, 41), (2, 5, 30), (1, 10, 33), (1, 2, 200), (1, 2, 161), (2, 3, 100), (3, 2, 21), (1, 4, 64), (1, 2, 128)])
+@pytest.mark.parametrize("Bp,F,n", [(5, 2, 41), (2, 5, 30), (1, 10, 33), (1, 2, 200), (1, 2, 161), (2, 3, 100), (3, 2, 21), (1, 4, 64), (1, 2, 128),
+                                    (3, 1, 40), (70, 3, 1), (40, 2, 3), (300, 2, 7)])   # one frame; one token per frame; short runs over many tiles
 def test_trajectory_attention_oracle(ops, O, Bp, F, n):
     p, q, v, pk = _ta_case(ops, O, Bp, F, n, 1000 + Bp + F + n)
     ref, _ = O.trajectory_attention(q, q, v, p, F)
