@@ -477,10 +477,11 @@ def test_cross_clip_layer_oracle_64_clips(O):
     assert nerr(y, ref) < TOL
 
 
-@pytest.mark.parametrize("B,T,H,W", [(1, 5, 30, 40), (1, 2, 81, 81)])
+@pytest.mark.parametrize("B,T,H,W", [(1, 5, 30, 40), (1, 2, 81, 81), (2, 2, 25, 43), (1, 2, 49, 85)])
 def test_axial_layer_oracle_large_shapes(O, B, T, H, W):
-    """BASELINE configs[3] at its larger temporal level (T = 5, 30x40: sequences of 150 / 200 tokens, two query blocks each) and the
-    sweep's 81x81 point (sequences of 162 tokens), whole layer against the oracle."""
+    """BASELINE configs[3] at its larger temporal level (T = 5, 30x40: sequences of 150 / 200 tokens, two query blocks each), the
+    sweep's 81x81 point (sequences of 162 tokens) and the res5 / res4 maps of the shipped VIPSeg configs (769 x 1345 -> 25 x 43 and 49 x 85,
+    Vk/configs/VIPSeg/panoptic_segmentation/maxtron_wc_*.yaml: IMAGE_SIZE), whole layer against the oracle."""
     seed = 5000 + T + H + W
     p = synth.axial_layer_params(seed)
     src = synth.randn(seed + 1, B * T, H * W, 256)
