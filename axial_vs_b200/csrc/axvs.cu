@@ -1575,7 +1575,9 @@ int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int 
   // (its staging keeps two 16-byte pieces of q, k and of each V row pair per thread in registers; below 33 positions three SIMT CTAs per SM win)
   const bool use_tc = g_kmax_tc && L > 32 && L <= 48 && dk % 16 == 0 && dv % 8 == 0 && smem_tc <= 227 * 1024 &&
                       L * (dk / 4) <= 2 * KA_TC_THREADS && ((L + 15) / 16 * 8) * (dv / 4) <= 2 * KA_TC_THREADS;
-  const size_t smem = use_tc ? smem_tc : kmax_axial_smem_bytes(L, dk, dv);
+  size_t smem = use_tc ? smem_tc : kmax_axial_smem_bytes(L, dk, dv);
+  const bool overlay = !use_tc && smem > 227 * 1024;              // long axes: key-side and value-side operands share shared memory
+  if (overlay) smem = kmax_axial_smem_bytes_overlay(L, dk, dv);
   if (smem > 227 * 1024) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: %zu bytes of shared memory needed (L=%d, dk=%d, dv=%d)", smem, L, dk, dv);
   const long long rows = (long long)images * H * W;
   if (rows > 0x7fffffffLL) return fail(AXVS_E_UNSUPPORTED, "kmax_axial: too many pixels");
@@ -1598,6 +1600,7 @@ int axvs_kmax_axial_fwd(const float* x, int x_layout, int images, int c_in, int 
   g.a_split = 1;
   if (int rc = launch_gemm(g, st)) return rc;
   KmaxAxialParams p;
+  p.overlay = overlay ? 1 : 0;
   p.qkv = qkv; p.ld = n_qkv; p.L = L; p.heads = heads; p.dk = dk; p.dv = dv;
   const long long HW = (long long)H * W;
   p.row_outer = HW;

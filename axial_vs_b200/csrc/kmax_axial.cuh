@@ -19,7 +19,7 @@
 
 namespace axvs {
 
-constexpr int KA_MAX_L = 64;
+constexpr int KA_MAX_L = 128;          // SIMT kernel: any axis whose tables fit shared memory (the softmax walks the row in 32-lane pieces)
 constexpr int KA_MAX_SPAN = 255;
 constexpr int KA_THREADS = 256;
 constexpr int KA_TC_THREADS = 512;     // tensor-core variant: 16 warps hide the fragment-load / mma latencies of the small tiles
@@ -39,7 +39,8 @@ struct KmaxAxialParams {
   const float* out_s;          // [2 * heads * dv] folded batch norm of the retrieved output (content channels, then rpe channels)
   const float* out_t;
   float* out;                  // element (s, c, l) at (s / seq_inner) * out_outer + (s % seq_inner) * out_inner + c * out_chan + l * out_pos
-  long long out_outer, out_inner, out_chan, out_pos;
+  long long out_outer, out_inner, out_chan, out_pos;  int overlay;                 // SIMT kernel, long axes: the value-side operands (v, rv) share shared memory with the key-side ones (q, k, rq, rk)
+                               // and every table is re-staged per item (see kmax_axial_smem_bytes_overlay)
 };
 
 // fp32 activations -> bf16 [rows][hi (K) | lo (K)] token rows: the A operand of the split-precision qkv GEMM, converted ONCE (the GEMM's
@@ -82,6 +83,15 @@ __host__ __device__ inline size_t kmax_axial_smem_bytes(int L, int dk, int dv) {
   return sizeof(float) * ((size_t)2 * L * pk + (size_t)L * pv + (size_t)2 * R * pk + (size_t)R * pv + (size_t)L * (L + 1));
 }
 
+// Long axes (L > 64 at the default depths dk = 64, dv = 128): the logits phase needs q, k, rq, rk and the retrieval phase v, rv -- never
+// both -- so the two operand sets share one region (the larger of the two) beside the L x (L + 1) weights; the price is re-staging the
+// embedding rows for every item (from L2) instead of once per CTA.
+__host__ __device__ inline size_t kmax_axial_smem_bytes_overlay(int L, int dk, int dv) {
+  const int pk = dk + 4, pv = dv + 4, R = 2 * L - 1;
+  const size_t a = (size_t)2 * L * pk + (size_t)2 * R * pk, b = (size_t)L * pv + (size_t)R * pv;
+  return sizeof(float) * ((a > b ? a : b) + (size_t)L * (L + 1));
+}
+
 __global__ void __launch_bounds__(KA_THREADS) kmax_axial_attn_kernel(const KmaxAxialParams p) {
   extern __shared__ float ka_smem[];
   const int L = p.L, dk = p.dk, dv = p.dv, pk = dk + 4, pv = dv + 4, R = 2 * L - 1;
@@ -92,20 +102,33 @@ __global__ void __launch_bounds__(KA_THREADS) kmax_axial_attn_kernel(const KmaxA
   float* rk = rq + R * pk;                // [R][pk]
   float* rv = rk + R * pk;                // [R][pv]
   float* sw = rv + R * pv;                // [L][L + 1] logits -> weights
+  if (p.overlay) {                        // key side [sq | sk | rq | rk] and value side [sv | rv] on the same words, the weights behind the larger
+    rq = sk + L * pk;
+    rk = rq + R * pk;
+    sv = ka_smem;
+    rv = sv + L * pv;
+    const size_t a = (size_t)2 * L * pk + (size_t)2 * R * pk, b = (size_t)L * pv + (size_t)R * pv;
+    sw = ka_smem + (a > b ? a : b);
+  }
   const int tid = threadIdx.x;
   const int Kd = p.heads * dk;
 
   // ---- the addressable rows of the three embedding tables: shared by every head and sequence, staged once per (persistent) CTA
   const int e0 = KA_MAX_SPAN - 1 - (L - 1);                        // embedding row of relative distance -(L - 1)
-  for (int e = tid; e < R * (dk / 4); e += KA_THREADS) {
-    const int r = e / (dk / 4), d4 = e - r * (dk / 4);
-    reinterpret_cast<float4*>(rq + r * pk)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_q + (size_t)(e0 + r) * dk) + d4);
-    reinterpret_cast<float4*>(rk + r * pk)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_k + (size_t)(e0 + r) * dk) + d4);
-  }
-  for (int e = tid; e < R * (dv / 4); e += KA_THREADS) {
-    const int r = e / (dv / 4), d4 = e - r * (dv / 4);
-    reinterpret_cast<float4*>(rv + r * pv)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_v + (size_t)(e0 + r) * dv) + d4);
-  }
+  auto stage_key_tables = [&]() {
+    for (int e = tid; e < R * (dk / 4); e += KA_THREADS) {
+      const int r = e / (dk / 4), d4 = e - r * (dk / 4);
+      reinterpret_cast<float4*>(rq + r * pk)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_q + (size_t)(e0 + r) * dk) + d4);
+      reinterpret_cast<float4*>(rk + r * pk)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_k + (size_t)(e0 + r) * dk) + d4);
+    }
+  };
+  auto stage_value_table = [&]() {
+    for (int e = tid; e < R * (dv / 4); e += KA_THREADS) {
+      const int r = e / (dv / 4), d4 = e - r * (dv / 4);
+      reinterpret_cast<float4*>(rv + r * pv)[d4] = __ldg(reinterpret_cast<const float4*>(p.emb_v + (size_t)(e0 + r) * dv) + d4);
+    }
+  };
+  if (!p.overlay) { stage_key_tables(); stage_value_table(); }
 
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
   const int h = item % p.heads, s = item / p.heads;
@@ -118,11 +141,14 @@ __global__ void __launch_bounds__(KA_THREADS) kmax_axial_attn_kernel(const KmaxA
     reinterpret_cast<float4*>(sq + l * pk)[d4] = __ldg(reinterpret_cast<const float4*>(row + h * dk) + d4);
     reinterpret_cast<float4*>(sk + l * pk)[d4] = __ldg(reinterpret_cast<const float4*>(row + Kd + h * dk) + d4);
   }
-  for (int e = tid; e < L * (dv / 4); e += KA_THREADS) {
-    const int l = e / (dv / 4), d4 = e - l * (dv / 4);
-    reinterpret_cast<float4*>(sv + l * pv)[d4] =
-        __ldg(reinterpret_cast<const float4*>(p.qkv + (size_t)(row0 + l * p.row_pos) * p.ld + 2 * Kd + h * dv) + d4);
-  }
+  auto stage_v = [&]() {
+    for (int e = tid; e < L * (dv / 4); e += KA_THREADS) {
+      const int l = e / (dv / 4), d4 = e - l * (dv / 4);
+      reinterpret_cast<float4*>(sv + l * pv)[d4] =
+          __ldg(reinterpret_cast<const float4*>(p.qkv + (size_t)(row0 + l * p.row_pos) * p.ld + 2 * Kd + h * dv) + d4);
+    }
+  };
+  if (p.overlay) stage_key_tables(); else stage_v();
   __syncthreads();
 
   // ---- similarity logits: three dot products per (l, m), each through its own batch-norm affine        (:137-145)
@@ -168,19 +194,34 @@ __global__ void __launch_bounds__(KA_THREADS) kmax_axial_attn_kernel(const KmaxA
   for (int l = tid >> 5; l < L; l += KA_THREADS / 32) {
     float* row = sw + l * (L + 1);
     const int lane = tid & 31;
-    const float x0 = lane < L ? row[lane] : -INFINITY, x1 = lane + 32 < L ? row[lane + 32] : -INFINITY;
-    float mx = fmaxf(x0, x1);
+    float x[KA_MAX_L / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < KA_MAX_L / 32; ++u) {
+      x[u] = lane + 32 * u < L ? row[lane + 32 * u] : -INFINITY;
+      mx = fmaxf(mx, x[u]);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
-    const float y0 = lane < L ? expf(x0 - mx) : 0.f, y1 = lane + 32 < L ? expf(x1 - mx) : 0.f;
-    float sum = y0 + y1;
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < KA_MAX_L / 32; ++u) {
+      x[u] = lane + 32 * u < L ? expf(x[u] - mx) : 0.f;
+      sum += x[u];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
     const float inv = 1.f / sum;
-    if (lane < L) row[lane] = y0 * inv;
-    if (lane + 32 < L) row[lane + 32] = y1 * inv;
+#pragma unroll
+    for (int u = 0; u < KA_MAX_L / 32; ++u)
+      if (lane + 32 * u < L) row[lane + 32 * u] = x[u] * inv;
   }
   __syncthreads();
+  if (p.overlay) {                                                 // the key-side operands are dead: bring in v and the value embedding rows
+    stage_v();
+    stage_value_table();
+    __syncthreads();
+  }
 
   // ---- retrieval: content and positional parts, their batch-norm affines, sum                        (:150-157)
   const float* os = p.out_s;

@@ -357,7 +357,7 @@ typedef struct axvs_kmax_axial_weights {
 /* x: x_layout 0 = fp32 NCHW [images, c_in, H, W], 1 = fp32 token rows [images*H*W, c_in].  axis 1: one sequence per (image, w) running
  * along H (the `_height_axis` of AxialAttention2D, :179-182; also the 1-D module on [N, C, L] with H = L, W = 1); axis 2: one per
  * (image, h) along W (:184-187).  out: out_layout 0 = NCHW [images, heads*dv, H, W], 1 = token rows [images*H*W, heads*dv] (what the
- * next axis consumes: the reference's permutes at :183 and :188 are folded into these layouts).  Axis length <= 64. */
+ * next axis consumes: the reference's permutes at :183 and :188 are folded into these layouts).  Axis length <= 128 and within the shared-memory budget (112 at dk = 64, dv = 128). */
 /* 1 (default): axes of 33..48 positions run their attention core on the tensor cores (split-bf16 mma.sync, same accuracy, 1.8x faster at
  * 41 positions); 0: always the fp32 SIMT kernel (the validation baseline; also used for <= 32 and 49..64 positions).  Returns the previous setting. */
 int axvs_set_kmax_tensor_cores(int on);

@@ -1051,10 +1051,10 @@ def test_kmax_axial_2d_golden(golden):
     assert nerr(y, torch.from_numpy(gz["y"])) < TOL
 
 
-@pytest.mark.parametrize("N,C,H,W", [(2, 512, 21, 21), (1, 512, 41, 41), (3, 64, 64, 5), (2, 128, 1, 33)])
+@pytest.mark.parametrize("N,C,H,W", [(2, 512, 21, 21), (1, 512, 41, 41), (3, 64, 64, 5), (2, 128, 1, 33), (1, 256, 49, 85), (1, 64, 2, 110)])
 def test_kmax_axial_2d_oracle_config_sizes(N, C, H, W):
-    """kMaX R50 at 641x641: the axial blocks run at stride 32 (21x21) and stride 16 (41x41) on 512 channels; plus the longest supported
-    axis and a degenerate one."""
+    """kMaX R50 at 641x641: the axial blocks run at stride 32 (21x21) and stride 16 (41x41) on 512 channels; the stride-16 map of the shipped
+    769 x 1345 VIPSeg configs (49 x 85); plus a 110-long axis (the limit at the default depths is 112) and a degenerate one."""
     from axial_vs_b200.kmax_axial import AxialAttention2D
     from oracle import kmax_oracle as KO
     seed = 4000 + N + C + H + W
@@ -1079,7 +1079,7 @@ def test_kmax_axial_rejects_bad_arguments():
         with pytest.raises(RuntimeError):
             m(torch.zeros(1, 64, 9))                      # CPU tensor
         with pytest.raises(RuntimeError):
-            m(torch.zeros(1, 64, 65, device="cuda"))      # axis longer than the kernel's shared-memory budget allows
+            m(torch.zeros(1, 64, 129, device="cuda"))     # axis longer than the kernel supports (128)
         with pytest.raises(RuntimeError):
             m(torch.zeros(1, 32, 9, device="cuda"))       # wrong channel count
     m.train()
