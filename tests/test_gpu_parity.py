@@ -920,6 +920,24 @@ def test_within_clip_module_r50_shapes(O):
         assert e < 3e-2 and cos > 0.999, (name, e, cos)
 
 
+def test_within_clip_module_vipseg_config_shapes(O):
+    """The pyramid of the shipped VIPSeg configs (IMAGE_SIZE 769 x 1345, Vk/configs/VIPSeg/panoptic_segmentation/maxtron_wc_*.yaml) for one
+    clip (T = 2): res5 2048 x 25 x 43, res4 1024 x 49 x 85, res3 512 x 97 x 169 -- rectangular maps, frames of 85 tokens in the W pass --
+    against the oracle."""
+    chans, sizes, seed = [2048, 1024, 512], [(25, 43), (49, 85), (97, 169)], 769
+    p = synth.within_clip_module_params(seed, chans)
+    m = _wc_module(chans)
+    m.load_state_dict(p, strict=True)
+    m.cuda()
+    feats = [synth.randn(seed + 1 + i, 2, chans[i], *sizes[i]) for i in range(3)]
+    want = O.within_clip_module(feats, p, 1, 2)
+    out, _, _ = m.forward_features({f"res{5 - i}": feats[i].cuda() for i in range(3)})
+    for i, name in enumerate(("res5", "res4", "res3")):
+        e = nerr(out[name], want[i])
+        cos = torch.nn.functional.cosine_similarity(out[name].cpu().flatten(), want[i].flatten(), dim=0).item()
+        assert e < 3e-2 and cos > 0.999, (name, e, cos)
+
+
 def test_within_clip_module_convnext_channels_multi_clip_and_graph(O):
     """ConvNeXt-L channel counts (res5 1536, res4 768, res3 384: the output side is not a multiple of 256) on a small ragged pyramid with
     TWO clips (cross-clip training layout: B = 2, T = 2): the level slices of the multi-level token tensor are written / read in place
