@@ -9,7 +9,10 @@ p = synth.axial_layer_params(0)
 layer = TemporalAxialTrajectoryAttentionLayer(256, 1024, 0.0, 0.0, "relu", 8).eval()
 layer.load_state_dict(p)
 layer = layer.cuda()
-for (H, W) in ((21, 21), (41, 41)):
+shapes = ((21, 21), (41, 41))
+if len(sys.argv) > 2:                      # e.g. "25x43,49x85": the res5 / res4 maps of the shipped 769 x 1345 VIPSeg configs
+    shapes = tuple(tuple(int(v) for v in s_.split("x")) for s_ in sys.argv[2].split(","))
+for (H, W) in shapes:
     src = torch.randn(clips * 2, H * W, 256, device="cuda")
     pos = torch.randn(clips, 2, H, W, 256, device="cuda")
     with torch.no_grad():
