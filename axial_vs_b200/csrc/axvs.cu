@@ -147,7 +147,7 @@ int device_info(DeviceInfo** out) {
   if (!d.qkv_attr) {
     if (cudaFuncSetAttribute(qkv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QK_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(qkv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QD_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(qkv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(qkv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QQ_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(msda_front_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(msda_tail_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QP_SMEM_BYTES) != cudaSuccess)
       return fail(AXVS_E_CUDA, "cudaFuncSetAttribute(qkv_fused) failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -455,7 +455,7 @@ int traj_attn_impl(const float* q_in, const float* k_in, const float* v_in, cons
         ProfScope ps(((g_pair & 4) && tiles >= 2) ? KC_QKVPAIR : KC_QKVD, 2.0 * rows * 256.0 * 768.0, (double)rows * ((pos ? (dims.pos_mod ? 1024.0 + 1024.0 / B : 2048.0) : 1024.0) + 1536.0), st);
         if ((g_pair & 4) && tiles >= 2) {
           const int pair_tiles = (tiles + 1) / 2, max_pairs = d->sms / 2;
-          qkv_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), QD_THREADS, QP_SMEM_BYTES, st>>>(qp);
+          qkv_pair_kernel<<<2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs), QD_THREADS, QQ_SMEM_BYTES, st>>>(qp);
         } else
         qkv_direct_kernel<<<tiles < d->sms ? tiles : d->sms, QD_THREADS, QD_SMEM_BYTES, st>>>(qp);
       }

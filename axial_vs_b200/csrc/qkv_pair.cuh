@@ -14,6 +14,17 @@ namespace axvs {
 constexpr int QP_W_SLOTS = 5;                   // half units
 constexpr int QP_WH = 16384;
 constexpr int QP_STAGE_BYTES = 8 * 4096;        // per epilogue warp: two 32 rows x 64 B staging buffers (bulk stores read one while the next is written)
+// qkv_pair_kernel's own ring depths (the MSDeformAttn kernels that share this header keep QD_A_SLOTS / QP_W_SLOTS): FOUR A pair-slots hold a whole
+// tile (4 K-blocks), so the producers finish the next tile while the current one is computed and drained -- with three, the last K-block
+// could only be loaded after the issuer had started the tile, and the issuer waited for it (17 % of its time) -- paid for with a shorter weight ring
+#ifndef QQ_A_SLOTS
+#define QQ_A_SLOTS 4
+#endif
+#ifndef QQ_W_SLOTS
+#define QQ_W_SLOTS 3
+#endif
+constexpr int QQ_SMEM_BYTES = QQ_A_SLOTS * 2 * TF_KB + QQ_W_SLOTS * QP_WH + QP_STAGE_BYTES + QK_BIAS_BYTES + 512;
+static_assert(QQ_SMEM_BYTES <= 232448, "qkv_pair_kernel exceeds the 227 KiB shared-memory limit");
 constexpr int QP_SMEM_BYTES = QD_A_SLOTS * 2 * TF_KB + QP_W_SLOTS * QP_WH + QP_STAGE_BYTES + QK_BIAS_BYTES + 512;
 static_assert(QP_SMEM_BYTES <= 232448, "qkv_pair_kernel exceeds the 227 KiB shared-memory limit");
 
@@ -21,15 +32,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* a_ring = smem;
-  uint8_t* w_ring = a_ring + QD_A_SLOTS * 2 * TF_KB;
-  uint8_t* stage_all = w_ring + QP_W_SLOTS * QP_WH;
+  uint8_t* w_ring = a_ring + QQ_A_SLOTS * 2 * TF_KB;
+  uint8_t* stage_all = w_ring + QQ_W_SLOTS * QP_WH;
   float* sbias = reinterpret_cast<float*>(stage_all + QP_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 768);
-  uint64_t* a_full = bars;                      // [QD_A_SLOTS], one arrive per producer warp
-  uint64_t* a_empty = a_full + QD_A_SLOTS;      // tcgen05.commit after the slot's copies
-  uint64_t* w_full = a_empty + QD_A_SLOTS;      // [QP_W_SLOTS]
-  uint64_t* w_empty = w_full + QP_W_SLOTS;
-  uint64_t* s_full = w_empty + QP_W_SLOTS;      // [2] accumulator stage of group g complete
+  uint64_t* a_full = bars;                      // [QQ_A_SLOTS], one arrive per producer warp
+  uint64_t* a_empty = a_full + QQ_A_SLOTS;      // tcgen05.commit after the slot's copies
+  uint64_t* w_full = a_empty + QQ_A_SLOTS;      // [QQ_W_SLOTS]
+  uint64_t* w_empty = w_full + QQ_W_SLOTS;
+  uint64_t* s_full = w_empty + QQ_W_SLOTS;      // [2] accumulator stage of group g complete
   uint64_t* s_empty = s_full + 2;               // [2] drained by the 4 warps of group g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
 
@@ -41,8 +52,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
 
   if (threadIdx.x == 0) {
     const uint32_t extra = rank == 0 ? 1 : 0;                 // leader: + the peer's relay
-    for (int i = 0; i < QD_A_SLOTS; ++i) { mbar_init(&a_full[i], QD_PRODUCER_WARPS + extra); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < QP_W_SLOTS; ++i) { mbar_init(&w_full[i], 1 + extra); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < QQ_A_SLOTS; ++i) { mbar_init(&a_full[i], QD_PRODUCER_WARPS + extra); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < QQ_W_SLOTS; ++i) { mbar_init(&w_full[i], 1 + extra); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 16); }   // s_empty: the leader's copy is live (8 warps x 2 CTAs)
     fence_barrier_init();
   }
@@ -234,7 +245,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
 #pragma unroll
           for (int j = 0; j < 8; ++j) qv[j] = z;
         }
-        const uint32_t slot = cnt % QD_A_SLOTS, phase = (cnt / QD_A_SLOTS) & 1;
+        const uint32_t slot = cnt % QQ_A_SLOTS, phase = (cnt / QQ_A_SLOTS) & 1;
         AXVS_PROF_WAIT(0, mbar_wait_cluster(&a_empty[slot], phase ^ 1))
         uint8_t* dst = a_ring + slot * 2 * TF_KB;
         AXVS_PROF_MARK(t_cv_)
@@ -268,7 +279,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
         const uint8_t* src = p.w + (size_t)u * TF_WU + rank * 64 * 128;
         tma_bulk_g2s(w_ring + slot * QP_WH, src, 8192, &w_full[slot]);
         tma_bulk_g2s(w_ring + slot * QP_WH + 8192, src + TF_KB, 8192, &w_full[slot]);
-        if (++slot == QP_W_SLOTS) { slot = 0; phase ^= 1; }
+        if (++slot == QQ_W_SLOTS) { slot = 0; phase ^= 1; }
       }
     }
   } else if (warp == 17 && rank != 0) {
@@ -279,15 +290,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
       for (int pt = pair; pt < pair_tiles; pt += npairs) {
 #pragma unroll 1
         for (int kb = 0; kb < 4; ++kb, ++a_cnt) {
-          const uint32_t slot = a_cnt % QD_A_SLOTS;
-          mbar_wait_cluster(&a_full[slot], (a_cnt / QD_A_SLOTS) & 1);
+          const uint32_t slot = a_cnt % QQ_A_SLOTS;
+          mbar_wait_cluster(&a_full[slot], (a_cnt / QQ_A_SLOTS) & 1);
           mbar_arrive_cluster(&a_full[slot], 0);               // release: my producers' generic-proxy writes were fenced before their arrive
         }
 #pragma unroll 1
         for (int u = 0; u < 12; ++u) {
           mbar_wait_cluster(&w_full[w_slot], w_phase);
           mbar_arrive_cluster_relaxed(&w_full[w_slot], 0);
-          if (++w_slot == QP_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
+          if (++w_slot == QQ_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
         }
       }
     }
@@ -302,8 +313,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
       // previous tile (issued earlier by this thread), which still reads the old contents.
 #pragma unroll 1
       for (int kb = 0; kb < 4; ++kb, ++a_cnt) {
-        const uint32_t slot = a_cnt % QD_A_SLOTS;
-        AXVS_PROF_WAIT(2, mbar_wait_cluster(&a_full[slot], (a_cnt / QD_A_SLOTS) & 1))
+        const uint32_t slot = a_cnt % QQ_A_SLOTS;
+        AXVS_PROF_WAIT(2, mbar_wait_cluster(&a_full[slot], (a_cnt / QQ_A_SLOTS) & 1))
         tc_fence_after();
         const uint32_t sa = a_ring_addr + slot * 2 * TF_KB;
         if (elect_one()) {
@@ -325,7 +336,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QD_THREADS, 1) qkv_p
           AXVS_PROF_WAIT(0, mbar_wait_cluster(&w_full[w_slot], w_phase))
           tc_fence_after();
           const uint32_t ws = w_slot;
-          if (++w_slot == QP_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
+          if (++w_slot == QQ_W_SLOTS) { w_slot = 0; w_phase ^= 1; }
           umma_unit_elect_ts_pair(tmem + 256 + g * 128, t_a + 64 * kg, t_a + 64 * kg + 32, w_ring_addr + ws * QP_WH, idesc, kg != 0,
                                   &w_empty[ws], kg == 1 ? &s_full[g] : nullptr);
         }
